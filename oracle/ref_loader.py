@@ -1,0 +1,53 @@
+"""Import the UNMODIFIED reference `mdp_playground` from /root/reference.
+
+Only usable where the reference checkout exists (the build container); the
+GPU box has no /root/reference, so nothing that runs there may call this.
+gymnasium is absent from the image, so `oracle/gymnasium_standin` is put on
+sys.path first (see its docstring for what it restates).
+"""
+import contextlib
+import io
+import os
+import sys
+
+REFERENCE_ROOT = os.environ.get("MDPP_REFERENCE_ROOT", "/root/reference")
+_STANDIN = os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                        "gymnasium_standin")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "mdp_playground"))
+
+
+def load_reference():
+    """Return the reference's RLToyEnv class (imports are cached)."""
+    if not reference_available():
+        raise RuntimeError("reference checkout not present at " + REFERENCE_ROOT)
+    try:
+        import gymnasium  # noqa: F401  (a real install wins if present)
+    except ModuleNotFoundError:
+        if _STANDIN not in sys.path:
+            sys.path.insert(0, _STANDIN)
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.append(REFERENCE_ROOT)
+    with contextlib.redirect_stdout(io.StringIO()):
+        from mdp_playground.envs.rl_toy_env import RLToyEnv
+    return RLToyEnv
+
+
+def make_reference_env(config):
+    """Construct a reference env with its constructor chatter silenced."""
+    import copy
+    import logging
+    import warnings
+    cls = load_reference()
+    logging.disable(logging.WARNING)  # the ctor logs at WARNING (:336,:883)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()), \
+                warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            env = cls(**copy.deepcopy(config))
+    finally:
+        logging.disable(logging.NOTSET)
+    env.logger.setLevel(logging.ERROR)
+    return env
