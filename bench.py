@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched RLToyEnv step path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
+        --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): discrete toy MDP, 8 states x 8 actions,
+sequence_length 3, delay 2, transition_noise 0.1, reward_noise 0.25,
+65 536 envs per GPU, horizon 100 with auto-reset, native Philox noise.
+One bench "step" = one fused rollout launch of --inner (default 1000)
+env-steps over all envs of the rank: actions [T,N] int32 are read from HBM,
+obs i64 / reward f64 / terminated u8 / truncated u8 [T,N] are written
+(22 B per env-step, 1.44 GB per launch: larger than the 126 MB L2, so no
+flush is needed between launches).
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU port of the
+reference loop (oracle/scalar_env.py; the Python reference itself cannot
+travel to the GPU box) on all host cores instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+ENVS_PER_GPU = 65536
+ALGO_BYTES_ROLLOUT = 22   # action in + outputs out
+ALGO_BYTES_STEP = 58      # SURVEY.md 8d table, config C2 single step
+
+
+def workload_config():
+    return dict(seed=0, state_space_type="discrete",
+                action_space_type="discrete", state_space_size=8,
+                action_space_size=8, sequence_length=3, delay=2,
+                transition_noise=0.1, reward_noise=0.25, reward_density=0.25,
+                terminal_state_density=0.25, generate_random_mdp=True,
+                reward_every_n_steps=True)
+
+
+WORKLOAD_NAME = ("discrete toy (dqn_p_r_noises/dqn_seq_del shape): 8 states, "
+                 "8 actions, sequence_length=3, delay=2, transition_noise=0.1, "
+                 "reward_noise=0.25, 65536 envs per GPU, horizon 100 auto-reset")
+
+
+# --------------------------------------------------------------------------
+# CPU port of the reference loop
+# --------------------------------------------------------------------------
+def _cpu_loop(n_steps, seed=0, horizon=100):
+    """for t: env.step(a_t); reset on done or every `horizon` steps."""
+    import numpy as np
+    from oracle.scalar_env import ScalarRLToyEnv
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = ScalarRLToyEnv(**dict(workload_config(), seed=seed))
+    actions = np.random.default_rng(0xC0FFEE + seed).integers(
+        0, 8, size=n_steps).tolist()
+    t0 = time.perf_counter()
+    since = 0
+    for a in actions:
+        _, _, done, _, _ = env.step(a)
+        since += 1
+        if done or since == horizon:
+            env.reset()
+            since = 0
+    return time.perf_counter() - t0
+
+
+def _cpu_worker(args):
+    n_steps, seed = args
+    return _cpu_loop(n_steps, seed)
+
+
+def cpu_port_throughput(n_steps, procs):
+    """Aggregate steps/s of `procs` independent scalar envs (1 = in-process)."""
+    if procs == 1:
+        dt = _cpu_loop(n_steps)
+        return n_steps / dt
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(n_steps, s) for s in range(procs)])
+        wall = time.perf_counter() - t0
+    return procs * n_steps / wall
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    per_proc = args.ref_sample
+    _cpu_loop(2000)  # import + warm caches
+    for _ in range(args.warmup):
+        cpu_port_throughput(max(per_proc // 10, 1000), cores)
+    t0 = time.perf_counter()
+    vals = [cpu_port_throughput(per_proc, cores) for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    value = sum(vals) / len(vals)
+    sample = (f"{cores} processes x {per_proc} env-steps of the scalar CPU "
+              f"port per bench step, reset on done or every 100 steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME, "envs": cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores,
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,"
+              "clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index),
+                 "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0][0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                 "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names)
+                   if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1][0].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from mdp_playground_b200 import VectorRLToyEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    N, T = args.envs, args.inner
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = VectorRLToyEnv(N, device=dev, autoreset=True, horizon=100,
+                             env_id_offset=rank * N, **workload_config())
+    # synthetic actions: Philox, seed 0xC0FFEE + rank
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0xC0FFEE + rank)
+    actions = torch.randint(0, 8, (T, N), dtype=torch.int32, device=dev,
+                            generator=gen)
+    out = {
+        "obs": torch.empty((T, N), dtype=torch.int64, device=dev),
+        "reward": torch.empty((T, N), dtype=torch.float64, device=dev),
+        "terminated": torch.empty((T, N), dtype=torch.bool, device=dev),
+        "truncated": torch.empty((T, N), dtype=torch.bool, device=dev),
+    }
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident leg: `value` and the roofline --------------------
+    for _ in range(args.warmup):
+        env.rollout(T, actions=actions, out=out)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        env.rollout(T, actions=actions, out=out)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = world * N * T * args.steps / (ms_total * 1e-3)
+    per_gpu_steps_per_s = N * T / (ms_per_step * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    achieved = per_gpu_steps_per_s * ALGO_BYTES_ROLLOUT / 1e9
+
+    # ---- gym-style single step() calls (launch-bound; reported) -
+    n_single = 200
+    a1 = actions[0:1]
+    o1 = {k: v[0:1] for k, v in out.items()}
+    for _ in range(10):
+        env.rollout(1, actions=a1, out=o1)
+    barrier()
+    e0.record()
+    for _ in range(n_single):
+        env.rollout(1, actions=a1, out=o1)
+    e1.record()
+    barrier()
+    single_ms = max_over_ranks(e0.elapsed_time(e1)) / n_single
+    single_sps = world * N / (single_ms * 1e-3)
+
+    # ---- end-to-end leg: host buffers through the public API --------------
+    h_act = torch.empty((T, N), dtype=torch.int32).pin_memory()
+    h_act.copy_(actions.cpu())
+    h_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory()
+             for k, v in out.items()}
+    d_act = torch.empty_like(actions)
+
+    def e2e_step():
+        d_act.copy_(h_act, non_blocking=True)
+        env.rollout(T, actions=d_act, out=out)
+        for k in out:
+            h_out[k].copy_(out[k], non_blocking=True)
+
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * N * T * e2e_steps / (e2e_ms * 1e-3)
+    h2d = T * N * 4
+    d2h = T * N * (8 + 8 + 1 + 1)
+
+    if rank == 0:
+        # ---- CPU baseline: scalar port, one core, bounded sample ----------
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            _cpu_loop(2000)
+            n_cpu = args.cpu_sample
+            v = cpu_port_throughput(n_cpu, 1)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"{n_cpu} env-steps of oracle/scalar_env.py "
+                             "(CPU restatement of the reference loop), one "
+                             "process, reset on done or every 100 steps"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "envs_per_gpu": N,
+                       "env_steps_per_launch": T, "noise": "philox",
+                       "autoreset": "same-step", "l2_policy":
+                       f"inputs+outputs {T * N * 22 / 1e6:.0f} MB per launch "
+                       "> 126 MB L2 (no flush needed)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "discrete_rollout_kernel<PHILOX,smem>",
+                         "algorithmic_bytes_per_env_step": ALGO_BYTES_ROLLOUT,
+                         "env_steps_per_launch": N * T},
+            "single_step_api": {"value": single_sps, "unit": UNIT,
+                                "us_per_call": single_ms * 1e3,
+                                "roofline_frac": single_sps / world
+                                * ALGO_BYTES_STEP / 1e9 / peak},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU,
+                    help="envs per GPU")
+    ap.add_argument("--inner", type=int, default=1000,
+                    help="env-steps fused into one launch (one bench step)")
+    ap.add_argument("--cpu-sample", type=int, default=300000)
+    ap.add_argument("--ref-sample", type=int, default=100000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.gpus > 1 and world == 1:
+            # convenience: re-launch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                   "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,164 @@
+/*
+ * mdpp_b200.h -- C ABI of the B200-native RLToyEnv step path.
+ *
+ * The reference (automl/mdp-playground) has no FFI: its boundary is the
+ * Python class `RLToyEnv` (mdp_playground/envs/rl_toy_env.py:216 ctor,
+ * :2217 reset, :1992 step).  This header is the C-ABI a binding for that
+ * class calls into; `mdp_playground_b200/vector_env.py` is that binding
+ * (ctypes) and INTEGRATION.md shows the stub a reference maintainer would
+ * add.  Plain pointers and sizes only; every device buffer is owned by the
+ * caller (PyTorch in our binding) and borrowed for the duration of a call.
+ * All launches are enqueued on the caller's stream; nothing synchronises.
+ *
+ * Every function returns 0 on success or a negative MDPP_E* code;
+ * mdpp_last_error() returns the message of the last failure on that context
+ * (or of the last failed mdpp_create when ctx == NULL).
+ */
+#ifndef MDPP_B200_H
+#define MDPP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDPP_ABI_VERSION 1
+
+#define MDPP_OK 0
+#define MDPP_EINVAL (-1)   /* bad argument / unsupported configuration      */
+#define MDPP_ECUDA (-2)    /* a CUDA runtime call or launch failed          */
+#define MDPP_ENOMEM (-3)
+
+/* Where the step path's random draws come from (SURVEY.md 8b "Modes").     */
+#define MDPP_NOISE_OFF 0     /* no draw is consumed                         */
+#define MDPP_NOISE_REPLAY 1  /* draws are read from caller-provided arrays  */
+#define MDPP_NOISE_PHILOX 2  /* Philox4x32-10, counter = (env, step, stream)*/
+
+/* Per-group episode statistics (rl_toy_env.py:2360-2369 counters, summed
+ * over envs and episodes).  Layout of one row of `stats`.                  */
+#define MDPP_STAT_EPISODES 0          /* episodes ended (auto-reset or reset()) */
+#define MDPP_STAT_TRANSITIONS 1       /* total_transitions_episode          */
+#define MDPP_STAT_REWARD 2            /* total_reward_episode (pre-noise)   */
+#define MDPP_STAT_NOISY_TRANSITIONS 3 /* total_noisy_transitions_episode    */
+#define MDPP_STAT_ABS_REWARD_NOISE 4  /* total_abs_noise_in_reward_episode  */
+#define MDPP_STAT_ABS_TRANSITION_NOISE 5 /* ..._in_transition_episode (sum over dims) */
+#define MDPP_STAT_RESERVED 6
+#define MDPP_STAT_TERMINATED 7        /* steps that returned terminated     */
+#define MDPP_N_STATS 8
+
+typedef struct mdpp_ctx mdpp_ctx;
+
+int mdpp_abi_version(void);
+int mdpp_create(int device, mdpp_ctx** out_ctx);
+void mdpp_destroy(mdpp_ctx* ctx);
+const char* mdpp_last_error(const mdpp_ctx* ctx);
+
+/* ------------------------------------------------------------------------
+ * Discrete environments (replaces RLToyEnv.transition_function :1602-1622,
+ * reward_function :1817-1846 + tail :1968-1990, step epilogue :2098-2125,
+ * reset :2250-2278).
+ * --------------------------------------------------------------------- */
+
+/* One configuration group = one (P, R, scalars) set shared by a contiguous
+ * range of environments.  All pointers are HOST pointers, copied during the
+ * call.  Tables come from the host-side generators (seeded numpy, same draws
+ * as init_transition_function :1042 / init_reward_function :1253).        */
+typedef struct mdpp_discrete_group {
+  int32_t n_states;              /* S                                        */
+  int32_t n_actions;             /* A                                        */
+  int32_t sequence_length;       /* L >= 1                                   */
+  int32_t delay;                 /* d >= 0                                   */
+  int32_t reward_every_n_steps;  /* >= 1                                     */
+  int32_t custom_reward;         /* 1: r = R[s, a] (use_custom_mdp :1817)    */
+  int32_t n_sequences;           /* full-length rewardable sequences         */
+  int32_t has_transition_noise;  /* truthy transition_noise (:1604)          */
+  int32_t has_reward_noise;      /* "reward_noise" key present (:398, :1982) */
+  int32_t reserved0;
+  double transition_noise;       /* p                                        */
+  double reward_noise_std;       /* sigma                                    */
+  double reward_scale;
+  double reward_shift;
+  double term_state_reward;
+  const int32_t* transition;     /* [S*A]  P[s,a]                            */
+  const uint8_t* terminal;       /* [S]    1 = terminal                      */
+  const double* init_cdf;        /* [S]    cumsum(init_dist)/last            */
+  const double* noise_cdf;       /* [S*S]  row s' = cdf of the noisy draw
+                                           around s' (:1605-1612); may be
+                                           NULL when !has_transition_noise   */
+  const int32_t* sequences;      /* [n_sequences*L] rewardable sequences     */
+  const double* sequence_rewards;/* [n_sequences]                            */
+  const double* reward_matrix;   /* [S*A] when custom_reward, else NULL      */
+  int64_t env_begin;             /* first env (local index) of the group     */
+  int64_t env_count;
+} mdpp_discrete_group;
+
+int mdpp_set_discrete_groups(mdpp_ctx* ctx, const mdpp_discrete_group* groups,
+                             int32_t n_groups);
+
+/* Persistent per-env state, struct-of-arrays, DEVICE pointers owned by the
+ * caller.  `ring` holds the reward-delay FIFO (:1970-1973) as a ring of
+ * `ring_depth` rows (>= max delay over groups; NULL when that is 0).
+ * `history` (optional) keeps the last `history_depth` emitted states so the
+ * binding can rebuild `augmented_state` (:2127).                           */
+typedef struct mdpp_discrete_state {
+  int64_t n_envs;
+  int32_t* cur_state;   /* [N]                                              */
+  uint64_t* seq_key;    /* [N] last L states, key_bits each, newest lowest  */
+  int32_t* t_episode;   /* [N] total_transitions_episode                    */
+  uint32_t* episode;    /* [N] episodes started (reset-draw counter)        */
+  double* ring;         /* [ring_depth*N] or NULL                           */
+  int32_t ring_depth;
+  int32_t history_depth;
+  int32_t* history;     /* [history_depth*N] or NULL                        */
+  double* stats;        /* [n_groups*MDPP_N_STATS], accumulated atomically  */
+} mdpp_discrete_state;
+
+/* Inputs/outputs of T consecutive steps, time-major [T*N], DEVICE pointers.
+ * Any output pointer may be NULL (that output is skipped).                 */
+typedef struct mdpp_discrete_io {
+  const int32_t* actions;            /* [T*N]; NULL => uniform Philox policy */
+  int64_t* obs;                      /* [T*N] state after the step (after the
+                                        auto-reset when one happened)        */
+  int64_t* final_obs;                /* [T*N] state before any auto-reset    */
+  double* reward;                    /* [T*N]                                */
+  uint8_t* terminated;               /* [T*N]                                */
+  uint8_t* truncated;                /* [T*N]                                */
+  const double* replay_transition_u; /* [T*N] uniform of choice(p=) (:1612)  */
+  const double* replay_reward_noise; /* [T*N] value of normal(0,sigma) :1982 */
+  const double* replay_reset_u;      /* [T*N] uniform of the reset choice    */
+} mdpp_discrete_io;
+
+/* How the Philox mode turns words into N(0,1) reward noise.                 */
+#define MDPP_NORMAL_F64 0   /* Box-Muller in fp64 (log, sqrt, sincospi)      */
+#define MDPP_NORMAL_FAST 1  /* Box-Muller on the SFU in fp32 (~1e-6 rel.)    */
+
+typedef struct mdpp_step_opts {
+  int32_t n_steps;        /* T >= 1                                          */
+  int32_t noise_mode;     /* MDPP_NOISE_*                                    */
+  int32_t autoreset;      /* 1: reset in the same step on terminated/truncated */
+  int32_t horizon;        /* > 0: truncated = (t_episode >= horizon)         */
+  int32_t normal_mode;    /* MDPP_NORMAL_* (Philox mode only)                */
+  int32_t reserved0;
+  uint64_t seed;          /* Philox key                                      */
+  uint64_t step_index;    /* global index of the first step of this call     */
+  int64_t env_id_offset;  /* global id of local env 0 (multi-GPU sharding)   */
+} mdpp_step_opts;
+
+/* K1/K2: T fused steps, one thread per env, tables staged in shared memory. */
+int mdpp_discrete_rollout(mdpp_ctx* ctx, const mdpp_discrete_state* st,
+                          const mdpp_discrete_io* io,
+                          const mdpp_step_opts* opts, void* cuda_stream);
+
+/* K6: (masked) reset.  mask NULL = all envs.  The initial state comes from
+ * `init_states` when given, else from the init cdf driven by `replay_reset_u`
+ * (MDPP_NOISE_REPLAY) or Philox.  `obs` may be NULL.                        */
+int mdpp_discrete_reset(mdpp_ctx* ctx, const mdpp_discrete_state* st,
+                        const uint8_t* mask, const int32_t* init_states,
+                        const double* replay_reset_u, int64_t* obs,
+                        const mdpp_step_opts* opts, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDPP_B200_H */

@@ -1,0 +1,117 @@
+"""ctypes binding of libmdpp_b200.so (the C ABI in include/mdpp_b200.h).
+
+There is NO fallback: if the library is missing or a symbol is absent this
+module raises, and every VectorRLToyEnv operation goes through it.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmdpp_b200.so")
+
+MDPP_NOISE_OFF, MDPP_NOISE_REPLAY, MDPP_NOISE_PHILOX = 0, 1, 2
+MDPP_N_STATS = 8
+MDPP_NORMAL_F64, MDPP_NORMAL_FAST = 0, 1
+STAT_NAMES = ("episodes", "transitions", "reward", "noisy_transitions",
+              "abs_reward_noise", "abs_transition_noise", "reserved",
+              "terminated")
+
+# every symbol include/mdpp_b200.h declares
+EXPORTED_SYMBOLS = (
+    "mdpp_abi_version", "mdpp_create", "mdpp_destroy", "mdpp_last_error",
+    "mdpp_set_discrete_groups", "mdpp_discrete_rollout", "mdpp_discrete_reset",
+)
+
+
+class DiscreteGroup(C.Structure):
+    _fields_ = [
+        ("n_states", C.c_int32), ("n_actions", C.c_int32),
+        ("sequence_length", C.c_int32), ("delay", C.c_int32),
+        ("reward_every_n_steps", C.c_int32), ("custom_reward", C.c_int32),
+        ("n_sequences", C.c_int32), ("has_transition_noise", C.c_int32),
+        ("has_reward_noise", C.c_int32), ("reserved0", C.c_int32),
+        ("transition_noise", C.c_double), ("reward_noise_std", C.c_double),
+        ("reward_scale", C.c_double), ("reward_shift", C.c_double),
+        ("term_state_reward", C.c_double),
+        ("transition", C.c_void_p), ("terminal", C.c_void_p),
+        ("init_cdf", C.c_void_p), ("noise_cdf", C.c_void_p),
+        ("sequences", C.c_void_p), ("sequence_rewards", C.c_void_p),
+        ("reward_matrix", C.c_void_p),
+        ("env_begin", C.c_int64), ("env_count", C.c_int64),
+    ]
+
+
+class DiscreteState(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int64),
+        ("cur_state", C.c_void_p), ("seq_key", C.c_void_p),
+        ("t_episode", C.c_void_p), ("episode", C.c_void_p),
+        ("ring", C.c_void_p),
+        ("ring_depth", C.c_int32), ("history_depth", C.c_int32),
+        ("history", C.c_void_p), ("stats", C.c_void_p),
+    ]
+
+
+class DiscreteIO(C.Structure):
+    _fields_ = [
+        ("actions", C.c_void_p), ("obs", C.c_void_p), ("final_obs", C.c_void_p),
+        ("reward", C.c_void_p), ("terminated", C.c_void_p),
+        ("truncated", C.c_void_p), ("replay_transition_u", C.c_void_p),
+        ("replay_reward_noise", C.c_void_p), ("replay_reset_u", C.c_void_p),
+    ]
+
+
+class StepOpts(C.Structure):
+    _fields_ = [
+        ("n_steps", C.c_int32), ("noise_mode", C.c_int32),
+        ("autoreset", C.c_int32), ("horizon", C.c_int32),
+        ("normal_mode", C.c_int32), ("reserved0", C.c_int32),
+        ("seed", C.c_uint64), ("step_index", C.c_uint64),
+        ("env_id_offset", C.c_int64),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load the library once; raise loudly if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built. "
+            "Run `python -m mdp_playground_b200.build` (needs nvcc). There is "
+            "no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name in EXPORTED_SYMBOLS:
+        if not hasattr(lib, name):
+            raise RuntimeError(f"{LIB_PATH} does not export {name}")
+    P = C.c_void_p
+    lib.mdpp_abi_version.restype = C.c_int
+    lib.mdpp_create.argtypes = [C.c_int, C.POINTER(P)]
+    lib.mdpp_destroy.argtypes = [P]
+    lib.mdpp_destroy.restype = None
+    lib.mdpp_last_error.argtypes = [P]
+    lib.mdpp_last_error.restype = C.c_char_p
+    lib.mdpp_set_discrete_groups.argtypes = [P, C.POINTER(DiscreteGroup), C.c_int32]
+    lib.mdpp_discrete_rollout.argtypes = [
+        P, C.POINTER(DiscreteState), C.POINTER(DiscreteIO), C.POINTER(StepOpts), P]
+    lib.mdpp_discrete_reset.argtypes = [
+        P, C.POINTER(DiscreteState), P, P, P, P, C.POINTER(StepOpts), P]
+    if lib.mdpp_abi_version() != 1:
+        raise RuntimeError("libmdpp_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+class MdppError(RuntimeError):
+    pass
+
+
+def check(lib, ctx, rc):
+    if rc != 0:
+        msg = lib.mdpp_last_error(ctx)
+        raise MdppError(f"libmdpp_b200 error {rc}: "
+                        f"{msg.decode() if msg else '?'}")

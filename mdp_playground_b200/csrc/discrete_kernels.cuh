@@ -1,0 +1,490 @@
+// Discrete RLToyEnv step path on sm_100a: K1/K2 `discrete_rollout` (T fused
+// steps, T = 1 is the gym-style single step) and K6 `discrete_reset`.
+//
+// Restates (per env, per step) rl_toy_env.py
+//   transition_function :1602-1622   s' = P[s,a]; noisy redraw via cdf search
+//   step                :2050-2058   window shift, t += 1
+//   reward_function     :1817-1846   custom R[s,a] | gated sequence lookup
+//                       :1968-1990   delay FIFO, every-n gate, noise, scale, shift
+//   step epilogue       :2098-2109   done = terminal(s'), += term reward * scale
+//   reset               :2250-2278   s0 ~ init dist, window/FIFO/t cleared
+//
+// Work decomposition: one thread = one environment, state in registers for
+// the whole launch.  A CTA serves one configuration group; the group's tables
+// (P as u16, terminal mask, init / noise cdfs, sequence LUT or hash, reward
+// values) are staged once into shared memory with 128-bit copies.  Global
+// traffic is struct-of-arrays, time-major [T][N], so every warp access is one
+// contiguous segment.  Steps are processed in chunks of U: the chunk's
+// action loads and its state-independent Philox / Box-Muller work are issued
+// up front (memory- and instruction-level parallelism), then the short
+// state-dependent chain runs.
+#pragma once
+#include "internal.h"
+#include "philox.cuh"
+
+namespace mdpp {
+
+constexpr int kBlock = 128;
+constexpr int kChunk = 8;
+// 65 536 envs / 148 SMs = 443 threads per SM: all of them must be resident
+// at once (one wave), so cap registers at 65 536 / 512 = 128 per thread.
+constexpr int kMinBlocksPerSM = 4;
+
+struct RolloutParams {
+  DiscreteGroupDev group0;  // copy of groups[0]: FAST kernels (single group)
+                            // read it from the constant bank / uniform regs
+  const DiscreteGroupDev* groups;
+  const uint8_t* blob;
+  const CtaMapEntry* cta_map;
+  mdpp_discrete_state st;
+  mdpp_discrete_io io;
+  int32_t T, autoreset, horizon;
+  int32_t ring_smem_bytes;
+  uint32_t k0, k1;
+  uint64_t step_index;
+  int64_t env_id_offset;
+};
+
+__device__ __forceinline__ int32_t ld_stream_i32(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_stream_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream(int64_t* p, int64_t v) {
+  asm volatile("st.global.cs.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream(double* p, double v) {
+  asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream(uint8_t* p, uint8_t v) {
+  asm volatile("st.global.cs.u8 [%0], %1;" ::"l"(p), "r"((uint32_t)v) : "memory");
+}
+
+// numpy searchsorted(cdf, u, side='right') = number of entries <= u, as a
+// branch-free binary search over a row padded to 2^log2n entries with a
+// sentinel larger than any u (context.cu).  LOG2 >= 0 fixes the trip count at
+// compile time (fully unrolled); LOG2 < 0 reads it from the group.
+template <int LOG2>
+__device__ __forceinline__ int cdf_search(const double* cdf, int log2n, int n,
+                                          double u) {
+  int pos = 0;
+  if (LOG2 >= 0) {
+#pragma unroll
+    for (int b = LOG2 - 1; b >= 0; --b)
+      if (cdf[pos + (1 << b) - 1] <= u) pos += 1 << b;
+  } else {
+#pragma unroll 1
+    for (int step = (1 << log2n) >> 1; step > 0; step >>= 1)
+      if (cdf[pos + step - 1] <= u) pos += step;
+  }
+  return min(pos, n - 1);
+}
+
+struct GroupView {  // per-thread copy of the scalars + table pointers
+  int S, A, L, delay, every_n, lookup_kind, key_bits, hash_shift;
+  int cdf_log2, cdf_stride;
+  bool has_pnoise, has_rnoise, has_guide;
+  const uint8_t* guide;
+  uint32_t hash_mask;
+  uint64_t key_mask;
+  double r_std, scale, shift, term_reward_scaled;
+  const uint16_t* P;
+  const uint8_t* term;
+  const double* init_cdf;
+  const double* noise_cdf;
+  const double* lut;
+  const uint64_t* hash_keys;
+  const uint32_t* hash_vals;
+  const double* values;
+  const double* R;
+};
+
+__device__ __forceinline__ GroupView make_view(const DiscreteGroupDev& g,
+                                               const uint8_t* tab) {
+  GroupView v;
+  v.S = g.S; v.A = g.A; v.L = g.L; v.delay = g.delay; v.every_n = g.every_n;
+  v.lookup_kind = g.lookup_kind; v.key_bits = g.key_bits;
+  v.hash_shift = g.hash_shift; v.hash_mask = g.hash_mask;
+  v.has_pnoise = g.has_pnoise != 0; v.has_rnoise = g.has_rnoise != 0;
+  v.cdf_log2 = g.cdf_log2; v.cdf_stride = g.cdf_stride;
+  v.has_guide = g.has_guide != 0;
+  v.guide = tab + g.off_guide;
+  v.key_mask = g.key_mask;
+  v.r_std = g.r_std; v.scale = g.scale; v.shift = g.shift;
+  v.term_reward_scaled = g.term_reward_scaled;
+  v.P = reinterpret_cast<const uint16_t*>(tab + g.off_P);
+  v.term = tab + g.off_term;
+  v.init_cdf = reinterpret_cast<const double*>(tab + g.off_init_cdf);
+  v.noise_cdf = reinterpret_cast<const double*>(tab + g.off_noise_cdf);
+  v.lut = reinterpret_cast<const double*>(tab + g.off_lut);
+  v.hash_keys = reinterpret_cast<const uint64_t*>(tab + g.off_hash_keys);
+  v.hash_vals = reinterpret_cast<const uint32_t*>(tab + g.off_hash_vals);
+  v.values = reinterpret_cast<const double*>(tab + g.off_values);
+  v.R = reinterpret_cast<const double*>(tab + g.off_R);
+  return v;
+}
+
+__device__ __forceinline__ double sequence_reward(const GroupView& v,
+                                                  uint64_t key) {
+  if (v.lookup_kind == LOOKUP_LUT) return v.lut[key];
+  uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> v.hash_shift) &
+                  v.hash_mask;
+  while (true) {
+    uint64_t k = v.hash_keys[slot];
+    if (k == key) return v.values[v.hash_vals[slot]];
+    if (k == kHashEmpty) return 0.0;
+    slot = (slot + 1) & v.hash_mask;
+  }
+}
+
+struct EnvRegs {
+  int32_t s;
+  uint64_t key;
+  int32_t tl;
+  int32_t phase;  // tl % every_n, tracked incrementally (no division per step)
+  uint32_t ep;
+  int32_t ring_pos;  // step % delay
+  int32_t hist_pos;  // (step + 1) % history_depth
+  // statistics accumulated over the launch
+  double sum_reward, sum_abs_rnoise;
+  uint32_t n_noisy, n_episodes, n_terminated, n_steps;
+};
+
+// Philox-mode draws of a group of 4 consecutive steps (quad = step >> 2),
+// all state-independent so they are produced ahead of the state chain:
+//   STREAM_STEP   word j          -> 32-bit transition uniform of step 4q+j
+//   STREAM_NORMAL words (0,1),(2,3) -> two Box-Muller pairs = 4 reward normals
+//   STREAM_AUTORESET word j       -> 32-bit uniform of the auto-reset after
+//                                    step 4q+j
+template <int NORMAL>
+__device__ __forceinline__ void philox_quad_draws(
+    uint32_t gid, uint64_t quad, uint32_t k0, uint32_t k1, bool want_u,
+    bool want_normal, bool want_reset, double* u_tr, double* z, uint32_t* w_rs) {
+  const uint32_t q0 = (uint32_t)quad, q1 = (uint32_t)(quad >> 32);
+  if (want_u) {
+    U4 w = philox4x32_10(gid, q0, q1, STREAM_STEP, k0, k1);
+    u_tr[0] = uniform32(w.x); u_tr[1] = uniform32(w.y);
+    u_tr[2] = uniform32(w.z); u_tr[3] = uniform32(w.w);
+  }
+  if (want_normal) {
+    U4 w = philox4x32_10(gid, q0, q1, STREAM_NORMAL, k0, k1);
+    if (NORMAL == 0) {
+      normal_pair_f64(w.x, w.y, &z[0], &z[1]);
+      normal_pair_f64(w.z, w.w, &z[2], &z[3]);
+    } else {
+      normal_pair_fast(w.x, w.y, &z[0], &z[1]);
+      normal_pair_fast(w.z, w.w, &z[2], &z[3]);
+    }
+  }
+  if (want_reset) {
+    U4 w = philox4x32_10(gid, q0, q1, STREAM_AUTORESET, k0, k1);
+    w_rs[0] = w.x; w_rs[1] = w.y; w_rs[2] = w.z; w_rs[3] = w.w;
+  }
+}
+
+// Compile-time configuration of a rollout kernel.
+//   FAST  the standard rollout signature -- actions given; obs, reward,
+//         terminated, truncated all written; no final_obs, no history -- so
+//         none of the per-step NULL tests survive in the hot loop; tables and
+//         the delay ring are in shared memory.
+//   CDF_LOG2 >= 0: cdf rows have exactly 2^CDF_LOG2 entries (unrolled search).
+//   SINGLE the launch has one configuration group: its descriptor comes
+//         from the kernel parameters instead of shared memory.
+template <int NOISE_, int NORMAL_, bool SMEM_, bool RING_SMEM_, bool FAST_,
+          int CDF_LOG2_, bool SINGLE_ = false>
+struct Cfg {
+  static constexpr bool SINGLE = SINGLE_;
+  static constexpr int NOISE = NOISE_;
+  static constexpr int NORMAL = NORMAL_;
+  static constexpr bool SMEM = SMEM_;
+  static constexpr bool RING_SMEM = RING_SMEM_;
+  static constexpr bool FAST = FAST_;
+  static constexpr int CDF_LOG2 = CDF_LOG2_;
+};
+
+template <typename C, int U>
+__device__ __forceinline__ void run_chunk(const RolloutParams& p,
+                                          const GroupView& v, EnvRegs& e,
+                                          double* ring_smem, int64_t env,
+                                          uint32_t gid, int t0) {
+  constexpr int NOISE = C::NOISE;
+  constexpr int NORMAL = C::NORMAL;
+  constexpr bool RING_SMEM = C::RING_SMEM;
+  constexpr bool FAST = C::FAST;
+  const int64_t N = p.st.n_envs;
+  int32_t act[U], s0[U];
+  double u_tr[U], n_rw[U], u_rs[U];
+  const int64_t off0 = (int64_t)t0 * N + env;
+  const uint64_t step0 = p.step_index + (uint64_t)t0;
+  const bool have_actions = FAST || p.io.actions != nullptr;
+  // ---- phase A: loads and state-independent random draws -----------------
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const int64_t off = off0 + (int64_t)j * N;
+    const uint64_t step = step0 + (uint64_t)j;
+    if (have_actions) {
+      act[j] = ld_stream_i32(p.io.actions + off);
+    } else {
+      U4 w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
+                           STREAM_ACTION, p.k0, p.k1);
+      act[j] = (int32_t)__umulhi(w.x, (uint32_t)v.A);
+    }
+    u_tr[j] = 0.0; n_rw[j] = 0.0; u_rs[j] = 0.0;
+    if (NOISE == MDPP_NOISE_REPLAY) {
+      if (v.has_pnoise) u_tr[j] = ld_stream_f64(p.io.replay_transition_u + off);
+      if (v.has_rnoise) n_rw[j] = ld_stream_f64(p.io.replay_reward_noise + off);
+      if (p.autoreset) u_rs[j] = ld_stream_f64(p.io.replay_reset_u + off);
+    }
+  }
+  uint32_t w_rs[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) w_rs[j] = 0;
+  if (NOISE != MDPP_NOISE_REPLAY) {
+    const bool want_u = NOISE == MDPP_NOISE_PHILOX && v.has_pnoise;
+    const bool want_z = NOISE == MDPP_NOISE_PHILOX && v.has_rnoise;
+    const bool want_r = p.autoreset != 0;
+    if (U == 1) {
+      double u4[4] = {0, 0, 0, 0}, z4[4] = {0, 0, 0, 0};
+      uint32_t r4[4] = {0, 0, 0, 0};
+      philox_quad_draws<NORMAL>(gid, step0 >> 2, p.k0, p.k1, want_u, want_z,
+                                want_r, u4, z4, r4);
+      const int q = (int)(step0 & 3);
+      u_tr[0] = q == 0 ? u4[0] : q == 1 ? u4[1] : q == 2 ? u4[2] : u4[3];
+      double z = q == 0 ? z4[0] : q == 1 ? z4[1] : q == 2 ? z4[2] : z4[3];
+      w_rs[0] = q == 0 ? r4[0] : q == 1 ? r4[1] : q == 2 ? r4[2] : r4[3];
+      n_rw[0] = __dmul_rn(v.r_std, z);
+    } else {  // chunks start on a multiple-of-4 step (see the caller)
+#pragma unroll
+      for (int j = 0; j + 3 < U; j += 4) {
+        double z4[4] = {0, 0, 0, 0};
+        philox_quad_draws<NORMAL>(gid, (step0 + j) >> 2, p.k0, p.k1, want_u,
+                                  want_z, want_r, &u_tr[j], z4, &w_rs[j]);
+        // numpy: normal(0, sigma) = 0 + sigma * z
+#pragma unroll
+        for (int k = 0; k < 4; ++k) n_rw[j + k] = __dmul_rn(v.r_std, z4[k]);
+      }
+    }
+  }
+  if (p.autoreset) {  // candidate initial states, also state-independent
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      if (NOISE == MDPP_NOISE_REPLAY) {
+        s0[j] = cdf_search<C::CDF_LOG2>(v.init_cdf, v.cdf_log2, v.S, u_rs[j]);
+      } else if (v.has_guide) {
+        int32_t g = v.guide[w_rs[j] >> (32 - kGuideBits)];
+        if (g == kGuideMiss)  // the bucket straddles a cdf boundary (rare)
+          g = cdf_search<C::CDF_LOG2>(v.init_cdf, v.cdf_log2, v.S, uniform32(w_rs[j]));
+        s0[j] = g;
+      } else {
+        s0[j] = cdf_search<C::CDF_LOG2>(v.init_cdf, v.cdf_log2, v.S, uniform32(w_rs[j]));
+      }
+    }
+  }
+  // ---- phase B: the state-dependent chain --------------------------------
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const int64_t off = off0 + (int64_t)j * N;
+    uint32_t a = (uint32_t)act[j];
+    if (a >= (uint32_t)v.A) a = (uint32_t)v.A - 1;  // memory safety only
+    int32_t nxt = v.P[e.s * v.A + (int32_t)a];
+    if (NOISE != MDPP_NOISE_OFF && v.has_pnoise) {
+      int32_t noisy = cdf_search<C::CDF_LOG2>(v.noise_cdf + nxt * v.cdf_stride, v.cdf_log2,
+                                 v.S, u_tr[j]);
+      e.n_noisy += (noisy != nxt);
+      nxt = noisy;
+    }
+    e.key = ((e.key << v.key_bits) | (uint64_t)nxt) & v.key_mask;
+    e.tl += 1;
+    e.phase = (e.phase + 1 == v.every_n) ? 0 : e.phase + 1;
+    double r = 0.0;
+    if (v.lookup_kind == LOOKUP_MATRIX) {
+      r = v.R[e.s * v.A + (int32_t)a];
+    } else if (e.tl >= v.L) {  // isnan(aug[delay]) gate <=> t < L
+      r = sequence_reward(v, e.key);
+    }
+    if (v.delay > 0) {  // FIFO of depth d: pay out what was earned d steps ago
+      double* slot = RING_SMEM
+          ? ring_smem + e.ring_pos * kBlock
+          : p.st.ring + (int64_t)e.ring_pos * N + env;
+      double delayed = (e.tl > v.delay) ? *slot : 0.0;
+      *slot = r;
+      r = delayed;
+      e.ring_pos = (e.ring_pos + 1 == v.delay) ? 0 : e.ring_pos + 1;
+    }
+    if (e.phase != 0) r = 0.0;
+    e.sum_reward += r;
+    if (NOISE != MDPP_NOISE_OFF && v.has_rnoise) {
+      e.sum_abs_rnoise += fabs(n_rw[j]);
+      r = __dadd_rn(r, n_rw[j]);
+    }
+    r = __dmul_rn(r, v.scale);
+    r = __dadd_rn(r, v.shift);
+    const bool done = v.term[nxt] != 0;
+    if (done) r = __dadd_rn(r, v.term_reward_scaled);
+    const bool trunc = p.horizon > 0 && e.tl >= p.horizon;
+    e.n_terminated += done;
+    e.s = nxt;
+    if (!FAST && p.io.final_obs) st_stream(p.io.final_obs + off, (int64_t)nxt);
+    if (p.autoreset && (done || trunc)) {
+      e.s = s0[j];
+      e.key = (uint64_t)e.s;
+      e.tl = 0;
+      e.phase = 0;
+      e.ep += 1;
+      e.n_episodes += 1;
+    }
+    if (!FAST && p.st.history) {
+      p.st.history[(int64_t)e.hist_pos * N + env] = e.s;
+      e.hist_pos = (e.hist_pos + 1 == p.st.history_depth) ? 0 : e.hist_pos + 1;
+    }
+    if (FAST || p.io.obs) st_stream(p.io.obs + off, (int64_t)e.s);
+    if (FAST || p.io.reward) st_stream(p.io.reward + off, r);
+    if (FAST || p.io.terminated) st_stream(p.io.terminated + off, (uint8_t)done);
+    if (FAST || p.io.truncated) st_stream(p.io.truncated + off, (uint8_t)trunc);
+  }
+  e.n_steps += U;
+}
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+template <typename C>
+__global__ void __launch_bounds__(kBlock, kMinBlocksPerSM)
+discrete_rollout_kernel(const __grid_constant__ RolloutParams p) {
+  constexpr bool SMEM = C::SMEM;
+  constexpr bool RING_SMEM = C::RING_SMEM;
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  __shared__ DiscreteGroupDev grp;
+  const CtaMapEntry me = p.cta_map[blockIdx.x];
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.groups + me.group);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&grp);
+    for (int i = threadIdx.x; i < (int)(sizeof(DiscreteGroupDev) / 4); i += kBlock)
+      dst[i] = src[i];
+  }
+  __syncthreads();
+  const uint8_t* tab = p.blob + grp.blob_offset;
+  // dynamic smem: [ring: p.ring_smem_bytes][tables]
+  double* ring_smem = reinterpret_cast<double*>(smem_dyn) + threadIdx.x;
+  if (SMEM) {
+    uint8_t* smem_tab = smem_dyn + p.ring_smem_bytes;
+    const uint4* src = reinterpret_cast<const uint4*>(tab);
+    uint4* dst = reinterpret_cast<uint4*>(smem_tab);
+    for (int i = threadIdx.x; i < grp.blob_bytes / 16; i += kBlock) dst[i] = src[i];
+    __syncthreads();
+    tab = smem_tab;
+  }
+  const GroupView v = make_view(C::SINGLE ? p.group0 : grp, tab);
+  const int64_t local = (int64_t)me.chunk * kBlock + threadIdx.x;
+  const bool active = local < grp.env_count;
+  const int64_t env = grp.env_begin + (active ? local : 0);
+  const int64_t N = p.st.n_envs;
+  const uint32_t gid = (uint32_t)(p.env_id_offset + env);
+
+  EnvRegs e;
+  e.s = p.st.cur_state[env];
+  e.key = p.st.seq_key[env];
+  e.tl = p.st.t_episode[env];
+  e.ep = p.st.episode[env];
+  e.phase = e.tl % v.every_n;
+  e.ring_pos = v.delay > 0 ? (int32_t)(p.step_index % (uint64_t)v.delay) : 0;
+  e.hist_pos = p.st.history
+      ? (int32_t)((p.step_index + 1) % (uint64_t)p.st.history_depth) : 0;
+  e.sum_reward = e.sum_abs_rnoise = 0.0;
+  e.n_noisy = e.n_episodes = e.n_terminated = e.n_steps = 0;
+
+  if (active) {
+    if (RING_SMEM)
+      for (int k = 0; k < v.delay; ++k)
+        ring_smem[k * kBlock] = p.st.ring[(int64_t)k * N + env];
+    int t0 = 0;
+    // chunks of kChunk steps start on a multiple-of-4 global step (the Philox
+    // draws come in groups of 4 steps); peel single steps until aligned
+    while (t0 < p.T && ((p.step_index + (uint64_t)t0) & 3)) {
+      run_chunk<C, 1>(p, v, e, ring_smem, env, gid, t0);
+      ++t0;
+    }
+    for (; t0 + kChunk <= p.T; t0 += kChunk)
+      run_chunk<C, kChunk>(p, v, e, ring_smem, env, gid, t0);
+    for (; t0 < p.T; ++t0)
+      run_chunk<C, 1>(p, v, e, ring_smem, env, gid, t0);
+    p.st.cur_state[env] = e.s;
+    p.st.seq_key[env] = e.key;
+    p.st.t_episode[env] = e.tl;
+    p.st.episode[env] = e.ep;
+    if (RING_SMEM)
+      for (int k = 0; k < v.delay; ++k)
+        p.st.ring[(int64_t)k * N + env] = ring_smem[k * kBlock];
+  }
+  if (p.st.stats) {
+    double vals[MDPP_N_STATS];
+    vals[MDPP_STAT_EPISODES] = (double)e.n_episodes;
+    vals[MDPP_STAT_TRANSITIONS] = (double)e.n_steps;
+    vals[MDPP_STAT_REWARD] = e.sum_reward;
+    vals[MDPP_STAT_NOISY_TRANSITIONS] = (double)e.n_noisy;
+    vals[MDPP_STAT_ABS_REWARD_NOISE] = e.sum_abs_rnoise;
+    vals[MDPP_STAT_ABS_TRANSITION_NOISE] = 0.0;
+    vals[MDPP_STAT_RESERVED] = 0.0;
+    vals[MDPP_STAT_TERMINATED] = (double)e.n_terminated;
+    double* row = p.st.stats + (int64_t)me.group * MDPP_N_STATS;
+#pragma unroll
+    for (int k = 0; k < MDPP_N_STATS; ++k) {
+      if (k == MDPP_STAT_ABS_TRANSITION_NOISE || k == MDPP_STAT_RESERVED) continue;
+      double s = warp_sum(active ? vals[k] : 0.0);
+      if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(row + k, s);
+    }
+  }
+}
+
+// Ring of delayed rewards lives in shared memory when it is small enough.
+constexpr int kRingSmemMaxDelay = 16;
+
+template <typename C>
+inline int launch_one(mdpp_ctx* ctx, RolloutParams& p, int smem_tab,
+                      cudaStream_t stream) {
+  auto kern = discrete_rollout_kernel<C>;
+  p.ring_smem_bytes = C::RING_SMEM ? ctx->max_delay * kBlock * 8 : 0;
+  const int smem = p.ring_smem_bytes + (C::SMEM ? smem_tab : 0);
+  if (smem > 48 * 1024 - 512)
+    MDPP_CUDA(ctx, cudaFuncSetAttribute(
+                       kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<(unsigned)ctx->n_ctas, kBlock, smem, stream>>>(p);
+  MDPP_CUDA(ctx, cudaGetLastError());
+  return MDPP_OK;
+}
+
+// Kernel variants.  The FAST ones (standard signature, tables + ring in
+// shared memory) exist for the throughput-relevant noise modes, with the cdf
+// search unrolled for <= 8 states (the toy sizes of BASELINE.json) or looped;
+// everything else (replay, huge tables, deep delay rings, optional outputs)
+// takes the generic variants.
+template <int NOISE, int NORMAL>
+inline int launch_rollout(mdpp_ctx* ctx, RolloutParams& p, cudaStream_t stream) {
+  const int smem_tab = ctx->max_group_blob;
+  const bool ring_ok = ctx->max_delay <= kRingSmemMaxDelay;
+  const int ring_bytes = ring_ok ? ctx->max_delay * kBlock * 8 : 0;
+  const bool smem_ok = smem_tab + ring_bytes <= ctx->max_smem_optin - 1024;
+  const bool fast_io = p.io.actions && p.io.obs && p.io.reward &&
+                       p.io.terminated && p.io.truncated && !p.io.final_obs &&
+                       !p.st.history;
+  if constexpr (NOISE != MDPP_NOISE_REPLAY) {
+    if (smem_ok && ring_ok && fast_io && ctx->d_groups_host.size() == 1) {
+      return ctx->d_groups_host[0].cdf_log2 == 3
+          ? launch_one<Cfg<NOISE, NORMAL, true, true, true, 3, true>>(ctx, p, smem_tab, stream)
+          : launch_one<Cfg<NOISE, NORMAL, true, true, true, -1, true>>(ctx, p, smem_tab, stream);
+    }
+  }
+  if (smem_ok && ring_ok)
+    return launch_one<Cfg<NOISE, NORMAL, true, true, false, -1>>(ctx, p, smem_tab, stream);
+  return launch_one<Cfg<NOISE, NORMAL, false, false, false, -1>>(ctx, p, smem_tab, stream);
+}
+
+}  // namespace mdpp

@@ -1,0 +1,361 @@
+"""VectorRLToyEnv: N independent RLToyEnv instances stepped by sm_100a kernels.
+
+Drop-in for the reference's `RLToyEnv` on the step path (constructor keys,
+`reset` / `step` return tuples, `get_augmented_state`; rl_toy_env.py:216,
+:2217, :1992, :2127), batched over a leading env axis.  All state lives in
+PyTorch-owned device tensors; every operation is a call into libmdpp_b200.so
+(include/mdpp_b200.h) on the current CUDA stream.  There is no CPU path.
+
+Noise modes:
+  "philox"  (default) native counter-based noise, stream = (seed, env, step)
+  "replay"  the caller passes the draws (bit-exact replays of reference runs)
+  "numpy"   the host draws from the reference's own PCG64 streams and feeds
+            them through the replay inputs: lane 0 reproduces the reference
+            env with the same seed bit for bit (small N; parity / debugging)
+  "off" is implied when the config has no noise.
+"""
+import copy
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import np_random, parse_config
+from .spaces import BoxSpace, DiscreteSpace
+from .tables import build_discrete_tables
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class VectorRLToyEnv:
+    metadata = {"render_modes": []}
+
+    def __init__(self, num_envs, device=None, noise="philox", autoreset=False,
+                 horizon=0, env_id_offset=0, philox_seed=None,
+                 normal_precision="fp64", track_history=None, **config):
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "VectorRLToyEnv needs a CUDA device: the step path is CUDA "
+                "only, there is no CPU fallback")
+        self._lib = _lib.load()
+        self.num_envs = int(num_envs)
+        assert self.num_envs > 0
+        self.device = torch.device(
+            "cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        assert noise in ("philox", "replay", "numpy")
+        self.noise = noise
+        self.autoreset = bool(autoreset)
+        self.horizon = int(horizon)
+        self.env_id_offset = int(env_id_offset)
+        assert normal_precision in ("fp64", "fast")
+        self.normal_mode = (_lib.MDPP_NORMAL_FAST if normal_precision == "fast"
+                            else _lib.MDPP_NORMAL_F64)
+        # the state history behind get_augmented_state() costs one extra
+        # store per step; on by default for gym-style (non-autoreset) use
+        self.track_history = (not self.autoreset) if track_history is None \
+            else bool(track_history)
+        self.spec = parse_config(config)
+        self.config = self.spec.config
+        self.seed_dict = self.spec.seed_dict
+        if philox_seed is None:
+            philox_seed = self.seed_dict["env"]
+            if philox_seed is None:
+                philox_seed = int(np.random.SeedSequence().entropy & (2**63 - 1))
+        self.philox_seed = int(philox_seed) & (2**64 - 1)
+        self._step_index = 0
+        self._ctx = C.c_void_p()
+        _lib.check(self._lib, None,
+                   self._lib.mdpp_create(self.device.index, C.byref(self._ctx)))
+        if self.spec.kind == "discrete":
+            self._init_discrete()
+        else:
+            raise NotImplementedError("continuous backend: see continuous.py")
+        # rl_toy_env.py:831-833: the constructor ends with reset(seed=env seed)
+        self.curr_obs, _ = self.reset(seed=self.seed_dict["env"],
+                                      options={"_ctor": True})
+
+    # ------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.mdpp_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        _lib.check(self._lib, self._ctx, rc)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------
+    # discrete backend
+    # ------------------------------------------------------------------
+    def _init_discrete(self):
+        sp = self.spec
+        self.tables = tb = build_discrete_tables(sp)
+        self.transition_matrix = tb.transition
+        self.rewardable_sequences = tb.rewardable_sequences
+        self.reward_matrix = tb.reward_matrix
+        self.observation_space = DiscreteSpace(
+            tb.n_states, seed=self.seed_dict.get("relevant_state_space"))
+        self.action_space = DiscreteSpace(
+            tb.n_actions, seed=self.seed_dict.get("relevant_action_space"))
+        self.has_pnoise = bool(sp.transition_noise)
+        self.has_rnoise = sp.has_reward_noise
+        N, dev = self.num_envs, self.device
+        g = _lib.DiscreteGroup()
+        g.n_states, g.n_actions = tb.n_states, tb.n_actions
+        g.sequence_length, g.delay = sp.sequence_length, sp.delay
+        g.reward_every_n_steps = sp.reward_every_n_steps
+        g.custom_reward = int(sp.use_custom_mdp)
+        g.n_sequences = int(tb.sequences.shape[0])
+        g.has_transition_noise = int(self.has_pnoise)
+        g.has_reward_noise = int(self.has_rnoise)
+        g.transition_noise = sp.transition_noise
+        g.reward_noise_std = sp.reward_noise_std
+        g.reward_scale, g.reward_shift = sp.reward_scale, sp.reward_shift
+        g.term_state_reward = sp.term_state_reward
+        keep = [tb.transition, tb.terminal_mask, tb.init_cdf, tb.noise_cdf,
+                tb.sequences, tb.sequence_rewards, tb.reward_matrix]
+        hp = [None if a is None else a.ctypes.data_as(C.c_void_p) for a in keep]
+        (g.transition, g.terminal, g.init_cdf, g.noise_cdf, g.sequences,
+         g.sequence_rewards, g.reward_matrix) = hp
+        g.env_begin, g.env_count = 0, N
+        self._check(self._lib.mdpp_set_discrete_groups(self._ctx, C.byref(g), 1))
+        self.n_groups = 1
+
+        self._cur = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._key = torch.zeros(N, dtype=torch.int64, device=dev)
+        self._t = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._episode = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._ring = torch.zeros((max(sp.delay, 1), N), dtype=torch.float64,
+                                 device=dev) if sp.delay > 0 else None
+        self._hist_depth = sp.sequence_length + sp.delay + 1
+        self._history = torch.zeros((self._hist_depth, N), dtype=torch.int32,
+                                    device=dev) if self.track_history else None
+        self._stats = torch.zeros((self.n_groups, _lib.MDPP_N_STATS),
+                                  dtype=torch.float64, device=dev)
+        st = _lib.DiscreteState()
+        st.n_envs = N
+        st.cur_state, st.seq_key = _ptr(self._cur), _ptr(self._key)
+        st.t_episode, st.episode = _ptr(self._t), _ptr(self._episode)
+        st.ring = _ptr(self._ring)
+        st.ring_depth = sp.delay
+        st.history_depth = self._hist_depth
+        st.history = _ptr(self._history)
+        st.stats = _ptr(self._stats)
+        self._state = st
+        if self.noise == "numpy":
+            self._init_numpy_streams()
+
+    def _init_numpy_streams(self):
+        """Per-lane PCG64 streams; lane 0 = the reference's own (appendix C):
+        S continues after the P-table draws, E is re-seeded at the first reset."""
+        sd = self.seed_dict
+        self._rng_S = []
+        for i in range(self.num_envs):
+            s = sd.get("relevant_state_space")
+            rng, _ = np_random(None if s is None else s + i)
+            self._rng_S.append(rng)
+        if not self.spec.use_custom_mdp:
+            # replay lane 0's consumption during P generation
+            S, A = self.tables.n_states, self.tables.n_actions
+            from .tables import _next_set_probabilities
+            rng = self._rng_S[0]
+            for s in range(S):
+                if self.spec.maximally_connected:
+                    p = None if self.spec.diameter == 1 else \
+                        _next_set_probabilities(s, S, A)
+                    rng.choice(S, size=A, p=p, replace=False)
+                else:
+                    p = _next_set_probabilities(s, S, A)
+                    for _ in range(A):
+                        rng.choice(S, size=1, p=p)
+        self._rng_E = [None] * self.num_envs
+
+    def _opts(self, T, noise_mode=None):
+        o = _lib.StepOpts()
+        o.n_steps = T
+        if noise_mode is None:
+            noise_mode = {"philox": _lib.MDPP_NOISE_PHILOX,
+                          "replay": _lib.MDPP_NOISE_REPLAY,
+                          "numpy": _lib.MDPP_NOISE_REPLAY}[self.noise]
+            if not (self.has_pnoise or self.has_rnoise) and self.noise == "philox":
+                pass  # philox still drives resets
+        o.noise_mode = noise_mode
+        o.autoreset = int(self.autoreset)
+        o.horizon = self.horizon
+        o.normal_mode = self.normal_mode
+        o.seed = self.philox_seed
+        o.step_index = self._step_index
+        o.env_id_offset = self.env_id_offset
+        return o
+
+    # ------------------------------------------------------------------
+    def reset(self, seed=None, options=None):
+        """(obs, info) like RLToyEnv.reset (:2217).  options: {"mask": bool[N],
+        "init_state": int[N], "reset_u": float64[N] (replay mode)}."""
+        options = options or {}
+        N, dev = self.num_envs, self.device
+        mask = options.get("mask")
+        if mask is not None:
+            mask = torch.as_tensor(mask, device=dev).to(torch.uint8).contiguous()
+        init = options.get("init_state")
+        if init is not None:
+            init = torch.as_tensor(init, device=dev).to(torch.int32).contiguous()
+        reset_u = options.get("reset_u")
+        if self.noise == "numpy" and init is None:
+            if seed is not None:
+                for i in range(N):
+                    self._rng_E[i], _ = np_random(seed + i)
+            elif self._rng_E[0] is None:
+                for i in range(N):
+                    self._rng_E[i], _ = np_random(None)
+            m = None if mask is None else mask.cpu().numpy()
+            reset_u = np.zeros(N)
+            for i in range(N):
+                if m is None or m[i]:
+                    reset_u[i] = self._rng_E[i].random()
+        elif (seed is not None and self.noise == "philox"
+              and not options.get("_ctor")):
+            # re-keying the counter-based streams is the analogue of re-seeding
+            self.philox_seed = int(seed) & (2**64 - 1)
+        if reset_u is not None:
+            reset_u = torch.as_tensor(reset_u, dtype=torch.float64,
+                                      device=dev).contiguous()
+        obs = torch.empty(N, dtype=torch.int64, device=dev)
+        mode = _lib.MDPP_NOISE_REPLAY if reset_u is not None \
+            else _lib.MDPP_NOISE_PHILOX
+        if (init is None and reset_u is None and self.noise == "replay"
+                and not options.get("_ctor")):
+            raise ValueError("replay mode: pass options['reset_u'] or "
+                             "options['init_state'] to reset()")
+        opts = self._opts(1, mode)
+        self._check(self._lib.mdpp_discrete_reset(
+            self._ctx, C.byref(self._state), _ptr(mask), _ptr(init),
+            _ptr(reset_u), _ptr(obs), C.byref(opts), self._stream()))
+        self.curr_obs = obs
+        return self._cast_obs(obs), {}
+
+    def _cast_obs(self, obs):
+        dt = np.dtype(self.spec.dtype_o)
+        if dt == np.int64:
+            return obs
+        return obs.to(getattr(torch, dt.name))
+
+    def step(self, actions, replay=None):
+        """(obs, reward, terminated, truncated, info) like RLToyEnv.step
+        (:1992).  `replay`: dict with "transition_u", "reward_noise",
+        "reset_u" float64[N] arrays (noise='replay')."""
+        out = self.rollout(1, actions=torch.as_tensor(actions).reshape(1, -1),
+                           replay=None if replay is None else
+                           {k: torch.as_tensor(v).reshape(1, -1)
+                            for k, v in replay.items()})
+        self.curr_obs = out["obs"][0]
+        return (self._cast_obs(out["obs"][0]), out["reward"][0],
+                out["terminated"][0], out["truncated"][0],
+                {"final_obs": out["final_obs"][0]})
+
+    def rollout(self, n_steps, actions=None, replay=None, out=None,
+                want_final_obs=True):
+        """T fused steps in ONE kernel launch.  actions: int[T, N] tensor or
+        None (uniform random policy drawn on device).  Returns dict of
+        time-major [T, N] tensors: obs, final_obs, reward, terminated,
+        truncated."""
+        T, N, dev = int(n_steps), self.num_envs, self.device
+        if actions is not None:
+            actions = torch.as_tensor(actions, device=dev)
+            if actions.dtype != torch.int32:
+                actions = actions.to(torch.int32)
+            actions = actions.contiguous()
+            assert actions.shape == (T, N), (actions.shape, (T, N))
+        io = _lib.DiscreteIO()
+        if out is None:
+            out = {
+                "obs": torch.empty((T, N), dtype=torch.int64, device=dev),
+                "reward": torch.empty((T, N), dtype=torch.float64, device=dev),
+                "terminated": torch.empty((T, N), dtype=torch.bool, device=dev),
+                "truncated": torch.empty((T, N), dtype=torch.bool, device=dev),
+            }
+            if want_final_obs:
+                out["final_obs"] = torch.empty((T, N), dtype=torch.int64,
+                                               device=dev)
+        io.actions = _ptr(actions)
+        io.obs, io.reward = _ptr(out.get("obs")), _ptr(out.get("reward"))
+        io.final_obs = _ptr(out.get("final_obs"))
+        io.terminated = _ptr(out.get("terminated"))
+        io.truncated = _ptr(out.get("truncated"))
+        keep = []
+        if self.noise == "numpy":
+            replay = self._draw_numpy(T)
+        if self.noise in ("replay", "numpy"):
+            replay = replay or {}
+            for name, field in (("transition_u", "replay_transition_u"),
+                                ("reward_noise", "replay_reward_noise"),
+                                ("reset_u", "replay_reset_u")):
+                if name in replay and replay[name] is not None:
+                    t = torch.as_tensor(replay[name], dtype=torch.float64,
+                                        device=dev).reshape(T, N).contiguous()
+                    keep.append(t)
+                    setattr(io, field, _ptr(t))
+        opts = self._opts(T)
+        self._check(self._lib.mdpp_discrete_rollout(
+            self._ctx, C.byref(self._state), C.byref(io), C.byref(opts),
+            self._stream()))
+        self._step_index += T
+        return out
+
+    def _draw_numpy(self, T):
+        assert not self.autoreset, \
+            "noise='numpy' needs explicit resets (draw order is host-driven)"
+        N = self.num_envs
+        rep = {}
+        if self.has_pnoise:
+            rep["transition_u"] = np.array(
+                [[self._rng_S[i].random() for i in range(N)] for _ in range(T)])
+        if self.has_rnoise:
+            std = self.spec.reward_noise_std
+            rep["reward_noise"] = np.array(
+                [[self._rng_E[i].normal(0, std) for i in range(N)]
+                 for _ in range(T)])
+        return rep
+
+    # ------------------------------------------------------------------
+    def get_augmented_state(self):
+        """Batched analogue of RLToyEnv.get_augmented_state (:2127):
+        curr_state int64[N], curr_obs, augmented_state float64[N, L+d+1]
+        (NaN where the reference has NaN)."""
+        if self._history is None:
+            raise RuntimeError("construct with track_history=True to use "
+                               "get_augmented_state()")
+        H = self._hist_depth
+        idx = (self._step_index - torch.arange(H - 1, -1, -1,
+                                               device=self.device)) % H
+        hist = self._history[idx].to(torch.float64).t().contiguous()  # [N, H]
+        age = torch.arange(H - 1, -1, -1, device=self.device)[None, :]
+        hist = torch.where(age <= self._t[:, None].to(torch.int64), hist,
+                           torch.full_like(hist, float("nan")))
+        return {"curr_state": self._cur.to(torch.int64),
+                "curr_obs": self.curr_obs, "augmented_state": hist}
+
+    def episode_stats(self, reduce=False):
+        """Per-group counters of rl_toy_env.py:2360-2369 summed over envs and
+        episodes; `reduce=True` all-reduces over torch.distributed ranks."""
+        stats = self._stats.clone()
+        if reduce:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        host = stats.cpu().numpy()
+        return {name: host[:, i].copy() for i, name in enumerate(_lib.STAT_NAMES)}

@@ -1,0 +1,102 @@
+"""numpy restatement of mdp_playground_b200/csrc/philox.cuh (TEST ONLY).
+
+Philox4x32-10 (Salmon et al., SC'11) with the same counter layout and draw
+conversions as the CUDA kernels, vectorised over environments, so the oracle
+can reproduce the native-noise trajectories: integer words and the 53-bit
+uniforms bit for bit, normals to libm accuracy (device log/cospi vs numpy).
+"""
+import numpy as np
+
+STREAM_STEP, STREAM_RESET, STREAM_ACTION, STREAM_IMAGE = 0, 1, 2, 3
+STREAM_NORMAL, STREAM_AUTORESET = 4, 5
+STREAM_STATE_NOISE, STREAM_RESET_BOX = 8, 64
+
+_M0, _M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_W0, _W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+_LO = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, seed):
+    """Counters broadcast to a common shape; returns 4 uint32 arrays."""
+    c0, c1, c2, c3 = np.broadcast_arrays(
+        *(np.asarray(c, dtype=np.uint32) for c in (c0, c1, c2, c3)))
+    c0, c1, c2, c3 = (c.astype(np.uint64) for c in (c0, c1, c2, c3))
+    k0 = np.uint32(seed & 0xFFFFFFFF)
+    k1 = np.uint32((seed >> 32) & 0xFFFFFFFF)
+    with np.errstate(over="ignore"):
+        for _ in range(10):
+            p0 = _M0 * c0
+            p1 = _M1 * c2
+            n0 = (p1 >> np.uint64(32)) ^ c1 ^ np.uint64(k0)
+            n2 = (p0 >> np.uint64(32)) ^ c3 ^ np.uint64(k1)
+            c1 = p1 & _LO
+            c3 = p0 & _LO
+            c0, c2 = n0 & _LO, n2 & _LO
+            k0 = np.uint32(k0 + _W0)
+            k1 = np.uint32(k1 + _W1)
+    return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
+
+
+def uniform53(lo, hi):
+    x = (hi.astype(np.uint64) << np.uint64(32)) | lo.astype(np.uint64)
+    return (x >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def uniform32(w):
+    return (w.astype(np.float64) + 0.5) * (1.0 / 4294967296.0)
+
+
+def normal_pair_f64(a, b):
+    """Box-Muller pair (philox.cuh normal_pair_f64)."""
+    r = np.sqrt(-2.0 * np.log(uniform32(a)))
+    ang = 2.0 * np.pi * uniform32(b)
+    return r * np.cos(ang), r * np.sin(ang)
+
+
+def normal_pair_fast(a, b):
+    """fp32 restatement of philox.cuh normal_pair_fast (the device uses SFU
+    approximations, so agreement is ~1e-6 relative, not bitwise)."""
+    u1 = ((a >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) \
+        * np.float32(1.0 / 16777216.0)
+    u2 = ((b >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) \
+        * np.float32(1.0 / 16777216.0)
+    r = np.sqrt(np.float32(-1.3862943611198906) * np.log2(u1))
+    ang = np.float32(6.283185307179586) * u2
+    return ((r * np.cos(ang)).astype(np.float64),
+            (r * np.sin(ang)).astype(np.float64))
+
+
+def _quad_words(seed, env_ids, step, stream):
+    quad = int(step) >> 2
+    return philox4x32_10(env_ids, quad & 0xFFFFFFFF, (quad >> 32) & 0xFFFFFFFF,
+                         stream, seed)
+
+
+def step_noise(seed, env_ids, step, want_normal=True, fast=False):
+    """(transition uniform, N(0,1)) of global step `step`.  The draws come in
+    groups of 4 steps (counter = step >> 2): STREAM_STEP word j is the 32-bit
+    transition uniform of step 4q+j; STREAM_NORMAL words (0,1) and (2,3) feed
+    two Box-Muller pairs = the 4 reward normals."""
+    j = int(step) & 3
+    u = uniform32(_quad_words(seed, env_ids, step, STREAM_STEP)[j])
+    z = None
+    if want_normal:
+        w = _quad_words(seed, env_ids, step, STREAM_NORMAL)
+        pair = normal_pair_fast if fast else normal_pair_f64
+        z = pair(w[0], w[1])[j] if j < 2 else pair(w[2], w[3])[j - 2]
+    return u, z
+
+
+def autoreset_uniform(seed, env_ids, step):
+    """32-bit uniform of the same-step auto-reset after global step `step`."""
+    return uniform32(_quad_words(seed, env_ids, step, STREAM_AUTORESET)[int(step) & 3])
+
+
+def step_words(seed, env_ids, step, stream=STREAM_STEP):
+    step = int(step)
+    return philox4x32_10(env_ids, step & 0xFFFFFFFF, (step >> 32) & 0xFFFFFFFF,
+                         stream, seed)
+
+
+def mulhi32(w, n):
+    return ((w.astype(np.uint64) * np.uint64(n)) >> np.uint64(32)).astype(np.int64)

@@ -1,0 +1,166 @@
+"""Batched numpy oracle for the discrete step path (TEST INFRASTRUCTURE ONLY).
+
+N environments sharing the tables of one `ScalarRLToyEnv` (the scalar
+oracle, itself pinned to the reference), stepped with the batched-API
+semantics the CUDA path adds on top of the reference: same-step auto-reset,
+`horizon` truncation, and noise from replayed arrays or from the Philox
+streams of oracle/philox.py.  Per-env arithmetic follows
+rl_toy_env.py:1602-1622 (transition), :1817-1846 + :1968-1990 (reward),
+:2098-2109 (done / terminal reward), :2250-2278 (reset).  Plain Python loop
+over time, numpy over environments.
+"""
+import numpy as np
+
+from . import philox as px
+
+
+class VectorDiscreteOracle:
+    def __init__(self, scalar_env, num_envs, autoreset=False, horizon=0,
+                 seed=0, env_id_offset=0, fast_normal=False):
+        e = scalar_env
+        assert e.kind == "discrete"
+        self.N = int(num_envs)
+        self.S, self.A = int(e.state_space_size), int(e.action_space_size)
+        self.L, self.d = e.sequence_length, e.delay
+        self.every_n = int(e.reward_every_n_steps)
+        self.P = np.array(e.transition_matrix, dtype=np.int64)
+        self.term = np.zeros(self.S, dtype=bool)
+        self.term[np.array(e.terminal_states, dtype=np.int64)] = True
+        self.init_cdf = e.init_cdf
+        self.custom = e.use_custom_mdp
+        if self.custom:
+            self.R = np.asarray(e.reward_matrix, dtype=np.float64)
+        else:
+            self.seq = {k: float(v) for k, v in e.rewardable_sequences.items()
+                        if len(k) == self.L}
+        self.has_pnoise = bool(e.transition_noise)
+        self.noise_cdf = e.noise_cdf if self.has_pnoise else None
+        self.has_rnoise = e.has_reward_noise and e.reward_noise_std is not None
+        self.r_std = e.reward_noise_std
+        self.scale, self.shift = e.reward_scale, e.reward_shift
+        self.term_reward = e.term_state_reward
+        self.autoreset, self.horizon = autoreset, int(horizon)
+        self.seed = int(seed)
+        self.fast_normal = fast_normal
+        self.gid = (np.arange(self.N, dtype=np.int64) + env_id_offset).astype(
+            np.uint32)
+        self.step_index = 0
+        self.cur = np.zeros(self.N, dtype=np.int64)
+        self.t = np.zeros(self.N, dtype=np.int64)
+        self.episode = np.zeros(self.N, dtype=np.int64)
+        self.window = [[] for _ in range(self.N)]   # last L states
+        self.fifo = [[0.0] * self.d for _ in range(self.N)]
+        self.stats = dict(episodes=0, transitions=0, reward=0.0,
+                          noisy_transitions=0, abs_reward_noise=0.0,
+                          returned_reward=0.0, terminated=0)
+
+    # -- draws -------------------------------------------------------------
+    def _reset_u(self, idx):
+        w = px.philox4x32_10(self.gid[idx], self.episode[idx].astype(np.uint32),
+                             0, px.STREAM_RESET, self.seed)
+        return px.uniform53(w[0], w[1])
+
+    def reset(self, mask=None, init_state=None, reset_u=None):
+        idx = np.arange(self.N) if mask is None else np.nonzero(mask)[0]
+        if init_state is not None:
+            s0 = np.asarray(init_state, dtype=np.int64)[idx]
+        else:
+            u = self._reset_u(idx) if reset_u is None else np.asarray(reset_u)[idx]
+            s0 = np.minimum(np.searchsorted(self.init_cdf, u, side="right"),
+                            self.S - 1)
+        self.stats["episodes"] += int((self.t[idx] > 0).sum())
+        for i, s in zip(idx, s0):
+            self._reset_one(i, int(s))
+        return self.cur.copy()
+
+    def _reset_one(self, i, s0):
+        self.cur[i] = s0
+        self.t[i] = 0
+        self.episode[i] += 1
+        self.window[i] = [s0]
+        self.fifo[i] = [0.0] * self.d
+
+    def rollout(self, T, actions=None, replay=None):
+        N = self.N
+        obs = np.zeros((T, N), dtype=np.int64)
+        final_obs = np.zeros((T, N), dtype=np.int64)
+        reward = np.zeros((T, N), dtype=np.float64)
+        term = np.zeros((T, N), dtype=bool)
+        trunc = np.zeros((T, N), dtype=bool)
+        for t in range(T):
+            step = self.step_index + t
+            if actions is not None:
+                a = np.asarray(actions[t], dtype=np.int64)
+            else:
+                w = px.step_words(self.seed, self.gid, step, px.STREAM_ACTION)
+                a = px.mulhi32(w[0], self.A)
+            a = np.minimum(a, self.A - 1)
+            u_tr = n_rw = None
+            if replay is not None:
+                if self.has_pnoise:
+                    u_tr = np.asarray(replay["transition_u"][t])
+                if self.has_rnoise:
+                    n_rw = np.asarray(replay["reward_noise"][t])
+            elif self.has_pnoise or self.has_rnoise:
+                u_tr, z = px.step_noise(self.seed, self.gid, step,
+                                        want_normal=self.has_rnoise,
+                                        fast=self.fast_normal)
+                if self.has_rnoise:
+                    n_rw = self.r_std * z
+            nxt = self.P[self.cur, a]
+            if self.has_pnoise:
+                noisy = np.array([
+                    min(int(np.searchsorted(self.noise_cdf[nxt[i]], u_tr[i],
+                                            side="right")), self.S - 1)
+                    for i in range(N)], dtype=np.int64)
+                self.stats["noisy_transitions"] += int((noisy != nxt).sum())
+                nxt = noisy
+            for i in range(N):
+                s_prev = int(self.cur[i])
+                win = self.window[i]
+                win.append(int(nxt[i]))
+                if len(win) > self.L:
+                    del win[0]
+                self.t[i] += 1
+                ti = int(self.t[i])
+                if self.custom:
+                    r = float(self.R[s_prev, a[i]])
+                elif ti >= self.L:
+                    r = self.seq.get(tuple(win), 0.0)
+                else:
+                    r = 0.0
+                fifo = self.fifo[i]
+                fifo.append(r)
+                r = fifo.pop(0)
+                if ti % self.every_n != 0:
+                    r = 0.0
+                self.stats["reward"] += r
+                if self.has_rnoise:
+                    self.stats["abs_reward_noise"] += abs(float(n_rw[i]))
+                    r = r + float(n_rw[i])
+                r = r * self.scale
+                r = r + self.shift
+                done = bool(self.term[nxt[i]])
+                if done:
+                    r = r + self.term_reward * self.scale
+                tr = self.horizon > 0 and ti >= self.horizon
+                reward[t, i], term[t, i], trunc[t, i] = r, done, tr
+                final_obs[t, i] = nxt[i]
+                self.cur[i] = nxt[i]
+                self.stats["returned_reward"] += r
+                self.stats["terminated"] += int(done)
+                self.stats["transitions"] += 1
+                if self.autoreset and (done or tr):
+                    if replay is not None:
+                        u = float(replay["reset_u"][t][i])
+                    else:
+                        u = float(px.autoreset_uniform(
+                            self.seed, self.gid[i:i + 1], step)[0])
+                    s0 = min(int(np.searchsorted(self.init_cdf, u,
+                                                 side="right")), self.S - 1)
+                    self._reset_one(i, s0)
+                    self.stats["episodes"] += 1
+                obs[t, i] = self.cur[i]
+        self.step_index += T
+        return dict(obs=obs, final_obs=final_obs, reward=reward,
+                    terminated=term, truncated=trunc)

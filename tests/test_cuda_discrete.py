@@ -1,0 +1,243 @@
+"""GPU parity tests of the discrete step path: CUDA kernels (through the
+C ABI) against the reference's golden vectors, the scalar oracle and the
+batched oracle.  Bit-exact for states / flags / fp64 rewards whenever the
+noise is off or replayed; native Philox noise: states bit-exact against the
+oracle's Philox restatement, rewards to libm accuracy, and distribution
+tests (chi-squared / KS) with the thresholds written below."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.scalar_env import ScalarRLToyEnv
+from oracle.vector_oracle import VectorDiscreteOracle
+from tests import golden_util as gu
+from tests.golden.cases import CASES
+from tests.test_vector_oracle import CASES_D, replay_golden_through
+
+pytestmark = pytest.mark.gpu
+
+
+def make_env(*a, **k):
+    from mdp_playground_b200 import VectorRLToyEnv
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return VectorRLToyEnv(*a, **k)
+
+
+def scalar_oracle(cfg):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return ScalarRLToyEnv(**cfg)
+
+
+@pytest.mark.parametrize("name", CASES_D)
+def test_cuda_replays_reference_golden(name):
+    """Recorded reference draws replayed through the kernels: bit-exact."""
+    g = gu.load(name)
+    K = g["done"].shape[0]
+    env = make_env(K, noise="replay", **gu.case_config(name))
+    assert np.array_equal(env.transition_matrix, g["P"])
+
+    def vec_reset(mask, reset_u):
+        obs, _ = env.reset(options={"mask": mask, "reset_u": reset_u})
+        return obs.cpu().numpy()
+
+    def vec_step(a, u, n):
+        obs, r, term, trunc, _ = env.step(
+            a, replay=dict(transition_u=np.nan_to_num(u),
+                           reward_noise=np.nan_to_num(n)))
+        assert not trunc.any()
+        return obs.cpu().numpy(), r.cpu().numpy(), term.cpu().numpy()
+
+    replay_golden_through(vec_reset, vec_step, g)
+
+
+@pytest.mark.parametrize("name", ["c1_seq1", "c2_seq3_del2_noise",
+                                  "rdist_scale_shift", "custom_8x5",
+                                  "diam3_seq4"])
+def test_same_seed_drop_in_numpy_streams(name):
+    """noise='numpy': one env, same config and seed as the (oracle of the)
+    reference => the same trajectory, constructor included."""
+    cfg = gu.case_config(name)
+    ref = scalar_oracle(gu.case_config(name))
+    env = make_env(1, noise="numpy", **cfg)
+    assert int(env.curr_obs[0]) == int(ref.curr_obs)
+    rng = np.random.default_rng(9)
+    for t in range(150):
+        a = int(rng.integers(ref.action_space_size))
+        o1, r1, d1, _, _ = ref.step(a)
+        o2, r2, d2, tr2, _ = env.step([a])
+        assert int(o2[0]) == int(o1) and float(r2[0]) == float(r1), t
+        assert bool(d2[0]) == d1
+        if d1 or t % 20 == 19:
+            o1, _ = ref.reset()
+            o2, _ = env.reset()
+            assert int(o2[0]) == int(o1)
+
+
+@pytest.mark.parametrize("name,N,T,autoreset,horizon", [
+    ("c2_every1", 1500, 40, True, 9),
+    ("c2_seq3_del2_noise", 700, 33, True, 0),
+    ("big50", 300, 30, True, 11),
+    ("diam3_seq4", 257, 25, False, 0),
+    ("custom_8x5", 300, 20, True, 5),
+    ("notmax_diam2", 300, 40, True, 13),
+])
+def test_philox_rollout_matches_oracle(name, N, T, autoreset, horizon):
+    cfg = gu.case_config(name)
+    ora = VectorDiscreteOracle(scalar_oracle(gu.case_config(name)), N,
+                               autoreset=autoreset, horizon=horizon, seed=77,
+                               env_id_offset=1000)
+    env = make_env(N, autoreset=autoreset, horizon=horizon, philox_seed=77,
+                   env_id_offset=1000, **cfg)
+    ora.reset()  # mirrors the reset at the end of the env constructor
+    assert np.array_equal(env._cur.cpu().numpy(), ora.cur)
+    for part, acts in ((T, None), (7, "given")):
+        actions = None
+        if acts:
+            actions = np.random.default_rng(3).integers(
+                0, ora.A, size=(part, N))
+        want = ora.rollout(part, actions=actions)
+        got = env.rollout(part, actions=actions)
+        for k in ("obs", "final_obs", "terminated", "truncated"):
+            assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+        np.testing.assert_allclose(got["reward"].cpu().numpy(), want["reward"],
+                                   rtol=1e-12, atol=1e-12)
+    st = env.episode_stats()
+    for k in ("episodes", "transitions", "noisy_transitions", "terminated"):
+        assert st[k][0] == ora.stats[k], k
+    for k in ("reward", "abs_reward_noise"):
+        np.testing.assert_allclose(st[k][0], ora.stats[k], rtol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["c2_every1", "big50"])
+def test_fast_normal_matches_oracle_within_1e5(name):
+    """normal_precision='fast' (SFU Box-Muller): states exact, rewards within
+    1e-5 absolute of the oracle's fp32 restatement."""
+    cfg = gu.case_config(name)
+    N, T = 1000, 24
+    ora = VectorDiscreteOracle(scalar_oracle(gu.case_config(name)), N,
+                               autoreset=True, horizon=10, seed=5,
+                               fast_normal=True)
+    env = make_env(N, autoreset=True, horizon=10, philox_seed=5,
+                   normal_precision="fast", **cfg)
+    ora.reset()
+    want, got = ora.rollout(T), env.rollout(T)
+    for k in ("obs", "final_obs", "terminated", "truncated"):
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+    np.testing.assert_allclose(got["reward"].cpu().numpy(), want["reward"],
+                               rtol=0, atol=1e-5 * max(1.0, cfg.get("reward_noise", 1.0)))
+
+
+def test_rollout_equals_repeated_steps():
+    cfg = gu.case_config("c2_every1")
+    a = make_env(513, autoreset=True, horizon=10, **cfg)
+    b = make_env(513, autoreset=True, horizon=10, **gu.case_config("c2_every1"))
+    ra = a.rollout(19)
+    for t in range(19):
+        acts = None
+        rb = b.rollout(1)
+        for k in ra:
+            assert torch.equal(ra[k][t], rb[k][0]), (k, t)
+
+
+def test_sharding_invariance():
+    """Global env ids key the noise: 2 shards == 1 big batch."""
+    cfg = lambda: gu.case_config("c2_every1")  # noqa: E731
+    whole = make_env(600, autoreset=True, horizon=12, **cfg())
+    lo = make_env(300, autoreset=True, horizon=12, env_id_offset=0, **cfg())
+    hi = make_env(300, autoreset=True, horizon=12, env_id_offset=300, **cfg())
+    rw, rl, rh = whole.rollout(30), lo.rollout(30), hi.rollout(30)
+    for k in rw:
+        assert torch.equal(rw[k], torch.cat([rl[k], rh[k]], dim=1)), k
+
+
+def test_augmented_state_and_masked_reset():
+    cfg = gu.case_config("c2_every1")
+    ref = scalar_oracle(gu.case_config("c2_every1"))
+    env = make_env(3, noise="numpy", **cfg)
+    for t in range(9):
+        a = t % 8
+        ref.step(a)
+        env.step([a, a, a])
+        aug = env.get_augmented_state()["augmented_state"][0].cpu().numpy()
+        want = np.array(ref.augmented_state, dtype=np.float64)
+        assert np.array_equal(np.isnan(aug), np.isnan(want)), (t, aug, want)
+        assert np.array_equal(np.nan_to_num(aug), np.nan_to_num(want))
+    before = env._cur.clone()
+    env.reset(options={"mask": [False, True, False]})
+    assert int(env._t[0]) == 9 and int(env._t[1]) == 0
+    assert int(env._cur[0]) == int(before[0])
+
+
+def test_transition_noise_distribution_chi2():
+    """chi-squared of the noisy next-state histogram against the reference's
+    probabilities (1-p at P[s,a], p/(S-1) elsewhere); 7 dof, reject at
+    p < 1e-4 (statistic > 29.9)."""
+    cfg = dict(gu.case_config("c1_seq1"), transition_noise=0.25,
+               terminal_state_density=0.0)
+    N = 200000
+    env = make_env(N, philox_seed=123, **cfg)
+    s0 = 3
+    env.reset(options={"init_state": np.full(N, s0)})
+    out = env.rollout(1, actions=np.full((1, N), 2))
+    nxt = int(env.transition_matrix[s0, 2])
+    counts = np.bincount(out["final_obs"][0].cpu().numpy(), minlength=8)
+    probs = np.full(8, 0.25 / 7)
+    probs[nxt] = 0.75
+    chi2 = float(((counts - N * probs) ** 2 / (N * probs)).sum())
+    assert chi2 < 29.9, (chi2, counts)
+    assert env.episode_stats()["noisy_transitions"][0] == N - counts[nxt]
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fast"])
+def test_reward_noise_distribution_ks(precision):
+    """Kolmogorov-Smirnov of the reward noise against N(0, sigma); reject at
+    p < 1e-4 (D * sqrt(n) > 2.23).  Also mean/variance within 5 sigma."""
+    from scipy import special
+    sigma = 0.25
+    cfg = dict(gu.case_config("c1_seq1"), reward_noise=sigma,
+               reward_density=0.0001, terminal_state_density=0.0)
+    N = 200000
+    env = make_env(N, philox_seed=321, normal_precision=precision, **cfg)
+    out = env.rollout(5, want_final_obs=False)
+    r = out["reward"].cpu().numpy().ravel()
+    # reward = {0, 1} + noise: remove the integer part the sequences paid
+    z = r - np.round(r)
+    zs = np.sort(z) / sigma
+    cdf = special.ndtr(zs)
+    n = zs.size
+    d = max(np.max(cdf - np.arange(n) / n), np.max(np.arange(1, n + 1) / n - cdf))
+    assert d * np.sqrt(n) < 2.23, d
+    assert abs(z.mean()) < 5 * sigma / np.sqrt(z.size)
+    assert abs(z.var() - sigma ** 2) < 5 * sigma ** 2 * np.sqrt(2 / z.size)
+
+
+def test_init_state_distribution_and_full_size_properties():
+    """BASELINE config #2 at full size (65 536 envs x 1000 steps): properties
+    that need no oracle run -- states in range, terminated <=> terminal
+    state, truncation exactly at the horizon, auto-reset lands on
+    non-terminal states uniformly (chi-squared, 5 dof, < 25.7 at p=1e-4),
+    delayed reward pattern: nothing paid before t > delay."""
+    cfg = gu.case_config("c2_every1")
+    N, T, H = 65536, 1000, 100
+    env = make_env(N, autoreset=True, horizon=H, **cfg)
+    out = env.rollout(T)
+    obs, fin = out["obs"], out["final_obs"]
+    term, trunc = out["terminated"], out["truncated"]
+    assert int(fin.min()) >= 0 and int(fin.max()) < 8
+    mask = torch.zeros(8, dtype=torch.bool, device=fin.device)
+    mask[torch.as_tensor(env.tables.terminal_states, device=fin.device)] = True
+    assert torch.equal(term, mask[fin])
+    reset = term | trunc
+    assert torch.equal(obs[~reset], fin[~reset])
+    assert not mask[obs[reset]].any()
+    counts = torch.bincount(obs[reset], minlength=8).cpu().numpy()[:6]
+    exp = counts.sum() / 6
+    assert ((counts - exp) ** 2 / exp).sum() < 25.7
+    st = env.episode_stats()
+    assert st["transitions"][0] == N * T
+    assert st["episodes"][0] == int(reset.sum())
+    assert st["terminated"][0] == int(term.sum())
