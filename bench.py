@@ -200,7 +200,9 @@ def run_gpu_arm(args):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         env = VectorRLToyEnv(N, device=dev, autoreset=True, horizon=100,
-                             env_id_offset=rank * N, **workload_config())
+                             env_id_offset=rank * N,
+                             normal_precision=args.normal, **workload_config())
+    env.set_jit(not args.no_jit)
     # synthetic actions: Philox, seed 0xC0FFEE + rank
     gen = torch.Generator(device=dev)
     gen.manual_seed(0xC0FFEE + rank)
@@ -306,14 +308,20 @@ def run_gpu_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "envs_per_gpu": N,
-                       "env_steps_per_launch": T, "noise": "philox",
+                       "env_steps_per_launch": T,
+                       "noise": "philox4x32-10; reward normals: "
+                                + ("fp32 SFU Box-Muller" if args.normal == "fast"
+                                   else "fp64 Box-Muller"),
+                       "kernel_build": "nvrtc-specialised" if env.jit_last_used
+                       else "ahead-of-time",
                        "autoreset": "same-step", "l2_policy":
                        f"inputs+outputs {T * N * 22 / 1e6:.0f} MB per launch "
                        "> 126 MB L2 (no flush needed)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "kernel": "discrete_rollout_kernel<PHILOX,smem>",
+                         "kernel": "mdpp_jit_rollout" if env.jit_last_used
+                         else "discrete_rollout_kernel<PHILOX,smem>",
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_ROLLOUT,
                          "env_steps_per_launch": N * T},
             "single_step_api": {"value": single_sps, "unit": UNIT,
@@ -344,6 +352,11 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=300000)
     ap.add_argument("--ref-sample", type=int, default=100000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--normal", default="fast", choices=["fast", "fp64"],
+                    help="reward-noise normals: SFU fp32 Box-Muller or fp64")
+    ap.add_argument("--no-jit", action="store_true",
+                    help="use the ahead-of-time kernels instead of the "
+                         "NVRTC-specialised one")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -49,10 +49,26 @@ extern "C" {
 
 typedef struct mdpp_ctx mdpp_ctx;
 
+#ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
 int mdpp_abi_version(void);
 int mdpp_create(int device, mdpp_ctx** out_ctx);
 void mdpp_destroy(mdpp_ctx* ctx);
 const char* mdpp_last_error(const mdpp_ctx* ctx);
+#endif
+
+/* Runtime specialisation (NVRTC) of the rollout kernel for single-group
+ * launches.  On by default (MDPP_JIT=0 in the environment, or
+ * mdpp_set_jit(ctx, 0), disables it; the ahead-of-time kernels then run).
+ * mdpp_jit_last_used() tells whether the last rollout ran a specialised
+ * kernel, mdpp_jit_log() why not.  mdpp_jit_selftest() compiles (does not
+ * load) one specialisation with NVRTC only -- no GPU needed -- and returns 0
+ * on success, copying the compiler log into `log`.                          */
+#ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
+void mdpp_set_jit(mdpp_ctx* ctx, int enabled);
+int mdpp_jit_last_used(const mdpp_ctx* ctx);
+const char* mdpp_jit_log(const mdpp_ctx* ctx);
+int mdpp_jit_selftest(char* log, int log_bytes);
+#endif
 
 /* ------------------------------------------------------------------------
  * Discrete environments (replaces RLToyEnv.transition_function :1602-1622,
@@ -93,8 +109,10 @@ typedef struct mdpp_discrete_group {
   int64_t env_count;
 } mdpp_discrete_group;
 
+#ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
 int mdpp_set_discrete_groups(mdpp_ctx* ctx, const mdpp_discrete_group* groups,
                              int32_t n_groups);
+#endif
 
 /* Persistent per-env state, struct-of-arrays, DEVICE pointers owned by the
  * caller.  `ring` holds the reward-delay FIFO (:1970-1973) as a ring of
@@ -146,17 +164,21 @@ typedef struct mdpp_step_opts {
 } mdpp_step_opts;
 
 /* K1/K2: T fused steps, one thread per env, tables staged in shared memory. */
+#ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
 int mdpp_discrete_rollout(mdpp_ctx* ctx, const mdpp_discrete_state* st,
                           const mdpp_discrete_io* io,
                           const mdpp_step_opts* opts, void* cuda_stream);
+#endif
 
 /* K6: (masked) reset.  mask NULL = all envs.  The initial state comes from
  * `init_states` when given, else from the init cdf driven by `replay_reset_u`
  * (MDPP_NOISE_REPLAY) or Philox.  `obs` may be NULL.                        */
+#ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
 int mdpp_discrete_reset(mdpp_ctx* ctx, const mdpp_discrete_state* st,
                         const uint8_t* mask, const int32_t* init_states,
                         const double* replay_reset_u, int64_t* obs,
                         const mdpp_step_opts* opts, void* cuda_stream);
+#endif
 
 #ifdef __cplusplus
 }

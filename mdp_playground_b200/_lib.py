@@ -20,6 +20,7 @@ STAT_NAMES = ("episodes", "transitions", "reward", "noisy_transitions",
 EXPORTED_SYMBOLS = (
     "mdpp_abi_version", "mdpp_create", "mdpp_destroy", "mdpp_last_error",
     "mdpp_set_discrete_groups", "mdpp_discrete_rollout", "mdpp_discrete_reset",
+    "mdpp_set_jit", "mdpp_jit_last_used", "mdpp_jit_log", "mdpp_jit_selftest",
 )
 
 
@@ -100,6 +101,12 @@ def load():
         P, C.POINTER(DiscreteState), C.POINTER(DiscreteIO), C.POINTER(StepOpts), P]
     lib.mdpp_discrete_reset.argtypes = [
         P, C.POINTER(DiscreteState), P, P, P, P, C.POINTER(StepOpts), P]
+    lib.mdpp_set_jit.argtypes = [P, C.c_int]
+    lib.mdpp_set_jit.restype = None
+    lib.mdpp_jit_last_used.argtypes = [P]
+    lib.mdpp_jit_log.argtypes = [P]
+    lib.mdpp_jit_log.restype = C.c_char_p
+    lib.mdpp_jit_selftest.argtypes = [C.c_char_p, C.c_int]
     if lib.mdpp_abi_version() != 1:
         raise RuntimeError("libmdpp_b200.so ABI version mismatch; rebuild")
     _lib = lib

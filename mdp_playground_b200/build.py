@@ -12,15 +12,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmdpp_b200.so")
 SOURCES = ["context.cu", "discrete.cu", "discrete_off.cu", "discrete_replay.cu",
-           "discrete_philox_f64.cu", "discrete_philox_fast.cu"]
-HEADERS = ["internal.h", "philox.cuh", "discrete_kernels.cuh",
-           "../../include/mdpp_b200.h"]
+           "discrete_philox_f64.cu", "discrete_philox_fast.cu", "jit.cu"]
+HEADERS = ["internal.h", "device_types.h", "philox.cuh", "discrete_kernels.cuh",
+           "discrete_launch.h", "../../include/mdpp_b200.h"]
+# device-side sources embedded into the library for the NVRTC specialisation
+EMBEDDED = ["discrete_kernels.cuh", "device_types.h", "philox.cuh",
+            "../../include/mdpp_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
     "-std=c++17", "-Xcompiler", "-fPIC",
+    "-I", os.path.join(HERE, "..", "include"), "-I", os.path.join(HERE, "build"),
 ]
 LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "--shared",
-              "-cudart", "static"]
+              "-cudart", "static", "-ldl"]
 OBJ_DIR = os.path.join(HERE, "build")
 
 
@@ -45,6 +49,12 @@ def build(force=False, verbose=False):
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ_DIR, exist_ok=True)
+    with open(os.path.join(OBJ_DIR, "embedded_sources.inc"), "w") as f:
+        for name in EMBEDDED:
+            ident = os.path.basename(name).replace(".", "_")
+            text = open(os.path.join(CSRC, name)).read()
+            assert ")MDPPSRC\"" not in text
+            f.write(f'static const char* kSrc_{ident} = R"MDPPSRC({text})MDPPSRC";\n')
     jobs = []
     for src in SOURCES:
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))

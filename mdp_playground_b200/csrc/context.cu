@@ -1,5 +1,6 @@
 // Context lifetime, error reporting and host-side packing of the discrete
 // tables into the device blob (LUT / open-addressing hash of sequence keys).
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.h"
@@ -44,6 +45,8 @@ extern "C" int mdpp_create(int device, mdpp_ctx** out_ctx) {
     delete ctx;
     return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
   }
+  const char* jit_env = std::getenv("MDPP_JIT");
+  ctx->jit_enabled = !(jit_env && jit_env[0] == '0');
   ctx->sm_count = prop.multiProcessorCount;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   *out_ctx = ctx;
@@ -64,6 +67,7 @@ static void free_discrete(mdpp_ctx* ctx) {
 extern "C" void mdpp_destroy(mdpp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  jit_release(ctx);
   free_discrete(ctx);
   delete ctx;
 }

@@ -1,0 +1,72 @@
+// Types shared by host and device code of libmdpp_b200.so.  Also compiled by
+// NVRTC (jit.cu), so it only needs the fixed-width integer types.
+#pragma once
+#include "mdpp_b200.h"
+
+namespace mdpp {
+
+// Device-side descriptor of one discrete configuration group.  The tables of
+// the group live in one contiguous, 16-byte aligned blob so that a CTA can
+// stage them into shared memory with 128-bit copies.
+struct DiscreteGroupDev {
+  int32_t S, A, L, delay, every_n, custom_reward, n_seq, key_bits;
+  int32_t has_pnoise, has_rnoise, lookup_kind, hash_shift;  // kind: 0 LUT 1 hash 2 R
+  uint32_t hash_mask;
+  int32_t cdf_log2;    // cdf rows hold 2^cdf_log2 entries (sentinel padded)
+  int32_t cdf_stride;  // = 2^cdf_log2
+  int32_t has_guide;
+  uint64_t key_mask;
+  double p_noise, r_std, scale, shift, term_reward_scaled;
+  // byte offsets inside the blob
+  int32_t off_P, off_term, off_init_cdf, off_noise_cdf;
+  int32_t off_lut, off_hash_keys, off_hash_vals, off_values, off_R, off_guide;
+  int32_t pad1;
+  int32_t blob_bytes;
+  int64_t blob_offset;  // of this group's blob inside the context blob buffer
+  int64_t env_begin, env_count;
+};
+
+struct CtaMapEntry {
+  int32_t group;
+  int32_t chunk;  // chunk index inside the group (units of block size)
+};
+
+enum { LOOKUP_LUT = 0, LOOKUP_HASH = 1, LOOKUP_MATRIX = 2 };
+constexpr int kLutMaxBits = 12;
+constexpr uint64_t kHashEmpty = ~0ull;
+constexpr int kGuideBits = 12;
+constexpr int kGuideEntries = 1 << kGuideBits;
+constexpr uint8_t kGuideMiss = 0xFF;
+
+
+struct RolloutParams {
+  DiscreteGroupDev group0;  // copy of groups[0]: FAST kernels (single group)
+                            // read it from the constant bank / uniform regs
+  const DiscreteGroupDev* groups;
+  const uint8_t* blob;
+  const CtaMapEntry* cta_map;
+  mdpp_discrete_state st;
+  mdpp_discrete_io io;
+  int32_t T, autoreset, horizon;
+  int32_t ring_smem_bytes;
+  uint32_t k0, k1;
+  uint64_t step_index;
+  int64_t env_id_offset;
+};
+
+struct ResetParams {
+  const DiscreteGroupDev* groups;
+  const uint8_t* blob;
+  const CtaMapEntry* cta_map;
+  mdpp_discrete_state st;
+  const uint8_t* mask;
+  const int32_t* init_states;
+  const double* replay_reset_u;
+  int64_t* obs;
+  int32_t noise_mode;
+  uint32_t k0, k1;
+  uint64_t step_index;
+  int64_t env_id_offset;
+};
+
+}  // namespace mdpp

@@ -3,6 +3,7 @@
 // discrete_kernels.cuh and are instantiated per noise mode in
 // discrete_{off,replay,philox_f64,philox_fast}.cu so they compile in parallel.
 #include "discrete_kernels.cuh"
+#include "internal.h"
 
 namespace mdpp {
 
@@ -11,20 +12,6 @@ int launch_rollout_replay(mdpp_ctx*, RolloutParams&, cudaStream_t);
 int launch_rollout_philox_f64(mdpp_ctx*, RolloutParams&, cudaStream_t);
 int launch_rollout_philox_fast(mdpp_ctx*, RolloutParams&, cudaStream_t);
 
-struct ResetParams {
-  const DiscreteGroupDev* groups;
-  const uint8_t* blob;
-  const CtaMapEntry* cta_map;
-  mdpp_discrete_state st;
-  const uint8_t* mask;
-  const int32_t* init_states;
-  const double* replay_reset_u;
-  int64_t* obs;
-  int32_t noise_mode;
-  uint32_t k0, k1;
-  uint64_t step_index;
-  int64_t env_id_offset;
-};
 
 __global__ void __launch_bounds__(kBlock)
 discrete_reset_kernel(const __grid_constant__ ResetParams p) {
@@ -143,6 +130,11 @@ extern "C" int mdpp_discrete_rollout(mdpp_ctx* ctx,
   p.step_index = opts->step_index;
   p.env_id_offset = opts->env_id_offset;
   cudaStream_t s = (cudaStream_t)cuda_stream;
+  if (opts->noise_mode < MDPP_NOISE_OFF || opts->noise_mode > MDPP_NOISE_PHILOX)
+    return fail(ctx, MDPP_EINVAL, "unknown noise_mode");
+  // single-group launches: a kernel compiled for exactly this configuration
+  rc = jit_try_rollout(ctx, p, opts->noise_mode, opts->normal_mode, s);
+  if (rc != 0) return rc < 0 ? rc : MDPP_OK;
   switch (opts->noise_mode) {
     case MDPP_NOISE_OFF: return launch_rollout_off(ctx, p, s);
     case MDPP_NOISE_REPLAY: return launch_rollout_replay(ctx, p, s);

@@ -19,31 +19,42 @@
 // up front (memory- and instruction-level parallelism), then the short
 // state-dependent chain runs.
 #pragma once
-#include "internal.h"
+#include "device_types.h"
 #include "philox.cuh"
 
 namespace mdpp {
 
-constexpr int kBlock = 128;
+constexpr int kBlock = 64;
 constexpr int kChunk = 8;
-// 65 536 envs / 148 SMs = 443 threads per SM: all of them must be resident
-// at once (one wave), so cap registers at 65 536 / 512 = 128 per thread.
-constexpr int kMinBlocksPerSM = 4;
+// 65 536 envs / 148 SMs = 443 threads per SM: all of them must be resident at
+// once (one wave), so cap registers at 65 536 / 512 = 128 per thread.  Small
+// CTAs (64 threads) keep the per-SM load within one CTA of the average
+// (7 vs 6.9 CTAs) -- the kernel is issue-bound, so imbalance is lost time.
+constexpr int kMinBlocksPerSM = 8;
 
-struct RolloutParams {
-  DiscreteGroupDev group0;  // copy of groups[0]: FAST kernels (single group)
-                            // read it from the constant bank / uniform regs
-  const DiscreteGroupDev* groups;
-  const uint8_t* blob;
-  const CtaMapEntry* cta_map;
-  mdpp_discrete_state st;
-  mdpp_discrete_io io;
-  int32_t T, autoreset, horizon;
-  int32_t ring_smem_bytes;
-  uint32_t k0, k1;
-  uint64_t step_index;
-  int64_t env_id_offset;
-};
+
+// Launch-wide scalars: literals in a runtime-specialised build (jit.cu).
+__device__ __forceinline__ int64_t n_envs_of(const RolloutParams& p) {
+#ifdef MDPP_JIT
+  return MDPP_N_ENVS;
+#else
+  return p.st.n_envs;
+#endif
+}
+__device__ __forceinline__ bool autoreset_of(const RolloutParams& p) {
+#ifdef MDPP_JIT
+  return MDPP_AUTORESET != 0;
+#else
+  return p.autoreset != 0;
+#endif
+}
+__device__ __forceinline__ int horizon_of(const RolloutParams& p) {
+#ifdef MDPP_JIT
+  return MDPP_HORIZON;
+#else
+  return p.horizon;
+#endif
+}
 
 __device__ __forceinline__ int32_t ld_stream_i32(const int32_t* p) {
   int32_t v;
@@ -126,6 +137,20 @@ __device__ __forceinline__ GroupView make_view(const DiscreteGroupDev& g,
   v.hash_vals = reinterpret_cast<const uint32_t*>(tab + g.off_hash_vals);
   v.values = reinterpret_cast<const double*>(tab + g.off_values);
   v.R = reinterpret_cast<const double*>(tab + g.off_R);
+#ifdef MDPP_JIT
+  // Runtime-compiled specialisation (jit.cu): every scalar of the (single)
+  // group is a literal, so the compiler folds the branches, unrolls the
+  // searches and drops the dead features.
+  v.S = MDPP_S; v.A = MDPP_A; v.L = MDPP_L; v.delay = MDPP_DELAY;
+  v.every_n = MDPP_EVERY_N; v.lookup_kind = MDPP_LOOKUP;
+  v.key_bits = MDPP_KEY_BITS; v.hash_shift = MDPP_HASH_SHIFT;
+  v.hash_mask = MDPP_HASH_MASK; v.key_mask = MDPP_KEY_MASK;
+  v.has_pnoise = MDPP_PNOISE; v.has_rnoise = MDPP_RNOISE;
+  v.cdf_log2 = MDPP_CDF_LOG2; v.cdf_stride = 1 << MDPP_CDF_LOG2;
+  v.has_guide = MDPP_HAS_GUIDE;
+  v.r_std = MDPP_R_STD; v.scale = MDPP_SCALE; v.shift = MDPP_SHIFT;
+  v.term_reward_scaled = MDPP_TERM_REWARD;
+#endif
   return v;
 }
 
@@ -216,7 +241,9 @@ __device__ __forceinline__ void run_chunk(const RolloutParams& p,
   constexpr int NORMAL = C::NORMAL;
   constexpr bool RING_SMEM = C::RING_SMEM;
   constexpr bool FAST = C::FAST;
-  const int64_t N = p.st.n_envs;
+  const int64_t N = n_envs_of(p);
+  const bool autoreset = autoreset_of(p);
+  const int horizon = horizon_of(p);
   int32_t act[U], s0[U];
   double u_tr[U], n_rw[U], u_rs[U];
   const int64_t off0 = (int64_t)t0 * N + env;
@@ -238,7 +265,7 @@ __device__ __forceinline__ void run_chunk(const RolloutParams& p,
     if (NOISE == MDPP_NOISE_REPLAY) {
       if (v.has_pnoise) u_tr[j] = ld_stream_f64(p.io.replay_transition_u + off);
       if (v.has_rnoise) n_rw[j] = ld_stream_f64(p.io.replay_reward_noise + off);
-      if (p.autoreset) u_rs[j] = ld_stream_f64(p.io.replay_reset_u + off);
+      if (autoreset) u_rs[j] = ld_stream_f64(p.io.replay_reset_u + off);
     }
   }
   uint32_t w_rs[U];
@@ -247,7 +274,7 @@ __device__ __forceinline__ void run_chunk(const RolloutParams& p,
   if (NOISE != MDPP_NOISE_REPLAY) {
     const bool want_u = NOISE == MDPP_NOISE_PHILOX && v.has_pnoise;
     const bool want_z = NOISE == MDPP_NOISE_PHILOX && v.has_rnoise;
-    const bool want_r = p.autoreset != 0;
+    const bool want_r = autoreset;
     if (U == 1) {
       double u4[4] = {0, 0, 0, 0}, z4[4] = {0, 0, 0, 0};
       uint32_t r4[4] = {0, 0, 0, 0};
@@ -270,7 +297,7 @@ __device__ __forceinline__ void run_chunk(const RolloutParams& p,
       }
     }
   }
-  if (p.autoreset) {  // candidate initial states, also state-independent
+  if (autoreset) {  // candidate initial states, also state-independent
 #pragma unroll
     for (int j = 0; j < U; ++j) {
       if (NOISE == MDPP_NOISE_REPLAY) {
@@ -326,11 +353,11 @@ __device__ __forceinline__ void run_chunk(const RolloutParams& p,
     r = __dadd_rn(r, v.shift);
     const bool done = v.term[nxt] != 0;
     if (done) r = __dadd_rn(r, v.term_reward_scaled);
-    const bool trunc = p.horizon > 0 && e.tl >= p.horizon;
+    const bool trunc = horizon > 0 && e.tl >= horizon;
     e.n_terminated += done;
     e.s = nxt;
     if (!FAST && p.io.final_obs) st_stream(p.io.final_obs + off, (int64_t)nxt);
-    if (p.autoreset && (done || trunc)) {
+    if (autoreset && (done || trunc)) {
       e.s = s0[j];
       e.key = (uint64_t)e.s;
       e.tl = 0;
@@ -357,8 +384,7 @@ __device__ __forceinline__ double warp_sum(double x) {
 }
 
 template <typename C>
-__global__ void __launch_bounds__(kBlock, kMinBlocksPerSM)
-discrete_rollout_kernel(const __grid_constant__ RolloutParams p) {
+__device__ __forceinline__ void rollout_body(const RolloutParams& p) {
   constexpr bool SMEM = C::SMEM;
   constexpr bool RING_SMEM = C::RING_SMEM;
   extern __shared__ __align__(16) uint8_t smem_dyn[];
@@ -386,7 +412,7 @@ discrete_rollout_kernel(const __grid_constant__ RolloutParams p) {
   const int64_t local = (int64_t)me.chunk * kBlock + threadIdx.x;
   const bool active = local < grp.env_count;
   const int64_t env = grp.env_begin + (active ? local : 0);
-  const int64_t N = p.st.n_envs;
+  const int64_t N = n_envs_of(p);
   const uint32_t gid = (uint32_t)(p.env_id_offset + env);
 
   EnvRegs e;
@@ -444,47 +470,10 @@ discrete_rollout_kernel(const __grid_constant__ RolloutParams p) {
   }
 }
 
-// Ring of delayed rewards lives in shared memory when it is small enough.
-constexpr int kRingSmemMaxDelay = 16;
-
 template <typename C>
-inline int launch_one(mdpp_ctx* ctx, RolloutParams& p, int smem_tab,
-                      cudaStream_t stream) {
-  auto kern = discrete_rollout_kernel<C>;
-  p.ring_smem_bytes = C::RING_SMEM ? ctx->max_delay * kBlock * 8 : 0;
-  const int smem = p.ring_smem_bytes + (C::SMEM ? smem_tab : 0);
-  if (smem > 48 * 1024 - 512)
-    MDPP_CUDA(ctx, cudaFuncSetAttribute(
-                       kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<(unsigned)ctx->n_ctas, kBlock, smem, stream>>>(p);
-  MDPP_CUDA(ctx, cudaGetLastError());
-  return MDPP_OK;
-}
-
-// Kernel variants.  The FAST ones (standard signature, tables + ring in
-// shared memory) exist for the throughput-relevant noise modes, with the cdf
-// search unrolled for <= 8 states (the toy sizes of BASELINE.json) or looped;
-// everything else (replay, huge tables, deep delay rings, optional outputs)
-// takes the generic variants.
-template <int NOISE, int NORMAL>
-inline int launch_rollout(mdpp_ctx* ctx, RolloutParams& p, cudaStream_t stream) {
-  const int smem_tab = ctx->max_group_blob;
-  const bool ring_ok = ctx->max_delay <= kRingSmemMaxDelay;
-  const int ring_bytes = ring_ok ? ctx->max_delay * kBlock * 8 : 0;
-  const bool smem_ok = smem_tab + ring_bytes <= ctx->max_smem_optin - 1024;
-  const bool fast_io = p.io.actions && p.io.obs && p.io.reward &&
-                       p.io.terminated && p.io.truncated && !p.io.final_obs &&
-                       !p.st.history;
-  if constexpr (NOISE != MDPP_NOISE_REPLAY) {
-    if (smem_ok && ring_ok && fast_io && ctx->d_groups_host.size() == 1) {
-      return ctx->d_groups_host[0].cdf_log2 == 3
-          ? launch_one<Cfg<NOISE, NORMAL, true, true, true, 3, true>>(ctx, p, smem_tab, stream)
-          : launch_one<Cfg<NOISE, NORMAL, true, true, true, -1, true>>(ctx, p, smem_tab, stream);
-    }
-  }
-  if (smem_ok && ring_ok)
-    return launch_one<Cfg<NOISE, NORMAL, true, true, false, -1>>(ctx, p, smem_tab, stream);
-  return launch_one<Cfg<NOISE, NORMAL, false, false, false, -1>>(ctx, p, smem_tab, stream);
+__global__ void __launch_bounds__(kBlock, kMinBlocksPerSM)
+discrete_rollout_kernel(const __grid_constant__ RolloutParams p) {
+  rollout_body<C>(p);
 }
 
 }  // namespace mdpp

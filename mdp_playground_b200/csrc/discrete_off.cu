@@ -1,5 +1,5 @@
 // Rollout kernel instantiations, noise mode: off.
-#include "discrete_kernels.cuh"
+#include "discrete_launch.h"
 
 namespace mdpp {
 int launch_rollout_off(mdpp_ctx* ctx, RolloutParams& p, cudaStream_t stream) {

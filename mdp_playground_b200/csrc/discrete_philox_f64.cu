@@ -1,5 +1,5 @@
 // Rollout kernel instantiations, noise mode: philox_f64.
-#include "discrete_kernels.cuh"
+#include "discrete_launch.h"
 
 namespace mdpp {
 int launch_rollout_philox_f64(mdpp_ctx* ctx, RolloutParams& p, cudaStream_t stream) {

@@ -1,5 +1,5 @@
 // Rollout kernel instantiations, noise mode: philox_fast.
-#include "discrete_kernels.cuh"
+#include "discrete_launch.h"
 
 namespace mdpp {
 int launch_rollout_philox_fast(mdpp_ctx* ctx, RolloutParams& p, cudaStream_t stream) {

@@ -1,5 +1,5 @@
 // Rollout kernel instantiations, noise mode: replay.
-#include "discrete_kernels.cuh"
+#include "discrete_launch.h"
 
 namespace mdpp {
 int launch_rollout_replay(mdpp_ctx* ctx, RolloutParams& p, cudaStream_t stream) {

@@ -1,0 +1,327 @@
+// Runtime specialisation of the discrete rollout kernel (NVRTC).
+//
+// The ahead-of-time kernels read every group scalar (S, A, L, delay, noise
+// flags, scale, ...) at run time, which costs ~290 issued instructions per
+// env-step on a path that is issue-bound at 65 536 envs.  For single-group
+// launches the same hand-written source (discrete_kernels.cuh, embedded in
+// the library at build time) is compiled once per configuration with those
+// scalars as literals (-DMDPP_JIT -DMDPP_S=8 ...): searches unroll, dead
+// features vanish, ~160 instructions per env-step remain.  The cubin is
+// loaded through the driver API and cached in the context.
+//
+// libnvrtc / libcuda are dlopen()ed lazily so the library still loads on
+// machines without a driver (the CPU-side ABI tests).  If either is missing,
+// or MDPP_JIT=0 is set, the caller falls back to the AOT kernels.
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "discrete_kernels.cuh"
+#include "embedded_sources.inc"
+#include "internal.h"
+
+namespace mdpp {
+namespace {
+
+typedef int nvrtcResult;
+typedef struct _nvrtcProgram* nvrtcProgram;
+typedef int CUresult;
+typedef struct CUmod_st* CUmodule;
+typedef struct CUfunc_st* CUfunction;
+typedef struct CUstream_st* CUstream;
+
+struct Api {
+  bool tried = false, ok = false;
+  std::string why;
+  nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int,
+                               const char* const*, const char* const*);
+  nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*);
+  nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*GetCUBIN)(nvrtcProgram, char*);
+  nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*GetProgramLog)(nvrtcProgram, char*);
+  nvrtcResult (*DestroyProgram)(nvrtcProgram*);
+  CUresult (*ModuleLoadData)(CUmodule*, const void*);
+  CUresult (*ModuleUnload)(CUmodule);
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*);
+  CUresult (*FuncSetAttribute)(CUfunction, int, int);
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned,
+                           unsigned, unsigned, unsigned, CUstream, void**,
+                           void**);
+};
+
+Api& api() {
+  static Api a;
+  if (a.tried) return a;
+  a.tried = true;
+  void* rtc = nullptr;
+  for (const char* n : {"libnvrtc.so.12", "libnvrtc.so",
+                        "/usr/local/cuda/lib64/libnvrtc.so.12"}) {
+    rtc = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (rtc) break;
+  }
+  if (!rtc) { a.why = "libnvrtc not found"; return a; }
+  void* drv = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!drv) { a.why = "libcuda.so.1 not found"; return a; }
+#define LOAD(lib, field, sym)                                   \
+  *(void**)(&a.field) = dlsym(lib, sym);                        \
+  if (!a.field) { a.why = std::string("missing ") + sym; return a; }
+  LOAD(rtc, CreateProgram, "nvrtcCreateProgram")
+  LOAD(rtc, CompileProgram, "nvrtcCompileProgram")
+  LOAD(rtc, GetCUBINSize, "nvrtcGetCUBINSize")
+  LOAD(rtc, GetCUBIN, "nvrtcGetCUBIN")
+  LOAD(rtc, GetProgramLogSize, "nvrtcGetProgramLogSize")
+  LOAD(rtc, GetProgramLog, "nvrtcGetProgramLog")
+  LOAD(rtc, DestroyProgram, "nvrtcDestroyProgram")
+  LOAD(drv, ModuleLoadData, "cuModuleLoadData")
+  LOAD(drv, ModuleUnload, "cuModuleUnload")
+  LOAD(drv, ModuleGetFunction, "cuModuleGetFunction")
+  LOAD(drv, FuncSetAttribute, "cuFuncSetAttribute")
+  LOAD(drv, LaunchKernel, "cuLaunchKernel")
+#undef LOAD
+  a.ok = true;
+  return a;
+}
+
+std::string hexf(double x) {
+  char buf[64];
+  std::snprintf(buf, sizeof buf, "%a", x);
+  return buf;
+}
+
+// The -D list that makes one specialisation; also its cache key.
+std::vector<std::string> defines_for(const DiscreteGroupDev& g,
+                                     const RolloutParams& p, int noise,
+                                     int normal, bool fast, bool ring_smem,
+                                     int cdf_log2_tpl) {
+  auto D = [](const char* k, const std::string& v) {
+    return std::string("-DMDPP_") + k + "=" + v;
+  };
+  auto I = [](long long v) { return std::to_string(v); };
+  std::vector<std::string> d = {
+      "-DMDPP_JIT",
+      D("S", I(g.S)), D("A", I(g.A)), D("L", I(g.L)), D("DELAY", I(g.delay)),
+      D("EVERY_N", I(g.every_n)), D("LOOKUP", I(g.lookup_kind)),
+      D("KEY_BITS", I(g.key_bits)), D("HASH_SHIFT", I(g.hash_shift)),
+      D("HASH_MASK", I(g.hash_mask) + "u"),
+      D("KEY_MASK", std::to_string((unsigned long long)g.key_mask) + "ull"),
+      D("PNOISE", g.has_pnoise ? "true" : "false"),
+      D("RNOISE", g.has_rnoise ? "true" : "false"),
+      D("CDF_LOG2", I(g.cdf_log2)), D("HAS_GUIDE", g.has_guide ? "true" : "false"),
+      D("R_STD", hexf(g.r_std)), D("SCALE", hexf(g.scale)),
+      D("SHIFT", hexf(g.shift)), D("TERM_REWARD", hexf(g.term_reward_scaled)),
+      D("N_ENVS", I(p.st.n_envs) + "ll"), D("AUTORESET", I(p.autoreset)),
+      D("HORIZON", I(p.horizon)),
+      D("CFG_NOISE", I(noise)), D("CFG_NORMAL", I(normal)),
+      D("CFG_FAST", fast ? "true" : "false"),
+      D("CFG_RING", ring_smem ? "true" : "false"),
+      D("CFG_CDF", I(cdf_log2_tpl)),
+  };
+  return d;
+}
+
+const char* kEntrySource = R"SRC(
+#include "discrete_kernels.cuh"
+using JitCfg = mdpp::Cfg<MDPP_CFG_NOISE, MDPP_CFG_NORMAL, true, MDPP_CFG_RING,
+                         MDPP_CFG_FAST, MDPP_CFG_CDF, true>;
+extern "C" __global__ void __launch_bounds__(mdpp::kBlock, mdpp::kMinBlocksPerSM)
+mdpp_jit_rollout(const __grid_constant__ mdpp::RolloutParams p) {
+  mdpp::rollout_body<JitCfg>(p);
+}
+)SRC";
+
+const char* kStdintShim = R"SRC(
+#pragma once
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+)SRC";
+
+void* compile(mdpp_ctx* ctx, const std::vector<std::string>& defs,
+              void** module_out) {
+  Api& a = api();
+  const char* names[] = {"discrete_kernels.cuh", "device_types.h", "philox.cuh",
+                         "mdpp_b200.h", "stdint.h"};
+  const char* srcs[] = {kSrc_discrete_kernels_cuh, kSrc_device_types_h,
+                        kSrc_philox_cuh, kSrc_mdpp_b200_h, kStdintShim};
+  nvrtcProgram prog = nullptr;
+  if (a.CreateProgram(&prog, kEntrySource, "mdpp_jit_rollout.cu", 5, srcs, names)) {
+    ctx->jit_log = "nvrtcCreateProgram failed";
+    return nullptr;
+  }
+  std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17",
+                                   "-lineinfo"};
+  opts.insert(opts.end(), defs.begin(), defs.end());
+  std::vector<const char*> copts;
+  for (auto& o : opts) copts.push_back(o.c_str());
+  nvrtcResult rc = a.CompileProgram(prog, (int)copts.size(), copts.data());
+  if (rc != 0) {
+    size_t n = 0;
+    a.GetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) a.GetProgramLog(prog, &log[0]);
+    ctx->jit_log = "nvrtc compile failed: " + log;
+    a.DestroyProgram(&prog);
+    return nullptr;
+  }
+  size_t size = 0;
+  a.GetCUBINSize(prog, &size);
+  std::vector<char> cubin(size);
+  a.GetCUBIN(prog, cubin.data());
+  a.DestroyProgram(&prog);
+  CUmodule mod = nullptr;
+  if (a.ModuleLoadData(&mod, cubin.data())) {
+    ctx->jit_log = "cuModuleLoadData failed";
+    return nullptr;
+  }
+  CUfunction fn = nullptr;
+  if (a.ModuleGetFunction(&fn, mod, "mdpp_jit_rollout")) {
+    ctx->jit_log = "cuModuleGetFunction failed";
+    a.ModuleUnload(mod);
+    return nullptr;
+  }
+  *module_out = mod;
+  return fn;
+}
+
+}  // namespace
+
+int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
+                    int normal_mode, cudaStream_t stream) {
+  ctx->jit_last_used = 0;
+  if (!ctx->jit_enabled) return 0;
+  if (ctx->d_groups_host.size() != 1) { ctx->jit_log = "multi-group launch"; return 0; }
+  if (noise_mode == MDPP_NOISE_REPLAY) { ctx->jit_log = "replay mode"; return 0; }
+  const DiscreteGroupDev& g = ctx->d_groups_host[0];
+  constexpr int kRingSmemMaxDelay = 16;
+  const bool ring_ok = g.delay <= kRingSmemMaxDelay;
+  const int ring_bytes = ring_ok ? g.delay * kBlock * 8 : 0;
+  if (!ring_ok || g.blob_bytes + ring_bytes > ctx->max_smem_optin - 1024) {
+    ctx->jit_log = "tables or delay ring do not fit shared memory";
+    return 0;
+  }
+  Api& a = api();
+  if (!a.ok) { ctx->jit_log = a.why; return 0; }
+  const bool fast = p.io.actions && p.io.obs && p.io.reward && p.io.terminated &&
+                    p.io.truncated && !p.io.final_obs && !p.st.history;
+  const int cdf_tpl = g.cdf_log2 <= 6 ? g.cdf_log2 : -1;
+  std::vector<std::string> defs =
+      defines_for(g, p, noise_mode, normal_mode, fast, true, cdf_tpl);
+  std::string key;
+  for (auto& d : defs) { key += d; key += ' '; }
+  auto it = ctx->jit_functions.find(key);
+  void* fn = nullptr;
+  if (it != ctx->jit_functions.end()) {
+    fn = it->second;
+    if (!fn) return 0;  // compile failed before: do not retry every call
+  } else {
+    void* mod = nullptr;
+    fn = compile(ctx, defs, &mod);
+    ctx->jit_functions[key] = fn;
+    if (!fn) return 0;
+    ctx->jit_modules.push_back(mod);
+  }
+  p.ring_smem_bytes = ring_bytes;
+  const int smem = ring_bytes + g.blob_bytes;
+  if (smem > 48 * 1024 - 512) {
+    // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8
+    if (a.FuncSetAttribute((CUfunction)fn, 8, smem))
+      return fail(ctx, MDPP_ECUDA, "cuFuncSetAttribute(max dynamic smem) failed");
+  }
+  void* args[] = {&p};
+  CUresult rc = a.LaunchKernel((CUfunction)fn, (unsigned)ctx->n_ctas, 1, 1,
+                               kBlock, 1, 1, (unsigned)smem, (CUstream)stream,
+                               args, nullptr);
+  if (rc != 0)
+    return fail(ctx, MDPP_ECUDA,
+                "cuLaunchKernel(jit rollout) failed: " + std::to_string(rc));
+  ctx->jit_last_used = 1;
+  return 1;
+}
+
+void jit_release(mdpp_ctx* ctx) {
+  Api& a = api();
+  if (a.ok)
+    for (void* m : ctx->jit_modules) a.ModuleUnload((CUmodule)m);
+  ctx->jit_modules.clear();
+  ctx->jit_functions.clear();
+}
+
+}  // namespace mdpp
+
+// Compile (not load) the specialisation of the BASELINE config #2 shape with
+// NVRTC only -- usable without a GPU; returns 0 on success and copies the
+// compiler log into `log` (may be NULL).
+extern "C" int mdpp_jit_selftest(char* log, int log_bytes) {
+  using namespace mdpp;
+  mdpp_ctx tmp;
+  DiscreteGroupDev g;
+  std::memset(&g, 0, sizeof g);
+  g.S = 8; g.A = 8; g.L = 3; g.delay = 2; g.every_n = 1; g.key_bits = 3;
+  g.key_mask = 511; g.has_pnoise = 1; g.has_rnoise = 1; g.cdf_log2 = 3;
+  g.has_guide = 1; g.r_std = 0.25; g.scale = 1.0;
+  RolloutParams p;
+  std::memset(&p, 0, sizeof p);
+  p.st.n_envs = 65536; p.autoreset = 1; p.horizon = 100;
+  std::vector<std::string> defs =
+      defines_for(g, p, MDPP_NOISE_PHILOX, MDPP_NORMAL_FAST, true, true, 3);
+  // compile() loads the module too, which needs a driver: stop after NVRTC
+  void* rtc = dlopen("libnvrtc.so.12", RTLD_NOW | RTLD_GLOBAL);
+  if (!rtc) rtc = dlopen("/usr/local/cuda/lib64/libnvrtc.so.12", RTLD_NOW | RTLD_GLOBAL);
+  std::string msg;
+  int rc = -1;
+  if (!rtc) {
+    msg = "libnvrtc not found";
+  } else {
+    auto Create = (nvrtcResult(*)(nvrtcProgram*, const char*, const char*, int,
+                                  const char* const*, const char* const*))
+        dlsym(rtc, "nvrtcCreateProgram");
+    auto Compile = (nvrtcResult(*)(nvrtcProgram, int, const char* const*))
+        dlsym(rtc, "nvrtcCompileProgram");
+    auto LogSize = (nvrtcResult(*)(nvrtcProgram, size_t*))
+        dlsym(rtc, "nvrtcGetProgramLogSize");
+    auto Log = (nvrtcResult(*)(nvrtcProgram, char*)) dlsym(rtc, "nvrtcGetProgramLog");
+    auto Destroy = (nvrtcResult(*)(nvrtcProgram*)) dlsym(rtc, "nvrtcDestroyProgram");
+    const char* names[] = {"discrete_kernels.cuh", "device_types.h", "philox.cuh",
+                           "mdpp_b200.h", "stdint.h"};
+    const char* srcs[] = {kSrc_discrete_kernels_cuh, kSrc_device_types_h,
+                          kSrc_philox_cuh, kSrc_mdpp_b200_h, kStdintShim};
+    nvrtcProgram prog = nullptr;
+    Create(&prog, kEntrySource, "mdpp_jit_rollout.cu", 5, srcs, names);
+    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17",
+                                     "-lineinfo"};
+    opts.insert(opts.end(), defs.begin(), defs.end());
+    std::vector<const char*> copts;
+    for (auto& o : opts) copts.push_back(o.c_str());
+    rc = Compile(prog, (int)copts.size(), copts.data());
+    size_t n = 0;
+    LogSize(prog, &n);
+    msg.assign(n, '\0');
+    if (n) Log(prog, &msg[0]);
+    Destroy(&prog);
+  }
+  if (log && log_bytes > 0) {
+    std::strncpy(log, msg.c_str(), log_bytes - 1);
+    log[log_bytes - 1] = '\0';
+  }
+  return rc;
+}
+
+extern "C" int mdpp_jit_last_used(const mdpp_ctx* ctx) {
+  return ctx ? ctx->jit_last_used : 0;
+}
+
+extern "C" const char* mdpp_jit_log(const mdpp_ctx* ctx) {
+  return ctx ? ctx->jit_log.c_str() : "";
+}
+
+extern "C" void mdpp_set_jit(mdpp_ctx* ctx, int enabled) {
+  if (ctx) ctx->jit_enabled = enabled;
+}

@@ -92,6 +92,19 @@ class VectorRLToyEnv:
         except Exception:
             pass
 
+    def set_jit(self, enabled):
+        """Enable/disable the NVRTC-specialised rollout kernel (on by default;
+        the ahead-of-time kernels are used when off or unavailable)."""
+        self._lib.mdpp_set_jit(self._ctx, int(bool(enabled)))
+
+    @property
+    def jit_last_used(self):
+        return bool(self._lib.mdpp_jit_last_used(self._ctx))
+
+    @property
+    def jit_log(self):
+        return self._lib.mdpp_jit_log(self._ctx).decode()
+
     def _check(self, rc):
         _lib.check(self._lib, self._ctx, rc)
 

@@ -109,3 +109,11 @@ def test_no_gpu_means_loud_failure():
     from mdp_playground_b200 import VectorRLToyEnv
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         VectorRLToyEnv(4, state_space_type="discrete", action_space_size=4)
+
+
+def test_nvrtc_specialisation_compiles_without_a_gpu():
+    """The embedded kernel sources must be NVRTC-clean (sm_100a)."""
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(1 << 16)
+    rc = lib.mdpp_jit_selftest(buf, len(buf))
+    assert rc == 0, buf.value.decode()
