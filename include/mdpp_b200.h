@@ -180,6 +180,85 @@ int mdpp_discrete_reset(mdpp_ctx* ctx, const mdpp_discrete_state* st,
                         const mdpp_step_opts* opts, void* cuda_stream);
 #endif
 
+/* ------------------------------------------------------------------------
+ * Continuous environments, reward_function "move_to_a_point" (replaces
+ * RLToyEnv.transition_function :1625-1725, reward_function :1848-1864 +
+ * :1912-1945 + tail :1968-1990, step epilogue :2098-2109, reset :2284-2323).
+ * One configuration per context.  `real` is float (dtype_s float32, the
+ * reference default) or double (the fp64 verification build).
+ * --------------------------------------------------------------------- */
+#define MDPP_MAX_DIM 16
+#define MDPP_MAX_ORDER 4
+#define MDPP_MAX_TERM_BOXES 8
+
+typedef struct mdpp_continuous_config {
+  int32_t dim;                  /* state_space_dim = action_space_dim        */
+  int32_t order;                /* transition_dynamics_order, 1..4           */
+  int32_t n_relevant;           /* len(relevant_indices)                     */
+  int32_t delay;
+  int32_t reward_every_n_steps;
+  int32_t dense;                /* make_denser (:1915) vs sparse (:1931)     */
+  int32_t has_transition_noise; /* "transition_noise" key present (:407)     */
+  int32_t has_reward_noise;     /* "reward_noise" key present (:398)         */
+  int32_t image_mode;           /* image observations: every step takes the
+                                   out-of-bounds branch (:1694, quirk q4)    */
+  int32_t target_is_f64;        /* default target_point (float64 zeros :654) */
+  int32_t n_term_boxes;
+  int32_t is_f64;               /* 1: real = double                          */
+  double inertia, time_unit;
+  double state_space_max, action_space_max;   /* +inf = unbounded            */
+  double target_radius, action_loss_weight;
+  double transition_noise_std, reward_noise_std;
+  double reward_scale, reward_shift, term_state_reward;
+  int32_t relevant_indices[MDPP_MAX_DIM];
+  double target_point[MDPP_MAX_DIM];          /* [n_relevant]                */
+  double term_low[MDPP_MAX_TERM_BOXES * MDPP_MAX_DIM];   /* [box][relevant], */
+  double term_high[MDPP_MAX_TERM_BOXES * MDPP_MAX_DIM];  /* cast to dtype_s  */
+} mdpp_continuous_config;
+
+#ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
+int mdpp_set_continuous_config(mdpp_ctx* ctx, const mdpp_continuous_config* cfg);
+#endif
+
+/* Persistent state, struct-of-arrays over envs (DEVICE pointers, `real`).   */
+typedef struct mdpp_continuous_state {
+  int64_t n_envs;
+  void* derivs;        /* real [(order+1)][dim][N]  state_derivatives        */
+  void* emitted;       /* real [dim][N]  curr_state (noised / clipped)       */
+  int32_t* t_episode;  /* [N]                                                */
+  uint32_t* episode;   /* [N]                                                */
+  uint8_t* reached;    /* [N] sticky reached_terminal (:1725)                */
+  void* ring;          /* real [delay][N] reward FIFO, or NULL               */
+  double* stats;       /* [MDPP_N_STATS]                                     */
+} mdpp_continuous_state;
+
+/* T steps, time-major; actions / obs are env-major rows of `dim` reals
+ * ([T][N][dim], the gym layout).                                            */
+typedef struct mdpp_continuous_io {
+  const void* actions;             /* real [T][N][dim]                       */
+  void* obs;                       /* real [T][N][dim] emitted state (after
+                                      the auto-reset when one happened)      */
+  void* final_obs;                 /* real [T][N][dim] before any auto-reset */
+  void* reward;                    /* real [T][N]                            */
+  uint8_t* terminated;             /* [T][N]                                 */
+  uint8_t* truncated;              /* [T][N]                                 */
+  const double* replay_state_noise;  /* [T][N][dim] normal(0,s,dim) :413     */
+  const double* replay_reward_noise; /* [T][N]                               */
+  const void* replay_reset_state;    /* real [T][N][dim] accepted Box sample */
+} mdpp_continuous_io;
+
+#ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
+int mdpp_continuous_rollout(mdpp_ctx* ctx, const mdpp_continuous_state* st,
+                            const mdpp_continuous_io* io,
+                            const mdpp_step_opts* opts, void* cuda_stream);
+/* (masked) reset: `init_states` real [N][dim] when given, else Philox Box
+ * sampling with rejection of the terminal boxes.  `obs` real [N][dim].      */
+int mdpp_continuous_reset(mdpp_ctx* ctx, const mdpp_continuous_state* st,
+                          const uint8_t* mask, const void* init_states,
+                          void* obs, const mdpp_step_opts* opts,
+                          void* cuda_stream);
+#endif
+
 #ifdef __cplusplus
 }
 #endif

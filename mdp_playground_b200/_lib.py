@@ -21,7 +21,10 @@ EXPORTED_SYMBOLS = (
     "mdpp_abi_version", "mdpp_create", "mdpp_destroy", "mdpp_last_error",
     "mdpp_set_discrete_groups", "mdpp_discrete_rollout", "mdpp_discrete_reset",
     "mdpp_set_jit", "mdpp_jit_last_used", "mdpp_jit_log", "mdpp_jit_selftest",
+    "mdpp_set_continuous_config", "mdpp_continuous_rollout",
+    "mdpp_continuous_reset",
 )
+MDPP_MAX_DIM, MDPP_MAX_ORDER, MDPP_MAX_TERM_BOXES = 16, 4, 8
 
 
 class DiscreteGroup(C.Structure):
@@ -72,6 +75,44 @@ class StepOpts(C.Structure):
     ]
 
 
+class ContinuousConfig(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32), ("order", C.c_int32), ("n_relevant", C.c_int32),
+        ("delay", C.c_int32), ("reward_every_n_steps", C.c_int32),
+        ("dense", C.c_int32), ("has_transition_noise", C.c_int32),
+        ("has_reward_noise", C.c_int32), ("image_mode", C.c_int32),
+        ("target_is_f64", C.c_int32), ("n_term_boxes", C.c_int32),
+        ("is_f64", C.c_int32),
+        ("inertia", C.c_double), ("time_unit", C.c_double),
+        ("state_space_max", C.c_double), ("action_space_max", C.c_double),
+        ("target_radius", C.c_double), ("action_loss_weight", C.c_double),
+        ("transition_noise_std", C.c_double), ("reward_noise_std", C.c_double),
+        ("reward_scale", C.c_double), ("reward_shift", C.c_double),
+        ("term_state_reward", C.c_double),
+        ("relevant_indices", C.c_int32 * MDPP_MAX_DIM),
+        ("target_point", C.c_double * MDPP_MAX_DIM),
+        ("term_low", C.c_double * (MDPP_MAX_TERM_BOXES * MDPP_MAX_DIM)),
+        ("term_high", C.c_double * (MDPP_MAX_TERM_BOXES * MDPP_MAX_DIM)),
+    ]
+
+
+class ContinuousState(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int64), ("derivs", C.c_void_p), ("emitted", C.c_void_p),
+        ("t_episode", C.c_void_p), ("episode", C.c_void_p),
+        ("reached", C.c_void_p), ("ring", C.c_void_p), ("stats", C.c_void_p),
+    ]
+
+
+class ContinuousIO(C.Structure):
+    _fields_ = [
+        ("actions", C.c_void_p), ("obs", C.c_void_p), ("final_obs", C.c_void_p),
+        ("reward", C.c_void_p), ("terminated", C.c_void_p),
+        ("truncated", C.c_void_p), ("replay_state_noise", C.c_void_p),
+        ("replay_reward_noise", C.c_void_p), ("replay_reset_state", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -107,6 +148,12 @@ def load():
     lib.mdpp_jit_log.argtypes = [P]
     lib.mdpp_jit_log.restype = C.c_char_p
     lib.mdpp_jit_selftest.argtypes = [C.c_char_p, C.c_int]
+    lib.mdpp_set_continuous_config.argtypes = [P, C.POINTER(ContinuousConfig)]
+    lib.mdpp_continuous_rollout.argtypes = [
+        P, C.POINTER(ContinuousState), C.POINTER(ContinuousIO),
+        C.POINTER(StepOpts), P]
+    lib.mdpp_continuous_reset.argtypes = [
+        P, C.POINTER(ContinuousState), P, P, P, C.POINTER(StepOpts), P]
     if lib.mdpp_abi_version() != 1:
         raise RuntimeError("libmdpp_b200.so ABI version mismatch; rebuild")
     _lib = lib

@@ -1,0 +1,478 @@
+// Continuous RLToyEnv step path ("move_to_a_point") on sm_100a: K3
+// `continuous_rollout` (T fused steps; T = 1 is the gym-style step) and the
+// continuous reset.  Device-only header, also compiled by NVRTC (jit.cu) with
+// the configuration as literals (MDPP_JIT): dim / order / relevant indices
+// become compile-time, every per-dimension loop unrolls and the whole state
+// ((order+1) x dim derivatives + the emitted state) lives in registers.  The
+// ahead-of-time build keeps them as run-time values (arrays in local memory):
+// a correct but slow fallback for hosts without NVRTC.
+//
+// Restates (per env, per step) rl_toy_env.py
+//   transition_function :1625-1725  Taylor update of state_derivatives in the
+//        reference's exact dtype path: (f32 * f32(tu^k)) -> / f64 factorial
+//        -> += rounds back to f32; frozen state on an out-of-range action;
+//        noise added to the emitted state only; clip => all derivatives
+//        zeroed; sticky reached_terminal inside target_radius
+//   reward_function :1912-1945 dense / sparse move_to_a_point, action loss,
+//        :1968-1990 delay FIFO, every-n gate, noise, scale, shift -- including
+//        numpy's scalar typing: the reward is np.float32 except when it comes
+//        from the zero-initialised FIFO or the every-n gate (python float),
+//        in which case the tail runs in double
+//   step epilogue :2098-2109, reset :2284-2323
+//
+// One thread = one environment.  State is struct-of-arrays ([component][N],
+// coalesced); actions / observations use the gym layout ([N][dim] rows).
+// No FMA contraction anywhere on the parity path (explicit _rn intrinsics).
+#pragma once
+#include "device_types.h"
+#include "philox.cuh"
+
+namespace mdpp {
+
+constexpr int kCBlock = 128;
+
+struct ContinuousParams {
+  mdpp_continuous_config cfg;
+  double tu_pow[MDPP_MAX_ORDER];  // time_unit ** (j + 1), computed by the host
+  mdpp_continuous_state st;
+  mdpp_continuous_io io;
+  int32_t T, autoreset, horizon, noise_mode;
+  uint32_t k0, k1;
+  uint64_t step_index;
+  int64_t env_id_offset;
+  // reset kernel only
+  const uint8_t* mask;
+  const void* init_states;
+  void* reset_obs;
+};
+
+template <typename R> struct RealOps;
+template <> struct RealOps<float> {
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+};
+template <> struct RealOps<double> {
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+};
+
+#ifdef MDPP_JIT
+#define MDPP_C_CONST(name, runtime) (MDPP_C_##name)
+#else
+#define MDPP_C_CONST(name, runtime) (runtime)
+#endif
+
+// relevant_indices[k]: a literal table in the specialised build so that
+// indexing the register-resident state with it stays static.
+__device__ __forceinline__ int rel_index(const ContinuousParams& p, int k) {
+#ifdef MDPP_JIT
+  constexpr int kRel[MDPP_MAX_DIM] = {
+      MDPP_C_REL0, MDPP_C_REL1, MDPP_C_REL2, MDPP_C_REL3, MDPP_C_REL4, MDPP_C_REL5,
+      MDPP_C_REL6, MDPP_C_REL7, MDPP_C_REL8, MDPP_C_REL9, MDPP_C_REL10,
+      MDPP_C_REL11, MDPP_C_REL12, MDPP_C_REL13, MDPP_C_REL14, MDPP_C_REL15};
+  return kRel[k];
+#else
+  return p.cfg.relevant_indices[k];
+#endif
+}
+
+// np.linalg.norm of a short vector: sqrt of the sequentially accumulated,
+// separately rounded sum of squares (bit-identical to numpy/OpenBLAS for the
+// 1- and 2-element vectors that move_to_a_point uses).
+template <typename R, typename F>
+__device__ __forceinline__ R seq_norm(int n, F elem) {
+  R s = 0;
+#pragma unroll
+  for (int k = 0; k < MDPP_MAX_DIM; ++k)
+    if (k < n) {
+      R x = elem(k);
+      s = RealOps<R>::add(s, RealOps<R>::mul(x, x));
+    }
+  return RealOps<R>::sqrt(s);
+}
+
+// Philox Box sample of one env (gymnasium Box.sample: uniform in [-max, max]
+// when bounded, N(0,1) when unbounded, cast to dtype_s).
+template <typename R>
+__device__ __forceinline__ void box_sample(const ContinuousParams& p, int D,
+                                           uint32_t gid, uint32_t ep,
+                                           int attempt, R* out) {
+  const bool bounded = isfinite(p.cfg.state_space_max);
+  const double hi = (double)(R)p.cfg.state_space_max, lo = -hi;
+#pragma unroll
+  for (int c = 0; c < MDPP_MAX_DIM / 2; ++c) {
+    if (2 * c < D) {
+      U4 w = philox4x32_10(gid, ep, (uint32_t)attempt,
+                           STREAM_RESET_BOX + (uint32_t)c, p.k0, p.k1);
+      double v0, v1;
+      if (bounded) {
+        v0 = lo + (hi - lo) * uniform53(w.x, w.y);
+        v1 = lo + (hi - lo) * uniform53(w.z, w.w);
+      } else {
+        normal_pair_f64(w.x, w.y, &v0, &v1);
+      }
+      out[2 * c] = (R)v0;
+      if (2 * c + 1 < D) out[2 * c + 1] = (R)v1;
+    }
+  }
+}
+
+template <typename R>
+__device__ __forceinline__ bool in_term_box(const ContinuousParams& p, int NREL,
+                                            const R* x /* full state */) {
+  bool any = false;
+  for (int b = 0; b < p.cfg.n_term_boxes; ++b) {
+    bool in = true;
+#pragma unroll
+    for (int k = 0; k < MDPP_MAX_DIM; ++k)
+      if (k < NREL) {
+        const R v = x[rel_index(p, k)];
+        in = in && v >= (R)p.cfg.term_low[b * MDPP_MAX_DIM + k] &&
+             v <= (R)p.cfg.term_high[b * MDPP_MAX_DIM + k];
+      }
+    any = any || in;
+  }
+  return any;
+}
+
+template <typename R, int NOISE>
+__device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
+  using O = RealOps<R>;
+  const int D = MDPP_C_CONST(DIM, p.cfg.dim);
+  const int ORDER = MDPP_C_CONST(ORDER, p.cfg.order);
+  const int NREL = MDPP_C_CONST(NREL, p.cfg.n_relevant);
+  const int DELAY = MDPP_C_CONST(DELAY, p.cfg.delay);
+  const int EVERY_N = MDPP_C_CONST(EVERY_N, p.cfg.reward_every_n_steps);
+  const bool DENSE = MDPP_C_CONST(DENSE, p.cfg.dense != 0);
+  const bool PNOISE = MDPP_C_CONST(PNOISE, p.cfg.has_transition_noise != 0);
+  const bool RNOISE = MDPP_C_CONST(RNOISE, p.cfg.has_reward_noise != 0);
+  const bool IMAGE = MDPP_C_CONST(IMAGE, p.cfg.image_mode != 0);
+  const bool TARGET64 = MDPP_C_CONST(TARGET64, p.cfg.target_is_f64 != 0);
+  const int64_t N = p.st.n_envs;
+  const int64_t env = (int64_t)blockIdx.x * kCBlock + threadIdx.x;
+  if (env >= N) return;
+  const uint32_t gid = (uint32_t)(p.env_id_offset + env);
+
+  const R amax = (R)p.cfg.action_space_max, smax = (R)p.cfg.state_space_max;
+  const R inertia = (R)p.cfg.inertia;
+  const R radius_r = (R)p.cfg.target_radius;
+
+  R sd[MDPP_MAX_ORDER + 1][MDPP_MAX_DIM];
+  R em[MDPP_MAX_DIM];
+  R* derivs = reinterpret_cast<R*>(p.st.derivs);
+  R* emitted = reinterpret_cast<R*>(p.st.emitted);
+  R* ring = reinterpret_cast<R*>(p.st.ring);
+#pragma unroll
+  for (int k = 0; k <= MDPP_MAX_ORDER; ++k)
+#pragma unroll
+    for (int d = 0; d < MDPP_MAX_DIM; ++d)
+      if (k <= ORDER && d < D) sd[k][d] = derivs[((int64_t)k * D + d) * N + env];
+#pragma unroll
+  for (int d = 0; d < MDPP_MAX_DIM; ++d)
+    if (d < D) em[d] = emitted[(int64_t)d * N + env];
+  int32_t tl = p.st.t_episode[env];
+  uint32_t ep = p.st.episode[env];
+  bool reached = p.st.reached[env] != 0;
+  int32_t phase = tl % EVERY_N;
+  int32_t ring_pos = DELAY > 0 ? (int32_t)(p.step_index % (uint64_t)DELAY) : 0;
+
+  double sum_reward = 0, sum_abs_rnoise = 0, sum_abs_pnoise = 0;
+  uint32_t n_episodes = 0, n_terminated = 0;
+
+  // distance of a state's relevant part to the target, in the dtype numpy
+  // would use: R when target_point was given (cast to dtype_s :646), float64
+  // for the default float64 zeros (:654)
+  auto dist_to_target = [&](const R* x) -> double {
+    if (TARGET64) {
+      return seq_norm<double>(NREL, [&](int k) {
+        return __dadd_rn((double)x[rel_index(p, k)], -p.cfg.target_point[k]);
+      });
+    }
+    return (double)seq_norm<R>(NREL, [&](int k) {
+      return O::add(x[rel_index(p, k)], -(R)p.cfg.target_point[k]);
+    });
+  };
+
+  for (int t = 0; t < p.T; ++t) {
+    const uint64_t step = p.step_index + (uint64_t)t;
+    const int64_t row = ((int64_t)t * N + env);
+    const R* ap = reinterpret_cast<const R*>(p.io.actions) + row * D;
+    R a[MDPP_MAX_DIM], nxt[MDPP_MAX_DIM];
+    bool in_range = true;
+#pragma unroll
+    for (int d = 0; d < MDPP_MAX_DIM; ++d)
+      if (d < D) {
+        a[d] = ap[d];
+        in_range = in_range && a[d] >= -amax && a[d] <= amax;  // Box.contains
+      }
+    const double dist_old = dist_to_target(em);  // ||aug[-2][rel] - target||
+
+    // ---- transition -----------------------------------------------------
+    if (in_range) {
+#pragma unroll
+      for (int d = 0; d < MDPP_MAX_DIM; ++d)
+        if (d < D) sd[ORDER][d] = O::div(a[d], inertia);
+#pragma unroll
+      for (int i = 0; i < MDPP_MAX_ORDER; ++i)
+#pragma unroll
+        for (int j = 0; j < MDPP_MAX_ORDER; ++j)
+          if (i < ORDER && j < ORDER - i) {
+            const R tu = (R)p.tu_pow[j];
+            // (j+1)! as the float64 scipy.special.factorial returns
+            const double fact = j == 0 ? 1.0 : j == 1 ? 2.0 : j == 2 ? 6.0 : 24.0;
+#pragma unroll
+            for (int d = 0; d < MDPP_MAX_DIM; ++d)
+              if (d < D) {
+                const R term = O::mul(sd[i + j + 1][d], tu);
+                sd[i][d] = (R)__dadd_rn((double)sd[i][d],
+                                        __ddiv_rn((double)term, fact));
+              }
+          }
+#pragma unroll
+      for (int d = 0; d < MDPP_MAX_DIM; ++d)
+        if (d < D) nxt[d] = sd[0][d];
+    } else {  // frozen state, derivatives kept (:1671-1679)
+#pragma unroll
+      for (int d = 0; d < MDPP_MAX_DIM; ++d)
+        if (d < D) nxt[d] = em[d];
+    }
+    if (NOISE != MDPP_NOISE_OFF && PNOISE) {
+      double nz[MDPP_MAX_DIM];
+      if (NOISE == MDPP_NOISE_REPLAY) {
+#pragma unroll
+        for (int d = 0; d < MDPP_MAX_DIM; ++d)
+          if (d < D) nz[d] = p.io.replay_state_noise[row * D + d];
+      } else {
+#pragma unroll
+        for (int c = 0; c < MDPP_MAX_DIM / 4; ++c)
+          if (4 * c < D) {
+            U4 w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
+                                 STREAM_STATE_NOISE + (uint32_t)c, p.k0, p.k1);
+            double z[4];
+            normal_pair_f64(w.x, w.y, &z[0], &z[1]);
+            normal_pair_f64(w.z, w.w, &z[2], &z[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (4 * c + k < D)
+                nz[4 * c + k] = __dmul_rn(p.cfg.transition_noise_std, z[k]);
+          }
+      }
+#pragma unroll
+      for (int d = 0; d < MDPP_MAX_DIM; ++d)
+        if (d < D) {
+          sum_abs_pnoise += fabs(nz[d]);
+          nxt[d] = (R)__dadd_rn((double)nxt[d], nz[d]);  // f32 += f64 array
+        }
+    }
+    bool in_bounds = !IMAGE;
+#pragma unroll
+    for (int d = 0; d < MDPP_MAX_DIM; ++d)
+      if (d < D) in_bounds = in_bounds && nxt[d] >= -smax && nxt[d] <= smax;
+    if (!in_bounds) {  // clip, zero every derivative (:1702-1717)
+#pragma unroll
+      for (int d = 0; d < MDPP_MAX_DIM; ++d)
+        if (d < D) {
+          nxt[d] = nxt[d] < -smax ? -smax : (nxt[d] > smax ? smax : nxt[d]);
+#pragma unroll
+          for (int k = 1; k <= MDPP_MAX_ORDER; ++k)
+            if (k <= ORDER) sd[k][d] = 0;
+          sd[0][d] = nxt[d];
+        }
+    }
+    const double dist_new = dist_to_target(nxt);
+    const double radius = TARGET64 ? p.cfg.target_radius : (double)radius_r;
+    if (dist_new < radius) reached = true;
+    tl += 1;
+    phase = (phase + 1 == EVERY_N) ? 0 : phase + 1;
+
+    // ---- reward ------------------------------------------------------------
+    // `rr` is the np.float32 (dtype_s) reward, `rd` the python-float one;
+    // `is_real` says which of the two numpy would be carrying.
+    R rr;
+    double rd = 0.0;
+    bool is_real = true;
+    if (DENSE) {
+      if (TARGET64) {  // float64 norms make the reward float64
+        rd = __dadd_rn(-dist_new, dist_old);
+        is_real = false;
+      } else {
+        rr = O::add(-(R)dist_new, (R)dist_old);
+      }
+    } else {
+      rd = dist_new < radius ? 1.0 : 0.0;
+      is_real = false;
+    }
+    {  // reward -= action_loss_weight * ||action||  (always makes it dtype_s)
+      const R an = seq_norm<R>(D, [&](int k) { return a[k]; });
+      const R loss = O::mul((R)p.cfg.action_loss_weight, an);
+      if (is_real) rr = O::add(rr, -loss);
+      else if (sizeof(R) == 4 && TARGET64 && DENSE)
+        rd = __dadd_rn(rd, -(double)loss);  // float64 - float32 -> float64
+      else { rr = O::add((R)rd, -loss); is_real = true; }
+    }
+    if (DELAY > 0) {
+      R* slot = ring + (int64_t)ring_pos * N + env;
+      const bool have = tl > DELAY;
+      const R delayed = have ? *slot : (R)0;
+      *slot = is_real ? rr : (R)rd;
+      if (have) { rr = delayed; is_real = true; }
+      else { rd = 0.0; is_real = false; }  // zero-initialised python floats
+      ring_pos = (ring_pos + 1 == DELAY) ? 0 : ring_pos + 1;
+    }
+    if (phase != 0) { rd = 0.0; is_real = false; }
+    sum_reward += is_real ? (double)rr : rd;
+    double nrw = 0.0;
+    if (NOISE != MDPP_NOISE_OFF && RNOISE) {
+      if (NOISE == MDPP_NOISE_REPLAY) {
+        nrw = p.io.replay_reward_noise[row];
+      } else {
+        U4 w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
+                             STREAM_NORMAL, p.k0, p.k1);
+        double z0, z1;
+        normal_pair_f64(w.x, w.y, &z0, &z1);
+        nrw = __dmul_rn(p.cfg.reward_noise_std, z0);
+      }
+      sum_abs_rnoise += fabs(nrw);
+    }
+    const bool box = p.cfg.n_term_boxes > 0 && in_term_box<R>(p, NREL, nxt);
+    const bool done = box || reached;
+    const double term_add = __dmul_rn(p.cfg.term_state_reward, p.cfg.reward_scale);
+    R out_r;
+    if (is_real) {  // np.float32 op python-float: the scalar is cast first
+      if (RNOISE) rr = O::add(rr, (R)nrw);
+      rr = O::mul(rr, (R)p.cfg.reward_scale);
+      rr = O::add(rr, (R)p.cfg.reward_shift);
+      if (done) rr = O::add(rr, (R)term_add);
+      out_r = rr;
+    } else {
+      if (RNOISE) rd = __dadd_rn(rd, nrw);
+      rd = __dmul_rn(rd, p.cfg.reward_scale);
+      rd = __dadd_rn(rd, p.cfg.reward_shift);
+      if (done) rd = __dadd_rn(rd, term_add);
+      out_r = (R)rd;
+    }
+    const bool trunc = p.horizon > 0 && tl >= p.horizon;
+    n_terminated += done;
+#pragma unroll
+    for (int d = 0; d < MDPP_MAX_DIM; ++d)
+      if (d < D) em[d] = nxt[d];
+    if (p.io.final_obs) {
+      R* fo = reinterpret_cast<R*>(p.io.final_obs) + row * D;
+#pragma unroll
+      for (int d = 0; d < MDPP_MAX_DIM; ++d)
+        if (d < D) fo[d] = nxt[d];
+    }
+    if (p.autoreset && (done || trunc)) {
+      R s0[MDPP_MAX_DIM];
+      if (NOISE == MDPP_NOISE_REPLAY) {
+        const R* rs = reinterpret_cast<const R*>(p.io.replay_reset_state) + row * D;
+#pragma unroll
+        for (int d = 0; d < MDPP_MAX_DIM; ++d)
+          if (d < D) s0[d] = rs[d];
+      } else {
+        for (int attempt = 0; attempt < 64; ++attempt) {
+          box_sample<R>(p, D, gid, ep, attempt, s0);
+          if (!(p.cfg.n_term_boxes > 0 && in_term_box<R>(p, NREL, s0))) break;
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < MDPP_MAX_DIM; ++d)
+        if (d < D) {
+          em[d] = s0[d];
+#pragma unroll
+          for (int k = 1; k <= MDPP_MAX_ORDER; ++k)
+            if (k <= ORDER) sd[k][d] = 0;
+          sd[0][d] = s0[d];
+        }
+      tl = 0; phase = 0; reached = false;
+      ep += 1; n_episodes += 1;
+    }
+    if (p.io.obs) {
+      R* ob = reinterpret_cast<R*>(p.io.obs) + row * D;
+#pragma unroll
+      for (int d = 0; d < MDPP_MAX_DIM; ++d)
+        if (d < D) ob[d] = em[d];
+    }
+    if (p.io.reward) reinterpret_cast<R*>(p.io.reward)[row] = out_r;
+    if (p.io.terminated) p.io.terminated[row] = (uint8_t)done;
+    if (p.io.truncated) p.io.truncated[row] = (uint8_t)trunc;
+  }
+
+#pragma unroll
+  for (int k = 0; k <= MDPP_MAX_ORDER; ++k)
+#pragma unroll
+    for (int d = 0; d < MDPP_MAX_DIM; ++d)
+      if (k <= ORDER && d < D) derivs[((int64_t)k * D + d) * N + env] = sd[k][d];
+#pragma unroll
+  for (int d = 0; d < MDPP_MAX_DIM; ++d)
+    if (d < D) emitted[(int64_t)d * N + env] = em[d];
+  p.st.t_episode[env] = tl;
+  p.st.episode[env] = ep;
+  p.st.reached[env] = (uint8_t)reached;
+  if (p.st.stats) {  // per-env atomics: continuous launches are bandwidth-
+                     // bound and long, the 6 adds per env per launch are noise
+    atomicAdd(p.st.stats + MDPP_STAT_EPISODES, (double)n_episodes);
+    atomicAdd(p.st.stats + MDPP_STAT_TRANSITIONS, (double)p.T);
+    atomicAdd(p.st.stats + MDPP_STAT_REWARD, sum_reward);
+    atomicAdd(p.st.stats + MDPP_STAT_ABS_REWARD_NOISE, sum_abs_rnoise);
+    atomicAdd(p.st.stats + MDPP_STAT_ABS_TRANSITION_NOISE, sum_abs_pnoise);
+    atomicAdd(p.st.stats + MDPP_STAT_TERMINATED, (double)n_terminated);
+  }
+}
+
+template <typename R>
+__device__ __forceinline__ void continuous_reset_body(const ContinuousParams& p) {
+  const int D = p.cfg.dim, ORDER = p.cfg.order, NREL = p.cfg.n_relevant;
+  const int64_t N = p.st.n_envs;
+  const int64_t env = (int64_t)blockIdx.x * kCBlock + threadIdx.x;
+  if (env >= N) return;
+  R* derivs = reinterpret_cast<R*>(p.st.derivs);
+  R* emitted = reinterpret_cast<R*>(p.st.emitted);
+  R* obs = reinterpret_cast<R*>(p.reset_obs);
+  if (p.mask && !p.mask[env]) {
+    if (obs)
+      for (int d = 0; d < D; ++d) obs[env * D + d] = emitted[(int64_t)d * N + env];
+    return;
+  }
+  const uint32_t gid = (uint32_t)(p.env_id_offset + env);
+  const uint32_t ep = p.st.episode[env];
+  R s0[MDPP_MAX_DIM];
+  if (p.init_states) {
+    const R* src = reinterpret_cast<const R*>(p.init_states) + env * D;
+    for (int d = 0; d < D; ++d) s0[d] = src[d];
+  } else {
+    for (int attempt = 0; attempt < 64; ++attempt) {
+      box_sample<R>(p, D, gid, ep, attempt, s0);
+      if (!(p.cfg.n_term_boxes > 0 && in_term_box<R>(p, NREL, s0))) break;
+    }
+  }
+  if (p.st.stats && p.st.t_episode[env] > 0)
+    atomicAdd(p.st.stats + MDPP_STAT_EPISODES, 1.0);
+  for (int d = 0; d < D; ++d) {
+    emitted[(int64_t)d * N + env] = s0[d];
+    for (int k = 0; k <= ORDER; ++k)
+      derivs[((int64_t)k * D + d) * N + env] = k == 0 ? s0[d] : (R)0;
+    if (obs) obs[env * D + d] = s0[d];
+  }
+  p.st.t_episode[env] = 0;
+  p.st.episode[env] = ep + 1;
+  p.st.reached[env] = 0;
+}
+
+template <typename R, int NOISE>
+__global__ void __launch_bounds__(kCBlock)
+continuous_rollout_kernel(const __grid_constant__ ContinuousParams p) {
+  continuous_body<R, NOISE>(p);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kCBlock)
+continuous_reset_kernel(const __grid_constant__ ContinuousParams p) {
+  continuous_reset_body<R>(p);
+}
+
+}  // namespace mdpp

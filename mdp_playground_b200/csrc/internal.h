@@ -28,6 +28,9 @@ struct mdpp_ctx {
   mdpp::CtaMapEntry* d_cta_map = nullptr;
   int cta_map_block = 0;
   int64_t n_ctas = 0;
+  // continuous configuration (one per context)
+  bool have_continuous = false;
+  mdpp_continuous_config c_cfg;
   // runtime-specialised kernels (jit.cu), keyed by their define string
   std::map<std::string, void*> jit_functions;   // CUfunction
   std::vector<void*> jit_modules;               // CUmodule
@@ -42,6 +45,8 @@ namespace mdpp {
 // falls back to the ahead-of-time kernels), < 0 on a launch error.
 int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
                     int normal_mode, cudaStream_t stream);
+struct ContinuousParams;
+int jit_try_continuous(mdpp_ctx* ctx, ContinuousParams& p, cudaStream_t stream);
 void jit_release(mdpp_ctx* ctx);
 int fail(mdpp_ctx* ctx, int code, const std::string& msg);
 int cuda_fail(mdpp_ctx* ctx, cudaError_t e, const char* what);

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "continuous_kernels.cuh"
 #include "discrete_kernels.cuh"
 #include "embedded_sources.inc"
 #include "internal.h"
@@ -144,15 +145,20 @@ typedef long long int64_t;
 typedef unsigned long long uint64_t;
 )SRC";
 
-void* compile(mdpp_ctx* ctx, const std::vector<std::string>& defs,
-              void** module_out) {
+const char* kHeaderNames[] = {"discrete_kernels.cuh", "continuous_kernels.cuh",
+                              "device_types.h", "philox.cuh", "mdpp_b200.h",
+                              "stdint.h"};
+const char* kHeaderSources[] = {kSrc_discrete_kernels_cuh,
+                                kSrc_continuous_kernels_cuh, kSrc_device_types_h,
+                                kSrc_philox_cuh, kSrc_mdpp_b200_h, kStdintShim};
+constexpr int kNumHeaders = 6;
+
+void* compile(mdpp_ctx* ctx, const char* entry_source, const char* entry_name,
+              const std::vector<std::string>& defs, void** module_out) {
   Api& a = api();
-  const char* names[] = {"discrete_kernels.cuh", "device_types.h", "philox.cuh",
-                         "mdpp_b200.h", "stdint.h"};
-  const char* srcs[] = {kSrc_discrete_kernels_cuh, kSrc_device_types_h,
-                        kSrc_philox_cuh, kSrc_mdpp_b200_h, kStdintShim};
   nvrtcProgram prog = nullptr;
-  if (a.CreateProgram(&prog, kEntrySource, "mdpp_jit_rollout.cu", 5, srcs, names)) {
+  if (a.CreateProgram(&prog, entry_source, "mdpp_jit_entry.cu", kNumHeaders,
+                      kHeaderSources, kHeaderNames)) {
     ctx->jit_log = "nvrtcCreateProgram failed";
     return nullptr;
   }
@@ -182,7 +188,7 @@ void* compile(mdpp_ctx* ctx, const std::vector<std::string>& defs,
     return nullptr;
   }
   CUfunction fn = nullptr;
-  if (a.ModuleGetFunction(&fn, mod, "mdpp_jit_rollout")) {
+  if (a.ModuleGetFunction(&fn, mod, entry_name)) {
     ctx->jit_log = "cuModuleGetFunction failed";
     a.ModuleUnload(mod);
     return nullptr;
@@ -191,7 +197,76 @@ void* compile(mdpp_ctx* ctx, const std::vector<std::string>& defs,
   return fn;
 }
 
+const char* kContinuousEntrySource = R"SRC(
+#include "continuous_kernels.cuh"
+extern "C" __global__ void __launch_bounds__(mdpp::kCBlock)
+mdpp_jit_continuous(const __grid_constant__ mdpp::ContinuousParams p) {
+  mdpp::continuous_body<MDPP_C_REAL, MDPP_C_NOISE>(p);
+}
+)SRC";
+
+// Cached lookup: returns the CUfunction of (entry, defines), compiling it on
+// first use; nullptr if NVRTC / the driver API is unavailable or it failed.
+void* get_function(mdpp_ctx* ctx, const char* entry_source,
+                   const char* entry_name,
+                   const std::vector<std::string>& defs) {
+  Api& a = api();
+  if (!a.ok) { ctx->jit_log = a.why; return nullptr; }
+  std::string key = entry_name;
+  for (auto& d : defs) { key += ' '; key += d; }
+  auto it = ctx->jit_functions.find(key);
+  if (it != ctx->jit_functions.end()) return it->second;
+  void* mod = nullptr;
+  void* fn = compile(ctx, entry_source, entry_name, defs, &mod);
+  ctx->jit_functions[key] = fn;  // failures are cached too: no retry per call
+  if (fn) ctx->jit_modules.push_back(mod);
+  return fn;
+}
+
+int launch(mdpp_ctx* ctx, void* fn, unsigned grid, unsigned block, int smem,
+           cudaStream_t stream, void* param) {
+  Api& a = api();
+  if (smem > 48 * 1024 - 512) {
+    // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8
+    if (a.FuncSetAttribute((CUfunction)fn, 8, smem))
+      return fail(ctx, MDPP_ECUDA, "cuFuncSetAttribute(max dynamic smem) failed");
+  }
+  void* args[] = {param};
+  CUresult rc = a.LaunchKernel((CUfunction)fn, grid, 1, 1, block, 1, 1,
+                               (unsigned)smem, (CUstream)stream, args, nullptr);
+  if (rc != 0)
+    return fail(ctx, MDPP_ECUDA, "cuLaunchKernel(jit) failed: " + std::to_string(rc));
+  ctx->jit_last_used = 1;
+  return 1;
+}
+
 }  // namespace
+
+int jit_try_continuous(mdpp_ctx* ctx, ContinuousParams& p, cudaStream_t stream) {
+  ctx->jit_last_used = 0;
+  if (!ctx->jit_enabled) return 0;
+  const mdpp_continuous_config& c = p.cfg;
+  auto D = [](const char* k, const std::string& v) {
+    return std::string("-DMDPP_C_") + k + "=" + v;
+  };
+  auto I = [](long long v) { return std::to_string(v); };
+  auto B = [](bool v) { return std::string(v ? "true" : "false"); };
+  std::vector<std::string> defs = {
+      "-DMDPP_JIT", D("REAL", c.is_f64 ? "double" : "float"),
+      D("NOISE", I(p.noise_mode)), D("DIM", I(c.dim)), D("ORDER", I(c.order)),
+      D("NREL", I(c.n_relevant)), D("DELAY", I(c.delay)),
+      D("EVERY_N", I(c.reward_every_n_steps)), D("DENSE", B(c.dense)),
+      D("PNOISE", B(c.has_transition_noise)), D("RNOISE", B(c.has_reward_noise)),
+      D("IMAGE", B(c.image_mode)), D("TARGET64", B(c.target_is_f64)),
+  };
+  for (int k = 0; k < MDPP_MAX_DIM; ++k)
+    defs.push_back(D(("REL" + std::to_string(k)).c_str(),
+                     I(k < c.n_relevant ? c.relevant_indices[k] : 0)));
+  void* fn = get_function(ctx, kContinuousEntrySource, "mdpp_jit_continuous", defs);
+  if (!fn) return 0;
+  const unsigned grid = (unsigned)((p.st.n_envs + kCBlock - 1) / kCBlock);
+  return launch(ctx, fn, grid, kCBlock, 0, stream, &p);
+}
 
 int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
                     int normal_mode, cudaStream_t stream) {
@@ -207,43 +282,16 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
     ctx->jit_log = "tables or delay ring do not fit shared memory";
     return 0;
   }
-  Api& a = api();
-  if (!a.ok) { ctx->jit_log = a.why; return 0; }
   const bool fast = p.io.actions && p.io.obs && p.io.reward && p.io.terminated &&
                     p.io.truncated && !p.io.final_obs && !p.st.history;
   const int cdf_tpl = g.cdf_log2 <= 6 ? g.cdf_log2 : -1;
   std::vector<std::string> defs =
       defines_for(g, p, noise_mode, normal_mode, fast, true, cdf_tpl);
-  std::string key;
-  for (auto& d : defs) { key += d; key += ' '; }
-  auto it = ctx->jit_functions.find(key);
-  void* fn = nullptr;
-  if (it != ctx->jit_functions.end()) {
-    fn = it->second;
-    if (!fn) return 0;  // compile failed before: do not retry every call
-  } else {
-    void* mod = nullptr;
-    fn = compile(ctx, defs, &mod);
-    ctx->jit_functions[key] = fn;
-    if (!fn) return 0;
-    ctx->jit_modules.push_back(mod);
-  }
+  void* fn = get_function(ctx, kEntrySource, "mdpp_jit_rollout", defs);
+  if (!fn) return 0;
   p.ring_smem_bytes = ring_bytes;
-  const int smem = ring_bytes + g.blob_bytes;
-  if (smem > 48 * 1024 - 512) {
-    // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8
-    if (a.FuncSetAttribute((CUfunction)fn, 8, smem))
-      return fail(ctx, MDPP_ECUDA, "cuFuncSetAttribute(max dynamic smem) failed");
-  }
-  void* args[] = {&p};
-  CUresult rc = a.LaunchKernel((CUfunction)fn, (unsigned)ctx->n_ctas, 1, 1,
-                               kBlock, 1, 1, (unsigned)smem, (CUstream)stream,
-                               args, nullptr);
-  if (rc != 0)
-    return fail(ctx, MDPP_ECUDA,
-                "cuLaunchKernel(jit rollout) failed: " + std::to_string(rc));
-  ctx->jit_last_used = 1;
-  return 1;
+  return launch(ctx, fn, (unsigned)ctx->n_ctas, kBlock, ring_bytes + g.blob_bytes,
+                stream, &p);
 }
 
 void jit_release(mdpp_ctx* ctx) {
@@ -289,23 +337,34 @@ extern "C" int mdpp_jit_selftest(char* log, int log_bytes) {
         dlsym(rtc, "nvrtcGetProgramLogSize");
     auto Log = (nvrtcResult(*)(nvrtcProgram, char*)) dlsym(rtc, "nvrtcGetProgramLog");
     auto Destroy = (nvrtcResult(*)(nvrtcProgram*)) dlsym(rtc, "nvrtcDestroyProgram");
-    const char* names[] = {"discrete_kernels.cuh", "device_types.h", "philox.cuh",
-                           "mdpp_b200.h", "stdint.h"};
-    const char* srcs[] = {kSrc_discrete_kernels_cuh, kSrc_device_types_h,
-                          kSrc_philox_cuh, kSrc_mdpp_b200_h, kStdintShim};
-    nvrtcProgram prog = nullptr;
-    Create(&prog, kEntrySource, "mdpp_jit_rollout.cu", 5, srcs, names);
-    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17",
-                                     "-lineinfo"};
-    opts.insert(opts.end(), defs.begin(), defs.end());
-    std::vector<const char*> copts;
-    for (auto& o : opts) copts.push_back(o.c_str());
-    rc = Compile(prog, (int)copts.size(), copts.data());
-    size_t n = 0;
-    LogSize(prog, &n);
-    msg.assign(n, '\0');
-    if (n) Log(prog, &msg[0]);
-    Destroy(&prog);
+    // BASELINE config #3 shape for the continuous kernel
+    std::vector<std::string> cdefs = {
+        "-DMDPP_JIT", "-DMDPP_C_REAL=float", "-DMDPP_C_NOISE=2", "-DMDPP_C_DIM=6",
+        "-DMDPP_C_ORDER=2", "-DMDPP_C_NREL=2", "-DMDPP_C_DELAY=0",
+        "-DMDPP_C_EVERY_N=1", "-DMDPP_C_DENSE=true", "-DMDPP_C_PNOISE=false",
+        "-DMDPP_C_RNOISE=false", "-DMDPP_C_IMAGE=false", "-DMDPP_C_TARGET64=false",
+        "-DMDPP_C_REL0=0", "-DMDPP_C_REL1=1"};
+    for (int k = 2; k < MDPP_MAX_DIM; ++k)
+      cdefs.push_back("-DMDPP_C_REL" + std::to_string(k) + "=0");
+    rc = 0;
+    for (int which = 0; which < 2 && rc == 0; ++which) {
+      nvrtcProgram prog = nullptr;
+      Create(&prog, which ? kContinuousEntrySource : kEntrySource,
+             "mdpp_jit_entry.cu", kNumHeaders, kHeaderSources, kHeaderNames);
+      std::vector<std::string> opts = {"--gpu-architecture=sm_100a",
+                                       "-std=c++17", "-lineinfo"};
+      auto& dd = which ? cdefs : defs;
+      opts.insert(opts.end(), dd.begin(), dd.end());
+      std::vector<const char*> copts;
+      for (auto& o : opts) copts.push_back(o.c_str());
+      rc = Compile(prog, (int)copts.size(), copts.data());
+      size_t n = 0;
+      LogSize(prog, &n);
+      std::string part(n, '\0');
+      if (n) Log(prog, &part[0]);
+      msg += part;
+      Destroy(&prog);
+    }
   }
   if (log && log_bytes > 0) {
     std::strncpy(log, msg.c_str(), log_bytes - 1);

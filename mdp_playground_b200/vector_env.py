@@ -75,7 +75,7 @@ class VectorRLToyEnv:
         if self.spec.kind == "discrete":
             self._init_discrete()
         else:
-            raise NotImplementedError("continuous backend: see continuous.py")
+            self._init_continuous()
         # rl_toy_env.py:831-833: the constructor ends with reset(seed=env seed)
         self.curr_obs, _ = self.reset(seed=self.seed_dict["env"],
                                       options={"_ctor": True})
@@ -220,6 +220,8 @@ class VectorRLToyEnv:
         """(obs, info) like RLToyEnv.reset (:2217).  options: {"mask": bool[N],
         "init_state": int[N], "reset_u": float64[N] (replay mode)}."""
         options = options or {}
+        if self.spec.kind == "continuous":
+            return self._reset_continuous(seed, options)
         N, dev = self.num_envs, self.device
         mask = options.get("mask")
         if mask is not None:
@@ -258,8 +260,20 @@ class VectorRLToyEnv:
         self._check(self._lib.mdpp_discrete_reset(
             self._ctx, C.byref(self._state), _ptr(mask), _ptr(init),
             _ptr(reset_u), _ptr(obs), C.byref(opts), self._stream()))
-        self.curr_obs = obs
-        return self._cast_obs(obs), {}
+        self.curr_obs = self._observe(obs)
+        return self.curr_obs, {}
+
+    def _observe(self, state):
+        """Underlying state -> observation (identity, dtype_o cast, or the
+        image renderer when image_representations is on)."""
+        if self.spec.image_representations:
+            return self.render_observation(state)
+        if self.spec.kind == "continuous":
+            return state
+        return self._cast_obs(state)
+
+    def render_observation(self, state):
+        return state  # replaced by the CUDA renderers (render.py)
 
     def _cast_obs(self, obs):
         dt = np.dtype(self.spec.dtype_o)
@@ -271,14 +285,23 @@ class VectorRLToyEnv:
         """(obs, reward, terminated, truncated, info) like RLToyEnv.step
         (:1992).  `replay`: dict with "transition_u", "reward_noise",
         "reset_u" float64[N] arrays (noise='replay')."""
-        out = self.rollout(1, actions=torch.as_tensor(actions).reshape(1, -1),
+        N = self.num_envs
+        actions = torch.as_tensor(actions)
+        if self.spec.kind == "continuous":
+            actions = actions.reshape(1, N, self.spec.state_space_dim)
+        else:
+            actions = actions.reshape(1, N)
+        out = self.rollout(1, actions=actions,
                            replay=None if replay is None else
-                           {k: torch.as_tensor(v).reshape(1, -1)
+                           {k: torch.as_tensor(v).reshape((1,) + tuple(
+                               torch.as_tensor(v).shape))
                             for k, v in replay.items()})
-        self.curr_obs = out["obs"][0]
-        return (self._cast_obs(out["obs"][0]), out["reward"][0],
-                out["terminated"][0], out["truncated"][0],
-                {"final_obs": out["final_obs"][0]})
+        state = out["obs"][0]
+        obs = self._observe(state)
+        self.curr_obs = obs
+        return (obs, out["reward"][0], out["terminated"][0],
+                out["truncated"][0],
+                {"final_obs": out["final_obs"][0], "state": state})
 
     def rollout(self, n_steps, actions=None, replay=None, out=None,
                 want_final_obs=True):
@@ -286,6 +309,9 @@ class VectorRLToyEnv:
         None (uniform random policy drawn on device).  Returns dict of
         time-major [T, N] tensors: obs, final_obs, reward, terminated,
         truncated."""
+        if self.spec.kind == "continuous":
+            return self._rollout_continuous(n_steps, actions, replay, out,
+                                            want_final_obs)
         T, N, dev = int(n_steps), self.num_envs, self.device
         if actions is not None:
             actions = torch.as_tensor(actions, device=dev)
@@ -345,7 +371,216 @@ class VectorRLToyEnv:
         return rep
 
     # ------------------------------------------------------------------
+    # continuous backend (move_to_a_point)
+    # ------------------------------------------------------------------
+    def _init_continuous(self):
+        sp = self.spec
+        D, N, dev = sp.state_space_dim, self.num_envs, self.device
+        if D > _lib.MDPP_MAX_DIM or sp.dynamics_order > _lib.MDPP_MAX_ORDER:
+            raise NotImplementedError("state_space_dim <= 16 and order <= 4")
+        np_dt = np.dtype(sp.dtype_s)
+        if np_dt not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise NotImplementedError("continuous dtype_s must be float32/64")
+        if not np.isscalar(sp.inertia):
+            raise NotImplementedError("per-dimension inertia is not supported")
+        self._real = torch.float64 if np_dt == np.float64 else torch.float32
+        self._np_real = np_dt.type
+        self.observation_space = BoxSpace(
+            -sp.state_space_max, sp.state_space_max, (D,), np_dt,
+            seed=self.seed_dict.get("state_space"))
+        self.action_space = BoxSpace(
+            -sp.action_space_max, sp.action_space_max, (D,), np_dt,
+            seed=self.seed_dict.get("action_space"))
+        self.has_pnoise = sp.has_transition_noise
+        self.has_rnoise = sp.has_reward_noise
+        c = _lib.ContinuousConfig()
+        c.dim, c.order = D, sp.dynamics_order
+        c.n_relevant = len(sp.relevant_indices)
+        c.delay, c.reward_every_n_steps = sp.delay, sp.reward_every_n_steps
+        c.dense = int(sp.make_denser)
+        c.has_transition_noise = int(self.has_pnoise)
+        c.has_reward_noise = int(self.has_rnoise)
+        c.image_mode = int(sp.image_representations)
+        c.target_is_f64 = int("target_point" not in self.config)
+        c.is_f64 = int(np_dt == np.float64)
+        c.inertia, c.time_unit = float(sp.inertia), float(sp.time_unit)
+        c.state_space_max = float(sp.state_space_max)
+        c.action_space_max = float(sp.action_space_max)
+        c.target_radius = float(sp.target_radius)
+        c.action_loss_weight = float(sp.action_loss_weight)
+        c.transition_noise_std = sp.transition_noise
+        c.reward_noise_std = sp.reward_noise_std
+        c.reward_scale, c.reward_shift = sp.reward_scale, sp.reward_shift
+        c.term_state_reward = sp.term_state_reward
+        for k, i in enumerate(sp.relevant_indices):
+            c.relevant_indices[k] = i
+        tp = np.asarray(sp.target_point, dtype=np.float64)
+        assert tp.shape[0] == c.n_relevant, \
+            "target_point must have one entry per relevant index"
+        for k in range(c.n_relevant):
+            c.target_point[k] = float(tp[k])
+        # terminal hypercubes (:895-952); Box casts its bounds to dtype_s
+        self._term_lows, self._term_highs = [], []
+        for centre in (sp.terminal_centres or []):
+            lo = np.array([x - sp.term_state_edge / 2 for x in centre]).astype(np_dt)
+            hi = np.array([x + sp.term_state_edge / 2 for x in centre]).astype(np_dt)
+            self._term_lows.append(lo)
+            self._term_highs.append(hi)
+        if len(self._term_lows) > _lib.MDPP_MAX_TERM_BOXES:
+            raise NotImplementedError("at most 8 terminal regions")
+        c.n_term_boxes = len(self._term_lows)
+        for b, (lo, hi) in enumerate(zip(self._term_lows, self._term_highs)):
+            for k in range(c.n_relevant):
+                c.term_low[b * _lib.MDPP_MAX_DIM + k] = float(lo[k])
+                c.term_high[b * _lib.MDPP_MAX_DIM + k] = float(hi[k])
+        self._check(self._lib.mdpp_set_continuous_config(self._ctx, C.byref(c)))
+        self.n_groups = 1
+        real = self._real
+        self._derivs = torch.zeros((sp.dynamics_order + 1, D, N), dtype=real,
+                                   device=dev)
+        self._emitted = torch.zeros((D, N), dtype=real, device=dev)
+        self._t = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._episode = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._reached = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._ring = torch.zeros((sp.delay, N), dtype=real, device=dev) \
+            if sp.delay > 0 else None
+        self._stats = torch.zeros((1, _lib.MDPP_N_STATS), dtype=torch.float64,
+                                  device=dev)
+        st = _lib.ContinuousState()
+        st.n_envs = N
+        st.derivs, st.emitted = _ptr(self._derivs), _ptr(self._emitted)
+        st.t_episode, st.episode = _ptr(self._t), _ptr(self._episode)
+        st.reached, st.ring = _ptr(self._reached), _ptr(self._ring)
+        st.stats = _ptr(self._stats)
+        self._state = st
+        self._history = None
+        if self.noise == "numpy":
+            self._rng_F = [np_random(None if self.seed_dict.get("state_space") is None
+                                     else self.seed_dict["state_space"] + i)[0]
+                           for i in range(N)]
+            self._rng_E = [None] * N
+
+    def _host_box_sample(self, rng):
+        """gymnasium Box.sample of the feature space + the reference's
+        rejection of terminal regions (rl_toy_env.py:2284-2307)."""
+        sp = self.spec
+        D = sp.state_space_dim
+        rel = sp.relevant_indices
+        while True:
+            if np.isinf(sp.state_space_max):
+                s = rng.normal(size=(D,))
+            else:
+                hi = np.full((D,), sp.state_space_max).astype(self._np_real)
+                s = rng.uniform(low=-hi, high=hi, size=(D,))
+            s = s.astype(self._np_real)
+            if not any(np.all(s[rel] >= lo) and np.all(s[rel] <= hi)
+                       for lo, hi in zip(self._term_lows, self._term_highs)):
+                return s
+
+    def _reset_continuous(self, seed, options):
+        N, dev, D = self.num_envs, self.device, self.spec.state_space_dim
+        mask = options.get("mask")
+        if mask is not None:
+            mask = torch.as_tensor(mask, device=dev).to(torch.uint8).contiguous()
+        init = options.get("init_state")
+        if self.noise == "numpy" and init is None:
+            if seed is not None:
+                for i in range(N):
+                    self._rng_E[i], _ = np_random(seed + i)
+            elif self._rng_E[0] is None:
+                for i in range(N):
+                    self._rng_E[i], _ = np_random(None)
+            m = None if mask is None else mask.cpu().numpy()
+            init = self._emitted.t().cpu().numpy().copy()
+            for i in range(N):
+                if m is None or m[i]:
+                    init[i] = self._host_box_sample(self._rng_F[i])
+        elif (seed is not None and self.noise == "philox"
+              and not options.get("_ctor")):
+            self.philox_seed = int(seed) & (2**64 - 1)
+        if init is not None:
+            init = torch.as_tensor(init, device=dev).to(self._real).reshape(
+                N, D).contiguous()
+        elif self.noise == "replay" and not options.get("_ctor"):
+            raise ValueError("replay mode: pass options['init_state'] to reset()")
+        obs = torch.empty((N, D), dtype=self._real, device=dev)
+        opts = self._opts(1, _lib.MDPP_NOISE_PHILOX)
+        self._check(self._lib.mdpp_continuous_reset(
+            self._ctx, C.byref(self._state), _ptr(mask), _ptr(init), _ptr(obs),
+            C.byref(opts), self._stream()))
+        self.curr_obs = self._observe(obs)
+        return self.curr_obs, {}
+
+    def _rollout_continuous(self, n_steps, actions, replay, out, want_final_obs):
+        T, N, dev = int(n_steps), self.num_envs, self.device
+        D, real = self.spec.state_space_dim, self._real
+        if actions is None:
+            raise ValueError("continuous rollout needs an actions tensor [T,N,D]")
+        actions = torch.as_tensor(actions, device=dev)
+        if actions.dtype != real:
+            # the reference freezes the state (and warns) on a dtype that does
+            # not cast safely to dtype_s (:1640); failing loudly is safer here
+            raise TypeError(f"actions must be {real}, got {actions.dtype}")
+        actions = actions.contiguous()
+        assert actions.shape == (T, N, D), (actions.shape, (T, N, D))
+        if out is None:
+            out = {
+                "obs": torch.empty((T, N, D), dtype=real, device=dev),
+                "reward": torch.empty((T, N), dtype=real, device=dev),
+                "terminated": torch.empty((T, N), dtype=torch.bool, device=dev),
+                "truncated": torch.empty((T, N), dtype=torch.bool, device=dev),
+            }
+            if want_final_obs:
+                out["final_obs"] = torch.empty((T, N, D), dtype=real, device=dev)
+        io = _lib.ContinuousIO()
+        io.actions = _ptr(actions)
+        io.obs, io.reward = _ptr(out.get("obs")), _ptr(out.get("reward"))
+        io.final_obs = _ptr(out.get("final_obs"))
+        io.terminated = _ptr(out.get("terminated"))
+        io.truncated = _ptr(out.get("truncated"))
+        keep = []
+        if self.noise == "numpy":
+            assert not self.autoreset, \
+                "noise='numpy' needs explicit resets (draw order is host-driven)"
+            replay = {}
+            sn = np.zeros((T, N, D))
+            rn = np.zeros((T, N))
+            for t in range(T):
+                for i in range(N):
+                    if self.has_pnoise:
+                        sn[t, i] = self._rng_E[i].normal(
+                            0, self.spec.transition_noise, (D,))
+                    if self.has_rnoise:
+                        rn[t, i] = self._rng_E[i].normal(
+                            0, self.spec.reward_noise_std)
+            replay["state_noise"], replay["reward_noise"] = sn, rn
+        if self.noise in ("replay", "numpy"):
+            replay = replay or {}
+            for name, field, dt, shp in (
+                    ("state_noise", "replay_state_noise", torch.float64, (T, N, D)),
+                    ("reward_noise", "replay_reward_noise", torch.float64, (T, N)),
+                    ("reset_state", "replay_reset_state", real, (T, N, D))):
+                if replay.get(name) is not None:
+                    t_ = torch.as_tensor(replay[name], device=dev).to(dt).reshape(
+                        shp).contiguous()
+                    keep.append(t_)
+                    setattr(io, field, _ptr(t_))
+        opts = self._opts(T)
+        if not (self.has_pnoise or self.has_rnoise) and self.noise == "philox" \
+                and not self.autoreset:
+            opts.noise_mode = _lib.MDPP_NOISE_OFF
+        self._check(self._lib.mdpp_continuous_rollout(
+            self._ctx, C.byref(self._state), C.byref(io), C.byref(opts),
+            self._stream()))
+        self._step_index += T
+        return out
+
+    # ------------------------------------------------------------------
     def get_augmented_state(self):
+        if self.spec.kind == "continuous":
+            return {"curr_state": self._emitted.t().contiguous(),
+                    "curr_obs": self.curr_obs,
+                    "state_derivatives": self._derivs.permute(2, 0, 1).contiguous()}
         """Batched analogue of RLToyEnv.get_augmented_state (:2127):
         curr_state int64[N], curr_obs, augmented_state float64[N, L+d+1]
         (NaN where the reference has NaN)."""
