@@ -153,8 +153,9 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   const bool IMAGE = MDPP_C_CONST(IMAGE, p.cfg.image_mode != 0);
   const bool TARGET64 = MDPP_C_CONST(TARGET64, p.cfg.target_is_f64 != 0);
   const int64_t N = p.st.n_envs;
-  const int64_t env = (int64_t)blockIdx.x * kCBlock + threadIdx.x;
-  if (env >= N) return;
+  const int64_t env_raw = (int64_t)blockIdx.x * kCBlock + threadIdx.x;
+  const bool active = env_raw < N;
+  const int64_t env = active ? env_raw : 0;
   const uint32_t gid = (uint32_t)(p.env_id_offset + env);
 
   const R amax = (R)p.cfg.action_space_max, smax = (R)p.cfg.state_space_max;
@@ -182,6 +183,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
 
   double sum_reward = 0, sum_abs_rnoise = 0, sum_abs_pnoise = 0;
   uint32_t n_episodes = 0, n_terminated = 0;
+  if (active) {
 
   // distance of a state's relevant part to the target, in the dtype numpy
   // would use: R when target_point was given (cast to dtype_s :646), float64
@@ -413,14 +415,20 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   p.st.t_episode[env] = tl;
   p.st.episode[env] = ep;
   p.st.reached[env] = (uint8_t)reached;
-  if (p.st.stats) {  // per-env atomics: continuous launches are bandwidth-
-                     // bound and long, the 6 adds per env per launch are noise
-    atomicAdd(p.st.stats + MDPP_STAT_EPISODES, (double)n_episodes);
-    atomicAdd(p.st.stats + MDPP_STAT_TRANSITIONS, (double)p.T);
-    atomicAdd(p.st.stats + MDPP_STAT_REWARD, sum_reward);
-    atomicAdd(p.st.stats + MDPP_STAT_ABS_REWARD_NOISE, sum_abs_rnoise);
-    atomicAdd(p.st.stats + MDPP_STAT_ABS_TRANSITION_NOISE, sum_abs_pnoise);
-    atomicAdd(p.st.stats + MDPP_STAT_TERMINATED, (double)n_terminated);
+  }  // active
+  if (p.st.stats) {  // warp-reduced: one atomic per warp and counter
+    double vals[6] = {(double)n_episodes, active ? (double)p.T : 0.0, sum_reward,
+                      sum_abs_rnoise, sum_abs_pnoise, (double)n_terminated};
+    const int slots[6] = {MDPP_STAT_EPISODES, MDPP_STAT_TRANSITIONS,
+                          MDPP_STAT_REWARD, MDPP_STAT_ABS_REWARD_NOISE,
+                          MDPP_STAT_ABS_TRANSITION_NOISE, MDPP_STAT_TERMINATED};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double v = vals[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(p.st.stats + slots[k], v);
+    }
   }
 }
 
