@@ -62,8 +62,11 @@ template <> struct RealOps<double> {
 
 #ifdef MDPP_JIT
 #define MDPP_C_CONST(name, runtime) (MDPP_C_##name)
+// double constants travel as their bit pattern (exact, inf-safe)
+#define MDPP_C_F64(name, runtime) (__longlong_as_double(MDPP_C_##name##_BITS))
 #else
 #define MDPP_C_CONST(name, runtime) (runtime)
+#define MDPP_C_F64(name, runtime) (runtime)
 #endif
 
 // relevant_indices[k]: a literal table in the specialised build so that
@@ -158,9 +161,21 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   const int64_t env = active ? env_raw : 0;
   const uint32_t gid = (uint32_t)(p.env_id_offset + env);
 
-  const R amax = (R)p.cfg.action_space_max, smax = (R)p.cfg.state_space_max;
-  const R inertia = (R)p.cfg.inertia;
-  const R radius_r = (R)p.cfg.target_radius;
+  const R amax = (R)MDPP_C_F64(AMAX, p.cfg.action_space_max);
+  const R smax = (R)MDPP_C_F64(SMAX, p.cfg.state_space_max);
+  const R inertia = (R)MDPP_C_F64(INERTIA, p.cfg.inertia);
+  const double radius64 = MDPP_C_F64(RADIUS, p.cfg.target_radius);
+  const R radius_r = (R)radius64;
+  const double alw = MDPP_C_F64(ALW, p.cfg.action_loss_weight);
+  const double r_scale = MDPP_C_F64(SCALE, p.cfg.reward_scale);
+  const double r_shift = MDPP_C_F64(SHIFT, p.cfg.reward_shift);
+  const double term_add = MDPP_C_F64(
+      TERM_ADD, __dmul_rn(p.cfg.term_state_reward, p.cfg.reward_scale));
+  const double p_std = MDPP_C_F64(P_STD, p.cfg.transition_noise_std);
+  const double r_std = MDPP_C_F64(R_STD, p.cfg.reward_noise_std);
+  const double tu_pow[MDPP_MAX_ORDER] = {
+      MDPP_C_F64(TU1, p.tu_pow[0]), MDPP_C_F64(TU2, p.tu_pow[1]),
+      MDPP_C_F64(TU3, p.tu_pow[2]), MDPP_C_F64(TU4, p.tu_pow[3])};
 
   R sd[MDPP_MAX_ORDER + 1][MDPP_MAX_DIM];
   R em[MDPP_MAX_DIM];
@@ -199,19 +214,35 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
     });
   };
 
+  // ||aug[-2][rel] - target||: the distance of the previous emitted state is
+  // last step's dist_new, so it is carried instead of recomputed
+  double dist_prev = dist_to_target(em);
+  // the next step's action row is fetched one step ahead of its use
+  R a_next[MDPP_MAX_DIM];
+  {
+    const R* ap = reinterpret_cast<const R*>(p.io.actions) + env * D;
+#pragma unroll
+    for (int d = 0; d < MDPP_MAX_DIM; ++d)
+      if (d < D) a_next[d] = ap[d];
+  }
   for (int t = 0; t < p.T; ++t) {
     const uint64_t step = p.step_index + (uint64_t)t;
     const int64_t row = ((int64_t)t * N + env);
-    const R* ap = reinterpret_cast<const R*>(p.io.actions) + row * D;
     R a[MDPP_MAX_DIM], nxt[MDPP_MAX_DIM];
     bool in_range = true;
 #pragma unroll
     for (int d = 0; d < MDPP_MAX_DIM; ++d)
       if (d < D) {
-        a[d] = ap[d];
+        a[d] = a_next[d];
         in_range = in_range && a[d] >= -amax && a[d] <= amax;  // Box.contains
       }
-    const double dist_old = dist_to_target(em);  // ||aug[-2][rel] - target||
+    if (t + 1 < p.T) {
+      const R* ap = reinterpret_cast<const R*>(p.io.actions) + (row + N) * D;
+#pragma unroll
+      for (int d = 0; d < MDPP_MAX_DIM; ++d)
+        if (d < D) a_next[d] = ap[d];
+    }
+    const double dist_old = dist_prev;
 
     // ---- transition -----------------------------------------------------
     if (in_range) {
@@ -223,15 +254,23 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
 #pragma unroll
         for (int j = 0; j < MDPP_MAX_ORDER; ++j)
           if (i < ORDER && j < ORDER - i) {
-            const R tu = (R)p.tu_pow[j];
+            const R tu = (R)tu_pow[j];
             // (j+1)! as the float64 scipy.special.factorial returns
             const double fact = j == 0 ? 1.0 : j == 1 ? 2.0 : j == 2 ? 6.0 : 24.0;
 #pragma unroll
             for (int d = 0; d < MDPP_MAX_DIM; ++d)
               if (d < D) {
                 const R term = O::mul(sd[i + j + 1][d], tu);
-                sd[i][d] = (R)__dadd_rn((double)sd[i][d],
-                                        __ddiv_rn((double)term, fact));
+                if (sizeof(R) == 4 && j <= 1) {
+                  // f32(f64(x) + f64(t) / {1,2}): the quotient is exact and a
+                  // sum rounded to 53 then 24 bits equals the sum rounded to
+                  // 24 bits directly (53 >= 2*24 + 2), so this IS the
+                  // reference's mixed-precision result, without conversions
+                  sd[i][d] = O::add(sd[i][d], j == 0 ? term : O::mul(term, (R)0.5));
+                } else {
+                  sd[i][d] = (R)__dadd_rn((double)sd[i][d],
+                                          __ddiv_rn((double)term, fact));
+                }
               }
           }
 #pragma unroll
@@ -260,7 +299,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               if (4 * c + k < D)
-                nz[4 * c + k] = __dmul_rn(p.cfg.transition_noise_std, z[k]);
+                nz[4 * c + k] = __dmul_rn(p_std, z[k]);
           }
       }
 #pragma unroll
@@ -286,7 +325,8 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
         }
     }
     const double dist_new = dist_to_target(nxt);
-    const double radius = TARGET64 ? p.cfg.target_radius : (double)radius_r;
+    dist_prev = dist_new;
+    const double radius = TARGET64 ? radius64 : (double)radius_r;
     if (dist_new < radius) reached = true;
     tl += 1;
     phase = (phase + 1 == EVERY_N) ? 0 : phase + 1;
@@ -309,8 +349,10 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
       is_real = false;
     }
     {  // reward -= action_loss_weight * ||action||  (always makes it dtype_s)
-      const R an = seq_norm<R>(D, [&](int k) { return a[k]; });
-      const R loss = O::mul((R)p.cfg.action_loss_weight, an);
+      // weight 0: 0 * ||a|| = 0 (finite actions); the subtraction still
+      // happens for its dtype effect, the norm is skipped
+      const R loss = alw == 0.0 ? (R)0
+                                : O::mul((R)alw, seq_norm<R>(D, [&](int k) { return a[k]; }));
       if (is_real) rr = O::add(rr, -loss);
       else if (sizeof(R) == 4 && TARGET64 && DENSE)
         rd = __dadd_rn(rd, -(double)loss);  // float64 - float32 -> float64
@@ -336,24 +378,23 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
                              STREAM_NORMAL, p.k0, p.k1);
         double z0, z1;
         normal_pair_f64(w.x, w.y, &z0, &z1);
-        nrw = __dmul_rn(p.cfg.reward_noise_std, z0);
+        nrw = __dmul_rn(r_std, z0);
       }
       sum_abs_rnoise += fabs(nrw);
     }
     const bool box = p.cfg.n_term_boxes > 0 && in_term_box<R>(p, NREL, nxt);
     const bool done = box || reached;
-    const double term_add = __dmul_rn(p.cfg.term_state_reward, p.cfg.reward_scale);
     R out_r;
     if (is_real) {  // np.float32 op python-float: the scalar is cast first
       if (RNOISE) rr = O::add(rr, (R)nrw);
-      rr = O::mul(rr, (R)p.cfg.reward_scale);
-      rr = O::add(rr, (R)p.cfg.reward_shift);
+      rr = O::mul(rr, (R)r_scale);
+      rr = O::add(rr, (R)r_shift);
       if (done) rr = O::add(rr, (R)term_add);
       out_r = rr;
     } else {
       if (RNOISE) rd = __dadd_rn(rd, nrw);
-      rd = __dmul_rn(rd, p.cfg.reward_scale);
-      rd = __dadd_rn(rd, p.cfg.reward_shift);
+      rd = __dmul_rn(rd, r_scale);
+      rd = __dadd_rn(rd, r_shift);
       if (done) rd = __dadd_rn(rd, term_add);
       out_r = (R)rd;
     }
@@ -392,6 +433,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
         }
       tl = 0; phase = 0; reached = false;
       ep += 1; n_episodes += 1;
+      dist_prev = dist_to_target(em);
     }
     if (p.io.obs) {
       R* ob = reinterpret_cast<R*>(p.io.obs) + row * D;

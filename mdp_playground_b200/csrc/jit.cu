@@ -259,6 +259,21 @@ int jit_try_continuous(mdpp_ctx* ctx, ContinuousParams& p, cudaStream_t stream) 
       D("PNOISE", B(c.has_transition_noise)), D("RNOISE", B(c.has_reward_noise)),
       D("IMAGE", B(c.image_mode)), D("TARGET64", B(c.target_is_f64)),
   };
+  auto F = [&](const char* k, double v) {
+    unsigned long long bits;
+    std::memcpy(&bits, &v, 8);
+    char buf[40];
+    std::snprintf(buf, sizeof buf, "0x%llxll", bits);
+    defs.push_back(D((std::string(k) + "_BITS").c_str(), buf));
+  };
+  F("AMAX", c.action_space_max); F("SMAX", c.state_space_max);
+  F("INERTIA", c.inertia); F("RADIUS", c.target_radius);
+  F("ALW", c.action_loss_weight); F("SCALE", c.reward_scale);
+  F("SHIFT", c.reward_shift);
+  F("TERM_ADD", c.term_state_reward * c.reward_scale);
+  F("P_STD", c.transition_noise_std); F("R_STD", c.reward_noise_std);
+  F("TU1", p.tu_pow[0]); F("TU2", p.tu_pow[1]); F("TU3", p.tu_pow[2]);
+  F("TU4", p.tu_pow[3]);
   for (int k = 0; k < MDPP_MAX_DIM; ++k)
     defs.push_back(D(("REL" + std::to_string(k)).c_str(),
                      I(k < c.n_relevant ? c.relevant_indices[k] : 0)));
@@ -346,6 +361,10 @@ extern "C" int mdpp_jit_selftest(char* log, int log_bytes) {
         "-DMDPP_C_REL0=0", "-DMDPP_C_REL1=1"};
     for (int k = 2; k < MDPP_MAX_DIM; ++k)
       cdefs.push_back("-DMDPP_C_REL" + std::to_string(k) + "=0");
+    for (const char* k : {"AMAX", "SMAX", "INERTIA", "RADIUS", "ALW", "SCALE",
+                          "SHIFT", "TERM_ADD", "P_STD", "R_STD", "TU1", "TU2",
+                          "TU3", "TU4"})
+      cdefs.push_back(std::string("-DMDPP_C_") + k + "_BITS=0x3ff0000000000000ll");
     rc = 0;
     for (int which = 0; which < 2 && rc == 0; ++which) {
       nvrtcProgram prog = nullptr;
