@@ -259,6 +259,70 @@ int mdpp_continuous_reset(mdpp_ctx* ctx, const mdpp_continuous_state* st,
                           void* cuda_stream);
 #endif
 
+/* ------------------------------------------------------------------------
+ * Image observations (replaces ImageMultiDiscrete.generate_image,
+ * spaces/image_multi_discrete.py:129-270, and ImageContinuous.generate_image
+ * / get_image_representation, spaces/image_continuous.py:116-277).
+ * Stateless kernels: states in, uint8 images out, obs[x][y] = pil[y][x].
+ * The tables are DEVICE arrays built on the host by
+ * mdp_playground_b200/image_tables.py (Pillow is the raster authority).
+ * --------------------------------------------------------------------- */
+typedef struct mdpp_image_discrete_tables {
+  int32_t width, height, n_states;
+  int32_t r_min, n_radii;          /* polygon radius R in [r_min, r_min+n)   */
+  int32_t n_xvar, n_yvar;          /* vertex-offset variants per (state, R)  */
+  int32_t has_scale, has_shift, has_rotate, has_flip;
+  int32_t sh_quant, ro_quant;
+  int32_t reserved0;
+  const uint64_t* mask_bits;       /* [n_masks][64] row bitmaps              */
+  const int32_t* mask_index;       /* [S][n_radii][n_xvar][n_yvar]           */
+  const uint8_t* xvar;             /* [S][n_radii][width]  by shift_w        */
+  const uint8_t* yvar;             /* [S][n_radii][height] by shift_h        */
+  const int32_t* rot_coeff;        /* [360][6] 16.16 inverse affine          */
+  const double* r_thresholds;      /* [n_radii-1] uniform -> R               */
+} mdpp_image_discrete_tables;
+
+#ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
+/* Renders n_images polygon images.  Image m belongs to env (m % n_envs) at
+ * step opts->step_index + m / n_envs (so a [T][N] block of states renders in
+ * one launch).  params_in [n_images][5] = (R, shift_w, shift_h, rotation or
+ * -1, flip 0/1 LR/2 TB) replays recorded transforms; NULL draws them from
+ * Philox (stream `image_stream`: 3 for step observations, 6 for reset
+ * observations).  params_out (optional) receives the parameters used.      */
+int mdpp_render_discrete(mdpp_ctx* ctx, const mdpp_image_discrete_tables* tb,
+                         const int64_t* states, const int32_t* params_in,
+                         int32_t* params_out, uint8_t* out, int64_t n_images,
+                         int64_t n_envs, int32_t image_stream,
+                         const mdpp_step_opts* opts, void* cuda_stream);
+#endif
+
+#define MDPP_MAX_STAMP_ROWS 32
+
+typedef struct mdpp_image_continuous_config {
+  int32_t width, height;
+  int32_t dim;                     /* state_space_dim                        */
+  int32_t n_sub_images;            /* 1, or 2 with irrelevant dimensions     */
+  int32_t rel_index[2];            /* ImageContinuous.relevant_indices [0,1] */
+  int32_t irr_index[2];
+  int32_t is_f64;                  /* dtype of the states                    */
+  int32_t n_rects;                 /* terminal regions (relevant image only) */
+  int32_t has_target;
+  int32_t stamp_rows;              /* 2*radius+1                             */
+  int32_t stamp_radius;
+  int32_t reserved0;
+  double feat_low[2], feat_high[2];    /* feature-space bounds of rel_index   */
+  int32_t rect[MDPP_MAX_TERM_BOXES][4];  /* x0, y0, x1, y1 inclusive pixels   */
+  int32_t target_pixel[2];
+  int32_t stamp[MDPP_MAX_STAMP_ROWS][2]; /* row: x offset, width (Pillow)     */
+} mdpp_image_continuous_config;
+
+#ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
+/* states: real [n_images][dim]; out: uint8 [n_images][n_sub*width][height][3] */
+int mdpp_render_continuous(mdpp_ctx* ctx, const mdpp_image_continuous_config* cfg,
+                           const void* states, uint8_t* out, int64_t n_images,
+                           void* cuda_stream);
+#endif
+
 #ifdef __cplusplus
 }
 #endif

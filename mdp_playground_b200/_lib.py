@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = (
     "mdpp_set_discrete_groups", "mdpp_discrete_rollout", "mdpp_discrete_reset",
     "mdpp_set_jit", "mdpp_jit_last_used", "mdpp_jit_log", "mdpp_jit_selftest",
     "mdpp_set_continuous_config", "mdpp_continuous_rollout",
-    "mdpp_continuous_reset",
+    "mdpp_continuous_reset", "mdpp_render_discrete", "mdpp_render_continuous",
 )
 MDPP_MAX_DIM, MDPP_MAX_ORDER, MDPP_MAX_TERM_BOXES = 16, 4, 8
 
@@ -113,6 +113,38 @@ class ContinuousIO(C.Structure):
     ]
 
 
+class ImageDiscreteTables(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("n_states", C.c_int32),
+        ("r_min", C.c_int32), ("n_radii", C.c_int32),
+        ("n_xvar", C.c_int32), ("n_yvar", C.c_int32),
+        ("has_scale", C.c_int32), ("has_shift", C.c_int32),
+        ("has_rotate", C.c_int32), ("has_flip", C.c_int32),
+        ("sh_quant", C.c_int32), ("ro_quant", C.c_int32), ("reserved0", C.c_int32),
+        ("mask_bits", C.c_void_p), ("mask_index", C.c_void_p),
+        ("xvar", C.c_void_p), ("yvar", C.c_void_p), ("rot_coeff", C.c_void_p),
+        ("r_thresholds", C.c_void_p),
+    ]
+
+
+MDPP_MAX_STAMP_ROWS = 32
+
+
+class ImageContinuousConfig(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("dim", C.c_int32),
+        ("n_sub_images", C.c_int32),
+        ("rel_index", C.c_int32 * 2), ("irr_index", C.c_int32 * 2),
+        ("is_f64", C.c_int32), ("n_rects", C.c_int32), ("has_target", C.c_int32),
+        ("stamp_rows", C.c_int32), ("stamp_radius", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("feat_low", C.c_double * 2), ("feat_high", C.c_double * 2),
+        ("rect", (C.c_int32 * 4) * MDPP_MAX_TERM_BOXES),
+        ("target_pixel", C.c_int32 * 2),
+        ("stamp", (C.c_int32 * 2) * MDPP_MAX_STAMP_ROWS),
+    ]
+
+
 _lib = None
 
 
@@ -154,6 +186,11 @@ def load():
         C.POINTER(StepOpts), P]
     lib.mdpp_continuous_reset.argtypes = [
         P, C.POINTER(ContinuousState), P, P, P, C.POINTER(StepOpts), P]
+    lib.mdpp_render_discrete.argtypes = [
+        P, C.POINTER(ImageDiscreteTables), P, P, P, P, C.c_int64, C.c_int64,
+        C.c_int32, C.POINTER(StepOpts), P]
+    lib.mdpp_render_continuous.argtypes = [
+        P, C.POINTER(ImageContinuousConfig), P, P, C.c_int64, P]
     if lib.mdpp_abi_version() != 1:
         raise RuntimeError("libmdpp_b200.so ABI version mismatch; rebuild")
     _lib = lib

@@ -1,0 +1,299 @@
+// Image-observation renderers (K4 ImageMultiDiscrete, K5 ImageContinuous).
+//
+// K4 restates spaces/image_multi_discrete.py:129-270: polygon -> rotate ->
+// flip -> transpose, as ONE gather per output byte: the final pixel is mapped
+// back through the flip and Pillow's 16.16 fixed-point rotation to the polygon
+// image, where a bit of the (state, R, vertex-variant) mask decides 0 / 255.
+// K5 restates spaces/image_continuous.py:116-246: background 208, black
+// terminal rectangles, green target disc, blue agent disc (painter's order),
+// relevant and irrelevant sub-images stacked along x.
+//
+// One CTA renders one image; a thread produces 16 consecutive output bytes and
+// writes them with one 128-bit streaming store.  Chunks outside the shape's
+// bounding box are emitted without per-pixel work (most of the image is
+// background), so the kernel stays store-bandwidth bound.
+#include "internal.h"
+#include "philox.cuh"
+
+namespace mdpp {
+
+constexpr int kRBlock = 128;
+constexpr int kMaskRows = 64;
+constexpr int kMaskCentre = 31;
+
+struct RenderDParams {
+  mdpp_image_discrete_tables tb;
+  const int64_t* states;
+  const int32_t* params_in;
+  int32_t* params_out;
+  uint8_t* out;
+  int64_t n_envs;
+  uint32_t k0, k1, stream;
+  uint64_t step_index;
+  int64_t env_id_offset;
+};
+
+__device__ __forceinline__ int floor_div(int a, int b) {
+  int q = a / b;
+  return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+__global__ void __launch_bounds__(kRBlock)
+render_discrete_kernel(const __grid_constant__ RenderDParams p) {
+  __shared__ uint64_t mask[kMaskRows];
+  __shared__ int prm[8];
+  const int64_t m = blockIdx.x;
+  const mdpp_image_discrete_tables& tb = p.tb;
+  const int W = tb.width, H = tb.height;
+  if (threadIdx.x == 0) {
+    int state = (int)p.states[m];
+    state = min(max(state, 0), tb.n_states - 1);
+    int R, sw, sh, rot, flip;
+    if (p.params_in) {
+      const int32_t* q = p.params_in + m * 5;
+      R = q[0]; sw = q[1]; sh = q[2]; rot = q[3]; flip = q[4];
+    } else {
+      // draw order of the reference (:149-181, :251, :258-259); one Philox
+      // call per image: w0 scale, w1 / w2 shifts, w3 rotation + flip bits
+      const uint32_t gid = (uint32_t)(p.env_id_offset + m % p.n_envs);
+      const uint64_t step = p.step_index + (uint64_t)(m / p.n_envs);
+      U4 w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32), p.stream,
+                           p.k0, p.k1);
+      R = tb.r_min;
+      if (tb.has_scale) {
+        const double u = uniform32(w.x);
+        for (int k = 0; k < tb.n_radii - 1; ++k) R += tb.r_thresholds[k] <= u;
+      }
+      sw = W / 2; sh = H / 2;
+      if (tb.has_shift) {  // integers(-m + 1, m), m = W/2 - R, then quantise
+        const int mw = W / 2 - R, mh = H / 2 - R;
+        const int aw = -mw + 1 + (int)__umulhi(w.y, (uint32_t)max(2 * mw - 1, 1));
+        const int ah = -mh + 1 + (int)__umulhi(w.z, (uint32_t)max(2 * mh - 1, 1));
+        sw += floor_div(aw, tb.sh_quant) * tb.sh_quant;
+        sh += floor_div(ah, tb.sh_quant) * tb.sh_quant;
+      }
+      rot = -1;
+      if (tb.has_rotate)
+        rot = ((int)__umulhi(w.w, 360u) / tb.ro_quant) * tb.ro_quant;
+      flip = 0;
+      if (tb.has_flip && (w.w & 1u) == 0) flip = (w.w & 2u) == 0 ? 1 : 2;
+    }
+    prm[0] = state; prm[1] = R; prm[2] = sw; prm[3] = sh; prm[4] = rot; prm[5] = flip;
+    if (p.params_out) {
+      int32_t* q = p.params_out + m * 5;
+      q[0] = R; q[1] = sw; q[2] = sh; q[3] = rot; q[4] = flip;
+    }
+  }
+  __syncthreads();
+  const int state = prm[0], R = prm[1], sw = prm[2], sh = prm[3], rot = prm[4],
+            flip = prm[5];
+  if (threadIdx.x < kMaskRows) {
+    const int ri = min(max(R - tb.r_min, 0), tb.n_radii - 1);
+    const int cell = state * tb.n_radii + ri;
+    const int xv = tb.xvar[(int64_t)cell * W + min(max(sw, 0), W - 1)];
+    const int yv = tb.yvar[(int64_t)cell * H + min(max(sh, 0), H - 1)];
+    const int id = tb.mask_index[((int64_t)cell * tb.n_xvar + xv) * tb.n_yvar + yv];
+    mask[threadIdx.x] = tb.mask_bits[(int64_t)id * kMaskRows + threadIdx.x];
+  }
+  int a0 = 65536, a1 = 0, a2 = 0, a3 = 0, a4 = 65536, a5 = 0;
+  if (rot >= 0) {
+    const int32_t* c = tb.rot_coeff + (rot % 360) * 6;
+    a0 = c[0]; a1 = c[1]; a2 = c[2]; a3 = c[3]; a4 = c[4]; a5 = c[5];
+  }
+  // bounding box of the polygon (disc of radius R around the centre) in the
+  // FINAL image: forward-map the centre through the rotation and the flip
+  float cx = (float)sw, cy = (float)sh;
+  if (rot >= 0) {
+    const float X = (float)sw * 65536.f - (float)a2, Y = (float)sh * 65536.f - (float)a5;
+    const float det = (float)a0 * (float)a4 - (float)a1 * (float)a3;
+    cx = ((float)a4 * X - (float)a1 * Y) / det;
+    cy = ((float)a0 * Y - (float)a3 * X) / det;
+  }
+  if (flip == 1) cx = (float)(W - 1) - cx;
+  if (flip == 2) cy = (float)(H - 1) - cy;
+  const int bx0 = (int)floorf(cx) - R - 3, bx1 = (int)ceilf(cx) + R + 3;
+  const int by0 = (int)floorf(cy) - R - 3, by1 = (int)ceilf(cy) + R + 3;
+  __syncthreads();
+
+  auto pixel = [&](int x, int y) -> uint32_t {
+    int fx = x, fy = y;
+    if (flip == 1) fx = W - 1 - x;
+    if (flip == 2) fy = H - 1 - y;
+    int rx = fx, ry = fy;
+    if (rot >= 0) {
+      rx = (a2 + a1 * fy + a0 * fx) >> 16;
+      ry = (a5 + a4 * fy + a3 * fx) >> 16;
+      if ((unsigned)rx >= (unsigned)W || (unsigned)ry >= (unsigned)H) return 0u;
+    }
+    const int mx = rx - sw + kMaskCentre, my = ry - sh + kMaskCentre;
+    if ((unsigned)mx >= 64u || (unsigned)my >= (unsigned)kMaskRows) return 0u;
+    return ((mask[my] >> mx) & 1ull) ? 255u : 0u;
+  };
+
+  const int total = W * H;
+  uint8_t* out = p.out + m * (int64_t)total;
+  const bool aligned = (total % 16) == 0;  // every image starts 16-B aligned
+  if (aligned) {
+    uint4* out4 = reinterpret_cast<uint4*>(out);
+    for (int i = threadIdx.x; i < total / 16; i += kRBlock) {
+      const int idx = i * 16;
+      const int x0 = idx / H, y0 = idx - x0 * H;
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      const bool one_col = y0 + 15 < H;
+      const bool skip = one_col
+          ? (x0 < bx0 || x0 > bx1 || y0 > by1 || y0 + 15 < by0)
+          : (x0 + 1 < bx0 || x0 > bx1);
+      if (!skip) {
+        int x = x0, y = y0;
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+          w[b >> 2] |= pixel(x, y) << ((b & 3) * 8);
+          if (++y == H) { y = 0; ++x; }
+        }
+      }
+      __stcs(out4 + i, make_uint4(w[0], w[1], w[2], w[3]));
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < total; idx += kRBlock)
+      out[idx] = (uint8_t)pixel(idx / H, idx % H);
+  }
+}
+
+struct RenderCParams {
+  mdpp_image_continuous_config cfg;
+  const void* states;
+  uint8_t* out;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(kRBlock)
+render_continuous_kernel(const __grid_constant__ RenderCParams p) {
+  const mdpp_image_continuous_config& c = p.cfg;
+  const int W = c.width, H = c.height;
+  const int64_t m = blockIdx.x / c.n_sub_images;
+  const int sub = blockIdx.x % c.n_sub_images;  // 0 relevant, 1 irrelevant
+  const R* st = reinterpret_cast<const R*>(p.states) + m * c.dim;
+  // convert_to_pixel (:248-277): ((v - lo) / (hi - lo)) in dtype_s, promoted
+  // to float64 by the integer image shape, truncated
+  int px[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const R v = st[sub == 0 ? c.rel_index[k] : c.irr_index[k]];
+    const R lo = (R)c.feat_low[k], hi = (R)c.feat_high[k];
+    R frac;
+    if (sizeof(R) == 4) frac = (R)__fdiv_rn(__fsub_rn((float)v, (float)lo),
+                                           __fsub_rn((float)hi, (float)lo));
+    else frac = (R)__ddiv_rn(__dsub_rn((double)v, (double)lo),
+                             __dsub_rn((double)hi, (double)lo));
+    px[k] = (int)__dmul_rn((double)frac, (double)(k == 0 ? W : H));
+  }
+  const int rad = c.stamp_radius;
+  const bool rel = sub == 0;
+  auto in_stamp = [&](int x, int y, int cx, int cy) -> bool {
+    const int r = y - cy + rad;
+    if ((unsigned)r >= (unsigned)c.stamp_rows) return false;
+    const int dx = x - cx - c.stamp[r][0];
+    return (unsigned)dx < (unsigned)c.stamp[r][1];
+  };
+  auto colour = [&](int x, int y, int ch) -> uint32_t {
+    if (in_stamp(x, y, px[0], px[1])) return ch == 2 ? 255u : 0u;  // agent, blue
+    if (rel) {
+      if (c.has_target && in_stamp(x, y, c.target_pixel[0], c.target_pixel[1]))
+        return ch == 1 ? 255u : 0u;                                 // target, green
+      for (int b = 0; b < c.n_rects; ++b)
+        if (x >= c.rect[b][0] && x <= c.rect[b][2] && y >= c.rect[b][1] &&
+            y <= c.rect[b][3])
+          return 0u;                                                // terminal, black
+    }
+    return 208u;
+  };
+  const int total = W * H * 3;
+  uint8_t* out = p.out + ((int64_t)m * c.n_sub_images + sub) * (int64_t)total;
+  if (total % 16 == 0) {
+    uint4* out4 = reinterpret_cast<uint4*>(out);
+    for (int i = threadIdx.x; i < total / 16; i += kRBlock) {
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      int pix = (i * 16) / 3, ch = (i * 16) % 3;
+      int x = pix / H, y = pix - x * H;
+#pragma unroll
+      for (int b = 0; b < 16; ++b) {
+        w[b >> 2] |= colour(x, y, ch) << ((b & 3) * 8);
+        if (++ch == 3) { ch = 0; if (++y == H) { y = 0; ++x; } }
+      }
+      __stcs(out4 + i, make_uint4(w[0], w[1], w[2], w[3]));
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < total; idx += kRBlock) {
+      const int pix = idx / 3;
+      out[idx] = (uint8_t)colour(pix / H, pix % H, idx % 3);
+    }
+  }
+}
+
+}  // namespace mdpp
+
+using namespace mdpp;
+
+extern "C" int mdpp_render_discrete(mdpp_ctx* ctx,
+                                    const mdpp_image_discrete_tables* tb,
+                                    const int64_t* states,
+                                    const int32_t* params_in,
+                                    int32_t* params_out, uint8_t* out,
+                                    int64_t n_images, int64_t n_envs,
+                                    int32_t image_stream,
+                                    const mdpp_step_opts* opts,
+                                    void* cuda_stream) {
+  if (!ctx) return MDPP_EINVAL;
+  if (!tb || !states || !out || !opts || n_images < 1 || n_envs < 1)
+    return fail(ctx, MDPP_EINVAL, "render_discrete: bad arguments");
+  if (tb->width < 1 || tb->height < 1 || !tb->mask_bits || !tb->mask_index ||
+      !tb->xvar || !tb->yvar || !tb->rot_coeff)
+    return fail(ctx, MDPP_EINVAL, "render_discrete: incomplete tables");
+  if (tb->has_scale && tb->n_radii > 1 && !tb->r_thresholds)
+    return fail(ctx, MDPP_EINVAL, "render_discrete: missing r_thresholds");
+  if (n_images > 0x7fffffffLL)
+    return fail(ctx, MDPP_EINVAL, "render_discrete: too many images per call");
+  MDPP_CUDA(ctx, cudaSetDevice(ctx->device));
+  RenderDParams p;
+  p.tb = *tb;
+  p.states = states;
+  p.params_in = params_in;
+  p.params_out = params_out;
+  p.out = out;
+  p.n_envs = n_envs;
+  p.k0 = (uint32_t)opts->seed;
+  p.k1 = (uint32_t)(opts->seed >> 32);
+  p.stream = (uint32_t)image_stream;
+  p.step_index = opts->step_index;
+  p.env_id_offset = opts->env_id_offset;
+  render_discrete_kernel<<<(unsigned)n_images, kRBlock, 0,
+                           (cudaStream_t)cuda_stream>>>(p);
+  MDPP_CUDA(ctx, cudaGetLastError());
+  return MDPP_OK;
+}
+
+extern "C" int mdpp_render_continuous(mdpp_ctx* ctx,
+                                      const mdpp_image_continuous_config* cfg,
+                                      const void* states, uint8_t* out,
+                                      int64_t n_images, void* cuda_stream) {
+  if (!ctx) return MDPP_EINVAL;
+  if (!cfg || !states || !out || n_images < 1)
+    return fail(ctx, MDPP_EINVAL, "render_continuous: bad arguments");
+  if (cfg->n_sub_images < 1 || cfg->n_sub_images > 2 ||
+      cfg->stamp_rows > MDPP_MAX_STAMP_ROWS || cfg->n_rects > MDPP_MAX_TERM_BOXES)
+    return fail(ctx, MDPP_EINVAL, "render_continuous: bad configuration");
+  if (n_images * cfg->n_sub_images > 0x7fffffffLL)
+    return fail(ctx, MDPP_EINVAL, "render_continuous: too many images per call");
+  MDPP_CUDA(ctx, cudaSetDevice(ctx->device));
+  RenderCParams p;
+  p.cfg = *cfg;
+  p.states = states;
+  p.out = out;
+  const unsigned grid = (unsigned)(n_images * cfg->n_sub_images);
+  if (cfg->is_f64)
+    render_continuous_kernel<double><<<grid, kRBlock, 0, (cudaStream_t)cuda_stream>>>(p);
+  else
+    render_continuous_kernel<float><<<grid, kRBlock, 0, (cudaStream_t)cuda_stream>>>(p);
+  MDPP_CUDA(ctx, cudaGetLastError());
+  return MDPP_OK;
+}

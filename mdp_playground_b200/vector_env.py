@@ -76,6 +76,8 @@ class VectorRLToyEnv:
             self._init_discrete()
         else:
             self._init_continuous()
+        if self.spec.image_representations:
+            self._init_images()
         # rl_toy_env.py:831-833: the constructor ends with reset(seed=env seed)
         self.curr_obs, _ = self.reset(seed=self.seed_dict["env"],
                                       options={"_ctor": True})
@@ -260,20 +262,165 @@ class VectorRLToyEnv:
         self._check(self._lib.mdpp_discrete_reset(
             self._ctx, C.byref(self._state), _ptr(mask), _ptr(init),
             _ptr(reset_u), _ptr(obs), C.byref(opts), self._stream()))
-        self.curr_obs = self._observe(obs)
+        self.curr_obs = self._observe(obs, options.get("image_params"), reset=True,
+                                      ctor=bool(options.get("_ctor")))
         return self.curr_obs, {}
 
-    def _observe(self, state):
+    def _observe(self, state, image_params=None, reset=False, ctor=False):
         """Underlying state -> observation (identity, dtype_o cast, or the
         image renderer when image_representations is on)."""
         if self.spec.image_representations:
-            return self.render_observation(state)
+            return self.render_observation(state, image_params=image_params,
+                                           reset=reset, allow_philox=ctor)
         if self.spec.kind == "continuous":
             return state
         return self._cast_obs(state)
 
-    def render_observation(self, state):
-        return state  # replaced by the CUDA renderers (render.py)
+    # ------------------------------------------------------------------
+    # image observations
+    # ------------------------------------------------------------------
+    def _init_images(self):
+        from . import image_tables as it
+        sp, dev = self.spec, self.device
+        W, H = sp.image_width, sp.image_height
+        self._img_keep = []
+
+        def up(a, dtype):
+            t = torch.as_tensor(np.ascontiguousarray(a)).to(dtype).to(dev).contiguous()
+            self._img_keep.append(t)
+            return _ptr(t)
+        if sp.kind == "discrete":
+            tb = it.build_discrete_image_tables(
+                self.tables.n_states, W, H, sp.image_transforms,
+                sp.image_sh_quant, sp.image_ro_quant, sp.image_scale_range)
+            self.image_tables = tb
+            c = _lib.ImageDiscreteTables()
+            c.width, c.height, c.n_states = W, H, tb.n_states
+            c.r_min, c.n_radii = tb.r_min, tb.n_radii
+            c.n_xvar, c.n_yvar = tb.n_xvar, tb.n_yvar
+            c.has_scale, c.has_shift = int(tb.has_scale), int(tb.has_shift)
+            c.has_rotate, c.has_flip = int(tb.has_rotate), int(tb.has_flip)
+            c.sh_quant, c.ro_quant = tb.sh_quant, tb.ro_quant
+            c.mask_bits = up(tb.mask_bits.view(np.int64), torch.int64)
+            c.mask_index = up(tb.mask_index, torch.int32)
+            c.xvar, c.yvar = up(tb.xvar, torch.uint8), up(tb.yvar, torch.uint8)
+            c.rot_coeff = up(tb.rot_coeff, torch.int32)
+            c.r_thresholds = up(tb.r_thresholds if len(tb.r_thresholds)
+                                else np.zeros(1), torch.float64)
+            self._img_cfg = c
+            self.obs_shape = (W, H, 1)
+            if self.noise == "numpy":
+                s = self.seed_dict.get("image_representations")
+                self._rng_I = [np_random(None if s is None else s + i)[0]
+                               for i in range(self.num_envs)]
+        else:
+            D = sp.state_space_dim
+            assert np.isfinite(sp.state_space_max), \
+                "image observations need a bounded state space"
+            rel = [0, 1]  # ImageContinuous default; the env does not pass its own
+            irr = sorted(set(range(D)) - set(rel))
+            if D < 2 or len(irr) not in (0, 2):
+                raise NotImplementedError(
+                    "continuous image observations: 2 relevant (+ 0 or 2 "
+                    "irrelevant) dimensions")
+            dt = self._np_real
+            lo = np.full((D,), -sp.state_space_max).astype(dt)[rel]
+            hi = np.full((D,), sp.state_space_max).astype(dt)[rel]
+
+            def to_pixel(vec):  # image_continuous.py:248-277
+                frac = (np.asarray(vec) - lo) / (hi - lo)
+                return (frac * (W, H)).astype(int)
+            c = _lib.ImageContinuousConfig()
+            c.width, c.height, c.dim = W, H, D
+            c.n_sub_images = 2 if irr else 1
+            for k in range(2):
+                c.rel_index[k] = rel[k]
+                c.irr_index[k] = irr[k] if irr else 0
+                c.feat_low[k], c.feat_high[k] = float(lo[k]), float(hi[k])
+            c.is_f64 = int(self._real == torch.float64)
+            c.n_rects = len(self._term_lows)
+            for b, (tl_, th_) in enumerate(zip(self._term_lows, self._term_highs)):
+                p0, p1 = to_pixel(tl_), to_pixel(th_)
+                c.rect[b][0], c.rect[b][1] = int(p0[0]), int(p0[1])
+                c.rect[b][2], c.rect[b][3] = int(p1[0]), int(p1[1])
+            c.has_target = 1
+            tp = to_pixel(np.asarray(sp.target_point, dtype=dt))
+            c.target_pixel[0], c.target_pixel[1] = int(tp[0]), int(tp[1])
+            spans = it.disc_stamp(5)  # circle_radius=5 (rl_toy_env.py:774)
+            c.stamp_rows, c.stamp_radius = len(spans), 5
+            for r, (x0, wdt) in enumerate(spans):
+                c.stamp[r][0], c.stamp[r][1] = int(x0), int(wdt)
+            self._img_cfg = c
+            self.obs_shape = (W * c.n_sub_images, H, 3)
+
+    def _numpy_image_params(self, states_host):
+        """The reference's I-stream draws (image_multi_discrete.py:149-181,
+        :251, :258-259), one image per lane, lane 0 = the reference."""
+        tb, sp = self.image_tables, self.spec
+        W, H = tb.width, tb.height
+        out = np.zeros((self.num_envs, 5), dtype=np.int32)
+        for i in range(self.num_envs):
+            rng = self._rng_I[i]
+            R, sw, sh, rot, flip = 20, int(W / 2), int(H / 2), -1, 0
+            if tb.has_scale:
+                lo, hi = sp.image_scale_range
+                mx, mn = np.log(hi * 20), np.log(lo * 20)
+                R = int(np.exp(mn + rng.random() * (mx - mn)))
+            if tb.has_shift:
+                mw, mh = W / 2 - R, H / 2 - R
+                aw = rng.integers(-mw + 1, mw).item()
+                ah = rng.integers(-mh + 1, mh).item()
+                sw += (aw // tb.sh_quant) * tb.sh_quant
+                sh += (ah // tb.sh_quant) * tb.sh_quant
+            if tb.has_rotate:
+                rot = (rng.integers(360).item() // tb.ro_quant) * tb.ro_quant
+            if tb.has_flip:
+                if rng.integers(2).item() == 0:
+                    flip = 1 if rng.integers(2).item() == 0 else 2
+            out[i] = (R, sw, sh, rot, flip)
+        return out
+
+    def render_observation(self, state, image_params=None, reset=False,
+                           step_index=None, allow_philox=False):
+        """State tensor -> uint8 image observations on the GPU.
+        discrete: int64 [..., N] -> [..., N, W, H, 1]; continuous:
+        real [..., N, D] -> [..., N, k*W, H, 3]."""
+        sp, dev = self.spec, self.device
+        N = self.num_envs
+        if step_index is None:
+            step_index = self._step_index
+        opts = self._opts(1)
+        opts.step_index = step_index
+        if sp.kind == "discrete":
+            st = state.to(torch.int64).contiguous()
+            M = st.numel()
+            lead = tuple(st.shape)
+            if self.noise == "numpy" and image_params is None:
+                assert M == N, "noise='numpy' renders one step at a time"
+                image_params = self._numpy_image_params(None)
+            if image_params is not None:
+                image_params = torch.as_tensor(image_params, device=dev).to(
+                    torch.int32).reshape(M, 5).contiguous()
+            elif self.noise == "replay" and not allow_philox and (
+                    self.image_tables.has_scale or self.image_tables.has_shift
+                    or self.image_tables.has_rotate or self.image_tables.has_flip):
+                raise ValueError("replay mode: pass image_params [N, 5]")
+            out = torch.empty(lead + self.obs_shape, dtype=torch.uint8, device=dev)
+            self.last_image_params = torch.empty((M, 5), dtype=torch.int32,
+                                                 device=dev)
+            self._check(self._lib.mdpp_render_discrete(
+                self._ctx, C.byref(self._img_cfg), _ptr(st), _ptr(image_params),
+                _ptr(self.last_image_params), _ptr(out), M, N,
+                6 if reset else 3, C.byref(opts), self._stream()))
+            return out
+        st = state.to(self._real).contiguous()
+        M = st.numel() // sp.state_space_dim
+        lead = tuple(st.shape[:-1])
+        out = torch.empty(lead + self.obs_shape, dtype=torch.uint8, device=dev)
+        self._check(self._lib.mdpp_render_continuous(
+            self._ctx, C.byref(self._img_cfg), _ptr(st), _ptr(out), M,
+            self._stream()))
+        return out
 
     def _cast_obs(self, obs):
         dt = np.dtype(self.spec.dtype_o)
@@ -297,7 +444,8 @@ class VectorRLToyEnv:
                                torch.as_tensor(v).shape))
                             for k, v in replay.items()})
         state = out["obs"][0]
-        obs = self._observe(state)
+        obs = self._observe(
+            state, None if replay is None else replay.get("image_params"))
         self.curr_obs = obs
         return (obs, out["reward"][0], out["terminated"][0],
                 out["truncated"][0],
@@ -508,7 +656,8 @@ class VectorRLToyEnv:
         self._check(self._lib.mdpp_continuous_reset(
             self._ctx, C.byref(self._state), _ptr(mask), _ptr(init), _ptr(obs),
             C.byref(opts), self._stream()))
-        self.curr_obs = self._observe(obs)
+        self.curr_obs = self._observe(obs, options.get("image_params"), reset=True,
+                                      ctor=bool(options.get("_ctor")))
         return self.curr_obs, {}
 
     def _rollout_continuous(self, n_steps, actions, replay, out, want_final_obs):
