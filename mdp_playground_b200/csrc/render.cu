@@ -40,12 +40,13 @@ __device__ __forceinline__ int floor_div(int a, int b) {
 
 __global__ void __launch_bounds__(kRBlock)
 render_discrete_kernel(const __grid_constant__ RenderDParams p) {
-  __shared__ uint64_t mask[kMaskRows];
+  __shared__ uint64_t mask[kMaskRows];   // column bitmaps of the polygon
   __shared__ int prm[8];
   const int64_t m = blockIdx.x;
   const mdpp_image_discrete_tables& tb = p.tb;
   const int W = tb.width, H = tb.height;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {  // warp 0 decides the transform parameters
+    const int lane = threadIdx.x;
     int state = (int)p.states[m];
     state = min(max(state, 0), tb.n_states - 1);
     int R, sw, sh, rot, flip;
@@ -60,9 +61,13 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
       U4 w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32), p.stream,
                            p.k0, p.k1);
       R = tb.r_min;
-      if (tb.has_scale) {
+      if (tb.has_scale) {  // R = r_min + #{thresholds <= u}, one lane each
         const double u = uniform32(w.x);
-        for (int k = 0; k < tb.n_radii - 1; ++k) R += tb.r_thresholds[k] <= u;
+        for (int base = 0; base < tb.n_radii - 1; base += 32) {
+          const int k = base + lane;
+          const bool le = k < tb.n_radii - 1 && tb.r_thresholds[k] <= u;
+          R += __popc(__ballot_sync(0xffffffffu, le));
+        }
       }
       sw = W / 2; sh = H / 2;
       if (tb.has_shift) {  // integers(-m + 1, m), m = W/2 - R, then quantise
@@ -78,10 +83,13 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
       flip = 0;
       if (tb.has_flip && (w.w & 1u) == 0) flip = (w.w & 2u) == 0 ? 1 : 2;
     }
-    prm[0] = state; prm[1] = R; prm[2] = sw; prm[3] = sh; prm[4] = rot; prm[5] = flip;
-    if (p.params_out) {
-      int32_t* q = p.params_out + m * 5;
-      q[0] = R; q[1] = sw; q[2] = sh; q[3] = rot; q[4] = flip;
+    if (lane == 0) {
+      prm[0] = state; prm[1] = R; prm[2] = sw; prm[3] = sh; prm[4] = rot;
+      prm[5] = flip;
+      if (p.params_out) {
+        int32_t* q = p.params_out + m * 5;
+        q[0] = R; q[1] = sw; q[2] = sh; q[3] = rot; q[4] = flip;
+      }
     }
   }
   __syncthreads();
@@ -114,48 +122,93 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
   const int bx0 = (int)floorf(cx) - R - 3, bx1 = (int)ceilf(cx) + R + 3;
   const int by0 = (int)floorf(cy) - R - 3, by1 = (int)ceilf(cy) + R + 3;
   __syncthreads();
+  // 4 mask bits -> 4 bytes of 0 / 255: bit k of b lands on bit 8k of
+  // b * (1 + 2^7 + 2^14 + 2^21); the isolated 0/1 bytes times 255 fill up
+  auto expand4 = [](uint32_t b) -> uint32_t {
+    return (((b & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+  };
 
-  auto pixel = [&](int x, int y) -> uint32_t {
+  // Unrotated images: 16 consecutive output bytes = 16 consecutive y at one x
+  // = 16 consecutive bits of one column bitmap (reversed under a top-bottom
+  // flip).  n pixels of column x starting at y, as a bit string (bit j = y+j).
+  auto column_bits = [&](int x, int y, int n) -> uint32_t {
+    const int fx = flip == 1 ? W - 1 - x : x;
+    const int mx = fx - sw + kMaskCentre;
+    if ((unsigned)mx >= (unsigned)kMaskRows) return 0u;
+    uint64_t col = mask[mx];
+    int start;  // mask bit of pixel y, ascending with y after the optional flip
+    if (flip == 2) {
+      col = __brevll(col);                       // bit k <- bit 63-k
+      start = 63 - ((H - 1 - y) - sh + kMaskCentre);
+    } else {
+      start = y - sh + kMaskCentre;
+    }
+    uint64_t v;
+    if (start >= 64 || start <= -64) v = 0;
+    else v = start >= 0 ? col >> start : col << (-start);
+    return (uint32_t)v & ((1u << n) - 1u);
+  };
+  auto pixel = [&](int x, int y) -> uint32_t {  // rotated images: one gather
     int fx = x, fy = y;
     if (flip == 1) fx = W - 1 - x;
     if (flip == 2) fy = H - 1 - y;
-    int rx = fx, ry = fy;
-    if (rot >= 0) {
-      rx = (a2 + a1 * fy + a0 * fx) >> 16;
-      ry = (a5 + a4 * fy + a3 * fx) >> 16;
-      if ((unsigned)rx >= (unsigned)W || (unsigned)ry >= (unsigned)H) return 0u;
-    }
+    const int rx = (a2 + a1 * fy + a0 * fx) >> 16;
+    const int ry = (a5 + a4 * fy + a3 * fx) >> 16;
+    if ((unsigned)rx >= (unsigned)W || (unsigned)ry >= (unsigned)H) return 0u;
     const int mx = rx - sw + kMaskCentre, my = ry - sh + kMaskCentre;
-    if ((unsigned)mx >= 64u || (unsigned)my >= (unsigned)kMaskRows) return 0u;
-    return ((mask[my] >> mx) & 1ull) ? 255u : 0u;
+    if ((unsigned)mx >= (unsigned)kMaskRows || (unsigned)my >= 64u) return 0u;
+    return (uint32_t)((mask[mx] >> my) & 1ull);
   };
 
   const int total = W * H;
   uint8_t* out = p.out + m * (int64_t)total;
-  const bool aligned = (total % 16) == 0;  // every image starts 16-B aligned
-  if (aligned) {
+  if (total % 16 == 0) {  // every image starts 16-byte aligned
     uint4* out4 = reinterpret_cast<uint4*>(out);
-    for (int i = threadIdx.x; i < total / 16; i += kRBlock) {
-      const int idx = i * 16;
-      const int x0 = idx / H, y0 = idx - x0 * H;
-      uint32_t w[4] = {0u, 0u, 0u, 0u};
-      const bool one_col = y0 + 15 < H;
-      const bool skip = one_col
-          ? (x0 < bx0 || x0 > bx1 || y0 > by1 || y0 + 15 < by0)
-          : (x0 + 1 < bx0 || x0 > bx1);
-      if (!skip) {
+    // phase 1: the image is mostly background -- stream zeros everywhere
+    for (int i = threadIdx.x; i < total / 16; i += kRBlock)
+      __stcs(out4 + i, make_uint4(0u, 0u, 0u, 0u));
+    // phase 2: recompute only the 16-byte chunks that meet the shape's
+    // bounding box (after the barrier, so these stores land last)
+    const int cx0 = max(bx0, 0), cx1 = min(bx1, W - 1);
+    const int cy0 = max(by0, 0), cy1 = min(by1, H - 1);
+    __syncthreads();
+    if (cx0 > cx1 || cy0 > cy1) return;
+    // chunks a column span can touch, rounded up to a power of two so the
+    // (column, k) decomposition of a work item is a shift and a mask
+    const int per_col = ((cy1 - cy0) >> 4) + 2;
+    // (for the cheap unrotated items; the rotated ones cost 16 gathers each,
+    // there an exact division wastes fewer lanes)
+    const int lg = per_col <= 4 ? 2 : per_col <= 8 ? 3 : per_col <= 16 ? 4 : 5;
+    const int n_work = rot < 0 ? (cx1 - cx0 + 1) << lg : (cx1 - cx0 + 1) * per_col;
+    for (int wi = threadIdx.x; wi < n_work; wi += kRBlock) {
+      const int q = rot < 0 ? wi >> lg : wi / per_col;
+      const int col = cx0 + q, k = rot < 0 ? wi & ((1 << lg) - 1) : wi - q * per_col;
+      const int chunk = ((col * H + cy0) >> 4) + k;
+      if (chunk > ((col * H + cy1) >> 4)) continue;
+      const int idx0 = chunk * 16;
+      const int x0 = idx0 >= col * H ? col : col - 1;
+      const int y0 = idx0 - x0 * H;
+      const int n0 = min(16, H - y0);  // pixels of the chunk in column x0
+      uint32_t bits = 0;
+      if (rot < 0) {
+        bits = column_bits(x0, y0, n0);
+        if (n0 < 16 && x0 + 1 < W) bits |= column_bits(x0 + 1, 0, 16 - n0) << n0;
+      } else {
         int x = x0, y = y0;
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
-          w[b >> 2] |= pixel(x, y) << ((b & 3) * 8);
+          bits |= pixel(x, y) << b;
           if (++y == H) { y = 0; ++x; }
         }
       }
-      __stcs(out4 + i, make_uint4(w[0], w[1], w[2], w[3]));
+      __stcs(out4 + chunk, make_uint4(expand4(bits), expand4(bits >> 4),
+                                      expand4(bits >> 8), expand4(bits >> 12)));
     }
   } else {
-    for (int idx = threadIdx.x; idx < total; idx += kRBlock)
-      out[idx] = (uint8_t)pixel(idx / H, idx % H);
+    for (int idx = threadIdx.x; idx < total; idx += kRBlock) {
+      const int x = idx / H, y = idx % H;
+      out[idx] = (rot < 0 ? column_bits(x, y, 1) : pixel(x, y)) ? 255 : 0;
+    }
   }
 }
 

@@ -111,7 +111,7 @@ class DiscreteImageTables:
     has_flip: bool
     sh_quant: int
     ro_quant: int
-    mask_bits: np.ndarray      # uint64 [n_masks][MASK_ROWS]
+    mask_bits: np.ndarray      # uint64 [n_masks][MASK_ROWS], column bitmaps
     mask_index: np.ndarray     # int32 [S][n_radii][n_xvar][n_yvar]
     xvar: np.ndarray           # uint8 [S][n_radii][W]   variant of shift_w
     yvar: np.ndarray           # uint8 [S][n_radii][H]   variant of shift_h
@@ -134,12 +134,15 @@ def _polygon_mask(dx, dy):
     pts = [(MASK_CENTRE + x, MASK_CENTRE + y) for x, y in zip(dx, dy)]
     ImageDraw.Draw(img).polygon(pts, fill=255)
     arr = np.array(img) > 0            # [y][x]
+    # column-major bitmaps: word x holds the column, bit y is pixel (x, y).
+    # The observation is the transposed image (obs[x][y] = pil[y][x]), so 16
+    # consecutive output bytes are 16 consecutive bits of one word.
     bits = np.zeros(MASK_ROWS, dtype=np.uint64)
-    for y in range(MASK_ROWS):
+    for x in range(MASK_ROWS):
         v = 0
-        for x in np.nonzero(arr[y])[0]:
-            v |= 1 << int(x)
-        bits[y] = v
+        for y in np.nonzero(arr[:, x])[0]:
+            v |= 1 << int(y)
+        bits[x] = v
     return bits
 
 

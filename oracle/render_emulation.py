@@ -33,8 +33,8 @@ def render_discrete(tb, state, R, shift_w, shift_h, rotation, flip):
     mx = rx - shift_w + it.MASK_CENTRE
     my = ry - shift_h + it.MASK_CENTRE
     inside = valid & (mx >= 0) & (mx < it.MASK_ROWS) & (my >= 0) & (my < it.MASK_ROWS)
-    rows = mask[np.clip(my, 0, it.MASK_ROWS - 1)]
-    bit = (rows >> np.clip(mx, 0, 63).astype(np.uint64)) & np.uint64(1)
+    cols = mask[np.clip(mx, 0, it.MASK_ROWS - 1)]   # column-major bitmaps
+    bit = (cols >> np.clip(my, 0, 63).astype(np.uint64)) & np.uint64(1)
     pil = np.where(inside & (bit == 1), 255, 0).astype(np.uint8)  # [y][x]
     return pil.T.copy()
 
