@@ -107,6 +107,10 @@ typedef struct mdpp_discrete_group {
   const double* reward_matrix;   /* [S*A] when custom_reward, else NULL      */
   int64_t env_begin;             /* first env (local index) of the group     */
   int64_t env_count;
+  int64_t global_id_base;        /* Philox id of the group's first env, added
+                                    to opts->env_id_offset: keeps the noise of
+                                    an env independent of how groups / envs
+                                    are sharded over GPUs                    */
 } mdpp_discrete_group;
 
 #ifndef __CUDACC_RTC__ /* NVRTC sees the types only */

@@ -42,6 +42,7 @@ class DiscreteGroup(C.Structure):
         ("sequences", C.c_void_p), ("sequence_rewards", C.c_void_p),
         ("reward_matrix", C.c_void_p),
         ("env_begin", C.c_int64), ("env_count", C.c_int64),
+        ("global_id_base", C.c_int64),
     ]
 
 

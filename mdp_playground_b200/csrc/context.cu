@@ -137,6 +137,7 @@ extern "C" int mdpp_set_discrete_groups(mdpp_ctx* ctx,
     // rl_toy_env.py:2107-2109: reward += term_state_reward * reward_scale
     d.term_reward_scaled = in.term_state_reward * in.reward_scale;
     d.env_begin = in.env_begin;
+    d.gid_base = in.global_id_base;
     d.env_count = in.env_count;
     if (in.delay > ctx->max_delay) ctx->max_delay = in.delay;
 

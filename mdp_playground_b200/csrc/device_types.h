@@ -24,6 +24,7 @@ struct DiscreteGroupDev {
   int32_t blob_bytes;
   int64_t blob_offset;  // of this group's blob inside the context blob buffer
   int64_t env_begin, env_count;
+  int64_t gid_base;  // global Philox id of the group's first env
 };
 
 struct CtaMapEntry {

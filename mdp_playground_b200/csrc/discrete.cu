@@ -25,7 +25,7 @@ discrete_reset_kernel(const __grid_constant__ ResetParams p) {
     if (p.obs) p.obs[env] = p.st.cur_state[env];
     return;
   }
-  const uint32_t gid = (uint32_t)(p.env_id_offset + env);
+  const uint32_t gid = (uint32_t)(p.env_id_offset + g.gid_base + local);
   const uint32_t ep = p.st.episode[env];
   int32_t s0;
   if (p.init_states) {

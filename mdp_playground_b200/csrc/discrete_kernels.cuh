@@ -413,7 +413,8 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
   const bool active = local < grp.env_count;
   const int64_t env = grp.env_begin + (active ? local : 0);
   const int64_t N = n_envs_of(p);
-  const uint32_t gid = (uint32_t)(p.env_id_offset + env);
+  const DiscreteGroupDev& gsel = C::SINGLE ? p.group0 : grp;
+  const uint32_t gid = (uint32_t)(p.env_id_offset + gsel.gid_base + (active ? local : 0));
 
   EnvRegs e;
   e.s = p.st.cur_state[env];

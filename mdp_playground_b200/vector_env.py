@@ -35,7 +35,13 @@ class VectorRLToyEnv:
 
     def __init__(self, num_envs, device=None, noise="philox", autoreset=False,
                  horizon=0, env_id_offset=0, philox_seed=None,
-                 normal_precision="fp64", track_history=None, **config):
+                 normal_precision="fp64", track_history=None,
+                 config_groups=None, group_sizes=None, shard=(0, 1), **config):
+        """config_groups: optional list of config dicts (a heterogeneous
+        sweep: each entry is merged over **config); envs are laid out
+        group-major, `group_sizes` per group (default: as equal as possible).
+        shard=(rank, world): this object holds rank's share of a job that
+        runs the same groups on `world` GPUs (global Philox ids follow)."""
         if not torch.cuda.is_available():
             raise RuntimeError(
                 "VectorRLToyEnv needs a CUDA device: the step path is CUDA "
@@ -60,7 +66,25 @@ class VectorRLToyEnv:
         # store per step; on by default for gym-style (non-autoreset) use
         self.track_history = (not self.autoreset) if track_history is None \
             else bool(track_history)
-        self.spec = parse_config(config)
+        self._shard = (int(shard[0]), int(shard[1]))
+        if config_groups:
+            cfgs = [dict(copy.deepcopy(config), **copy.deepcopy(c))
+                    for c in config_groups]
+            self._group_specs = [parse_config(c) for c in cfgs]
+            kinds = {s_.kind for s_ in self._group_specs}
+            if kinds != {"discrete"}:
+                raise NotImplementedError("config_groups: discrete envs only")
+            G = len(cfgs)
+            if group_sizes is None:
+                group_sizes = [self.num_envs // G + (1 if g < self.num_envs % G else 0)
+                               for g in range(G)]
+            assert len(group_sizes) == G and sum(group_sizes) == self.num_envs
+            self._group_sizes = [int(x) for x in group_sizes]
+            self.spec = self._group_specs[0]
+        else:
+            self.spec = parse_config(config)
+            self._group_specs = [self.spec]
+            self._group_sizes = [self.num_envs]
         self.config = self.spec.config
         self.seed_dict = self.spec.seed_dict
         if philox_seed is None:
@@ -117,8 +141,16 @@ class VectorRLToyEnv:
     # discrete backend
     # ------------------------------------------------------------------
     def _init_discrete(self):
+        """One configuration group per entry of self._group_specs (a single
+        one for the plain drop-in use).  Envs are laid out group-major: group
+        g owns the contiguous range group_slices[g]."""
         sp = self.spec
-        self.tables = tb = build_discrete_tables(sp)
+        N, dev = self.num_envs, self.device
+        specs = self._group_specs
+        G = len(specs)
+        sizes = self._group_sizes
+        self.group_tables = [build_discrete_tables(s_) for s_ in specs]
+        self.tables = tb = self.group_tables[0]
         self.transition_matrix = tb.transition
         self.rewardable_sequences = tb.rewardable_sequences
         self.reward_matrix = tb.reward_matrix
@@ -126,37 +158,53 @@ class VectorRLToyEnv:
             tb.n_states, seed=self.seed_dict.get("relevant_state_space"))
         self.action_space = DiscreteSpace(
             tb.n_actions, seed=self.seed_dict.get("relevant_action_space"))
-        self.has_pnoise = bool(sp.transition_noise)
-        self.has_rnoise = sp.has_reward_noise
-        N, dev = self.num_envs, self.device
-        g = _lib.DiscreteGroup()
-        g.n_states, g.n_actions = tb.n_states, tb.n_actions
-        g.sequence_length, g.delay = sp.sequence_length, sp.delay
-        g.reward_every_n_steps = sp.reward_every_n_steps
-        g.custom_reward = int(sp.use_custom_mdp)
-        g.n_sequences = int(tb.sequences.shape[0])
-        g.has_transition_noise = int(self.has_pnoise)
-        g.has_reward_noise = int(self.has_rnoise)
-        g.transition_noise = sp.transition_noise
-        g.reward_noise_std = sp.reward_noise_std
-        g.reward_scale, g.reward_shift = sp.reward_scale, sp.reward_shift
-        g.term_state_reward = sp.term_state_reward
-        keep = [tb.transition, tb.terminal_mask, tb.init_cdf, tb.noise_cdf,
-                tb.sequences, tb.sequence_rewards, tb.reward_matrix]
-        hp = [None if a is None else a.ctypes.data_as(C.c_void_p) for a in keep]
-        (g.transition, g.terminal, g.init_cdf, g.noise_cdf, g.sequences,
-         g.sequence_rewards, g.reward_matrix) = hp
-        g.env_begin, g.env_count = 0, N
-        self._check(self._lib.mdpp_set_discrete_groups(self._ctx, C.byref(g), 1))
-        self.n_groups = 1
+        self.has_pnoise = any(bool(s_.transition_noise) for s_ in specs)
+        self.has_rnoise = any(s_.has_reward_noise for s_ in specs)
+        rank, world = self._shard
+        groups = (_lib.DiscreteGroup * G)()
+        self._host_keep = []
+        begin, gbegin = 0, 0
+        self.group_slices = []
+        for gi, (s_, t_) in enumerate(zip(specs, self.group_tables)):
+            g = groups[gi]
+            g.n_states, g.n_actions = t_.n_states, t_.n_actions
+            g.sequence_length, g.delay = s_.sequence_length, s_.delay
+            g.reward_every_n_steps = s_.reward_every_n_steps
+            g.custom_reward = int(s_.use_custom_mdp)
+            g.n_sequences = int(t_.sequences.shape[0])
+            g.has_transition_noise = int(bool(s_.transition_noise))
+            g.has_reward_noise = int(s_.has_reward_noise)
+            g.transition_noise = s_.transition_noise
+            g.reward_noise_std = s_.reward_noise_std
+            g.reward_scale, g.reward_shift = s_.reward_scale, s_.reward_shift
+            g.term_state_reward = s_.term_state_reward
+            keep = [t_.transition, t_.terminal_mask, t_.init_cdf, t_.noise_cdf,
+                    t_.sequences, t_.sequence_rewards, t_.reward_matrix]
+            self._host_keep.append(keep)
+            hp = [None if a is None else a.ctypes.data_as(C.c_void_p)
+                  for a in keep]
+            (g.transition, g.terminal, g.init_cdf, g.noise_cdf, g.sequences,
+             g.sequence_rewards, g.reward_matrix) = hp
+            g.env_begin, g.env_count = begin, sizes[gi]
+            # global Philox ids: all ranks' envs of group g are contiguous
+            g.global_id_base = gbegin + rank * sizes[gi]
+            self.group_slices.append(slice(begin, begin + sizes[gi]))
+            begin += sizes[gi]
+            gbegin += world * sizes[gi]
+        assert begin == N
+        self._check(self._lib.mdpp_set_discrete_groups(self._ctx, groups, G))
+        self.n_groups = G
+        max_delay = max(s_.delay for s_ in specs)
 
         self._cur = torch.zeros(N, dtype=torch.int32, device=dev)
         self._key = torch.zeros(N, dtype=torch.int64, device=dev)
         self._t = torch.zeros(N, dtype=torch.int32, device=dev)
         self._episode = torch.zeros(N, dtype=torch.int32, device=dev)
-        self._ring = torch.zeros((max(sp.delay, 1), N), dtype=torch.float64,
-                                 device=dev) if sp.delay > 0 else None
+        self._ring = torch.zeros((max_delay, N), dtype=torch.float64,
+                                 device=dev) if max_delay > 0 else None
         self._hist_depth = sp.sequence_length + sp.delay + 1
+        if G > 1:
+            self.track_history = False  # augmented_state differs per group
         self._history = torch.zeros((self._hist_depth, N), dtype=torch.int32,
                                     device=dev) if self.track_history else None
         self._stats = torch.zeros((self.n_groups, _lib.MDPP_N_STATS),
@@ -166,12 +214,13 @@ class VectorRLToyEnv:
         st.cur_state, st.seq_key = _ptr(self._cur), _ptr(self._key)
         st.t_episode, st.episode = _ptr(self._t), _ptr(self._episode)
         st.ring = _ptr(self._ring)
-        st.ring_depth = sp.delay
+        st.ring_depth = max_delay
         st.history_depth = self._hist_depth
         st.history = _ptr(self._history)
         st.stats = _ptr(self._stats)
         self._state = st
         if self.noise == "numpy":
+            assert G == 1, "noise='numpy' is a single-configuration mode"
             self._init_numpy_streams()
 
     def _init_numpy_streams(self):

@@ -1,0 +1,100 @@
+"""GPU tests of heterogeneous config groups (BASELINE config #5 shape) and of
+the shard-aware global env ids: a multi-group launch equals the per-group
+single-config envs, and a job split over 2 shards equals the unsplit job."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from tests import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+def make_env(*a, **k):
+    from mdp_playground_b200 import VectorRLToyEnv
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return VectorRLToyEnv(*a, **k)
+
+
+NAMES = ["c1_seq1", "c2_every1", "big50", "custom_8x5", "diam3_seq4",
+         "seq2_denser", "notmax_diam2"]
+SIZES = [300, 500, 200, 100, 257, 64, 131]
+
+
+def groups():
+    return [gu.case_config(n) for n in NAMES]
+
+
+def test_multi_group_launch_equals_single_group_envs():
+    N, T = sum(SIZES), 40
+    het = make_env(N, autoreset=True, horizon=9, philox_seed=5,
+                   config_groups=groups(), group_sizes=SIZES)
+    out = het.rollout(T, want_final_obs=True)
+    assert not het.jit_last_used
+    begin = 0
+    for cfg, n, sl in zip(groups(), SIZES, het.group_slices):
+        one = make_env(n, autoreset=True, horizon=9, philox_seed=5,
+                       env_id_offset=begin, **cfg)
+        ref = one.rollout(T, want_final_obs=True)
+        for k in ref:
+            assert torch.equal(out[k][:, sl], ref[k]), (k, begin)
+        begin += n
+    st = het.episode_stats()
+    assert st["transitions"].tolist() == [n * T for n in SIZES]
+    assert st["episodes"].sum() == int((out["terminated"] | out["truncated"]).sum())
+
+
+def test_two_shards_equal_the_unsplit_job():
+    T = 25
+    half = [s // 2 for s in SIZES]
+    full = [2 * h for h in half]
+    whole = make_env(sum(full), autoreset=True, horizon=7, philox_seed=3,
+                     config_groups=groups(), group_sizes=full)
+    r0 = make_env(sum(half), autoreset=True, horizon=7, philox_seed=3,
+                  config_groups=groups(), group_sizes=half, shard=(0, 2))
+    r1 = make_env(sum(half), autoreset=True, horizon=7, philox_seed=3,
+                  config_groups=groups(), group_sizes=half, shard=(1, 2))
+    ow, o0, o1 = whole.rollout(T), r0.rollout(T), r1.rollout(T)
+    for k in ow:
+        for sw, s0 in zip(whole.group_slices, r0.group_slices):
+            want = ow[k][:, sw]
+            got = torch.cat([o0[k][:, s0], o1[k][:, s0]], dim=1)
+            assert torch.equal(want, got), k
+    s = whole.episode_stats()
+    a, b = r0.episode_stats(), r1.episode_stats()
+    for k in ("episodes", "transitions", "noisy_transitions", "terminated"):
+        assert np.array_equal(s[k], a[k] + b[k]), k
+    np.testing.assert_allclose(s["reward"], a["reward"] + b["reward"], rtol=1e-12)
+
+
+def test_sweep_grid_smoke_1000_groups():
+    """The C5 grid: delay x seq_len x P-noise x R-noise x make_denser."""
+    base = gu.case_config("c1_seq1")
+    cfgs = []
+    for d in (0, 1, 2, 4, 8):
+        for L in (1, 2, 3, 4):
+            for pn in (0, 0.01, 0.02, 0.1, 0.25):
+                for rn in (0, 1, 5, 10, 25):
+                    for md in (False, True):
+                        cfgs.append(dict(base, delay=d, sequence_length=L,
+                                         transition_noise=pn, reward_noise=rn,
+                                         make_denser=md,
+                                         reward_every_n_steps=True))
+    assert len(cfgs) == 1000
+    N = 64 * 1000
+    env = make_env(N, autoreset=True, horizon=100, config_groups=cfgs)
+    out = env.rollout(50, want_final_obs=False)
+    st = env.episode_stats()
+    assert np.all(st["transitions"] == 64 * 50)
+    # noise-free groups draw nothing, noisy ones do
+    pn = np.array([c["transition_noise"] for c in cfgs])
+    assert np.all(st["noisy_transitions"][pn == 0] == 0)
+    assert np.all(st["noisy_transitions"][pn == 0.25] > 0)
+    rn = np.array([c["reward_noise"] for c in cfgs])
+    assert np.all(st["abs_reward_noise"][rn == 0] == 0)
+    ratio = st["abs_reward_noise"][rn == 25].mean() / st["abs_reward_noise"][rn == 5].mean()
+    assert abs(ratio - 5) < 0.3
+    assert int(out["obs"].max()) < 8
