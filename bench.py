@@ -129,45 +129,53 @@ def run_reference_arm(args):
 # clocks
 # --------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,"
-              "clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML,
+    every 2 ms; nvidia-smi polling is too coarse for a 20-50 ms region)."""
+    HW_SLOWDOWN, SW_POWER_CAP = 0x8, 0x4
+    HW_THERMAL, SW_THERMAL = 0x40, 0x20
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons = index, [], 0
+        self.stop_flag, self.thread, self.max_mhz = False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(
+                self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.reasons |= nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index),
-                 "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        if self.nv is None:
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
+        if self.thread is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        self.stop_flag = True
         self.thread.join(timeout=2)
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0][0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                 "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names)
-                   if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1][0].isdigit()]
+        sm = sorted(self.sm)
+        names = [(self.HW_SLOWDOWN, "hw_slowdown"),
+                 (self.HW_THERMAL, "hw_thermal_slowdown"),
+                 (self.SW_THERMAL, "sw_thermal_slowdown"),
+                 (self.SW_POWER_CAP, "sw_power_cap")]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "sm_max_mhz": self.max_mhz,
+                "reasons": [n for bit, n in names if self.reasons & bit],
                 "samples": len(sm)}
 
 
@@ -178,6 +186,125 @@ def measured_peak_gbs():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(n_envs, n_steps, jit):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant
+    kernel, from the committed `ncu --set full` capture (profiles/), when the
+    launch shape matches the captured one; else null."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)
+        k = t["mdpp_jit_rollout" if jit else "discrete_rollout_kernel"]
+        if k["envs"] == n_envs and k["steps_per_launch"] == n_steps:
+            return k["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
+def _time_launches(torch, fn, n, barrier, max_over_ranks):
+    for _ in range(3):
+        fn()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1)) / n
+
+
+def other_configs(torch, Env, dev, rank, world, barrier, max_over_ranks, peak):
+    """The other BASELINE.json shapes, device-resident, one line each:
+    env-steps/s (all ranks) and fraction of the HBM roofline with the
+    algorithmic bytes of SURVEY.md 8d."""
+    import numpy as np
+    res = {}
+    base = dict(seed=0, state_space_type="discrete", action_space_type="discrete",
+                state_space_size=8, action_space_size=8, reward_density=0.25,
+                terminal_state_density=0.25)
+
+    def line(name, n_envs, steps_per_launch, ms, bytes_per_step, note):
+        sps = world * n_envs * steps_per_launch / (ms * 1e-3)
+        res[name] = {"value": sps, "unit": UNIT, "envs_per_gpu": n_envs,
+                     "env_steps_per_launch": steps_per_launch,
+                     "ms_per_launch": ms,
+                     "algorithmic_bytes_per_env_step": bytes_per_step,
+                     "roofline_frac": sps / world * bytes_per_step / 1e9 / peak,
+                     "what": note}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # C1: seq 1, delay 0, no noise
+        N, T = 65536, 1000
+        env = Env(N, device=dev, autoreset=True, horizon=100,
+                  env_id_offset=rank * N, sequence_length=1, delay=0, **base)
+        acts = torch.randint(0, 8, (T, N), dtype=torch.int32, device=dev)
+        out = env.rollout(T, actions=acts, want_final_obs=False)
+        ms = _time_launches(torch, lambda: env.rollout(T, actions=acts, out=out),
+                            10, barrier, max_over_ranks)
+        line("C1_discrete_seq1_rollout", N, T, ms, 22,
+             "fused rollout, noise off")
+        del env, acts, out
+        # C3: continuous move_to_a_point, 1M envs
+        N, T = 1 << 20, 100
+        c3 = dict(seed=0, state_space_type="continuous", state_space_dim=6,
+                  relevant_indices=[0, 1], irrelevant_features=True,
+                  transition_dynamics_order=2, inertia=1.0, time_unit=0.5,
+                  target_radius=0.05, target_point=[0.0, 0.0],
+                  state_space_max=10.0, action_space_max=1.0)
+        env = Env(N, device=dev, autoreset=True, horizon=100,
+                  env_id_offset=rank * N, **c3)
+        acts = torch.rand((T, N, 6), device=dev) * 2 - 1
+        out = env.rollout(T, actions=acts, want_final_obs=False)
+        ms = _time_launches(torch, lambda: env.rollout(T, actions=acts, out=out),
+                            5, barrier, max_over_ranks)
+        line("C3_continuous_rollout", N, T, ms, 54, "fused rollout, fp32")
+        a1, o1 = acts[:1], {k: v[:1] for k, v in out.items()}
+        ms = _time_launches(torch, lambda: env.rollout(1, actions=a1, out=o1),
+                            50, barrier, max_over_ranks)
+        line("C3_continuous_single_step", N, 1, ms, 256,
+             "gym-style step(): one launch per step")
+        del env, acts, out
+        # C4: 100x100 image observations, 16384 envs
+        N = 16384
+        for tr, extra in (("shift", dict(image_sh_quant=4)),
+                          ("shift,scale,rotate", dict(image_sh_quant=1,
+                                                      image_ro_quant=1,
+                                                      image_scale_range=(0.5, 1.5)))):
+            env = Env(N, device=dev, autoreset=True, horizon=100,
+                      env_id_offset=rank * N, sequence_length=1, delay=0,
+                      image_representations=True, image_transforms=tr,
+                      image_width=100, image_height=100, **extra, **base)
+            a = torch.randint(0, 8, (N,), dtype=torch.int32, device=dev)
+            ms = _time_launches(torch, lambda: env.step(a), 30, barrier,
+                                max_over_ranks)
+            line(f"C4_image_step[{tr}]", N, 1, ms, 10034,
+                 "step() + render, two launches per step")
+            del env
+        # C5: 1000-cell heterogeneous grid, 1M envs per GPU
+        cfgs = [dict(base, delay=d, sequence_length=L, transition_noise=pn,
+                     reward_noise=rn, make_denser=md, reward_every_n_steps=True)
+                for d in (0, 1, 2, 4, 8) for L in (1, 2, 3, 4)
+                for pn in (0, 0.01, 0.02, 0.1, 0.25) for rn in (0, 1, 5, 10, 25)
+                for md in (False, True)]
+        N, T = 1 << 20, 100
+        env = Env(N, device=dev, autoreset=True, horizon=100, config_groups=cfgs,
+                  shard=(rank, world), normal_precision="fast")
+        acts = torch.randint(0, 8, (T, N), dtype=torch.int32, device=dev)
+        out = env.rollout(T, actions=acts, want_final_obs=False)
+        ms = _time_launches(torch, lambda: env.rollout(T, actions=acts, out=out),
+                            5, barrier, max_over_ranks)
+        line("C5_heterogeneous_1000_groups_rollout", N, T, ms, 22,
+             "fused rollout, ahead-of-time multi-group kernel")
+        s5 = env.episode_stats(reduce=True)
+        res["C5_heterogeneous_1000_groups_rollout"]["stats_allreduce"] = {
+            "groups": len(cfgs),
+            "episode_len_mean_min_max": [float(np.min(s5["episode_len_mean"])),
+                                         float(np.max(s5["episode_len_mean"]))]}
+    return res
 
 
 def run_gpu_arm(args):
@@ -269,13 +396,9 @@ def run_gpu_arm(args):
     h_act.copy_(actions.cpu())
     h_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory()
              for k, v in out.items()}
-    d_act = torch.empty_like(actions)
 
-    def e2e_step():
-        d_act.copy_(h_act, non_blocking=True)
-        env.rollout(T, actions=d_act, out=out)
-        for k in out:
-            h_out[k].copy_(out[k], non_blocking=True)
+    def e2e_step():  # public host-buffer API: pipelined H2D / kernel / D2H
+        env.rollout_host(T, h_act, h_out, chunk_steps=50)
 
     e2e_steps = max(1, min(args.steps, 5))
     e2e_step()
@@ -289,6 +412,17 @@ def run_gpu_arm(args):
     e2e_value = world * N * T * e2e_steps / (e2e_ms * 1e-3)
     h2d = T * N * 4
     d2h = T * N * (8 + 8 + 1 + 1)
+
+    # ---- end-of-run episode statistics: ONE all-reduce (NCCL) -------------
+    summ = env.episode_stats(reduce=True)
+    stats = {"episodes": float(summ["episodes"][0]),
+             "transitions": float(summ["transitions"][0]),
+             "episode_reward_mean": float(summ["episode_reward_mean"][0]),
+             "episode_len_mean": float(summ["episode_len_mean"][0]),
+             "noisy_transition_frac": float(summ["noisy_transitions"][0]
+                                            / max(summ["transitions"][0], 1))}
+    others = None if args.no_other_configs else other_configs(
+        torch, VectorRLToyEnv, dev, rank, world, barrier, max_over_ranks, peak)
 
     if rank == 0:
         # ---- CPU baseline: scalar port, one core, bounded sample ----------
@@ -319,7 +453,8 @@ def run_gpu_arm(args):
                        "> 126 MB L2 (no flush needed)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": ncu_traffic(N, T, env.jit_last_used),
+                         "peak_source": peak_src,
                          "kernel": "mdpp_jit_rollout" if env.jit_last_used
                          else "discrete_rollout_kernel<PHILOX,smem>",
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_ROLLOUT,
@@ -333,6 +468,8 @@ def run_gpu_arm(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": args.steps,
             "clocks": clocks,
+            "episode_stats_allreduced": stats,
+            "other_configs": others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -352,6 +489,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=300000)
     ap.add_argument("--ref-sample", type=int, default=100000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the extra BASELINE.json shapes (C1/C3/C4/C5)")
     ap.add_argument("--normal", default="fast", choices=["fast", "fp64"],
                     help="reward-noise normals: SFU fp32 Box-Muller or fp64")
     ap.add_argument("--no-jit", action="store_true",

@@ -1,0 +1,61 @@
+"""Multi-GPU layout of a batch of independent environments.
+
+Environments never exchange data on the step path, so a job on `world` GPUs
+is `world` independent VectorRLToyEnv objects (one process per GPU).  What
+must agree between them is (a) the global environment ids that key the Philox
+streams -- so results do not depend on the number of GPUs -- and (b) the
+end-of-run episode statistics, combined with ONE all-reduce (NCCL on GPUs,
+gloo in the CPU tests) of the [n_groups, 8] counter matrix.
+"""
+import numpy as np
+import torch
+
+STAT_NAMES = ("episodes", "transitions", "reward", "noisy_transitions",
+              "abs_reward_noise", "abs_transition_noise", "reserved",
+              "terminated")
+
+
+def even_group_sizes(num_envs, n_groups):
+    """Local envs per group, as equal as possible (first groups get +1)."""
+    return [num_envs // n_groups + (1 if g < num_envs % n_groups else 0)
+            for g in range(n_groups)]
+
+
+def group_id_bases(group_sizes, rank, world):
+    """Global Philox id of each group's first LOCAL env: every group's envs
+    are contiguous over ranks, groups follow each other."""
+    bases, gbegin = [], 0
+    for n in group_sizes:
+        bases.append(gbegin + rank * n)
+        gbegin += world * n
+    return bases
+
+
+def local_slices(group_sizes):
+    out, begin = [], 0
+    for n in group_sizes:
+        out.append(slice(begin, begin + n))
+        begin += n
+    return out
+
+
+def reduce_stats(stats):
+    """Sum the [n_groups, 8] counters over all ranks of the default process
+    group (no-op without torch.distributed)."""
+    import torch.distributed as dist
+    stats = stats.clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    return stats
+
+
+def summarize_stats(stats):
+    """The quantities Ray logs per config (config_processor.py:351-373):
+    episode_reward_mean / episode_len_mean, from the summed counters."""
+    s = stats.detach().cpu().numpy() if isinstance(stats, torch.Tensor) \
+        else np.asarray(stats)
+    out = {name: s[:, i].copy() for i, name in enumerate(STAT_NAMES)}
+    ep = np.maximum(out["episodes"], 1)
+    out["episode_reward_mean"] = out["reward"] / ep
+    out["episode_len_mean"] = out["transitions"] / ep
+    return out

@@ -76,8 +76,8 @@ class VectorRLToyEnv:
                 raise NotImplementedError("config_groups: discrete envs only")
             G = len(cfgs)
             if group_sizes is None:
-                group_sizes = [self.num_envs // G + (1 if g < self.num_envs % G else 0)
-                               for g in range(G)]
+                from .sharding import even_group_sizes
+                group_sizes = even_group_sizes(self.num_envs, G)
             assert len(group_sizes) == G and sum(group_sizes) == self.num_envs
             self._group_sizes = [int(x) for x in group_sizes]
             self.spec = self._group_specs[0]
@@ -160,10 +160,12 @@ class VectorRLToyEnv:
             tb.n_actions, seed=self.seed_dict.get("relevant_action_space"))
         self.has_pnoise = any(bool(s_.transition_noise) for s_ in specs)
         self.has_rnoise = any(s_.has_reward_noise for s_ in specs)
+        from .sharding import group_id_bases
         rank, world = self._shard
+        id_bases = group_id_bases(sizes, rank, world)
         groups = (_lib.DiscreteGroup * G)()
         self._host_keep = []
-        begin, gbegin = 0, 0
+        begin = 0
         self.group_slices = []
         for gi, (s_, t_) in enumerate(zip(specs, self.group_tables)):
             g = groups[gi]
@@ -187,10 +189,9 @@ class VectorRLToyEnv:
              g.sequence_rewards, g.reward_matrix) = hp
             g.env_begin, g.env_count = begin, sizes[gi]
             # global Philox ids: all ranks' envs of group g are contiguous
-            g.global_id_base = gbegin + rank * sizes[gi]
+            g.global_id_base = id_bases[gi]
             self.group_slices.append(slice(begin, begin + sizes[gi]))
             begin += sizes[gi]
-            gbegin += world * sizes[gi]
         assert begin == N
         self._check(self._lib.mdpp_set_discrete_groups(self._ctx, groups, G))
         self.n_groups = G
@@ -552,6 +553,61 @@ class VectorRLToyEnv:
         self._step_index += T
         return out
 
+    def rollout_host(self, n_steps, actions_host, out_host, chunk_steps=100):
+        """rollout() for HOST buffers: `actions_host` [T, N(, D)] and the
+        tensors of `out_host` (obs / reward / terminated / truncated, [T, N...])
+        are pinned CPU tensors.  The T steps are cut into chunks whose
+        host->device copy, kernel and device->host copy run on three streams
+        with double-buffered device staging, so PCIe (both directions) and the
+        GPU overlap.  Results are complete once the current stream is
+        synchronised."""
+        T, N = int(n_steps), self.num_envs
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_h2d_stream"):
+            self._h2d_stream = torch.cuda.Stream(dev)
+            self._d2h_stream = torch.cuda.Stream(dev)
+            self._stage = {}
+        chunk = max(1, min(int(chunk_steps), T))
+        key = (chunk,) + tuple(actions_host.shape[1:]) + (actions_host.dtype,)
+        if self._stage.get("key") != key:
+            acts = [torch.empty((chunk,) + tuple(actions_host.shape[1:]),
+                                dtype=actions_host.dtype, device=dev)
+                    for _ in range(2)]
+            outs = [{k: torch.empty((chunk,) + tuple(v.shape[1:]), dtype=v.dtype,
+                                    device=dev) for k, v in out_host.items()}
+                    for _ in range(2)]
+            self._stage = {"key": key, "acts": acts, "outs": outs}
+        acts, outs = self._stage["acts"], self._stage["outs"]
+        ev_in, ev_comp, ev_out = {}, {}, {}
+        self._h2d_stream.wait_stream(cur)
+        self._d2h_stream.wait_stream(cur)
+        n_chunks = (T + chunk - 1) // chunk
+        for c in range(n_chunks):
+            t0, t1 = c * chunk, min(T, (c + 1) * chunk)
+            n, b = t1 - t0, c % 2
+            with torch.cuda.stream(self._h2d_stream):
+                if c >= 2:  # staging buffer b is free once chunk c-2 has run
+                    self._h2d_stream.wait_event(ev_comp[c - 2])
+                acts[b][:n].copy_(actions_host[t0:t1], non_blocking=True)
+                ev_in[c] = torch.cuda.Event()
+                ev_in[c].record(self._h2d_stream)
+            cur.wait_event(ev_in[c])
+            if c >= 2:  # output staging b is free once chunk c-2 is on the host
+                cur.wait_event(ev_out[c - 2])
+            self.rollout(n, actions=acts[b][:n],
+                         out={k: v[:n] for k, v in outs[b].items()})
+            ev_comp[c] = torch.cuda.Event()
+            ev_comp[c].record(cur)
+            with torch.cuda.stream(self._d2h_stream):
+                self._d2h_stream.wait_event(ev_comp[c])
+                for k, v in out_host.items():
+                    v[t0:t1].copy_(outs[b][k][:n], non_blocking=True)
+                ev_out[c] = torch.cuda.Event()
+                ev_out[c].record(self._d2h_stream)
+        cur.wait_stream(self._d2h_stream)
+        return out_host
+
     def _draw_numpy(self, T):
         assert not self.autoreset, \
             "noise='numpy' needs explicit resets (draw order is host-driven)"
@@ -798,10 +854,7 @@ class VectorRLToyEnv:
     def episode_stats(self, reduce=False):
         """Per-group counters of rl_toy_env.py:2360-2369 summed over envs and
         episodes; `reduce=True` all-reduces over torch.distributed ranks."""
-        stats = self._stats.clone()
-        if reduce:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
-                dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-        host = stats.cpu().numpy()
-        return {name: host[:, i].copy() for i, name in enumerate(_lib.STAT_NAMES)}
+        from . import sharding
+        stats = sharding.reduce_stats(self._stats) if reduce \
+            else self._stats.clone()
+        return sharding.summarize_stats(stats)
