@@ -358,9 +358,9 @@ def run_gpu_arm(args):
     for _ in range(args.warmup):
         env.rollout(T, actions=actions, out=out)
     sampler = ClockSampler(local_rank)
+    barrier()
     if rank == 0:
         sampler.start()
-    barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
