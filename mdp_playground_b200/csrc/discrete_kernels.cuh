@@ -25,7 +25,11 @@
 namespace mdpp {
 
 constexpr int kBlock = 64;
+#ifdef MDPP_JIT_CHUNK  // tuning override of the NVRTC build
+constexpr int kChunk = MDPP_JIT_CHUNK;
+#else
 constexpr int kChunk = 8;
+#endif
 // 65 536 envs / 148 SMs = 443 threads per SM: all of them must be resident at
 // once (one wave), so cap registers at 65 536 / 512 = 128 per thread.  Small
 // CTAs (64 threads) keep the per-SM load within one CTA of the average
@@ -232,37 +236,39 @@ struct Cfg {
   static constexpr int CDF_LOG2 = CDF_LOG2_;
 };
 
+// ---- phase A: loads and state-independent random draws -------------------
+// Everything a chunk of U steps needs that does not depend on the env state:
+// the actions, the transition uniforms, the (sigma-scaled) reward normals and
+// the candidate initial states of a possible auto-reset.  `n_valid` < U only
+// on the last chunk of a launch (guards the action / replay loads).
 template <typename C, int U>
-__device__ __forceinline__ void run_chunk(const RolloutParams& p,
-                                          const GroupView& v, EnvRegs& e,
-                                          double* ring_smem, int64_t env,
-                                          uint32_t gid, int t0) {
+__device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView& v,
+                                        int64_t env, uint32_t gid, int t0,
+                                        int n_valid, int32_t* act, double* u_tr,
+                                        double* n_rw, int32_t* s0) {
   constexpr int NOISE = C::NOISE;
   constexpr int NORMAL = C::NORMAL;
-  constexpr bool RING_SMEM = C::RING_SMEM;
   constexpr bool FAST = C::FAST;
   const int64_t N = n_envs_of(p);
   const bool autoreset = autoreset_of(p);
-  const int horizon = horizon_of(p);
-  int32_t act[U], s0[U];
-  double u_tr[U], n_rw[U], u_rs[U];
+  double u_rs[U];
   const int64_t off0 = (int64_t)t0 * N + env;
   const uint64_t step0 = p.step_index + (uint64_t)t0;
   const bool have_actions = FAST || p.io.actions != nullptr;
-  // ---- phase A: loads and state-independent random draws -----------------
 #pragma unroll
   for (int j = 0; j < U; ++j) {
     const int64_t off = off0 + (int64_t)j * N;
     const uint64_t step = step0 + (uint64_t)j;
+    act[j] = 0;
     if (have_actions) {
-      act[j] = ld_stream_i32(p.io.actions + off);
+      if (j < n_valid) act[j] = ld_stream_i32(p.io.actions + off);
     } else {
       U4 w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
                            STREAM_ACTION, p.k0, p.k1);
       act[j] = (int32_t)__umulhi(w.x, (uint32_t)v.A);
     }
-    u_tr[j] = 0.0; n_rw[j] = 0.0; u_rs[j] = 0.0;
-    if (NOISE == MDPP_NOISE_REPLAY) {
+    u_tr[j] = 0.0; n_rw[j] = 0.0; u_rs[j] = 0.0; s0[j] = 0;
+    if (NOISE == MDPP_NOISE_REPLAY && j < n_valid) {
       if (v.has_pnoise) u_tr[j] = ld_stream_f64(p.io.replay_transition_u + off);
       if (v.has_rnoise) n_rw[j] = ld_stream_f64(p.io.replay_reward_noise + off);
       if (autoreset) u_rs[j] = ld_stream_f64(p.io.replay_reset_u + off);
@@ -285,7 +291,7 @@ __device__ __forceinline__ void run_chunk(const RolloutParams& p,
       double z = q == 0 ? z4[0] : q == 1 ? z4[1] : q == 2 ? z4[2] : z4[3];
       w_rs[0] = q == 0 ? r4[0] : q == 1 ? r4[1] : q == 2 ? r4[2] : r4[3];
       n_rw[0] = __dmul_rn(v.r_std, z);
-    } else {  // chunks start on a multiple-of-4 step (see the caller)
+    } else {  // chunks start on a multiple-of-4 step (see the callers)
 #pragma unroll
       for (int j = 0; j + 3 < U; j += 4) {
         double z4[4] = {0, 0, 0, 0};
@@ -312,16 +318,32 @@ __device__ __forceinline__ void run_chunk(const RolloutParams& p,
       }
     }
   }
-  // ---- phase B: the state-dependent chain --------------------------------
+}
+
+// ---- phase B: the state-dependent chain -----------------------------------
+template <typename C, int U, bool PARTIAL>
+__device__ __forceinline__ void phase_b(const RolloutParams& p, const GroupView& v,
+                                        EnvRegs& e, double* ring_smem, int ring_stride,
+                                        int64_t env, int t0, int n_valid,
+                                        const int32_t* act, const double* u_tr,
+                                        const double* n_rw, const int32_t* s0) {
+  constexpr int NOISE = C::NOISE;
+  constexpr bool RING_SMEM = C::RING_SMEM;
+  constexpr bool FAST = C::FAST;
+  const int64_t N = n_envs_of(p);
+  const bool autoreset = autoreset_of(p);
+  const int horizon = horizon_of(p);
+  const int64_t off0 = (int64_t)t0 * N + env;
 #pragma unroll
   for (int j = 0; j < U; ++j) {
+    if (PARTIAL && j >= n_valid) break;
     const int64_t off = off0 + (int64_t)j * N;
     uint32_t a = (uint32_t)act[j];
     if (a >= (uint32_t)v.A) a = (uint32_t)v.A - 1;  // memory safety only
     int32_t nxt = v.P[e.s * v.A + (int32_t)a];
     if (NOISE != MDPP_NOISE_OFF && v.has_pnoise) {
-      int32_t noisy = cdf_search<C::CDF_LOG2>(v.noise_cdf + nxt * v.cdf_stride, v.cdf_log2,
-                                 v.S, u_tr[j]);
+      int32_t noisy = cdf_search<C::CDF_LOG2>(v.noise_cdf + nxt * v.cdf_stride,
+                                              v.cdf_log2, v.S, u_tr[j]);
       e.n_noisy += (noisy != nxt);
       nxt = noisy;
     }
@@ -336,7 +358,7 @@ __device__ __forceinline__ void run_chunk(const RolloutParams& p,
     }
     if (v.delay > 0) {  // FIFO of depth d: pay out what was earned d steps ago
       double* slot = RING_SMEM
-          ? ring_smem + e.ring_pos * kBlock
+          ? ring_smem + e.ring_pos * ring_stride
           : p.st.ring + (int64_t)e.ring_pos * N + env;
       double delayed = (e.tl > v.delay) ? *slot : 0.0;
       *slot = r;
@@ -374,7 +396,18 @@ __device__ __forceinline__ void run_chunk(const RolloutParams& p,
     if (FAST || p.io.terminated) st_stream(p.io.terminated + off, (uint8_t)done);
     if (FAST || p.io.truncated) st_stream(p.io.truncated + off, (uint8_t)trunc);
   }
-  e.n_steps += U;
+  e.n_steps += PARTIAL ? n_valid : U;
+}
+
+template <typename C, int U>
+__device__ __forceinline__ void run_chunk(const RolloutParams& p,
+                                          const GroupView& v, EnvRegs& e,
+                                          double* ring_smem, int64_t env,
+                                          uint32_t gid, int t0) {
+  int32_t act[U], s0[U];
+  double u_tr[U], n_rw[U];
+  phase_a<C, U>(p, v, env, gid, t0, U, act, u_tr, n_rw, s0);
+  phase_b<C, U, false>(p, v, e, ring_smem, kBlock, env, t0, U, act, u_tr, n_rw, s0);
 }
 
 __device__ __forceinline__ double warp_sum(double x) {

@@ -302,9 +302,11 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
   const int cdf_tpl = g.cdf_log2 <= 6 ? g.cdf_log2 : -1;
   std::vector<std::string> defs =
       defines_for(g, p, noise_mode, normal_mode, fast, true, cdf_tpl);
+  p.ring_smem_bytes = ring_bytes;
+  if (const char* ch = std::getenv("MDPP_JIT_CHUNK"))  // tuning knob (4/8/16)
+    defs.push_back(std::string("-DMDPP_JIT_CHUNK=") + ch);
   void* fn = get_function(ctx, kEntrySource, "mdpp_jit_rollout", defs);
   if (!fn) return 0;
-  p.ring_smem_bytes = ring_bytes;
   return launch(ctx, fn, (unsigned)ctx->n_ctas, kBlock, ring_bytes + g.blob_bytes,
                 stream, &p);
 }
@@ -368,11 +370,11 @@ extern "C" int mdpp_jit_selftest(char* log, int log_bytes) {
     rc = 0;
     for (int which = 0; which < 2 && rc == 0; ++which) {
       nvrtcProgram prog = nullptr;
-      Create(&prog, which ? kContinuousEntrySource : kEntrySource,
+      Create(&prog, which == 1 ? kContinuousEntrySource : kEntrySource,
              "mdpp_jit_entry.cu", kNumHeaders, kHeaderSources, kHeaderNames);
       std::vector<std::string> opts = {"--gpu-architecture=sm_100a",
                                        "-std=c++17", "-lineinfo"};
-      auto& dd = which ? cdefs : defs;
+      auto& dd = which == 1 ? cdefs : defs;
       opts.insert(opts.end(), dd.begin(), dd.end());
       std::vector<const char*> copts;
       for (auto& o : opts) copts.push_back(o.c_str());
