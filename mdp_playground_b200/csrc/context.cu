@@ -1,5 +1,6 @@
 // Context lifetime, error reporting and host-side packing of the discrete
 // tables into the device blob (LUT / open-addressing hash of sequence keys).
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -175,6 +176,23 @@ extern "C" int mdpp_set_discrete_groups(mdpp_ctx* ctx,
       for (int r = 0; r < S; ++r)
         put_row(reinterpret_cast<double*>(gb.data() + d.off_noise_cdf) + (size_t)r * Sp,
                 in.noise_cdf + (size_t)r * S);
+    }
+    // Integer form of the noise cdf for the Philox mode: u = (w + 0.5) 2^-32,
+    // so cdf <= u  <=>  w >= ceil(cdf 2^32 - 0.5).  cdf * 2^32 and the - 0.5 are
+    // exact in fp64 (cdf < 2, 53-bit mantissa), hence the integer compare
+    // decides exactly like the fp64 one.  Saturated thresholds (cdf ~ 1 and
+    // the sentinels) can only pass at w = 2^32 - 1, where the search result is
+    // clamped to S-1 -- which is also the exact answer there.
+    if (in.has_transition_noise) {
+      d.off_noise_thr = reserve(S * Sp * 4, 16);
+      uint32_t* thr = reinterpret_cast<uint32_t*>(gb.data() + d.off_noise_thr);
+      for (int r = 0; r < S; ++r)
+        for (int k = 0; k < Sp; ++k) {
+          const double c = k < S ? in.noise_cdf[(size_t)r * S + k] : 2.0;
+          const double t = std::ceil(c * 4294967296.0 - 0.5);
+          thr[(size_t)r * Sp + k] = t <= 0.0 ? 0u : t >= 4294967295.0 ? 0xFFFFFFFFu
+                                                                       : (uint32_t)t;
+        }
     }
     // Guide table of the auto-reset draw: bucket b = top 12 bits of the 32-bit
     // Philox word w (u = (w + 0.5) 2^-32).  If every w of the bucket maps to

@@ -20,7 +20,7 @@ struct DiscreteGroupDev {
   // byte offsets inside the blob
   int32_t off_P, off_term, off_init_cdf, off_noise_cdf;
   int32_t off_lut, off_hash_keys, off_hash_vals, off_values, off_R, off_guide;
-  int32_t pad1;
+  int32_t off_noise_thr;  // u32 [S][2^cdf_log2] integer thresholds of noise_cdf
   int32_t blob_bytes;
   int64_t blob_offset;  // of this group's blob inside the context blob buffer
   int64_t env_begin, env_count;

@@ -100,6 +100,23 @@ __device__ __forceinline__ int cdf_search(const double* cdf, int log2n, int n,
   return min(pos, n - 1);
 }
 
+// The same search over integer thresholds: number of entries <= w.
+template <int LOG2>
+__device__ __forceinline__ int thr_search(const uint32_t* thr, int log2n, int n,
+                                          uint32_t w) {
+  int pos = 0;
+  if (LOG2 >= 0) {
+#pragma unroll
+    for (int b = LOG2 - 1; b >= 0; --b)
+      if (thr[pos + (1 << b) - 1] <= w) pos += 1 << b;
+  } else {
+#pragma unroll 1
+    for (int step = (1 << log2n) >> 1; step > 0; step >>= 1)
+      if (thr[pos + step - 1] <= w) pos += step;
+  }
+  return min(pos, n - 1);
+}
+
 struct GroupView {  // per-thread copy of the scalars + table pointers
   int S, A, L, delay, every_n, lookup_kind, key_bits, hash_shift;
   int cdf_log2, cdf_stride;
@@ -112,6 +129,7 @@ struct GroupView {  // per-thread copy of the scalars + table pointers
   const uint8_t* term;
   const double* init_cdf;
   const double* noise_cdf;
+  const uint32_t* noise_thr;
   const double* lut;
   const uint64_t* hash_keys;
   const uint32_t* hash_vals;
@@ -136,6 +154,7 @@ __device__ __forceinline__ GroupView make_view(const DiscreteGroupDev& g,
   v.term = tab + g.off_term;
   v.init_cdf = reinterpret_cast<const double*>(tab + g.off_init_cdf);
   v.noise_cdf = reinterpret_cast<const double*>(tab + g.off_noise_cdf);
+  v.noise_thr = reinterpret_cast<const uint32_t*>(tab + g.off_noise_thr);
   v.lut = reinterpret_cast<const double*>(tab + g.off_lut);
   v.hash_keys = reinterpret_cast<const uint64_t*>(tab + g.off_hash_keys);
   v.hash_vals = reinterpret_cast<const uint32_t*>(tab + g.off_hash_vals);
@@ -193,12 +212,11 @@ struct EnvRegs {
 template <int NORMAL>
 __device__ __forceinline__ void philox_quad_draws(
     uint32_t gid, uint64_t quad, uint32_t k0, uint32_t k1, bool want_u,
-    bool want_normal, bool want_reset, double* u_tr, double* z, uint32_t* w_rs) {
+    bool want_normal, bool want_reset, uint32_t* w_tr, double* z, uint32_t* w_rs) {
   const uint32_t q0 = (uint32_t)quad, q1 = (uint32_t)(quad >> 32);
   if (want_u) {
     U4 w = philox4x32_10(gid, q0, q1, STREAM_STEP, k0, k1);
-    u_tr[0] = uniform32(w.x); u_tr[1] = uniform32(w.y);
-    u_tr[2] = uniform32(w.z); u_tr[3] = uniform32(w.w);
+    w_tr[0] = w.x; w_tr[1] = w.y; w_tr[2] = w.z; w_tr[3] = w.w;
   }
   if (want_normal) {
     U4 w = philox4x32_10(gid, q0, q1, STREAM_NORMAL, k0, k1);
@@ -245,7 +263,7 @@ template <typename C, int U>
 __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView& v,
                                         int64_t env, uint32_t gid, int t0,
                                         int n_valid, int32_t* act, double* u_tr,
-                                        double* n_rw, int32_t* s0) {
+                                        uint32_t* w_tr, double* n_rw, int32_t* s0) {
   constexpr int NOISE = C::NOISE;
   constexpr int NORMAL = C::NORMAL;
   constexpr bool FAST = C::FAST;
@@ -267,7 +285,7 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
                            STREAM_ACTION, p.k0, p.k1);
       act[j] = (int32_t)__umulhi(w.x, (uint32_t)v.A);
     }
-    u_tr[j] = 0.0; n_rw[j] = 0.0; u_rs[j] = 0.0; s0[j] = 0;
+    u_tr[j] = 0.0; w_tr[j] = 0u; n_rw[j] = 0.0; u_rs[j] = 0.0; s0[j] = 0;
     if (NOISE == MDPP_NOISE_REPLAY && j < n_valid) {
       if (v.has_pnoise) u_tr[j] = ld_stream_f64(p.io.replay_transition_u + off);
       if (v.has_rnoise) n_rw[j] = ld_stream_f64(p.io.replay_reward_noise + off);
@@ -282,12 +300,12 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
     const bool want_z = NOISE == MDPP_NOISE_PHILOX && v.has_rnoise;
     const bool want_r = autoreset;
     if (U == 1) {
-      double u4[4] = {0, 0, 0, 0}, z4[4] = {0, 0, 0, 0};
-      uint32_t r4[4] = {0, 0, 0, 0};
+      double z4[4] = {0, 0, 0, 0};
+      uint32_t u4[4] = {0, 0, 0, 0}, r4[4] = {0, 0, 0, 0};
       philox_quad_draws<NORMAL>(gid, step0 >> 2, p.k0, p.k1, want_u, want_z,
                                 want_r, u4, z4, r4);
       const int q = (int)(step0 & 3);
-      u_tr[0] = q == 0 ? u4[0] : q == 1 ? u4[1] : q == 2 ? u4[2] : u4[3];
+      w_tr[0] = q == 0 ? u4[0] : q == 1 ? u4[1] : q == 2 ? u4[2] : u4[3];
       double z = q == 0 ? z4[0] : q == 1 ? z4[1] : q == 2 ? z4[2] : z4[3];
       w_rs[0] = q == 0 ? r4[0] : q == 1 ? r4[1] : q == 2 ? r4[2] : r4[3];
       n_rw[0] = __dmul_rn(v.r_std, z);
@@ -296,7 +314,7 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
       for (int j = 0; j + 3 < U; j += 4) {
         double z4[4] = {0, 0, 0, 0};
         philox_quad_draws<NORMAL>(gid, (step0 + j) >> 2, p.k0, p.k1, want_u,
-                                  want_z, want_r, &u_tr[j], z4, &w_rs[j]);
+                                  want_z, want_r, &w_tr[j], z4, &w_rs[j]);
         // numpy: normal(0, sigma) = 0 + sigma * z
 #pragma unroll
         for (int k = 0; k < 4; ++k) n_rw[j + k] = __dmul_rn(v.r_std, z4[k]);
@@ -326,7 +344,8 @@ __device__ __forceinline__ void phase_b(const RolloutParams& p, const GroupView&
                                         EnvRegs& e, double* ring_smem, int ring_stride,
                                         int64_t env, int t0, int n_valid,
                                         const int32_t* act, const double* u_tr,
-                                        const double* n_rw, const int32_t* s0) {
+                                        const uint32_t* w_tr, const double* n_rw,
+                                        const int32_t* s0) {
   constexpr int NOISE = C::NOISE;
   constexpr bool RING_SMEM = C::RING_SMEM;
   constexpr bool FAST = C::FAST;
@@ -342,8 +361,13 @@ __device__ __forceinline__ void phase_b(const RolloutParams& p, const GroupView&
     if (a >= (uint32_t)v.A) a = (uint32_t)v.A - 1;  // memory safety only
     int32_t nxt = v.P[e.s * v.A + (int32_t)a];
     if (NOISE != MDPP_NOISE_OFF && v.has_pnoise) {
-      int32_t noisy = cdf_search<C::CDF_LOG2>(v.noise_cdf + nxt * v.cdf_stride,
-                                              v.cdf_log2, v.S, u_tr[j]);
+      // replay: the recorded fp64 uniform against the fp64 cdf; Philox: the
+      // 32-bit word against the equivalent integer thresholds
+      const int32_t noisy = NOISE == MDPP_NOISE_REPLAY
+          ? cdf_search<C::CDF_LOG2>(v.noise_cdf + nxt * v.cdf_stride, v.cdf_log2,
+                                    v.S, u_tr[j])
+          : thr_search<C::CDF_LOG2>(v.noise_thr + nxt * v.cdf_stride, v.cdf_log2,
+                                    v.S, w_tr[j]);
       e.n_noisy += (noisy != nxt);
       nxt = noisy;
     }
@@ -405,9 +429,11 @@ __device__ __forceinline__ void run_chunk(const RolloutParams& p,
                                           double* ring_smem, int64_t env,
                                           uint32_t gid, int t0) {
   int32_t act[U], s0[U];
+  uint32_t w_tr[U];
   double u_tr[U], n_rw[U];
-  phase_a<C, U>(p, v, env, gid, t0, U, act, u_tr, n_rw, s0);
-  phase_b<C, U, false>(p, v, e, ring_smem, kBlock, env, t0, U, act, u_tr, n_rw, s0);
+  phase_a<C, U>(p, v, env, gid, t0, U, act, u_tr, w_tr, n_rw, s0);
+  phase_b<C, U, false>(p, v, e, ring_smem, kBlock, env, t0, U, act, u_tr, w_tr,
+                       n_rw, s0);
 }
 
 __device__ __forceinline__ double warp_sum(double x) {
