@@ -51,6 +51,7 @@ struct RolloutParams {
   int32_t T, autoreset, horizon;
   int32_t ring_smem_bytes;
   uint32_t k0, k1;
+  uint32_t rk[20];  // Philox round keys expanded from (k0, k1) by the host
   uint64_t step_index;
   int64_t env_id_offset;
 };

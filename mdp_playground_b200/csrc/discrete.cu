@@ -127,6 +127,7 @@ extern "C" int mdpp_discrete_rollout(mdpp_ctx* ctx,
   p.horizon = opts->horizon;
   p.k0 = (uint32_t)opts->seed;
   p.k1 = (uint32_t)(opts->seed >> 32);
+  philox_round_keys(p.k0, p.k1, p.rk);
   p.step_index = opts->step_index;
   p.env_id_offset = opts->env_id_offset;
   cudaStream_t s = (cudaStream_t)cuda_stream;

@@ -211,15 +211,15 @@ struct EnvRegs {
 //                                    step 4q+j
 template <int NORMAL>
 __device__ __forceinline__ void philox_quad_draws(
-    uint32_t gid, uint64_t quad, uint32_t k0, uint32_t k1, bool want_u,
+    uint32_t gid, uint64_t quad, const uint32_t* rk, bool want_u,
     bool want_normal, bool want_reset, uint32_t* w_tr, double* z, uint32_t* w_rs) {
   const uint32_t q0 = (uint32_t)quad, q1 = (uint32_t)(quad >> 32);
   if (want_u) {
-    U4 w = philox4x32_10(gid, q0, q1, STREAM_STEP, k0, k1);
+    U4 w = philox4x32_10_rk(gid, q0, q1, STREAM_STEP, rk);
     w_tr[0] = w.x; w_tr[1] = w.y; w_tr[2] = w.z; w_tr[3] = w.w;
   }
   if (want_normal) {
-    U4 w = philox4x32_10(gid, q0, q1, STREAM_NORMAL, k0, k1);
+    U4 w = philox4x32_10_rk(gid, q0, q1, STREAM_NORMAL, rk);
     if (NORMAL == 0) {
       normal_pair_f64(w.x, w.y, &z[0], &z[1]);
       normal_pair_f64(w.z, w.w, &z[2], &z[3]);
@@ -229,7 +229,7 @@ __device__ __forceinline__ void philox_quad_draws(
     }
   }
   if (want_reset) {
-    U4 w = philox4x32_10(gid, q0, q1, STREAM_AUTORESET, k0, k1);
+    U4 w = philox4x32_10_rk(gid, q0, q1, STREAM_AUTORESET, rk);
     w_rs[0] = w.x; w_rs[1] = w.y; w_rs[2] = w.z; w_rs[3] = w.w;
   }
 }
@@ -302,7 +302,7 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
     if (U == 1) {
       double z4[4] = {0, 0, 0, 0};
       uint32_t u4[4] = {0, 0, 0, 0}, r4[4] = {0, 0, 0, 0};
-      philox_quad_draws<NORMAL>(gid, step0 >> 2, p.k0, p.k1, want_u, want_z,
+      philox_quad_draws<NORMAL>(gid, step0 >> 2, p.rk, want_u, want_z,
                                 want_r, u4, z4, r4);
       const int q = (int)(step0 & 3);
       w_tr[0] = q == 0 ? u4[0] : q == 1 ? u4[1] : q == 2 ? u4[2] : u4[3];
@@ -313,7 +313,7 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
 #pragma unroll
       for (int j = 0; j + 3 < U; j += 4) {
         double z4[4] = {0, 0, 0, 0};
-        philox_quad_draws<NORMAL>(gid, (step0 + j) >> 2, p.k0, p.k1, want_u,
+        philox_quad_draws<NORMAL>(gid, (step0 + j) >> 2, p.rk, want_u,
                                   want_z, want_r, &w_tr[j], z4, &w_rs[j]);
         // numpy: normal(0, sigma) = 0 + sigma * z
 #pragma unroll

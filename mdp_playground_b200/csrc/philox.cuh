@@ -44,6 +44,34 @@ __host__ __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1,
   return U4{c0, c1, c2, c3};
 }
 
+// The 10 round keys depend only on the launch-constant seed: the host expands
+// them once into the kernel parameters (constant bank), so the hot loop spends
+// no instructions on the key schedule.
+__host__ __device__ __forceinline__ void philox_round_keys(uint32_t k0, uint32_t k1,
+                                                           uint32_t* rk) {
+  for (int r = 0; r < 10; ++r) {
+    rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u;
+    rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u;
+  }
+}
+__host__ __device__ __forceinline__ U4 philox4x32_10_rk(uint32_t c0, uint32_t c1,
+                                                        uint32_t c2, uint32_t c3,
+                                                        const uint32_t* rk) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)M0 * c0;
+    uint64_t p1 = (uint64_t)M1 * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk[2 * r];
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+  }
+  return U4{c0, c1, c2, c3};
+}
+
 // 53-bit uniform in [0,1): same construction as numpy's PCG64 double
 // ((x >> 11) * 2^-53) applied to the 64-bit word (hi:lo).
 __host__ __device__ __forceinline__ double uniform53(uint32_t lo, uint32_t hi) {
