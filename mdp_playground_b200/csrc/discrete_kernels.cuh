@@ -161,18 +161,65 @@ __device__ __forceinline__ GroupView make_view(const DiscreteGroupDev& g,
   v.values = reinterpret_cast<const double*>(tab + g.off_values);
   v.R = reinterpret_cast<const double*>(tab + g.off_R);
 #ifdef MDPP_JIT
-  // Runtime-compiled specialisation (jit.cu): every scalar of the (single)
-  // group is a literal, so the compiler folds the branches, unrolls the
-  // searches and drops the dead features.
-  v.S = MDPP_S; v.A = MDPP_A; v.L = MDPP_L; v.delay = MDPP_DELAY;
-  v.every_n = MDPP_EVERY_N; v.lookup_kind = MDPP_LOOKUP;
-  v.key_bits = MDPP_KEY_BITS; v.hash_shift = MDPP_HASH_SHIFT;
-  v.hash_mask = MDPP_HASH_MASK; v.key_mask = MDPP_KEY_MASK;
-  v.has_pnoise = MDPP_PNOISE; v.has_rnoise = MDPP_RNOISE;
+  // Runtime-compiled specialisation (jit.cu): every group scalar that is the
+  // same for all groups of the launch arrives as a literal, so the compiler
+  // folds the branches, unrolls the searches and drops the dead features.
+  // Scalars that differ between groups stay run-time (read from the group
+  // descriptor above).
+#ifdef MDPP_S
+  v.S = MDPP_S;
+#endif
+#ifdef MDPP_A
+  v.A = MDPP_A;
+#endif
+#ifdef MDPP_L
+  v.L = MDPP_L;
+#endif
+#ifdef MDPP_DELAY
+  v.delay = MDPP_DELAY;
+#endif
+#ifdef MDPP_EVERY_N
+  v.every_n = MDPP_EVERY_N;
+#endif
+#ifdef MDPP_LOOKUP
+  v.lookup_kind = MDPP_LOOKUP;
+#endif
+#ifdef MDPP_KEY_BITS
+  v.key_bits = MDPP_KEY_BITS;
+#endif
+#ifdef MDPP_HASH_SHIFT
+  v.hash_shift = MDPP_HASH_SHIFT;
+#endif
+#ifdef MDPP_HASH_MASK
+  v.hash_mask = MDPP_HASH_MASK;
+#endif
+#ifdef MDPP_KEY_MASK
+  v.key_mask = MDPP_KEY_MASK;
+#endif
+#ifdef MDPP_PNOISE
+  v.has_pnoise = MDPP_PNOISE;
+#endif
+#ifdef MDPP_RNOISE
+  v.has_rnoise = MDPP_RNOISE;
+#endif
+#ifdef MDPP_CDF_LOG2
   v.cdf_log2 = MDPP_CDF_LOG2; v.cdf_stride = 1 << MDPP_CDF_LOG2;
+#endif
+#ifdef MDPP_HAS_GUIDE
   v.has_guide = MDPP_HAS_GUIDE;
-  v.r_std = MDPP_R_STD; v.scale = MDPP_SCALE; v.shift = MDPP_SHIFT;
+#endif
+#ifdef MDPP_R_STD
+  v.r_std = MDPP_R_STD;
+#endif
+#ifdef MDPP_SCALE
+  v.scale = MDPP_SCALE;
+#endif
+#ifdef MDPP_SHIFT
+  v.shift = MDPP_SHIFT;
+#endif
+#ifdef MDPP_TERM_REWARD
   v.term_reward_scaled = MDPP_TERM_REWARD;
+#endif
 #endif
   return v;
 }

@@ -92,8 +92,9 @@ std::string hexf(double x) {
   return buf;
 }
 
-// The -D list that makes one specialisation; also its cache key.
-std::vector<std::string> defines_for(const DiscreteGroupDev& g,
+// The -D list that makes one specialisation; also its cache key.  A group
+// scalar becomes a literal only if every group of the launch agrees on it.
+std::vector<std::string> defines_for(const std::vector<DiscreteGroupDev>& groups,
                                      const RolloutParams& p, int noise,
                                      int normal, bool fast, bool ring_smem,
                                      int cdf_log2_tpl) {
@@ -101,32 +102,50 @@ std::vector<std::string> defines_for(const DiscreteGroupDev& g,
     return std::string("-DMDPP_") + k + "=" + v;
   };
   auto I = [](long long v) { return std::to_string(v); };
-  std::vector<std::string> d = {
-      "-DMDPP_JIT",
-      D("S", I(g.S)), D("A", I(g.A)), D("L", I(g.L)), D("DELAY", I(g.delay)),
-      D("EVERY_N", I(g.every_n)), D("LOOKUP", I(g.lookup_kind)),
-      D("KEY_BITS", I(g.key_bits)), D("HASH_SHIFT", I(g.hash_shift)),
-      D("HASH_MASK", I(g.hash_mask) + "u"),
-      D("KEY_MASK", std::to_string((unsigned long long)g.key_mask) + "ull"),
-      D("PNOISE", g.has_pnoise ? "true" : "false"),
-      D("RNOISE", g.has_rnoise ? "true" : "false"),
-      D("CDF_LOG2", I(g.cdf_log2)), D("HAS_GUIDE", g.has_guide ? "true" : "false"),
-      D("R_STD", hexf(g.r_std)), D("SCALE", hexf(g.scale)),
-      D("SHIFT", hexf(g.shift)), D("TERM_REWARD", hexf(g.term_reward_scaled)),
-      D("N_ENVS", I(p.st.n_envs) + "ll"), D("AUTORESET", I(p.autoreset)),
-      D("HORIZON", I(p.horizon)),
-      D("CFG_NOISE", I(noise)), D("CFG_NORMAL", I(normal)),
-      D("CFG_FAST", fast ? "true" : "false"),
-      D("CFG_RING", ring_smem ? "true" : "false"),
-      D("CFG_CDF", I(cdf_log2_tpl)),
-  };
+  const DiscreteGroupDev& g = groups[0];
+  std::vector<std::string> d = {"-DMDPP_JIT"};
+#define UNIFORM(field)                                                    \
+  [&] {                                                                   \
+    for (auto& h : groups)                                                \
+      if (std::memcmp(&h.field, &g.field, sizeof(g.field)) != 0) return false; \
+    return true;                                                          \
+  }()
+  if (UNIFORM(S)) d.push_back(D("S", I(g.S)));
+  if (UNIFORM(A)) d.push_back(D("A", I(g.A)));
+  if (UNIFORM(L)) d.push_back(D("L", I(g.L)));
+  if (UNIFORM(delay)) d.push_back(D("DELAY", I(g.delay)));
+  if (UNIFORM(every_n)) d.push_back(D("EVERY_N", I(g.every_n)));
+  if (UNIFORM(lookup_kind)) d.push_back(D("LOOKUP", I(g.lookup_kind)));
+  if (UNIFORM(key_bits)) d.push_back(D("KEY_BITS", I(g.key_bits)));
+  if (UNIFORM(hash_shift)) d.push_back(D("HASH_SHIFT", I(g.hash_shift)));
+  if (UNIFORM(hash_mask)) d.push_back(D("HASH_MASK", I(g.hash_mask) + "u"));
+  if (UNIFORM(key_mask))
+    d.push_back(D("KEY_MASK", std::to_string((unsigned long long)g.key_mask) + "ull"));
+  if (UNIFORM(has_pnoise)) d.push_back(D("PNOISE", g.has_pnoise ? "true" : "false"));
+  if (UNIFORM(has_rnoise)) d.push_back(D("RNOISE", g.has_rnoise ? "true" : "false"));
+  if (UNIFORM(cdf_log2)) d.push_back(D("CDF_LOG2", I(g.cdf_log2)));
+  if (UNIFORM(has_guide)) d.push_back(D("HAS_GUIDE", g.has_guide ? "true" : "false"));
+  if (UNIFORM(r_std)) d.push_back(D("R_STD", hexf(g.r_std)));
+  if (UNIFORM(scale)) d.push_back(D("SCALE", hexf(g.scale)));
+  if (UNIFORM(shift)) d.push_back(D("SHIFT", hexf(g.shift)));
+  if (UNIFORM(term_reward_scaled)) d.push_back(D("TERM_REWARD", hexf(g.term_reward_scaled)));
+#undef UNIFORM
+  d.push_back(D("N_ENVS", I(p.st.n_envs) + "ll"));
+  d.push_back(D("AUTORESET", I(p.autoreset)));
+  d.push_back(D("HORIZON", I(p.horizon)));
+  d.push_back(D("CFG_NOISE", I(noise)));
+  d.push_back(D("CFG_NORMAL", I(normal)));
+  d.push_back(D("CFG_FAST", fast ? "true" : "false"));
+  d.push_back(D("CFG_RING", ring_smem ? "true" : "false"));
+  d.push_back(D("CFG_CDF", I(cdf_log2_tpl)));
+  d.push_back(D("CFG_SINGLE", groups.size() == 1 ? "true" : "false"));
   return d;
 }
 
 const char* kEntrySource = R"SRC(
 #include "discrete_kernels.cuh"
 using JitCfg = mdpp::Cfg<MDPP_CFG_NOISE, MDPP_CFG_NORMAL, true, MDPP_CFG_RING,
-                         MDPP_CFG_FAST, MDPP_CFG_CDF, true>;
+                         MDPP_CFG_FAST, MDPP_CFG_CDF, MDPP_CFG_SINGLE>;
 extern "C" __global__ void __launch_bounds__(mdpp::kBlock, mdpp::kMinBlocksPerSM)
 mdpp_jit_rollout(const __grid_constant__ mdpp::RolloutParams p) {
   mdpp::rollout_body<JitCfg>(p);
@@ -287,28 +306,29 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
                     int normal_mode, cudaStream_t stream) {
   ctx->jit_last_used = 0;
   if (!ctx->jit_enabled) return 0;
-  if (ctx->d_groups_host.size() != 1) { ctx->jit_log = "multi-group launch"; return 0; }
   if (noise_mode == MDPP_NOISE_REPLAY) { ctx->jit_log = "replay mode"; return 0; }
-  const DiscreteGroupDev& g = ctx->d_groups_host[0];
+  const auto& groups = ctx->d_groups_host;
   constexpr int kRingSmemMaxDelay = 16;
-  const bool ring_ok = g.delay <= kRingSmemMaxDelay;
-  const int ring_bytes = ring_ok ? g.delay * kBlock * 8 : 0;
-  if (!ring_ok || g.blob_bytes + ring_bytes > ctx->max_smem_optin - 1024) {
+  const bool ring_ok = ctx->max_delay <= kRingSmemMaxDelay;
+  const int ring_bytes = ring_ok ? ctx->max_delay * kBlock * 8 : 0;
+  if (!ring_ok || ctx->max_group_blob + ring_bytes > ctx->max_smem_optin - 1024) {
     ctx->jit_log = "tables or delay ring do not fit shared memory";
     return 0;
   }
   const bool fast = p.io.actions && p.io.obs && p.io.reward && p.io.terminated &&
                     p.io.truncated && !p.io.final_obs && !p.st.history;
-  const int cdf_tpl = g.cdf_log2 <= 6 ? g.cdf_log2 : -1;
+  int cdf_tpl = groups[0].cdf_log2 <= 6 ? groups[0].cdf_log2 : -1;
+  for (auto& g : groups)
+    if (g.cdf_log2 != groups[0].cdf_log2) cdf_tpl = -1;
   std::vector<std::string> defs =
-      defines_for(g, p, noise_mode, normal_mode, fast, true, cdf_tpl);
-  p.ring_smem_bytes = ring_bytes;
+      defines_for(groups, p, noise_mode, normal_mode, fast, true, cdf_tpl);
   if (const char* ch = std::getenv("MDPP_JIT_CHUNK"))  // tuning knob (4/8/16)
     defs.push_back(std::string("-DMDPP_JIT_CHUNK=") + ch);
   void* fn = get_function(ctx, kEntrySource, "mdpp_jit_rollout", defs);
   if (!fn) return 0;
-  return launch(ctx, fn, (unsigned)ctx->n_ctas, kBlock, ring_bytes + g.blob_bytes,
-                stream, &p);
+  p.ring_smem_bytes = ring_bytes;
+  return launch(ctx, fn, (unsigned)ctx->n_ctas, kBlock,
+                ring_bytes + ctx->max_group_blob, stream, &p);
 }
 
 void jit_release(mdpp_ctx* ctx) {
@@ -335,8 +355,9 @@ extern "C" int mdpp_jit_selftest(char* log, int log_bytes) {
   RolloutParams p;
   std::memset(&p, 0, sizeof p);
   p.st.n_envs = 65536; p.autoreset = 1; p.horizon = 100;
-  std::vector<std::string> defs =
-      defines_for(g, p, MDPP_NOISE_PHILOX, MDPP_NORMAL_FAST, true, true, 3);
+  std::vector<std::string> defs = defines_for(
+      std::vector<DiscreteGroupDev>{g}, p, MDPP_NOISE_PHILOX, MDPP_NORMAL_FAST,
+      true, true, 3);
   // compile() loads the module too, which needs a driver: stop after NVRTC
   void* rtc = dlopen("libnvrtc.so.12", RTLD_NOW | RTLD_GLOBAL);
   if (!rtc) rtc = dlopen("/usr/local/cuda/lib64/libnvrtc.so.12", RTLD_NOW | RTLD_GLOBAL);

@@ -33,7 +33,6 @@ def test_multi_group_launch_equals_single_group_envs():
     het = make_env(N, autoreset=True, horizon=9, philox_seed=5,
                    config_groups=groups(), group_sizes=SIZES)
     out = het.rollout(T, want_final_obs=True)
-    assert not het.jit_last_used
     begin = 0
     for cfg, n, sl in zip(groups(), SIZES, het.group_slices):
         one = make_env(n, autoreset=True, horizon=9, philox_seed=5,
@@ -45,6 +44,23 @@ def test_multi_group_launch_equals_single_group_envs():
     st = het.episode_stats()
     assert st["transitions"].tolist() == [n * T for n in SIZES]
     assert st["episodes"].sum() == int((out["terminated"] | out["truncated"]).sum())
+
+
+def test_multi_group_jit_equals_aot():
+    """Partially specialised NVRTC kernel (scalars shared by all groups are
+    literals) vs the ahead-of-time kernel: bit-identical."""
+    N, T = sum(SIZES), 48
+    outs = []
+    for jit in (True, False):
+        env = make_env(N, autoreset=True, horizon=11, philox_seed=8,
+                       config_groups=groups(), group_sizes=SIZES)
+        env.set_jit(jit)
+        acts = torch.randint(0, 5, (T, N), dtype=torch.int32, device="cuda",
+                             generator=torch.Generator("cuda").manual_seed(2))
+        outs.append(env.rollout(T, actions=acts, want_final_obs=False))
+        assert env.jit_last_used == jit, env.jit_log
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
 
 
 def test_two_shards_equal_the_unsplit_job():
