@@ -267,6 +267,11 @@ def other_configs(torch, Env, dev, rank, world, barrier, max_over_ranks, peak):
                             50, barrier, max_over_ranks)
         line("C3_continuous_single_step", N, 1, ms, 256,
              "gym-style step(): one launch per step")
+        gstep = env.make_graphed_step()
+        ms = _time_launches(torch, lambda: gstep(a1), 50, barrier, max_over_ranks)
+        line("C3_continuous_single_step_cuda_graph", N, 1, ms, 256,
+             "step() replayed from a CUDA graph")
+        del gstep
         del env, acts, out
         # C4: 100x100 image observations, 16384 envs
         N = 16384
@@ -283,7 +288,12 @@ def other_configs(torch, Env, dev, rank, world, barrier, max_over_ranks, peak):
                                 max_over_ranks)
             line(f"C4_image_step[{tr}]", N, 1, ms, 10034,
                  "step() + render, two launches per step")
-            del env
+            gstep = env.make_graphed_step()
+            ms = _time_launches(torch, lambda: gstep(a), 30, barrier,
+                                max_over_ranks)
+            line(f"C4_image_step_cuda_graph[{tr}]", N, 1, ms, 10034,
+                 "step() + render replayed from a CUDA graph")
+            del env, gstep
         # C5: 1000-cell heterogeneous grid, 1M envs per GPU
         cfgs = [dict(base, delay=d, sequence_length=L, transition_noise=pn,
                      reward_noise=rn, make_denser=md, reward_every_n_steps=True)
@@ -390,6 +400,12 @@ def run_gpu_arm(args):
     barrier()
     single_ms = max_over_ranks(e0.elapsed_time(e1)) / n_single
     single_sps = world * N / (single_ms * 1e-3)
+    # the same call replayed from a CUDA graph (env.make_graphed_step())
+    gstep = env.make_graphed_step()
+    a_step = actions[0]
+    graph_ms = _time_launches(torch, lambda: gstep(a_step), n_single, barrier,
+                              max_over_ranks)
+    graph_sps = world * N / (graph_ms * 1e-3)
 
     # ---- end-to-end leg: host buffers through the public API --------------
     h_act = torch.empty((T, N), dtype=torch.int32).pin_memory()
@@ -462,7 +478,12 @@ def run_gpu_arm(args):
             "single_step_api": {"value": single_sps, "unit": UNIT,
                                 "us_per_call": single_ms * 1e3,
                                 "roofline_frac": single_sps / world
-                                * ALGO_BYTES_STEP / 1e9 / peak},
+                                * ALGO_BYTES_STEP / 1e9 / peak,
+                                "cuda_graph": {
+                                    "value": graph_sps, "unit": UNIT,
+                                    "us_per_call": graph_ms * 1e3,
+                                    "roofline_frac": graph_sps / world
+                                    * ALGO_BYTES_STEP / 1e9 / peak}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

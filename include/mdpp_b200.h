@@ -165,6 +165,10 @@ typedef struct mdpp_step_opts {
   uint64_t seed;          /* Philox key                                      */
   uint64_t step_index;    /* global index of the first step of this call     */
   int64_t env_id_offset;  /* global id of local env 0 (multi-GPU sharding)   */
+  const uint64_t* step_index_dev; /* optional DEVICE counter added to
+                                     step_index when the kernel runs: lets a
+                                     captured CUDA graph advance the Philox
+                                     step without re-recording (NULL = unused) */
 } mdpp_step_opts;
 
 /* K1/K2: T fused steps, one thread per env, tables staged in shared memory. */

@@ -72,7 +72,7 @@ class StepOpts(C.Structure):
         ("autoreset", C.c_int32), ("horizon", C.c_int32),
         ("normal_mode", C.c_int32), ("reserved0", C.c_int32),
         ("seed", C.c_uint64), ("step_index", C.c_uint64),
-        ("env_id_offset", C.c_int64),
+        ("env_id_offset", C.c_int64), ("step_index_dev", C.c_void_p),
     ]
 
 

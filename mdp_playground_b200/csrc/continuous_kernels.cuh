@@ -39,6 +39,7 @@ struct ContinuousParams {
   int32_t T, autoreset, horizon, noise_mode;
   uint32_t k0, k1;
   uint64_t step_index;
+  const uint64_t* step_index_dev;
   int64_t env_id_offset;
   // reset kernel only
   const uint8_t* mask;
@@ -194,7 +195,9 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   uint32_t ep = p.st.episode[env];
   bool reached = p.st.reached[env] != 0;
   int32_t phase = tl % EVERY_N;
-  int32_t ring_pos = DELAY > 0 ? (int32_t)(p.step_index % (uint64_t)DELAY) : 0;
+  const uint64_t step_base =
+      p.step_index + (p.step_index_dev ? *p.step_index_dev : 0ull);
+  int32_t ring_pos = DELAY > 0 ? (int32_t)(step_base % (uint64_t)DELAY) : 0;
 
   double sum_reward = 0, sum_abs_rnoise = 0, sum_abs_pnoise = 0;
   uint32_t n_episodes = 0, n_terminated = 0;
@@ -226,7 +229,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
       if (d < D) a_next[d] = ap[d];
   }
   for (int t = 0; t < p.T; ++t) {
-    const uint64_t step = p.step_index + (uint64_t)t;
+    const uint64_t step = step_base + (uint64_t)t;
     const int64_t row = ((int64_t)t * N + env);
     R a[MDPP_MAX_DIM], nxt[MDPP_MAX_DIM];
     bool in_range = true;

@@ -53,6 +53,7 @@ struct RolloutParams {
   uint32_t k0, k1;
   uint32_t rk[20];  // Philox round keys expanded from (k0, k1) by the host
   uint64_t step_index;
+  const uint64_t* step_index_dev;  // optional device counter added to step_index
   int64_t env_id_offset;
 };
 

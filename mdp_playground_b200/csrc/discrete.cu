@@ -129,6 +129,7 @@ extern "C" int mdpp_discrete_rollout(mdpp_ctx* ctx,
   p.k1 = (uint32_t)(opts->seed >> 32);
   philox_round_keys(p.k0, p.k1, p.rk);
   p.step_index = opts->step_index;
+  p.step_index_dev = opts->step_index_dev;
   p.env_id_offset = opts->env_id_offset;
   cudaStream_t s = (cudaStream_t)cuda_stream;
   if (opts->noise_mode < MDPP_NOISE_OFF || opts->noise_mode > MDPP_NOISE_PHILOX)

@@ -308,7 +308,8 @@ struct Cfg {
 // on the last chunk of a launch (guards the action / replay loads).
 template <typename C, int U>
 __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView& v,
-                                        int64_t env, uint32_t gid, int t0,
+                                        int64_t env, uint32_t gid,
+                                        uint64_t step_base, int t0,
                                         int n_valid, int32_t* act, double* u_tr,
                                         uint32_t* w_tr, double* n_rw, int32_t* s0) {
   constexpr int NOISE = C::NOISE;
@@ -318,7 +319,7 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
   const bool autoreset = autoreset_of(p);
   double u_rs[U];
   const int64_t off0 = (int64_t)t0 * N + env;
-  const uint64_t step0 = p.step_index + (uint64_t)t0;
+  const uint64_t step0 = step_base + (uint64_t)t0;
   const bool have_actions = FAST || p.io.actions != nullptr;
 #pragma unroll
   for (int j = 0; j < U; ++j) {
@@ -474,11 +475,11 @@ template <typename C, int U>
 __device__ __forceinline__ void run_chunk(const RolloutParams& p,
                                           const GroupView& v, EnvRegs& e,
                                           double* ring_smem, int64_t env,
-                                          uint32_t gid, int t0) {
+                                          uint32_t gid, uint64_t step_base, int t0) {
   int32_t act[U], s0[U];
   uint32_t w_tr[U];
   double u_tr[U], n_rw[U];
-  phase_a<C, U>(p, v, env, gid, t0, U, act, u_tr, w_tr, n_rw, s0);
+  phase_a<C, U>(p, v, env, gid, step_base, t0, U, act, u_tr, w_tr, n_rw, s0);
   phase_b<C, U, false>(p, v, e, ring_smem, kBlock, env, t0, U, act, u_tr, w_tr,
                        n_rw, s0);
 }
@@ -528,9 +529,13 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
   e.tl = p.st.t_episode[env];
   e.ep = p.st.episode[env];
   e.phase = e.tl % v.every_n;
-  e.ring_pos = v.delay > 0 ? (int32_t)(p.step_index % (uint64_t)v.delay) : 0;
+  // global index of the launch's first step (+ the optional device counter
+  // that lets a captured CUDA graph advance between replays)
+  const uint64_t step_base =
+      p.step_index + (p.step_index_dev ? *p.step_index_dev : 0ull);
+  e.ring_pos = v.delay > 0 ? (int32_t)(step_base % (uint64_t)v.delay) : 0;
   e.hist_pos = p.st.history
-      ? (int32_t)((p.step_index + 1) % (uint64_t)p.st.history_depth) : 0;
+      ? (int32_t)((step_base + 1) % (uint64_t)p.st.history_depth) : 0;
   e.sum_reward = e.sum_abs_rnoise = 0.0;
   e.n_noisy = e.n_episodes = e.n_terminated = e.n_steps = 0;
 
@@ -541,14 +546,14 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
     int t0 = 0;
     // chunks of kChunk steps start on a multiple-of-4 global step (the Philox
     // draws come in groups of 4 steps); peel single steps until aligned
-    while (t0 < p.T && ((p.step_index + (uint64_t)t0) & 3)) {
-      run_chunk<C, 1>(p, v, e, ring_smem, env, gid, t0);
+    while (t0 < p.T && ((step_base + (uint64_t)t0) & 3)) {
+      run_chunk<C, 1>(p, v, e, ring_smem, env, gid, step_base, t0);
       ++t0;
     }
     for (; t0 + kChunk <= p.T; t0 += kChunk)
-      run_chunk<C, kChunk>(p, v, e, ring_smem, env, gid, t0);
+      run_chunk<C, kChunk>(p, v, e, ring_smem, env, gid, step_base, t0);
     for (; t0 < p.T; ++t0)
-      run_chunk<C, 1>(p, v, e, ring_smem, env, gid, t0);
+      run_chunk<C, 1>(p, v, e, ring_smem, env, gid, step_base, t0);
     p.st.cur_state[env] = e.s;
     p.st.seq_key[env] = e.key;
     p.st.t_episode[env] = e.tl;

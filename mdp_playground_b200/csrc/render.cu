@@ -30,6 +30,7 @@ struct RenderDParams {
   int64_t n_envs;
   uint32_t k0, k1, stream;
   uint64_t step_index;
+  const uint64_t* step_index_dev;
   int64_t env_id_offset;
 };
 
@@ -57,7 +58,8 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
       // draw order of the reference (:149-181, :251, :258-259); one Philox
       // call per image: w0 scale, w1 / w2 shifts, w3 rotation + flip bits
       const uint32_t gid = (uint32_t)(p.env_id_offset + m % p.n_envs);
-      const uint64_t step = p.step_index + (uint64_t)(m / p.n_envs);
+      const uint64_t step = p.step_index + (uint64_t)(m / p.n_envs) +
+                            (p.step_index_dev ? *p.step_index_dev : 0ull);
       U4 w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32), p.stream,
                            p.k0, p.k1);
       R = tb.r_min;
@@ -318,6 +320,7 @@ extern "C" int mdpp_render_discrete(mdpp_ctx* ctx,
   p.k1 = (uint32_t)(opts->seed >> 32);
   p.stream = (uint32_t)image_stream;
   p.step_index = opts->step_index;
+  p.step_index_dev = opts->step_index_dev;
   p.env_id_offset = opts->env_id_offset;
   render_discrete_kernel<<<(unsigned)n_images, kRBlock, 0,
                            (cudaStream_t)cuda_stream>>>(p);

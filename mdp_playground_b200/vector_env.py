@@ -265,6 +265,11 @@ class VectorRLToyEnv:
         o.seed = self.philox_seed
         o.step_index = self._step_index
         o.env_id_offset = self.env_id_offset
+        if getattr(self, "_use_dev_counter", False):
+            # CUDA-graph mode: the step index lives in a device scalar that
+            # the graph itself advances (see make_graphed_step)
+            o.step_index = 0
+            o.step_index_dev = self._step_ctr.data_ptr()
         return o
 
     # ------------------------------------------------------------------
@@ -440,7 +445,8 @@ class VectorRLToyEnv:
         if step_index is None:
             step_index = self._step_index
         opts = self._opts(1)
-        opts.step_index = step_index
+        if not getattr(self, "_use_dev_counter", False):
+            opts.step_index = step_index
         if sp.kind == "discrete":
             st = state.to(torch.int64).contiguous()
             M = st.numel()
@@ -552,6 +558,81 @@ class VectorRLToyEnv:
             self._stream()))
         self._step_index += T
         return out
+
+    # ------------------------------------------------------------------
+    # CUDA-graph step: the gym-style path without per-step launch overhead
+    # ------------------------------------------------------------------
+    def _state_tensors(self):
+        names = ("_cur", "_key", "_t", "_episode", "_ring", "_history",
+                 "_stats", "_derivs", "_emitted", "_reached")
+        return [getattr(self, n) for n in names
+                if getattr(self, n, None) is not None]
+
+    def make_graphed_step(self):
+        """Capture one step() -- the step kernel, the renderer when images
+        are on, and the advance of the Philox step counter -- into a CUDA
+        graph.  Returns `fn(actions) -> (obs, reward, terminated, truncated,
+        info)` with the same meaning as step(); the returned tensors are
+        static buffers that the next call overwrites.  Philox noise only."""
+        assert self.noise == "philox", "graphed step needs noise='philox'"
+        N, dev = self.num_envs, self.device
+        cont = self.spec.kind == "continuous"
+        D = self.spec.state_space_dim
+        a_shape = (1, N, D) if cont else (1, N)
+        static_a = torch.zeros(a_shape, dtype=self._real if cont else torch.int32,
+                               device=dev)
+        if cont:
+            out = {"obs": torch.empty((1, N, D), dtype=self._real, device=dev),
+                   "reward": torch.empty((1, N), dtype=self._real, device=dev)}
+        else:
+            out = {"obs": torch.empty((1, N), dtype=torch.int64, device=dev),
+                   "reward": torch.empty((1, N), dtype=torch.float64, device=dev)}
+        out["terminated"] = torch.empty((1, N), dtype=torch.bool, device=dev)
+        out["truncated"] = torch.empty((1, N), dtype=torch.bool, device=dev)
+        self._step_ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+
+        def body():
+            self.rollout(1, actions=static_a, out=out)
+            self._step_index -= 1  # the device counter is the clock here
+            self._step_ctr += 1
+            return self._observe(out["obs"][0])
+
+        snapshot = [t.clone() for t in self._state_tensors()]
+        host_index = self._step_index
+        self._step_ctr.fill_(host_index)
+        self._use_dev_counter = True
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):  # warm-up: JIT compile, allocator
+                    body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                obs = body()
+        finally:
+            self._use_dev_counter = False
+        for t, saved in zip(self._state_tensors(), snapshot):
+            t.copy_(saved)  # warm-up and capture must not advance the envs
+        self._step_index = host_index
+        self._step_ctr.fill_(host_index)
+        mirror = [host_index]
+
+        def step_fn(actions):
+            if mirror[0] != self._step_index:  # eager calls happened in between
+                self._step_ctr.fill_(self._step_index)
+            static_a.copy_(torch.as_tensor(actions).reshape(a_shape),
+                           non_blocking=True)
+            graph.replay()
+            self._step_index += 1
+            mirror[0] = self._step_index
+            self.curr_obs = obs
+            return (obs, out["reward"][0], out["terminated"][0],
+                    out["truncated"][0], {"state": out["obs"][0]})
+
+        step_fn.graph = graph
+        return step_fn
 
     def rollout_host(self, n_steps, actions_host, out_host, chunk_steps=100):
         """rollout() for HOST buffers: `actions_host` [T, N(, D)] and the

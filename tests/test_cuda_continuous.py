@@ -170,3 +170,18 @@ def test_full_size_config3_properties():
     never_done = ~out["terminated"].any(dim=0)
     tot = out["reward"].sum(dim=0)
     assert torch.allclose(tot[never_done], (d0 - dT)[never_done], atol=1e-3)
+
+
+def test_graphed_step_equals_eager_step_continuous():
+    cfg = gu.case_config("cont_noise_delay")
+    a = make_env(200, autoreset=True, horizon=9, philox_seed=4, **cfg)
+    b = make_env(200, autoreset=True, horizon=9, philox_seed=4,
+                 **gu.case_config("cont_noise_delay"))
+    fn = b.make_graphed_step()
+    rng = np.random.default_rng(0)
+    for t in range(15):
+        acts = torch.as_tensor(rng.uniform(-1, 1, size=(200, 6)).astype(np.float32),
+                               device="cuda")
+        ra, rb = a.step(acts), fn(acts)
+        for x, y in zip(ra[:4], rb[:4]):
+            assert torch.equal(x, y), t

@@ -261,3 +261,23 @@ def test_init_state_distribution_and_full_size_properties():
     assert st["transitions"][0] == N * T
     assert st["episodes"][0] == int(reset.sum())
     assert st["terminated"][0] == int(term.sum())
+
+
+@pytest.mark.parametrize("name", ["c2_every1", "c4_img_all"])
+def test_graphed_step_equals_eager_step(name):
+    """A CUDA-graph replay of step() (+ renderer) == eager step() calls, also
+    when eager calls are mixed in between replays."""
+    cfg = gu.case_config(name)
+    a = make_env(300, autoreset=True, horizon=6, philox_seed=4, **cfg)
+    b = make_env(300, autoreset=True, horizon=6, philox_seed=4,
+                 **gu.case_config(name))
+    fn = b.make_graphed_step()
+    assert torch.equal(a._cur, b._cur)
+    rng = np.random.default_rng(0)
+    for t in range(20):
+        acts = torch.as_tensor(rng.integers(0, 8, size=300), dtype=torch.int32,
+                               device="cuda")
+        ra = a.step(acts)
+        rb = fn(acts) if t % 5 != 4 else b.step(acts)
+        for x, y in zip(ra[:4], rb[:4]):
+            assert torch.equal(x, y), t
