@@ -1,0 +1,235 @@
+"""The reference's own known-answer tests for the step path
+(/root/reference/tests/test_mdp_playground.py), ported with their golden
+numbers and run against (a) the scalar oracle on CPU and (b) the CUDA path
+(`VectorRLToyEnv(1, noise="numpy")`, i.e. same seeds => same streams) on GPU.
+Each test cites the reference test it restates.  Only the 14 reference tests
+that pass at HEAD are ported (the other 6 are stale), and
+of those the ones on the supported path (no grid / move_along_a_line)."""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle.scalar_env import ScalarRLToyEnv
+
+
+class OracleAdapter:
+    def __init__(self, **cfg):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            self.env = ScalarRLToyEnv(**cfg)
+
+    def state(self):
+        return self.env.curr_state
+
+    def step(self, a):
+        obs, r, done, _, _ = self.env.step(a)
+        return obs, r, done, self.env.curr_state
+
+
+class CudaAdapter:
+    def __init__(self, **cfg):
+        import torch
+        from mdp_playground_b200 import VectorRLToyEnv
+        self.torch = torch
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            self.env = VectorRLToyEnv(1, noise="numpy", **cfg)
+        self.cont = self.env.spec.kind == "continuous"
+
+    def state(self):
+        st = self.env.get_augmented_state()["curr_state"][0].cpu().numpy()
+        return st if self.cont else int(st)
+
+    def step(self, a):
+        act = self.torch.as_tensor(np.asarray(a))[None] if self.cont else [int(a)]
+        obs, r, term, _, info = self.env.step(act)
+        st = info["state"][0].cpu().numpy()
+        r = r[0].cpu().numpy()
+        return (obs[0].cpu().numpy(), r.item(), bool(term[0]),
+                st if self.cont else int(st))
+
+
+IMPLS = [pytest.param(OracleAdapter, id="oracle"),
+         pytest.param(CudaAdapter, id="cuda", marks=pytest.mark.gpu)]
+
+
+def _discrete(**kw):
+    cfg = dict(seed={"env": 0, "relevant_state_space": 8, "relevant_action_space": 8},
+               state_space_type="discrete", action_space_type="discrete",
+               state_space_size=8, action_space_size=8, reward_density=0.25,
+               make_denser=False, terminal_state_density=0.25,
+               maximally_connected=True, repeats_in_sequences=False, delay=0,
+               sequence_length=1, reward_scale=1.0, generate_random_mdp=True)
+    cfg.update(kw)
+    return cfg
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_discrete_dynamics(impl):
+    """test_mdp_playground.py:1221-1298: P dynamics, terminal self-loop."""
+    env = impl(**_discrete(
+        seed={"env": 0, "relevant_state_space": 6, "relevant_action_space": 6},
+        state_space_size=6, action_space_size=6, make_denser=True,
+        sequence_length=3))
+    for a, want in ((2, 4), (4, 2), (0, 5)):
+        _, _, done, s = env.step(a)
+        assert s == want
+    assert done
+    _, _, done, s = env.step(3)
+    assert s == 5 and done
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_discrete_reward_delay(impl):
+    """:1300-1349: delay 3."""
+    env = impl(**_discrete(make_denser=True, delay=3))
+    for a, want in zip([3, 2, 5, 4, 5, 2, 3, 1, 4], [0, 0, 0, 1, 0, 0, 0, 1, 0]):
+        assert env.step(a)[1] == want
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_discrete_p_noise(impl):
+    """:1406-1454: transition_noise 0.9, states from the S stream."""
+    env = impl(**_discrete(transition_noise=0.9))
+    last = int(np.random.default_rng(0).integers(8))
+    for a, want in zip([6, 6, 2, last], [0, 4, 3, 1]):
+        assert env.step(a)[3] == want
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_discrete_r_noise(impl):
+    """:1456-1504: reward noise N(0, 0.5) from the E stream."""
+    env = impl(**_discrete(reward_noise=0.5))
+    for a, want in zip([3, 6], [1 - 0.0660524, 0.320211]):
+        np.testing.assert_allclose(env.step(a)[1], want, rtol=1e-5)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_discrete_reward_every_n_steps(impl):
+    """:1879-1985: the three sub-cases."""
+    env = impl(**_discrete(sequence_length=3))
+    for a, want in zip([6, 2, 2, 4, 4, 6], [0, 0, 1, 0, 0, 1]):
+        assert env.step(a)[1] == want
+    env = impl(**_discrete(sequence_length=3, delay=1, reward_every_n_steps=2))
+    for a, want in zip([6, 2, 2, 4, 4, 6], [0, 0, 0, 1, 0, 0]):
+        assert env.step(a)[1] == want
+    env = impl(**_discrete(sequence_length=1, delay=1, reward_every_n_steps=2))
+    for a, want in zip([6, 3, 4, 4, 4, 6, 6], [0, 0, 0, 1, 0, 1, 0]):
+        assert env.step(a)[1] == want
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_discrete_custom_P_R(impl):
+    """:1990-2040: custom 8x5 P and R matrices, delay 1, scale 2."""
+    cfg = dict(seed=0, state_space_type="discrete", action_space_type="discrete",
+               state_space_size=8, action_space_size=5,
+               terminal_state_density=0.25, repeats_in_sequences=False, delay=1,
+               reward_scale=2.0, use_custom_mdp=True,
+               transition_function=np.random.default_rng(0).integers(8, size=(8, 5)),
+               reward_function=np.random.default_rng(1).integers(4, size=(8, 5)),
+               init_state_dist=np.array([1 / 8] * 8))
+    env = impl(**cfg)
+    last = int(np.random.default_rng(0).integers(5))
+    for a, want in zip([4, 4, 2, 3, 4, 2, 4, 1, 0, last, 4],
+                       [0, 2, 2, 6, 6, 2, 0, 2, 6, 2, 2]):
+        assert env.step(a)[1] == want
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_discrete_image_representations(impl):
+    """:1776-1873: seq 3, delay 1, scale 2.5, shift -1.75, R-noise, and the
+    pixel sums of the first three 100x100 observations with
+    shift,scale,rotate,flip."""
+    cfg = _discrete(
+        seed={"env": 0, "relevant_state_space": 8, "relevant_action_space": 8,
+              "image_representations": 0},
+        delay=1, sequence_length=3, reward_every_n_steps=1, reward_scale=2.5,
+        reward_shift=-1.75, reward_noise=0.5, image_representations=True,
+        image_width=100, image_height=100,
+        image_transforms="shift,scale,rotate,flip", image_scale_range=(0.5, 1.5))
+    env = impl(**cfg)
+    rewards = [0, 0, 0, 0, 1]
+    noises = [-0.0660524, 0.3202113, 0.052450, -0.267834, 0.1807975]
+    sums = [364395, 342465, 412335]
+    for i, a in enumerate([4, 6, 2, 7, 4]):
+        obs, r, _, _ = env.step(a)
+        assert obs.shape == (100, 100, 1) and obs.dtype == np.uint8
+        if i < len(sums):
+            assert int(obs.sum()) == sums[i]
+        np.testing.assert_allclose(r, (rewards[i] + noises[i]) * 2.5 - 1.75,
+                                   rtol=1e-5)
+
+
+def _continuous(**kw):
+    cfg = dict(seed={"env": 3, "state_space": 10000, "action_space": 101},
+               state_space_type="continuous", action_space_type="continuous",
+               state_space_dim=2, action_space_dim=2, transition_dynamics_order=1,
+               inertia=2.0, time_unit=0.1, delay=0, sequence_length=1,
+               reward_scale=1.0, reward_function="move_to_a_point",
+               target_point=[0.69422, 1.27494], target_radius=0.05,
+               make_denser=True)
+    cfg.update(kw)
+    return cfg
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_continuous_dynamics_target_point_dense(impl):
+    """:489-603: dense reward 0.0353553 per step, final states, 5-D variant
+    with irrelevant dimensions, delay 10."""
+    env = impl(**_continuous())
+    for _ in range(20):
+        _, r, _, s = env.step(np.array([0.5] * 2, dtype=np.float32))
+        np.testing.assert_allclose(r, 0.0353553, atol=1e-5)
+    np.testing.assert_allclose(s, [0.69422, 1.27494], atol=1e-5)
+    cfg5 = _continuous(state_space_dim=5, action_space_dim=5,
+                       relevant_indices=[1, 2],
+                       action_space_relevant_indices=[1, 2],
+                       target_point=[1.27494, -0.780999])
+    env = impl(**cfg5)
+    for _ in range(20):
+        _, r, _, s = env.step(np.array([0.5] * 5, dtype=np.float32))
+        np.testing.assert_allclose(r, 0.035355, atol=1e-5)
+    np.testing.assert_allclose(
+        s, [0.69422, 1.27494, -0.780999, 1.52398, -0.311794], atol=1e-5)
+    _, r, _, _ = env.step(np.array([0.5] * 5, dtype=np.float32))
+    np.testing.assert_allclose(r, -0.035355, atol=1e-5)
+    env = impl(**dict(cfg5, delay=10))
+    for i in range(20):
+        _, r, _, s = env.step(np.array([0.5] * 5, dtype=np.float32))
+        np.testing.assert_allclose(r, 0.0 if i < 10 else 0.035355, atol=1e-5)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_continuous_dynamics_target_point_sparse(impl):
+    """:605-715: sparse reward inside the radius, with and without delay."""
+    sparse = dict(make_denser=False, target_radius=0.072, reward_scale=2.0)
+    env = impl(**_continuous(**sparse))
+    for i in range(20):
+        _, r, _, s = env.step(np.array([0.5] * 2, dtype=np.float32))
+        np.testing.assert_allclose(r, 0.0 if i < 17 else 2.0, atol=1e-5)
+    np.testing.assert_allclose(s, [0.69422, 1.27494], atol=1e-5)
+    env = impl(**_continuous(delay=10, **sparse))
+    for i in range(35):
+        _, r, _, s = env.step(np.array([0.5] * 2, dtype=np.float32))
+        np.testing.assert_allclose(r, 2.0 if 27 <= i <= 31 else 0.0, atol=1e-5)
+    np.testing.assert_allclose(s, [1.06922, 1.64994], atol=1e-5)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_continuous_image_representations(impl):
+    """:717-787: pixel sums of the RGB observations, sparse reward."""
+    cfg = dict(seed=0, state_space_type="continuous",
+               action_space_type="continuous", state_space_dim=2,
+               action_space_dim=2, delay=0, sequence_length=1,
+               transition_dynamics_order=1, inertia=1.0, time_unit=1,
+               reward_function="move_to_a_point", state_space_max=5,
+               target_point=[0.146517, -0.397534], target_radius=0.172,
+               reward_scale=2.0, make_denser=False, image_representations=True,
+               image_width=100, image_height=100)
+    env = impl(**cfg)
+    sums = [6168414, 6168414, 6168414, 6171735, 6204207]
+    for i in range(5):
+        obs, r, done, s = env.step(np.array([-0.45, -0.8], dtype=np.float32))
+        assert obs.shape == (100, 100, 3) and int(obs.sum()) == sums[i]
+    assert np.linalg.norm(s - np.array(cfg["target_point"])) < 0.172
