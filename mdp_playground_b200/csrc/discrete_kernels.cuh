@@ -387,6 +387,83 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
 }
 
 // ---- phase B: the state-dependent chain -----------------------------------
+// One environment step given its pre-drawn randomness.
+template <typename C>
+__device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupView& v,
+                                           EnvRegs& e, double* ring_smem,
+                                           int ring_stride, int64_t env, int64_t off,
+                                           int32_t act, double u_tr, uint32_t w_tr,
+                                           double n_rw, int32_t s0) {
+  constexpr int NOISE = C::NOISE;
+  constexpr bool RING_SMEM = C::RING_SMEM;
+  constexpr bool FAST = C::FAST;
+  const int64_t N = n_envs_of(p);
+  const bool autoreset = autoreset_of(p);
+  const int horizon = horizon_of(p);
+  uint32_t a = (uint32_t)act;
+  if (a >= (uint32_t)v.A) a = (uint32_t)v.A - 1;  // memory safety only
+  int32_t nxt = v.P[e.s * v.A + (int32_t)a];
+  if (NOISE != MDPP_NOISE_OFF && v.has_pnoise) {
+    // replay: the recorded fp64 uniform against the fp64 cdf; Philox: the
+    // 32-bit word against the equivalent integer thresholds
+    const int32_t noisy = NOISE == MDPP_NOISE_REPLAY
+        ? cdf_search<C::CDF_LOG2>(v.noise_cdf + nxt * v.cdf_stride, v.cdf_log2,
+                                  v.S, u_tr)
+        : thr_search<C::CDF_LOG2>(v.noise_thr + nxt * v.cdf_stride, v.cdf_log2,
+                                  v.S, w_tr);
+    e.n_noisy += (noisy != nxt);
+    nxt = noisy;
+  }
+  e.key = ((e.key << v.key_bits) | (uint64_t)nxt) & v.key_mask;
+  e.tl += 1;
+  e.phase = (e.phase + 1 == v.every_n) ? 0 : e.phase + 1;
+  double r = 0.0;
+  if (v.lookup_kind == LOOKUP_MATRIX) {
+    r = v.R[e.s * v.A + (int32_t)a];
+  } else if (e.tl >= v.L) {  // isnan(aug[delay]) gate <=> t < L
+    r = sequence_reward(v, e.key);
+  }
+  if (v.delay > 0) {  // FIFO of depth d: pay out what was earned d steps ago
+    double* slot = RING_SMEM
+        ? ring_smem + e.ring_pos * ring_stride
+        : p.st.ring + (int64_t)e.ring_pos * N + env;
+    double delayed = (e.tl > v.delay) ? *slot : 0.0;
+    *slot = r;
+    r = delayed;
+    e.ring_pos = (e.ring_pos + 1 == v.delay) ? 0 : e.ring_pos + 1;
+  }
+  if (e.phase != 0) r = 0.0;
+  e.sum_reward += r;
+  if (NOISE != MDPP_NOISE_OFF && v.has_rnoise) {
+    e.sum_abs_rnoise += fabs(n_rw);
+    r = __dadd_rn(r, n_rw);
+  }
+  r = __dmul_rn(r, v.scale);
+  r = __dadd_rn(r, v.shift);
+  const bool done = v.term[nxt] != 0;
+  if (done) r = __dadd_rn(r, v.term_reward_scaled);
+  const bool trunc = horizon > 0 && e.tl >= horizon;
+  e.n_terminated += done;
+  e.s = nxt;
+  if (!FAST && p.io.final_obs) st_stream(p.io.final_obs + off, (int64_t)nxt);
+  if (autoreset && (done || trunc)) {
+    e.s = s0;
+    e.key = (uint64_t)e.s;
+    e.tl = 0;
+    e.phase = 0;
+    e.ep += 1;
+    e.n_episodes += 1;
+  }
+  if (!FAST && p.st.history) {
+    p.st.history[(int64_t)e.hist_pos * N + env] = e.s;
+    e.hist_pos = (e.hist_pos + 1 == p.st.history_depth) ? 0 : e.hist_pos + 1;
+  }
+  if (FAST || p.io.obs) st_stream(p.io.obs + off, (int64_t)e.s);
+  if (FAST || p.io.reward) st_stream(p.io.reward + off, r);
+  if (FAST || p.io.terminated) st_stream(p.io.terminated + off, (uint8_t)done);
+  if (FAST || p.io.truncated) st_stream(p.io.truncated + off, (uint8_t)trunc);
+}
+
 template <typename C, int U, bool PARTIAL>
 __device__ __forceinline__ void phase_b(const RolloutParams& p, const GroupView& v,
                                         EnvRegs& e, double* ring_smem, int ring_stride,
@@ -394,79 +471,13 @@ __device__ __forceinline__ void phase_b(const RolloutParams& p, const GroupView&
                                         const int32_t* act, const double* u_tr,
                                         const uint32_t* w_tr, const double* n_rw,
                                         const int32_t* s0) {
-  constexpr int NOISE = C::NOISE;
-  constexpr bool RING_SMEM = C::RING_SMEM;
-  constexpr bool FAST = C::FAST;
   const int64_t N = n_envs_of(p);
-  const bool autoreset = autoreset_of(p);
-  const int horizon = horizon_of(p);
   const int64_t off0 = (int64_t)t0 * N + env;
 #pragma unroll
   for (int j = 0; j < U; ++j) {
     if (PARTIAL && j >= n_valid) break;
-    const int64_t off = off0 + (int64_t)j * N;
-    uint32_t a = (uint32_t)act[j];
-    if (a >= (uint32_t)v.A) a = (uint32_t)v.A - 1;  // memory safety only
-    int32_t nxt = v.P[e.s * v.A + (int32_t)a];
-    if (NOISE != MDPP_NOISE_OFF && v.has_pnoise) {
-      // replay: the recorded fp64 uniform against the fp64 cdf; Philox: the
-      // 32-bit word against the equivalent integer thresholds
-      const int32_t noisy = NOISE == MDPP_NOISE_REPLAY
-          ? cdf_search<C::CDF_LOG2>(v.noise_cdf + nxt * v.cdf_stride, v.cdf_log2,
-                                    v.S, u_tr[j])
-          : thr_search<C::CDF_LOG2>(v.noise_thr + nxt * v.cdf_stride, v.cdf_log2,
-                                    v.S, w_tr[j]);
-      e.n_noisy += (noisy != nxt);
-      nxt = noisy;
-    }
-    e.key = ((e.key << v.key_bits) | (uint64_t)nxt) & v.key_mask;
-    e.tl += 1;
-    e.phase = (e.phase + 1 == v.every_n) ? 0 : e.phase + 1;
-    double r = 0.0;
-    if (v.lookup_kind == LOOKUP_MATRIX) {
-      r = v.R[e.s * v.A + (int32_t)a];
-    } else if (e.tl >= v.L) {  // isnan(aug[delay]) gate <=> t < L
-      r = sequence_reward(v, e.key);
-    }
-    if (v.delay > 0) {  // FIFO of depth d: pay out what was earned d steps ago
-      double* slot = RING_SMEM
-          ? ring_smem + e.ring_pos * ring_stride
-          : p.st.ring + (int64_t)e.ring_pos * N + env;
-      double delayed = (e.tl > v.delay) ? *slot : 0.0;
-      *slot = r;
-      r = delayed;
-      e.ring_pos = (e.ring_pos + 1 == v.delay) ? 0 : e.ring_pos + 1;
-    }
-    if (e.phase != 0) r = 0.0;
-    e.sum_reward += r;
-    if (NOISE != MDPP_NOISE_OFF && v.has_rnoise) {
-      e.sum_abs_rnoise += fabs(n_rw[j]);
-      r = __dadd_rn(r, n_rw[j]);
-    }
-    r = __dmul_rn(r, v.scale);
-    r = __dadd_rn(r, v.shift);
-    const bool done = v.term[nxt] != 0;
-    if (done) r = __dadd_rn(r, v.term_reward_scaled);
-    const bool trunc = horizon > 0 && e.tl >= horizon;
-    e.n_terminated += done;
-    e.s = nxt;
-    if (!FAST && p.io.final_obs) st_stream(p.io.final_obs + off, (int64_t)nxt);
-    if (autoreset && (done || trunc)) {
-      e.s = s0[j];
-      e.key = (uint64_t)e.s;
-      e.tl = 0;
-      e.phase = 0;
-      e.ep += 1;
-      e.n_episodes += 1;
-    }
-    if (!FAST && p.st.history) {
-      p.st.history[(int64_t)e.hist_pos * N + env] = e.s;
-      e.hist_pos = (e.hist_pos + 1 == p.st.history_depth) ? 0 : e.hist_pos + 1;
-    }
-    if (FAST || p.io.obs) st_stream(p.io.obs + off, (int64_t)e.s);
-    if (FAST || p.io.reward) st_stream(p.io.reward + off, r);
-    if (FAST || p.io.terminated) st_stream(p.io.terminated + off, (uint8_t)done);
-    if (FAST || p.io.truncated) st_stream(p.io.truncated + off, (uint8_t)trunc);
+    chain_step<C>(p, v, e, ring_smem, ring_stride, env, off0 + (int64_t)j * N,
+                  act[j], u_tr[j], w_tr[j], n_rw[j], s0[j]);
   }
   e.n_steps += PARTIAL ? n_valid : U;
 }
