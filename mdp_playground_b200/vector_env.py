@@ -932,6 +932,66 @@ class VectorRLToyEnv:
         return {"curr_state": self._cur.to(torch.int64),
                 "curr_obs": self.curr_obs, "augmented_state": hist}
 
+    def set_augmented_state(self, state):
+        """Batched analogue of RLToyEnv.set_augmented_state (:2168): accepts
+        the dict returned by get_augmented_state() or a bare state tensor
+        ([N] discrete, [N, D] continuous; then the window holds only that state
+        and continuous derivatives are zeroed).  Like the reference it does not
+        touch the reward-delay FIFO or the RNG streams."""
+        dev, N = self.device, self.num_envs
+        if self.spec.kind == "continuous":
+            D, order = self.spec.state_space_dim, self.spec.dynamics_order
+            if isinstance(state, dict):
+                cur = torch.as_tensor(state["curr_state"], device=dev).to(self._real)
+                sd = torch.as_tensor(state["state_derivatives"], device=dev).to(
+                    self._real).reshape(N, order + 1, D)
+            else:
+                cur = torch.as_tensor(state, device=dev).to(self._real)
+                sd = torch.zeros((N, order + 1, D), dtype=self._real, device=dev)
+                sd[:, 0] = cur.reshape(N, D)
+            self._emitted.copy_(cur.reshape(N, D).t())
+            self._derivs.copy_(sd.permute(1, 2, 0))
+            self.curr_obs = self._observe(cur.reshape(N, D), reset=True, ctor=True)
+            return
+        if self._history is None:
+            raise RuntimeError("construct with track_history=True to use "
+                               "set_augmented_state()")
+        H, L = self._hist_depth, self.spec.sequence_length
+        if isinstance(state, dict):
+            aug = torch.as_tensor(state["augmented_state"], device=dev).to(
+                torch.float64).reshape(N, H)
+        else:
+            aug = torch.full((N, H), float("nan"), dtype=torch.float64, device=dev)
+            aug[:, -1] = torch.as_tensor(state, device=dev).to(torch.float64)
+        valid = ~torch.isnan(aug)
+        n_valid = valid.to(torch.int32).sum(dim=1)          # trailing entries
+        states = torch.nan_to_num(aug, nan=0.0).to(torch.int64)
+        self._cur.copy_(states[:, -1].to(torch.int32))
+        bits = max(1, int(np.ceil(np.log2(max(self.tables.n_states, 2)))))
+        key = torch.zeros(N, dtype=torch.int64, device=dev)
+        for j in range(L):  # oldest of the last L first, newest lowest
+            key = (key << bits) | states[:, H - L + j]
+        mask = (1 << (bits * L)) - 1
+        self._key.copy_(key & mask)
+        # t such that the kernel's NaN gate (t >= L) sees the same window; a
+        # full window keeps the current count when it is already large enough
+        t_new = (n_valid - 1).clamp(min=0)
+        keep = (n_valid == H) & (self._t >= H - 1)
+        self._t.copy_(torch.where(keep, self._t, t_new))
+        idx = (self._step_index - torch.arange(H - 1, -1, -1, device=dev)) % H
+        self._history[idx] = states.t().to(torch.int32)
+        self.curr_obs = self._observe(self._cur.to(torch.int64), reset=True,
+                                      ctor=True)
+
+    def seed(self, seed=None):
+        """RLToyEnv.seed (:2379): re-keys the environment's noise stream."""
+        if self.noise == "numpy":
+            for i in range(self.num_envs):
+                self._rng_E[i], _ = np_random(None if seed is None else seed + i)
+        elif seed is not None:
+            self.philox_seed = int(seed) & (2**64 - 1)
+        return seed
+
     def episode_stats(self, reduce=False):
         """Per-group counters of rl_toy_env.py:2360-2369 summed over envs and
         episodes; `reduce=True` all-reduces over torch.distributed ranks."""

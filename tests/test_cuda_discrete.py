@@ -281,3 +281,28 @@ def test_graphed_step_equals_eager_step(name):
         rb = fn(acts) if t % 5 != 4 else b.step(acts)
         for x, y in zip(ra[:4], rb[:4]):
             assert torch.equal(x, y), t
+
+
+def test_set_augmented_state_round_trip_and_bare_state():
+    """get_augmented_state() -> set_augmented_state() on a fresh env continues
+    the same trajectory (delay 0, so no hidden FIFO contents); a bare state
+    behaves like a fresh episode in that state (:2168-2215)."""
+    cfg = dict(gu.case_config("c2_every1"), delay=0)
+    a = make_env(64, philox_seed=3, **dict(cfg))
+    b = make_env(64, philox_seed=3, **dict(cfg))
+    acts = torch.randint(0, 8, (9, 64), dtype=torch.int32, device="cuda")
+    a.rollout(5, actions=acts[:5])
+    b._step_index = a._step_index            # same Philox clock
+    b.set_augmented_state(a.get_augmented_state())
+    ra, rb = a.rollout(4, actions=acts[5:]), b.rollout(4, actions=acts[5:])
+    for k in ra:
+        assert torch.equal(ra[k], rb[k]), k
+    ref = scalar_oracle(dict(cfg))
+    c = make_env(1, noise="numpy", **dict(cfg))
+    ref.augmented_state = [np.nan] * (len(ref.augmented_state) - 1) + [2]
+    ref.curr_state = 2
+    c.set_augmented_state(torch.tensor([2]))
+    for t, act in enumerate([1, 5, 3, 3, 0, 6]):
+        o1, r1, d1, _, _ = ref.step(act)
+        o2, r2, d2, _, _ = c.step([act])
+        assert int(o2[0]) == int(o1) and float(r2[0]) == float(r1), t
