@@ -1,0 +1,160 @@
+"""Experiment-grid front end: run a reference experiment
+file's environment grid as ONE heterogeneous VectorRLToyEnv.
+
+The reference expands `var_env_configs` of an `experiments/*.py` module into
+a Cartesian grid (config_processor.get_grid_of_configs,
+config_processor/config_processor.py:492-517), merges every cell over the
+static `env_config["env_config"]` and hands each to a separate Ray trial
+(scripts/run_experiments.py:231-276).  Here every cell becomes one
+configuration group of a single batched env, stepped by one kernel launch,
+and the per-cell episode statistics are written in the reference's CSV layout
+(config_processor.py:241-259, :340-373) so its analysis code can read them.
+No agent is trained: the policy is uniform random (or supplied by the caller).
+"""
+import copy
+import importlib.util
+import itertools
+import os
+import sys
+import types
+from collections import OrderedDict
+
+import numpy as np
+
+
+def _ray_stub():
+    """The experiment files do `from ray import tune` and only use
+    `tune.grid_search([...])` in agent configs; ray itself is not needed to
+    read the environment grid."""
+    ray = types.ModuleType("ray")
+    tune = types.ModuleType("ray.tune")
+    tune.grid_search = lambda values: {"grid_search": list(values)}
+    tune.choice = lambda values: {"choice": list(values)}
+    tune.uniform = lambda a, b: {"uniform": (a, b)}
+    tune.function = lambda f: f  # old Ray API the eval configs still use
+    ray.tune = tune
+    return {"ray": ray, "ray.tune": tune}
+
+
+def load_experiment(path):
+    """Import an experiment module (stubbing `ray` if it is not installed)."""
+    path = os.path.abspath(path)
+    if not path.endswith(".py"):
+        path += ".py"
+    stubs = {}
+    try:
+        import ray  # noqa: F401
+    except ModuleNotFoundError:
+        stubs = _ray_stub()
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location(
+            "mdpp_experiment_" + os.path.basename(path)[:-3], path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
+def expand_grid(var_configs):
+    """get_grid_of_configs (:492-517): Cartesian product of every leaf list,
+    in the dict's iteration order.  Returns (keys, list of value tuples) with
+    keys as (config_type, key) pairs."""
+    keys, values = [], []
+    for config_type, config_dict in var_configs.items():
+        for key, leaf in config_dict.items():
+            assert isinstance(leaf, list), (
+                "var_configs should be a dict of dicts with lists as the leaf "
+                "values to allow each configuration option to take multiple "
+                "possible values")
+            keys.append((config_type, key))
+            values.append(leaf)
+    cells = list(itertools.product(*values)) if values else []
+    return keys, cells
+
+
+def env_grid(module):
+    """(var env keys, list of per-cell env config dicts) of an experiment."""
+    var_configs = getattr(module, "var_configs", None)
+    if var_configs is None:
+        var_configs = OrderedDict({"env": module.var_env_configs})
+    keys, cells = expand_grid(var_configs)
+    static = copy.deepcopy(module.env_config.get("env_config", {}))
+    env_keys = [k for t, k in keys if t == "env"]
+    out = []
+    for cell in cells:
+        cfg = copy.deepcopy(static)
+        for (t, k), v in zip(keys, cell):
+            if t == "env":
+                cfg[k] = v
+        out.append(cfg)
+    return env_keys, out
+
+
+class Sweep:
+    """All cells of an experiment's env grid in one VectorRLToyEnv."""
+
+    def __init__(self, experiment, envs_per_cell=64, horizon=None, device=None,
+                 shard=(0, 1), **env_kwargs):
+        from .vector_env import VectorRLToyEnv
+        self.module = load_experiment(experiment) if isinstance(experiment, str) \
+            else experiment
+        self.env_keys, self.cell_configs = env_grid(self.module)
+        self.n_cells = len(self.cell_configs)
+        if horizon is None:
+            horizon = int(self.module.env_config.get("horizon", 100))
+        self.envs_per_cell = int(envs_per_cell)
+        self.env = VectorRLToyEnv(
+            self.n_cells * self.envs_per_cell, device=device, autoreset=True,
+            horizon=horizon, config_groups=self.cell_configs,
+            group_sizes=[self.envs_per_cell] * self.n_cells, shard=shard,
+            **env_kwargs)
+        self.timesteps = 0
+        self._returned = np.zeros(self.n_cells)
+
+    def run(self, steps_per_env, chunk=256, actions_fn=None):
+        """Random-policy (or `actions_fn(t0, T) -> int32[T, N]`) rollouts."""
+        import torch
+        done = 0
+        while done < steps_per_env:
+            T = min(chunk, steps_per_env - done)
+            acts = None if actions_fn is None else actions_fn(done, T)
+            out = self.env.rollout(T, actions=acts, want_final_obs=False)
+            r = out["reward"].sum(dim=0).reshape(self.n_cells, self.envs_per_cell)
+            self._returned += r.sum(dim=1).to(torch.float64).cpu().numpy()
+            done += T
+        self.timesteps += steps_per_env
+        return self.results()
+
+    def results(self, reduce=False):
+        st = self.env.episode_stats(reduce=reduce)
+        ep = np.maximum(st["episodes"], 1)
+        return {"episodes": st["episodes"], "transitions": st["transitions"],
+                "episode_reward_mean": self._returned / ep,
+                "episode_len_mean": st["transitions"] / ep,
+                "noisy_transitions": st["noisy_transitions"]}
+
+    def write_csv(self, path, algorithm="RandomPolicy"):
+        """One row per grid cell in the reference's stats-file layout."""
+        res = self.results()
+        with open(path, "w") as f:
+            f.write("# training_iteration, algorithm, "
+                    + "".join(k + ", " for k in self.env_keys)
+                    + "timesteps_total, episode_reward_mean, episode_len_mean\n")
+            for i, cfg in enumerate(self.cell_configs):
+                row = ["1", algorithm]
+                for k in self.env_keys:
+                    v = cfg[k]
+                    row.append("%.2e" % v if isinstance(v, float)
+                               else str(v).replace(" ", ""))
+                row += [str(int(res["transitions"][i])),
+                        "%.2e" % res["episode_reward_mean"][i],
+                        "%.2e" % res["episode_len_mean"][i]]
+                f.write(" ".join(row) + "\n")
+        return path

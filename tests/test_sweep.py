@@ -1,0 +1,68 @@
+"""Experiment-grid front end: reading reference-format experiment files,
+grid expansion (config_processor.get_grid_of_configs), and on the GPU the
+whole grid as one heterogeneous batched env with the reference's CSV layout."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from mdp_playground_b200 import sweep
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIXTURE = os.path.join(HERE, "fixtures", "dqn_seq_del_like.py")
+
+
+def test_grid_expansion_matches_get_grid_of_configs_semantics():
+    mod = sweep.load_experiment(FIXTURE)
+    keys, cells = sweep.expand_grid(mod.var_configs)
+    assert [k for _, k in keys][:4] == ["state_space_size", "action_space_size",
+                                        "delay", "sequence_length"]
+    assert len(cells) == 3 * 3 * 2 * 2
+    # itertools.product order: the last key varies fastest
+    assert cells[0][-1] == 0 and cells[1][-1] == 1 and cells[2][7] == 0.1
+    env_keys, cfgs = sweep.env_grid(mod)
+    assert cfgs[0]["seed"] == 0 and cfgs[0]["state_space_type"] == "discrete"
+    assert cfgs[-1]["delay"] == 2 and cfgs[-1]["sequence_length"] == 3
+    assert cfgs[-1]["transition_noise"] == 0.1 and cfgs[-1]["dummy_seed"] == 1
+    assert sweep.expand_grid({"env": {}}) == ([], [])
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("name,n", [("dqn_seq_del", 5 * 4 * 10),
+                                    ("dqn_p_r_noises", 5 * 5 * 10)])
+def test_reads_the_reference_experiment_files(name, n):
+    from oracle.ref_loader import REFERENCE_ROOT
+    mod = sweep.load_experiment(os.path.join(REFERENCE_ROOT, "experiments", name))
+    env_keys, cfgs = sweep.env_grid(mod)
+    assert len(cfgs) == n
+    assert "delay" in env_keys and "dummy_seed" in env_keys
+    assert all(c["state_space_type"] == "discrete" for c in cfgs)
+
+
+@pytest.mark.gpu
+def test_sweep_runs_the_grid_and_writes_the_reference_csv(tmp_path):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sw = sweep.Sweep(FIXTURE, envs_per_cell=128)
+    assert sw.n_cells == 36 and sw.env.num_envs == 36 * 128
+    res = sw.run(400)
+    assert np.all(res["transitions"] == 128 * 400)
+    # random policy on the 8-state toy MDP: episodes last ~4 steps
+    assert np.all(np.abs(res["episode_len_mean"] - 4.0) < 0.5)
+    pn = np.array([c["transition_noise"] for c in sw.cell_configs])
+    assert np.all(res["noisy_transitions"][pn == 0] == 0)
+    assert np.all(res["noisy_transitions"][pn > 0] > 0)
+    # longer sequences are rewarded less often
+    L = np.array([c["sequence_length"] for c in sw.cell_configs])
+    assert res["episode_reward_mean"][L == 1].mean() > \
+        res["episode_reward_mean"][L == 3].mean()
+    path = sw.write_csv(str(tmp_path / "dqn_seq_del_like.csv"))
+    lines = open(path).read().splitlines()
+    assert lines[0].startswith("# training_iteration, algorithm, state_space_size,")
+    assert lines[0].endswith("timesteps_total, episode_reward_mean, episode_len_mean")
+    assert len(lines) == 37
+    first = lines[1].split(" ")
+    assert first[:4] == ["1", "RandomPolicy", "8", "8"]
+    assert first[6] == "2.50e-01" and first[7] == "False"
+    assert len(first) == 2 + 10 + 3
