@@ -20,6 +20,7 @@ namespace mdpp {
 constexpr int kRBlock = 128;
 constexpr int kMaskRows = 64;
 constexpr int kMaskCentre = 31;
+constexpr int kRotCols = 80;  // bounding box of the rotated polygon: <= 2*30+7+2
 
 struct RenderDParams {
   mdpp_image_discrete_tables tb;
@@ -39,9 +40,12 @@ __device__ __forceinline__ int floor_div(int a, int b) {
   return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
 }
 
-__global__ void __launch_bounds__(kRBlock)
+// 12 CTAs per SM (40 registers): the kernel is short, occupancy hides the
+// per-image prologue latency
+__global__ void __launch_bounds__(kRBlock, 12)
 render_discrete_kernel(const __grid_constant__ RenderDParams p) {
   __shared__ uint64_t mask[kMaskRows];   // column bitmaps of the polygon
+  __shared__ uint64_t rmask[kRotCols][2]; // rotated + flipped polygon, box-local
   __shared__ int prm[8];
   const int64_t m = blockIdx.x;
   const mdpp_image_discrete_tables& tb = p.tb;
@@ -162,6 +166,59 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
     return (uint32_t)((mask[mx] >> my) & 1ull);
   };
 
+  // Rotated images: gather the polygon ONCE into box-local column bitmaps of
+  // the final image (two threads per column, the inverse affine stepped
+  // incrementally along y); the output pass then reads bit strings exactly
+  // like the unrotated case.  Bit k of column c is final pixel
+  // (rcx0 + c, rcy0 + k).
+  const int rcx0 = max(bx0, 0), rcx1 = min(min(bx1, W - 1), rcx0 + kRotCols - 1);
+  const int rcy0 = max(by0, 0), rcy1 = min(min(by1, H - 1), rcy0 + 127);
+  if (rot >= 0) {
+    const int ncols = rcx1 - rcx0 + 1, nrows = rcy1 - rcy0 + 1;
+    for (int w = threadIdx.x; w < 2 * kRotCols; w += kRBlock) (&rmask[0][0])[w] = 0ull;
+    __syncthreads();
+    // work item = 8 consecutive rows of one column (keeps all lanes busy);
+    // items of a column OR their bits into the column's two words
+    const int segs = (nrows + 7) >> 3;
+    for (int w = threadIdx.x; w < ncols * segs; w += kRBlock) {
+      const int c = w / segs, sgm = w - c * segs;
+      const int x = rcx0 + c;
+      const int fx = flip == 1 ? W - 1 - x : x;
+      const int k0 = sgm * 8, k1 = min(nrows, k0 + 8);      // box-local rows
+      const int sy = flip == 2 ? -1 : 1;                    // d(fy) / d(y)
+      const int fy = flip == 2 ? H - 1 - (rcy0 + k0) : rcy0 + k0;
+      int X = a2 + a1 * fy + a0 * fx, Y = a5 + a4 * fy + a3 * fx;
+      const int dX = a1 * sy, dY = a4 * sy;
+      uint32_t bits = 0;
+      for (int k = k0; k < k1; ++k) {
+        const int rx = X >> 16, ry = Y >> 16;
+        const int mx = rx - sw + kMaskCentre, my = ry - sh + kMaskCentre;
+        if ((unsigned)rx < (unsigned)W && (unsigned)ry < (unsigned)H &&
+            (unsigned)mx < (unsigned)kMaskRows && (unsigned)my < 64u)
+          bits |= (uint32_t)((mask[mx] >> my) & 1ull) << (k - k0);
+        X += dX; Y += dY;
+      }
+      if (bits)
+        atomicOr(reinterpret_cast<unsigned long long*>(&rmask[c][k0 >> 6]),
+                 (unsigned long long)bits << (k0 & 63));
+    }
+    __syncthreads();
+  }
+  // n (<= 16) pixels of final column x starting at y, from the rotated bitmaps
+  auto rot_bits = [&](int x, int y, int n) -> uint32_t {
+    const int c = x - rcx0;
+    if ((unsigned)c > (unsigned)(rcx1 - rcx0)) return 0u;
+    const uint64_t lo = rmask[c][0], hi = rmask[c][1];
+    const int k = y - rcy0;  // bit of pixel y
+    uint64_t v;
+    if (k <= -64 || k >= 128) v = 0;
+    else if (k < 0) v = lo << (-k);
+    else if (k == 0) v = lo;
+    else if (k < 64) v = (lo >> k) | (hi << (64 - k));
+    else v = hi >> (k - 64);
+    return (uint32_t)v & ((1u << n) - 1u);
+  };
+
   const int total = W * H;
   uint8_t* out = p.out + m * (int64_t)total;
   if (total % 16 == 0) {  // every image starts 16-byte aligned
@@ -178,13 +235,10 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
     // chunks a column span can touch, rounded up to a power of two so the
     // (column, k) decomposition of a work item is a shift and a mask
     const int per_col = ((cy1 - cy0) >> 4) + 2;
-    // (for the cheap unrotated items; the rotated ones cost 16 gathers each,
-    // there an exact division wastes fewer lanes)
     const int lg = per_col <= 4 ? 2 : per_col <= 8 ? 3 : per_col <= 16 ? 4 : 5;
-    const int n_work = rot < 0 ? (cx1 - cx0 + 1) << lg : (cx1 - cx0 + 1) * per_col;
+    const int n_work = (cx1 - cx0 + 1) << lg;
     for (int wi = threadIdx.x; wi < n_work; wi += kRBlock) {
-      const int q = rot < 0 ? wi >> lg : wi / per_col;
-      const int col = cx0 + q, k = rot < 0 ? wi & ((1 << lg) - 1) : wi - q * per_col;
+      const int col = cx0 + (wi >> lg), k = wi & ((1 << lg) - 1);
       const int chunk = ((col * H + cy0) >> 4) + k;
       if (chunk > ((col * H + cy1) >> 4)) continue;
       const int idx0 = chunk * 16;
@@ -196,12 +250,8 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
         bits = column_bits(x0, y0, n0);
         if (n0 < 16 && x0 + 1 < W) bits |= column_bits(x0 + 1, 0, 16 - n0) << n0;
       } else {
-        int x = x0, y = y0;
-#pragma unroll
-        for (int b = 0; b < 16; ++b) {
-          bits |= pixel(x, y) << b;
-          if (++y == H) { y = 0; ++x; }
-        }
+        bits = rot_bits(x0, y0, n0);
+        if (n0 < 16 && x0 + 1 < W) bits |= rot_bits(x0 + 1, 0, 16 - n0) << n0;
       }
       __stcs(out4 + chunk, make_uint4(expand4(bits), expand4(bits >> 4),
                                       expand4(bits >> 8), expand4(bits >> 12)));
