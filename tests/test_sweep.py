@@ -66,3 +66,54 @@ def test_sweep_runs_the_grid_and_writes_the_reference_csv(tmp_path):
     assert first[:4] == ["1", "RandomPolicy", "8", "8"]
     assert first[6] == "2.50e-01" and first[7] == "False"
     assert len(first) == 2 + 10 + 3
+
+
+@pytest.mark.reference
+def test_every_rltoy_experiment_of_the_reference_is_accepted():
+    """Drop-in coverage: the env grid of every `RLToy-v0` experiment file in
+    the reference's experiments/ directory goes through our config parser and
+    (for discrete envs) table builder.  The only rejections are the files the
+    reference itself cannot run at HEAD or that need a 'next' row:
+    *_move_to_a_point_irr_dims (target_point / relevant_indices mismatch --
+    the reference's own assert, rl_toy_env.py:649-651) and dqn_irr_dims
+    (discrete irrelevant_features)."""
+    import contextlib
+    import copy
+    import glob
+    import io
+    from oracle.ref_loader import REFERENCE_ROOT
+    from mdp_playground_b200.config import parse_config
+    from mdp_playground_b200.tables import build_discrete_tables
+    ok, rejected = [], {}
+    for f in sorted(glob.glob(os.path.join(REFERENCE_ROOT, "experiments", "*.py"))):
+        name = os.path.basename(f)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                mod = sweep.load_experiment(f)
+        except (FileNotFoundError, ModuleNotFoundError):
+            continue  # needs files / packages that are not part of the repo
+        if getattr(mod, "env_config", {}).get("env") != "RLToy-v0" \
+                or not hasattr(mod, "var_env_configs"):
+            continue
+        _, cfgs = sweep.env_grid(mod)
+        seen = set()
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                for c in cfgs:
+                    key = repr(sorted((k, repr(v)) for k, v in c.items()
+                                      if k != "dummy_seed"))
+                    if key in seen:
+                        continue
+                    seen.add(key)
+                    sp = parse_config(copy.deepcopy(c))
+                    if sp.kind == "discrete":
+                        build_discrete_tables(sp)
+            ok.append(name)
+        except (AssertionError, NotImplementedError) as e:
+            rejected[name] = repr(e)
+    assert len(ok) >= 84, (len(ok), rejected)
+    assert set(rejected) <= {"ddpg_move_to_a_point_irr_dims.py",
+                             "sac_move_to_a_point_irr_dims.py",
+                             "td3_move_to_a_point_irr_dims.py",
+                             "dqn_irr_dims.py"}, rejected
