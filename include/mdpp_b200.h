@@ -91,7 +91,10 @@ typedef struct mdpp_discrete_group {
   int32_t has_transition_noise;  /* truthy transition_noise (:1604)          */
   int32_t has_reward_noise;      /* "reward_noise" key present (:398, :1982) */
   int32_t reserved0;
-  double transition_noise;       /* p                                        */
+  double transition_noise;       /* p: MDPP_NOISE_PHILOX draws the noisy state
+                                    from (p, S) in closed form -- P[s,a] w.p.
+                                    1 - p, each other state p / (S - 1), the
+                                    distribution of :1606-1617               */
   double reward_noise_std;       /* sigma                                    */
   double reward_scale;
   double reward_shift;
@@ -100,8 +103,10 @@ typedef struct mdpp_discrete_group {
   const uint8_t* terminal;       /* [S]    1 = terminal                      */
   const double* init_cdf;        /* [S]    cumsum(init_dist)/last            */
   const double* noise_cdf;       /* [S*S]  row s' = cdf of the noisy draw
-                                           around s' (:1605-1612); may be
-                                           NULL when !has_transition_noise   */
+                                           around s' (:1605-1612), searched with
+                                           the recorded uniform in
+                                           MDPP_NOISE_REPLAY; may be NULL when
+                                           !has_transition_noise             */
   const int32_t* sequences;      /* [n_sequences*L] rewardable sequences     */
   const double* sequence_rewards;/* [n_sequences]                            */
   const double* reward_matrix;   /* [S*A] when custom_reward, else NULL      */

@@ -177,23 +177,30 @@ extern "C" int mdpp_set_discrete_groups(mdpp_ctx* ctx,
         put_row(reinterpret_cast<double*>(gb.data() + d.off_noise_cdf) + (size_t)r * Sp,
                 in.noise_cdf + (size_t)r * S);
     }
-    // Integer form of the noise cdf for the Philox mode: u = (w + 0.5) 2^-32,
-    // so cdf <= u  <=>  w >= ceil(cdf 2^32 - 0.5).  cdf * 2^32 and the - 0.5 are
-    // exact in fp64 (cdf < 2, 53-bit mantissa), hence the integer compare
-    // decides exactly like the fp64 one.  Saturated thresholds (cdf ~ 1 and
-    // the sentinels) can only pass at w = 2^32 - 1, where the search result is
-    // clamped to S-1 -- which is also the exact answer there.
-    if (in.has_transition_noise) {
-      d.off_noise_thr = reserve(S * Sp * 4, 16);
-      uint32_t* thr = reinterpret_cast<uint32_t*>(gb.data() + d.off_noise_thr);
-      for (int r = 0; r < S; ++r)
-        for (int k = 0; k < Sp; ++k) {
-          const double c = k < S ? in.noise_cdf[(size_t)r * S + k] : 2.0;
-          const double t = std::ceil(c * 4294967296.0 - 0.5);
-          thr[(size_t)r * Sp + k] = t <= 0.0 ? 0u : t >= 4294967295.0 ? 0xFFFFFFFFu
-                                                                       : (uint32_t)t;
-        }
+    // Philox-mode transition noise in closed form.  The reference's noisy
+    // distribution (rl_toy_env.py:1606-1617) is P(P[s,a]) = 1 - p and p / (S-1)
+    // for each other state, so a 32-bit word w decides: noisy iff w < T with
+    // T = round(p 2^32); given that, w is uniform on [0, T) and
+    // k = floor(w M / 2^sh), M = floor((S-1) 2^sh / T), picks one of the S-1
+    // other states (every state within 2^-32 of its probability; k <= S-2
+    // because M is rounded down).  The noisy state is k + (k >= P[s,a]).  Only
+    // that last step depends on the env state; the rest is drawn ahead.
+    if (in.has_transition_noise && S >= 2) {
+      double t = std::floor(in.transition_noise * 4294967296.0 + 0.5);
+      uint64_t T = t <= 0.0 ? 0ull : t >= 4294967296.0 ? (1ull << 32) : (uint64_t)t;
+      d.pn_T = T;
+      if (T > 0) {
+        int sh = 63;
+        unsigned __int128 M;
+        while (((M = (((unsigned __int128)(S - 1)) << sh) / T) >> 32) && sh > 32) --sh;
+        // T < S-1 (p below ~S 2^-32) cannot be uniform over the others anyway
+        d.pn_M = (M >> 32) ? 0xFFFFFFFFu : (uint32_t)M;
+        d.pn_shift = sh - 32;
+      }
     }
+    if (S <= 64)
+      for (int k = 0; k < S; ++k)
+        if (in.terminal[k]) d.term_mask |= 1ull << k;
     // Guide table of the auto-reset draw: bucket b = top 12 bits of the 32-bit
     // Philox word w (u = (w + 0.5) 2^-32).  If every w of the bucket maps to
     // the same initial state the entry holds it, else kGuideMiss (the device
@@ -221,7 +228,11 @@ extern "C" int mdpp_set_discrete_groups(mdpp_ctx* ctx,
         return fail(ctx, MDPP_EINVAL, "custom_reward needs reward_matrix");
       d.lookup_kind = LOOKUP_MATRIX;
       d.off_R = reserve(S * A * 8, 16);
-      std::memcpy(gb.data() + d.off_R, in.reward_matrix, (size_t)S * A * 8);
+      // "+ 0.0" maps a -0.0 entry to +0.0 (same for the value tables below):
+      // with no negative zero entering the reward arithmetic the kernels may
+      // drop `* 1.0` and `+ 0.0` without changing a single result bit
+      double* R = reinterpret_cast<double*>(gb.data() + d.off_R);
+      for (int i = 0; i < S * A; ++i) R[i] = in.reward_matrix[i] + 0.0;
     } else {
       if (in.n_sequences < 0 || (in.n_sequences > 0 &&
                                  (!in.sequences || !in.sequence_rewards)))
@@ -242,14 +253,14 @@ extern "C" int mdpp_set_discrete_groups(mdpp_ctx* ctx,
       {
         double* v = reinterpret_cast<double*>(gb.data() + d.off_values);
         v[0] = 0.0;
-        for (int i = 0; i < n; ++i) v[i + 1] = in.sequence_rewards[i];
+        for (int i = 0; i < n; ++i) v[i + 1] = in.sequence_rewards[i] + 0.0;
       }
       if (b * L <= kLutMaxBits) {
         d.lookup_kind = LOOKUP_LUT;
         const int entries = 1 << (b * L);
         d.off_lut = reserve(entries * 8, 16);  // rewards stored directly
         double* lut = reinterpret_cast<double*>(gb.data() + d.off_lut);
-        for (int i = 0; i < n; ++i) lut[keys[i]] = in.sequence_rewards[i];
+        for (int i = 0; i < n; ++i) lut[keys[i]] = in.sequence_rewards[i] + 0.0;
       } else {
         d.lookup_kind = LOOKUP_HASH;
         int log2cap = 4;

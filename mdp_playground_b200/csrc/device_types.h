@@ -20,8 +20,13 @@ struct DiscreteGroupDev {
   // byte offsets inside the blob
   int32_t off_P, off_term, off_init_cdf, off_noise_cdf;
   int32_t off_lut, off_hash_keys, off_hash_vals, off_values, off_R, off_guide;
-  int32_t off_noise_thr;  // u32 [S][2^cdf_log2] integer thresholds of noise_cdf
   int32_t blob_bytes;
+  // Philox-mode transition noise in closed form (context.cu, noise_params):
+  // noisy iff w < pn_T; index among the S-1 other states = (w * pn_M) >> (32 + pn_shift)
+  uint32_t pn_M;
+  int32_t pn_shift;
+  uint64_t pn_T;
+  uint64_t term_mask;  // bit s = terminal(s); valid when S <= 64
   int64_t blob_offset;  // of this group's blob inside the context blob buffer
   int64_t env_begin, env_count;
   int64_t gid_base;  // global Philox id of the group's first env

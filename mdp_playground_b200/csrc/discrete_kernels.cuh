@@ -100,22 +100,15 @@ __device__ __forceinline__ int cdf_search(const double* cdf, int log2n, int n,
   return min(pos, n - 1);
 }
 
-// The same search over integer thresholds: number of entries <= w.
-template <int LOG2>
-__device__ __forceinline__ int thr_search(const uint32_t* thr, int log2n, int n,
-                                          uint32_t w) {
-  int pos = 0;
-  if (LOG2 >= 0) {
-#pragma unroll
-    for (int b = LOG2 - 1; b >= 0; --b)
-      if (thr[pos + (1 << b) - 1] <= w) pos += 1 << b;
-  } else {
-#pragma unroll 1
-    for (int step = (1 << log2n) >> 1; step > 0; step >>= 1)
-      if (thr[pos + step - 1] <= w) pos += step;
-  }
-  return min(pos, n - 1);
-}
+// Identities a specialised build may use (see chain_step).
+#if defined(MDPP_SCALE) && defined(MDPP_SHIFT) && defined(MDPP_TERM_REWARD)
+constexpr bool kScaleIsOne = (MDPP_SCALE) == 1.0;
+constexpr bool kShiftIsZero = (MDPP_SHIFT) == 0.0 && !MDPP_SHIFT_NEGZERO;
+constexpr bool kTermRewardIsZero =
+    (MDPP_TERM_REWARD) == 0.0 && !MDPP_TERM_NEGZERO && !MDPP_SHIFT_NEGZERO;
+#else
+constexpr bool kScaleIsOne = false, kShiftIsZero = false, kTermRewardIsZero = false;
+#endif
 
 struct GroupView {  // per-thread copy of the scalars + table pointers
   int S, A, L, delay, every_n, lookup_kind, key_bits, hash_shift;
@@ -124,12 +117,14 @@ struct GroupView {  // per-thread copy of the scalars + table pointers
   const uint8_t* guide;
   uint32_t hash_mask;
   uint64_t key_mask;
+  uint64_t pn_T, term_mask;  // closed-form transition noise (device_types.h)
+  uint32_t pn_M;
+  int pn_shift;
   double r_std, scale, shift, term_reward_scaled;
   const uint16_t* P;
   const uint8_t* term;
   const double* init_cdf;
   const double* noise_cdf;
-  const uint32_t* noise_thr;
   const double* lut;
   const uint64_t* hash_keys;
   const uint32_t* hash_vals;
@@ -154,7 +149,8 @@ __device__ __forceinline__ GroupView make_view(const DiscreteGroupDev& g,
   v.term = tab + g.off_term;
   v.init_cdf = reinterpret_cast<const double*>(tab + g.off_init_cdf);
   v.noise_cdf = reinterpret_cast<const double*>(tab + g.off_noise_cdf);
-  v.noise_thr = reinterpret_cast<const uint32_t*>(tab + g.off_noise_thr);
+  v.pn_T = g.pn_T; v.pn_M = g.pn_M; v.pn_shift = g.pn_shift;
+  v.term_mask = g.term_mask;
   v.lut = reinterpret_cast<const double*>(tab + g.off_lut);
   v.hash_keys = reinterpret_cast<const uint64_t*>(tab + g.off_hash_keys);
   v.hash_vals = reinterpret_cast<const uint32_t*>(tab + g.off_hash_vals);
@@ -208,6 +204,9 @@ __device__ __forceinline__ GroupView make_view(const DiscreteGroupDev& g,
 #ifdef MDPP_HAS_GUIDE
   v.has_guide = MDPP_HAS_GUIDE;
 #endif
+#ifdef MDPP_PN_T
+  v.pn_T = MDPP_PN_T; v.pn_M = MDPP_PN_M; v.pn_shift = MDPP_PN_SHIFT;
+#endif
 #ifdef MDPP_R_STD
   v.r_std = MDPP_R_STD;
 #endif
@@ -237,6 +236,8 @@ __device__ __forceinline__ double sequence_reward(const GroupView& v,
   }
 }
 
+constexpr int kMaxRingRegs = 4;
+
 struct EnvRegs {
   int32_t s;
   uint64_t key;
@@ -245,6 +246,7 @@ struct EnvRegs {
   uint32_t ep;
   int32_t ring_pos;  // step % delay
   int32_t hist_pos;  // (step + 1) % history_depth
+  double fifo[kMaxRingRegs];  // Cfg::RING_REGS: the delay FIFO, newest first
   // statistics accumulated over the launch
   double sum_reward, sum_abs_rnoise;
   uint32_t n_noisy, n_episodes, n_terminated, n_steps;
@@ -289,10 +291,14 @@ __device__ __forceinline__ void philox_quad_draws(
 //   CDF_LOG2 >= 0: cdf rows have exactly 2^CDF_LOG2 entries (unrolled search).
 //   SINGLE the launch has one configuration group: its descriptor comes
 //         from the kernel parameters instead of shared memory.
+//   RING_REGS = d > 0: every group has delay d <= kMaxRingRegs and the FIFO
+//         lives in registers as a shift register (in unrolled code the shift
+//         is a renaming, i.e. free); 0: ring buffer in shared / global memory.
 template <int NOISE_, int NORMAL_, bool SMEM_, bool RING_SMEM_, bool FAST_,
-          int CDF_LOG2_, bool SINGLE_ = false>
+          int CDF_LOG2_, bool SINGLE_ = false, int RING_REGS_ = 0>
 struct Cfg {
   static constexpr bool SINGLE = SINGLE_;
+  static constexpr int RING_REGS = RING_REGS_;
   static constexpr int NOISE = NOISE_;
   static constexpr int NORMAL = NORMAL_;
   static constexpr bool SMEM = SMEM_;
@@ -311,7 +317,7 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
                                         int64_t env, uint32_t gid,
                                         uint64_t step_base, int t0,
                                         int n_valid, int32_t* act, double* u_tr,
-                                        uint32_t* w_tr, double* n_rw, int32_t* s0) {
+                                        int32_t* k_tr, double* n_rw, int32_t* s0) {
   constexpr int NOISE = C::NOISE;
   constexpr int NORMAL = C::NORMAL;
   constexpr bool FAST = C::FAST;
@@ -333,16 +339,16 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
                            STREAM_ACTION, p.k0, p.k1);
       act[j] = (int32_t)__umulhi(w.x, (uint32_t)v.A);
     }
-    u_tr[j] = 0.0; w_tr[j] = 0u; n_rw[j] = 0.0; u_rs[j] = 0.0; s0[j] = 0;
+    u_tr[j] = 0.0; k_tr[j] = -1; n_rw[j] = 0.0; u_rs[j] = 0.0; s0[j] = 0;
     if (NOISE == MDPP_NOISE_REPLAY && j < n_valid) {
       if (v.has_pnoise) u_tr[j] = ld_stream_f64(p.io.replay_transition_u + off);
       if (v.has_rnoise) n_rw[j] = ld_stream_f64(p.io.replay_reward_noise + off);
       if (autoreset) u_rs[j] = ld_stream_f64(p.io.replay_reset_u + off);
     }
   }
-  uint32_t w_rs[U];
+  uint32_t w_rs[U], w_tr[U];
 #pragma unroll
-  for (int j = 0; j < U; ++j) w_rs[j] = 0;
+  for (int j = 0; j < U; ++j) w_rs[j] = w_tr[j] = 0;
   if (NOISE != MDPP_NOISE_REPLAY) {
     const bool want_u = NOISE == MDPP_NOISE_PHILOX && v.has_pnoise;
     const bool want_z = NOISE == MDPP_NOISE_PHILOX && v.has_rnoise;
@@ -369,6 +375,15 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
       }
     }
   }
+  if (NOISE == MDPP_NOISE_PHILOX && v.has_pnoise) {
+    // closed-form noisy draw (device_types.h): -1 = keep P[s,a], else the
+    // index among the S-1 other states; state-independent, so done here
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const uint32_t k = __umulhi(w_tr[j], v.pn_M) >> v.pn_shift;
+      k_tr[j] = ((uint64_t)w_tr[j] < v.pn_T) ? (int32_t)k : -1;
+    }
+  }
   if (autoreset) {  // candidate initial states, also state-independent
 #pragma unroll
     for (int j = 0; j < U; ++j) {
@@ -392,7 +407,7 @@ template <typename C>
 __device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupView& v,
                                            EnvRegs& e, double* ring_smem,
                                            int ring_stride, int64_t env, int64_t off,
-                                           int32_t act, double u_tr, uint32_t w_tr,
+                                           int32_t act, double u_tr, int32_t k_tr,
                                            double n_rw, int32_t s0) {
   constexpr int NOISE = C::NOISE;
   constexpr bool RING_SMEM = C::RING_SMEM;
@@ -403,16 +418,17 @@ __device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupVi
   uint32_t a = (uint32_t)act;
   if (a >= (uint32_t)v.A) a = (uint32_t)v.A - 1;  // memory safety only
   int32_t nxt = v.P[e.s * v.A + (int32_t)a];
-  if (NOISE != MDPP_NOISE_OFF && v.has_pnoise) {
-    // replay: the recorded fp64 uniform against the fp64 cdf; Philox: the
-    // 32-bit word against the equivalent integer thresholds
-    const int32_t noisy = NOISE == MDPP_NOISE_REPLAY
-        ? cdf_search<C::CDF_LOG2>(v.noise_cdf + nxt * v.cdf_stride, v.cdf_log2,
-                                  v.S, u_tr)
-        : thr_search<C::CDF_LOG2>(v.noise_thr + nxt * v.cdf_stride, v.cdf_log2,
-                                  v.S, w_tr);
+  if (NOISE == MDPP_NOISE_REPLAY && v.has_pnoise) {
+    // the recorded fp64 uniform against the fp64 cdf, like the reference
+    const int32_t noisy = cdf_search<C::CDF_LOG2>(
+        v.noise_cdf + nxt * v.cdf_stride, v.cdf_log2, v.S, u_tr);
     e.n_noisy += (noisy != nxt);
     nxt = noisy;
+  } else if (NOISE == MDPP_NOISE_PHILOX && v.has_pnoise) {
+    if (k_tr >= 0) {  // one of the S-1 other states: skip over P[s,a]
+      nxt = k_tr + (k_tr >= nxt);
+      e.n_noisy += 1;
+    }
   }
   e.key = ((e.key << v.key_bits) | (uint64_t)nxt) & v.key_mask;
   e.tl += 1;
@@ -423,7 +439,14 @@ __device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupVi
   } else if (e.tl >= v.L) {  // isnan(aug[delay]) gate <=> t < L
     r = sequence_reward(v, e.key);
   }
-  if (v.delay > 0) {  // FIFO of depth d: pay out what was earned d steps ago
+  if (C::RING_REGS > 0) {
+    constexpr int D = C::RING_REGS > 0 ? C::RING_REGS : 1;
+    const double delayed = (e.tl > D) ? e.fifo[D - 1] : 0.0;
+#pragma unroll
+    for (int k = D - 1; k > 0; --k) e.fifo[k] = e.fifo[k - 1];
+    e.fifo[0] = r;
+    r = delayed;
+  } else if (v.delay > 0) {  // FIFO of depth d: pay out what was earned d steps ago
     double* slot = RING_SMEM
         ? ring_smem + e.ring_pos * ring_stride
         : p.st.ring + (int64_t)e.ring_pos * N + env;
@@ -438,10 +461,16 @@ __device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupVi
     e.sum_abs_rnoise += fabs(n_rw);
     r = __dadd_rn(r, n_rw);
   }
-  r = __dmul_rn(r, v.scale);
-  r = __dadd_rn(r, v.shift);
-  const bool done = v.term[nxt] != 0;
-  if (done) r = __dadd_rn(r, v.term_reward_scaled);
+  // `* 1.0` is the identity; `+ 0.0` only turns -0.0 into +0.0, and no -0.0
+  // can reach this point when scale == 1 (context.cu stores no negative
+  // zero and x + y is -0.0 only if both are) -- so a specialised build whose
+  // literals say so drops these operations, bit-exactly
+  if (!kScaleIsOne) r = __dmul_rn(r, v.scale);
+  if (!(kScaleIsOne && kShiftIsZero)) r = __dadd_rn(r, v.shift);
+  const bool done = v.S <= 64 ? ((v.term_mask >> nxt) & 1ull) != 0
+                              : v.term[nxt] != 0;
+  if (!kTermRewardIsZero)
+    if (done) r = __dadd_rn(r, v.term_reward_scaled);
   const bool trunc = horizon > 0 && e.tl >= horizon;
   e.n_terminated += done;
   e.s = nxt;
@@ -469,7 +498,7 @@ __device__ __forceinline__ void phase_b(const RolloutParams& p, const GroupView&
                                         EnvRegs& e, double* ring_smem, int ring_stride,
                                         int64_t env, int t0, int n_valid,
                                         const int32_t* act, const double* u_tr,
-                                        const uint32_t* w_tr, const double* n_rw,
+                                        const int32_t* k_tr, const double* n_rw,
                                         const int32_t* s0) {
   const int64_t N = n_envs_of(p);
   const int64_t off0 = (int64_t)t0 * N + env;
@@ -477,7 +506,7 @@ __device__ __forceinline__ void phase_b(const RolloutParams& p, const GroupView&
   for (int j = 0; j < U; ++j) {
     if (PARTIAL && j >= n_valid) break;
     chain_step<C>(p, v, e, ring_smem, ring_stride, env, off0 + (int64_t)j * N,
-                  act[j], u_tr[j], w_tr[j], n_rw[j], s0[j]);
+                  act[j], u_tr[j], k_tr[j], n_rw[j], s0[j]);
   }
   e.n_steps += PARTIAL ? n_valid : U;
 }
@@ -488,10 +517,10 @@ __device__ __forceinline__ void run_chunk(const RolloutParams& p,
                                           double* ring_smem, int64_t env,
                                           uint32_t gid, uint64_t step_base, int t0) {
   int32_t act[U], s0[U];
-  uint32_t w_tr[U];
+  int32_t k_tr[U];
   double u_tr[U], n_rw[U];
-  phase_a<C, U>(p, v, env, gid, step_base, t0, U, act, u_tr, w_tr, n_rw, s0);
-  phase_b<C, U, false>(p, v, e, ring_smem, kBlock, env, t0, U, act, u_tr, w_tr,
+  phase_a<C, U>(p, v, env, gid, step_base, t0, U, act, u_tr, k_tr, n_rw, s0);
+  phase_b<C, U, false>(p, v, e, ring_smem, kBlock, env, t0, U, act, u_tr, k_tr,
                        n_rw, s0);
 }
 
@@ -551,9 +580,17 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
   e.n_noisy = e.n_episodes = e.n_terminated = e.n_steps = 0;
 
   if (active) {
-    if (RING_SMEM)
+    // the value written j steps ago sits in ring slot (pos - j) mod d
+    if (C::RING_REGS > 0) {
+#pragma unroll
+      for (int k = 0; k < C::RING_REGS; ++k) {
+        const int slot = (e.ring_pos + 2 * C::RING_REGS - 1 - k) % C::RING_REGS;
+        e.fifo[k] = p.st.ring[(int64_t)slot * N + env];
+      }
+    } else if (RING_SMEM) {
       for (int k = 0; k < v.delay; ++k)
         ring_smem[k * kBlock] = p.st.ring[(int64_t)k * N + env];
+    }
     int t0 = 0;
     // chunks of kChunk steps start on a multiple-of-4 global step (the Philox
     // draws come in groups of 4 steps); peel single steps until aligned
@@ -569,9 +606,17 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
     p.st.seq_key[env] = e.key;
     p.st.t_episode[env] = e.tl;
     p.st.episode[env] = e.ep;
-    if (RING_SMEM)
+    if (C::RING_REGS > 0) {
+      const int pos_end = (int)((step_base + (uint64_t)p.T) % (uint64_t)C::RING_REGS);
+#pragma unroll
+      for (int k = 0; k < C::RING_REGS; ++k) {
+        const int slot = (pos_end + 2 * C::RING_REGS - 1 - k) % C::RING_REGS;
+        p.st.ring[(int64_t)slot * N + env] = e.fifo[k];
+      }
+    } else if (RING_SMEM) {
       for (int k = 0; k < v.delay; ++k)
         p.st.ring[(int64_t)k * N + env] = ring_smem[k * kBlock];
+    }
   }
   if (p.st.stats) {
     double vals[MDPP_N_STATS];

@@ -14,6 +14,7 @@
 // or MDPP_JIT=0 is set, the caller falls back to the AOT kernels.
 #include <dlfcn.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -129,6 +130,18 @@ std::vector<std::string> defines_for(const std::vector<DiscreteGroupDev>& groups
   if (UNIFORM(scale)) d.push_back(D("SCALE", hexf(g.scale)));
   if (UNIFORM(shift)) d.push_back(D("SHIFT", hexf(g.shift)));
   if (UNIFORM(term_reward_scaled)) d.push_back(D("TERM_REWARD", hexf(g.term_reward_scaled)));
+  if (UNIFORM(shift)) d.push_back(D("SHIFT_NEGZERO", std::signbit(g.shift) && g.shift == 0.0 ? "1" : "0"));
+  if (UNIFORM(term_reward_scaled))
+    d.push_back(D("TERM_NEGZERO",
+                  std::signbit(g.term_reward_scaled) && g.term_reward_scaled == 0.0 ? "1" : "0"));
+  if (UNIFORM(pn_T) && UNIFORM(pn_M) && UNIFORM(pn_shift)) {
+    d.push_back(D("PN_T", std::to_string((unsigned long long)g.pn_T) + "ull"));
+    d.push_back(D("PN_M", std::to_string(g.pn_M) + "u"));
+    d.push_back(D("PN_SHIFT", I(g.pn_shift)));
+  }
+  // delay FIFO in registers when every group has the same small delay
+  d.push_back(D("CFG_RING_REGS",
+                I(UNIFORM(delay) && g.delay >= 1 && g.delay <= kMaxRingRegs ? g.delay : 0)));
 #undef UNIFORM
   d.push_back(D("N_ENVS", I(p.st.n_envs) + "ll"));
   d.push_back(D("AUTORESET", I(p.autoreset)));
@@ -145,7 +158,8 @@ std::vector<std::string> defines_for(const std::vector<DiscreteGroupDev>& groups
 const char* kEntrySource = R"SRC(
 #include "discrete_kernels.cuh"
 using JitCfg = mdpp::Cfg<MDPP_CFG_NOISE, MDPP_CFG_NORMAL, true, MDPP_CFG_RING,
-                         MDPP_CFG_FAST, MDPP_CFG_CDF, MDPP_CFG_SINGLE>;
+                         MDPP_CFG_FAST, MDPP_CFG_CDF, MDPP_CFG_SINGLE,
+                         MDPP_CFG_RING_REGS>;
 extern "C" __global__ void __launch_bounds__(mdpp::kBlock, mdpp::kMinBlocksPerSM)
 mdpp_jit_rollout(const __grid_constant__ mdpp::RolloutParams p) {
   mdpp::rollout_body<JitCfg>(p);
@@ -352,6 +366,7 @@ extern "C" int mdpp_jit_selftest(char* log, int log_bytes) {
   g.S = 8; g.A = 8; g.L = 3; g.delay = 2; g.every_n = 1; g.key_bits = 3;
   g.key_mask = 511; g.has_pnoise = 1; g.has_rnoise = 1; g.cdf_log2 = 3;
   g.has_guide = 1; g.r_std = 0.25; g.scale = 1.0;
+  g.pn_T = 429496730ull; g.pn_M = 2348810237u; g.pn_shift = 25;
   RolloutParams p;
   std::memset(&p, 0, sizeof p);
   p.st.n_envs = 65536; p.autoreset = 1; p.horizon = 100;

@@ -102,7 +102,10 @@ __device__ __forceinline__ void normal_pair_fast(uint32_t a, uint32_t b,
   const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);
   const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
   // -2 ln u = -2 ln2 * log2 u
-  const float r = __fsqrt_rn(-1.3862943611198906f * __log2f(u1));
+  // u1 is in [2^-25, 1): no denormal handling needed, so the bare SFU forms
+  float lg, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * lg));
   float s, c;
   __sincosf(6.283185307179586f * u2, &s, &c);
   *z0 = (double)(r * c);

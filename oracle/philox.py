@@ -72,13 +72,42 @@ def _quad_words(seed, env_ids, step, stream):
                          stream, seed)
 
 
-def step_noise(seed, env_ids, step, want_normal=True, fast=False):
-    """(transition uniform, N(0,1)) of global step `step`.  The draws come in
+def transition_noise_params(p, n_states):
+    """Closed-form Philox-mode transition noise (csrc/context.cu): the
+    reference's noisy distribution (rl_toy_env.py:1606-1617) gives P[s,a]
+    probability 1 - p and each of the S-1 other states p / (S-1).  A 32-bit
+    word w is noisy iff w < T = round(p 2^32); then floor(w M / 2^sh) with
+    M = floor((S-1) 2^sh / T) < 2^32 (largest such sh) indexes the others."""
+    T = min(max(int(np.floor(float(p) * 4294967296.0 + 0.5)), 0), 1 << 32)
+    if T == 0 or n_states < 2:
+        return 0, 0, 32
+    sh = 63
+    while sh > 32 and (((n_states - 1) << sh) // T) >> 32:
+        sh -= 1
+    # T < S-1 (p below ~S 2^-32) cannot be uniform over the others anyway
+    return T, min(((n_states - 1) << sh) // T, 0xFFFFFFFF), sh
+
+
+def noisy_next_state(w, nxt, params):
+    """Philox-mode noisy transition: words `w`, noise-free next states `nxt`."""
+    T, M, sh = params
+    w = np.asarray(w).astype(np.uint64)
+    nxt = np.asarray(nxt, dtype=np.int64)
+    # (w * M) >> sh with sh >= 32, as the device does: mulhi, then shift
+    k = (((w * np.uint64(M)) >> np.uint64(32)) >> np.uint64(sh - 32)).astype(np.int64)
+    return np.where(w < np.uint64(T), k + (k >= nxt), nxt)
+
+
+def step_noise(seed, env_ids, step, want_normal=True, fast=False, raw=False):
+    """(transition uniform, N(0,1)) of global step `step` (`raw`: the 32-bit
+    transition word instead of the uniform).  The draws come in
     groups of 4 steps (counter = step >> 2): STREAM_STEP word j is the 32-bit
     transition uniform of step 4q+j; STREAM_NORMAL words (0,1) and (2,3) feed
     two Box-Muller pairs = the 4 reward normals."""
     j = int(step) & 3
-    u = uniform32(_quad_words(seed, env_ids, step, STREAM_STEP)[j])
+    u = _quad_words(seed, env_ids, step, STREAM_STEP)[j]
+    if not raw:
+        u = uniform32(u)
     z = None
     if want_normal:
         w = _quad_words(seed, env_ids, step, STREAM_NORMAL)

@@ -35,6 +35,8 @@ class VectorDiscreteOracle:
                         if len(k) == self.L}
         self.has_pnoise = bool(e.transition_noise)
         self.noise_cdf = e.noise_cdf if self.has_pnoise else None
+        self.pn_params = px.transition_noise_params(
+            float(e.transition_noise) if self.has_pnoise else 0.0, self.S)
         self.has_rnoise = e.has_reward_noise and e.reward_noise_std is not None
         self.r_std = e.reward_noise_std
         self.scale, self.shift = e.reward_scale, e.reward_shift
@@ -104,11 +106,15 @@ class VectorDiscreteOracle:
             elif self.has_pnoise or self.has_rnoise:
                 u_tr, z = px.step_noise(self.seed, self.gid, step,
                                         want_normal=self.has_rnoise,
-                                        fast=self.fast_normal)
+                                        fast=self.fast_normal, raw=True)
                 if self.has_rnoise:
                     n_rw = self.r_std * z
             nxt = self.P[self.cur, a]
-            if self.has_pnoise:
+            if self.has_pnoise and replay is None:
+                noisy = px.noisy_next_state(u_tr, nxt, self.pn_params)
+                self.stats["noisy_transitions"] += int((noisy != nxt).sum())
+                nxt = noisy
+            elif self.has_pnoise:
                 noisy = np.array([
                     min(int(np.searchsorted(self.noise_cdf[nxt[i]], u_tr[i],
                                             side="right")), self.S - 1)

@@ -66,3 +66,28 @@ def test_philox_oracle_rollout_is_chunk_invariant():
     for k in ra:
         assert np.array_equal(ra[k], np.concatenate([rb1[k], rb2[k]])), k
     assert ra["terminated"].any() and ra["truncated"].any()
+
+
+@pytest.mark.parametrize("p", [1e-9, 0.001, 0.1, 0.25, 1 / 3, 0.5, 0.9, 0.999, 1.0])
+@pytest.mark.parametrize("S", [2, 3, 8, 13, 100, 65535])
+def test_closed_form_transition_noise_is_exact_to_2_pow_minus_32(p, S):
+    """The Philox-mode noisy draw (oracle/philox.py, csrc/context.cu): P(noisy)
+    = T / 2^32 with T = round(p 2^32), and the S-1 other states share [0, T)
+    in bins whose sizes differ from T / (S-1) by less than 2 words."""
+    from oracle import philox as px
+    T, M, sh = px.transition_noise_params(p, S)
+    assert T == int(np.floor(p * 2.0 ** 32 + 0.5)) and 0 < M < 2 ** 32 and 32 <= sh <= 63
+    assert ((T - 1) * M) >> sh <= S - 2          # the index never overflows
+    n = S - 1
+    if T < n:
+        return
+    ks = np.unique(np.concatenate([np.arange(min(n, 50)), np.arange(max(n - 50, 0), n)]))
+    for k in ks.tolist():
+        lo = -((-k << sh) // M)                  # first w with (w M) >> sh == k
+        hi = min(-((-(k + 1) << sh) // M), T)
+        assert abs((hi - lo) - T / n) < 2, (k, lo, hi)
+    w = np.array([0, T // 2, T - 1, T, min(T + 5, 2 ** 32 - 1), 2 ** 32 - 1], dtype=np.uint64)
+    for nxt in (0, S // 2, S - 1):
+        out = px.noisy_next_state(w, np.full(w.shape, nxt), (T, M, sh))
+        assert ((out != nxt) == (w < T)).all()   # noisy <=> state changed
+        assert ((0 <= out) & (out < S)).all()
