@@ -84,6 +84,98 @@ __device__ __forceinline__ int rel_index(const ContinuousParams& p, int k) {
 #endif
 }
 
+// a / inertia (:1655).  For inertia = 2^k the product with 2^-k is the same
+// correctly rounded value as the quotient, without the IEEE division's ~15
+// instructions and slow-path branch; a literal inertia folds the test away.
+__device__ __forceinline__ float div_inertia(float a, float inertia) {
+  const float inv = 1.0f / inertia;  // (plain operator: folds for a literal)
+  const uint32_t bi = __float_as_uint(inertia), bv = __float_as_uint(inv);
+  const bool pow2 = (bi & 0x7FFFFFu) == 0 && (bv & 0x7FFFFFu) == 0 &&
+                    ((bi >> 23) & 0xFF) != 0 && ((bi >> 23) & 0xFF) != 0xFF &&
+                    ((bv >> 23) & 0xFF) != 0 && ((bv >> 23) & 0xFF) != 0xFF;
+  return pow2 ? __fmul_rn(a, inv) : __fdiv_rn(a, inertia);
+}
+__device__ __forceinline__ double div_inertia(double a, double inertia) {
+  const double inv = 1.0 / inertia;
+  const uint64_t bi = (uint64_t)__double_as_longlong(inertia);
+  const uint64_t bv = (uint64_t)__double_as_longlong(inv);
+  const uint64_t man = 0xFFFFFFFFFFFFFull;
+  const bool pow2 = (bi & man) == 0 && (bv & man) == 0 &&
+                    ((bi >> 52) & 0x7FF) != 0 && ((bi >> 52) & 0x7FF) != 0x7FF &&
+                    ((bv >> 52) & 0x7FF) != 0 && ((bv >> 52) & 0x7FF) != 0x7FF;
+  return pow2 ? __dmul_rn(a, inv) : __ddiv_rn(a, inertia);
+}
+
+// One [dim] row of the gym-layout action / observation arrays.  The
+// specialised build knows dim, so rows move as 16- or 8-byte vectors when the
+// row size allows (the C entry points require 16-byte aligned I/O buffers).
+template <typename R>
+__device__ __forceinline__ void load_row(const R* src, int D, R* out) {
+#ifdef MDPP_JIT
+  constexpr int kD = MDPP_C_DIM;
+  constexpr int kVec = (kD * sizeof(R)) % 16 == 0 ? 16 / sizeof(R)
+                     : (kD * sizeof(R)) % 8 == 0 ? 8 / sizeof(R) : 1;
+  if (kVec == 4) {
+#pragma unroll
+    for (int d = 0; d < kD; d += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
+      out[d] = (R)v.x; out[d + 1] = (R)v.y; out[d + 2] = (R)v.z; out[d + 3] = (R)v.w;
+    }
+    return;
+  }
+  if (kVec == 2 && sizeof(R) == 4) {
+#pragma unroll
+    for (int d = 0; d < kD; d += 2) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(src + d));
+      out[d] = (R)v.x; out[d + 1] = (R)v.y;
+    }
+    return;
+  }
+  if (kVec == 2 && sizeof(R) == 8) {
+#pragma unroll
+    for (int d = 0; d < kD; d += 2) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(src + d));
+      out[d] = (R)v.x; out[d + 1] = (R)v.y;
+    }
+    return;
+  }
+#endif
+#pragma unroll
+  for (int d = 0; d < MDPP_MAX_DIM; ++d)
+    if (d < D) out[d] = src[d];
+}
+
+template <typename R>
+__device__ __forceinline__ void store_row(R* dst, int D, const R* v) {
+#ifdef MDPP_JIT
+  constexpr int kD = MDPP_C_DIM;
+  constexpr int kVec = (kD * sizeof(R)) % 16 == 0 ? 16 / sizeof(R)
+                     : (kD * sizeof(R)) % 8 == 0 ? 8 / sizeof(R) : 1;
+  if (kVec == 4) {
+#pragma unroll
+    for (int d = 0; d < kD; d += 4)
+      *reinterpret_cast<float4*>(dst + d) =
+          make_float4((float)v[d], (float)v[d + 1], (float)v[d + 2], (float)v[d + 3]);
+    return;
+  }
+  if (kVec == 2 && sizeof(R) == 4) {
+#pragma unroll
+    for (int d = 0; d < kD; d += 2)
+      *reinterpret_cast<float2*>(dst + d) = make_float2((float)v[d], (float)v[d + 1]);
+    return;
+  }
+  if (kVec == 2 && sizeof(R) == 8) {
+#pragma unroll
+    for (int d = 0; d < kD; d += 2)
+      *reinterpret_cast<double2*>(dst + d) = make_double2((double)v[d], (double)v[d + 1]);
+    return;
+  }
+#endif
+#pragma unroll
+  for (int d = 0; d < MDPP_MAX_DIM; ++d)
+    if (d < D) dst[d] = v[d];
+}
+
 // np.linalg.norm of a short vector: sqrt of the sequentially accumulated,
 // separately rounded sum of squares (bit-identical to numpy/OpenBLAS for the
 // 1- and 2-element vectors that move_to_a_point uses).
@@ -156,7 +248,14 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   const bool RNOISE = MDPP_C_CONST(RNOISE, p.cfg.has_reward_noise != 0);
   const bool IMAGE = MDPP_C_CONST(IMAGE, p.cfg.image_mode != 0);
   const bool TARGET64 = MDPP_C_CONST(TARGET64, p.cfg.target_is_f64 != 0);
-  const int64_t N = p.st.n_envs;
+  // launch shape: literals in the specialised build.  FAST = the standard
+  // rollout signature (obs, reward, terminated, truncated written, no
+  // final_obs), so no per-step NULL tests survive in the loop.
+  const int NBOX = MDPP_C_CONST(NBOX, p.cfg.n_term_boxes);
+  const int HORIZON = MDPP_C_CONST(HORIZON, p.horizon);
+  const bool AUTORESET = MDPP_C_CONST(AUTORESET, p.autoreset != 0);
+  const bool FAST = MDPP_C_CONST(FAST, false);
+  const int64_t N = MDPP_C_CONST(N_ENVS, p.st.n_envs);
   const int64_t env_raw = (int64_t)blockIdx.x * kCBlock + threadIdx.x;
   const bool active = env_raw < N;
   const int64_t env = active ? env_raw : 0;
@@ -222,12 +321,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   double dist_prev = dist_to_target(em);
   // the next step's action row is fetched one step ahead of its use
   R a_next[MDPP_MAX_DIM];
-  {
-    const R* ap = reinterpret_cast<const R*>(p.io.actions) + env * D;
-#pragma unroll
-    for (int d = 0; d < MDPP_MAX_DIM; ++d)
-      if (d < D) a_next[d] = ap[d];
-  }
+  load_row<R>(reinterpret_cast<const R*>(p.io.actions) + env * D, D, a_next);
   for (int t = 0; t < p.T; ++t) {
     const uint64_t step = step_base + (uint64_t)t;
     const int64_t row = ((int64_t)t * N + env);
@@ -239,19 +333,15 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
         a[d] = a_next[d];
         in_range = in_range && a[d] >= -amax && a[d] <= amax;  // Box.contains
       }
-    if (t + 1 < p.T) {
-      const R* ap = reinterpret_cast<const R*>(p.io.actions) + (row + N) * D;
-#pragma unroll
-      for (int d = 0; d < MDPP_MAX_DIM; ++d)
-        if (d < D) a_next[d] = ap[d];
-    }
+    if (t + 1 < p.T)
+      load_row<R>(reinterpret_cast<const R*>(p.io.actions) + (row + N) * D, D, a_next);
     const double dist_old = dist_prev;
 
     // ---- transition -----------------------------------------------------
     if (in_range) {
 #pragma unroll
       for (int d = 0; d < MDPP_MAX_DIM; ++d)
-        if (d < D) sd[ORDER][d] = O::div(a[d], inertia);
+        if (d < D) sd[ORDER][d] = div_inertia(a[d], inertia);
 #pragma unroll
       for (int i = 0; i < MDPP_MAX_ORDER; ++i)
 #pragma unroll
@@ -385,7 +475,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
       }
       sum_abs_rnoise += fabs(nrw);
     }
-    const bool box = p.cfg.n_term_boxes > 0 && in_term_box<R>(p, NREL, nxt);
+    const bool box = NBOX > 0 && in_term_box<R>(p, NREL, nxt);
     const bool done = box || reached;
     R out_r;
     if (is_real) {  // np.float32 op python-float: the scalar is cast first
@@ -401,18 +491,14 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
       if (done) rd = __dadd_rn(rd, term_add);
       out_r = (R)rd;
     }
-    const bool trunc = p.horizon > 0 && tl >= p.horizon;
+    const bool trunc = HORIZON > 0 && tl >= HORIZON;
     n_terminated += done;
 #pragma unroll
     for (int d = 0; d < MDPP_MAX_DIM; ++d)
       if (d < D) em[d] = nxt[d];
-    if (p.io.final_obs) {
-      R* fo = reinterpret_cast<R*>(p.io.final_obs) + row * D;
-#pragma unroll
-      for (int d = 0; d < MDPP_MAX_DIM; ++d)
-        if (d < D) fo[d] = nxt[d];
-    }
-    if (p.autoreset && (done || trunc)) {
+    if (!FAST && p.io.final_obs)
+      store_row<R>(reinterpret_cast<R*>(p.io.final_obs) + row * D, D, nxt);
+    if (AUTORESET && (done || trunc)) {
       R s0[MDPP_MAX_DIM];
       if (NOISE == MDPP_NOISE_REPLAY) {
         const R* rs = reinterpret_cast<const R*>(p.io.replay_reset_state) + row * D;
@@ -422,7 +508,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
       } else {
         for (int attempt = 0; attempt < 64; ++attempt) {
           box_sample<R>(p, D, gid, ep, attempt, s0);
-          if (!(p.cfg.n_term_boxes > 0 && in_term_box<R>(p, NREL, s0))) break;
+          if (!(NBOX > 0 && in_term_box<R>(p, NREL, s0))) break;
         }
       }
 #pragma unroll
@@ -438,15 +524,10 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
       ep += 1; n_episodes += 1;
       dist_prev = dist_to_target(em);
     }
-    if (p.io.obs) {
-      R* ob = reinterpret_cast<R*>(p.io.obs) + row * D;
-#pragma unroll
-      for (int d = 0; d < MDPP_MAX_DIM; ++d)
-        if (d < D) ob[d] = em[d];
-    }
-    if (p.io.reward) reinterpret_cast<R*>(p.io.reward)[row] = out_r;
-    if (p.io.terminated) p.io.terminated[row] = (uint8_t)done;
-    if (p.io.truncated) p.io.truncated[row] = (uint8_t)trunc;
+    if (FAST || p.io.obs) store_row<R>(reinterpret_cast<R*>(p.io.obs) + row * D, D, em);
+    if (FAST || p.io.reward) reinterpret_cast<R*>(p.io.reward)[row] = out_r;
+    if (FAST || p.io.terminated) p.io.terminated[row] = (uint8_t)done;
+    if (FAST || p.io.truncated) p.io.truncated[row] = (uint8_t)trunc;
   }
 
 #pragma unroll
