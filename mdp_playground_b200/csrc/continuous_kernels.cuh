@@ -235,6 +235,26 @@ __device__ __forceinline__ bool in_term_box(const ContinuousParams& p, int NREL,
   return any;
 }
 
+template <typename R> struct RowVal { R v[MDPP_MAX_DIM]; };
+
+// Initial state of a new episode (:2284-2323): Box sample, rejected while it
+// falls into a terminal box.  Rare and big (Philox + fp64), so out of line;
+// the row comes back by value and the caller's state stays in registers.
+template <typename R>
+__device__ __noinline__ RowVal<R> sample_reset_state(const ContinuousParams& p, int D,
+                                                     int NREL, int NBOX,
+                                                     uint32_t gid, uint32_t ep) {
+  RowVal<R> s0;
+#pragma unroll 1
+  for (int attempt = 0; attempt < 64; ++attempt) {
+    box_sample<R>(p, D, gid, ep, attempt, s0.v);
+    if (!(NBOX > 0 && in_term_box<R>(p, NREL, s0.v))) break;
+  }
+  return s0;
+}
+
+constexpr int kActionPrefetch = 4;  // action rows in flight per env
+
 template <typename R, int NOISE>
 __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   using O = RealOps<R>;
@@ -319,10 +339,24 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   // ||aug[-2][rel] - target||: the distance of the previous emitted state is
   // last step's dist_new, so it is carried instead of recomputed
   double dist_prev = dist_to_target(em);
-  // the next step's action row is fetched one step ahead of its use
-  R a_next[MDPP_MAX_DIM];
-  load_row<R>(reinterpret_cast<const R*>(p.io.actions) + env * D, D, a_next);
-  for (int t = 0; t < p.T; ++t) {
+  // Action rows are fetched kActionPrefetch steps ahead of their use, into a
+  // register ring indexed statically (the time loop is unrolled by the ring
+  // size): under a write-heavy DRAM stream a read takes several step times.
+  // (with Philox noise the fp64 Box-Muller body is too big to unroll: the
+  // instruction cache would thrash; the generic build keeps one row as well)
+#ifdef MDPP_JIT
+  constexpr int PF =
+      (MDPP_C_NOISE != MDPP_NOISE_OFF && (MDPP_C_PNOISE || MDPP_C_RNOISE)) ? 1 : kActionPrefetch;
+#else
+  constexpr int PF = 1;
+#endif
+  R abuf[PF][MDPP_MAX_DIM];
+#pragma unroll
+  for (int u = 0; u < PF; ++u)
+    if (u < p.T)
+      load_row<R>(reinterpret_cast<const R*>(p.io.actions) + ((int64_t)u * N + env) * D,
+                  D, abuf[u]);
+  auto one_step = [&](const int t, R* a_slot) {
     const uint64_t step = step_base + (uint64_t)t;
     const int64_t row = ((int64_t)t * N + env);
     R a[MDPP_MAX_DIM], nxt[MDPP_MAX_DIM];
@@ -330,11 +364,12 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
 #pragma unroll
     for (int d = 0; d < MDPP_MAX_DIM; ++d)
       if (d < D) {
-        a[d] = a_next[d];
+        a[d] = a_slot[d];
         in_range = in_range && a[d] >= -amax && a[d] <= amax;  // Box.contains
       }
-    if (t + 1 < p.T)
-      load_row<R>(reinterpret_cast<const R*>(p.io.actions) + (row + N) * D, D, a_next);
+    if (t + PF < p.T)
+      load_row<R>(reinterpret_cast<const R*>(p.io.actions) + (row + (int64_t)PF * N) * D,
+                  D, a_slot);
     const double dist_old = dist_prev;
 
     // ---- transition -----------------------------------------------------
@@ -506,10 +541,10 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
         for (int d = 0; d < MDPP_MAX_DIM; ++d)
           if (d < D) s0[d] = rs[d];
       } else {
-        for (int attempt = 0; attempt < 64; ++attempt) {
-          box_sample<R>(p, D, gid, ep, attempt, s0);
-          if (!(NBOX > 0 && in_term_box<R>(p, NREL, s0))) break;
-        }
+        const RowVal<R> fresh = sample_reset_state<R>(p, D, NREL, NBOX, gid, ep);
+#pragma unroll
+        for (int d = 0; d < MDPP_MAX_DIM; ++d)
+          if (d < D) s0[d] = fresh.v[d];
       }
 #pragma unroll
       for (int d = 0; d < MDPP_MAX_DIM; ++d)
@@ -528,7 +563,16 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
     if (FAST || p.io.reward) reinterpret_cast<R*>(p.io.reward)[row] = out_r;
     if (FAST || p.io.terminated) p.io.terminated[row] = (uint8_t)done;
     if (FAST || p.io.truncated) p.io.truncated[row] = (uint8_t)trunc;
+  };
+  int t = 0;
+#pragma unroll 1
+  for (; t + PF <= p.T; t += PF) {
+#pragma unroll
+    for (int u = 0; u < PF; ++u) one_step(t + u, abuf[u]);
   }
+#pragma unroll
+  for (int u = 0; u < PF - 1; ++u)  // tail: t is a multiple of PF here
+    if (t + u < p.T) one_step(t + u, abuf[u]);
 
 #pragma unroll
   for (int k = 0; k <= MDPP_MAX_ORDER; ++k)
