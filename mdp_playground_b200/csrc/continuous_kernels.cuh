@@ -586,18 +586,30 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   p.st.episode[env] = ep;
   p.st.reached[env] = (uint8_t)reached;
   }  // active
-  if (p.st.stats) {  // warp-reduced: one atomic per warp and counter
-    double vals[6] = {(double)n_episodes, active ? (double)p.T : 0.0, sum_reward,
+  if (p.st.stats) {  // block-reduced: one atomic per CTA and counter (the
+    // counters are single addresses; at T = 1 a per-warp atomic was the
+    // launch's critical path)
+    // (transitions = envs x T is known up front: one thread adds it)
+    double vals[6] = {(double)n_episodes, 0.0, sum_reward,
                       sum_abs_rnoise, sum_abs_pnoise, (double)n_terminated};
     const int slots[6] = {MDPP_STAT_EPISODES, MDPP_STAT_TRANSITIONS,
                           MDPP_STAT_REWARD, MDPP_STAT_ABS_REWARD_NOISE,
                           MDPP_STAT_ABS_TRANSITION_NOISE, MDPP_STAT_TERMINATED};
+    __shared__ double red[6][kCBlock / 32];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       double v = vals[k];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(p.st.stats + slots[k], v);
+      if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kCBlock / 32; ++w) v += red[threadIdx.x][w];
+      if (blockIdx.x == 0 && threadIdx.x == 1) v = (double)N * (double)p.T;
+      if (v != 0.0) atomicAdd(p.st.stats + slots[threadIdx.x], v);
     }
   }
 }

@@ -232,7 +232,10 @@ void* compile(mdpp_ctx* ctx, const char* entry_source, const char* entry_name,
 
 const char* kContinuousEntrySource = R"SRC(
 #include "continuous_kernels.cuh"
-extern "C" __global__ void __launch_bounds__(mdpp::kCBlock)
+#ifndef MDPP_C_MINBLOCKS
+#define MDPP_C_MINBLOCKS 6  // measured best of 1/5/6/8 on C3 (rollout and T = 1)
+#endif
+extern "C" __global__ void __launch_bounds__(mdpp::kCBlock, MDPP_C_MINBLOCKS)
 mdpp_jit_continuous(const __grid_constant__ mdpp::ContinuousParams p) {
   mdpp::continuous_body<MDPP_C_REAL, MDPP_C_NOISE>(p);
 }
@@ -314,6 +317,8 @@ int jit_try_continuous(mdpp_ctx* ctx, ContinuousParams& p, cudaStream_t stream) 
   for (int k = 0; k < MDPP_MAX_DIM; ++k)
     defs.push_back(D(("REL" + std::to_string(k)).c_str(),
                      I(k < c.n_relevant ? c.relevant_indices[k] : 0)));
+  if (const char* mb = std::getenv("MDPP_JIT_C_MINBLOCKS"))  // tuning knob
+    defs.push_back(std::string("-DMDPP_C_MINBLOCKS=") + mb);
   void* fn = get_function(ctx, kContinuousEntrySource, "mdpp_jit_continuous", defs);
   if (!fn) return 0;
   const unsigned grid = (unsigned)((p.st.n_envs + kCBlock - 1) / kCBlock);
