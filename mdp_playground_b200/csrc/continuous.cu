@@ -54,8 +54,10 @@ static int fill_params(mdpp_ctx* ctx, const mdpp_continuous_state* st,
   p->autoreset = opts->autoreset;
   p->horizon = opts->horizon;
   p->noise_mode = opts->noise_mode;
+  p->normal_mode = opts->normal_mode;
   p->k0 = (uint32_t)opts->seed;
   p->k1 = (uint32_t)(opts->seed >> 32);
+  philox_round_keys(p->k0, p->k1, p->rk);
   p->step_index = opts->step_index;
   p->step_index_dev = opts->step_index_dev;
   p->env_id_offset = opts->env_id_offset;
@@ -97,6 +99,9 @@ extern "C" int mdpp_continuous_rollout(mdpp_ctx* ctx,
         (opts->autoreset && !io->replay_reset_state))
       return fail(ctx, MDPP_EINVAL, "replay mode: missing replay array");
   }
+  // rows move as 8- / 16-byte vectors in the specialised kernels
+  if (((uintptr_t)io->actions | (uintptr_t)io->obs | (uintptr_t)io->final_obs) & 15)
+    return fail(ctx, MDPP_EINVAL, "actions / obs / final_obs must be 16-byte aligned");
   p.io = *io;
   MDPP_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = (cudaStream_t)cuda_stream;

@@ -37,7 +37,9 @@ struct ContinuousParams {
   mdpp_continuous_state st;
   mdpp_continuous_io io;
   int32_t T, autoreset, horizon, noise_mode;
+  int32_t normal_mode, reserved0;  // MDPP_NORMAL_*: Box-Muller in fp64 or on the SFU
   uint32_t k0, k1;
+  uint32_t rk[20];  // Philox round keys expanded from (k0, k1) by the host
   uint64_t step_index;
   const uint64_t* step_index_dev;
   int64_t env_id_offset;
@@ -275,6 +277,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   const int HORIZON = MDPP_C_CONST(HORIZON, p.horizon);
   const bool AUTORESET = MDPP_C_CONST(AUTORESET, p.autoreset != 0);
   const bool FAST = MDPP_C_CONST(FAST, false);
+  const bool FAST_NORMAL = MDPP_C_CONST(NORMAL, p.normal_mode) == MDPP_NORMAL_FAST;
   const int64_t N = MDPP_C_CONST(N_ENVS, p.st.n_envs);
   const int64_t env_raw = (int64_t)blockIdx.x * kCBlock + threadIdx.x;
   const bool active = env_raw < N;
@@ -342,11 +345,11 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   // Action rows are fetched kActionPrefetch steps ahead of their use, into a
   // register ring indexed statically (the time loop is unrolled by the ring
   // size): under a write-heavy DRAM stream a read takes several step times.
-  // (with Philox noise the fp64 Box-Muller body is too big to unroll: the
+  // (with fp64 Box-Muller noise the body is too big to unroll: the
   // instruction cache would thrash; the generic build keeps one row as well)
 #ifdef MDPP_JIT
-  constexpr int PF =
-      (MDPP_C_NOISE != MDPP_NOISE_OFF && (MDPP_C_PNOISE || MDPP_C_RNOISE)) ? 1 : kActionPrefetch;
+  constexpr int PF = (MDPP_C_NOISE != MDPP_NOISE_OFF && (MDPP_C_PNOISE || MDPP_C_RNOISE) &&
+                      MDPP_C_NORMAL != MDPP_NORMAL_FAST) ? 1 : kActionPrefetch;
 #else
   constexpr int PF = 1;
 #endif
@@ -419,11 +422,16 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
 #pragma unroll
         for (int c = 0; c < MDPP_MAX_DIM / 4; ++c)
           if (4 * c < D) {
-            U4 w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
-                                 STREAM_STATE_NOISE + (uint32_t)c, p.k0, p.k1);
+            U4 w = philox4x32_10_rk(gid, (uint32_t)step, (uint32_t)(step >> 32),
+                                    STREAM_STATE_NOISE + (uint32_t)c, p.rk);
             double z[4];
-            normal_pair_f64(w.x, w.y, &z[0], &z[1]);
-            normal_pair_f64(w.z, w.w, &z[2], &z[3]);
+            if (FAST_NORMAL) {
+              normal_pair_fast(w.x, w.y, &z[0], &z[1]);
+              normal_pair_fast(w.z, w.w, &z[2], &z[3]);
+            } else {
+              normal_pair_f64(w.x, w.y, &z[0], &z[1]);
+              normal_pair_f64(w.z, w.w, &z[2], &z[3]);
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               if (4 * c + k < D)
@@ -502,10 +510,11 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
       if (NOISE == MDPP_NOISE_REPLAY) {
         nrw = p.io.replay_reward_noise[row];
       } else {
-        U4 w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
-                             STREAM_NORMAL, p.k0, p.k1);
+        U4 w = philox4x32_10_rk(gid, (uint32_t)step, (uint32_t)(step >> 32),
+                                STREAM_NORMAL, p.rk);
         double z0, z1;
-        normal_pair_f64(w.x, w.y, &z0, &z1);
+        if (FAST_NORMAL) normal_pair_fast(w.x, w.y, &z0, &z1);
+        else normal_pair_f64(w.x, w.y, &z0, &z1);
         nrw = __dmul_rn(r_std, z0);
       }
       sum_abs_rnoise += fabs(nrw);

@@ -18,9 +18,10 @@ from . import philox as px
 
 class VectorContinuousOracle:
     def __init__(self, scalar_env, num_envs, autoreset=False, horizon=0,
-                 seed=0, env_id_offset=0):
+                 seed=0, env_id_offset=0, fast_normal=False):
         e = scalar_env
         assert e.kind == "continuous"
+        self._pair = px.normal_pair_fast if fast_normal else px.normal_pair_f64
         self.e = e
         self.N, self.D = int(num_envs), e.state_space_dim
         self.R = np.dtype(e.dtype_s).type
@@ -144,8 +145,8 @@ class VectorContinuousOracle:
                     for c in range((D + 3) // 4):
                         w = px.step_words(self.seed, self.gid, step,
                                           px.STREAM_STATE_NOISE + c)
-                        z01 = px.normal_pair_f64(w[0], w[1])
-                        z23 = px.normal_pair_f64(w[2], w[3])
+                        z01 = self._pair(w[0], w[1])
+                        z23 = self._pair(w[2], w[3])
                         for k, z in enumerate((*z01, *z23)):
                             if 4 * c + k < D:
                                 nz[:, 4 * c + k] = e.transition_noise * z
@@ -196,7 +197,7 @@ class VectorContinuousOracle:
                     nrw = np.asarray(replay["reward_noise"][t], dtype=np.float64)
                 else:
                     w = px.step_words(self.seed, self.gid, step, px.STREAM_NORMAL)
-                    nrw = e.reward_noise_std * px.normal_pair_f64(w[0], w[1])[0]
+                    nrw = e.reward_noise_std * self._pair(w[0], w[1])[0]
             else:
                 nrw = np.zeros(N)
             done = self._in_box(nxt) | self.reached

@@ -126,6 +126,35 @@ def test_philox_rollout_matches_oracle(name, N, T, autoreset, horizon):
                                rtol=1e-4, atol=1e-5)
 
 
+def test_fast_normal_noise_matches_oracle():
+    """normal_precision='fast' (SFU Box-Muller) on the continuous path: the
+    oracle restates the same fp32 Box-Muller; 1e-5 contract tolerance (the SFU
+    approximations differ from numpy's libm in the last bits, and transition
+    noise feeds back into the state)."""
+    cfg = gu.case_config("cont_noise_delay")
+    N, T = 2000, 40
+    ora = VectorContinuousOracle(scalar_oracle(gu.case_config("cont_noise_delay")), N,
+                                 autoreset=True, horizon=15, seed=9,
+                                 env_id_offset=50, fast_normal=True)
+    env = make_env(N, autoreset=True, horizon=15, philox_seed=9, env_id_offset=50,
+                   normal_precision="fast", **cfg)
+    ora.reset()
+    D = cfg["state_space_dim"]
+    amax = cfg.get("action_space_max", 1.0)
+    acts = np.random.default_rng(2).uniform(-amax, amax, size=(T, N, D)).astype(np.float32)
+    want = ora.rollout(T, acts)
+    got = env.rollout(T, torch.as_tensor(acts))
+    # a 1e-6 difference can flip a terminal test on a boundary: compare where
+    # the trajectories agree on the flags, and require that almost everywhere
+    same = np.array_equal(got["terminated"].cpu().numpy(), want["terminated"])
+    agree = (got["terminated"].cpu().numpy() == want["terminated"]).mean()
+    assert same or agree > 0.9999
+    ok = np.isclose(got["obs"].cpu().numpy(), want["obs"], rtol=1e-4, atol=1e-4)
+    assert ok.mean() > 0.999
+    okr = np.isclose(got["reward"].cpu().numpy(), want["reward"], rtol=1e-3, atol=1e-4)
+    assert okr.mean() > 0.999
+
+
 def test_fp64_build_matches_oracle_1e12():
     """dtype_s=float64 (the fp64 verification build): 1e-12 relative."""
     cfg = dict(gu.case_config("c3_order2"), dtype_s=np.float64,
