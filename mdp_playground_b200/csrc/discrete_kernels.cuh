@@ -316,12 +316,10 @@ struct Cfg {
 // the actions, the transition uniforms, the (sigma-scaled) reward normals and
 // the candidate initial states of a possible auto-reset.  `n_valid` < U only
 // on the last chunk of a launch (guards the action / replay loads).
-// Returns true if a guide lookup missed and FIXUP is off: the caller then
-// runs guide_fixup() before it uses s0.
 // PRELOADED: act[] already holds the chunk's actions (prefetched by the
 // caller one chunk ahead, see rollout_body).
-template <typename C, int U, bool FIXUP = true, bool PRELOADED = false>
-__device__ __forceinline__ bool phase_a(const RolloutParams& p, const GroupView& v,
+template <typename C, int U, bool PRELOADED = false>
+__device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView& v,
                                         int64_t env, uint32_t gid,
                                         uint64_t step_base, int t0,
                                         int n_valid, int32_t* act, double* u_tr,
@@ -404,7 +402,6 @@ __device__ __forceinline__ bool phase_a(const RolloutParams& p, const GroupView&
         s0[j] = v.guide[w_rs[j] >> (32 - kGuideBits)];
         worst = max(worst, s0[j]);
       }
-      if (!FIXUP) return worst == kGuideMiss;
       if (worst == kGuideMiss) {
 #pragma unroll  // (a rolled loop would index s0 / w_rs dynamically: local memory)
         for (int j = 0; j < U; ++j)
@@ -420,33 +417,6 @@ __device__ __forceinline__ bool phase_a(const RolloutParams& p, const GroupView&
       }
     }
   }
-  return false;
-}
-
-// The rare second half of the guide lookup for a pipelined chunk: the
-// auto-reset word of a missed entry is drawn again (cheaper than keeping all
-// of them alive) and searched in the cdf.  Out of line, scalars by value: the
-// callers' arrays stay in registers.
-template <int CDF_LOG2>
-__device__ __noinline__ int32_t guide_fix_one(const RolloutParams& p,
-                                              const double* init_cdf, int cdf_log2,
-                                              int S, uint32_t gid, uint64_t step) {
-  const uint64_t quad = step >> 2;
-  const U4 w = philox4x32_10_rk(gid, (uint32_t)quad, (uint32_t)(quad >> 32),
-                                STREAM_AUTORESET, p.rk);
-  const int j = (int)(step & 3);
-  const uint32_t wj = j == 0 ? w.x : j == 1 ? w.y : j == 2 ? w.z : w.w;
-  return cdf_search<CDF_LOG2>(init_cdf, cdf_log2, S, uniform32(wj));
-}
-
-template <typename C, int U>
-__device__ __forceinline__ void guide_fixup(const RolloutParams& p, const GroupView& v,
-                                            uint32_t gid, uint64_t step0, int32_t* s0) {
-#pragma unroll
-  for (int j = 0; j < U; ++j)
-    if (s0[j] == kGuideMiss)
-      s0[j] = guide_fix_one<C::CDF_LOG2>(p, v.init_cdf, v.cdf_log2, v.S, gid,
-                                         step0 + (uint64_t)j);
 }
 
 // ---- phase B: the state-dependent chain -----------------------------------
@@ -559,12 +529,6 @@ __device__ __forceinline__ void phase_b(const RolloutParams& p, const GroupView&
   e.n_steps += PARTIAL ? n_valid : U;
 }
 
-template <int U>
-struct ChunkBuf {  // phase A's results for one chunk
-  int32_t act[U], s0[U], k_tr[U];
-  double u_tr[U], n_rw[U];
-};
-
 // A full chunk whose actions were prefetched into act[].
 template <typename C, int U>
 __device__ __forceinline__ void run_chunk_preloaded(
@@ -572,7 +536,7 @@ __device__ __forceinline__ void run_chunk_preloaded(
     int64_t env, uint32_t gid, uint64_t step_base, int t0, int32_t* act) {
   int32_t s0[U], k_tr[U];
   double u_tr[U], n_rw[U];
-  phase_a<C, U, true, true>(p, v, env, gid, step_base, t0, U, act, u_tr, k_tr,
+  phase_a<C, U, true>(p, v, env, gid, step_base, t0, U, act, u_tr, k_tr,
                             n_rw, s0);
   phase_b<C, U, false>(p, v, e, ring_smem, kBlock, env, t0, U, act, u_tr, k_tr,
                        n_rw, s0);
@@ -665,49 +629,6 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
       run_chunk<C, 1>(p, v, e, ring_smem, env, gid, step_base, t0);
       ++t0;
     }
-#ifdef MDPP_PIPELINE
-    // Software pipeline over chunks: phase A of the next chunk (independent
-    // work: loads, Philox, Box-Muller) shares a basic block with the
-    // state-dependent chain of the current one, so the scheduler can fill the
-    // chain's latency.  Two buffers, loop unrolled by two: no register moves.
-    if (t0 + kChunk <= p.T) {
-      ChunkBuf<kChunk> b0, b1;
-      const int n_chunks = (p.T - t0) / kChunk;
-      int c = 0;
-      auto A = [&](ChunkBuf<kChunk>& b, int tc) {
-        return phase_a<C, kChunk, false>(p, v, env, gid, step_base, tc, kChunk,
-                                         b.act, b.u_tr, b.k_tr, b.n_rw, b.s0);
-      };
-      auto B = [&](const ChunkBuf<kChunk>& b, int tc) {
-        phase_b<C, kChunk, false>(p, v, e, ring_smem, kBlock, env, tc, kChunk,
-                                  b.act, b.u_tr, b.k_tr, b.n_rw, b.s0);
-      };
-      auto F = [&](ChunkBuf<kChunk>& b, int tc) {
-        guide_fixup<C, kChunk>(p, v, gid, step_base + (uint64_t)tc, b.s0);
-      };
-      if (A(b0, t0)) F(b0, t0);
-#pragma unroll 1
-      for (; c + 2 < n_chunks; c += 2) {
-        const int ta = t0 + c * kChunk;
-        const bool m1 = A(b1, ta + kChunk);
-        B(b0, ta);
-        if (m1) F(b1, ta + kChunk);
-        const bool m0 = A(b0, ta + 2 * kChunk);
-        B(b1, ta + kChunk);
-        if (m0) F(b0, ta + 2 * kChunk);
-      }
-      if (c + 1 < n_chunks) {
-        const int ta = t0 + c * kChunk;
-        const bool m1 = A(b1, ta + kChunk);
-        B(b0, ta);
-        if (m1) F(b1, ta + kChunk);
-        B(b1, ta + kChunk);
-      } else {
-        B(b0, t0 + c * kChunk);
-      }
-      t0 += n_chunks * kChunk;
-    }
-#else
     if (C::FAST) {
       // Action rows are fetched one chunk ahead: under a write-heavy DRAM
       // stream a read takes longer than phase A (ncu: 28 % of all stall
@@ -717,8 +638,9 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
       const int t_last = p.T - kChunk;  // start of the last possible chunk
       if (t0 <= t_last) {
 #pragma unroll
-        for (int j = 0; j < kChunk; ++j)
+        for (int j = 0; j < kChunk; ++j) {
           act_next[j] = ld_stream_i32(p.io.actions + (int64_t)(t0 + j) * N + env);
+        }
       }
       for (; t0 <= t_last; t0 += kChunk) {
         int32_t act[kChunk];
@@ -735,7 +657,6 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
       for (; t0 + kChunk <= p.T; t0 += kChunk)
         run_chunk<C, kChunk>(p, v, e, ring_smem, env, gid, step_base, t0);
     }
-#endif
     for (; t0 < p.T; ++t0)
       run_chunk<C, 1>(p, v, e, ring_smem, env, gid, step_base, t0);
     p.st.cur_state[env] = e.s;

@@ -348,8 +348,6 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
       defines_for(groups, p, noise_mode, normal_mode, fast, true, cdf_tpl);
   if (const char* ch = std::getenv("MDPP_JIT_CHUNK"))  // tuning knob (4/8/16)
     defs.push_back(std::string("-DMDPP_JIT_CHUNK=") + ch);
-  if (const char* pl = std::getenv("MDPP_JIT_PIPELINE"))  // tuning knob (0/1)
-    if (pl[0] == '1') defs.push_back("-DMDPP_PIPELINE");
   if (const char* mb = std::getenv("MDPP_JIT_MINBLOCKS"))  // tuning knob
     defs.push_back(std::string("-DMDPP_JIT_MINBLOCKS=") + mb);
   void* fn = get_function(ctx, kEntrySource, "mdpp_jit_rollout", defs);
