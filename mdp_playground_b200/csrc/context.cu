@@ -249,20 +249,39 @@ extern "C" int mdpp_set_discrete_groups(mdpp_ctx* ctx,
         }
         keys[i] = k;
       }
-      d.off_values = reserve((n + 1) * 8, 16);
-      {
-        double* v = reinterpret_cast<double*>(gb.data() + d.off_values);
-        v[0] = 0.0;
-        for (int i = 0; i < n; ++i) v[i + 1] = in.sequence_rewards[i] + 0.0;
+      // distinct reward values (by bit pattern), 0.0 first
+      std::vector<double> uniq = {0.0};
+      std::vector<int> uidx(n);
+      for (int i = 0; i < n; ++i) {
+        const double r = in.sequence_rewards[i] + 0.0;
+        size_t k = 0;
+        while (k < uniq.size() && std::memcmp(&uniq[k], &r, 8) != 0) ++k;
+        if (k == uniq.size()) uniq.push_back(r);
+        uidx[i] = (int)k;
       }
-      if (b * L <= kLutMaxBits) {
+      const int entries = b * L <= kLutMaxBits ? 1 << (b * L) : 0;
+      if (entries && entries * 8 <= kLutF64MaxBytes) {
         d.lookup_kind = LOOKUP_LUT;
-        const int entries = 1 << (b * L);
         d.off_lut = reserve(entries * 8, 16);  // rewards stored directly
         double* lut = reinterpret_cast<double*>(gb.data() + d.off_lut);
         for (int i = 0; i < n; ++i) lut[keys[i]] = in.sequence_rewards[i] + 0.0;
+      } else if (entries && uniq.size() <= 255) {
+        // a big fp64 table per CTA would cap the occupancy of multi-group
+        // launches (every CTA gets the largest group's shared memory)
+        d.lookup_kind = LOOKUP_LUT8;
+        d.off_values = reserve((int)uniq.size() * 8, 16);  // replaces the per-sequence list
+        std::memcpy(gb.data() + d.off_values, uniq.data(), uniq.size() * 8);
+        d.off_lut = reserve(entries, 16);
+        uint8_t* lut = gb.data() + d.off_lut;
+        for (int i = 0; i < n; ++i) lut[keys[i]] = (uint8_t)uidx[i];
       } else {
         d.lookup_kind = LOOKUP_HASH;
+        d.off_values = reserve((n + 1) * 8, 16);
+        {
+          double* v = reinterpret_cast<double*>(gb.data() + d.off_values);
+          v[0] = 0.0;
+          for (int i = 0; i < n; ++i) v[i + 1] = in.sequence_rewards[i] + 0.0;
+        }
         int log2cap = 4;
         while ((1 << log2cap) < 2 * n) ++log2cap;
         const uint32_t cap = 1u << log2cap;

@@ -37,7 +37,11 @@ struct CtaMapEntry {
   int32_t chunk;  // chunk index inside the group (units of block size)
 };
 
-enum { LOOKUP_LUT = 0, LOOKUP_HASH = 1, LOOKUP_MATRIX = 2 };
+// LUT: fp64 rewards indexed by the key; LUT8: one byte per key indexing the
+// (<= 255) distinct reward values -- 8x smaller, for keys of 10-12 bits;
+// HASH: open addressing on the 64-bit key; MATRIX: custom R[s, a].
+enum { LOOKUP_LUT = 0, LOOKUP_HASH = 1, LOOKUP_MATRIX = 2, LOOKUP_LUT8 = 3 };
+constexpr int kLutF64MaxBytes = 4096;
 constexpr int kLutMaxBits = 12;
 constexpr uint64_t kHashEmpty = ~0ull;
 constexpr int kGuideBits = 12;

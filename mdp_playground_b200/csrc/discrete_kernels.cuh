@@ -230,6 +230,8 @@ __device__ __forceinline__ GroupView make_view(const DiscreteGroupDev& g,
 __device__ __forceinline__ double sequence_reward(const GroupView& v,
                                                   uint64_t key) {
   if (v.lookup_kind == LOOKUP_LUT) return v.lut[key];
+  if (v.lookup_kind == LOOKUP_LUT8)
+    return v.values[reinterpret_cast<const uint8_t*>(v.lut)[key]];
   uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> v.hash_shift) &
                   v.hash_mask;
   while (true) {

@@ -62,6 +62,19 @@ def test_hash_lookup_long_sequences(jit):
 
 
 @pytest.mark.parametrize("jit", [True, False])
+@pytest.mark.parametrize("denser", [False, True])
+def test_byte_indexed_lut_for_12_bit_keys(jit, denser):
+    """8 states x L=4: 12 key bits -> an fp64 table would be 32 KB per CTA, so
+    the key indexes a byte table of the distinct reward values (LOOKUP_LUT8).
+    Delay 3 also exercises the register FIFO of the specialised build."""
+    cfg = dict(BASE, state_space_size=8, action_space_size=8, sequence_length=4,
+               delay=3, make_denser=denser, transition_noise=0.05,
+               terminal_state_density=0.0)
+    env = check(cfg, 900, 80, jit, horizon=40)
+    assert env.episode_stats()["reward"][0] > 0
+
+
+@pytest.mark.parametrize("jit", [True, False])
 def test_delay_deeper_than_the_shared_memory_ring(jit):
     """delay 20 > 16: the FIFO stays in global memory."""
     cfg = dict(BASE, state_space_size=8, action_space_size=8, sequence_length=1,
