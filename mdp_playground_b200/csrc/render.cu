@@ -107,7 +107,16 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
     const int xv = tb.xvar[(int64_t)cell * W + min(max(sw, 0), W - 1)];
     const int yv = tb.yvar[(int64_t)cell * H + min(max(sh, 0), H - 1)];
     const int id = tb.mask_index[((int64_t)cell * tb.n_xvar + xv) * tb.n_yvar + yv];
-    mask[threadIdx.x] = tb.mask_bits[(int64_t)id * kMaskRows + threadIdx.x];
+    uint64_t col = tb.mask_bits[(int64_t)id * kMaskRows + threadIdx.x];
+    // A quantised shift can push the polygon up to q-1 pixels over the image
+    // edge (Pillow clips it there): clear the mask bits whose pixel lies
+    // outside the image, so "inside the mask" implies "inside the image".
+    const int rx = threadIdx.x + sw - kMaskCentre;
+    const int lo = max(0, kMaskCentre - sh), hi = min(63, H - 1 + kMaskCentre - sh);
+    uint64_t rows = 0;
+    if (hi >= lo) rows = (hi - lo == 63 ? ~0ull : ((1ull << (hi - lo + 1)) - 1ull)) << lo;
+    if ((unsigned)rx >= (unsigned)W) rows = 0;
+    mask[threadIdx.x] = col & rows;
   }
   int a0 = 65536, a1 = 0, a2 = 0, a3 = 0, a4 = 65536, a5 = 0;
   if (rot >= 0) {
@@ -184,20 +193,27 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
       const int c = w / segs, sgm = w - c * segs;
       const int x = rcx0 + c;
       const int fx = flip == 1 ? W - 1 - x : x;
-      const int k0 = sgm * 8, k1 = min(nrows, k0 + 8);      // box-local rows
+      const int k0 = sgm * 8;                               // box-local rows
       const int sy = flip == 2 ? -1 : 1;                    // d(fy) / d(y)
       const int fy = flip == 2 ? H - 1 - (rcy0 + k0) : rcy0 + k0;
-      int X = a2 + a1 * fy + a0 * fx, Y = a5 + a4 * fy + a3 * fx;
+      // 16.16 source coordinates, pre-shifted into mask space (mx = X >> 16,
+      // my = Y >> 16).  Mask bits outside the image were cleared at load, so
+      // the image-bounds test of the rotation is implied by the mask-bounds
+      // test -- one compare on (mx | my).
+      int X = a2 + a1 * fy + a0 * fx + (kMaskCentre - sw) * 65536;
+      int Y = a5 + a4 * fy + a3 * fx + (kMaskCentre - sh) * 65536;
       const int dX = a1 * sy, dY = a4 * sy;
       uint32_t bits = 0;
-      for (int k = k0; k < k1; ++k) {
-        const int rx = X >> 16, ry = Y >> 16;
-        const int mx = rx - sw + kMaskCentre, my = ry - sh + kMaskCentre;
-        if ((unsigned)rx < (unsigned)W && (unsigned)ry < (unsigned)H &&
-            (unsigned)mx < (unsigned)kMaskRows && (unsigned)my < 64u)
-          bits |= (uint32_t)((mask[mx] >> my) & 1ull) << (k - k0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {  // bit k enters at the top and slides down
+        const int mx = X >> 16, my = Y >> 16;
+        uint32_t v = 0;
+        if ((unsigned)(mx | my) < 64u) v = (uint32_t)(mask[mx] >> my);
+        bits = __funnelshift_r(bits, v, 1);
         X += dX; Y += dY;
       }
+      bits >>= 24;
+      if (k0 + 8 > nrows) bits &= (1u << (nrows - k0)) - 1u;
       if (bits)
         atomicOr(reinterpret_cast<unsigned long long*>(&rmask[c][k0 >> 6]),
                  (unsigned long long)bits << (k0 & 63));
