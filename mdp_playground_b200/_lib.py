@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmdpp_b200.so")
+# MDPP_LIB: A/B timing of two builds (tools/); the default is the in-tree library
+LIB_PATH = os.environ.get("MDPP_LIB") or os.path.join(HERE, "libmdpp_b200.so")
 
 MDPP_NOISE_OFF, MDPP_NOISE_REPLAY, MDPP_NOISE_PHILOX = 0, 1, 2
 MDPP_N_STATS = 8
