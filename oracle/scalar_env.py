@@ -24,7 +24,7 @@ Pillow (12.2.0 in this image) is called directly for polygon/ellipse/rotate,
 exactly as the reference does.
 
 Not covered (SURVEY.md section 8f "next" rows): grid envs, move_along_a_line,
-discrete irrelevant_features, callable P/R/noise.
+callable P/R/noise.
 """
 import math
 import sys
@@ -51,6 +51,12 @@ class NumpyDraws:
     def transition_uniform(self):
         # Generator.choice(p=...) draws exactly one random()
         return self.env.rng_S.random()
+
+    def irr_transition_uniform(self):
+        return self.env.rng_S1.random()
+
+    def irr_reset_uniform(self):
+        return self.env.rng_E.random()
 
     def reward_normal(self, std):
         return self.env.rng_E.normal(0, std)
@@ -83,6 +89,12 @@ class ReplayDraws:
 
     def transition_uniform(self):
         return self._pop("transition_u")
+
+    def irr_transition_uniform(self):
+        return self._pop("irr_transition_u")
+
+    def irr_reset_uniform(self):
+        return self._pop("irr_reset_u")
 
     def reward_normal(self, std):
         return self._pop("reward_noise")
@@ -151,8 +163,7 @@ class ScalarRLToyEnv:
         assert not callable(self.transition_noise), "callable noise: next row"
         self.reward_scale = g("reward_scale", 1.0)
         self.reward_shift = g("reward_shift", 0.0)
-        assert not g("irrelevant_features", False) or kind == "continuous", \
-            "discrete irrelevant_features: next row (parity unpinned)"
+        self.irrelevant_features = bool(g("irrelevant_features", False))
         self.image_representations = g("image_representations", False)
         if "image_transforms" in cfg:
             assert kind == "discrete"
@@ -192,8 +203,16 @@ class ScalarRLToyEnv:
 
         if kind == "discrete":  # :570-591
             self.dtype_s = g("dtype_s", np.int64)
-            assert isinstance(cfg["action_space_size"], int)
-            self.action_space_size = cfg["action_space_size"]
+            if self.irrelevant_features:  # :574-578, sizes are [relevant, irrelevant]
+                assert len(cfg["action_space_size"]) == 2
+                assert not self.use_custom_mdp
+                self.action_space_size = cfg["action_space_size"][0]
+                self.action_space_size_irr = cfg["action_space_size"][1]
+                self.state_space_size_irr = (self.action_space_size_irr
+                                             * self.diameter)
+            else:
+                assert isinstance(cfg["action_space_size"], int)
+                self.action_space_size = cfg["action_space_size"]
             if self.use_custom_mdp:
                 self.state_space_size = cfg["state_space_size"]
             else:
@@ -223,6 +242,18 @@ class ScalarRLToyEnv:
         # spaces (:668-776): only their generators matter here
         if kind == "discrete":
             self.rng_S, _ = np_random(self.seed_dict["relevant_state_space"])
+            if self.irrelevant_features:
+                self.rng_S1, _ = np_random(self.seed_dict["irrelevant_state_space"])
+                if not self.image_representations:
+                    # :738-741 wraps both sub-spaces in a TupleExtended seeded
+                    # with an int: gymnasium 1.x Tuple.seed then RE-SEEDS every
+                    # sub-space with integers(int32.max, size=2) of its own
+                    # stream (gymnasium_standin/spaces/tuple.py; parity of this
+                    # cascade is unpinned by the reference)
+                    rng_T, _ = np_random(self.seed_dict["state_space"])
+                    sub = rng_T.integers(np.iinfo(np.int32).max, size=2)
+                    self.rng_S, _ = np_random(int(sub[0]))
+                    self.rng_S1, _ = np_random(int(sub[1]))
             if self.image_representations:
                 self.rng_I, _ = np_random(self.seed_dict["image_representations"])
         else:
@@ -327,6 +358,10 @@ class ScalarRLToyEnv:
             cfg["relevant_init_state_dist"] = np.array(per_set * self.diameter)
         self.init_state_dist = np.asarray(cfg["relevant_init_state_dist"])
         self.init_cdf = normalised_cdf(self.init_state_dist)
+        if self.irrelevant_features:  # :1024-1035, uniform over ALL states
+            S1 = self.state_space_size_irr
+            cfg["irrelevant_init_state_dist"] = np.array([1 / S1] * S1)
+            self.init_cdf_irr = normalised_cdf(cfg["irrelevant_init_state_dist"])
 
     def _next_set_prob(self, s):
         """Uniform over the next independent set (:1074-1092)."""
@@ -369,14 +404,45 @@ class ScalarRLToyEnv:
                 for s in range(A - self.num_terminal_states, A):
                     P[i_s * A + s, :] = i_s * A + s
             self.transition_matrix = P
+            if self.irrelevant_features:
+                self._init_transition_function_irr()
         # A1': the noisy-transition cdf depends only on (P[s,a], p)
         if self.kind == "discrete" and self.transition_noise:
-            S = self.state_space_size
-            self.noise_cdf = np.empty((S, S))
-            for nxt in range(S):
-                probs = np.ones((S,)) * self.transition_noise / (S - 1)
-                probs[nxt] = 1 - self.transition_noise
-                self.noise_cdf[nxt] = normalised_cdf(probs)
+            self.noise_cdf = self._noise_cdf(self.state_space_size)
+            if self.irrelevant_features:
+                self.noise_cdf_irr = self._noise_cdf(self.state_space_size_irr)
+
+    def _noise_cdf(self, S):
+        cdf = np.empty((S, S))
+        for nxt in range(S):
+            probs = np.ones((S,)) * self.transition_noise / (S - 1)
+            probs[nxt] = 1 - self.transition_noise
+            cdf[nxt] = normalised_cdf(probs)
+        return cdf
+
+    def _init_transition_function_irr(self):
+        """rl_toy_env.py:1154-1230 (S' stream): like the relevant table, but
+        the next-set probabilities are always passed (also for diameter 1) and
+        there are no terminal self-loops."""
+        S1, A1 = self.state_space_size_irr, self.action_space_size_irr
+        P = np.zeros((S1, A1), dtype=object)
+        P[:] = -1
+        for s in range(S1):
+            i_s = s // A1
+            prob = np.zeros((S1,))
+            ind_1 = ((i_s + 1) * A1) % S1
+            ind_2 = ((i_s + 2) * A1) % S1
+            if ind_2 <= ind_1:
+                ind_2 += S1
+            prob[ind_1:ind_2] = np.ones((A1,)) / A1
+            if self.maximally_connected:
+                P[s] = np.squeeze(self.rng_S1.choice(
+                    S1, size=A1, p=prob, replace=False))
+            else:
+                for a in range(A1):
+                    P[s, a] = int(np.squeeze(self.rng_S1.choice(
+                        S1, size=1, p=prob, replace=True)))
+        self.transition_matrix_irr = P
 
     def _sequences_with_repeats(self, n, length, fraction, diameter):
         """get_sequences(repeats=True) :1291-1338 (one E draw in total)."""
@@ -463,6 +529,9 @@ class ScalarRLToyEnv:
             u = self.draws.reset_uniform()
             s0 = choice_from_uniform(self.init_cdf, u)
             self.curr_state = s0
+            if self.irrelevant_features:  # second E draw :2260-2264
+                u1 = self.draws.irr_reset_uniform()
+                self.curr_state = (s0, choice_from_uniform(self.init_cdf_irr, u1))
             self.augmented_state = [np.nan] * L1 + [s0]
         else:
             while True:
@@ -585,7 +654,12 @@ class ScalarRLToyEnv:
     # ---- step -------------------------------------------------------------
     def step(self, action):
         """rl_toy_env.py:1992-2125."""
-        if self.kind == "discrete":
+        irr = self.kind == "discrete" and self.irrelevant_features
+        if irr:  # :2029-2035
+            state_irr, action_irr = self.curr_state[1], action[1]
+            state, action = self.curr_state[0], action[0]
+            nxt = self._transition_discrete(state, action)
+        elif self.kind == "discrete":
             nxt = self._transition_discrete(self.curr_state, action)
         else:
             nxt = self._transition_continuous(self.curr_state, action)
@@ -594,6 +668,12 @@ class ScalarRLToyEnv:
                                     else nxt.copy())
         self.total_transitions_episode += 1
         self.reward = self._reward(action)
+        if irr:  # :2062-2082, after the reward (draw order S, E, S')
+            nxt_irr = int(self.transition_matrix_irr[state_irr, action_irr])
+            if self.transition_noise:
+                u = self.draws.irr_transition_uniform()
+                nxt_irr = choice_from_uniform(self.noise_cdf_irr[nxt_irr], u)
+            nxt = (nxt, nxt_irr)
         obs = self._image(nxt) if self.image_representations else nxt
         self.curr_state = self.dtype_s(nxt)
         self.curr_obs = self.dtype_o(obs)
@@ -607,6 +687,9 @@ class ScalarRLToyEnv:
     # ---- images -----------------------------------------------------------
     def _image(self, state):
         if self.kind == "discrete":
+            if self.irrelevant_features:  # image_multi_discrete.py:272-288
+                return np.atleast_3d(np.concatenate(
+                    [self._image_discrete(int(s)) for s in state], axis=0))
             return np.atleast_3d(self._image_discrete(int(state)))
         return self._image_continuous(state)
 

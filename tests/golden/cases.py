@@ -68,6 +68,26 @@ CASES = {
         init_state_dist=np.array([1 / 6] * 6 + [0, 0]),
         terminal_states=[6, 7], delay=1, reward_noise=0.1,
         transition_noise=0.2, reward_scale=0.5)),
+    # discrete irrelevant_features (dqn_irr_dims.py shape: sizes [8, 8]; plus
+    # unequal sub-spaces, diameter, noise, images of both sub-states)
+    "irr_8x8_noise": dict(config=dict(
+        _D, seed=8, state_space_size=[8, 8], action_space_size=[8, 8],
+        irrelevant_features=True, sequence_length=2, delay=1,
+        transition_noise=0.1, reward_noise=0.5, reward_every_n_steps=1)),
+    "irr_6x10_diam2": dict(config=dict(
+        _D, seed=5, state_space_size=[12, 20], action_space_size=[6, 10],
+        irrelevant_features=True, diameter=2, sequence_length=3,
+        transition_noise=0.3, reward_every_n_steps=1)),
+    "irr_8x5_det": dict(config=dict(
+        _D, seed=3, state_space_size=[8, 5], action_space_size=[8, 5],
+        irrelevant_features=True)),
+    "irr_img_all": dict(config=dict(
+        _D, seed=2, state_space_size=[8, 8], action_space_size=[8, 8],
+        irrelevant_features=True, transition_noise=0.1,
+        image_representations=True,
+        image_transforms="shift,scale,rotate,flip", image_sh_quant=2,
+        image_ro_quant=1, image_scale_range=(0.5, 1.5)),
+        lanes=2, steps=24, horizon=8),
     "c4_img_shift": dict(config=dict(
         _D, seed=2, sequence_length=1, image_representations=True,
         image_transforms="shift", image_sh_quant=4, image_width=100,

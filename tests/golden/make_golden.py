@@ -39,6 +39,7 @@ def run_case(name, spec):
     env = make_reference_env(cfg)
     cont = cfg["state_space_type"] == "continuous"
     image = bool(cfg.get("image_representations", False))
+    irr = (not cont) and bool(cfg.get("irrelevant_features", False))
     D = cfg.get("state_space_dim", 0)
     out = {}
     if not cont:
@@ -54,10 +55,13 @@ def run_case(name, spec):
                                           dtype=np.int64)
         out["init_state_dist"] = np.array(
             env.config["relevant_init_state_dist"], dtype=np.float64)
+    if irr:
+        out["P_irr"] = np.array(env.config["transition_function_irrelevant"],
+                                dtype=np.int64)
     out["seed_dict"] = np.array(json.dumps(env.seed_dict))
     out["reward_every_n_steps"] = np.array(int(env.reward_every_n_steps))
 
-    sshape = (K, T, D) if cont else (K, T)
+    sshape = (K, T, D) if cont else ((K, T, 2) if irr else (K, T))
     sdtype = np.float32 if cont else np.int64
     rec = dict(
         actions=np.zeros(sshape, dtype=np.float32 if cont else np.int64),
@@ -67,7 +71,8 @@ def run_case(name, spec):
         done=np.zeros((K, T), dtype=bool),
         reset_after=np.zeros((K, T), dtype=bool),
         reset_state=np.zeros(sshape, dtype=sdtype),
-        init_state=np.zeros((K, D) if cont else (K,), dtype=sdtype),
+        init_state=np.zeros((K, D) if cont else ((K, 2) if irr else (K,)),
+                            dtype=sdtype),
         transition_u=np.full((K, T), np.nan),
         reward_noise=np.full((K, T), np.nan),
         reset_u=np.full((K, T), np.nan),
@@ -77,6 +82,12 @@ def run_case(name, spec):
         rec["state_noise"] = np.full((K, T, D), np.nan)
         rec["derivs"] = np.zeros(
             (K, T, env.dynamics_order + 1, D), dtype=np.float32)
+    if irr:  # draws of the irrelevant sub-space (S' stream / second E draw)
+        rec["irr_transition_u"] = np.full((K, T), np.nan)
+        rec["irr_reset_u"] = np.full((K, T), np.nan)
+        rec["init_irr_reset_u"] = np.full((K,), np.nan)
+    n_sub = 2 if irr else 1
+    pshape = (n_sub, 5) if irr else (5,)
     if image:
         shp = env.curr_obs[0].shape if isinstance(env.curr_obs, tuple) \
             else env.curr_obs.shape
@@ -85,15 +96,21 @@ def run_case(name, spec):
         rec["reset_image"] = np.zeros((K, T) + shp, dtype=np.uint8)
         if not cont:
             # R, shift_w, shift_h, rotation(-1 = none), flip(0/1 LR/2 TB)
-            rec["image_params"] = np.full((K, T, 5), -1, dtype=np.int64)
-            rec["init_image_params"] = np.full((K, 5), -1, dtype=np.int64)
-            rec["reset_image_params"] = np.full((K, T, 5), -1, dtype=np.int64)
+            rec["image_params"] = np.full((K, T) + pshape, -1, dtype=np.int64)
+            rec["init_image_params"] = np.full((K,) + pshape, -1, dtype=np.int64)
+            rec["reset_image_params"] = np.full((K, T) + pshape, -1,
+                                                dtype=np.int64)
 
     def image_params_from(log_slice):
         """Decode the I-stream draws of one generate_image call."""
         tr = cfg.get("image_transforms", "none")
         W, Ht = cfg.get("image_width", 100), cfg.get("image_height", 100)
         it = iter([e for e in log_slice if e[0] == "image"])
+        res = [one_image_params(it, tr, W, Ht) for _ in range(n_sub)]
+        assert next(it, None) is None
+        return res if irr else res[0]
+
+    def one_image_params(it, tr, W, Ht):
         R = 20
         sw, sh, rot, flip = int(W / 2), int(Ht / 2), -1, 0
         if "scale" in tr:
@@ -111,7 +128,6 @@ def run_case(name, spec):
         if "flip" in tr:
             if int(next(it)[3]) == 0:
                 flip = 1 if int(next(it)[3]) == 0 else 2
-        assert next(it, None) is None
         return [R, sw, sh, rot, flip]
 
     for k in range(K):
@@ -119,6 +135,8 @@ def run_case(name, spec):
         # re-seed every stream the step path draws from
         if not cont:
             env.observation_spaces[0].seed(lane_seed + 1)
+            if irr:
+                env.observation_spaces[1].seed(lane_seed + 4)
         else:
             env.feature_space.seed(lane_seed + 2)
         if image:
@@ -126,9 +144,11 @@ def run_case(name, spec):
         log = draw_recorder.install(env)
         obs0, _ = env.reset(seed=lane_seed)  # E replaced: re-wrap it below
         if not cont:
-            u0 = np.random.Generator(np.random.PCG64(
-                np.random.SeedSequence(lane_seed))).random()
-            rec["init_reset_u"][k] = u0
+            g0 = np.random.Generator(np.random.PCG64(
+                np.random.SeedSequence(lane_seed)))
+            rec["init_reset_u"][k] = g0.random()
+            if irr:
+                rec["init_irr_reset_u"][k] = g0.random()
             rec["init_state"][k] = env.curr_state
         else:
             rec["init_state"][k] = env.curr_state
@@ -146,6 +166,8 @@ def run_case(name, spec):
                 # ~5 % of the actions fall outside the action space
                 a = arng.uniform(-1.05 * amax, 1.05 * amax, size=D).astype(
                     np.float32)
+            elif irr:
+                a = np.array([arng.integers(n) for n in env.action_space_size])
             else:
                 a = int(arng.integers(env.action_space_size[0]))
             rec["actions"][k, t] = a
@@ -157,6 +179,8 @@ def run_case(name, spec):
             for e in log:
                 if e[1] == "choice_u" and e[0] == "obs0":
                     rec["transition_u"][k, t] = e[2]
+                elif e[1] == "choice_u" and e[0] == "obs1":
+                    rec["irr_transition_u"][k, t] = e[2]
                 elif e[1] == "normal" and np.ndim(e[3]) == 0:
                     rec["reward_noise"][k, t] = float(e[3])
                 elif e[1] == "normal":
@@ -172,9 +196,10 @@ def run_case(name, spec):
                 rec["reset_after"][k, t] = True
                 obs_r, _ = env.reset()
                 rec["reset_state"][k, t] = env.curr_state
-                for e in log:
-                    if e[1] == "choice_u" and e[0] == "env":
-                        rec["reset_u"][k, t] = e[2]
+                us = [e[2] for e in log if e[1] == "choice_u" and e[0] == "env"]
+                rec["reset_u"][k, t] = us[0]
+                if irr:
+                    rec["irr_reset_u"][k, t] = us[1]
                 if image:
                     rec["reset_image"][k, t] = obs_r
                     if not cont:

@@ -7,8 +7,12 @@ from tests.golden.cases import CASES, LANE_SEED, materialise
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
+IRR_CASES = [k for k, v in CASES.items()
+             if v["config"]["state_space_type"] == "discrete"
+             and v["config"].get("irrelevant_features")]
 DISCRETE_CASES = [k for k, v in CASES.items()
-                  if v["config"]["state_space_type"] == "discrete"]
+                  if v["config"]["state_space_type"] == "discrete"
+                  and k not in IRR_CASES]
 CONTINUOUS_CASES = [k for k, v in CASES.items()
                     if v["config"]["state_space_type"] == "continuous"]
 

@@ -21,6 +21,9 @@ def _tables_equal(env, g, cfg):
     assert np.array_equal(np.array(env.transition_matrix, dtype=np.int64), g["P"])
     assert np.array_equal(np.array(env.terminal_states), g["terminal_states"])
     assert np.array_equal(env.init_state_dist, g["init_state_dist"])
+    if cfg.get("irrelevant_features"):
+        assert np.array_equal(np.array(env.transition_matrix_irr, dtype=np.int64),
+                              g["P_irr"])
     if not cfg.get("use_custom_mdp"):
         gold = gu.golden_sequences(g)
         assert list(env.rewardable_sequences.items()) == list(gold.items())
@@ -33,7 +36,7 @@ def _check_lane(env, g, k, cfg, H):
     T = g["done"].shape[1]
     for t in range(T):
         a = g["actions"][k, t]
-        a = a.copy() if cont else int(a)
+        a = a.copy() if (cont or np.ndim(a)) else int(a)
         obs, r, done, trunc, _ = env.step(a)
         assert np.array_equal(env.curr_state, g["state"][k, t]), (k, t)
         assert float(r) == g["reward"][k, t], (k, t, r, g["reward"][k, t])
@@ -45,10 +48,10 @@ def _check_lane(env, g, k, cfg, H):
         if image:
             assert np.array_equal(obs, g["obs_image"][k, t]), (k, t)
             if not cont:
-                p = env.last_image_params
+                p = env.last_image_params  # of the last sub-image drawn
                 got = [p["R"], p["shift_w"], p["shift_h"],
                        -1 if p["rotation"] is None else p["rotation"], p["flip"]]
-                assert got == list(g["image_params"][k, t])
+                assert got == list(g["image_params"][k, t].reshape(-1, 5)[-1])
         do_reset = done or t % H == H - 1
         assert do_reset == bool(g["reset_after"][k, t])
         if do_reset:
@@ -72,6 +75,8 @@ def test_oracle_numpy_streams_match_reference_golden(name):
         s = gu.lane_seed(k)
         if not cont:
             env.rng_S, _ = np_random(s + 1)
+            if cfg.get("irrelevant_features"):
+                env.rng_S1, _ = np_random(s + 4)
         else:
             env.rng_F, _ = np_random(s + 2)
         if cfg.get("image_representations") and not cont:
@@ -88,16 +93,21 @@ def _lane_feed(g, k, cont, image_params=None):
     T = g["done"].shape[1]
     feed = {"transition_u": [], "reward_noise": [], "reset_u": [],
             "state_noise": [], "reset_state": [], "image_scale_u": [],
-            "image_int": []}
+            "image_int": [], "irr_transition_u": [], "irr_reset_u": []}
+    irr = "irr_reset_u" in g
     if cont:
         feed["reset_state"].append(g["init_state"][k])
     else:
         feed["reset_u"].append(float(g["init_reset_u"][k]))
+        if irr:
+            feed["irr_reset_u"].append(float(g["init_irr_reset_u"][k]))
     for t in range(T):
         if not np.isnan(g["transition_u"][k, t]):
             feed["transition_u"].append(float(g["transition_u"][k, t]))
         if not np.isnan(g["reward_noise"][k, t]):
             feed["reward_noise"].append(float(g["reward_noise"][k, t]))
+        if irr and not np.isnan(g["irr_transition_u"][k, t]):
+            feed["irr_transition_u"].append(float(g["irr_transition_u"][k, t]))
         if cont and not np.isnan(g["state_noise"][k, t]).any():
             feed["state_noise"].append(g["state_noise"][k, t])
         if g["reset_after"][k, t]:
@@ -105,6 +115,8 @@ def _lane_feed(g, k, cont, image_params=None):
                 feed["reset_state"].append(g["reset_state"][k, t])
             else:
                 feed["reset_u"].append(float(g["reset_u"][k, t]))
+                if irr:
+                    feed["irr_reset_u"].append(float(g["irr_reset_u"][k, t]))
     return feed
 
 
@@ -123,6 +135,8 @@ def test_oracle_replay_of_recorded_draws(name):
             feed["reset_state"].insert(0, g["init_state"][k])
         else:
             feed["reset_u"].insert(0, 0.0)
+            if cfg.get("irrelevant_features"):
+                feed["irr_reset_u"].insert(0, 0.0)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             env = ScalarRLToyEnv(draws=ReplayDraws(feed), **gu.case_config(name))
