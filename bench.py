@@ -248,6 +248,19 @@ def other_configs(torch, Env, dev, rank, world, barrier, max_over_ranks, peak):
         line("C1_discrete_seq1_rollout", N, T, ms, 22,
              "fused rollout, noise off")
         del env, acts, out
+        # N2: discrete irrelevant_features, dqn_irr_dims.py
+        # shape; rows (relevant, irrelevant): 8 B actions in, 16 B obs out
+        env = Env(N, device=dev, autoreset=True, horizon=100,
+                  env_id_offset=rank * N, sequence_length=1, delay=0,
+                  irrelevant_features=True, transition_noise=0.1,
+                  **dict(base, state_space_size=[8, 8], action_space_size=[8, 8]))
+        acts = torch.randint(0, 8, (T, N, 2), dtype=torch.int32, device=dev)
+        out = env.rollout(T, actions=acts, want_final_obs=False)
+        ms = _time_launches(torch, lambda: env.rollout(T, actions=acts, out=out),
+                            10, barrier, max_over_ranks)
+        line("N2_discrete_irrelevant_features_rollout", N, T, ms, 34,
+             "fused rollout, two sub-MDPs per env, transition noise 0.1")
+        del env, acts, out
         # C3: continuous move_to_a_point, 1M envs
         N, T = 1 << 20, 100
         c3 = dict(seed=0, state_space_type="continuous", state_space_dim=6,

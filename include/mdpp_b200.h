@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MDPP_ABI_VERSION 1
+#define MDPP_ABI_VERSION 2
 
 #define MDPP_OK 0
 #define MDPP_EINVAL (-1)   /* bad argument / unsupported configuration      */
@@ -116,6 +116,15 @@ typedef struct mdpp_discrete_group {
                                     to opts->env_id_offset: keeps the noise of
                                     an env independent of how groups / envs
                                     are sharded over GPUs                    */
+  /* irrelevant_features (:1154-1230, :2062-2082, :2260-2264): a second,
+   * reward-free sub-MDP with its own transition table, uniform start and the
+   * same transition_noise p.  n_states_irr == 0 = none; all groups of a
+   * context must agree on having one.                                       */
+  int32_t n_states_irr;          /* S1                                       */
+  int32_t n_actions_irr;         /* A1                                       */
+  const int32_t* transition_irr; /* [S1*A1]                                  */
+  const double* init_cdf_irr;    /* [S1]                                     */
+  const double* noise_cdf_irr;   /* [S1*S1], may be NULL without noise       */
 } mdpp_discrete_group;
 
 #ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
@@ -139,10 +148,15 @@ typedef struct mdpp_discrete_state {
   int32_t history_depth;
   int32_t* history;     /* [history_depth*N] or NULL                        */
   double* stats;        /* [n_groups*MDPP_N_STATS], accumulated atomically  */
+  int32_t* cur_state_irr; /* [N] irrelevant sub-state (irrelevant_features)  */
 } mdpp_discrete_state;
 
 /* Inputs/outputs of T consecutive steps, time-major [T*N], DEVICE pointers.
- * Any output pointer may be NULL (that output is skipped).                 */
+ * Any output pointer may be NULL (that output is skipped).
+ * With irrelevant_features every state-like quantity is a ROW OF 2 per env,
+ * (relevant, irrelevant) -- the reference's (s, s_irr) tuples (:2085-2088):
+ * actions, obs, final_obs, replay_transition_u and replay_reset_u are then
+ * [T*N*2] (one 8- / 16-byte vector access per env and step).                */
 typedef struct mdpp_discrete_io {
   const int32_t* actions;            /* [T*N]; NULL => uniform Philox policy */
   int64_t* obs;                      /* [T*N] state after the step (after the
@@ -185,7 +199,8 @@ int mdpp_discrete_rollout(mdpp_ctx* ctx, const mdpp_discrete_state* st,
 
 /* K6: (masked) reset.  mask NULL = all envs.  The initial state comes from
  * `init_states` when given, else from the init cdf driven by `replay_reset_u`
- * (MDPP_NOISE_REPLAY) or Philox.  `obs` may be NULL.                        */
+ * (MDPP_NOISE_REPLAY) or Philox.  `obs` may be NULL.  With
+ * irrelevant_features init_states, replay_reset_u and obs are [N*2] rows.    */
 #ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
 int mdpp_discrete_reset(mdpp_ctx* ctx, const mdpp_discrete_state* st,
                         const uint8_t* mask, const int32_t* init_states,
@@ -286,7 +301,10 @@ typedef struct mdpp_image_discrete_tables {
   int32_t n_xvar, n_yvar;          /* vertex-offset variants per (state, R)  */
   int32_t has_scale, has_shift, has_rotate, has_flip;
   int32_t sh_quant, ro_quant;
-  int32_t reserved0;
+  int32_t n_sub_images;            /* 0 / 1: one image per env; 2: the images
+                                      of the (relevant, irrelevant) sub-states,
+                                      consecutive in `states` and `out`, i.e.
+                                      stacked along x (:272-288)              */
   const uint64_t* mask_bits;       /* [n_masks][64] row bitmaps              */
   const int32_t* mask_index;       /* [S][n_radii][n_xvar][n_yvar]           */
   const uint8_t* xvar;             /* [S][n_radii][width]  by shift_w        */
@@ -298,7 +316,8 @@ typedef struct mdpp_image_discrete_tables {
 #ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
 /* Renders n_images polygon images.  Image m belongs to env (m % n_envs) at
  * step opts->step_index + m / n_envs (so a [T][N] block of states renders in
- * one launch).  params_in [n_images][5] = (R, shift_w, shift_h, rotation or
+ * one launch); with n_sub_images = 2, m / 2 takes that role and sub-image
+ * m % 2 draws from Philox stream image_stream + 16 * (m % 2).  params_in [n_images][5] = (R, shift_w, shift_h, rotation or
  * -1, flip 0/1 LR/2 TB) replays recorded transforms; NULL draws them from
  * Philox (stream `image_stream`: 3 for step observations, 6 for reset
  * observations).  params_out (optional) receives the parameters used.      */

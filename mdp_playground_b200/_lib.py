@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # MDPP_LIB: A/B timing of two builds (tools/); the default is the in-tree library
 LIB_PATH = os.environ.get("MDPP_LIB") or os.path.join(HERE, "libmdpp_b200.so")
 
+ABI_VERSION = 2  # MDPP_ABI_VERSION of include/mdpp_b200.h
 MDPP_NOISE_OFF, MDPP_NOISE_REPLAY, MDPP_NOISE_PHILOX = 0, 1, 2
 MDPP_N_STATS = 8
 MDPP_NORMAL_F64, MDPP_NORMAL_FAST = 0, 1
@@ -44,6 +45,9 @@ class DiscreteGroup(C.Structure):
         ("reward_matrix", C.c_void_p),
         ("env_begin", C.c_int64), ("env_count", C.c_int64),
         ("global_id_base", C.c_int64),
+        ("n_states_irr", C.c_int32), ("n_actions_irr", C.c_int32),
+        ("transition_irr", C.c_void_p), ("init_cdf_irr", C.c_void_p),
+        ("noise_cdf_irr", C.c_void_p),
     ]
 
 
@@ -55,6 +59,7 @@ class DiscreteState(C.Structure):
         ("ring", C.c_void_p),
         ("ring_depth", C.c_int32), ("history_depth", C.c_int32),
         ("history", C.c_void_p), ("stats", C.c_void_p),
+        ("cur_state_irr", C.c_void_p),
     ]
 
 
@@ -122,7 +127,8 @@ class ImageDiscreteTables(C.Structure):
         ("n_xvar", C.c_int32), ("n_yvar", C.c_int32),
         ("has_scale", C.c_int32), ("has_shift", C.c_int32),
         ("has_rotate", C.c_int32), ("has_flip", C.c_int32),
-        ("sh_quant", C.c_int32), ("ro_quant", C.c_int32), ("reserved0", C.c_int32),
+        ("sh_quant", C.c_int32), ("ro_quant", C.c_int32),
+        ("n_sub_images", C.c_int32),
         ("mask_bits", C.c_void_p), ("mask_index", C.c_void_p),
         ("xvar", C.c_void_p), ("yvar", C.c_void_p), ("rot_coeff", C.c_void_p),
         ("r_thresholds", C.c_void_p),
@@ -193,7 +199,7 @@ def load():
         C.c_int32, C.POINTER(StepOpts), P]
     lib.mdpp_render_continuous.argtypes = [
         P, C.POINTER(ImageContinuousConfig), P, P, C.c_int64, P]
-    if lib.mdpp_abi_version() != 1:
+    if lib.mdpp_abi_version() != ABI_VERSION:
         raise RuntimeError("libmdpp_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

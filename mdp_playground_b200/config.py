@@ -57,6 +57,9 @@ class EnvSpec:
     diameter: int = 1
     action_space_size: int = 0
     state_space_size: int = 0
+    irrelevant_features: bool = False  # discrete: a second, reward-free sub-MDP
+    action_space_size_irr: int = 0
+    state_space_size_irr: int = 0
     dtype_s: Any = None
     dtype_o: Any = None
     # continuous
@@ -125,9 +128,7 @@ def parse_config(config):
     sp.transition_noise = float(g("transition_noise") or 0.0)
     sp.reward_scale = float(g("reward_scale", 1.0))
     sp.reward_shift = float(g("reward_shift", 0.0))
-    if g("irrelevant_features", False) and kind == "discrete":
-        raise NotImplementedError(
-            "discrete irrelevant_features is a 'next' row (SURVEY.md 8f N2)")
+    sp.irrelevant_features = bool(g("irrelevant_features", False))
     sp.image_representations = bool(g("image_representations", False))
     if "image_transforms" in config:
         assert kind == "discrete", \
@@ -165,10 +166,22 @@ def parse_config(config):
 
     if kind == "discrete":  # :570-591
         sp.dtype_s = g("dtype_s", np.int64)
-        assert isinstance(config["action_space_size"], int), (
-            "Did you mean to turn irrelevant_features? If not, please provide "
-            "an int for action_space_size.")
-        sp.action_space_size = config["action_space_size"]
+        if sp.irrelevant_features:  # :574-578, sizes are [relevant, irrelevant]
+            assert len(config["action_space_size"]) == 2, (
+                "Currently, 1st sub-state (and action) space is assumed to be "
+                "relevant to rewards and 2nd one is irrelevant. Please provide "
+                "a list with sizes for the 2.")
+            if sp.use_custom_mdp:
+                raise NotImplementedError(
+                    "irrelevant_features with use_custom_mdp")
+            sp.action_space_size = int(config["action_space_size"][0])
+            sp.action_space_size_irr = int(config["action_space_size"][1])
+            sp.state_space_size_irr = sp.action_space_size_irr * sp.diameter
+        else:
+            assert isinstance(config["action_space_size"], int), (
+                "Did you mean to turn irrelevant_features? If not, please "
+                "provide an int for action_space_size.")
+            sp.action_space_size = config["action_space_size"]
         if sp.use_custom_mdp:
             sp.state_space_size = int(config["state_space_size"])
         else:

@@ -103,6 +103,7 @@ extern "C" int mdpp_set_discrete_groups(mdpp_ctx* ctx,
   int64_t next_env = 0;
   ctx->max_group_blob = 0;
   ctx->max_delay = 0;
+  ctx->d_irr = groups[0].n_states_irr > 0;
   for (int g = 0; g < n_groups; ++g) {
     const mdpp_discrete_group& in = groups[g];
     DiscreteGroupDev& d = dev[g];
@@ -115,6 +116,13 @@ extern "C" int mdpp_set_discrete_groups(mdpp_ctx* ctx,
       return fail(ctx, MDPP_EINVAL, "discrete group: missing table");
     if (in.has_transition_noise && !in.noise_cdf)
       return fail(ctx, MDPP_EINVAL, "transition noise needs noise_cdf");
+    if ((in.n_states_irr > 0) != (ctx->d_irr != 0))
+      return fail(ctx, MDPP_EINVAL,
+                  "all groups must agree on having an irrelevant sub-MDP");
+    if (in.n_states_irr > 0 &&
+        (in.n_states_irr > 65535 || in.n_actions_irr < 1 || !in.transition_irr ||
+         !in.init_cdf_irr || (in.has_transition_noise && !in.noise_cdf_irr)))
+      return fail(ctx, MDPP_EINVAL, "discrete group: bad irrelevant sub-MDP");
     if (in.env_begin != next_env || in.env_count < 0)
       return fail(ctx, MDPP_EINVAL,
                   "groups must tile the env range contiguously, in order");
@@ -185,17 +193,47 @@ extern "C" int mdpp_set_discrete_groups(mdpp_ctx* ctx,
     // other states (every state within 2^-32 of its probability; k <= S-2
     // because M is rounded down).  The noisy state is k + (k >= P[s,a]).  Only
     // that last step depends on the env state; the rest is drawn ahead.
-    if (in.has_transition_noise && S >= 2) {
+    auto noise_params = [&](int n_states, uint32_t* pn_M, int32_t* pn_shift) {
       double t = std::floor(in.transition_noise * 4294967296.0 + 0.5);
       uint64_t T = t <= 0.0 ? 0ull : t >= 4294967296.0 ? (1ull << 32) : (uint64_t)t;
       d.pn_T = T;
       if (T > 0) {
         int sh = 63;
         unsigned __int128 M;
-        while (((M = (((unsigned __int128)(S - 1)) << sh) / T) >> 32) && sh > 32) --sh;
+        while (((M = (((unsigned __int128)(n_states - 1)) << sh) / T) >> 32) && sh > 32) --sh;
         // T < S-1 (p below ~S 2^-32) cannot be uniform over the others anyway
-        d.pn_M = (M >> 32) ? 0xFFFFFFFFu : (uint32_t)M;
-        d.pn_shift = sh - 32;
+        *pn_M = (M >> 32) ? 0xFFFFFFFFu : (uint32_t)M;
+        *pn_shift = sh - 32;
+      }
+    };
+    if (in.has_transition_noise && S >= 2) noise_params(S, &d.pn_M, &d.pn_shift);
+    if (in.n_states_irr > 0) {  // the irrelevant sub-MDP's tables, same formats
+      const int S1 = in.n_states_irr, A1 = in.n_actions_irr;
+      d.S1 = S1; d.A1 = A1;
+      for (int i = 0; i < S1 * A1; ++i)
+        if (in.transition_irr[i] < 0 || in.transition_irr[i] >= S1)
+          return fail(ctx, MDPP_EINVAL, "irrelevant transition entry out of range");
+      d.off_P_irr = reserve(S1 * A1 * 2, 16);
+      {
+        uint16_t* P = reinterpret_cast<uint16_t*>(gb.data() + d.off_P_irr);
+        for (int i = 0; i < S1 * A1; ++i) P[i] = (uint16_t)in.transition_irr[i];
+      }
+      int lg = 0;
+      while ((1 << lg) < S1) ++lg;
+      const int S1p = 1 << lg;
+      d.irr_cdf_log2 = lg;
+      d.irr_cdf_stride = S1p;
+      auto put_row1 = [&](double* dst, const double* src) {
+        for (int k = 0; k < S1p; ++k) dst[k] = k < S1 ? src[k] : 2.0;
+      };
+      d.off_init_cdf_irr = reserve(S1p * 8, 16);
+      put_row1(reinterpret_cast<double*>(gb.data() + d.off_init_cdf_irr), in.init_cdf_irr);
+      if (in.has_transition_noise) {
+        d.off_noise_cdf_irr = reserve(S1 * S1p * 8, 16);
+        for (int r = 0; r < S1; ++r)
+          put_row1(reinterpret_cast<double*>(gb.data() + d.off_noise_cdf_irr) + (size_t)r * S1p,
+                   in.noise_cdf_irr + (size_t)r * S1);
+        if (S1 >= 2) noise_params(S1, &d.irr_pn_M, &d.irr_pn_shift);
       }
     }
     if (S <= 64)

@@ -30,6 +30,12 @@ struct DiscreteGroupDev {
   int64_t blob_offset;  // of this group's blob inside the context blob buffer
   int64_t env_begin, env_count;
   int64_t gid_base;  // global Philox id of the group's first env
+  // irrelevant sub-MDP (S1 == 0: none): u16 table, padded cdfs like above
+  int32_t S1, A1, irr_cdf_log2, irr_cdf_stride;
+  int32_t off_P_irr, off_init_cdf_irr, off_noise_cdf_irr;
+  int32_t irr_pn_shift;
+  uint32_t irr_pn_M;  // noisy iff w < pn_T (same p); index among the S1-1 others
+  uint32_t pad0;
 };
 
 struct CtaMapEntry {
@@ -64,6 +70,7 @@ struct RolloutParams {
   uint64_t step_index;
   const uint64_t* step_index_dev;  // optional device counter added to step_index
   int64_t env_id_offset;
+  int32_t irr;  // every group has an irrelevant sub-MDP: I/O rows of 2
 };
 
 struct ResetParams {
@@ -79,6 +86,7 @@ struct ResetParams {
   uint32_t k0, k1;
   uint64_t step_index;
   int64_t env_id_offset;
+  int32_t irr;
 };
 
 }  // namespace mdpp

@@ -21,36 +21,56 @@ discrete_reset_kernel(const __grid_constant__ ResetParams p) {
   if (local >= g.env_count) return;
   const int64_t env = g.env_begin + local;
   const int64_t N = p.st.n_envs;
+  const bool irr = p.irr != 0;  // rows (relevant, irrelevant) in init / u / obs
   if (p.mask && !p.mask[env]) {
-    if (p.obs) p.obs[env] = p.st.cur_state[env];
+    if (p.obs && irr) {
+      p.obs[2 * env] = p.st.cur_state[env];
+      p.obs[2 * env + 1] = p.st.cur_state_irr[env];
+    } else if (p.obs) {
+      p.obs[env] = p.st.cur_state[env];
+    }
     return;
   }
   const uint32_t gid = (uint32_t)(p.env_id_offset + g.gid_base + local);
   const uint32_t ep = p.st.episode[env];
-  int32_t s0;
+  int32_t s0, s0_irr = 0;
   if (p.init_states) {
-    s0 = p.init_states[env];
+    s0 = p.init_states[irr ? 2 * env : env];
+    if (irr) s0_irr = p.init_states[2 * env + 1];
   } else {
-    double u;
+    double u, u_irr = 0.0;
     if (p.noise_mode == MDPP_NOISE_REPLAY) {
-      u = p.replay_reset_u[env];
+      u = p.replay_reset_u[irr ? 2 * env : env];
+      if (irr) u_irr = p.replay_reset_u[2 * env + 1];
     } else {
       U4 w = philox4x32_10(gid, ep, 0u, STREAM_RESET, p.k0, p.k1);
       u = uniform53(w.x, w.y);
+      u_irr = uniform53(w.z, w.w);  // second E draw of reset() (:2260-2264)
     }
     const double* cdf =
         reinterpret_cast<const double*>(p.blob + g.blob_offset + g.off_init_cdf);
     s0 = cdf_search<-1>(cdf, g.cdf_log2, g.S, u);
+    if (irr) {
+      const double* cdf1 = reinterpret_cast<const double*>(
+          p.blob + g.blob_offset + g.off_init_cdf_irr);
+      s0_irr = cdf_search<-1>(cdf1, g.irr_cdf_log2, g.S1, u_irr);
+    }
   }
   if (p.st.stats && p.st.t_episode[env] > 0)
     atomicAdd(p.st.stats + (int64_t)me.group * MDPP_N_STATS + MDPP_STAT_EPISODES, 1.0);
   p.st.cur_state[env] = s0;
+  if (irr) p.st.cur_state_irr[env] = min(max(s0_irr, 0), g.S1 - 1);
   p.st.seq_key[env] = (uint64_t)s0;
   p.st.t_episode[env] = 0;
   p.st.episode[env] = ep + 1;
   if (p.st.history)
     p.st.history[(int64_t)(p.step_index % (uint64_t)p.st.history_depth) * N + env] = s0;
-  if (p.obs) p.obs[env] = s0;
+  if (p.obs && irr) {
+    p.obs[2 * env] = s0;
+    p.obs[2 * env + 1] = p.st.cur_state_irr[env];
+  } else if (p.obs) {
+    p.obs[env] = s0;
+  }
 }
 
 static int ensure_cta_map(mdpp_ctx* ctx) {
@@ -89,6 +109,8 @@ static int check_state(mdpp_ctx* ctx, const mdpp_discrete_state* st) {
     return fail(ctx, MDPP_EINVAL, "delay ring missing or too shallow");
   if (st->history && st->history_depth < 1)
     return fail(ctx, MDPP_EINVAL, "history_depth must be >= 1");
+  if (ctx->d_irr && !st->cur_state_irr)
+    return fail(ctx, MDPP_EINVAL, "irrelevant sub-MDP: cur_state_irr is NULL");
   return MDPP_OK;
 }
 
@@ -131,6 +153,7 @@ extern "C" int mdpp_discrete_rollout(mdpp_ctx* ctx,
   p.step_index = opts->step_index;
   p.step_index_dev = opts->step_index_dev;
   p.env_id_offset = opts->env_id_offset;
+  p.irr = ctx->d_irr;
   cudaStream_t s = (cudaStream_t)cuda_stream;
   if (opts->noise_mode < MDPP_NOISE_OFF || opts->noise_mode > MDPP_NOISE_PHILOX)
     return fail(ctx, MDPP_EINVAL, "unknown noise_mode");
@@ -176,6 +199,7 @@ extern "C" int mdpp_discrete_reset(mdpp_ctx* ctx, const mdpp_discrete_state* st,
   p.k1 = (uint32_t)(opts->seed >> 32);
   p.step_index = opts->step_index;
   p.env_id_offset = opts->env_id_offset;
+  p.irr = ctx->d_irr;
   discrete_reset_kernel<<<(unsigned)ctx->n_ctas, kBlock, 0,
                           (cudaStream_t)cuda_stream>>>(p);
   MDPP_CUDA(ctx, cudaGetLastError());

@@ -64,6 +64,34 @@ __device__ __forceinline__ int horizon_of(const RolloutParams& p) {
 #endif
 }
 
+// irrelevant_features: launch-wide (all groups agree, context.cu).  The
+// ahead-of-time FAST kernels never see it (discrete_launch.h routes such
+// launches to the generic variants), a specialised build gets a literal.
+template <typename C>
+__device__ __forceinline__ bool irr_of(const RolloutParams& p) {
+#ifdef MDPP_JIT
+  return MDPP_IRR != 0;
+#else
+  return !C::FAST && p.irr != 0;
+#endif
+}
+
+__device__ __forceinline__ int2 ld_stream_i32x2(const int32_t* p) {
+  int2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];"
+               : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ld_stream_f64x2(const double* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+               : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream_x2(int64_t* p, int64_t a, int64_t b) {
+  asm volatile("st.global.cs.v2.s64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+
 __device__ __forceinline__ int32_t ld_stream_i32(const int32_t* p) {
   int32_t v;
   asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -134,6 +162,12 @@ struct GroupView {  // per-thread copy of the scalars + table pointers
   const uint32_t* hash_vals;
   const double* values;
   const double* R;
+  // irrelevant sub-MDP
+  int S1, A1, irr_cdf_log2, irr_cdf_stride, irr_pn_shift;
+  uint32_t irr_pn_M;
+  const uint16_t* P_irr;
+  const double* init_cdf_irr;
+  const double* noise_cdf_irr;
 };
 
 __device__ __forceinline__ GroupView make_view(const DiscreteGroupDev& g,
@@ -160,6 +194,12 @@ __device__ __forceinline__ GroupView make_view(const DiscreteGroupDev& g,
   v.hash_vals = reinterpret_cast<const uint32_t*>(tab + g.off_hash_vals);
   v.values = reinterpret_cast<const double*>(tab + g.off_values);
   v.R = reinterpret_cast<const double*>(tab + g.off_R);
+  v.S1 = g.S1; v.A1 = g.A1;
+  v.irr_cdf_log2 = g.irr_cdf_log2; v.irr_cdf_stride = g.irr_cdf_stride;
+  v.irr_pn_M = g.irr_pn_M; v.irr_pn_shift = g.irr_pn_shift;
+  v.P_irr = reinterpret_cast<const uint16_t*>(tab + g.off_P_irr);
+  v.init_cdf_irr = reinterpret_cast<const double*>(tab + g.off_init_cdf_irr);
+  v.noise_cdf_irr = reinterpret_cast<const double*>(tab + g.off_noise_cdf_irr);
 #ifdef MDPP_JIT
   // Runtime-compiled specialisation (jit.cu): every group scalar that is the
   // same for all groups of the launch arrives as a literal, so the compiler
@@ -246,6 +286,7 @@ constexpr int kMaxRingRegs = 4;
 
 struct EnvRegs {
   int32_t s;
+  int32_t s_irr;  // irrelevant sub-state (irrelevant_features)
   uint64_t key;
   int32_t tl;
   int32_t phase;  // tl % every_n, tracked incrementally (no division per step)
@@ -320,18 +361,42 @@ struct Cfg {
 // on the last chunk of a launch (guards the action / replay loads).
 // PRELOADED: act[] already holds the chunk's actions (prefetched by the
 // caller one chunk ahead, see rollout_body).
+
+// The same quantities for the irrelevant sub-MDP (irrelevant_features): dead
+// code, hence no registers, in builds without one.
+template <int U>
+struct IrrDraws {
+  int32_t act[U];
+  double u_tr[U];
+  int32_t k_tr[U];
+  int32_t s0[U];
+};
+
+template <typename C>
+__device__ __forceinline__ void load_action(const RolloutParams& p, int64_t off,
+                                            int32_t& a, int32_t& a_irr) {
+  if (irr_of<C>(p)) {  // rows (relevant, irrelevant): one 8-byte load
+    const int2 v = ld_stream_i32x2(p.io.actions + 2 * off);
+    a = v.x; a_irr = v.y;
+  } else {
+    a = ld_stream_i32(p.io.actions + off); a_irr = 0;
+  }
+}
+
 template <typename C, int U, bool PRELOADED = false>
 __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView& v,
                                         int64_t env, uint32_t gid,
                                         uint64_t step_base, int t0,
                                         int n_valid, int32_t* act, double* u_tr,
-                                        int32_t* k_tr, double* n_rw, int32_t* s0) {
+                                        int32_t* k_tr, double* n_rw, int32_t* s0,
+                                        IrrDraws<U>& q) {
   constexpr int NOISE = C::NOISE;
   constexpr int NORMAL = C::NORMAL;
   constexpr bool FAST = C::FAST;
   const int64_t N = n_envs_of(p);
   const bool autoreset = autoreset_of(p);
-  double u_rs[U];
+  const bool irr = irr_of<C>(p);
+  double u_rs[U], u_rs_i[U];
   const int64_t off0 = (int64_t)t0 * N + env;
   const uint64_t step0 = step_base + (uint64_t)t0;
   const bool have_actions = FAST || p.io.actions != nullptr;
@@ -341,18 +406,31 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
     const uint64_t step = step0 + (uint64_t)j;
     if (PRELOADED) {
     } else if (have_actions) {
-      act[j] = 0;
-      if (j < n_valid) act[j] = ld_stream_i32(p.io.actions + off);
+      act[j] = 0; q.act[j] = 0;
+      if (j < n_valid) load_action<C>(p, off, act[j], q.act[j]);
     } else {
       U4 w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
                            STREAM_ACTION, p.k0, p.k1);
       act[j] = (int32_t)__umulhi(w.x, (uint32_t)v.A);
+      q.act[j] = irr ? (int32_t)__umulhi(w.y, (uint32_t)v.A1) : 0;
     }
     u_tr[j] = 0.0; k_tr[j] = -1; n_rw[j] = 0.0; u_rs[j] = 0.0; s0[j] = 0;
+    q.u_tr[j] = 0.0; q.k_tr[j] = -1; q.s0[j] = 0; u_rs_i[j] = 0.0;
     if (NOISE == MDPP_NOISE_REPLAY && j < n_valid) {
-      if (v.has_pnoise) u_tr[j] = ld_stream_f64(p.io.replay_transition_u + off);
+      if (irr) {  // rows (relevant, irrelevant)
+        if (v.has_pnoise) {
+          const double2 u = ld_stream_f64x2(p.io.replay_transition_u + 2 * off);
+          u_tr[j] = u.x; q.u_tr[j] = u.y;
+        }
+        if (autoreset) {
+          const double2 u = ld_stream_f64x2(p.io.replay_reset_u + 2 * off);
+          u_rs[j] = u.x; u_rs_i[j] = u.y;
+        }
+      } else {
+        if (v.has_pnoise) u_tr[j] = ld_stream_f64(p.io.replay_transition_u + off);
+        if (autoreset) u_rs[j] = ld_stream_f64(p.io.replay_reset_u + off);
+      }
       if (v.has_rnoise) n_rw[j] = ld_stream_f64(p.io.replay_reward_noise + off);
-      if (autoreset) u_rs[j] = ld_stream_f64(p.io.replay_reset_u + off);
     }
   }
   uint32_t w_rs[U], w_tr[U];
@@ -367,10 +445,10 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
       uint32_t u4[4] = {0, 0, 0, 0}, r4[4] = {0, 0, 0, 0};
       philox_quad_draws<NORMAL>(gid, step0 >> 2, p.rk, want_u, want_z,
                                 want_r, u4, z4, r4);
-      const int q = (int)(step0 & 3);
-      w_tr[0] = q == 0 ? u4[0] : q == 1 ? u4[1] : q == 2 ? u4[2] : u4[3];
-      double z = q == 0 ? z4[0] : q == 1 ? z4[1] : q == 2 ? z4[2] : z4[3];
-      w_rs[0] = q == 0 ? r4[0] : q == 1 ? r4[1] : q == 2 ? r4[2] : r4[3];
+      const int q4 = (int)(step0 & 3);
+      w_tr[0] = q4 == 0 ? u4[0] : q4 == 1 ? u4[1] : q4 == 2 ? u4[2] : u4[3];
+      double z = q4 == 0 ? z4[0] : q4 == 1 ? z4[1] : q4 == 2 ? z4[2] : z4[3];
+      w_rs[0] = q4 == 0 ? r4[0] : q4 == 1 ? r4[1] : q4 == 2 ? r4[2] : r4[3];
       n_rw[0] = __dmul_rn(v.r_std, z);
     } else {  // chunks start on a multiple-of-4 step (see the callers)
 #pragma unroll
@@ -419,6 +497,58 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
       }
     }
   }
+  if (irr) {
+    // the irrelevant sub-MDP's own words: STREAM_IRR_STEP / _AUTORESET, word j
+    // of quad (step >> 2) like the relevant streams
+    if (NOISE != MDPP_NOISE_REPLAY) {
+      const bool want_u = NOISE == MDPP_NOISE_PHILOX && v.has_pnoise;
+      uint32_t wi_tr[U], wi_rs[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) wi_tr[j] = wi_rs[j] = 0;
+      if (U == 1) {
+        const uint64_t quad = step0 >> 2;
+        const int q4 = (int)(step0 & 3);
+        if (want_u) {
+          U4 w = philox4x32_10_rk(gid, (uint32_t)quad, (uint32_t)(quad >> 32),
+                                  STREAM_IRR_STEP, p.rk);
+          wi_tr[0] = q4 == 0 ? w.x : q4 == 1 ? w.y : q4 == 2 ? w.z : w.w;
+        }
+        if (autoreset) {
+          U4 w = philox4x32_10_rk(gid, (uint32_t)quad, (uint32_t)(quad >> 32),
+                                  STREAM_IRR_AUTORESET, p.rk);
+          wi_rs[0] = q4 == 0 ? w.x : q4 == 1 ? w.y : q4 == 2 ? w.z : w.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j + 3 < U; j += 4) {
+          const uint64_t quad = (step0 + j) >> 2;
+          if (want_u) {
+            U4 w = philox4x32_10_rk(gid, (uint32_t)quad, (uint32_t)(quad >> 32),
+                                    STREAM_IRR_STEP, p.rk);
+            wi_tr[j] = w.x; wi_tr[j + 1] = w.y; wi_tr[j + 2] = w.z; wi_tr[j + 3] = w.w;
+          }
+          if (autoreset) {
+            U4 w = philox4x32_10_rk(gid, (uint32_t)quad, (uint32_t)(quad >> 32),
+                                    STREAM_IRR_AUTORESET, p.rk);
+            wi_rs[j] = w.x; wi_rs[j + 1] = w.y; wi_rs[j + 2] = w.z; wi_rs[j + 3] = w.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        if (want_u) {
+          const uint32_t k = __umulhi(wi_tr[j], v.irr_pn_M) >> v.irr_pn_shift;
+          q.k_tr[j] = ((uint64_t)wi_tr[j] < v.pn_T) ? (int32_t)k : -1;
+        }
+        u_rs_i[j] = uniform32(wi_rs[j]);
+      }
+    }
+    if (autoreset) {
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        q.s0[j] = cdf_search<-1>(v.init_cdf_irr, v.irr_cdf_log2, v.S1, u_rs_i[j]);
+    }
+  }
 }
 
 // ---- phase B: the state-dependent chain -----------------------------------
@@ -428,13 +558,30 @@ __device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupVi
                                            EnvRegs& e, double* ring_smem,
                                            int ring_stride, int64_t env, int64_t off,
                                            int32_t act, double u_tr, int32_t k_tr,
-                                           double n_rw, int32_t s0) {
+                                           double n_rw, int32_t s0,
+                                           int32_t act_i, double u_tr_i,
+                                           int32_t k_tr_i, int32_t s0_i) {
   constexpr int NOISE = C::NOISE;
   constexpr bool RING_SMEM = C::RING_SMEM;
   constexpr bool FAST = C::FAST;
   const int64_t N = n_envs_of(p);
   const bool autoreset = autoreset_of(p);
   const int horizon = horizon_of(p);
+  const bool irr = irr_of<C>(p);
+  if (irr) {
+    // the irrelevant sub-MDP (rl_toy_env.py:2062-2082): same table walk and
+    // noisy redraw, no reward, no terminal states
+    uint32_t ai = (uint32_t)act_i;
+    if (ai >= (uint32_t)v.A1) ai = (uint32_t)v.A1 - 1;  // memory safety only
+    int32_t nxt_i = v.P_irr[e.s_irr * v.A1 + (int32_t)ai];
+    if (NOISE == MDPP_NOISE_REPLAY && v.has_pnoise) {
+      nxt_i = cdf_search<-1>(v.noise_cdf_irr + nxt_i * v.irr_cdf_stride,
+                             v.irr_cdf_log2, v.S1, u_tr_i);
+    } else if (NOISE == MDPP_NOISE_PHILOX && v.has_pnoise) {
+      if (k_tr_i >= 0) nxt_i = k_tr_i + (k_tr_i >= nxt_i);
+    }
+    e.s_irr = nxt_i;
+  }
   uint32_t a = (uint32_t)act;
   if (a >= (uint32_t)v.A) a = (uint32_t)v.A - 1;  // memory safety only
   int32_t nxt = v.P[e.s * v.A + (int32_t)a];
@@ -494,9 +641,13 @@ __device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupVi
   const bool trunc = horizon > 0 && e.tl >= horizon;
   e.n_terminated += done;
   e.s = nxt;
-  if (!FAST && p.io.final_obs) st_stream(p.io.final_obs + off, (int64_t)nxt);
+  if (!FAST && p.io.final_obs) {
+    if (irr) st_stream_x2(p.io.final_obs + 2 * off, (int64_t)nxt, (int64_t)e.s_irr);
+    else st_stream(p.io.final_obs + off, (int64_t)nxt);
+  }
   if (autoreset && (done || trunc)) {
     e.s = s0;
+    if (irr) e.s_irr = s0_i;
     e.key = (uint64_t)e.s;
     e.tl = 0;
     e.phase = 0;
@@ -507,7 +658,10 @@ __device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupVi
     p.st.history[(int64_t)e.hist_pos * N + env] = e.s;
     e.hist_pos = (e.hist_pos + 1 == p.st.history_depth) ? 0 : e.hist_pos + 1;
   }
-  if (FAST || p.io.obs) st_stream(p.io.obs + off, (int64_t)e.s);
+  if (FAST || p.io.obs) {
+    if (irr) st_stream_x2(p.io.obs + 2 * off, (int64_t)e.s, (int64_t)e.s_irr);
+    else st_stream(p.io.obs + off, (int64_t)e.s);
+  }
   if (FAST || p.io.reward) st_stream(p.io.reward + off, r);
   if (FAST || p.io.terminated) st_stream(p.io.terminated + off, (uint8_t)done);
   if (FAST || p.io.truncated) st_stream(p.io.truncated + off, (uint8_t)trunc);
@@ -519,29 +673,34 @@ __device__ __forceinline__ void phase_b(const RolloutParams& p, const GroupView&
                                         int64_t env, int t0, int n_valid,
                                         const int32_t* act, const double* u_tr,
                                         const int32_t* k_tr, const double* n_rw,
-                                        const int32_t* s0) {
+                                        const int32_t* s0, const IrrDraws<U>& q) {
   const int64_t N = n_envs_of(p);
   const int64_t off0 = (int64_t)t0 * N + env;
 #pragma unroll
   for (int j = 0; j < U; ++j) {
     if (PARTIAL && j >= n_valid) break;
     chain_step<C>(p, v, e, ring_smem, ring_stride, env, off0 + (int64_t)j * N,
-                  act[j], u_tr[j], k_tr[j], n_rw[j], s0[j]);
+                  act[j], u_tr[j], k_tr[j], n_rw[j], s0[j],
+                  q.act[j], q.u_tr[j], q.k_tr[j], q.s0[j]);
   }
   e.n_steps += PARTIAL ? n_valid : U;
 }
 
-// A full chunk whose actions were prefetched into act[].
+// A full chunk whose actions were prefetched into act[] (and act_i[]).
 template <typename C, int U>
 __device__ __forceinline__ void run_chunk_preloaded(
     const RolloutParams& p, const GroupView& v, EnvRegs& e, double* ring_smem,
-    int64_t env, uint32_t gid, uint64_t step_base, int t0, int32_t* act) {
+    int64_t env, uint32_t gid, uint64_t step_base, int t0, int32_t* act,
+    const int32_t* act_i) {
   int32_t s0[U], k_tr[U];
   double u_tr[U], n_rw[U];
+  IrrDraws<U> q;
+#pragma unroll
+  for (int j = 0; j < U; ++j) q.act[j] = act_i[j];
   phase_a<C, U, true>(p, v, env, gid, step_base, t0, U, act, u_tr, k_tr,
-                            n_rw, s0);
+                            n_rw, s0, q);
   phase_b<C, U, false>(p, v, e, ring_smem, kBlock, env, t0, U, act, u_tr, k_tr,
-                       n_rw, s0);
+                       n_rw, s0, q);
 }
 
 template <typename C, int U>
@@ -552,9 +711,10 @@ __device__ __forceinline__ void run_chunk(const RolloutParams& p,
   int32_t act[U], s0[U];
   int32_t k_tr[U];
   double u_tr[U], n_rw[U];
-  phase_a<C, U>(p, v, env, gid, step_base, t0, U, act, u_tr, k_tr, n_rw, s0);
+  IrrDraws<U> q;
+  phase_a<C, U>(p, v, env, gid, step_base, t0, U, act, u_tr, k_tr, n_rw, s0, q);
   phase_b<C, U, false>(p, v, e, ring_smem, kBlock, env, t0, U, act, u_tr, k_tr,
-                       n_rw, s0);
+                       n_rw, s0, q);
 }
 
 __device__ __forceinline__ double warp_sum(double x) {
@@ -601,6 +761,8 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
   e.key = p.st.seq_key[env];
   e.tl = p.st.t_episode[env];
   e.ep = p.st.episode[env];
+  const bool irr = irr_of<C>(p);
+  e.s_irr = irr ? p.st.cur_state_irr[env] : 0;
   e.phase = e.tl % v.every_n;
   // global index of the launch's first step (+ the optional device counter
   // that lets a captured CUDA graph advance between replays)
@@ -636,24 +798,26 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
       // stream a read takes longer than phase A (ncu: 28 % of all stall
       // samples sat on the first use of an action), a whole chunk hides it.
       // The last prefetch re-reads the final chunk instead of branching.
-      int32_t act_next[kChunk];
+      int32_t act_next[kChunk], act_next_i[kChunk];
       const int t_last = p.T - kChunk;  // start of the last possible chunk
+#pragma unroll
+      for (int j = 0; j < kChunk; ++j) act_next[j] = act_next_i[j] = 0;
       if (t0 <= t_last) {
 #pragma unroll
-        for (int j = 0; j < kChunk; ++j) {
-          act_next[j] = ld_stream_i32(p.io.actions + (int64_t)(t0 + j) * N + env);
-        }
+        for (int j = 0; j < kChunk; ++j)
+          load_action<C>(p, (int64_t)(t0 + j) * N + env, act_next[j], act_next_i[j]);
       }
       for (; t0 <= t_last; t0 += kChunk) {
-        int32_t act[kChunk];
+        int32_t act[kChunk], act_i[kChunk];
         const int tn = min(t0 + kChunk, t_last);
 #pragma unroll
         for (int j = 0; j < kChunk; ++j) {
           act[j] = act_next[j];
-          act_next[j] = ld_stream_i32(p.io.actions + (int64_t)(tn + j) * N + env);
+          act_i[j] = act_next_i[j];
+          load_action<C>(p, (int64_t)(tn + j) * N + env, act_next[j], act_next_i[j]);
         }
         run_chunk_preloaded<C, kChunk>(p, v, e, ring_smem, env, gid, step_base,
-                                       t0, act);
+                                       t0, act, act_i);
       }
     } else {
       for (; t0 + kChunk <= p.T; t0 += kChunk)
@@ -662,6 +826,7 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
     for (; t0 < p.T; ++t0)
       run_chunk<C, 1>(p, v, e, ring_smem, env, gid, step_base, t0);
     p.st.cur_state[env] = e.s;
+    if (irr) p.st.cur_state_irr[env] = e.s_irr;
     p.st.seq_key[env] = e.key;
     p.st.t_episode[env] = e.tl;
     p.st.episode[env] = e.ep;

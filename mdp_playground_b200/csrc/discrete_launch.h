@@ -35,7 +35,7 @@ inline int launch_rollout(mdpp_ctx* ctx, RolloutParams& p, cudaStream_t stream) 
   const bool smem_ok = smem_tab + ring_bytes <= ctx->max_smem_optin - 1024;
   const bool fast_io = p.io.actions && p.io.obs && p.io.reward &&
                        p.io.terminated && p.io.truncated && !p.io.final_obs &&
-                       !p.st.history;
+                       !p.st.history && !p.irr;  // (FAST kernels: no sub-MDP)
   if constexpr (NOISE != MDPP_NOISE_REPLAY) {
     if (smem_ok && ring_ok && fast_io && ctx->d_groups_host.size() == 1) {
       return ctx->d_groups_host[0].cdf_log2 == 3

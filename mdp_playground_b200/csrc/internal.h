@@ -24,6 +24,7 @@ struct mdpp_ctx {
   int max_group_blob = 0;
   int max_delay = 0;
   int64_t d_total_envs = 0;
+  int d_irr = 0;  // groups carry an irrelevant sub-MDP
   // CTA -> (group, chunk) map, one per supported block size
   mdpp::CtaMapEntry* d_cta_map = nullptr;
   int cta_map_block = 0;

@@ -143,6 +143,7 @@ std::vector<std::string> defines_for(const std::vector<DiscreteGroupDev>& groups
   d.push_back(D("CFG_RING_REGS",
                 I(UNIFORM(delay) && g.delay >= 1 && g.delay <= kMaxRingRegs ? g.delay : 0)));
 #undef UNIFORM
+  d.push_back(D("IRR", I(p.irr)));
   d.push_back(D("N_ENVS", I(p.st.n_envs) + "ll"));
   d.push_back(D("AUTORESET", I(p.autoreset)));
   d.push_back(D("HORIZON", I(p.horizon)));

@@ -18,6 +18,8 @@ enum PhiloxStream : uint32_t {
   STREAM_NORMAL = 4,     // (w0,w1),(w2,w3) -> two Box-Muller pairs (reward noise)
   STREAM_AUTORESET = 5,  // 32-bit uniforms of the same-step auto-reset
   STREAM_STATE_NOISE = 8,  // + pair index: continuous transition noise
+  STREAM_IRR_STEP = 32,       // like STREAM_STEP / STREAM_AUTORESET, for the
+  STREAM_IRR_AUTORESET = 33,  // irrelevant sub-MDP (irrelevant_features)
   STREAM_RESET_BOX = 64,   // + attempt*16 + dim/4 (continuous reset sampling)
 };
 

@@ -93,11 +93,13 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
   } else {
     // draw order of the reference (:149-181, :251, :258-259); one Philox
     // call per image: w0 scale, w1 / w2 shifts, w3 rotation + flip bits
-    const uint32_t gid = (uint32_t)(p.env_id_offset + m % p.n_envs);
-    const uint64_t step = p.step_index + (uint64_t)(m / p.n_envs) +
+    const int n_sub = max(tb.n_sub_images, 1);
+    const int64_t e = m / n_sub;  // (step, env); sub-image m % n_sub of it
+    const uint32_t gid = (uint32_t)(p.env_id_offset + e % p.n_envs);
+    const uint64_t step = p.step_index + (uint64_t)(e / p.n_envs) +
                           (p.step_index_dev ? *p.step_index_dev : 0ull);
-    U4 w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32), p.stream,
-                         p.k0, p.k1);
+    U4 w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
+                         p.stream + 16u * (uint32_t)(m % n_sub), p.k0, p.k1);
     R = tb.r_min;
     if (tb.has_scale) {  // R = r_min + #{thresholds <= u}, one lane each
       const double u = uniform32(w.x);

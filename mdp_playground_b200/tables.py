@@ -32,6 +32,12 @@ class DiscreteTables:
     sequence_rewards: np.ndarray  # float64 [n_seq]
     rewardable_sequences: Dict[tuple, float]  # incl. dead make_denser prefixes
     reward_matrix: Optional[np.ndarray]  # float64 [S, A] (custom MDP)
+    # irrelevant sub-MDP (irrelevant_features): own P, uniform start, own noise
+    n_states_irr: int = 0
+    n_actions_irr: int = 0
+    transition_irr: Optional[np.ndarray] = None      # int32 [S1, A1]
+    init_cdf_irr: Optional[np.ndarray] = None        # float64 [S1]
+    noise_cdf_irr: Optional[np.ndarray] = None       # float64 [S1, S1]
 
 
 def normalised_cdf(p):
@@ -83,6 +89,50 @@ def _next_set_probabilities(s, S, A):
     return prob
 
 
+def sub_space_rngs(sp: EnvSpec):
+    """Generators of observation_spaces[0] / [1] at table-generation time.
+    Without images the two sub-spaces of an irrelevant_features env are wrapped
+    in a TupleExtended seeded with an int (:738-741), and gymnasium 1.x
+    Tuple.seed re-seeds every sub-space with integers(int32.max, size=2) of
+    its own stream (parity of this cascade is unpinned by the reference,
+    SURVEY.md 8c; it matches oracle/gymnasium_standin)."""
+    sd = sp.seed_dict
+    if not sp.irrelevant_features:
+        return np_random(sd["relevant_state_space"])[0], None
+    if sp.image_representations:
+        return (np_random(sd["relevant_state_space"])[0],
+                np_random(sd["irrelevant_state_space"])[0])
+    rng_t, _ = np_random(sd["state_space"])
+    sub = rng_t.integers(np.iinfo(np.int32).max, size=2)
+    return np_random(int(sub[0]))[0], np_random(int(sub[1]))[0]
+
+
+def _transition_matrix_irr(sp: EnvSpec):
+    """init_transition_function, irrelevant part (:1154-1230): the next-set
+    probabilities are always passed to choice() and no state self-loops."""
+    S1, A1 = sp.state_space_size_irr, sp.action_space_size_irr
+    rng = sub_space_rngs(sp)[1]
+    P = np.full((S1, A1), -1, dtype=np.int64)
+    for s in range(S1):
+        p = _next_set_probabilities(s, S1, A1)
+        if sp.maximally_connected:
+            P[s] = np.squeeze(rng.choice(S1, size=A1, p=p, replace=False))
+        else:
+            for a in range(A1):
+                P[s, a] = int(np.squeeze(rng.choice(S1, size=1, p=p)))
+    return P.astype(np.int32)
+
+
+def _noise_cdf(p, S):
+    """Row s' = cdf of the noisy redraw around s' (:1605-1612)."""
+    cdf = np.empty((S, S), dtype=np.float64)
+    for nxt in range(S):
+        probs = np.ones((S,)) * p / (S - 1)
+        probs[nxt] = 1 - p
+        cdf[nxt] = normalised_cdf(probs)
+    return cdf
+
+
 def _transition_matrix(sp: EnvSpec, n_term):
     """init_transition_function (:1046-1152)."""
     cfg = sp.config
@@ -94,7 +144,7 @@ def _transition_matrix(sp: EnvSpec, n_term):
         P = np.asarray(P, dtype=np.int64)
         assert P.shape == (S, A), "custom transition_function must be [S, A]"
         return P.astype(np.int32)
-    rng, _ = np_random(sp.seed_dict["relevant_state_space"])
+    rng = sub_space_rngs(sp)[0]
     P = np.full((S, A), -1, dtype=np.int64)
     for s in range(S):
         if sp.maximally_connected:
@@ -195,14 +245,19 @@ def build_discrete_tables(sp: EnvSpec) -> DiscreteTables:
 
     noise_cdf = None
     if sp.transition_noise:  # falsy => the reference draws nothing (:1604)
-        p = sp.transition_noise
-        noise_cdf = np.empty((S, S), dtype=np.float64)
-        for nxt in range(S):
-            probs = np.ones((S,)) * p / (S - 1)
-            probs[nxt] = 1 - p
-            noise_cdf[nxt] = normalised_cdf(probs)
+        noise_cdf = _noise_cdf(sp.transition_noise, S)
+    irr = {}
+    if sp.irrelevant_features:
+        S1 = sp.state_space_size_irr
+        cfg["irrelevant_init_state_dist"] = np.array([1 / S1] * S1)  # :1024-1035
+        irr = dict(
+            n_states_irr=S1, n_actions_irr=sp.action_space_size_irr,
+            transition_irr=np.ascontiguousarray(_transition_matrix_irr(sp)),
+            init_cdf_irr=normalised_cdf(cfg["irrelevant_init_state_dist"]),
+            noise_cdf_irr=(_noise_cdf(sp.transition_noise, S1)
+                           if sp.transition_noise else None))
 
-    return DiscreteTables(
+    return DiscreteTables(**irr, 
         n_states=S, n_actions=A, transition=np.ascontiguousarray(P),
         terminal_states=term_states, terminal_mask=mask,
         init_state_dist=init_dist, init_cdf=normalised_cdf(init_dist),

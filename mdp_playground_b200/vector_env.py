@@ -158,6 +158,22 @@ class VectorRLToyEnv:
             tb.n_states, seed=self.seed_dict.get("relevant_state_space"))
         self.action_space = DiscreteSpace(
             tb.n_actions, seed=self.seed_dict.get("relevant_action_space"))
+        # irrelevant_features: a second sub-MDP; states, actions and
+        # observations become rows (relevant, irrelevant) -- the reference's
+        # tuples (rl_toy_env.py:2085-2088)
+        self._irr = bool(sp.irrelevant_features)
+        assert all(bool(s_.irrelevant_features) == self._irr for s_ in specs), \
+            "config_groups must agree on irrelevant_features"
+        if self._irr:
+            self.transition_matrix_irrelevant = tb.transition_irr
+            self.observation_spaces = [
+                self.observation_space,
+                DiscreteSpace(tb.n_states_irr,
+                              seed=self.seed_dict.get("irrelevant_state_space"))]
+            self.action_spaces = [
+                self.action_space,
+                DiscreteSpace(tb.n_actions_irr,
+                              seed=self.seed_dict.get("irrelevant_action_space"))]
         self.has_pnoise = any(bool(s_.transition_noise) for s_ in specs)
         self.has_rnoise = any(s_.has_reward_noise for s_ in specs)
         from .sharding import group_id_bases
@@ -187,6 +203,13 @@ class VectorRLToyEnv:
                   for a in keep]
             (g.transition, g.terminal, g.init_cdf, g.noise_cdf, g.sequences,
              g.sequence_rewards, g.reward_matrix) = hp
+            if t_.n_states_irr:
+                g.n_states_irr, g.n_actions_irr = t_.n_states_irr, t_.n_actions_irr
+                keep_irr = [t_.transition_irr, t_.init_cdf_irr, t_.noise_cdf_irr]
+                keep.extend(keep_irr)
+                (g.transition_irr, g.init_cdf_irr, g.noise_cdf_irr) = [
+                    None if a is None else a.ctypes.data_as(C.c_void_p)
+                    for a in keep_irr]
             g.env_begin, g.env_count = begin, sizes[gi]
             # global Philox ids: all ranks' envs of group g are contiguous
             g.global_id_base = id_bases[gi]
@@ -198,6 +221,8 @@ class VectorRLToyEnv:
         max_delay = max(s_.delay for s_ in specs)
 
         self._cur = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._cur_irr = torch.zeros(N, dtype=torch.int32, device=dev) \
+            if self._irr else None
         self._key = torch.zeros(N, dtype=torch.int64, device=dev)
         self._t = torch.zeros(N, dtype=torch.int32, device=dev)
         self._episode = torch.zeros(N, dtype=torch.int32, device=dev)
@@ -219,6 +244,7 @@ class VectorRLToyEnv:
         st.history_depth = self._hist_depth
         st.history = _ptr(self._history)
         st.stats = _ptr(self._stats)
+        st.cur_state_irr = _ptr(self._cur_irr)
         self._state = st
         if self.noise == "numpy":
             assert G == 1, "noise='numpy' is a single-configuration mode"
@@ -228,15 +254,19 @@ class VectorRLToyEnv:
         """Per-lane PCG64 streams; lane 0 = the reference's own (appendix C):
         S continues after the P-table draws, E is re-seeded at the first reset."""
         sd = self.seed_dict
-        self._rng_S = []
-        for i in range(self.num_envs):
-            s = sd.get("relevant_state_space")
-            rng, _ = np_random(None if s is None else s + i)
-            self._rng_S.append(rng)
+        from .tables import _next_set_probabilities, sub_space_rngs
+
+        def lanes(key, rng0):
+            s = sd.get(key)
+            return [rng0] + [np_random(None if s is None else s + i)[0]
+                             for i in range(1, self.num_envs)]
+        rng0, rng1 = sub_space_rngs(self.spec)
+        self._rng_S = lanes("relevant_state_space", rng0)
+        if self._irr:
+            self._rng_S1 = lanes("irrelevant_state_space", rng1)
         if not self.spec.use_custom_mdp:
             # replay lane 0's consumption during P generation
             S, A = self.tables.n_states, self.tables.n_actions
-            from .tables import _next_set_probabilities
             rng = self._rng_S[0]
             for s in range(S):
                 if self.spec.maximally_connected:
@@ -247,6 +277,16 @@ class VectorRLToyEnv:
                     p = _next_set_probabilities(s, S, A)
                     for _ in range(A):
                         rng.choice(S, size=1, p=p)
+            if self._irr:
+                S1, A1 = self.tables.n_states_irr, self.tables.n_actions_irr
+                rng = self._rng_S1[0]
+                for s in range(S1):
+                    p = _next_set_probabilities(s, S1, A1)
+                    if self.spec.maximally_connected:
+                        rng.choice(S1, size=A1, p=p, replace=False)
+                    else:
+                        for _ in range(A1):
+                            rng.choice(S1, size=1, p=p)
         self._rng_E = [None] * self.num_envs
 
     def _opts(self, T, noise_mode=None):
@@ -275,7 +315,9 @@ class VectorRLToyEnv:
     # ------------------------------------------------------------------
     def reset(self, seed=None, options=None):
         """(obs, info) like RLToyEnv.reset (:2217).  options: {"mask": bool[N],
-        "init_state": int[N], "reset_u": float64[N] (replay mode)}."""
+        "init_state": int[N], "reset_u": float64[N] (replay mode)}; with
+        irrelevant_features init_state / reset_u / obs are [N, 2] rows
+        (relevant, irrelevant)."""
         options = options or {}
         if self.spec.kind == "continuous":
             return self._reset_continuous(seed, options)
@@ -295,10 +337,11 @@ class VectorRLToyEnv:
                 for i in range(N):
                     self._rng_E[i], _ = np_random(None)
             m = None if mask is None else mask.cpu().numpy()
-            reset_u = np.zeros(N)
+            reset_u = np.zeros((N, 2) if self._irr else N)
             for i in range(N):
-                if m is None or m[i]:
-                    reset_u[i] = self._rng_E[i].random()
+                if m is None or m[i]:  # one E draw per sub-space (:2255-2264)
+                    reset_u[i] = [self._rng_E[i].random() for _ in range(2)] \
+                        if self._irr else self._rng_E[i].random()
         elif (seed is not None and self.noise == "philox"
               and not options.get("_ctor")):
             # re-keying the counter-based streams is the analogue of re-seeding
@@ -306,7 +349,12 @@ class VectorRLToyEnv:
         if reset_u is not None:
             reset_u = torch.as_tensor(reset_u, dtype=torch.float64,
                                       device=dev).contiguous()
-        obs = torch.empty(N, dtype=torch.int64, device=dev)
+        row = (N, 2) if self._irr else (N,)
+        if init is not None:
+            assert tuple(init.shape) == row, (tuple(init.shape), row)
+        if reset_u is not None:
+            assert tuple(reset_u.shape) == row, (tuple(reset_u.shape), row)
+        obs = torch.empty(row, dtype=torch.int64, device=dev)
         mode = _lib.MDPP_NOISE_REPLAY if reset_u is not None \
             else _lib.MDPP_NOISE_PHILOX
         if (init is None and reset_u is None and self.noise == "replay"
@@ -346,7 +394,8 @@ class VectorRLToyEnv:
             return _ptr(t)
         if sp.kind == "discrete":
             tb = it.build_discrete_image_tables(
-                self.tables.n_states, W, H, sp.image_transforms,
+                max(self.tables.n_states, self.tables.n_states_irr), W, H,
+                sp.image_transforms,
                 sp.image_sh_quant, sp.image_ro_quant, sp.image_scale_range)
             self.image_tables = tb
             c = _lib.ImageDiscreteTables()
@@ -362,8 +411,12 @@ class VectorRLToyEnv:
             c.rot_coeff = up(tb.rot_coeff, torch.int32)
             c.r_thresholds = up(tb.r_thresholds if len(tb.r_thresholds)
                                 else np.zeros(1), torch.float64)
+            # irrelevant_features: one polygon image per sub-state, stacked
+            # along x (image_multi_discrete.py:272-288)
+            self._n_sub = 2 if self._irr else 1
+            c.n_sub_images = self._n_sub
             self._img_cfg = c
-            self.obs_shape = (W, H, 1)
+            self.obs_shape = (W * self._n_sub, H, 1)
             if self.noise == "numpy":
                 s = self.seed_dict.get("image_representations")
                 self._rng_I = [np_random(None if s is None else s + i)[0]
@@ -413,9 +466,10 @@ class VectorRLToyEnv:
         :251, :258-259), one image per lane, lane 0 = the reference."""
         tb, sp = self.image_tables, self.spec
         W, H = tb.width, tb.height
-        out = np.zeros((self.num_envs, 5), dtype=np.int32)
-        for i in range(self.num_envs):
-            rng = self._rng_I[i]
+        n_sub = self._n_sub
+        out = np.zeros((self.num_envs * n_sub, 5), dtype=np.int32)
+        for i in range(self.num_envs * n_sub):
+            rng = self._rng_I[i // n_sub]  # sub-images drawn in order
             R, sw, sh, rot, flip = 20, int(W / 2), int(H / 2), -1, 0
             if tb.has_scale:
                 lo, hi = sp.image_scale_range
@@ -449,10 +503,11 @@ class VectorRLToyEnv:
             opts.step_index = step_index
         if sp.kind == "discrete":
             st = state.to(torch.int64).contiguous()
-            M = st.numel()
-            lead = tuple(st.shape)
+            M = st.numel()  # images = sub-images when irrelevant_features
+            lead = tuple(st.shape[:-1]) if self._irr else tuple(st.shape)
             if self.noise == "numpy" and image_params is None:
-                assert M == N, "noise='numpy' renders one step at a time"
+                assert M == N * self._n_sub, \
+                    "noise='numpy' renders one step at a time"
                 image_params = self._numpy_image_params(None)
             if image_params is not None:
                 image_params = torch.as_tensor(image_params, device=dev).to(
@@ -492,6 +547,8 @@ class VectorRLToyEnv:
         actions = torch.as_tensor(actions)
         if self.spec.kind == "continuous":
             actions = actions.reshape(1, N, self.spec.state_space_dim)
+        elif self._irr:
+            actions = actions.reshape(1, N, 2)
         else:
             actions = actions.reshape(1, N)
         out = self.rollout(1, actions=actions,
@@ -517,22 +574,23 @@ class VectorRLToyEnv:
             return self._rollout_continuous(n_steps, actions, replay, out,
                                             want_final_obs)
         T, N, dev = int(n_steps), self.num_envs, self.device
+        row = (T, N, 2) if self._irr else (T, N)  # (relevant, irrelevant) rows
         if actions is not None:
             actions = torch.as_tensor(actions, device=dev)
             if actions.dtype != torch.int32:
                 actions = actions.to(torch.int32)
             actions = actions.contiguous()
-            assert actions.shape == (T, N), (actions.shape, (T, N))
+            assert actions.shape == row, (actions.shape, row)
         io = _lib.DiscreteIO()
         if out is None:
             out = {
-                "obs": torch.empty((T, N), dtype=torch.int64, device=dev),
+                "obs": torch.empty(row, dtype=torch.int64, device=dev),
                 "reward": torch.empty((T, N), dtype=torch.float64, device=dev),
                 "terminated": torch.empty((T, N), dtype=torch.bool, device=dev),
                 "truncated": torch.empty((T, N), dtype=torch.bool, device=dev),
             }
             if want_final_obs:
-                out["final_obs"] = torch.empty((T, N), dtype=torch.int64,
+                out["final_obs"] = torch.empty(row, dtype=torch.int64,
                                                device=dev)
         io.actions = _ptr(actions)
         io.obs, io.reward = _ptr(out.get("obs")), _ptr(out.get("reward"))
@@ -549,7 +607,14 @@ class VectorRLToyEnv:
                                 ("reset_u", "replay_reset_u")):
                 if name in replay and replay[name] is not None:
                     t = torch.as_tensor(replay[name], dtype=torch.float64,
-                                        device=dev).reshape(T, N).contiguous()
+                                        device=dev).reshape(T, N)
+                    if self._irr and name != "reward_noise":
+                        # the irrelevant sub-space's draw rides in the same row
+                        t1 = replay.get("irr_" + name)
+                        t1 = torch.zeros_like(t) if t1 is None else torch.as_tensor(
+                            t1, dtype=torch.float64, device=dev).reshape(T, N)
+                        t = torch.stack([t, t1], dim=-1)
+                    t = t.contiguous()
                     keep.append(t)
                     setattr(io, field, _ptr(t))
         opts = self._opts(T)
@@ -563,7 +628,7 @@ class VectorRLToyEnv:
     # CUDA-graph step: the gym-style path without per-step launch overhead
     # ------------------------------------------------------------------
     def _state_tensors(self):
-        names = ("_cur", "_key", "_t", "_episode", "_ring", "_history",
+        names = ("_cur", "_cur_irr", "_key", "_t", "_episode", "_ring", "_history",
                  "_stats", "_derivs", "_emitted", "_reached")
         return [getattr(self, n) for n in names
                 if getattr(self, n, None) is not None]
@@ -578,14 +643,14 @@ class VectorRLToyEnv:
         N, dev = self.num_envs, self.device
         cont = self.spec.kind == "continuous"
         D = self.spec.state_space_dim
-        a_shape = (1, N, D) if cont else (1, N)
+        a_shape = (1, N, D) if cont else ((1, N, 2) if self._irr else (1, N))
         static_a = torch.zeros(a_shape, dtype=self._real if cont else torch.int32,
                                device=dev)
         if cont:
             out = {"obs": torch.empty((1, N, D), dtype=self._real, device=dev),
                    "reward": torch.empty((1, N), dtype=self._real, device=dev)}
         else:
-            out = {"obs": torch.empty((1, N), dtype=torch.int64, device=dev),
+            out = {"obs": torch.empty(a_shape, dtype=torch.int64, device=dev),
                    "reward": torch.empty((1, N), dtype=torch.float64, device=dev)}
         out["terminated"] = torch.empty((1, N), dtype=torch.bool, device=dev)
         out["truncated"] = torch.empty((1, N), dtype=torch.bool, device=dev)
@@ -702,6 +767,9 @@ class VectorRLToyEnv:
             rep["reward_noise"] = np.array(
                 [[self._rng_E[i].normal(0, std) for i in range(N)]
                  for _ in range(T)])
+        if self.has_pnoise and self._irr:  # S' stream (:2075)
+            rep["irr_transition_u"] = np.array(
+                [[self._rng_S1[i].random() for i in range(N)] for _ in range(T)])
         return rep
 
     # ------------------------------------------------------------------
@@ -929,7 +997,10 @@ class VectorRLToyEnv:
         age = torch.arange(H - 1, -1, -1, device=self.device)[None, :]
         hist = torch.where(age <= self._t[:, None].to(torch.int64), hist,
                            torch.full_like(hist, float("nan")))
-        return {"curr_state": self._cur.to(torch.int64),
+        cur = self._cur.to(torch.int64)
+        if self._irr:  # (relevant, irrelevant); the window holds relevant states
+            cur = torch.stack([cur, self._cur_irr.to(torch.int64)], dim=-1)
+        return {"curr_state": cur,
                 "curr_obs": self.curr_obs, "augmented_state": hist}
 
     def set_augmented_state(self, state):
@@ -957,6 +1028,12 @@ class VectorRLToyEnv:
             raise RuntimeError("construct with track_history=True to use "
                                "set_augmented_state()")
         H, L = self._hist_depth, self.spec.sequence_length
+        if self._irr:
+            full = torch.as_tensor(state["curr_state"] if isinstance(state, dict)
+                                   else state, device=dev).reshape(N, 2)
+            self._cur_irr.copy_(full[:, 1].to(torch.int32))
+            if not isinstance(state, dict):
+                state = full[:, 0]
         if isinstance(state, dict):
             aug = torch.as_tensor(state["augmented_state"], device=dev).to(
                 torch.float64).reshape(N, H)
@@ -980,8 +1057,10 @@ class VectorRLToyEnv:
         self._t.copy_(torch.where(keep, self._t, t_new))
         idx = (self._step_index - torch.arange(H - 1, -1, -1, device=dev)) % H
         self._history[idx] = states.t().to(torch.int32)
-        self.curr_obs = self._observe(self._cur.to(torch.int64), reset=True,
-                                      ctor=True)
+        cur = self._cur.to(torch.int64)
+        if self._irr:
+            cur = torch.stack([cur, self._cur_irr.to(torch.int64)], dim=-1)
+        self.curr_obs = self._observe(cur, reset=True, ctor=True)
 
     def seed(self, seed=None):
         """RLToyEnv.seed (:2379): re-keys the environment's noise stream."""

@@ -10,6 +10,7 @@ import numpy as np
 STREAM_STEP, STREAM_RESET, STREAM_ACTION, STREAM_IMAGE = 0, 1, 2, 3
 STREAM_NORMAL, STREAM_AUTORESET = 4, 5
 STREAM_STATE_NOISE, STREAM_RESET_BOX = 8, 64
+STREAM_IRR_STEP, STREAM_IRR_AUTORESET = 32, 33
 
 _M0, _M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 _W0, _W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
@@ -119,6 +120,11 @@ def step_noise(seed, env_ids, step, want_normal=True, fast=False, raw=False):
 def autoreset_uniform(seed, env_ids, step):
     """32-bit uniform of the same-step auto-reset after global step `step`."""
     return uniform32(_quad_words(seed, env_ids, step, STREAM_AUTORESET)[int(step) & 3])
+
+
+def quad_word(seed, env_ids, step, stream):
+    """Word (step & 3) of the 4-step group `step >> 2` of a per-step stream."""
+    return _quad_words(seed, env_ids, step, stream)[int(step) & 3]
 
 
 def step_words(seed, env_ids, step, stream=STREAM_STEP):

@@ -41,6 +41,16 @@ class VectorDiscreteOracle:
         self.r_std = e.reward_noise_std
         self.scale, self.shift = e.reward_scale, e.reward_shift
         self.term_reward = e.term_state_reward
+        # irrelevant_features (rl_toy_env.py:2062-2082, :2260-2264): a second,
+        # reward-free chain; obs / actions become rows (relevant, irrelevant)
+        self.irr = bool(getattr(e, "irrelevant_features", False))
+        if self.irr:
+            self.S1, self.A1 = int(e.state_space_size_irr), int(e.action_space_size_irr)
+            self.P1 = np.array(e.transition_matrix_irr, dtype=np.int64)
+            self.init_cdf1 = e.init_cdf_irr
+            self.noise_cdf1 = e.noise_cdf_irr if self.has_pnoise else None
+            self.pn_params1 = px.transition_noise_params(
+                float(e.transition_noise) if self.has_pnoise else 0.0, self.S1)
         self.autoreset, self.horizon = autoreset, int(horizon)
         self.seed = int(seed)
         self.fast_normal = fast_normal
@@ -48,6 +58,7 @@ class VectorDiscreteOracle:
             np.uint32)
         self.step_index = 0
         self.cur = np.zeros(self.N, dtype=np.int64)
+        self.cur1 = np.zeros(self.N, dtype=np.int64)
         self.t = np.zeros(self.N, dtype=np.int64)
         self.episode = np.zeros(self.N, dtype=np.int64)
         self.window = [[] for _ in range(self.N)]   # last L states
@@ -60,20 +71,34 @@ class VectorDiscreteOracle:
     def _reset_u(self, idx):
         w = px.philox4x32_10(self.gid[idx], self.episode[idx].astype(np.uint32),
                              0, px.STREAM_RESET, self.seed)
-        return px.uniform53(w[0], w[1])
+        return px.uniform53(w[0], w[1]), px.uniform53(w[2], w[3])
+
+    def _obs(self):
+        return np.stack([self.cur, self.cur1], axis=-1) if self.irr \
+            else self.cur.copy()
 
     def reset(self, mask=None, init_state=None, reset_u=None):
+        """With irrelevant_features init_state / reset_u are [N, 2] rows."""
         idx = np.arange(self.N) if mask is None else np.nonzero(mask)[0]
         if init_state is not None:
-            s0 = np.asarray(init_state, dtype=np.int64)[idx]
+            init = np.asarray(init_state, dtype=np.int64)[idx]
+            s0, s1 = (init[:, 0], init[:, 1]) if self.irr else (init, None)
         else:
-            u = self._reset_u(idx) if reset_u is None else np.asarray(reset_u)[idx]
+            if reset_u is None:
+                u, u1 = self._reset_u(idx)
+            else:
+                ru = np.asarray(reset_u)[idx]
+                u, u1 = (ru[:, 0], ru[:, 1]) if self.irr else (ru, None)
             s0 = np.minimum(np.searchsorted(self.init_cdf, u, side="right"),
                             self.S - 1)
+            s1 = np.minimum(np.searchsorted(self.init_cdf1, u1, side="right"),
+                            self.S1 - 1) if self.irr else None
         self.stats["episodes"] += int((self.t[idx] > 0).sum())
-        for i, s in zip(idx, s0):
+        for j, (i, s) in enumerate(zip(idx, s0)):
             self._reset_one(i, int(s))
-        return self.cur.copy()
+            if self.irr:
+                self.cur1[i] = int(s1[j])
+        return self._obs()
 
     def _reset_one(self, i, s0):
         self.cur[i] = s0
@@ -84,19 +109,37 @@ class VectorDiscreteOracle:
 
     def rollout(self, T, actions=None, replay=None):
         N = self.N
-        obs = np.zeros((T, N), dtype=np.int64)
-        final_obs = np.zeros((T, N), dtype=np.int64)
+        row = (T, N, 2) if self.irr else (T, N)
+        obs = np.zeros(row, dtype=np.int64)
+        final_obs = np.zeros(row, dtype=np.int64)
         reward = np.zeros((T, N), dtype=np.float64)
         term = np.zeros((T, N), dtype=bool)
         trunc = np.zeros((T, N), dtype=bool)
         for t in range(T):
             step = self.step_index + t
+            a1 = None
             if actions is not None:
                 a = np.asarray(actions[t], dtype=np.int64)
+                if self.irr:
+                    a, a1 = a[:, 0], a[:, 1]
             else:
                 w = px.step_words(self.seed, self.gid, step, px.STREAM_ACTION)
                 a = px.mulhi32(w[0], self.A)
+                if self.irr:
+                    a1 = px.mulhi32(w[1], self.A1)
             a = np.minimum(a, self.A - 1)
+            if self.irr:  # the irrelevant chain: table walk + noisy redraw
+                nxt1 = self.P1[self.cur1, np.minimum(a1, self.A1 - 1)]
+                if self.has_pnoise and replay is None:
+                    w1 = px.quad_word(self.seed, self.gid, step, px.STREAM_IRR_STEP)
+                    nxt1 = px.noisy_next_state(w1, nxt1, self.pn_params1)
+                elif self.has_pnoise:
+                    u1 = np.asarray(replay["irr_transition_u"][t])
+                    nxt1 = np.array([
+                        min(int(np.searchsorted(self.noise_cdf1[nxt1[i]], u1[i],
+                                                side="right")), self.S1 - 1)
+                        for i in range(N)], dtype=np.int64)
+                self.cur1 = nxt1.astype(np.int64)
             u_tr = n_rw = None
             if replay is not None:
                 if self.has_pnoise:
@@ -151,7 +194,7 @@ class VectorDiscreteOracle:
                     r = r + self.term_reward * self.scale
                 tr = self.horizon > 0 and ti >= self.horizon
                 reward[t, i], term[t, i], trunc[t, i] = r, done, tr
-                final_obs[t, i] = nxt[i]
+                final_obs[t, i] = (nxt[i], self.cur1[i]) if self.irr else nxt[i]
                 self.cur[i] = nxt[i]
                 self.stats["returned_reward"] += r
                 self.stats["terminated"] += int(done)
@@ -166,7 +209,16 @@ class VectorDiscreteOracle:
                                                  side="right")), self.S - 1)
                     self._reset_one(i, s0)
                     self.stats["episodes"] += 1
-                obs[t, i] = self.cur[i]
+                    if self.irr:
+                        if replay is not None:
+                            u1 = float(replay["irr_reset_u"][t][i])
+                        else:
+                            u1 = float(px.uniform32(px.quad_word(
+                                self.seed, self.gid[i:i + 1], step,
+                                px.STREAM_IRR_AUTORESET))[0])
+                        self.cur1[i] = min(int(np.searchsorted(
+                            self.init_cdf1, u1, side="right")), self.S1 - 1)
+                obs[t, i] = (self.cur[i], self.cur1[i]) if self.irr else self.cur[i]
         self.step_index += T
         return dict(obs=obs, final_obs=final_obs, reward=reward,
                     terminated=term, truncated=trunc)

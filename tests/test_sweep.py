@@ -73,10 +73,11 @@ def test_every_rltoy_experiment_of_the_reference_is_accepted():
     """Drop-in coverage: the env grid of every `RLToy-v0` experiment file in
     the reference's experiments/ directory goes through our config parser and
     (for discrete envs) table builder.  The only rejections are the files the
-    reference itself cannot run at HEAD or that need a 'next' row:
-    *_move_to_a_point_irr_dims (target_point / relevant_indices mismatch --
-    the reference's own assert, rl_toy_env.py:649-651) and dqn_irr_dims
-    (discrete irrelevant_features)."""
+    reference itself cannot run at HEAD: *_move_to_a_point_irr_dims
+    (target_point / relevant_indices mismatch -- the reference's own assert,
+    rl_toy_env.py:649-651) and dqn_irr_dims (list-valued action_space_size
+    without irrelevant_features=True -- the reference's assert :579-581; with
+    the flag added the file's grid is accepted, checked below)."""
     import contextlib
     import copy
     import glob
@@ -117,3 +118,12 @@ def test_every_rltoy_experiment_of_the_reference_is_accepted():
                              "sac_move_to_a_point_irr_dims.py",
                              "td3_move_to_a_point_irr_dims.py",
                              "dqn_irr_dims.py"}, rejected
+    assert "Did you mean to turn irrelevant_features" in rejected["dqn_irr_dims.py"]
+    mod = sweep.load_experiment(os.path.join(REFERENCE_ROOT, "experiments",
+                                             "dqn_irr_dims.py"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sp = parse_config(dict(copy.deepcopy(sweep.env_grid(mod)[1][0]),
+                               irrelevant_features=True))
+        tb = build_discrete_tables(sp)
+    assert tb.transition_irr.shape == (8, 8)
