@@ -321,7 +321,7 @@ def other_configs(torch, Env, dev, rank, world, barrier, max_over_ranks, peak):
         ms = _time_launches(torch, lambda: env.rollout(T, actions=acts, out=out),
                             5, barrier, max_over_ranks)
         line("C5_heterogeneous_1000_groups_rollout", N, T, ms, 22,
-             "fused rollout, ahead-of-time multi-group kernel")
+             "fused rollout, one multi-group launch (scalars shared by all groups specialised)")
         s5 = env.episode_stats(reduce=True)
         res["C5_heterogeneous_1000_groups_rollout"]["stats_allreduce"] = {
             "groups": len(cfgs),

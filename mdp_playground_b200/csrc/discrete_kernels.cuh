@@ -823,6 +823,11 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
       for (; t0 + kChunk <= p.T; t0 += kChunk)
         run_chunk<C, kChunk>(p, v, e, ring_smem, env, gid, step_base, t0);
     }
+    // remainder: a half chunk first (t0 is still quad-aligned here; single
+    // steps pay a whole Philox quad each), then single steps
+    if (kChunk > 4)
+      for (; t0 + 4 <= p.T; t0 += 4)
+        run_chunk<C, 4>(p, v, e, ring_smem, env, gid, step_base, t0);
     for (; t0 < p.T; ++t0)
       run_chunk<C, 1>(p, v, e, ring_smem, env, gid, step_base, t0);
     p.st.cur_state[env] = e.s;

@@ -25,6 +25,11 @@ def test_group_id_bases_tile_the_global_id_space():
     b1 = sharding.group_id_bases(sizes, 1, world)
     assert [y - x for x, y in zip(b0, b1)] == sizes
     assert sharding.even_group_sizes(10, 4) == [3, 3, 2, 2]
+    # whole CTAs per group when the batch allows it
+    assert sharding.even_group_sizes(64 * 10, 4) == [192, 192, 128, 128]
+    assert sum(sharding.even_group_sizes(1 << 20, 1000)) == 1 << 20
+    assert all(n % 64 == 0 for n in sharding.even_group_sizes(1 << 20, 1000))
+    assert sharding.even_group_sizes(64 * 3, 4) == [48] * 4
     assert [s.start for s in sharding.local_slices(sizes)] == [0, 5, 8]
 
 
