@@ -73,6 +73,11 @@ def install(env):
         sp.np_random
         if not isinstance(sp._np_random, RecordingGenerator):
             sp._np_random = RecordingGenerator(sp._np_random, log, "image")
+    if env.config.get("state_space_type") == "grid":  # GridActionSpace.sample
+        sp = env.action_space
+        sp.np_random
+        if not isinstance(sp._np_random, RecordingGenerator):
+            sp._np_random = RecordingGenerator(sp._np_random, log, "action")
     fs = getattr(env, "feature_space", None)
     if fs is not None:
         fs.np_random

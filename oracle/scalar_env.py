@@ -70,6 +70,13 @@ class NumpyDraws:
     def reset_box(self, env):
         return env._box_sample(self.env.rng_F)
 
+    def grid_noise_uniform(self):  # rl_toy_env.py:1736 (E stream)
+        return self.env.rng_E.uniform()
+
+    def grid_action_sample(self, ndim):  # GridActionSpace.sample (A stream)
+        ind = self.env.rng_A.integers(ndim).item()
+        return ind, self.env.rng_A.integers(3).item() - 1
+
     def image_scale_u(self):
         return self.env.rng_I.random()
 
@@ -107,6 +114,12 @@ class ReplayDraws:
 
     def reset_box(self, env):
         return np.asarray(self._pop("reset_state"))
+
+    def grid_noise_uniform(self):
+        return self._pop("grid_noise_u")
+
+    def grid_action_sample(self, ndim):
+        return tuple(self._pop("grid_noise_action"))
 
     def image_scale_u(self):
         return self._pop("image_scale_u")
@@ -191,8 +204,18 @@ class ScalarRLToyEnv:
             self.inertia = g("inertia", 1.0)
             self.time_unit = g("time_unit", 1.0)
             self.target_radius = g("target_radius", 0.05)
+        elif kind == "grid":  # :539-541, :655-657
+            assert "grid_shape" in cfg
+            self.grid_shape = tuple(cfg["grid_shape"])
+            assert cfg["reward_function"] == "move_to_a_point"
+            self.target_point = cfg["target_point"]
+            # the reference leaves make_denser unset for grid envs (:384-390)
+            # and crashes in the reward without it; delay / sequence_length
+            # other than 0 / 1 crash in np.array(augmented_state) (:1950)
+            assert "make_denser" in cfg and self.delay == 0 \
+                and self.sequence_length == 1
         else:
-            raise ValueError("oracle covers discrete and continuous only")
+            raise ValueError("Unknown state_space_type")
         self.action_loss_weight = g("action_loss_weight", 0.0)
         if "reward_every_n_steps" in cfg:
             self.reward_every_n_steps = cfg["reward_every_n_steps"]
@@ -217,6 +240,10 @@ class ScalarRLToyEnv:
                 self.state_space_size = cfg["state_space_size"]
             else:
                 self.state_space_size = self.action_space_size * self.diameter
+        elif kind == "grid":  # :604-608
+            self.dtype_s = g("dtype_s", np.int64)
+            if g("irrelevant_features", False):
+                self.grid_shape = self.grid_shape * 2
         else:  # :593-602
             self.dtype_s = g("dtype_s", np.float32)
             if "relevant_indices" not in cfg:
@@ -256,6 +283,9 @@ class ScalarRLToyEnv:
                     self.rng_S1, _ = np_random(int(sub[1]))
             if self.image_representations:
                 self.rng_I, _ = np_random(self.seed_dict["image_representations"])
+        elif kind == "grid":  # :780-812: Box(0, grid_shape) int64, GridActionSpace
+            self.rng_F, _ = np_random(self.seed_dict["state_space"])
+            self.rng_A, _ = np_random(self.seed_dict["action_space"])
         else:
             self.state_space_max = g("state_space_max", np.inf)
             self.action_space_max = g("action_space_max", np.inf)
@@ -309,6 +339,14 @@ class ScalarRLToyEnv:
                      for i in range(self.num_terminal_states)])
                 cfg["terminal_states"] = self.terminal_states
             self.is_terminal_state = lambda s: s in self.terminal_states
+        elif self.kind == "grid":
+            # :958-987: the terminal cells become int64 Boxes, but the state is
+            # tested as a FLOAT array, which Box.contains rejects (can_cast
+            # float64 -> int64 is False): no grid state is ever terminal.  The
+            # cells still show up in the image observations.
+            assert not callable(cfg.get("terminal_states"))
+            self.term_cells = [list(c) for c in cfg.get("terminal_states", [])]
+            self.is_terminal_state = lambda s: False
         else:
             self.term_lows, self.term_highs = [], []
             if "terminal_states" in cfg:
@@ -337,6 +375,10 @@ class ScalarRLToyEnv:
 
     def _box_sample(self, rng):
         """gymnasium Box.sample for the (homogeneous-bound) feature space."""
+        if self.kind == "grid":
+            hi = np.array(self.grid_shape, dtype=np.int64) + 1
+            return np.floor(rng.uniform(low=np.zeros(len(hi)), high=hi,
+                                        size=(len(hi),))).astype(np.int64)
         D = self.state_space_dim
         if np.isinf(self.state_space_max):
             sample = rng.normal(size=(D,))
@@ -533,6 +575,14 @@ class ScalarRLToyEnv:
                 u1 = self.draws.irr_reset_uniform()
                 self.curr_state = (s0, choice_from_uniform(self.init_cdf_irr, u1))
             self.augmented_state = [np.nan] * L1 + [s0]
+        elif self.kind == "grid":
+            # :2325-2345: Box(0, grid_shape).sample() of an int Box draws
+            # floor(uniform(0, shape + 1)) -- the cell index `shape` itself
+            # (one past the grid) can come out; no terminal rejection happens
+            s0 = self.draws.reset_box(self)
+            self.curr_state = np.asarray(s0).astype(self.dtype_s)
+            self.augmented_state = [np.nan] * L1 + [
+                list(self.curr_state[[0, 1]])]
         else:
             while True:
                 s0 = self.draws.reset_box(self)
@@ -612,6 +662,46 @@ class ScalarRLToyEnv:
             self.reached_terminal = True
         return nxt
 
+    @staticmethod
+    def _grid_action_valid(action):
+        """GridActionSpace.contains (grid_action_space.py:25-39) and the dtype
+        test of rl_toy_env.py:1730-1733."""
+        x = np.array(action)
+        if x.dtype.kind != "i" or x.dtype != np.int64:
+            return False
+        if not np.all((x == 0) | (x == 1) | (x == -1)):
+            return False
+        return int(np.sum(np.abs(x))) in (0, 1)
+
+    def _transition_grid(self, state, action):
+        """rl_toy_env.py:1727-1778."""
+        nd = len(self.grid_shape)
+        if self._grid_action_valid(action) and np.array(action).shape == (nd,):
+            action = list(action)
+            if self.transition_noise:
+                if self.draws.grid_noise_uniform() < self.transition_noise:
+                    while True:  # substitute a different action
+                        ind, val = self.draws.grid_action_sample(nd)
+                        new_action = [0] * nd
+                        new_action[ind] = val
+                        if new_action != [int(a) for a in action]:
+                            self.total_noisy_transitions_episode += 1
+                            action = new_action
+                            break
+            nxt = []
+            for i in range(nd):
+                v = int(state[i]) + int(action[i])
+                v = max(v, 0)
+                if v >= self.grid_shape[i]:
+                    v = self.grid_shape[i] - 1
+                nxt.append(v)
+        else:
+            nxt = [int(v) for v in state]  # noop (and a warning)
+        rel = nxt[:nd // 2] if self.config.get("irrelevant_features") else nxt
+        if list(self.target_point) == rel:
+            self.reached_terminal = True
+        return np.array(nxt)
+
     # ---- reward -----------------------------------------------------------
     def _reward(self, action):
         """rl_toy_env.py:1782-1990."""
@@ -623,6 +713,14 @@ class ScalarRLToyEnv:
             if not np.isnan(aug[d]):
                 key = tuple(aug[1 + d:self.augmented_state_length])
                 reward = self.rewardable_sequences.get(key, 0.0)
+        elif self.kind == "grid":  # :1947-1965, Manhattan distances
+            tgt = np.array(self.target_point)
+            new = np.array(aug)[-1]
+            if self.make_denser:
+                old = np.array(aug)[-2]
+                reward += np.abs(old - tgt).sum() - np.abs(new - tgt).sum()
+            elif list(new) == list(self.target_point):
+                reward += 1.0
         else:
             if not np.isnan(aug[d][0]):
                 window = np.array(aug, dtype=self.dtype_s)
@@ -661,11 +759,16 @@ class ScalarRLToyEnv:
             nxt = self._transition_discrete(state, action)
         elif self.kind == "discrete":
             nxt = self._transition_discrete(self.curr_state, action)
+        elif self.kind == "grid":
+            nxt = self._transition_grid(self.curr_state, action)
         else:
             nxt = self._transition_continuous(self.curr_state, action)
         del self.augmented_state[0]
-        self.augmented_state.append(nxt if self.kind == "discrete"
-                                    else nxt.copy())
+        if self.kind == "grid":  # :2055-2056, the relevant cell only
+            self.augmented_state.append([nxt[i] for i in range(2)])
+        else:
+            self.augmented_state.append(nxt if self.kind == "discrete"
+                                        else nxt.copy())
         self.total_transitions_episode += 1
         self.reward = self._reward(action)
         if irr:  # :2062-2082, after the reward (draw order S, E, S')
@@ -691,6 +794,8 @@ class ScalarRLToyEnv:
                 return np.atleast_3d(np.concatenate(
                     [self._image_discrete(int(s)) for s in state], axis=0))
             return np.atleast_3d(self._image_discrete(int(state)))
+        if self.kind == "grid":
+            return self._image_grid(np.asarray(state))
         return self._image_continuous(state)
 
     def image_params(self, state):
@@ -780,6 +885,47 @@ class ScalarRLToyEnv:
         pp = self._to_pixel(pos)
         draw.ellipse([tuple(pp - 5), tuple(pp + 5)], fill=(0, 0, 255))
         return np.transpose(np.array(img), axes=(1, 0, 2))
+
+    def _grid_pixel(self, vec):
+        """convert_to_pixel (image_continuous.py:248-277) over the int64 Box
+        [0, grid_shape] of the first two dimensions (also for the irrelevant
+        sub-image: "both sub-spaces have the same max and min")."""
+        hi = np.array(self.grid_shape[:2], dtype=np.int64)
+        frac = (np.asarray(vec) - 0) / (hi - 0)
+        return (frac * (self.image_width, self.image_height)).astype(int)
+
+    def _image_grid_one(self, pos, relevant):
+        """image_continuous.py:116-208 with draw_grid (grid lines, terminal
+        cells, target and agent discs at the cell centres)."""
+        import PIL.Image as Image
+        import PIL.ImageDraw as ImageDraw
+        W, H = self.image_width, self.image_height
+        img = Image.new("RGB", (W, H), color=(208, 208, 208))
+        draw = ImageDraw.Draw(img)
+        off = 0 if relevant else 2
+        gs = self.grid_shape
+        for i in range(1, gs[0 + off] + 1):
+            x = i * W // gs[0 + off] - 1
+            draw.line([(x, H), (x, 0)], fill=(255, 255, 255))
+        for j in range(1, gs[1 + off]):
+            y = j * H // gs[0 + off]  # (sic: the first extent, :152)
+            draw.line([(W, y), (0, y)], fill=(255, 255, 255))
+        if relevant:
+            for cell in self.term_cells:
+                c = np.array(cell, dtype=np.float64).astype(np.int64)
+                draw.rectangle([tuple(self._grid_pixel(c)),
+                                tuple(self._grid_pixel(c + 1.0))], fill=(0, 0, 0))
+            tp = self._grid_pixel(np.array(self.target_point, dtype=float) + 0.5)
+            draw.ellipse([tuple(tp - 5), tuple(tp + 5)], fill=(0, 255, 0))
+        pp = self._grid_pixel(np.asarray(pos).astype(float) + 0.5)
+        draw.ellipse([tuple(pp - 5), tuple(pp + 5)], fill=(0, 0, 255))
+        return np.transpose(np.array(img), axes=(1, 0, 2))
+
+    def _image_grid(self, obs):
+        parts = [self._image_grid_one(obs[[0, 1]], True)]
+        if len(self.grid_shape) == 4:
+            parts.append(self._image_grid_one(obs[[2, 3]], False))
+        return np.atleast_3d(np.concatenate(parts, axis=0))
 
     def _image_continuous(self, obs):
         """image_continuous.py:210-246."""

@@ -33,6 +33,10 @@ _P85[6, :] = 6
 _P85[7, :] = 7
 _R85 = np.round(_rngP.normal(size=(8, 5)), 3)
 
+_G = dict(seed=0, state_space_type="grid", grid_shape=(8, 8), delay=0,
+          sequence_length=1, reward_function="move_to_a_point",
+          target_point=[5, 5], make_denser=True)
+
 CASES = {
     "c1_seq1": dict(config=dict(_D, sequence_length=1, delay=0)),
     "c2_seq3_del2_noise": dict(config=dict(
@@ -87,6 +91,26 @@ CASES = {
         image_representations=True,
         image_transforms="shift,scale,rotate,flip", image_sh_quant=2,
         image_ro_quant=1, image_scale_range=(0.5, 1.5)),
+        lanes=2, steps=24, horizon=8),
+    # grid envs (tests/test_mdp_playground.py:792-1190 shapes)
+    "grid_dense_term": dict(config=dict(
+        _G, reward_scale=3.0, term_state_reward=-0.25,
+        terminal_states=[[5, 5], [2, 3], [2, 4], [3, 3], [3, 4]])),
+    "grid_sparse_noise": dict(config=dict(
+        _G, seed=4, make_denser=False, transition_noise=0.3, reward_noise=1.0,
+        reward_scale=2.0, reward_shift=0.5, term_state_reward=2.0)),
+    "grid_irr_5x9": dict(config=dict(
+        _G, seed=5, grid_shape=(5, 9), target_point=[1, 7],
+        irrelevant_features=True, transition_noise=0.2,
+        reward_every_n_steps=2)),
+    "grid_img": dict(config=dict(
+        _G, seed=1, image_representations=True, reward_scale=2.0,
+        terminal_states=[[5, 5], [2, 3], [2, 4]]),
+        lanes=2, steps=24, horizon=8),
+    "grid_img_irr": dict(config=dict(
+        _G, seed=2, grid_shape=(4, 6), target_point=[1, 2],
+        irrelevant_features=True, image_representations=True,
+        image_width=60, image_height=48, transition_noise=0.25),
         lanes=2, steps=24, horizon=8),
     "c4_img_shift": dict(config=dict(
         _D, seed=2, sequence_length=1, image_representations=True,

@@ -209,6 +209,97 @@ def run_case(name, spec):
     return out
 
 
+def run_grid_case(name, spec):
+    """Grid envs (rl_toy_env.py:1727-1778, :1947-1965, :2325-2345): actions are
+    unit moves, the draws are the E-stream uniform that decides whether the
+    action is replaced, the accepted replacement (GridActionSpace.sample, A
+    stream), the reward normal and the reset cell (F stream)."""
+    cfg = materialise(spec["config"])
+    K, T, H = spec.get("lanes", 6), spec.get("steps", 48), spec.get("horizon", 12)
+    env = make_reference_env(cfg)
+    nd = len(env.grid_shape)
+    image = bool(cfg.get("image_representations", False))
+    out = {"seed_dict": np.array(json.dumps(env.seed_dict)),
+           "reward_every_n_steps": np.array(int(env.reward_every_n_steps))}
+    rec = dict(
+        actions=np.zeros((K, T, nd), dtype=np.int64),
+        state=np.zeros((K, T, nd), dtype=np.int64),
+        reward=np.zeros((K, T), dtype=np.float64),
+        done=np.zeros((K, T), dtype=bool),
+        reset_after=np.zeros((K, T), dtype=bool),
+        reset_state=np.zeros((K, T, nd), dtype=np.int64),
+        init_state=np.zeros((K, nd), dtype=np.int64),
+        grid_noise_u=np.full((K, T), np.nan),
+        grid_noise_action=np.zeros((K, T, nd), dtype=np.int64),  # the action applied
+        grid_noise_attempts=np.zeros((K, T), dtype=np.int64),
+        reward_noise=np.full((K, T), np.nan))
+    if image:
+        shp = env.curr_obs[0].shape
+        rec["obs_image"] = np.zeros((K, T) + shp, dtype=np.uint8)
+        rec["init_image"] = np.zeros((K,) + shp, dtype=np.uint8)
+        rec["reset_image"] = np.zeros((K, T) + shp, dtype=np.uint8)
+    attempts_log = []
+    for k in range(K):
+        lane_seed = LANE_SEED + 17 * k
+        env.feature_space.seed(lane_seed + 2)
+        env.action_space.seed(lane_seed + 5)
+        log = draw_recorder.install(env)
+        obs0, _ = env.reset(seed=lane_seed)
+        rec["init_state"][k] = env.curr_state
+        if image:
+            rec["init_image"][k] = obs0
+        env._np_random = draw_recorder.RecordingGenerator(env._np_random, log, "env")
+        arng = np.random.default_rng(1000 + k)
+        for t in range(T):
+            del log[:]
+            a = [0] * nd
+            kind = arng.integers(12)
+            if kind < 5:
+                a[arng.integers(nd)] = int(arng.integers(-1, 2))
+            elif kind < 10:   # a greedy move, so that targets do get reached
+                d = int(arng.integers(2))
+                a[d] = int(np.sign(env.target_point[d] - env.curr_state[d]))
+            elif kind == 10:  # invalid: two moves at once -> noop
+                a = [int(x) for x in arng.integers(-1, 2, size=nd)]
+            else:             # invalid: out of range -> noop
+                a[0] = 2
+            rec["actions"][k, t] = a
+            obs, r, done, trunc, info = env.step(list(a))
+            rec["state"][k, t] = env.curr_state
+            rec["reward"][k, t] = float(r)
+            rec["done"][k, t] = done
+            applied = list(a)
+            acts = [e for e in log if e[0] == "action"]
+            for e in log:
+                if e[0] == "env" and e[1] == "uniform":
+                    rec["grid_noise_u"][k, t] = float(e[3])
+                elif e[0] == "env" and e[1] == "normal":
+                    rec["reward_noise"][k, t] = float(e[3])
+            if acts:  # (ind, val) pairs; the last pair is the accepted one
+                pairs = [(int(acts[i][3]), int(acts[i + 1][3]) - 1)
+                         for i in range(0, len(acts), 2)]
+                attempts_log.append((k, t, pairs))
+                rec["grid_noise_attempts"][k, t] = len(pairs)
+                applied = [0] * nd
+                applied[pairs[-1][0]] = pairs[-1][1]
+            rec["grid_noise_action"][k, t] = applied
+            if image:
+                rec["obs_image"][k, t] = obs
+            # odd lanes keep stepping after `done` (reached_terminal is sticky)
+            if (done and k % 2 == 0) or t % H == H - 1:
+                rec["reset_after"][k, t] = True
+                obs_r, _ = env.reset()
+                rec["reset_state"][k, t] = env.curr_state
+                if image:
+                    rec["reset_image"][k, t] = obs_r
+    # every attempt, flattened, for the scalar oracle's replay leg
+    flat = [(k, t, i, v) for k, t, ps in attempts_log for i, v in ps]
+    out["grid_attempts"] = np.array(flat, dtype=np.int64).reshape(-1, 4)
+    out.update(rec)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    return out
+
+
 if __name__ == "__main__":
     import warnings
     warnings.simplefilter("ignore")
@@ -216,7 +307,8 @@ if __name__ == "__main__":
     for name, spec in CASES.items():
         if only and name not in only:
             continue
-        o = run_case(name, spec)
+        grid = spec["config"]["state_space_type"] == "grid"
+        o = (run_grid_case if grid else run_case)(name, spec)
         print(f"{name}: lanes x steps = {o['done'].shape}, "
               f"done={int(o['done'].sum())}, resets={int(o['reset_after'].sum())}, "
               f"nonzero rewards={int((o['reward'] != 0).sum())}")

@@ -13,6 +13,8 @@ IRR_CASES = [k for k, v in CASES.items()
 DISCRETE_CASES = [k for k, v in CASES.items()
                   if v["config"]["state_space_type"] == "discrete"
                   and k not in IRR_CASES]
+GRID_CASES = [k for k, v in CASES.items()
+              if v["config"]["state_space_type"] == "grid"]
 CONTINUOUS_CASES = [k for k, v in CASES.items()
                     if v["config"]["state_space_type"] == "continuous"]
 
