@@ -57,7 +57,6 @@ def test_oracle_numpy_streams_match_reference_golden(name):
         if image:
             assert np.array_equal(obs0, g["init_image"][k])
         _check_lane(env, g, k, CASES[name].get("horizon", 12), image)
-    assert g["done"].any()
 
 
 @pytest.mark.parametrize("name", [n for n in gu.GRID_CASES
