@@ -288,6 +288,73 @@ int mdpp_continuous_reset(mdpp_ctx* ctx, const mdpp_continuous_state* st,
 #endif
 
 /* ------------------------------------------------------------------------
+ * Grid environments, reward_function "move_to_a_point" (replaces
+ * RLToyEnv.transition_function :1727-1778, reward_function :1947-1965 + tail
+ * :1968-1990, step epilogue :2098-2109, reset :2325-2345).  One configuration
+ * per context.  Cells are int64 rows of n_dims coordinates ([x, y] or, with
+ * irrelevant_features, [x, y, x_irr, y_irr]); an action is a row of n_dims
+ * values in {-1, 0, 1} with at most one non-zero entry (GridActionSpace,
+ * spaces/grid_action_space.py:25-39) -- anything else is a no-op, like the
+ * reference's warning branch (:1765-1770).
+ * Reference quirks kept: terminal cells never terminate (:958-987 test a float
+ * array against an int64 Box), only the sticky `reached_terminal` (:1775) ends
+ * an episode; reset() samples every coordinate from [0, shape] INCLUSIVE
+ * (gymnasium's int Box), one past the grid; delay / sequence_length other than
+ * 0 / 1 crash in the reference (:1950) and are rejected by the binding.
+ * --------------------------------------------------------------------- */
+#define MDPP_MAX_GRID_DIMS 4
+
+typedef struct mdpp_grid_config {
+  int32_t n_dims;               /* 2, or 4 with irrelevant_features           */
+  int32_t dense;                /* make_denser: Manhattan progress vs +1 at target */
+  int32_t reward_every_n_steps;
+  int32_t has_transition_noise; /* truthy transition_noise (:1734)            */
+  int32_t has_reward_noise;     /* "reward_noise" key present                 */
+  int32_t reserved0;
+  int32_t shape[MDPP_MAX_GRID_DIMS];  /* grid_shape (repeated when 4 dims)    */
+  int32_t target[2];            /* target_point (relevant cell)               */
+  double transition_noise;      /* p: the action is replaced by a different
+                                   GridActionSpace sample w.p. p (:1736-1750) */
+  double reward_noise_std, reward_scale, reward_shift, term_state_reward;
+} mdpp_grid_config;
+
+typedef struct mdpp_grid_state {   /* DEVICE pointers, struct-of-arrays      */
+  int64_t n_envs;
+  int32_t* pos;         /* [n_dims][N] current cell                           */
+  int32_t* t_episode;   /* [N]                                                */
+  uint32_t* episode;    /* [N]                                                */
+  uint8_t* reached;     /* [N] sticky reached_terminal                        */
+  double* stats;        /* [MDPP_N_STATS]                                     */
+} mdpp_grid_state;
+
+typedef struct mdpp_grid_io {      /* T steps, time-major, rows of n_dims    */
+  const int64_t* actions;          /* [T][N][n_dims]                          */
+  int64_t* obs;                    /* [T][N][n_dims] cell after the step (after
+                                      the auto-reset when one happened)       */
+  int64_t* final_obs;              /* [T][N][n_dims] before any auto-reset    */
+  double* reward;                  /* [T][N]                                  */
+  uint8_t* terminated;             /* [T][N]                                  */
+  uint8_t* truncated;              /* [T][N]                                  */
+  const double* replay_noise_u;      /* [T][N] uniform() of :1736             */
+  const int64_t* replay_noise_action;/* [T][N][n_dims] action applied when
+                                        that uniform is < p                   */
+  const double* replay_reward_noise; /* [T][N]                                */
+  const int64_t* replay_reset_state; /* [T][N][n_dims] cell of an auto-reset  */
+} mdpp_grid_io;
+
+#ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
+int mdpp_set_grid_config(mdpp_ctx* ctx, const mdpp_grid_config* cfg);
+int mdpp_grid_rollout(mdpp_ctx* ctx, const mdpp_grid_state* st,
+                      const mdpp_grid_io* io, const mdpp_step_opts* opts,
+                      void* cuda_stream);
+/* (masked) reset: `init_states` int64 [N][n_dims] when given, else Philox
+ * (every coordinate uniform on [0, shape]).  `obs` int64 [N][n_dims] or NULL. */
+int mdpp_grid_reset(mdpp_ctx* ctx, const mdpp_grid_state* st,
+                    const uint8_t* mask, const int64_t* init_states,
+                    int64_t* obs, const mdpp_step_opts* opts, void* cuda_stream);
+#endif
+
+/* ------------------------------------------------------------------------
  * Image observations (replaces ImageMultiDiscrete.generate_image,
  * spaces/image_multi_discrete.py:129-270, and ImageContinuous.generate_image
  * / get_image_representation, spaces/image_continuous.py:116-277).
@@ -346,6 +413,12 @@ typedef struct mdpp_image_continuous_config {
   int32_t rect[MDPP_MAX_TERM_BOXES][4];  /* x0, y0, x1, y1 inclusive pixels   */
   int32_t target_pixel[2];
   int32_t stamp[MDPP_MAX_STAMP_ROWS][2]; /* row: x offset, width (Pillow)     */
+  /* grid envs (image_continuous.py:139-164): white grid lines, drawn first.
+   * Bit x of vline[sub] = a full-height line in column x of sub-image `sub`
+   * (0 relevant, 1 irrelevant), bit y of hline[sub] = a full-width line in
+   * row y; width, height <= 256 when any bit is set.                         */
+  uint64_t vline[2][4];
+  uint64_t hline[2][4];
 } mdpp_image_continuous_config;
 
 #ifndef __CUDACC_RTC__ /* NVRTC sees the types only */

@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
     "mdpp_set_jit", "mdpp_jit_last_used", "mdpp_jit_log", "mdpp_jit_selftest",
     "mdpp_set_continuous_config", "mdpp_continuous_rollout",
     "mdpp_continuous_reset", "mdpp_render_discrete", "mdpp_render_continuous",
+    "mdpp_set_grid_config", "mdpp_grid_rollout", "mdpp_grid_reset",
 )
 MDPP_MAX_DIM, MDPP_MAX_ORDER, MDPP_MAX_TERM_BOXES = 16, 4, 8
 
@@ -150,6 +151,40 @@ class ImageContinuousConfig(C.Structure):
         ("rect", (C.c_int32 * 4) * MDPP_MAX_TERM_BOXES),
         ("target_pixel", C.c_int32 * 2),
         ("stamp", (C.c_int32 * 2) * MDPP_MAX_STAMP_ROWS),
+        ("vline", (C.c_uint64 * 4) * 2), ("hline", (C.c_uint64 * 4) * 2),
+    ]
+
+
+MDPP_MAX_GRID_DIMS = 4
+
+
+class GridConfig(C.Structure):
+    _fields_ = [
+        ("n_dims", C.c_int32), ("dense", C.c_int32),
+        ("reward_every_n_steps", C.c_int32),
+        ("has_transition_noise", C.c_int32), ("has_reward_noise", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("shape", C.c_int32 * MDPP_MAX_GRID_DIMS), ("target", C.c_int32 * 2),
+        ("transition_noise", C.c_double), ("reward_noise_std", C.c_double),
+        ("reward_scale", C.c_double), ("reward_shift", C.c_double),
+        ("term_state_reward", C.c_double),
+    ]
+
+
+class GridState(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int64), ("pos", C.c_void_p), ("t_episode", C.c_void_p),
+        ("episode", C.c_void_p), ("reached", C.c_void_p), ("stats", C.c_void_p),
+    ]
+
+
+class GridIO(C.Structure):
+    _fields_ = [
+        ("actions", C.c_void_p), ("obs", C.c_void_p), ("final_obs", C.c_void_p),
+        ("reward", C.c_void_p), ("terminated", C.c_void_p),
+        ("truncated", C.c_void_p), ("replay_noise_u", C.c_void_p),
+        ("replay_noise_action", C.c_void_p),
+        ("replay_reward_noise", C.c_void_p), ("replay_reset_state", C.c_void_p),
     ]
 
 
@@ -199,6 +234,11 @@ def load():
         C.c_int32, C.POINTER(StepOpts), P]
     lib.mdpp_render_continuous.argtypes = [
         P, C.POINTER(ImageContinuousConfig), P, P, C.c_int64, P]
+    lib.mdpp_set_grid_config.argtypes = [P, C.POINTER(GridConfig)]
+    lib.mdpp_grid_rollout.argtypes = [
+        P, C.POINTER(GridState), C.POINTER(GridIO), C.POINTER(StepOpts), P]
+    lib.mdpp_grid_reset.argtypes = [
+        P, C.POINTER(GridState), P, P, P, C.POINTER(StepOpts), P]
     if lib.mdpp_abi_version() != ABI_VERSION:
         raise RuntimeError("libmdpp_b200.so ABI version mismatch; rebuild")
     _lib = lib

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmdpp_b200.so")
 SOURCES = ["context.cu", "discrete.cu", "discrete_off.cu", "discrete_replay.cu",
            "discrete_philox_f64.cu", "discrete_philox_fast.cu", "continuous.cu",
-           "render.cu",
+           "render.cu", "grid.cu",
            "jit.cu"]
 HEADERS = ["internal.h", "device_types.h", "philox.cuh", "discrete_kernels.cuh",
            "continuous_kernels.cuh",

@@ -74,6 +74,9 @@ class EnvSpec:
     action_space_max: float = float("inf")
     terminal_centres: Any = None
     term_state_edge: float = 0.0
+    # grid
+    grid_shape: tuple = ()
+    terminal_cells: Any = None
 
 
 def parse_config(config):
@@ -98,11 +101,7 @@ def parse_config(config):
 
     config["state_space_type"] = config["state_space_type"].lower()
     kind = sp.kind = config["state_space_type"]
-    if kind not in ("discrete", "continuous"):
-        if kind == "grid":
-            raise NotImplementedError(
-                "grid environments are not on the B200 step path yet "
-                "(SURVEY.md 8f row N1)")
+    if kind not in ("discrete", "continuous", "grid"):
         raise ValueError("Unknown state_space_type")
     g = config.get
     sp.use_custom_mdp = bool(g("use_custom_mdp", False))
@@ -146,6 +145,31 @@ def parse_config(config):
         if callable(sp.reward_dist):
             raise NotImplementedError("callable reward_dist is not supported")
         sp.diameter = int(g("diameter", 1))
+    elif kind == "grid":  # :539-541, :655-657
+        assert "grid_shape" in config
+        sp.grid_shape = tuple(int(n) for n in config["grid_shape"])
+        assert len(sp.grid_shape) == 2, "grid_shape must be 2-D"
+        if config["reward_function"] != "move_to_a_point":
+            raise NotImplementedError("grid: only move_to_a_point (as in the reference)")
+        sp.target_point = [int(v) for v in config["target_point"]]
+        if "make_denser" not in config:
+            # the reference leaves the attribute unset for grid envs (:384-390)
+            # and raises AttributeError in the first reward computation
+            raise ValueError("grid environments need an explicit make_denser")
+        if sp.delay != 0 or sp.sequence_length != 1:
+            # np.array(augmented_state) is ragged then (:1950): the reference
+            # raises ValueError in the first step
+            raise NotImplementedError(
+                "grid environments: delay must be 0 and sequence_length 1 "
+                "(anything else crashes in the reference)")
+        if sp.irrelevant_features:
+            sp.grid_shape = sp.grid_shape * 2  # :604-608
+        if callable(config.get("terminal_states")):
+            raise NotImplementedError("callable terminal_states")
+        # terminal cells never end an episode in the reference (SURVEY 8f N1
+        # probe); they are drawn in image observations
+        sp.terminal_cells = [[int(v) for v in c]
+                             for c in config.get("terminal_states", [])]
     else:
         sp.state_space_dim = int(config["state_space_dim"])
         config.setdefault("reward_function", "move_to_a_point")
@@ -186,6 +210,10 @@ def parse_config(config):
             sp.state_space_size = int(config["state_space_size"])
         else:
             sp.state_space_size = sp.action_space_size * sp.diameter
+    elif kind == "grid":
+        sp.dtype_s = g("dtype_s", np.int64)
+        if np.dtype(sp.dtype_s) != np.dtype(np.int64):
+            raise NotImplementedError("grid dtype_s must be int64")
     else:  # :593-602
         sp.dtype_s = g("dtype_s", np.float32)
         if g("irrelevant_features", False):

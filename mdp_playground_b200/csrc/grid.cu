@@ -1,0 +1,380 @@
+// Grid environments on sm_100a: K8 `grid_rollout` (T fused steps) and the
+// (masked) reset.  Restates, per env and step, rl_toy_env.py
+//   transition_function :1727-1778  unit move with wall bounce; with prob. p
+//                                   the action is replaced by a different
+//                                   GridActionSpace sample; invalid = no-op
+//   reward_function     :1947-1965  Manhattan progress towards the target
+//                                   (dense) or +1 on it (sparse)
+//                       :1968-1990  every-n gate, noise, scale, shift
+//   step epilogue       :2098-2109  done = sticky reached_terminal, terminal reward
+//   reset               :2325-2345  every coordinate uniform on [0, shape]
+// One thread = one env, the cell lives in registers for the whole launch; I/O
+// is time-major with one 16- / 32-byte row per env and step (action rows are
+// prefetched a step ahead).  Integer arithmetic and fp64 rewards in the
+// reference's operation order: bit-exact.
+#include <cstring>
+
+#include "internal.h"
+#include "philox.cuh"
+
+namespace mdpp {
+
+constexpr int kGBlock = 128;
+
+struct GridParams {
+  mdpp_grid_config cfg;
+  mdpp_grid_state st;
+  mdpp_grid_io io;
+  int32_t T, autoreset, horizon, noise_mode;
+  uint32_t k0, k1;
+  uint64_t step_index;
+  const uint64_t* step_index_dev;
+  int64_t env_id_offset;
+  // reset
+  const uint8_t* mask;
+  const int64_t* init_states;
+  int64_t* reset_obs;
+};
+
+template <int ND>
+struct Row { int64_t v[ND]; };
+
+template <int ND>
+__device__ __forceinline__ Row<ND> ld_row(const int64_t* p) {
+  Row<ND> r;
+#pragma unroll
+  for (int k = 0; k < ND; k += 2) {
+    const longlong2 x = __ldcs(reinterpret_cast<const longlong2*>(p + k));
+    r.v[k] = x.x; r.v[k + 1] = x.y;
+  }
+  return r;
+}
+template <int ND>
+__device__ __forceinline__ void st_row(int64_t* p, const int32_t* c) {
+#pragma unroll
+  for (int k = 0; k < ND; k += 2)
+    __stcs(reinterpret_cast<longlong2*>(p + k), make_longlong2(c[k], c[k + 1]));
+}
+
+// Uniform over the GridActionSpace samples that differ from `a` (the
+// reference's rejection loop :1737-1750 in closed form): a sample is (dim,
+// value in {-1, 0, 1}), all ND zero-valued ones being the same no-op action.
+template <int ND>
+__device__ __forceinline__ void substitute_action(uint32_t w, int32_t* a) {
+  int dim = -1, val = 0;  // the valid action as (dim, val); no-op: dim = -1
+#pragma unroll
+  for (int k = 0; k < ND; ++k)
+    if (a[k] != 0) { dim = k; val = a[k]; }
+  int pick;  // index into the 3 * ND samples (dim * 3 + val + 1)
+  if (dim < 0) {  // current action is the no-op: one of the 2 * ND moves
+    const int q = (int)__umulhi(w, 2u * ND);
+    pick = (q >> 1) * 3 + ((q & 1) ? 2 : 0);
+  } else {        // one of the other 3 * ND - 1 samples
+    const int cur = dim * 3 + val + 1;
+    const int q = (int)__umulhi(w, 3u * ND - 1u);
+    pick = q + (q >= cur);
+  }
+#pragma unroll
+  for (int k = 0; k < ND; ++k) a[k] = 0;
+  const int d = pick / 3, v = pick - d * 3 - 1;
+#pragma unroll
+  for (int k = 0; k < ND; ++k)
+    if (k == d) a[k] = v;
+}
+
+__device__ __forceinline__ double block_sum(double x, double* smem) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = x;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0)
+    for (int k = 0; k < kGBlock / 32; ++k) s += smem[k];
+  __syncthreads();
+  return s;
+}
+
+template <int ND, int NOISE>
+__global__ void __launch_bounds__(kGBlock)
+grid_rollout_kernel(const __grid_constant__ GridParams p) {
+  __shared__ double red[kGBlock / 32];
+  const mdpp_grid_config& c = p.cfg;
+  const int64_t N = p.st.n_envs;
+  const int64_t env = (int64_t)blockIdx.x * kGBlock + threadIdx.x;
+  const bool active = env < N;
+  const int64_t e = active ? env : 0;
+  const uint32_t gid = (uint32_t)(p.env_id_offset + e);
+  const uint64_t step_base =
+      p.step_index + (p.step_index_dev ? *p.step_index_dev : 0ull);
+  int32_t pos[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) pos[k] = p.st.pos[(int64_t)k * N + e];
+  int32_t tl = p.st.t_episode[e];
+  uint32_t ep = p.st.episode[e];
+  bool reached = p.st.reached[e] != 0;
+  const uint32_t pn_T = (uint32_t)fmin(
+      floor(c.transition_noise * 4294967296.0 + 0.5), 4294967295.0);
+  const double term_add = c.term_state_reward * c.reward_scale;
+  double sum_reward = 0.0, sum_abs_rnoise = 0.0;
+  uint32_t n_noisy = 0, n_episodes = 0, n_term = 0, n_steps = 0;
+  if (active) {
+    Row<ND> nxt_a = ld_row<ND>(p.io.actions + e * ND);
+    for (int t = 0; t < p.T; ++t) {
+      const int64_t off = (int64_t)t * N + e;
+      const Row<ND> arow = nxt_a;
+      if (t + 1 < p.T) nxt_a = ld_row<ND>(p.io.actions + (off + N) * ND);
+      const uint64_t step = step_base + (uint64_t)t;
+      // GridActionSpace.contains: entries in {-1, 0, 1}, at most one move
+      int32_t a[ND];
+      bool valid = true;
+      int moves = 0;
+#pragma unroll
+      for (int k = 0; k < ND; ++k) {
+        valid &= arow.v[k] >= -1 && arow.v[k] <= 1;
+        a[k] = (int32_t)arow.v[k];
+        moves += a[k] != 0;
+      }
+      valid &= moves <= 1;
+      U4 w = {0u, 0u, 0u, 0u};
+      if (NOISE == MDPP_NOISE_PHILOX)
+        w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
+                          STREAM_GRID_STEP, p.k0, p.k1);
+      if (valid && c.has_transition_noise && NOISE != MDPP_NOISE_OFF) {
+        if (NOISE == MDPP_NOISE_REPLAY) {
+          if (__ldcs(p.io.replay_noise_u + off) < c.transition_noise) {
+            const Row<ND> r = ld_row<ND>(p.io.replay_noise_action + off * ND);
+#pragma unroll
+            for (int k = 0; k < ND; ++k) a[k] = (int32_t)r.v[k];
+            n_noisy += 1;
+          }
+        } else if (w.x < pn_T) {
+          substitute_action<ND>(w.y, a);
+          n_noisy += 1;
+        }
+      }
+      // dense reward: Manhattan distance moved towards the target
+      const int d_old = abs(pos[0] - c.target[0]) + abs(pos[1] - c.target[1]);
+      if (valid) {
+#pragma unroll
+        for (int k = 0; k < ND; ++k) {
+          int v = pos[k] + a[k];
+          v = max(v, 0);                       // bounce back from the walls;
+          if (v >= c.shape[k]) v = c.shape[k] - 1;  // (also pulls a one-past
+          pos[k] = v;                          //  reset cell in when it moves)
+        }
+      }
+      const bool at_target = pos[0] == c.target[0] && pos[1] == c.target[1];
+      reached |= at_target;
+      tl += 1;
+      double r = 0.0;
+      if (c.dense) {
+        const int d_new = abs(pos[0] - c.target[0]) + abs(pos[1] - c.target[1]);
+        r = (double)(d_old - d_new);
+      } else if (at_target) {
+        r = 1.0;
+      }
+      if (tl % c.reward_every_n_steps != 0) r = 0.0;
+      sum_reward += r;
+      if (c.has_reward_noise && NOISE != MDPP_NOISE_OFF) {
+        double z;
+        if (NOISE == MDPP_NOISE_REPLAY) {
+          z = __ldcs(p.io.replay_reward_noise + off);
+        } else {
+          double z0, z1;
+          normal_pair_f64(w.z, w.w, &z0, &z1);
+          z = __dmul_rn(c.reward_noise_std, z0);
+        }
+        sum_abs_rnoise += fabs(z);
+        r = __dadd_rn(r, z);
+      }
+      r = __dmul_rn(r, c.reward_scale);
+      r = __dadd_rn(r, c.reward_shift);
+      const bool done = reached;
+      if (done) r = __dadd_rn(r, term_add);
+      const bool trunc = p.horizon > 0 && tl >= p.horizon;
+      n_term += done;
+      n_steps += 1;
+      if (p.io.final_obs) st_row<ND>(p.io.final_obs + off * ND, pos);
+      if (p.autoreset && (done || trunc)) {
+        if (NOISE == MDPP_NOISE_REPLAY) {
+          const Row<ND> r0 = ld_row<ND>(p.io.replay_reset_state + off * ND);
+#pragma unroll
+          for (int k = 0; k < ND; ++k) pos[k] = (int32_t)r0.v[k];
+        } else {
+          U4 wr = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
+                                STREAM_GRID_AUTORESET, p.k0, p.k1);
+          const uint32_t ww[4] = {wr.x, wr.y, wr.z, wr.w};
+#pragma unroll
+          for (int k = 0; k < ND; ++k)
+            pos[k] = (int32_t)__umulhi(ww[k], (uint32_t)c.shape[k] + 1u);
+        }
+        tl = 0; ep += 1; reached = false; n_episodes += 1;
+      }
+      if (p.io.obs) st_row<ND>(p.io.obs + off * ND, pos);
+      if (p.io.reward) __stcs(p.io.reward + off, r);
+      if (p.io.terminated) __stcs(p.io.terminated + off, (uint8_t)done);
+      if (p.io.truncated) __stcs(p.io.truncated + off, (uint8_t)trunc);
+    }
+#pragma unroll
+    for (int k = 0; k < ND; ++k) p.st.pos[(int64_t)k * N + e] = pos[k];
+    p.st.t_episode[e] = tl;
+    p.st.episode[e] = ep;
+    p.st.reached[e] = (uint8_t)reached;
+  }
+  if (p.st.stats) {
+    const double vals[MDPP_N_STATS] = {
+        (double)n_episodes, (double)n_steps, sum_reward, (double)n_noisy,
+        sum_abs_rnoise, 0.0, 0.0, (double)n_term};
+#pragma unroll
+    for (int k = 0; k < MDPP_N_STATS; ++k) {
+      if (k == MDPP_STAT_ABS_TRANSITION_NOISE || k == MDPP_STAT_RESERVED) continue;
+      const double s = block_sum(vals[k], red);
+      if (threadIdx.x == 0 && s != 0.0) atomicAdd(p.st.stats + k, s);
+    }
+  }
+}
+
+template <int ND>
+__global__ void __launch_bounds__(kGBlock)
+grid_reset_kernel(const __grid_constant__ GridParams p) {
+  const int64_t N = p.st.n_envs;
+  const int64_t env = (int64_t)blockIdx.x * kGBlock + threadIdx.x;
+  if (env >= N) return;
+  int32_t pos[ND];
+  if (p.mask && !p.mask[env]) {
+    if (p.reset_obs)
+      for (int k = 0; k < ND; ++k)
+        p.reset_obs[env * ND + k] = p.st.pos[(int64_t)k * N + env];
+    return;
+  }
+  const uint32_t ep = p.st.episode[env];
+  if (p.init_states) {
+    for (int k = 0; k < ND; ++k) pos[k] = (int32_t)p.init_states[env * ND + k];
+  } else {
+    const uint32_t gid = (uint32_t)(p.env_id_offset + env);
+    U4 w = philox4x32_10(gid, ep, 0u, STREAM_GRID_RESET, p.k0, p.k1);
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+    for (int k = 0; k < ND; ++k)
+      pos[k] = (int32_t)__umulhi(ww[k], (uint32_t)p.cfg.shape[k] + 1u);
+  }
+  if (p.st.stats && p.st.t_episode[env] > 0)
+    atomicAdd(p.st.stats + MDPP_STAT_EPISODES, 1.0);
+  for (int k = 0; k < ND; ++k) {
+    p.st.pos[(int64_t)k * N + env] = pos[k];
+    if (p.reset_obs) p.reset_obs[env * ND + k] = pos[k];
+  }
+  p.st.t_episode[env] = 0;
+  p.st.episode[env] = ep + 1;
+  p.st.reached[env] = 0;
+}
+
+}  // namespace mdpp
+
+using namespace mdpp;
+
+extern "C" int mdpp_set_grid_config(mdpp_ctx* ctx, const mdpp_grid_config* cfg) {
+  if (!ctx) return MDPP_EINVAL;
+  if (!cfg) return fail(ctx, MDPP_EINVAL, "cfg is NULL");
+  if (cfg->n_dims != 2 && cfg->n_dims != 4)
+    return fail(ctx, MDPP_EINVAL, "grid: n_dims must be 2 or 4");
+  for (int k = 0; k < cfg->n_dims; ++k)
+    if (cfg->shape[k] < 1)
+      return fail(ctx, MDPP_EINVAL, "grid: bad grid_shape");
+  if (cfg->reward_every_n_steps < 1)
+    return fail(ctx, MDPP_EINVAL, "grid: bad reward_every_n_steps");
+  if (cfg->has_transition_noise &&
+      !(cfg->transition_noise > 0.0 && cfg->transition_noise <= 1.0))
+    return fail(ctx, MDPP_EINVAL, "grid: transition_noise must be in (0, 1]");
+  ctx->g_cfg = *cfg;
+  ctx->have_grid = true;
+  return MDPP_OK;
+}
+
+static int fill_grid(mdpp_ctx* ctx, const mdpp_grid_state* st,
+                     const mdpp_step_opts* opts, GridParams* p) {
+  if (!ctx) return MDPP_EINVAL;
+  if (!ctx->have_grid)
+    return fail(ctx, MDPP_EINVAL, "mdpp_set_grid_config was not called");
+  if (!st || !st->pos || !st->t_episode || !st->episode || !st->reached ||
+      st->n_envs < 1)
+    return fail(ctx, MDPP_EINVAL, "grid state has NULL arrays");
+  if (!opts) return fail(ctx, MDPP_EINVAL, "opts is NULL");
+  std::memset(p, 0, sizeof(*p));
+  p->cfg = ctx->g_cfg;
+  p->st = *st;
+  p->T = opts->n_steps;
+  p->autoreset = opts->autoreset;
+  p->horizon = opts->horizon;
+  p->noise_mode = opts->noise_mode;
+  p->k0 = (uint32_t)opts->seed;
+  p->k1 = (uint32_t)(opts->seed >> 32);
+  p->step_index = opts->step_index;
+  p->step_index_dev = opts->step_index_dev;
+  p->env_id_offset = opts->env_id_offset;
+  return MDPP_OK;
+}
+
+template <int ND>
+static int launch_grid(mdpp_ctx* ctx, const GridParams& p, cudaStream_t s) {
+  const unsigned grid = (unsigned)((p.st.n_envs + kGBlock - 1) / kGBlock);
+  switch (p.noise_mode) {
+    case MDPP_NOISE_OFF:
+      grid_rollout_kernel<ND, MDPP_NOISE_OFF><<<grid, kGBlock, 0, s>>>(p);
+      break;
+    case MDPP_NOISE_REPLAY:
+      grid_rollout_kernel<ND, MDPP_NOISE_REPLAY><<<grid, kGBlock, 0, s>>>(p);
+      break;
+    default:
+      grid_rollout_kernel<ND, MDPP_NOISE_PHILOX><<<grid, kGBlock, 0, s>>>(p);
+  }
+  MDPP_CUDA(ctx, cudaGetLastError());
+  return MDPP_OK;
+}
+
+extern "C" int mdpp_grid_rollout(mdpp_ctx* ctx, const mdpp_grid_state* st,
+                                 const mdpp_grid_io* io,
+                                 const mdpp_step_opts* opts, void* cuda_stream) {
+  GridParams p;
+  int rc = fill_grid(ctx, st, opts, &p);
+  if (rc) return rc;
+  if (!io || !io->actions || opts->n_steps < 1)
+    return fail(ctx, MDPP_EINVAL, "grid rollout needs actions and T >= 1");
+  if (opts->noise_mode < MDPP_NOISE_OFF || opts->noise_mode > MDPP_NOISE_PHILOX)
+    return fail(ctx, MDPP_EINVAL, "unknown noise_mode");
+  if (opts->noise_mode == MDPP_NOISE_REPLAY) {
+    if ((ctx->g_cfg.has_transition_noise &&
+         (!io->replay_noise_u || !io->replay_noise_action)) ||
+        (ctx->g_cfg.has_reward_noise && !io->replay_reward_noise) ||
+        (opts->autoreset && !io->replay_reset_state))
+      return fail(ctx, MDPP_EINVAL, "replay mode: missing replay array");
+  }
+  if (((uintptr_t)io->actions | (uintptr_t)io->obs | (uintptr_t)io->final_obs |
+       (uintptr_t)io->replay_noise_action | (uintptr_t)io->replay_reset_state) & 15)
+    return fail(ctx, MDPP_EINVAL, "grid rows must be 16-byte aligned");
+  p.io = *io;
+  MDPP_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  return ctx->g_cfg.n_dims == 4 ? launch_grid<4>(ctx, p, s)
+                                : launch_grid<2>(ctx, p, s);
+}
+
+extern "C" int mdpp_grid_reset(mdpp_ctx* ctx, const mdpp_grid_state* st,
+                               const uint8_t* mask, const int64_t* init_states,
+                               int64_t* obs, const mdpp_step_opts* opts,
+                               void* cuda_stream) {
+  GridParams p;
+  int rc = fill_grid(ctx, st, opts, &p);
+  if (rc) return rc;
+  if (!init_states && opts->noise_mode == MDPP_NOISE_REPLAY)
+    return fail(ctx, MDPP_EINVAL, "replay reset needs init_states");
+  p.mask = mask;
+  p.init_states = init_states;
+  p.reset_obs = obs;
+  MDPP_CUDA(ctx, cudaSetDevice(ctx->device));
+  const unsigned grid = (unsigned)((p.st.n_envs + kGBlock - 1) / kGBlock);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  if (ctx->g_cfg.n_dims == 4) grid_reset_kernel<4><<<grid, kGBlock, 0, s>>>(p);
+  else grid_reset_kernel<2><<<grid, kGBlock, 0, s>>>(p);
+  MDPP_CUDA(ctx, cudaGetLastError());
+  return MDPP_OK;
+}

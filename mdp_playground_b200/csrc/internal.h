@@ -32,6 +32,8 @@ struct mdpp_ctx {
   // continuous configuration (one per context)
   bool have_continuous = false;
   mdpp_continuous_config c_cfg;
+  bool have_grid = false;
+  mdpp_grid_config g_cfg;
   // runtime-specialised kernels (jit.cu), keyed by their define string
   std::map<std::string, void*> jit_functions;   // CUfunction
   std::vector<void*> jit_modules;               // CUmodule

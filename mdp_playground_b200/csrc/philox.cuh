@@ -20,6 +20,11 @@ enum PhiloxStream : uint32_t {
   STREAM_STATE_NOISE = 8,  // + pair index: continuous transition noise
   STREAM_IRR_STEP = 32,       // like STREAM_STEP / STREAM_AUTORESET, for the
   STREAM_IRR_AUTORESET = 33,  // irrelevant sub-MDP (irrelevant_features)
+  // grid envs: counter = (env, step): w0 noise decision, w1 substitute action,
+  // (w2, w3) Box-Muller reward normal; auto-reset / reset(): one word per dim
+  STREAM_GRID_STEP = 40,
+  STREAM_GRID_AUTORESET = 41,
+  STREAM_GRID_RESET = 42,     // counter word 1 = episode
   STREAM_RESET_BOX = 64,   // + attempt*16 + dim/4 (continuous reset sampling)
 };
 

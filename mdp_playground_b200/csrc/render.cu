@@ -312,6 +312,10 @@ render_continuous_kernel(const __grid_constant__ RenderCParams p) {
             y <= c.rect[b][3])
           return 0u;                                                // terminal, black
     }
+    // grid lines (white), drawn first by the reference, so tested last
+    if ((unsigned)x < 256u && (unsigned)y < 256u &&
+        (((c.vline[sub][x >> 6] >> (x & 63)) | (c.hline[sub][y >> 6] >> (y & 63))) & 1ull))
+      return 255u;
     return 208u;
   };
   const int total = W * H * 3;

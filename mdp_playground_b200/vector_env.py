@@ -98,6 +98,8 @@ class VectorRLToyEnv:
                    self._lib.mdpp_create(self.device.index, C.byref(self._ctx)))
         if self.spec.kind == "discrete":
             self._init_discrete()
+        elif self.spec.kind == "grid":
+            self._init_grid()
         else:
             self._init_continuous()
         if self.spec.image_representations:
@@ -321,6 +323,8 @@ class VectorRLToyEnv:
         options = options or {}
         if self.spec.kind == "continuous":
             return self._reset_continuous(seed, options)
+        if self.spec.kind == "grid":
+            return self._reset_grid(seed, options)
         N, dev = self.num_envs, self.device
         mask = options.get("mask")
         if mask is not None:
@@ -375,7 +379,7 @@ class VectorRLToyEnv:
         if self.spec.image_representations:
             return self.render_observation(state, image_params=image_params,
                                            reset=reset, allow_philox=ctor)
-        if self.spec.kind == "continuous":
+        if self.spec.kind in ("continuous", "grid"):
             return state
         return self._cast_obs(state)
 
@@ -421,6 +425,53 @@ class VectorRLToyEnv:
                 s = self.seed_dict.get("image_representations")
                 self._rng_I = [np_random(None if s is None else s + i)[0]
                                for i in range(self.num_envs)]
+        elif sp.kind == "grid":
+            # ImageContinuous with grid_shape (image_continuous.py:139-207):
+            # white grid lines, black terminal cells, green target and blue
+            # agent discs at the cell centres (+0.5), per sub-grid
+            nd, gs = self._nd, sp.grid_shape
+            if W > 256 or H > 256:
+                raise NotImplementedError("grid images: width, height <= 256")
+            hi = np.array(gs[:2], dtype=np.int64)
+
+            def to_pixel(vec):  # image_continuous.py:248-277 over Box(0, shape)
+                frac = (np.asarray(vec) - 0) / (hi - 0)
+                return (frac * (W, H)).astype(int)
+            c = _lib.ImageContinuousConfig()
+            c.width, c.height, c.dim = W, H, nd
+            c.n_sub_images = nd // 2
+            for k in range(2):
+                c.rel_index[k], c.irr_index[k] = k, (2 + k if nd == 4 else 0)
+                c.feat_low[k], c.feat_high[k] = 0.0, float(hi[k])
+            c.is_f64 = 1
+            cells = sp.terminal_cells or []
+            if len(cells) > _lib.MDPP_MAX_TERM_BOXES:
+                raise NotImplementedError("at most 8 terminal cells in images")
+            c.n_rects = len(cells)
+            for b, cell in enumerate(cells):
+                lo_ = np.array(cell, dtype=np.float64).astype(np.int64)
+                p0, p1 = to_pixel(lo_), to_pixel(lo_ + 1.0)
+                c.rect[b][0], c.rect[b][1] = int(p0[0]), int(p0[1])
+                c.rect[b][2], c.rect[b][3] = int(p1[0]), int(p1[1])
+            c.has_target = 1
+            tp = to_pixel(np.array(sp.target_point, dtype=float) + 0.5)
+            c.target_pixel[0], c.target_pixel[1] = int(tp[0]), int(tp[1])
+            spans = it.disc_stamp(5)
+            c.stamp_rows, c.stamp_radius = len(spans), 5
+            for r, (x0, wdt) in enumerate(spans):
+                c.stamp[r][0], c.stamp[r][1] = int(x0), int(wdt)
+            for sub in range(nd // 2):
+                off = 2 * sub
+                for i in range(1, gs[off] + 1):      # vertical lines (:141-151)
+                    x = i * W // gs[off] - 1
+                    if 0 <= x < W:
+                        c.vline[sub][x >> 6] |= 1 << (x & 63)
+                for j in range(1, gs[off + 1]):      # horizontal (:153-160; the
+                    y = j * H // gs[off]             # divisor is the FIRST extent)
+                    if 0 <= y < H:
+                        c.hline[sub][y >> 6] |= 1 << (y & 63)
+            self._img_cfg = c
+            self.obs_shape = (W * c.n_sub_images, H, 3)
         else:
             D = sp.state_space_dim
             assert np.isfinite(sp.state_space_max), \
@@ -524,8 +575,12 @@ class VectorRLToyEnv:
                 _ptr(self.last_image_params), _ptr(out), M, N,
                 6 if reset else 3, C.byref(opts), self._stream()))
             return out
-        st = state.to(self._real).contiguous()
-        M = st.numel() // sp.state_space_dim
+        if sp.kind == "grid":  # cell centres, float64 like the reference
+            st = (state.to(torch.float64) + 0.5).contiguous()
+            M = st.numel() // self._nd
+        else:
+            st = state.to(self._real).contiguous()
+            M = st.numel() // sp.state_space_dim
         lead = tuple(st.shape[:-1])
         out = torch.empty(lead + self.obs_shape, dtype=torch.uint8, device=dev)
         self._check(self._lib.mdpp_render_continuous(
@@ -547,6 +602,8 @@ class VectorRLToyEnv:
         actions = torch.as_tensor(actions)
         if self.spec.kind == "continuous":
             actions = actions.reshape(1, N, self.spec.state_space_dim)
+        elif self.spec.kind == "grid":
+            actions = actions.reshape(1, N, len(self.spec.grid_shape))
         elif self._irr:
             actions = actions.reshape(1, N, 2)
         else:
@@ -573,6 +630,9 @@ class VectorRLToyEnv:
         if self.spec.kind == "continuous":
             return self._rollout_continuous(n_steps, actions, replay, out,
                                             want_final_obs)
+        if self.spec.kind == "grid":
+            return self._rollout_grid(n_steps, actions, replay, out,
+                                      want_final_obs)
         T, N, dev = int(n_steps), self.num_envs, self.device
         row = (T, N, 2) if self._irr else (T, N)  # (relevant, irrelevant) rows
         if actions is not None:
@@ -629,7 +689,7 @@ class VectorRLToyEnv:
     # ------------------------------------------------------------------
     def _state_tensors(self):
         names = ("_cur", "_cur_irr", "_key", "_t", "_episode", "_ring", "_history",
-                 "_stats", "_derivs", "_emitted", "_reached")
+                 "_stats", "_derivs", "_emitted", "_reached", "_pos")
         return [getattr(self, n) for n in names
                 if getattr(self, n, None) is not None]
 
@@ -642,10 +702,14 @@ class VectorRLToyEnv:
         assert self.noise == "philox", "graphed step needs noise='philox'"
         N, dev = self.num_envs, self.device
         cont = self.spec.kind == "continuous"
+        grid = self.spec.kind == "grid"
         D = self.spec.state_space_dim
-        a_shape = (1, N, D) if cont else ((1, N, 2) if self._irr else (1, N))
-        static_a = torch.zeros(a_shape, dtype=self._real if cont else torch.int32,
-                               device=dev)
+        if grid:
+            a_shape = (1, N, len(self.spec.grid_shape))
+        else:
+            a_shape = (1, N, D) if cont else ((1, N, 2) if self._irr else (1, N))
+        static_a = torch.zeros(a_shape, dtype=self._real if cont else (
+            torch.int64 if grid else torch.int32), device=dev)
         if cont:
             out = {"obs": torch.empty((1, N, D), dtype=self._real, device=dev),
                    "reward": torch.empty((1, N), dtype=self._real, device=dev)}
@@ -978,8 +1042,181 @@ class VectorRLToyEnv:
         self._step_index += T
         return out
 
+
+    # ------------------------------------------------------------------
+    # grid backend (move_to_a_point on a 2-D grid)
+    # ------------------------------------------------------------------
+    def _init_grid(self):
+        """rl_toy_env.py:780-812: cells are int64 rows [x, y(, x_irr, y_irr)],
+        actions unit moves (GridActionSpace)."""
+        sp, N, dev = self.spec, self.num_envs, self.device
+        nd = len(sp.grid_shape)
+        self._irr = False
+        self._nd = nd
+        hi = np.array(sp.grid_shape, dtype=np.int64)
+        self.observation_space = BoxSpace(0 * hi, hi, (nd,), np.dtype(np.int64),
+                                          seed=self.seed_dict.get("state_space"))
+        self.action_space = BoxSpace(-np.ones(nd, dtype=np.int64),
+                                     np.ones(nd, dtype=np.int64), (nd,),
+                                     np.dtype(np.int64),
+                                     seed=self.seed_dict.get("action_space"))
+        self.has_pnoise = bool(sp.transition_noise)
+        self.has_rnoise = sp.has_reward_noise
+        c = _lib.GridConfig()
+        c.n_dims, c.dense = nd, int(sp.make_denser)
+        c.reward_every_n_steps = sp.reward_every_n_steps
+        c.has_transition_noise = int(self.has_pnoise)
+        c.has_reward_noise = int(self.has_rnoise)
+        for k in range(nd):
+            c.shape[k] = sp.grid_shape[k]
+        c.target[0], c.target[1] = sp.target_point[0], sp.target_point[1]
+        c.transition_noise = sp.transition_noise
+        c.reward_noise_std = sp.reward_noise_std
+        c.reward_scale, c.reward_shift = sp.reward_scale, sp.reward_shift
+        c.term_state_reward = sp.term_state_reward
+        self._check(self._lib.mdpp_set_grid_config(self._ctx, C.byref(c)))
+        self.n_groups = 1
+        self._pos = torch.zeros((nd, N), dtype=torch.int32, device=dev)
+        self._t = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._episode = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._reached = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._stats = torch.zeros((1, _lib.MDPP_N_STATS), dtype=torch.float64,
+                                  device=dev)
+        st = _lib.GridState()
+        st.n_envs = N
+        st.pos, st.t_episode = _ptr(self._pos), _ptr(self._t)
+        st.episode, st.reached = _ptr(self._episode), _ptr(self._reached)
+        st.stats = _ptr(self._stats)
+        self._state = st
+        self._history = None
+        if self.noise == "numpy":  # lane i: the reference seeded with seed + i
+            def lanes(key):
+                s = self.seed_dict.get(key)
+                return [np_random(None if s is None else s + i)[0]
+                        for i in range(N)]
+            self._rng_F, self._rng_A = lanes("state_space"), lanes("action_space")
+            self._rng_E = [None] * N
+
+    def _reset_grid(self, seed, options):
+        N, dev, nd = self.num_envs, self.device, self._nd
+        mask = options.get("mask")
+        if mask is not None:
+            mask = torch.as_tensor(mask, device=dev).to(torch.uint8).contiguous()
+        init = options.get("init_state")
+        if self.noise == "numpy" and init is None:
+            if seed is not None:
+                for i in range(N):
+                    self._rng_E[i], _ = np_random(seed + i)
+            elif self._rng_E[0] is None:
+                for i in range(N):
+                    self._rng_E[i], _ = np_random(None)
+            m = None if mask is None else mask.cpu().numpy()
+            init = self._pos.t().cpu().numpy().astype(np.int64)
+            hi = np.array(self.spec.grid_shape, dtype=np.int64) + 1
+            for i in range(N):
+                if m is None or m[i]:  # gymnasium's int Box: floor(U(0, shape+1))
+                    init[i] = np.floor(self._rng_F[i].uniform(
+                        low=np.zeros(nd), high=hi, size=(nd,))).astype(np.int64)
+        elif (seed is not None and self.noise == "philox"
+              and not options.get("_ctor")):
+            self.philox_seed = int(seed) & (2**64 - 1)
+        if init is not None:
+            init = torch.as_tensor(init, device=dev).to(torch.int64).reshape(
+                N, nd).contiguous()
+        elif self.noise == "replay" and not options.get("_ctor"):
+            raise ValueError("replay mode: pass options['init_state'] to reset()")
+        obs = torch.empty((N, nd), dtype=torch.int64, device=dev)
+        opts = self._opts(1, _lib.MDPP_NOISE_PHILOX)
+        self._check(self._lib.mdpp_grid_reset(
+            self._ctx, C.byref(self._state), _ptr(mask), _ptr(init), _ptr(obs),
+            C.byref(opts), self._stream()))
+        self.curr_obs = self._observe(obs, None, reset=True,
+                                      ctor=bool(options.get("_ctor")))
+        return self.curr_obs, {}
+
+    def _grid_numpy_draws(self, actions):
+        """The reference's draws for one step of every lane (:1734-1750 E
+        uniform + GridActionSpace samples, :1982 E normal), host side."""
+        N, nd = self.num_envs, self._nd
+        acts = actions.cpu().numpy().reshape(N, nd)
+        rep = {"noise_u": np.ones(N), "noise_action": acts.copy(),
+               "reward_noise": np.zeros(N)}
+        for i in range(N):
+            a = acts[i]
+            valid = bool(np.all((a >= -1) & (a <= 1)) and np.abs(a).sum() <= 1)
+            if valid and self.has_pnoise:
+                rep["noise_u"][i] = u = self._rng_E[i].uniform()
+                if u < self.spec.transition_noise:
+                    while True:
+                        new = np.zeros(nd, dtype=np.int64)
+                        ind = self._rng_A[i].integers(nd).item()
+                        new[ind] = self._rng_A[i].integers(3).item() - 1
+                        if not np.array_equal(new, a):
+                            rep["noise_action"][i] = new
+                            break
+            if self.has_rnoise:
+                rep["reward_noise"][i] = self._rng_E[i].normal(
+                    0, self.spec.reward_noise_std)
+        return {k: v[None] for k, v in rep.items()}
+
+    def _rollout_grid(self, n_steps, actions, replay, out, want_final_obs):
+        """actions: int64 [T, N, n_dims] unit moves; returns obs / final_obs
+        int64 [T, N, n_dims], reward float64 [T, N], terminated, truncated."""
+        T, N, dev, nd = int(n_steps), self.num_envs, self.device, self._nd
+        if actions is None:
+            raise ValueError("grid rollout needs an actions tensor [T, N, n_dims]")
+        actions = torch.as_tensor(actions, device=dev)
+        if actions.dtype.is_floating_point:
+            # the reference applies a no-op (and warns) for non-int64 actions
+            # (:1730-1733); a float tensor is most likely a caller bug
+            raise TypeError(f"grid actions must be integers, got {actions.dtype}")
+        actions = actions.to(torch.int64).contiguous()
+        assert actions.shape == (T, N, nd), (actions.shape, (T, N, nd))
+        if out is None:
+            out = {
+                "obs": torch.empty((T, N, nd), dtype=torch.int64, device=dev),
+                "reward": torch.empty((T, N), dtype=torch.float64, device=dev),
+                "terminated": torch.empty((T, N), dtype=torch.bool, device=dev),
+                "truncated": torch.empty((T, N), dtype=torch.bool, device=dev),
+            }
+            if want_final_obs:
+                out["final_obs"] = torch.empty((T, N, nd), dtype=torch.int64,
+                                               device=dev)
+        io = _lib.GridIO()
+        io.actions = _ptr(actions)
+        io.obs, io.reward = _ptr(out.get("obs")), _ptr(out.get("reward"))
+        io.final_obs = _ptr(out.get("final_obs"))
+        io.terminated = _ptr(out.get("terminated"))
+        io.truncated = _ptr(out.get("truncated"))
+        keep = []
+        if self.noise == "numpy":
+            assert not self.autoreset and T == 1, \
+                "noise='numpy' steps one at a time with explicit resets"
+            replay = self._grid_numpy_draws(actions)
+        if self.noise in ("replay", "numpy"):
+            replay = replay or {}
+            for name, field, dt, shp in (
+                    ("noise_u", "replay_noise_u", torch.float64, (T, N)),
+                    ("noise_action", "replay_noise_action", torch.int64, (T, N, nd)),
+                    ("reward_noise", "replay_reward_noise", torch.float64, (T, N)),
+                    ("reset_state", "replay_reset_state", torch.int64, (T, N, nd))):
+                if replay.get(name) is not None:
+                    t_ = torch.as_tensor(replay[name], device=dev).to(dt).reshape(
+                        shp).contiguous()
+                    keep.append(t_)
+                    setattr(io, field, _ptr(t_))
+        opts = self._opts(T)
+        self._check(self._lib.mdpp_grid_rollout(
+            self._ctx, C.byref(self._state), C.byref(io), C.byref(opts),
+            self._stream()))
+        self._step_index += T
+        return out
+
     # ------------------------------------------------------------------
     def get_augmented_state(self):
+        if self.spec.kind == "grid":
+            return {"curr_state": self._pos.t().to(torch.int64).contiguous(),
+                    "curr_obs": self.curr_obs}
         if self.spec.kind == "continuous":
             return {"curr_state": self._emitted.t().contiguous(),
                     "curr_obs": self.curr_obs,

@@ -75,3 +75,202 @@ def test_oracle_replay_of_recorded_draws(name):
         env.reset()
         _check_lane(env, g, k, CASES[name].get("horizon", 12), False)
         assert all(len(v) == 0 for v in env.draws.feed.values())
+
+
+# --------------------------------------------------------------------------
+# batched oracle (CPU) and the CUDA path (GPU)
+# --------------------------------------------------------------------------
+from oracle.vector_grid_oracle import VectorGridOracle  # noqa: E402
+
+GRID_PLAIN = [n for n in gu.GRID_CASES
+              if not CASES[n]["config"].get("image_representations")]
+
+
+def make_env(*a, **k):
+    from mdp_playground_b200 import VectorRLToyEnv
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return VectorRLToyEnv(*a, **k)
+
+
+def replay_grid_golden(vec_reset, vec_step, g):
+    """Every golden lane = one env of the batch; recorded draws replayed,
+    resets issued where the reference reset."""
+    K, T = g["done"].shape
+    cur = vec_reset(None, g["init_state"], None)
+    assert np.array_equal(cur, g["init_state"])
+    for t in range(T):
+        obs, r, done = vec_step(g["actions"][:, t], dict(
+            noise_u=np.nan_to_num(g["grid_noise_u"][:, t], nan=1.0),
+            noise_action=g["grid_noise_action"][:, t],
+            reward_noise=np.nan_to_num(g["reward_noise"][:, t])), t)
+        assert np.array_equal(obs, g["state"][:, t]), t
+        assert np.array_equal(r, g["reward"][:, t]), (t, r, g["reward"][:, t])
+        assert np.array_equal(done, g["done"][:, t]), t
+        m = g["reset_after"][:, t]
+        if m.any():
+            cur = vec_reset(m, np.where(m[:, None], g["reset_state"][:, t],
+                                        g["state"][:, t]), t)
+            assert np.array_equal(cur[m], g["reset_state"][m, t]), t
+
+
+@pytest.mark.parametrize("name", GRID_PLAIN)
+def test_vector_oracle_replays_reference_golden(name):
+    g = gu.load(name)
+    vec = VectorGridOracle(scalar_oracle(gu.case_config(name)), g["done"].shape[0])
+
+    def vec_reset(mask, init, t):
+        return vec.reset(mask=mask, init_state=init)
+
+    def vec_step(a, rep, t):
+        out = vec.rollout(1, a[None], replay={k: v[None] for k, v in rep.items()})
+        return out["obs"][0], out["reward"][0], out["terminated"][0]
+
+    replay_grid_golden(vec_reset, vec_step, g)
+
+
+def test_substitute_action_is_uniform_over_the_other_samples():
+    """Closed form of the reference's rejection loop: every GridActionSpace
+    sample (dim, value) other than the current action equally likely."""
+    from oracle.vector_grid_oracle import substitute_action
+    for nd in (2, 4):
+        for a in ([0] * nd, [1] + [0] * (nd - 1), [0] * (nd - 1) + [-1]):
+            ws = np.linspace(0, 2 ** 32 - 1, 6 * nd * 50).astype(np.uint64)
+            counts = {}
+            for w in ws:
+                b = tuple(substitute_action(w, a))
+                assert list(b) != a and sum(abs(v) for v in b) <= 1
+                counts[b] = counts.get(b, 0) + 1
+            moves = {k: v for k, v in counts.items() if any(k)}
+            assert len(moves) == 2 * nd - (1 if any(a) else 0)
+            assert max(moves.values()) - min(moves.values()) <= 2
+            if any(a):  # the no-op stands for nd of the 3*nd - 1 samples
+                assert abs(counts[(0,) * nd] - nd * np.mean(list(moves.values()))) <= 2 * nd
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", gu.GRID_CASES)
+def test_cuda_replays_reference_golden(name):
+    g = gu.load(name)
+    K = g["done"].shape[0]
+    image = "obs_image" in g
+    env = make_env(K, noise="replay", **gu.case_config(name))
+
+    def vec_reset(mask, init, t):
+        obs, _ = env.reset(options={"mask": mask, "init_state": init})
+        if image:
+            want = g["init_image"] if t is None else g["reset_image"][:, t]
+            sel = slice(None) if mask is None else mask
+            assert np.array_equal(obs.cpu().numpy()[sel], want[sel])
+        return env.get_augmented_state()["curr_state"].cpu().numpy()
+
+    def vec_step(a, rep, t):
+        obs, r, term, trunc, info = env.step(a, replay=rep)
+        assert not trunc.any()
+        if image:
+            assert np.array_equal(obs.cpu().numpy(), g["obs_image"][:, t]), t
+        return info["state"].cpu().numpy(), r.cpu().numpy(), term.cpu().numpy()
+
+    replay_grid_golden(vec_reset, vec_step, g)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", gu.GRID_CASES)
+def test_same_seed_drop_in_numpy_streams(name):
+    """noise='numpy': one env, same config and seed as the (oracle of the)
+    reference => the same trajectory, constructor included."""
+    cfg = gu.case_config(name)
+    ref = scalar_oracle(gu.case_config(name))
+    env = make_env(1, noise="numpy", **cfg)
+    nd = len(ref.grid_shape)
+    assert np.array_equal(env.curr_obs[0].cpu().numpy(), ref.curr_obs)
+    rng = np.random.default_rng(9)
+    for t in range(40 if cfg.get("image_representations") else 200):
+        a = [0] * nd
+        if rng.integers(8) < 7:
+            d = int(rng.integers(nd))
+            a[d] = int(np.sign(ref.target_point[d % 2] - ref.curr_state[d])) \
+                if rng.integers(2) else int(rng.integers(-1, 2))
+        else:
+            a = [int(v) for v in rng.integers(-1, 3, size=nd)]
+        o1, r1, d1, _, _ = ref.step(list(a))
+        o2, r2, d2, tr2, info = env.step(np.array([a]))
+        assert np.array_equal(o2[0].cpu().numpy(), o1), t
+        assert float(r2[0]) == float(r1) and bool(d2[0]) == d1, t
+        assert np.array_equal(info["state"][0].cpu().numpy(), ref.curr_state)
+        if t % 25 == 24 or (d1 and t % 2):
+            o1, _ = ref.reset()
+            o2, _ = env.reset()
+            assert np.array_equal(o2[0].cpu().numpy(), o1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,N,T,autoreset,horizon", [
+    ("grid_dense_term", 1000, 40, True, 9),
+    ("grid_sparse_noise", 777, 33, True, 0),
+    ("grid_irr_5x9", 300, 50, True, 11),
+    ("grid_sparse_noise", 257, 25, False, 0),
+])
+def test_philox_rollout_matches_oracle(name, N, T, autoreset, horizon):
+    cfg = gu.case_config(name)
+    ora = VectorGridOracle(scalar_oracle(gu.case_config(name)), N,
+                           autoreset=autoreset, horizon=horizon, seed=77,
+                           env_id_offset=1000)
+    env = make_env(N, autoreset=autoreset, horizon=horizon, philox_seed=77,
+                   env_id_offset=1000, **cfg)
+    first = ora.reset()
+    assert np.array_equal(env.get_augmented_state()["curr_state"].cpu().numpy(), first)
+    shape = np.array(ora.shape)
+    assert (first == shape).any() and (first <= shape).all()  # one-past cells occur
+    rng = np.random.default_rng(3)
+    for part in (T, 7, 1):
+        acts = np.zeros((part, N, ora.nd), dtype=np.int64)
+        d = rng.integers(ora.nd, size=(part, N))
+        np.put_along_axis(acts, d[..., None], rng.integers(-1, 2, size=(part, N, 1)), -1)
+        bad = rng.random((part, N)) < 0.05
+        acts[bad] = rng.integers(-2, 3, size=(int(bad.sum()), ora.nd))
+        want = ora.rollout(part, acts)
+        got = env.rollout(part, actions=acts)
+        for k in ("obs", "final_obs", "terminated", "truncated"):
+            assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+        np.testing.assert_allclose(got["reward"].cpu().numpy(), want["reward"],
+                                   rtol=1e-12, atol=1e-12)
+    st = env.episode_stats()
+    for k in ("episodes", "transitions", "noisy_transitions", "terminated"):
+        assert st[k][0] == ora.stats[k], k
+    np.testing.assert_allclose(st["reward"][0], ora.stats["reward"], rtol=1e-9)
+    if ora.has_pnoise:  # the action was replaced about p of the (valid) time
+        assert abs(ora.stats["noisy_transitions"] / ora.stats["transitions"]
+                   - ora.p * 0.95) < 0.03
+
+
+@pytest.mark.gpu
+def test_graphed_step_and_rollout_equal_repeated_steps():
+    import torch
+    cfg = gu.case_config("grid_sparse_noise")
+    a = make_env(512, autoreset=True, horizon=7, philox_seed=3, **cfg)
+    b = make_env(512, autoreset=True, horizon=7, philox_seed=3, **cfg)
+    c = make_env(512, autoreset=True, horizon=7, philox_seed=3, **cfg)
+    step = b.make_graphed_step()
+    gen = torch.Generator("cuda").manual_seed(0)
+    acts = torch.zeros((12, 512, 2), dtype=torch.int64, device="cuda")
+    acts[..., 0] = torch.randint(-1, 2, (12, 512), device="cuda", generator=gen)
+    whole = c.rollout(12, actions=acts)
+    for t in range(12):
+        o1, r1, d1, t1, _ = a.step(acts[t])
+        o2, r2, d2, t2, _ = step(acts[t])
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+        assert torch.equal(o1, whole["obs"][t]) and torch.equal(r1, whole["reward"][t])
+
+
+def test_grid_config_rejections():
+    from mdp_playground_b200.config import parse_config
+    base = gu.case_config("grid_dense_term")
+    with pytest.raises(NotImplementedError):
+        parse_config(dict(base, delay=1))
+    with pytest.raises(NotImplementedError):
+        parse_config(dict(base, sequence_length=2))
+    cfg = dict(base)
+    del cfg["make_denser"]
+    with pytest.raises(ValueError):
+        parse_config(cfg)

@@ -61,7 +61,10 @@ def _check_lane(env, g, k, cfg, H):
                 assert np.array_equal(obs_r, g["reset_image"][k, t])
 
 
-@pytest.mark.parametrize("name", list(CASES))
+NOT_GRID = [n for n in CASES if n not in gu.GRID_CASES]  # grid: tests/test_grid.py
+
+
+@pytest.mark.parametrize("name", NOT_GRID)
 def test_oracle_numpy_streams_match_reference_golden(name):
     g = gu.load(name)
     cfg = gu.case_config(name)
@@ -120,7 +123,7 @@ def _lane_feed(g, k, cont, image_params=None):
     return feed
 
 
-@pytest.mark.parametrize("name", [n for n in CASES
+@pytest.mark.parametrize("name", [n for n in NOT_GRID
                                   if not CASES[n]["config"].get(
                                       "image_representations")])
 def test_oracle_replay_of_recorded_draws(name):
