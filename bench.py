@@ -261,6 +261,22 @@ def other_configs(torch, Env, dev, rank, world, barrier, max_over_ranks, peak):
         line("N2_discrete_irrelevant_features_rollout", N, T, ms, 34,
              "fused rollout, two sub-MDPs per env, transition noise 0.1")
         del env, acts, out
+        # N1: grid env, tests/test_mdp_playground.py:1057 shape;
+        # int64 rows: 16 B action in, 16 B cell + 8 B reward + 2 B flags out
+        Ng, Tg = 1 << 20, 100
+        env = Env(Ng, device=dev, autoreset=True, horizon=100,
+                  env_id_offset=rank * Ng, seed=0, state_space_type="grid",
+                  grid_shape=(8, 8), delay=0, sequence_length=1,
+                  reward_function="move_to_a_point", target_point=[5, 5],
+                  make_denser=True, transition_noise=0.1)
+        acts = torch.zeros((Tg, Ng, 2), dtype=torch.int64, device=dev)
+        acts[..., 0] = torch.randint(-1, 2, (Tg, Ng), device=dev)
+        out = env.rollout(Tg, actions=acts, want_final_obs=False)
+        ms = _time_launches(torch, lambda: env.rollout(Tg, actions=acts, out=out),
+                            5, barrier, max_over_ranks)
+        line("N1_grid_rollout", Ng, Tg, ms, 42,
+             "fused rollout, 8x8 grid, dense reward, transition noise 0.1")
+        del env, acts, out
         # C3: continuous move_to_a_point, 1M envs
         N, T = 1 << 20, 100
         c3 = dict(seed=0, state_space_type="continuous", state_space_dim=6,

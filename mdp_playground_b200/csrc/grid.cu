@@ -25,7 +25,7 @@ struct GridParams {
   mdpp_grid_config cfg;
   mdpp_grid_state st;
   mdpp_grid_io io;
-  int32_t T, autoreset, horizon, noise_mode;
+  int32_t T, autoreset, horizon, noise_mode, normal_mode;
   uint32_t k0, k1;
   uint64_t step_index;
   const uint64_t* step_index_dev;
@@ -49,6 +49,24 @@ __device__ __forceinline__ Row<ND> ld_row(const int64_t* p) {
   }
   return r;
 }
+// An action row, validated and packed when it is loaded: 2 bits per entry
+// (value + 1), bit 31 = not a GridActionSpace member (-> no-op).  Keeps the
+// 4-step prefetch ring at one register per row.
+template <int ND>
+__device__ __forceinline__ uint32_t ld_action(const int64_t* p) {
+  const Row<ND> r = ld_row<ND>(p);
+  uint32_t code = 0;
+  bool valid = true;
+  int moves = 0;
+#pragma unroll
+  for (int k = 0; k < ND; ++k) {
+    valid &= r.v[k] >= -1 && r.v[k] <= 1;
+    moves += r.v[k] != 0;
+    code |= ((uint32_t)(r.v[k] + 1) & 3u) << (2 * k);
+  }
+  return (valid && moves <= 1) ? code : 0x80000000u;
+}
+
 template <int ND>
 __device__ __forceinline__ void st_row(int64_t* p, const int32_t* c) {
 #pragma unroll
@@ -95,7 +113,7 @@ __device__ __forceinline__ double block_sum(double x, double* smem) {
 }
 
 template <int ND, int NOISE>
-__global__ void __launch_bounds__(kGBlock)
+__global__ void __launch_bounds__(kGBlock, 6)
 grid_rollout_kernel(const __grid_constant__ GridParams p) {
   __shared__ double red[kGBlock / 32];
   const mdpp_grid_config& c = p.cfg;
@@ -117,103 +135,145 @@ grid_rollout_kernel(const __grid_constant__ GridParams p) {
   const double term_add = c.term_state_reward * c.reward_scale;
   double sum_reward = 0.0, sum_abs_rnoise = 0.0;
   uint32_t n_noisy = 0, n_episodes = 0, n_term = 0, n_steps = 0;
+  uint64_t cached_pair = ~0ull, cached_quad = ~0ull;
+  U4 w_pair = {0u, 0u, 0u, 0u};
+  double zq[4] = {0.0, 0.0, 0.0, 0.0};
   if (active) {
-    Row<ND> nxt_a = ld_row<ND>(p.io.actions + e * ND);
-    for (int t = 0; t < p.T; ++t) {
-      const int64_t off = (int64_t)t * N + e;
-      const Row<ND> arow = nxt_a;
-      if (t + 1 < p.T) nxt_a = ld_row<ND>(p.io.actions + (off + N) * ND);
-      const uint64_t step = step_base + (uint64_t)t;
-      // GridActionSpace.contains: entries in {-1, 0, 1}, at most one move
-      int32_t a[ND];
-      bool valid = true;
-      int moves = 0;
+    // action rows run 4 steps ahead of their use (a DRAM read under the
+    // write-heavy stream takes longer than one step's arithmetic)
+    constexpr int kAhead = 4;
+    uint32_t ring[kAhead];
 #pragma unroll
-      for (int k = 0; k < ND; ++k) {
-        valid &= arow.v[k] >= -1 && arow.v[k] <= 1;
-        a[k] = (int32_t)arow.v[k];
-        moves += a[k] != 0;
+    for (int j = 0; j < kAhead; ++j) {
+      ring[j] = 0x80000000u;
+      if (j < p.T) ring[j] = ld_action<ND>(p.io.actions + ((int64_t)j * N + e) * ND);
+    }
+    for (int t0 = 0; t0 < p.T; t0 += kAhead) {
+      uint32_t cur[kAhead];
+#pragma unroll
+      for (int j = 0; j < kAhead; ++j) {
+        cur[j] = ring[j];
+        if (t0 + kAhead + j < p.T)
+          ring[j] = ld_action<ND>(p.io.actions + ((int64_t)(t0 + kAhead + j) * N + e) * ND);
       }
-      valid &= moves <= 1;
-      U4 w = {0u, 0u, 0u, 0u};
-      if (NOISE == MDPP_NOISE_PHILOX)
-        w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
-                          STREAM_GRID_STEP, p.k0, p.k1);
-      if (valid && c.has_transition_noise && NOISE != MDPP_NOISE_OFF) {
-        if (NOISE == MDPP_NOISE_REPLAY) {
-          if (__ldcs(p.io.replay_noise_u + off) < c.transition_noise) {
-            const Row<ND> r = ld_row<ND>(p.io.replay_noise_action + off * ND);
 #pragma unroll
-            for (int k = 0; k < ND; ++k) a[k] = (int32_t)r.v[k];
+      for (int j = 0; j < kAhead; ++j) {
+        const int t = t0 + j;
+        if (t >= p.T) break;
+        const int64_t off = (int64_t)t * N + e;
+        const uint64_t step = step_base + (uint64_t)t;
+        // GridActionSpace.contains: entries in {-1, 0, 1}, at most one move
+        const bool valid = (cur[j] >> 31) == 0;
+        int32_t a[ND];
+#pragma unroll
+        for (int k = 0; k < ND; ++k)
+          a[k] = valid ? (int32_t)((cur[j] >> (2 * k)) & 3u) - 1 : 0;
+        // Philox draws are shared by consecutive steps (the step index is
+        // uniform over the launch, so these refills are uniform branches):
+        // STREAM_GRID_STEP, counter = step >> 1: words (0, 1) / (2, 3) = noise
+        // decision and substitute action of the even / odd step;
+        // STREAM_GRID_NORMAL, counter = step >> 2: two Box-Muller pairs = the
+        // reward normals of 4 steps
+        uint32_t w_u = 0, w_sub = 0;
+        if (NOISE == MDPP_NOISE_PHILOX && c.has_transition_noise) {
+          if ((step >> 1) != cached_pair) {
+            cached_pair = step >> 1;
+            w_pair = philox4x32_10(gid, (uint32_t)cached_pair,
+                                   (uint32_t)(cached_pair >> 32), STREAM_GRID_STEP,
+                                   p.k0, p.k1);
+          }
+          w_u = (step & 1) ? w_pair.z : w_pair.x;
+          w_sub = (step & 1) ? w_pair.w : w_pair.y;
+        }
+        if (valid && c.has_transition_noise && NOISE != MDPP_NOISE_OFF) {
+          if (NOISE == MDPP_NOISE_REPLAY) {
+            if (__ldcs(p.io.replay_noise_u + off) < c.transition_noise) {
+              const Row<ND> r = ld_row<ND>(p.io.replay_noise_action + off * ND);
+#pragma unroll
+              for (int k = 0; k < ND; ++k) a[k] = (int32_t)r.v[k];
+              n_noisy += 1;
+            }
+          } else if (w_u < pn_T) {
+            substitute_action<ND>(w_sub, a);
             n_noisy += 1;
           }
-        } else if (w.x < pn_T) {
-          substitute_action<ND>(w.y, a);
-          n_noisy += 1;
         }
-      }
-      // dense reward: Manhattan distance moved towards the target
-      const int d_old = abs(pos[0] - c.target[0]) + abs(pos[1] - c.target[1]);
-      if (valid) {
+        // dense reward: Manhattan distance moved towards the target
+        const int d_old = abs(pos[0] - c.target[0]) + abs(pos[1] - c.target[1]);
+        if (valid) {
 #pragma unroll
-        for (int k = 0; k < ND; ++k) {
-          int v = pos[k] + a[k];
-          v = max(v, 0);                       // bounce back from the walls;
-          if (v >= c.shape[k]) v = c.shape[k] - 1;  // (also pulls a one-past
-          pos[k] = v;                          //  reset cell in when it moves)
+          for (int k = 0; k < ND; ++k) {
+            int v = pos[k] + a[k];
+            v = max(v, 0);                       // bounce back from the walls;
+            if (v >= c.shape[k]) v = c.shape[k] - 1;  // (also pulls a one-past
+            pos[k] = v;                          //  reset cell in when it moves)
+          }
         }
-      }
-      const bool at_target = pos[0] == c.target[0] && pos[1] == c.target[1];
-      reached |= at_target;
-      tl += 1;
-      double r = 0.0;
-      if (c.dense) {
-        const int d_new = abs(pos[0] - c.target[0]) + abs(pos[1] - c.target[1]);
-        r = (double)(d_old - d_new);
-      } else if (at_target) {
-        r = 1.0;
-      }
-      if (tl % c.reward_every_n_steps != 0) r = 0.0;
-      sum_reward += r;
-      if (c.has_reward_noise && NOISE != MDPP_NOISE_OFF) {
-        double z;
-        if (NOISE == MDPP_NOISE_REPLAY) {
-          z = __ldcs(p.io.replay_reward_noise + off);
-        } else {
-          double z0, z1;
-          normal_pair_f64(w.z, w.w, &z0, &z1);
-          z = __dmul_rn(c.reward_noise_std, z0);
+        const bool at_target = pos[0] == c.target[0] && pos[1] == c.target[1];
+        reached |= at_target;
+        tl += 1;
+        double r = 0.0;
+        if (c.dense) {
+          const int d_new = abs(pos[0] - c.target[0]) + abs(pos[1] - c.target[1]);
+          r = (double)(d_old - d_new);
+        } else if (at_target) {
+          r = 1.0;
         }
-        sum_abs_rnoise += fabs(z);
-        r = __dadd_rn(r, z);
-      }
-      r = __dmul_rn(r, c.reward_scale);
-      r = __dadd_rn(r, c.reward_shift);
-      const bool done = reached;
-      if (done) r = __dadd_rn(r, term_add);
-      const bool trunc = p.horizon > 0 && tl >= p.horizon;
-      n_term += done;
-      n_steps += 1;
-      if (p.io.final_obs) st_row<ND>(p.io.final_obs + off * ND, pos);
-      if (p.autoreset && (done || trunc)) {
-        if (NOISE == MDPP_NOISE_REPLAY) {
-          const Row<ND> r0 = ld_row<ND>(p.io.replay_reset_state + off * ND);
+        if (tl % c.reward_every_n_steps != 0) r = 0.0;
+        sum_reward += r;
+        if (c.has_reward_noise && NOISE != MDPP_NOISE_OFF) {
+          double z;
+          if (NOISE == MDPP_NOISE_REPLAY) {
+            z = __ldcs(p.io.replay_reward_noise + off);
+          } else {
+            if ((step >> 2) != cached_quad) {
+              cached_quad = step >> 2;
+              const U4 wn = philox4x32_10(gid, (uint32_t)cached_quad,
+                                          (uint32_t)(cached_quad >> 32),
+                                          STREAM_GRID_NORMAL, p.k0, p.k1);
+              if (p.normal_mode == MDPP_NORMAL_FAST) {
+                normal_pair_fast(wn.x, wn.y, &zq[0], &zq[1]);
+                normal_pair_fast(wn.z, wn.w, &zq[2], &zq[3]);
+              } else {
+                normal_pair_f64(wn.x, wn.y, &zq[0], &zq[1]);
+                normal_pair_f64(wn.z, wn.w, &zq[2], &zq[3]);
+              }
+            }
+            const int j4 = (int)(step & 3);
+            const double z0 = j4 == 0 ? zq[0] : j4 == 1 ? zq[1] : j4 == 2 ? zq[2] : zq[3];
+            z = __dmul_rn(c.reward_noise_std, z0);
+          }
+          sum_abs_rnoise += fabs(z);
+          r = __dadd_rn(r, z);
+        }
+        r = __dmul_rn(r, c.reward_scale);
+        r = __dadd_rn(r, c.reward_shift);
+        const bool done = reached;
+        if (done) r = __dadd_rn(r, term_add);
+        const bool trunc = p.horizon > 0 && tl >= p.horizon;
+        n_term += done;
+        n_steps += 1;
+        if (p.io.final_obs) st_row<ND>(p.io.final_obs + off * ND, pos);
+        if (p.autoreset && (done || trunc)) {
+          if (NOISE == MDPP_NOISE_REPLAY) {
+            const Row<ND> r0 = ld_row<ND>(p.io.replay_reset_state + off * ND);
 #pragma unroll
-          for (int k = 0; k < ND; ++k) pos[k] = (int32_t)r0.v[k];
-        } else {
-          U4 wr = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
-                                STREAM_GRID_AUTORESET, p.k0, p.k1);
-          const uint32_t ww[4] = {wr.x, wr.y, wr.z, wr.w};
+            for (int k = 0; k < ND; ++k) pos[k] = (int32_t)r0.v[k];
+          } else {
+            U4 wr = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
+                                  STREAM_GRID_AUTORESET, p.k0, p.k1);
+            const uint32_t ww[4] = {wr.x, wr.y, wr.z, wr.w};
 #pragma unroll
-          for (int k = 0; k < ND; ++k)
-            pos[k] = (int32_t)__umulhi(ww[k], (uint32_t)c.shape[k] + 1u);
+            for (int k = 0; k < ND; ++k)
+              pos[k] = (int32_t)__umulhi(ww[k], (uint32_t)c.shape[k] + 1u);
+          }
+          tl = 0; ep += 1; reached = false; n_episodes += 1;
         }
-        tl = 0; ep += 1; reached = false; n_episodes += 1;
+        if (p.io.obs) st_row<ND>(p.io.obs + off * ND, pos);
+        if (p.io.reward) __stcs(p.io.reward + off, r);
+        if (p.io.terminated) __stcs(p.io.terminated + off, (uint8_t)done);
+        if (p.io.truncated) __stcs(p.io.truncated + off, (uint8_t)trunc);
       }
-      if (p.io.obs) st_row<ND>(p.io.obs + off * ND, pos);
-      if (p.io.reward) __stcs(p.io.reward + off, r);
-      if (p.io.terminated) __stcs(p.io.terminated + off, (uint8_t)done);
-      if (p.io.truncated) __stcs(p.io.truncated + off, (uint8_t)trunc);
     }
 #pragma unroll
     for (int k = 0; k < ND; ++k) p.st.pos[(int64_t)k * N + e] = pos[k];
@@ -306,6 +366,7 @@ static int fill_grid(mdpp_ctx* ctx, const mdpp_grid_state* st,
   p->autoreset = opts->autoreset;
   p->horizon = opts->horizon;
   p->noise_mode = opts->noise_mode;
+  p->normal_mode = opts->normal_mode;
   p->k0 = (uint32_t)opts->seed;
   p->k1 = (uint32_t)(opts->seed >> 32);
   p->step_index = opts->step_index;

@@ -20,11 +20,14 @@ enum PhiloxStream : uint32_t {
   STREAM_STATE_NOISE = 8,  // + pair index: continuous transition noise
   STREAM_IRR_STEP = 32,       // like STREAM_STEP / STREAM_AUTORESET, for the
   STREAM_IRR_AUTORESET = 33,  // irrelevant sub-MDP (irrelevant_features)
-  // grid envs: counter = (env, step): w0 noise decision, w1 substitute action,
-  // (w2, w3) Box-Muller reward normal; auto-reset / reset(): one word per dim
+  // grid envs: GRID_STEP counter = (env, step >> 1): (w0, w1) / (w2, w3) =
+  // noise decision + substitute action of the even / odd step; GRID_NORMAL
+  // counter = (env, step >> 2): 4 reward normals; auto-reset (counter = step)
+  // and reset() (counter word 1 = episode): one word per dimension
   STREAM_GRID_STEP = 40,
   STREAM_GRID_AUTORESET = 41,
-  STREAM_GRID_RESET = 42,     // counter word 1 = episode
+  STREAM_GRID_RESET = 42,
+  STREAM_GRID_NORMAL = 43,
   STREAM_RESET_BOX = 64,   // + attempt*16 + dim/4 (continuous reset sampling)
 };
 

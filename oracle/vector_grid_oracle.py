@@ -3,9 +3,9 @@
 N environments sharing the configuration of one `ScalarRLToyEnv` (kind
 "grid", itself pinned to the reference), with the batched-API semantics of the
 CUDA path: same-step auto-reset, `horizon` truncation, noise from replayed
-arrays or from the Philox streams (csrc/grid.cu: one Philox call per env and
-step -- w0 noise decision, w1 substitute action in closed form, (w2, w3) the
-reward normal).  Per-env arithmetic follows rl_toy_env.py:1727-1778
+arrays or from the Philox streams (csrc/grid.cu: a Philox call per env and 2
+steps for the noise decision + closed-form substitute action, one per 4 steps
+for the reward normals).  Per-env arithmetic follows rl_toy_env.py:1727-1778
 (transition), :1947-1965 + :1968-1990 (reward), :2098-2109 (done),
 :2325-2345 (reset).
 """
@@ -14,6 +14,7 @@ import numpy as np
 from . import philox as px
 
 STREAM_GRID_STEP, STREAM_GRID_AUTORESET, STREAM_GRID_RESET = 40, 41, 42
+STREAM_GRID_NORMAL = 43
 
 
 def substitute_action(w, a):
@@ -35,7 +36,7 @@ def substitute_action(w, a):
 
 class VectorGridOracle:
     def __init__(self, scalar_env, num_envs, autoreset=False, horizon=0, seed=0,
-                 env_id_offset=0):
+                 env_id_offset=0, fast_normal=False):
         e = scalar_env
         assert e.kind == "grid"
         self.N = int(num_envs)
@@ -53,6 +54,7 @@ class VectorGridOracle:
         self.term_reward = e.term_state_reward
         self.autoreset, self.horizon = autoreset, int(horizon)
         self.seed = int(seed)
+        self.fast_normal = fast_normal
         self.gid = (np.arange(self.N, dtype=np.int64) + env_id_offset).astype(np.uint32)
         self.step_index = 0
         self.pos = np.zeros((self.N, self.nd), dtype=np.int64)
@@ -91,8 +93,15 @@ class VectorGridOracle:
         tgt = np.array(self.target)
         for t in range(T):
             step = self.step_index + t
-            w = px.step_words(self.seed, self.gid, step, STREAM_GRID_STEP)
-            z0 = px.normal_pair_f64(w[2], w[3])[0] if self.has_rnoise else None
+            # draws shared by 2 (noise decision, substitute) / 4 (normals) steps
+            wp = px.step_words(self.seed, self.gid, step >> 1, STREAM_GRID_STEP)
+            w = (wp[2], wp[3]) if step & 1 else (wp[0], wp[1])
+            z0 = None
+            if self.has_rnoise:
+                wn = px.step_words(self.seed, self.gid, step >> 2, STREAM_GRID_NORMAL)
+                pair = px.normal_pair_fast if self.fast_normal else px.normal_pair_f64
+                j = step & 3
+                z0 = pair(wn[0], wn[1])[j] if j < 2 else pair(wn[2], wn[3])[j - 2]
             wr = None
             for i in range(N):
                 a = [int(v) for v in actions[t][i]]

@@ -245,6 +245,26 @@ def test_philox_rollout_matches_oracle(name, N, T, autoreset, horizon):
 
 
 @pytest.mark.gpu
+def test_fast_normal_matches_oracle_within_1e5():
+    """normal_precision='fast' (SFU Box-Muller): cells exact, rewards within
+    1e-5 absolute of the oracle's fp32 restatement."""
+    cfg = gu.case_config("grid_sparse_noise")
+    N, T = 1000, 24
+    ora = VectorGridOracle(scalar_oracle(gu.case_config("grid_sparse_noise")), N,
+                           autoreset=True, horizon=10, seed=5, fast_normal=True)
+    env = make_env(N, autoreset=True, horizon=10, philox_seed=5,
+                   normal_precision="fast", **cfg)
+    ora.reset()
+    acts = np.zeros((T, N, 2), dtype=np.int64)
+    acts[..., 1] = np.random.default_rng(1).integers(-1, 2, size=(T, N))
+    want, got = ora.rollout(T, acts), env.rollout(T, actions=acts)
+    for k in ("obs", "final_obs", "terminated", "truncated"):
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+    np.testing.assert_allclose(got["reward"].cpu().numpy(), want["reward"],
+                               rtol=0, atol=1e-5 * 2.0)
+
+
+@pytest.mark.gpu
 def test_graphed_step_and_rollout_equal_repeated_steps():
     import torch
     cfg = gu.case_config("grid_sparse_noise")
