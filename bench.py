@@ -322,7 +322,21 @@ def other_configs(torch, Env, dev, rank, world, barrier, max_over_ranks, peak):
                                 max_over_ranks)
             line(f"C4_image_step_cuda_graph[{tr}]", N, 1, ms, 10034,
                  "step() + render replayed from a CUDA graph")
-            del env, gstep
+            # fused form (SURVEY.md 8d ii): T steps in one rollout launch, all
+            # T x N observations rendered by one launch
+            Tr = 8
+            acts = torch.randint(0, 8, (Tr, N), dtype=torch.int32, device=dev)
+            out = env.rollout(Tr, actions=acts, want_final_obs=False)
+
+            def rollout_and_render():
+                env.rollout(Tr, actions=acts, out=out)
+                return env.render_observation(out["obs"],
+                                              step_index=env._step_index - Tr)
+            ms = _time_launches(torch, rollout_and_render, 10, barrier,
+                                max_over_ranks)
+            line(f"C4_image_rollout[{tr}]", N, Tr, ms, 10014,
+                 "rollout(8) + one render launch for the 8 x N observations")
+            del env, gstep, acts, out
         # C5: 1000-cell heterogeneous grid, 1M envs per GPU
         cfgs = [dict(base, delay=d, sequence_length=L, transition_noise=pn,
                      reward_noise=rn, make_denser=md, reward_every_n_steps=True)

@@ -174,13 +174,21 @@ typedef struct mdpp_discrete_io {
 #define MDPP_NORMAL_F64 0   /* Box-Muller in fp64 (log, sqrt, sincospi)      */
 #define MDPP_NORMAL_FAST 1  /* Box-Muller on the SFU in fp32 (~1e-6 rel.)    */
 
+/* mdpp_render_discrete only: the launch may START before the previous kernel
+ * of the stream has finished (programmatic dependent launch): its prologue --
+ * the zero fill of `out` -- depends on nothing; it waits for that kernel
+ * before it reads `states`.  The rollout kernels signal their dependents at
+ * once, so a step -> render pair overlaps.  `out` must not be read or written
+ * by the previous kernel.                                                    */
+#define MDPP_LAUNCH_OVERLAP_PREVIOUS 1
+
 typedef struct mdpp_step_opts {
   int32_t n_steps;        /* T >= 1                                          */
   int32_t noise_mode;     /* MDPP_NOISE_*                                    */
   int32_t autoreset;      /* 1: reset in the same step on terminated/truncated */
   int32_t horizon;        /* > 0: truncated = (t_episode >= horizon)         */
   int32_t normal_mode;    /* MDPP_NORMAL_* (Philox mode only)                */
-  int32_t reserved0;
+  int32_t flags;          /* MDPP_LAUNCH_*                                   */
   uint64_t seed;          /* Philox key                                      */
   uint64_t step_index;    /* global index of the first step of this call     */
   int64_t env_id_offset;  /* global id of local env 0 (multi-GPU sharding)   */

@@ -14,6 +14,7 @@ ABI_VERSION = 2  # MDPP_ABI_VERSION of include/mdpp_b200.h
 MDPP_NOISE_OFF, MDPP_NOISE_REPLAY, MDPP_NOISE_PHILOX = 0, 1, 2
 MDPP_N_STATS = 8
 MDPP_NORMAL_F64, MDPP_NORMAL_FAST = 0, 1
+MDPP_LAUNCH_OVERLAP_PREVIOUS = 1
 STAT_NAMES = ("episodes", "transitions", "reward", "noisy_transitions",
               "abs_reward_noise", "abs_transition_noise", "reserved",
               "terminated")
@@ -77,7 +78,7 @@ class StepOpts(C.Structure):
     _fields_ = [
         ("n_steps", C.c_int32), ("noise_mode", C.c_int32),
         ("autoreset", C.c_int32), ("horizon", C.c_int32),
-        ("normal_mode", C.c_int32), ("reserved0", C.c_int32),
+        ("normal_mode", C.c_int32), ("flags", C.c_int32),
         ("seed", C.c_uint64), ("step_index", C.c_uint64),
         ("env_id_offset", C.c_int64), ("step_index_dev", C.c_void_p),
     ]

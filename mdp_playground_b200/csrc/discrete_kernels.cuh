@@ -725,6 +725,11 @@ __device__ __forceinline__ double warp_sum(double x) {
 
 template <typename C>
 __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
+  // A kernel launched behind this one with programmatic stream serialisation
+  // (the renderer, MDPP_LAUNCH_OVERLAP_PREVIOUS) may start its independent
+  // prologue now; it still waits for this grid to finish before it reads the
+  // states.  No effect otherwise.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   constexpr bool SMEM = C::SMEM;
   constexpr bool RING_SMEM = C::RING_SMEM;
   extern __shared__ __align__(16) uint8_t smem_dyn[];

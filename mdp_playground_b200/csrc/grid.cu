@@ -49,12 +49,10 @@ __device__ __forceinline__ Row<ND> ld_row(const int64_t* p) {
   }
   return r;
 }
-// An action row, validated and packed when it is loaded: 2 bits per entry
-// (value + 1), bit 31 = not a GridActionSpace member (-> no-op).  Keeps the
-// 4-step prefetch ring at one register per row.
+// An action row, validated and packed: 2 bits per entry (value + 1), bit 31 =
+// not a GridActionSpace member (-> no-op).
 template <int ND>
-__device__ __forceinline__ uint32_t ld_action(const int64_t* p) {
-  const Row<ND> r = ld_row<ND>(p);
+__device__ __forceinline__ uint32_t pack_action(const Row<ND>& r) {
   uint32_t code = 0;
   bool valid = true;
   int moves = 0;
@@ -113,7 +111,7 @@ __device__ __forceinline__ double block_sum(double x, double* smem) {
 }
 
 template <int ND, int NOISE>
-__global__ void __launch_bounds__(kGBlock, 6)
+__global__ void __launch_bounds__(kGBlock, ND == 2 ? 5 : 4)
 grid_rollout_kernel(const __grid_constant__ GridParams p) {
   __shared__ double red[kGBlock / 32];
   const mdpp_grid_config& c = p.cfg;
@@ -142,19 +140,22 @@ grid_rollout_kernel(const __grid_constant__ GridParams p) {
     // action rows run 4 steps ahead of their use (a DRAM read under the
     // write-heavy stream takes longer than one step's arithmetic)
     constexpr int kAhead = 4;
-    uint32_t ring[kAhead];
+    // (the ring holds the RAW rows: touching a row before its turn would
+    // stall on the load and void the prefetch)
+    Row<ND> ring[kAhead];
 #pragma unroll
     for (int j = 0; j < kAhead; ++j) {
-      ring[j] = 0x80000000u;
-      if (j < p.T) ring[j] = ld_action<ND>(p.io.actions + ((int64_t)j * N + e) * ND);
+#pragma unroll
+      for (int k = 0; k < ND; ++k) ring[j].v[k] = 2;  // invalid: no-op
+      if (j < p.T) ring[j] = ld_row<ND>(p.io.actions + ((int64_t)j * N + e) * ND);
     }
     for (int t0 = 0; t0 < p.T; t0 += kAhead) {
       uint32_t cur[kAhead];
 #pragma unroll
       for (int j = 0; j < kAhead; ++j) {
-        cur[j] = ring[j];
+        cur[j] = pack_action<ND>(ring[j]);
         if (t0 + kAhead + j < p.T)
-          ring[j] = ld_action<ND>(p.io.actions + ((int64_t)(t0 + kAhead + j) * N + e) * ND);
+          ring[j] = ld_row<ND>(p.io.actions + ((int64_t)(t0 + kAhead + j) * N + e) * ND);
       }
 #pragma unroll
       for (int j = 0; j < kAhead; ++j) {

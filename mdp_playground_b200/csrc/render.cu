@@ -82,6 +82,10 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
     for (; i < n16; i += 32) __stcs(out4 + i, z);
   }
   for (int w = lane; w < 2 * kRotCols; w += 32) (&fmask[0][0])[w] = 0ull;
+  // launched with MDPP_LAUNCH_OVERLAP_PREVIOUS: everything above overlapped the
+  // previous kernel of the stream (the step that produces `states`); wait for
+  // it now.  Returns at once in an ordinary launch.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // ---- transform parameters (uniform over the warp) ------------------------
   int state = (int)p.states[m];
@@ -380,7 +384,16 @@ extern "C" int mdpp_render_discrete(mdpp_ctx* ctx,
   p.step_index_dev = opts->step_index_dev;
   p.env_id_offset = opts->env_id_offset;
   const unsigned grid = (unsigned)((n_images + kImagesPerCta - 1) / kImagesPerCta);
-  render_discrete_kernel<<<grid, kRBlock, 0, (cudaStream_t)cuda_stream>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kRBlock);
+  cfg.stream = (cudaStream_t)cuda_stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (opts->flags & MDPP_LAUNCH_OVERLAP_PREVIOUS) ? 1 : 0;
+  MDPP_CUDA(ctx, cudaLaunchKernelEx(&cfg, render_discrete_kernel, p));
   MDPP_CUDA(ctx, cudaGetLastError());
   return MDPP_OK;
 }

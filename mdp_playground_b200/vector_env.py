@@ -309,8 +309,9 @@ class VectorRLToyEnv:
         o.env_id_offset = self.env_id_offset
         if getattr(self, "_use_dev_counter", False):
             # CUDA-graph mode: the step index lives in a device scalar that
-            # the graph itself advances (see make_graphed_step)
-            o.step_index = 0
+            # the graph itself advances BEFORE the kernels run (see
+            # make_graphed_step): index = counter - 1 (mod 2^64)
+            o.step_index = 2**64 - 1
             o.step_index_dev = self._step_ctr.data_ptr()
         return o
 
@@ -552,6 +553,8 @@ class VectorRLToyEnv:
         opts = self._opts(1)
         if not getattr(self, "_use_dev_counter", False):
             opts.step_index = step_index
+        else:  # observation after the step: index + 1 = the device counter
+            opts.step_index = 0
         if sp.kind == "discrete":
             st = state.to(torch.int64).contiguous()
             M = st.numel()  # images = sub-images when irrelevant_features
@@ -570,6 +573,9 @@ class VectorRLToyEnv:
             out = torch.empty(lead + self.obs_shape, dtype=torch.uint8, device=dev)
             self.last_image_params = torch.empty((M, 5), dtype=torch.int32,
                                                  device=dev)
+            if getattr(self, "_overlap_render", False) and st.data_ptr() == state.data_ptr():
+                # (no cast / copy kernel sits between the step and this launch)
+                opts.flags = _lib.MDPP_LAUNCH_OVERLAP_PREVIOUS
             self._check(self._lib.mdpp_render_discrete(
                 self._ctx, C.byref(self._img_cfg), _ptr(st), _ptr(image_params),
                 _ptr(self.last_image_params), _ptr(out), M, N,
@@ -721,10 +727,18 @@ class VectorRLToyEnv:
         self._step_ctr = torch.zeros(1, dtype=torch.int64, device=dev)
 
         def body():
+            # counter first, so that the step kernel and the renderer are
+            # neighbours in the stream: the renderer is then launched as a
+            # programmatic dependent of the step and zero-fills the images
+            # while the step runs (MDPP_LAUNCH_OVERLAP_PREVIOUS)
+            self._step_ctr += 1
             self.rollout(1, actions=static_a, out=out)
             self._step_index -= 1  # the device counter is the clock here
-            self._step_ctr += 1
-            return self._observe(out["obs"][0])
+            self._overlap_render = True
+            try:
+                return self._observe(out["obs"][0])
+            finally:
+                self._overlap_render = False
 
         snapshot = [t.clone() for t in self._state_tensors()]
         host_index = self._step_index
