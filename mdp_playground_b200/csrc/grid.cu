@@ -58,9 +58,10 @@ __device__ __forceinline__ uint32_t pack_action(const Row<ND>& r) {
   int moves = 0;
 #pragma unroll
   for (int k = 0; k < ND; ++k) {
-    valid &= r.v[k] >= -1 && r.v[k] <= 1;
-    moves += r.v[k] != 0;
-    code |= ((uint32_t)(r.v[k] + 1) & 3u) << (2 * k);
+    const uint64_t u = (uint64_t)r.v[k] + 1ull;  // {-1, 0, 1} -> {0, 1, 2}
+    valid &= u <= 2ull;
+    moves += u != 1ull;
+    code |= ((uint32_t)u & 3u) << (2 * k);
   }
   return (valid && moves <= 1) ? code : 0x80000000u;
 }
@@ -92,7 +93,7 @@ __device__ __forceinline__ void substitute_action(uint32_t w, int32_t* a) {
   }
 #pragma unroll
   for (int k = 0; k < ND; ++k) a[k] = 0;
-  const int d = pick / 3, v = pick - d * 3 - 1;
+  const int d = (pick * 11) >> 5, v = pick - d * 3 - 1;  // pick / 3, pick < 12
 #pragma unroll
   for (int k = 0; k < ND; ++k)
     if (k == d) a[k] = v;
@@ -110,7 +111,140 @@ __device__ __forceinline__ double block_sum(double x, double* smem) {
   return s;
 }
 
-template <int ND, int NOISE>
+// Registers of one environment + the launch's running statistics.
+template <int ND>
+struct GridEnv {
+  int32_t pos[ND];
+  int32_t tl, phase;  // phase = tl % reward_every_n_steps, kept incrementally
+  uint32_t ep;
+  bool reached;
+  double sum_reward, sum_abs_rnoise;
+  uint32_t n_noisy, n_episodes, n_term;
+  // Philox draws shared by consecutive steps (see grid_step)
+  uint64_t cached_pair, cached_quad;
+  U4 w_pair;
+  double zq[4];
+};
+
+// One environment step.  FAST: the standard rollout signature (obs, reward,
+// terminated, truncated written, no final_obs), so no per-step NULL tests.
+template <int ND, int NOISE, bool FAST>
+__device__ __forceinline__ void grid_step(const GridParams& p, GridEnv<ND>& g,
+                                          uint32_t code, int64_t off, uint64_t step,
+                                          uint32_t gid, uint32_t pn_T, double term_add) {
+  const mdpp_grid_config& c = p.cfg;
+  // GridActionSpace.contains: entries in {-1, 0, 1}, at most one move
+  const bool valid = (code >> 31) == 0;
+  int32_t a[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k)
+    a[k] = valid ? (int32_t)((code >> (2 * k)) & 3u) - 1 : 0;
+  // Philox draws are shared by consecutive steps (the step index is uniform
+  // over the launch, so these refills are uniform branches):
+  // STREAM_GRID_STEP, counter = step >> 1: words (0, 1) / (2, 3) = noise
+  // decision and substitute action of the even / odd step;
+  // STREAM_GRID_NORMAL, counter = step >> 2: two Box-Muller pairs = the reward
+  // normals of 4 steps
+  if (NOISE != MDPP_NOISE_OFF && c.has_transition_noise) {
+    if (NOISE == MDPP_NOISE_REPLAY) {
+      if (valid && __ldcs(p.io.replay_noise_u + off) < c.transition_noise) {
+        const Row<ND> r = ld_row<ND>(p.io.replay_noise_action + off * ND);
+#pragma unroll
+        for (int k = 0; k < ND; ++k) a[k] = (int32_t)r.v[k];
+        g.n_noisy += 1;
+      }
+    } else {
+      if ((step >> 1) != g.cached_pair) {
+        g.cached_pair = step >> 1;
+        g.w_pair = philox4x32_10(gid, (uint32_t)g.cached_pair,
+                                 (uint32_t)(g.cached_pair >> 32), STREAM_GRID_STEP,
+                                 p.k0, p.k1);
+      }
+      const uint32_t w_u = (step & 1) ? g.w_pair.z : g.w_pair.x;
+      const uint32_t w_sub = (step & 1) ? g.w_pair.w : g.w_pair.y;
+      if (valid && w_u < pn_T) {
+        substitute_action<ND>(w_sub, a);
+        g.n_noisy += 1;
+      }
+    }
+  }
+  // dense reward: Manhattan distance moved towards the target
+  const int d_old = abs(g.pos[0] - c.target[0]) + abs(g.pos[1] - c.target[1]);
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      int v = g.pos[k] + a[k];
+      v = max(v, 0);                            // bounce back from the walls;
+      g.pos[k] = min(v, c.shape[k] - 1);        // (also pulls a one-past reset
+    }                                           //  cell in when it moves)
+  }
+  const bool at_target = g.pos[0] == c.target[0] && g.pos[1] == c.target[1];
+  g.reached |= at_target;
+  g.tl += 1;
+  g.phase = (g.phase + 1 == c.reward_every_n_steps) ? 0 : g.phase + 1;
+  double r = 0.0;
+  if (c.dense) {
+    const int d_new = abs(g.pos[0] - c.target[0]) + abs(g.pos[1] - c.target[1]);
+    r = (double)(d_old - d_new);
+  } else if (at_target) {
+    r = 1.0;
+  }
+  if (g.phase != 0) r = 0.0;
+  g.sum_reward += r;
+  if (NOISE != MDPP_NOISE_OFF && c.has_reward_noise) {
+    double z;
+    if (NOISE == MDPP_NOISE_REPLAY) {
+      z = __ldcs(p.io.replay_reward_noise + off);
+    } else {
+      if ((step >> 2) != g.cached_quad) {
+        g.cached_quad = step >> 2;
+        const U4 wn = philox4x32_10(gid, (uint32_t)g.cached_quad,
+                                    (uint32_t)(g.cached_quad >> 32),
+                                    STREAM_GRID_NORMAL, p.k0, p.k1);
+        if (p.normal_mode == MDPP_NORMAL_FAST) {
+          normal_pair_fast(wn.x, wn.y, &g.zq[0], &g.zq[1]);
+          normal_pair_fast(wn.z, wn.w, &g.zq[2], &g.zq[3]);
+        } else {
+          normal_pair_f64(wn.x, wn.y, &g.zq[0], &g.zq[1]);
+          normal_pair_f64(wn.z, wn.w, &g.zq[2], &g.zq[3]);
+        }
+      }
+      const int j4 = (int)(step & 3);
+      const double z0 = j4 == 0 ? g.zq[0] : j4 == 1 ? g.zq[1] : j4 == 2 ? g.zq[2] : g.zq[3];
+      z = __dmul_rn(c.reward_noise_std, z0);
+    }
+    g.sum_abs_rnoise += fabs(z);
+    r = __dadd_rn(r, z);
+  }
+  r = __dmul_rn(r, c.reward_scale);
+  r = __dadd_rn(r, c.reward_shift);
+  const bool done = g.reached;
+  if (done) r = __dadd_rn(r, term_add);
+  const bool trunc = p.horizon > 0 && g.tl >= p.horizon;
+  g.n_term += done;
+  if (!FAST && p.io.final_obs) st_row<ND>(p.io.final_obs + off * ND, g.pos);
+  if (p.autoreset && (done || trunc)) {
+    if (NOISE == MDPP_NOISE_REPLAY) {
+      const Row<ND> r0 = ld_row<ND>(p.io.replay_reset_state + off * ND);
+#pragma unroll
+      for (int k = 0; k < ND; ++k) g.pos[k] = (int32_t)r0.v[k];
+    } else {
+      U4 wr = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
+                            STREAM_GRID_AUTORESET, p.k0, p.k1);
+      const uint32_t ww[4] = {wr.x, wr.y, wr.z, wr.w};
+#pragma unroll
+      for (int k = 0; k < ND; ++k)
+        g.pos[k] = (int32_t)__umulhi(ww[k], (uint32_t)c.shape[k] + 1u);
+    }
+    g.tl = 0; g.phase = 0; g.ep += 1; g.reached = false; g.n_episodes += 1;
+  }
+  if (FAST || p.io.obs) st_row<ND>(p.io.obs + off * ND, g.pos);
+  if (FAST || p.io.reward) __stcs(p.io.reward + off, r);
+  if (FAST || p.io.terminated) __stcs(p.io.terminated + off, (uint8_t)done);
+  if (FAST || p.io.truncated) __stcs(p.io.truncated + off, (uint8_t)trunc);
+}
+
+template <int ND, int NOISE, bool FAST>
 __global__ void __launch_bounds__(kGBlock, ND == 2 ? 5 : 4)
 grid_rollout_kernel(const __grid_constant__ GridParams p) {
   __shared__ double red[kGBlock / 32];
@@ -122,170 +256,66 @@ grid_rollout_kernel(const __grid_constant__ GridParams p) {
   const uint32_t gid = (uint32_t)(p.env_id_offset + e);
   const uint64_t step_base =
       p.step_index + (p.step_index_dev ? *p.step_index_dev : 0ull);
-  int32_t pos[ND];
+  GridEnv<ND> g;
 #pragma unroll
-  for (int k = 0; k < ND; ++k) pos[k] = p.st.pos[(int64_t)k * N + e];
-  int32_t tl = p.st.t_episode[e];
-  uint32_t ep = p.st.episode[e];
-  bool reached = p.st.reached[e] != 0;
+  for (int k = 0; k < ND; ++k) g.pos[k] = p.st.pos[(int64_t)k * N + e];
+  g.tl = p.st.t_episode[e];
+  g.phase = g.tl % c.reward_every_n_steps;
+  g.ep = p.st.episode[e];
+  g.reached = p.st.reached[e] != 0;
+  g.sum_reward = g.sum_abs_rnoise = 0.0;
+  g.n_noisy = g.n_episodes = g.n_term = 0;
+  g.cached_pair = g.cached_quad = ~0ull;
+  g.w_pair = U4{0u, 0u, 0u, 0u};
+  g.zq[0] = g.zq[1] = g.zq[2] = g.zq[3] = 0.0;
   const uint32_t pn_T = (uint32_t)fmin(
       floor(c.transition_noise * 4294967296.0 + 0.5), 4294967295.0);
   const double term_add = c.term_state_reward * c.reward_scale;
-  double sum_reward = 0.0, sum_abs_rnoise = 0.0;
-  uint32_t n_noisy = 0, n_episodes = 0, n_term = 0, n_steps = 0;
-  uint64_t cached_pair = ~0ull, cached_quad = ~0ull;
-  U4 w_pair = {0u, 0u, 0u, 0u};
-  double zq[4] = {0.0, 0.0, 0.0, 0.0};
   if (active) {
-    // action rows run 4 steps ahead of their use (a DRAM read under the
-    // write-heavy stream takes longer than one step's arithmetic)
+    // Action rows run 4 steps ahead of their use (a DRAM read under the
+    // write-heavy stream takes longer than one step's arithmetic).  The ring
+    // holds the RAW rows: touching a row before its turn would stall on the
+    // load and void the prefetch.
     constexpr int kAhead = 4;
-    // (the ring holds the RAW rows: touching a row before its turn would
-    // stall on the load and void the prefetch)
+    const int64_t stride = N * ND;  // one time step of rows
+    const int64_t* arow = p.io.actions + e * ND;
     Row<ND> ring[kAhead];
 #pragma unroll
     for (int j = 0; j < kAhead; ++j) {
 #pragma unroll
       for (int k = 0; k < ND; ++k) ring[j].v[k] = 2;  // invalid: no-op
-      if (j < p.T) ring[j] = ld_row<ND>(p.io.actions + ((int64_t)j * N + e) * ND);
+      if (j < p.T) ring[j] = ld_row<ND>(arow + j * stride);
     }
-    for (int t0 = 0; t0 < p.T; t0 += kAhead) {
+    int t0 = 0;
+    for (; t0 + kAhead <= p.T; t0 += kAhead) {  // whole groups, no step guards
       uint32_t cur[kAhead];
+      const int64_t* nxt = arow + (int64_t)(t0 + kAhead) * stride;
 #pragma unroll
       for (int j = 0; j < kAhead; ++j) {
         cur[j] = pack_action<ND>(ring[j]);
-        if (t0 + kAhead + j < p.T)
-          ring[j] = ld_row<ND>(p.io.actions + ((int64_t)(t0 + kAhead + j) * N + e) * ND);
+        if (t0 + kAhead + j < p.T) ring[j] = ld_row<ND>(nxt + j * stride);
       }
 #pragma unroll
-      for (int j = 0; j < kAhead; ++j) {
-        const int t = t0 + j;
-        if (t >= p.T) break;
-        const int64_t off = (int64_t)t * N + e;
-        const uint64_t step = step_base + (uint64_t)t;
-        // GridActionSpace.contains: entries in {-1, 0, 1}, at most one move
-        const bool valid = (cur[j] >> 31) == 0;
-        int32_t a[ND];
-#pragma unroll
-        for (int k = 0; k < ND; ++k)
-          a[k] = valid ? (int32_t)((cur[j] >> (2 * k)) & 3u) - 1 : 0;
-        // Philox draws are shared by consecutive steps (the step index is
-        // uniform over the launch, so these refills are uniform branches):
-        // STREAM_GRID_STEP, counter = step >> 1: words (0, 1) / (2, 3) = noise
-        // decision and substitute action of the even / odd step;
-        // STREAM_GRID_NORMAL, counter = step >> 2: two Box-Muller pairs = the
-        // reward normals of 4 steps
-        uint32_t w_u = 0, w_sub = 0;
-        if (NOISE == MDPP_NOISE_PHILOX && c.has_transition_noise) {
-          if ((step >> 1) != cached_pair) {
-            cached_pair = step >> 1;
-            w_pair = philox4x32_10(gid, (uint32_t)cached_pair,
-                                   (uint32_t)(cached_pair >> 32), STREAM_GRID_STEP,
-                                   p.k0, p.k1);
-          }
-          w_u = (step & 1) ? w_pair.z : w_pair.x;
-          w_sub = (step & 1) ? w_pair.w : w_pair.y;
-        }
-        if (valid && c.has_transition_noise && NOISE != MDPP_NOISE_OFF) {
-          if (NOISE == MDPP_NOISE_REPLAY) {
-            if (__ldcs(p.io.replay_noise_u + off) < c.transition_noise) {
-              const Row<ND> r = ld_row<ND>(p.io.replay_noise_action + off * ND);
-#pragma unroll
-              for (int k = 0; k < ND; ++k) a[k] = (int32_t)r.v[k];
-              n_noisy += 1;
-            }
-          } else if (w_u < pn_T) {
-            substitute_action<ND>(w_sub, a);
-            n_noisy += 1;
-          }
-        }
-        // dense reward: Manhattan distance moved towards the target
-        const int d_old = abs(pos[0] - c.target[0]) + abs(pos[1] - c.target[1]);
-        if (valid) {
-#pragma unroll
-          for (int k = 0; k < ND; ++k) {
-            int v = pos[k] + a[k];
-            v = max(v, 0);                       // bounce back from the walls;
-            if (v >= c.shape[k]) v = c.shape[k] - 1;  // (also pulls a one-past
-            pos[k] = v;                          //  reset cell in when it moves)
-          }
-        }
-        const bool at_target = pos[0] == c.target[0] && pos[1] == c.target[1];
-        reached |= at_target;
-        tl += 1;
-        double r = 0.0;
-        if (c.dense) {
-          const int d_new = abs(pos[0] - c.target[0]) + abs(pos[1] - c.target[1]);
-          r = (double)(d_old - d_new);
-        } else if (at_target) {
-          r = 1.0;
-        }
-        if (tl % c.reward_every_n_steps != 0) r = 0.0;
-        sum_reward += r;
-        if (c.has_reward_noise && NOISE != MDPP_NOISE_OFF) {
-          double z;
-          if (NOISE == MDPP_NOISE_REPLAY) {
-            z = __ldcs(p.io.replay_reward_noise + off);
-          } else {
-            if ((step >> 2) != cached_quad) {
-              cached_quad = step >> 2;
-              const U4 wn = philox4x32_10(gid, (uint32_t)cached_quad,
-                                          (uint32_t)(cached_quad >> 32),
-                                          STREAM_GRID_NORMAL, p.k0, p.k1);
-              if (p.normal_mode == MDPP_NORMAL_FAST) {
-                normal_pair_fast(wn.x, wn.y, &zq[0], &zq[1]);
-                normal_pair_fast(wn.z, wn.w, &zq[2], &zq[3]);
-              } else {
-                normal_pair_f64(wn.x, wn.y, &zq[0], &zq[1]);
-                normal_pair_f64(wn.z, wn.w, &zq[2], &zq[3]);
-              }
-            }
-            const int j4 = (int)(step & 3);
-            const double z0 = j4 == 0 ? zq[0] : j4 == 1 ? zq[1] : j4 == 2 ? zq[2] : zq[3];
-            z = __dmul_rn(c.reward_noise_std, z0);
-          }
-          sum_abs_rnoise += fabs(z);
-          r = __dadd_rn(r, z);
-        }
-        r = __dmul_rn(r, c.reward_scale);
-        r = __dadd_rn(r, c.reward_shift);
-        const bool done = reached;
-        if (done) r = __dadd_rn(r, term_add);
-        const bool trunc = p.horizon > 0 && tl >= p.horizon;
-        n_term += done;
-        n_steps += 1;
-        if (p.io.final_obs) st_row<ND>(p.io.final_obs + off * ND, pos);
-        if (p.autoreset && (done || trunc)) {
-          if (NOISE == MDPP_NOISE_REPLAY) {
-            const Row<ND> r0 = ld_row<ND>(p.io.replay_reset_state + off * ND);
-#pragma unroll
-            for (int k = 0; k < ND; ++k) pos[k] = (int32_t)r0.v[k];
-          } else {
-            U4 wr = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
-                                  STREAM_GRID_AUTORESET, p.k0, p.k1);
-            const uint32_t ww[4] = {wr.x, wr.y, wr.z, wr.w};
-#pragma unroll
-            for (int k = 0; k < ND; ++k)
-              pos[k] = (int32_t)__umulhi(ww[k], (uint32_t)c.shape[k] + 1u);
-          }
-          tl = 0; ep += 1; reached = false; n_episodes += 1;
-        }
-        if (p.io.obs) st_row<ND>(p.io.obs + off * ND, pos);
-        if (p.io.reward) __stcs(p.io.reward + off, r);
-        if (p.io.terminated) __stcs(p.io.terminated + off, (uint8_t)done);
-        if (p.io.truncated) __stcs(p.io.truncated + off, (uint8_t)trunc);
-      }
+      for (int j = 0; j < kAhead; ++j)
+        grid_step<ND, NOISE, FAST>(p, g, cur[j], (int64_t)(t0 + j) * N + e,
+                                   step_base + (uint64_t)(t0 + j), gid, pn_T, term_add);
     }
 #pragma unroll
-    for (int k = 0; k < ND; ++k) p.st.pos[(int64_t)k * N + e] = pos[k];
-    p.st.t_episode[e] = tl;
-    p.st.episode[e] = ep;
-    p.st.reached[e] = (uint8_t)reached;
+    for (int j = 0; j < kAhead - 1; ++j)  // the last T % 4 steps
+      if (t0 + j < p.T)
+        grid_step<ND, NOISE, FAST>(p, g, pack_action<ND>(ring[j]),
+                                   (int64_t)(t0 + j) * N + e,
+                                   step_base + (uint64_t)(t0 + j), gid, pn_T, term_add);
+#pragma unroll
+    for (int k = 0; k < ND; ++k) p.st.pos[(int64_t)k * N + e] = g.pos[k];
+    p.st.t_episode[e] = g.tl;
+    p.st.episode[e] = g.ep;
+    p.st.reached[e] = (uint8_t)g.reached;
   }
   if (p.st.stats) {
     const double vals[MDPP_N_STATS] = {
-        (double)n_episodes, (double)n_steps, sum_reward, (double)n_noisy,
-        sum_abs_rnoise, 0.0, 0.0, (double)n_term};
+        (double)g.n_episodes, active ? (double)p.T : 0.0, g.sum_reward,
+        (double)g.n_noisy, g.sum_abs_rnoise, 0.0, 0.0, (double)g.n_term};
 #pragma unroll
     for (int k = 0; k < MDPP_N_STATS; ++k) {
       if (k == MDPP_STAT_ABS_TRANSITION_NOISE || k == MDPP_STAT_RESERVED) continue;
@@ -376,18 +406,18 @@ static int fill_grid(mdpp_ctx* ctx, const mdpp_grid_state* st,
   return MDPP_OK;
 }
 
-template <int ND>
+template <int ND, bool FAST>
 static int launch_grid(mdpp_ctx* ctx, const GridParams& p, cudaStream_t s) {
   const unsigned grid = (unsigned)((p.st.n_envs + kGBlock - 1) / kGBlock);
   switch (p.noise_mode) {
     case MDPP_NOISE_OFF:
-      grid_rollout_kernel<ND, MDPP_NOISE_OFF><<<grid, kGBlock, 0, s>>>(p);
+      grid_rollout_kernel<ND, MDPP_NOISE_OFF, FAST><<<grid, kGBlock, 0, s>>>(p);
       break;
     case MDPP_NOISE_REPLAY:
-      grid_rollout_kernel<ND, MDPP_NOISE_REPLAY><<<grid, kGBlock, 0, s>>>(p);
+      grid_rollout_kernel<ND, MDPP_NOISE_REPLAY, FAST><<<grid, kGBlock, 0, s>>>(p);
       break;
     default:
-      grid_rollout_kernel<ND, MDPP_NOISE_PHILOX><<<grid, kGBlock, 0, s>>>(p);
+      grid_rollout_kernel<ND, MDPP_NOISE_PHILOX, FAST><<<grid, kGBlock, 0, s>>>(p);
   }
   MDPP_CUDA(ctx, cudaGetLastError());
   return MDPP_OK;
@@ -416,8 +446,11 @@ extern "C" int mdpp_grid_rollout(mdpp_ctx* ctx, const mdpp_grid_state* st,
   p.io = *io;
   MDPP_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = (cudaStream_t)cuda_stream;
-  return ctx->g_cfg.n_dims == 4 ? launch_grid<4>(ctx, p, s)
-                                : launch_grid<2>(ctx, p, s);
+  const bool fast = io->obs && io->reward && io->terminated && io->truncated &&
+                    !io->final_obs;
+  if (ctx->g_cfg.n_dims == 4)
+    return fast ? launch_grid<4, true>(ctx, p, s) : launch_grid<4, false>(ctx, p, s);
+  return fast ? launch_grid<2, true>(ctx, p, s) : launch_grid<2, false>(ctx, p, s);
 }
 
 extern "C" int mdpp_grid_reset(mdpp_ctx* ctx, const mdpp_grid_state* st,
