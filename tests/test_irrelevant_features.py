@@ -222,3 +222,31 @@ def test_graphed_step_and_fast_signature_with_irrelevant_features():
         assert torch.equal(x[k], y[k]), k
     assert torch.equal(y["final_obs"][~(y["terminated"] | y["truncated"])],
                        y["obs"][~(y["terminated"] | y["truncated"])])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("jit", [True, False])
+def test_multi_group_launch_with_irrelevant_features(jit):
+    """Heterogeneous groups that all carry an irrelevant sub-MDP (different
+    sizes / noise / delay per group): one launch == the per-group envs; mixing
+    groups with and without one is rejected."""
+    import torch
+    names = ["irr_8x8_noise", "irr_6x10_diam2", "irr_8x5_det"]
+    sizes = [300, 129, 64]
+    cfgs = [gu.case_config(n) for n in names]
+    het = make_env(sum(sizes), autoreset=True, horizon=9, philox_seed=5,
+                   config_groups=cfgs, group_sizes=sizes)
+    het.set_jit(jit)
+    out = het.rollout(40, want_final_obs=True)
+    assert het.jit_last_used == jit, het.jit_log
+    begin = 0
+    for name, n, sl in zip(names, sizes, het.group_slices):
+        one = make_env(n, autoreset=True, horizon=9, philox_seed=5,
+                       env_id_offset=begin, **gu.case_config(name))
+        ref = one.rollout(40, want_final_obs=True)
+        for k in ref:
+            assert torch.equal(out[k][:, sl], ref[k]), (k, name)
+        begin += n
+    with pytest.raises(AssertionError):
+        make_env(128, config_groups=[gu.case_config("irr_8x8_noise"),
+                                     gu.case_config("c2_every1")])
