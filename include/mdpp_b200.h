@@ -147,8 +147,14 @@ typedef struct mdpp_discrete_state {
   int32_t ring_depth;
   int32_t history_depth;
   int32_t* history;     /* [history_depth*N] or NULL                        */
-  double* stats;        /* [n_groups*MDPP_N_STATS], accumulated atomically  */
+  double* stats;        /* [stats_slots][n_groups][MDPP_N_STATS], accumulated
+                           atomically; the counters are the SUM over slots   */
   int32_t* cur_state_irr; /* [N] irrelevant sub-state (irrelevant_features)  */
+  int32_t stats_slots;  /* >= 1 (0 reads as 1): CTAs spread their atomics over
+                           this many copies of the counter rows -- thousands
+                           of same-address fp64 atomics were 15 of the 19 us
+                           of a T = 1 launch                                  */
+  int32_t reserved1;
 } mdpp_discrete_state;
 
 /* Inputs/outputs of T consecutive steps, time-major [T*N], DEVICE pointers.
@@ -265,7 +271,9 @@ typedef struct mdpp_continuous_state {
   uint32_t* episode;   /* [N]                                                */
   uint8_t* reached;    /* [N] sticky reached_terminal (:1725)                */
   void* ring;          /* real [delay][N] reward FIFO, or NULL               */
-  double* stats;       /* [MDPP_N_STATS]                                     */
+  double* stats;       /* [stats_slots][MDPP_N_STATS], summed over slots      */
+  int32_t stats_slots; /* >= 1 (0 reads as 1), see mdpp_discrete_state        */
+  int32_t reserved1;
 } mdpp_continuous_state;
 
 /* T steps, time-major; actions / obs are env-major rows of `dim` reals
@@ -332,7 +340,9 @@ typedef struct mdpp_grid_state {   /* DEVICE pointers, struct-of-arrays      */
   int32_t* t_episode;   /* [N]                                                */
   uint32_t* episode;    /* [N]                                                */
   uint8_t* reached;     /* [N] sticky reached_terminal                        */
-  double* stats;        /* [MDPP_N_STATS]                                     */
+  double* stats;        /* [stats_slots][MDPP_N_STATS], summed over slots     */
+  int32_t stats_slots;  /* >= 1 (0 reads as 1), see mdpp_discrete_state       */
+  int32_t reserved1;
 } mdpp_grid_state;
 
 typedef struct mdpp_grid_io {      /* T steps, time-major, rows of n_dims    */

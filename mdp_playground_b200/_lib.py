@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("MDPP_LIB") or os.path.join(HERE, "libmdpp_b200.so")
 ABI_VERSION = 2  # MDPP_ABI_VERSION of include/mdpp_b200.h
 MDPP_NOISE_OFF, MDPP_NOISE_REPLAY, MDPP_NOISE_PHILOX = 0, 1, 2
 MDPP_N_STATS = 8
+STATS_SLOTS = 64  # copies of the counter rows the kernels spread their atomics over
 MDPP_NORMAL_F64, MDPP_NORMAL_FAST = 0, 1
 MDPP_LAUNCH_OVERLAP_PREVIOUS = 1
 STAT_NAMES = ("episodes", "transitions", "reward", "noisy_transitions",
@@ -62,6 +63,7 @@ class DiscreteState(C.Structure):
         ("ring_depth", C.c_int32), ("history_depth", C.c_int32),
         ("history", C.c_void_p), ("stats", C.c_void_p),
         ("cur_state_irr", C.c_void_p),
+        ("stats_slots", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -110,6 +112,7 @@ class ContinuousState(C.Structure):
         ("n_envs", C.c_int64), ("derivs", C.c_void_p), ("emitted", C.c_void_p),
         ("t_episode", C.c_void_p), ("episode", C.c_void_p),
         ("reached", C.c_void_p), ("ring", C.c_void_p), ("stats", C.c_void_p),
+        ("stats_slots", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -176,6 +179,7 @@ class GridState(C.Structure):
     _fields_ = [
         ("n_envs", C.c_int64), ("pos", C.c_void_p), ("t_episode", C.c_void_p),
         ("episode", C.c_void_p), ("reached", C.c_void_p), ("stats", C.c_void_p),
+        ("stats_slots", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 

@@ -355,5 +355,6 @@ extern "C" int mdpp_set_discrete_groups(mdpp_ctx* ctx,
                             sizeof(DiscreteGroupDev) * n_groups,
                             cudaMemcpyHostToDevice));
   ctx->d_groups_host = dev;
+  ctx->d_groups_version += 1;
   return MDPP_OK;
 }

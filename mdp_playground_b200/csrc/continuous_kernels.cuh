@@ -618,7 +618,10 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
 #pragma unroll
       for (int w = 0; w < kCBlock / 32; ++w) v += red[threadIdx.x][w];
       if (blockIdx.x == 0 && threadIdx.x == 1) v = (double)N * (double)p.T;
-      if (v != 0.0) atomicAdd(p.st.stats + slots[threadIdx.x], v);
+      // CTAs spread their atomics over the `stats_slots` copies of the row
+      if (v != 0.0)
+        atomicAdd(p.st.stats + (blockIdx.x % (unsigned)max(p.st.stats_slots, 1)) *
+                                   MDPP_N_STATS + slots[threadIdx.x], v);
     }
   }
 }
@@ -650,7 +653,8 @@ __device__ __forceinline__ void continuous_reset_body(const ContinuousParams& p)
     }
   }
   if (p.st.stats && p.st.t_episode[env] > 0)
-    atomicAdd(p.st.stats + MDPP_STAT_EPISODES, 1.0);
+    atomicAdd(p.st.stats + (blockIdx.x % (unsigned)max(p.st.stats_slots, 1)) *
+                               MDPP_N_STATS + MDPP_STAT_EPISODES, 1.0);
   for (int d = 0; d < D; ++d) {
     emitted[(int64_t)d * N + env] = s0[d];
     for (int k = 0; k <= ORDER; ++k)

@@ -71,6 +71,7 @@ struct RolloutParams {
   const uint64_t* step_index_dev;  // optional device counter added to step_index
   int64_t env_id_offset;
   int32_t irr;  // every group has an irrelevant sub-MDP: I/O rows of 2
+  int32_t n_groups;
 };
 
 struct ResetParams {
@@ -87,6 +88,7 @@ struct ResetParams {
   uint64_t step_index;
   int64_t env_id_offset;
   int32_t irr;
+  int32_t n_groups;
 };
 
 }  // namespace mdpp

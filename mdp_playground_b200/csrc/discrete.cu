@@ -56,8 +56,11 @@ discrete_reset_kernel(const __grid_constant__ ResetParams p) {
       s0_irr = cdf_search<-1>(cdf1, g.irr_cdf_log2, g.S1, u_irr);
     }
   }
-  if (p.st.stats && p.st.t_episode[env] > 0)
-    atomicAdd(p.st.stats + (int64_t)me.group * MDPP_N_STATS + MDPP_STAT_EPISODES, 1.0);
+  if (p.st.stats && p.st.t_episode[env] > 0) {
+    const int slot = (int)(blockIdx.x % (unsigned)max(p.st.stats_slots, 1));
+    atomicAdd(p.st.stats + ((int64_t)slot * p.n_groups + me.group) * MDPP_N_STATS +
+                  MDPP_STAT_EPISODES, 1.0);
+  }
   p.st.cur_state[env] = s0;
   if (irr) p.st.cur_state_irr[env] = min(max(s0_irr, 0), g.S1 - 1);
   p.st.seq_key[env] = (uint64_t)s0;
@@ -154,6 +157,7 @@ extern "C" int mdpp_discrete_rollout(mdpp_ctx* ctx,
   p.step_index_dev = opts->step_index_dev;
   p.env_id_offset = opts->env_id_offset;
   p.irr = ctx->d_irr;
+  p.n_groups = (int32_t)ctx->d_groups_host.size();
   cudaStream_t s = (cudaStream_t)cuda_stream;
   if (opts->noise_mode < MDPP_NOISE_OFF || opts->noise_mode > MDPP_NOISE_PHILOX)
     return fail(ctx, MDPP_EINVAL, "unknown noise_mode");
@@ -200,6 +204,7 @@ extern "C" int mdpp_discrete_reset(mdpp_ctx* ctx, const mdpp_discrete_state* st,
   p.step_index = opts->step_index;
   p.env_id_offset = opts->env_id_offset;
   p.irr = ctx->d_irr;
+  p.n_groups = (int32_t)ctx->d_groups_host.size();
   discrete_reset_kernel<<<(unsigned)ctx->n_ctas, kBlock, 0,
                           (cudaStream_t)cuda_stream>>>(p);
   MDPP_CUDA(ctx, cudaGetLastError());

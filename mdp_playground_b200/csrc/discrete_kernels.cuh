@@ -862,7 +862,10 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
     vals[MDPP_STAT_ABS_TRANSITION_NOISE] = 0.0;
     vals[MDPP_STAT_RESERVED] = 0.0;
     vals[MDPP_STAT_TERMINATED] = (double)e.n_terminated;
-    double* row = p.st.stats + (int64_t)me.group * MDPP_N_STATS;
+    // warps spread their atomics over the `stats_slots` copies of the rows
+    const int n_slots = max(p.st.stats_slots, 1);
+    const int slot = (int)((blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) % (unsigned)n_slots);
+    double* row = p.st.stats + ((int64_t)slot * p.n_groups + me.group) * MDPP_N_STATS;
 #pragma unroll
     for (int k = 0; k < MDPP_N_STATS; ++k) {
       if (k == MDPP_STAT_ABS_TRANSITION_NOISE || k == MDPP_STAT_RESERVED) continue;

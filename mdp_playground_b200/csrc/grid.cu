@@ -320,7 +320,9 @@ grid_rollout_kernel(const __grid_constant__ GridParams p) {
     for (int k = 0; k < MDPP_N_STATS; ++k) {
       if (k == MDPP_STAT_ABS_TRANSITION_NOISE || k == MDPP_STAT_RESERVED) continue;
       const double s = block_sum(vals[k], red);
-      if (threadIdx.x == 0 && s != 0.0) atomicAdd(p.st.stats + k, s);
+      if (threadIdx.x == 0 && s != 0.0)
+        atomicAdd(p.st.stats + (blockIdx.x % (unsigned)max(p.st.stats_slots, 1)) *
+                                   MDPP_N_STATS + k, s);
     }
   }
 }
@@ -349,7 +351,8 @@ grid_reset_kernel(const __grid_constant__ GridParams p) {
       pos[k] = (int32_t)__umulhi(ww[k], (uint32_t)p.cfg.shape[k] + 1u);
   }
   if (p.st.stats && p.st.t_episode[env] > 0)
-    atomicAdd(p.st.stats + MDPP_STAT_EPISODES, 1.0);
+    atomicAdd(p.st.stats + (blockIdx.x % (unsigned)max(p.st.stats_slots, 1)) *
+                               MDPP_N_STATS + MDPP_STAT_EPISODES, 1.0);
   for (int k = 0; k < ND; ++k) {
     p.st.pos[(int64_t)k * N + env] = pos[k];
     if (p.reset_obs) p.reset_obs[env * ND + k] = pos[k];

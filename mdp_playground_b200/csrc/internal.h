@@ -37,6 +37,14 @@ struct mdpp_ctx {
   // runtime-specialised kernels (jit.cu), keyed by their define string
   std::map<std::string, void*> jit_functions;   // CUfunction
   std::vector<void*> jit_modules;               // CUmodule
+  // last launch's (signature -> function): step()-granularity callers repeat
+  // the same launch shape, and building the -D list (the cache key of
+  // jit_functions) costs more than the T = 1 kernel itself
+  long long jit_sig_discrete[10] = {-1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  void* jit_fn_discrete = nullptr;
+  unsigned char jit_sig_continuous[sizeof(mdpp_continuous_config) + 64] = {0};
+  void* jit_fn_continuous = nullptr;
+  long long d_groups_version = 0;  // bumped by mdpp_set_discrete_groups
   int jit_enabled = 1;      // MDPP_JIT=0 in the environment disables it
   int jit_last_used = 0;    // 1 if the last rollout ran a JIT kernel
   std::string jit_log;      // why JIT was not used (informational)

@@ -283,6 +283,22 @@ int jit_try_continuous(mdpp_ctx* ctx, ContinuousParams& p, cudaStream_t stream) 
   ctx->jit_last_used = 0;
   if (!ctx->jit_enabled) return 0;
   const mdpp_continuous_config& c = p.cfg;
+  // signature of the -D list: the whole configuration + the launch shape
+  unsigned char sig[sizeof ctx->jit_sig_continuous];
+  std::memset(sig, 0, sizeof sig);
+  std::memcpy(sig, &c, sizeof c);
+  {
+    const long long extra[8] = {p.noise_mode, p.normal_mode, p.horizon, p.autoreset,
+                                (long long)p.st.n_envs,
+                                p.io.obs && p.io.reward && p.io.terminated &&
+                                    p.io.truncated && !p.io.final_obs, 1, 0};
+    std::memcpy(sig + sizeof c, extra, sizeof extra);
+  }
+  const unsigned grid0 = (unsigned)((p.st.n_envs + kCBlock - 1) / kCBlock);
+  if (std::memcmp(sig, ctx->jit_sig_continuous, sizeof sig) == 0) {
+    if (!ctx->jit_fn_continuous) return 0;
+    return launch(ctx, ctx->jit_fn_continuous, grid0, kCBlock, 0, stream, &p);
+  }
   auto D = [](const char* k, const std::string& v) {
     return std::string("-DMDPP_C_") + k + "=" + v;
   };
@@ -322,6 +338,8 @@ int jit_try_continuous(mdpp_ctx* ctx, ContinuousParams& p, cudaStream_t stream) 
   if (const char* mb = std::getenv("MDPP_JIT_C_MINBLOCKS"))  // tuning knob
     defs.push_back(std::string("-DMDPP_C_MINBLOCKS=") + mb);
   void* fn = get_function(ctx, kContinuousEntrySource, "mdpp_jit_continuous", defs);
+  std::memcpy(ctx->jit_sig_continuous, sig, sizeof sig);
+  ctx->jit_fn_continuous = fn;
   if (!fn) return 0;
   const unsigned grid = (unsigned)((p.st.n_envs + kCBlock - 1) / kCBlock);
   return launch(ctx, fn, grid, kCBlock, 0, stream, &p);
@@ -342,16 +360,27 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
   }
   const bool fast = p.io.actions && p.io.obs && p.io.reward && p.io.terminated &&
                     p.io.truncated && !p.io.final_obs && !p.st.history;
-  int cdf_tpl = groups[0].cdf_log2 <= 6 ? groups[0].cdf_log2 : -1;
-  for (auto& g : groups)
-    if (g.cdf_log2 != groups[0].cdf_log2) cdf_tpl = -1;
-  std::vector<std::string> defs =
-      defines_for(groups, p, noise_mode, normal_mode, fast, true, cdf_tpl);
-  if (const char* ch = std::getenv("MDPP_JIT_CHUNK"))  // tuning knob (4/8/16)
-    defs.push_back(std::string("-DMDPP_JIT_CHUNK=") + ch);
-  if (const char* mb = std::getenv("MDPP_JIT_MINBLOCKS"))  // tuning knob
-    defs.push_back(std::string("-DMDPP_JIT_MINBLOCKS=") + mb);
-  void* fn = get_function(ctx, kEntrySource, "mdpp_jit_rollout", defs);
+  // everything the -D list depends on besides the (versioned) group tables
+  const long long sig[10] = {ctx->d_groups_version, noise_mode, normal_mode, fast,
+                             (long long)p.st.n_envs, p.autoreset, p.horizon, p.irr,
+                             0, 0};
+  void* fn = nullptr;
+  if (std::memcmp(sig, ctx->jit_sig_discrete, sizeof sig) == 0) {
+    fn = ctx->jit_fn_discrete;
+  } else {
+    int cdf_tpl = groups[0].cdf_log2 <= 6 ? groups[0].cdf_log2 : -1;
+    for (auto& g : groups)
+      if (g.cdf_log2 != groups[0].cdf_log2) cdf_tpl = -1;
+    std::vector<std::string> defs =
+        defines_for(groups, p, noise_mode, normal_mode, fast, true, cdf_tpl);
+    if (const char* ch = std::getenv("MDPP_JIT_CHUNK"))  // tuning knob (4/8/16)
+      defs.push_back(std::string("-DMDPP_JIT_CHUNK=") + ch);
+    if (const char* mb = std::getenv("MDPP_JIT_MINBLOCKS"))  // tuning knob
+      defs.push_back(std::string("-DMDPP_JIT_MINBLOCKS=") + mb);
+    fn = get_function(ctx, kEntrySource, "mdpp_jit_rollout", defs);
+    std::memcpy(ctx->jit_sig_discrete, sig, sizeof sig);
+    ctx->jit_fn_discrete = fn;
+  }
   if (!fn) return 0;
   p.ring_smem_bytes = ring_bytes;
   return launch(ctx, fn, (unsigned)ctx->n_ctas, kBlock,

@@ -235,7 +235,8 @@ class VectorRLToyEnv:
             self.track_history = False  # augmented_state differs per group
         self._history = torch.zeros((self._hist_depth, N), dtype=torch.int32,
                                     device=dev) if self.track_history else None
-        self._stats = torch.zeros((self.n_groups, _lib.MDPP_N_STATS),
+        self._stats = torch.zeros((_lib.STATS_SLOTS, self.n_groups,
+                                   _lib.MDPP_N_STATS),
                                   dtype=torch.float64, device=dev)
         st = _lib.DiscreteState()
         st.n_envs = N
@@ -246,6 +247,7 @@ class VectorRLToyEnv:
         st.history_depth = self._hist_depth
         st.history = _ptr(self._history)
         st.stats = _ptr(self._stats)
+        st.stats_slots = _lib.STATS_SLOTS
         st.cur_state_irr = _ptr(self._cur_irr)
         self._state = st
         if self.noise == "numpy":
@@ -924,14 +926,15 @@ class VectorRLToyEnv:
         self._reached = torch.zeros(N, dtype=torch.uint8, device=dev)
         self._ring = torch.zeros((sp.delay, N), dtype=real, device=dev) \
             if sp.delay > 0 else None
-        self._stats = torch.zeros((1, _lib.MDPP_N_STATS), dtype=torch.float64,
-                                  device=dev)
+        self._stats = torch.zeros((_lib.STATS_SLOTS, 1, _lib.MDPP_N_STATS),
+                                  dtype=torch.float64, device=dev)
         st = _lib.ContinuousState()
         st.n_envs = N
         st.derivs, st.emitted = _ptr(self._derivs), _ptr(self._emitted)
         st.t_episode, st.episode = _ptr(self._t), _ptr(self._episode)
         st.reached, st.ring = _ptr(self._reached), _ptr(self._ring)
         st.stats = _ptr(self._stats)
+        st.stats_slots = _lib.STATS_SLOTS
         self._state = st
         self._history = None
         if self.noise == "numpy":
@@ -1094,13 +1097,14 @@ class VectorRLToyEnv:
         self._t = torch.zeros(N, dtype=torch.int32, device=dev)
         self._episode = torch.zeros(N, dtype=torch.int32, device=dev)
         self._reached = torch.zeros(N, dtype=torch.uint8, device=dev)
-        self._stats = torch.zeros((1, _lib.MDPP_N_STATS), dtype=torch.float64,
-                                  device=dev)
+        self._stats = torch.zeros((_lib.STATS_SLOTS, 1, _lib.MDPP_N_STATS),
+                                  dtype=torch.float64, device=dev)
         st = _lib.GridState()
         st.n_envs = N
         st.pos, st.t_episode = _ptr(self._pos), _ptr(self._t)
         st.episode, st.reached = _ptr(self._episode), _ptr(self._reached)
         st.stats = _ptr(self._stats)
+        st.stats_slots = _lib.STATS_SLOTS
         self._state = st
         self._history = None
         if self.noise == "numpy":  # lane i: the reference seeded with seed + i
@@ -1326,6 +1330,6 @@ class VectorRLToyEnv:
         """Per-group counters of rl_toy_env.py:2360-2369 summed over envs and
         episodes; `reduce=True` all-reduces over torch.distributed ranks."""
         from . import sharding
-        stats = sharding.reduce_stats(self._stats) if reduce \
-            else self._stats.clone()
+        total = self._stats.sum(dim=0)  # the kernels spread atomics over slots
+        stats = sharding.reduce_stats(total) if reduce else total
         return sharding.summarize_stats(stats)

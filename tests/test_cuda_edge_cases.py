@@ -122,8 +122,12 @@ def test_invalid_arguments_fail_loudly():
         env.rollout(1, actions=torch.zeros((1, 10), dtype=torch.int32))
     with pytest.raises(AssertionError):
         env.rollout(2, actions=torch.zeros((1, 10), dtype=torch.int32))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(KeyError):         # like the reference (:656): no default
         make_env(4, state_space_type="grid", grid_shape=(4, 4))
+    with pytest.raises(NotImplementedError):  # crashes in the reference (:1950)
+        make_env(4, state_space_type="grid", grid_shape=(4, 4), delay=1,
+                 reward_function="move_to_a_point", target_point=[1, 1],
+                 make_denser=True)
     c = make_env(4, state_space_type="continuous", state_space_dim=2)
     with pytest.raises(TypeError):        # the reference wants dtype_s actions
         c.step(torch.zeros((4, 2), dtype=torch.float64))
