@@ -343,6 +343,9 @@ typedef struct mdpp_grid_state {   /* DEVICE pointers, struct-of-arrays      */
   double* stats;        /* [stats_slots][MDPP_N_STATS], summed over slots     */
   int32_t stats_slots;  /* >= 1 (0 reads as 1), see mdpp_discrete_state       */
   int32_t reserved1;
+  int32_t* prev;        /* optional [2][N]: relevant cell BEFORE the last step
+                           (the other entry of `augmented_state`, :2055-2056);
+                           -1 right after a reset (the reference holds NaN)   */
 } mdpp_grid_state;
 
 typedef struct mdpp_grid_io {      /* T steps, time-major, rows of n_dims    */

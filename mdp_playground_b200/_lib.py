@@ -180,6 +180,7 @@ class GridState(C.Structure):
         ("n_envs", C.c_int64), ("pos", C.c_void_p), ("t_episode", C.c_void_p),
         ("episode", C.c_void_p), ("reached", C.c_void_p), ("stats", C.c_void_p),
         ("stats_slots", C.c_int32), ("reserved1", C.c_int32),
+        ("prev", C.c_void_p),
     ]
 
 

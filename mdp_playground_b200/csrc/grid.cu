@@ -115,6 +115,7 @@ __device__ __forceinline__ double block_sum(double x, double* smem) {
 template <int ND>
 struct GridEnv {
   int32_t pos[ND];
+  int32_t prev[2];    // relevant cell before the last step (-1: none yet)
   int32_t tl, phase;  // phase = tl % reward_every_n_steps, kept incrementally
   uint32_t ep;
   bool reached;
@@ -170,6 +171,7 @@ __device__ __forceinline__ void grid_step(const GridParams& p, GridEnv<ND>& g,
   }
   // dense reward: Manhattan distance moved towards the target
   const int d_old = abs(g.pos[0] - c.target[0]) + abs(g.pos[1] - c.target[1]);
+  g.prev[0] = g.pos[0]; g.prev[1] = g.pos[1];
   if (valid) {
 #pragma unroll
     for (int k = 0; k < ND; ++k) {
@@ -237,6 +239,7 @@ __device__ __forceinline__ void grid_step(const GridParams& p, GridEnv<ND>& g,
         g.pos[k] = (int32_t)__umulhi(ww[k], (uint32_t)c.shape[k] + 1u);
     }
     g.tl = 0; g.phase = 0; g.ep += 1; g.reached = false; g.n_episodes += 1;
+    g.prev[0] = g.prev[1] = -1;
   }
   if (FAST || p.io.obs) st_row<ND>(p.io.obs + off * ND, g.pos);
   if (FAST || p.io.reward) __stcs(p.io.reward + off, r);
@@ -263,6 +266,7 @@ grid_rollout_kernel(const __grid_constant__ GridParams p) {
   g.phase = g.tl % c.reward_every_n_steps;
   g.ep = p.st.episode[e];
   g.reached = p.st.reached[e] != 0;
+  g.prev[0] = g.prev[1] = -1;
   g.sum_reward = g.sum_abs_rnoise = 0.0;
   g.n_noisy = g.n_episodes = g.n_term = 0;
   g.cached_pair = g.cached_quad = ~0ull;
@@ -311,6 +315,10 @@ grid_rollout_kernel(const __grid_constant__ GridParams p) {
     p.st.t_episode[e] = g.tl;
     p.st.episode[e] = g.ep;
     p.st.reached[e] = (uint8_t)g.reached;
+    if (p.st.prev) {
+      p.st.prev[e] = g.prev[0];
+      p.st.prev[N + e] = g.prev[1];
+    }
   }
   if (p.st.stats) {
     const double vals[MDPP_N_STATS] = {
@@ -360,6 +368,7 @@ grid_reset_kernel(const __grid_constant__ GridParams p) {
   p.st.t_episode[env] = 0;
   p.st.episode[env] = ep + 1;
   p.st.reached[env] = 0;
+  if (p.st.prev) p.st.prev[env] = p.st.prev[N + env] = -1;
 }
 
 }  // namespace mdpp

@@ -697,7 +697,7 @@ class VectorRLToyEnv:
     # ------------------------------------------------------------------
     def _state_tensors(self):
         names = ("_cur", "_cur_irr", "_key", "_t", "_episode", "_ring", "_history",
-                 "_stats", "_derivs", "_emitted", "_reached", "_pos")
+                 "_stats", "_derivs", "_emitted", "_reached", "_pos", "_prev")
         return [getattr(self, n) for n in names
                 if getattr(self, n, None) is not None]
 
@@ -1105,6 +1105,9 @@ class VectorRLToyEnv:
         st.episode, st.reached = _ptr(self._episode), _ptr(self._reached)
         st.stats = _ptr(self._stats)
         st.stats_slots = _lib.STATS_SLOTS
+        self._prev = torch.full((2, N), -1, dtype=torch.int32, device=dev) \
+            if self.track_history else None
+        st.prev = _ptr(self._prev)
         self._state = st
         self._history = None
         if self.noise == "numpy":  # lane i: the reference seeded with seed + i
@@ -1233,8 +1236,16 @@ class VectorRLToyEnv:
     # ------------------------------------------------------------------
     def get_augmented_state(self):
         if self.spec.kind == "grid":
-            return {"curr_state": self._pos.t().to(torch.int64).contiguous(),
-                    "curr_obs": self.curr_obs}
+            # :2159-2164: augmented_state = [cell before the last step (NaN
+            # right after a reset), current relevant cell], float64 [N, 2, 2]
+            d = {"curr_state": self._pos.t().to(torch.int64).contiguous(),
+                 "curr_obs": self.curr_obs}
+            if self._prev is not None:
+                prev = self._prev.t().to(torch.float64)
+                prev = torch.where(prev < 0, torch.full_like(prev, float("nan")), prev)
+                cur = self._pos[:2].t().to(torch.float64)
+                d["augmented_state"] = torch.stack([prev, cur], dim=1)
+            return d
         if self.spec.kind == "continuous":
             return {"curr_state": self._emitted.t().contiguous(),
                     "curr_obs": self.curr_obs,
@@ -1265,6 +1276,20 @@ class VectorRLToyEnv:
         and continuous derivatives are zeroed).  Like the reference it does not
         touch the reward-delay FIFO or the RNG streams."""
         dev, N = self.device, self.num_envs
+        if self.spec.kind == "grid":
+            # the dict of get_augmented_state() or a bare [N, n_dims] cell
+            # tensor (then the window holds only that cell, :2203-2208)
+            cells = torch.as_tensor(state["curr_state"] if isinstance(state, dict)
+                                    else state, device=dev).reshape(N, self._nd)
+            self._pos.copy_(cells.t().to(torch.int32))
+            if self._prev is not None:
+                prev = torch.full((N, 2), float("nan"), dtype=torch.float64, device=dev)
+                if isinstance(state, dict) and "augmented_state" in state:
+                    prev = torch.as_tensor(state["augmented_state"], device=dev).to(
+                        torch.float64).reshape(N, 2, 2)[:, 0]
+                self._prev.copy_(torch.nan_to_num(prev, nan=-1.0).t().to(torch.int32))
+            self.curr_obs = self._observe(cells.to(torch.int64), reset=True, ctor=True)
+            return
         if self.spec.kind == "continuous":
             D, order = self.spec.state_space_dim, self.spec.dynamics_order
             if isinstance(state, dict):

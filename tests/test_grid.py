@@ -294,3 +294,30 @@ def test_grid_config_rejections():
     del cfg["make_denser"]
     with pytest.raises(ValueError):
         parse_config(cfg)
+
+
+@pytest.mark.gpu
+def test_augmented_state_round_trip():
+    """get_augmented_state() mirrors the reference's [previous cell or NaN,
+    current cell] window; set_augmented_state() on a fresh env continues the
+    same trajectory."""
+    import torch
+    cfg = gu.case_config("grid_dense_term")
+    ref = scalar_oracle(gu.case_config("grid_dense_term"))
+    a = make_env(1, noise="numpy", **cfg)
+    aug = a.get_augmented_state()["augmented_state"][0].cpu().numpy()
+    assert np.isnan(aug[0]).all() and list(aug[1]) == list(ref.augmented_state[-1])
+    for act in ([0, 1], [-1, 0], [1, 1], [0, -1]):
+        ref.step(list(act))
+        a.step(np.array([act]))
+        aug = a.get_augmented_state()["augmented_state"][0].cpu().numpy()
+        assert [list(x) for x in aug] == [list(x) for x in ref.augmented_state]
+    b = make_env(1, noise="numpy", **gu.case_config("grid_dense_term"))
+    b.set_augmented_state(a.get_augmented_state())
+    for act in ([0, -1], [1, 0], [1, 0]):
+        oa, ra, da, _, _ = a.step(np.array([act]))
+        ob, rb, db, _, _ = b.step(np.array([act]))
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
+    b.set_augmented_state(torch.tensor([[2, 3]]))
+    assert b.get_augmented_state()["curr_state"].tolist() == [[2, 3]]
+    assert torch.isnan(b.get_augmented_state()["augmented_state"][0, 0]).all()
