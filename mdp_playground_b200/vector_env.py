@@ -642,6 +642,23 @@ class VectorRLToyEnv:
             return self._rollout_grid(n_steps, actions, replay, out,
                                       want_final_obs)
         T, N, dev = int(n_steps), self.num_envs, self.device
+        # step()-granularity callers repeat the same launch (same action and
+        # output buffers): reuse the marshalled I/O struct -- the Python side is
+        # what bounds a T = 1 call (a 5 us kernel)
+        fast_key = None
+        if (out is not None and self.noise == "philox" and torch.is_tensor(actions)
+                and actions.dtype == torch.int32 and actions.is_cuda
+                and actions.is_contiguous()):
+            fast_key = (T, actions.data_ptr(), tuple(actions.shape)) + tuple(
+                (k, v.data_ptr()) for k, v in out.items())
+            hit = getattr(self, "_io_cache", None)
+            if hit is not None and hit[0] == fast_key:
+                opts = self._opts(T)
+                self._check(self._lib.mdpp_discrete_rollout(
+                    self._ctx, C.byref(self._state), C.byref(hit[1]),
+                    C.byref(opts), self._stream()))
+                self._step_index += T
+                return out
         row = (T, N, 2) if self._irr else (T, N)  # (relevant, irrelevant) rows
         if actions is not None:
             actions = torch.as_tensor(actions, device=dev)
@@ -690,6 +707,8 @@ class VectorRLToyEnv:
             self._ctx, C.byref(self._state), C.byref(io), C.byref(opts),
             self._stream()))
         self._step_index += T
+        if fast_key is not None:  # (holds the tensors, so the pointers stay valid)
+            self._io_cache = (fast_key, io, actions, dict(out))
         return out
 
     # ------------------------------------------------------------------

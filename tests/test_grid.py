@@ -321,3 +321,35 @@ def test_augmented_state_round_trip():
     b.set_augmented_state(torch.tensor([[2, 3]]))
     assert b.get_augmented_state()["curr_state"].tolist() == [[2, 3]]
     assert torch.isnan(b.get_augmented_state()["augmented_state"][0, 0]).all()
+
+
+@pytest.mark.gpu
+def test_action_substitution_distribution_chi2():
+    """transition_noise = 1: the action is always replaced by a GridActionSpace
+    sample different from it.  From an interior cell the displacement
+    histogram must match the reference's rejection sampler: for a no-op the 4
+    unit moves are equally likely; for a move, the other 3 moves have weight 1
+    and the no-op weight 2 (two of the six samples are no-ops) out of 5.
+    Chi-squared, threshold p > 1e-4 (3 / 3 dof: 21.1)."""
+    import torch
+    cfg = dict(gu.case_config("grid_sparse_noise"), transition_noise=1.0,
+               grid_shape=(9, 9), target_point=[0, 0])
+    N = 200_000
+    for act, weights in (([0, 0], {(1, 0): 1, (-1, 0): 1, (0, 1): 1, (0, -1): 1}),
+                         ([1, 0], {(0, 0): 2, (-1, 0): 1, (0, 1): 1, (0, -1): 1})):
+        env = make_env(N, philox_seed=11, **cfg)
+        start = torch.full((N, 2), 4, dtype=torch.int64)
+        env.reset(options={"init_state": start})
+        obs, *_ = env.step(torch.tensor([act]).repeat(N, 1))
+        d = (obs.cpu().numpy() - 4)
+        total = sum(weights.values())
+        chi2 = 0.0
+        seen = 0
+        for move, w in weights.items():
+            n = int(((d[:, 0] == move[0]) & (d[:, 1] == move[1])).sum())
+            seen += n
+            chi2 += (n - N * w / total) ** 2 / (N * w / total)
+        assert seen == N, "a displacement outside the substitute set occurred"
+        assert chi2 < 21.1, (act, chi2)
+        st = env.episode_stats()
+        assert st["noisy_transitions"][0] == N
