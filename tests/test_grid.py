@@ -353,3 +353,36 @@ def test_action_substitution_distribution_chi2():
         assert chi2 < 21.1, (act, chi2)
         st = env.episode_stats()
         assert st["noisy_transitions"][0] == N
+
+
+@pytest.mark.gpu
+def test_full_size_properties_1m_envs():
+    """BASELINE-sized batch (1 M envs x 64 steps, no noise, no auto-reset):
+    size-independent properties checked on the device -- every move follows
+    the wall-bounce rule, the dense reward telescopes to the Manhattan progress,
+    `terminated` is sticky from the first visit of the target."""
+    import torch
+    cfg = dict(gu.case_config("grid_dense_term"), reward_scale=1.0,
+               term_state_reward=0.0)
+    N, T = 1 << 20, 64
+    env = make_env(N, philox_seed=1, track_history=False, **cfg)
+    start = env.get_augmented_state()["curr_state"].clone()
+    gen = torch.Generator("cuda").manual_seed(0)
+    acts = torch.zeros((T, N, 2), dtype=torch.int64, device="cuda")
+    dim = torch.randint(0, 2, (T, N), device="cuda", generator=gen)
+    val = torch.randint(-1, 2, (T, N), device="cuda", generator=gen)
+    acts.scatter_(2, dim[..., None], val[..., None])
+    out = env.rollout(T, actions=acts)
+    obs = out["obs"]
+    prev = torch.cat([start[None], obs[:-1]], dim=0)
+    want = (prev + acts).clamp_(min=0)
+    want = torch.minimum(want, torch.tensor([7, 7], device="cuda"))
+    assert torch.equal(obs, want)
+    tgt = torch.tensor([5, 5], device="cuda")
+    dist = (obs - tgt).abs().sum(-1)
+    d0 = (start - tgt).abs().sum(-1)
+    assert torch.equal(out["reward"].sum(0), (d0 - dist[-1]).to(torch.float64))
+    at = (dist == 0)
+    sticky = torch.cummax(at.to(torch.uint8), dim=0).values.bool()
+    assert torch.equal(out["terminated"], sticky)
+    assert not out["truncated"].any() and 0.3 < sticky[-1].float().mean() < 0.99

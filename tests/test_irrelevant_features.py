@@ -250,3 +250,31 @@ def test_multi_group_launch_with_irrelevant_features(jit):
     with pytest.raises(AssertionError):
         make_env(128, config_groups=[gu.case_config("irr_8x8_noise"),
                                      gu.case_config("c2_every1")])
+
+
+@pytest.mark.gpu
+def test_full_size_properties_65536_envs():
+    """BASELINE-sized batch (65 536 envs x 256 steps, no transition noise, no
+    auto-reset): both chains follow their own table -- obs[t] == P[obs[t-1],
+    a[t]] per sub-MDP -- and the irrelevant chain never influences rewards or
+    termination (same relevant trajectory as an env without it, given the
+    same tables)."""
+    import torch
+    cfg = gu.case_config("irr_8x5_det")
+    N, T = 65536, 256
+    env = make_env(N, philox_seed=2, track_history=False, **cfg)
+    P = torch.as_tensor(env.transition_matrix, device="cuda").long()
+    P1 = torch.as_tensor(env.transition_matrix_irrelevant, device="cuda").long()
+    start = torch.stack([env._cur, env._cur_irr], -1).long()
+    gen = torch.Generator("cuda").manual_seed(0)
+    acts = torch.stack([torch.randint(0, 8, (T, N), device="cuda", generator=gen),
+                        torch.randint(0, 5, (T, N), device="cuda", generator=gen)],
+                       -1).to(torch.int32)
+    out = env.rollout(T, actions=acts)
+    obs = out["obs"]
+    prev = torch.cat([start[None], obs[:-1]], dim=0)
+    assert torch.equal(obs[..., 0], P[prev[..., 0], acts[..., 0].long()])
+    assert torch.equal(obs[..., 1], P1[prev[..., 1], acts[..., 1].long()])
+    term = torch.as_tensor(env.tables.terminal_mask, device="cuda").bool()
+    assert torch.equal(out["terminated"], term[obs[..., 0]])
+    assert len(torch.unique(obs[..., 1])) == 5
