@@ -255,7 +255,11 @@ __device__ __noinline__ RowVal<R> sample_reset_state(const ContinuousParams& p, 
   return s0;
 }
 
+#ifdef MDPP_C_PREFETCH  // tuning override of the NVRTC build
+constexpr int kActionPrefetch = MDPP_C_PREFETCH;
+#else
 constexpr int kActionPrefetch = 4;  // action rows in flight per env
+#endif
 
 template <typename R, int NOISE>
 __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {

@@ -337,6 +337,8 @@ int jit_try_continuous(mdpp_ctx* ctx, ContinuousParams& p, cudaStream_t stream) 
                      I(k < c.n_relevant ? c.relevant_indices[k] : 0)));
   if (const char* mb = std::getenv("MDPP_JIT_C_MINBLOCKS"))  // tuning knob
     defs.push_back(std::string("-DMDPP_C_MINBLOCKS=") + mb);
+  if (const char* pf = std::getenv("MDPP_JIT_C_PREFETCH"))   // tuning knob
+    defs.push_back(std::string("-DMDPP_C_PREFETCH=") + pf);
   void* fn = get_function(ctx, kContinuousEntrySource, "mdpp_jit_continuous", defs);
   std::memcpy(ctx->jit_sig_continuous, sig, sizeof sig);
   ctx->jit_fn_continuous = fn;
