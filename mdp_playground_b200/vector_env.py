@@ -725,7 +725,9 @@ class VectorRLToyEnv:
         are on, and the advance of the Philox step counter -- into a CUDA
         graph.  Returns `fn(actions) -> (obs, reward, terminated, truncated,
         info)` with the same meaning as step(); the returned tensors are
-        static buffers that the next call overwrites.  Philox noise only."""
+        static buffers that the next call overwrites.  `fn.actions` is the
+        graph's own input buffer: filling it in place and passing it to `fn`
+        avoids the device copy of the actions.  Philox noise only."""
         assert self.noise == "philox", "graphed step needs noise='philox'"
         N, dev = self.num_envs, self.device
         cont = self.spec.kind == "continuous"
@@ -786,8 +788,11 @@ class VectorRLToyEnv:
         def step_fn(actions):
             if mirror[0] != self._step_index:  # eager calls happened in between
                 self._step_ctr.fill_(self._step_index)
-            static_a.copy_(torch.as_tensor(actions).reshape(a_shape),
-                           non_blocking=True)
+            if not (torch.is_tensor(actions)
+                    and actions.data_ptr() == static_a.data_ptr()):
+                # (callers that fill `step_fn.actions` in place skip this copy)
+                static_a.copy_(torch.as_tensor(actions).reshape(a_shape),
+                               non_blocking=True)
             graph.replay()
             self._step_index += 1
             mirror[0] = self._step_index
@@ -796,6 +801,7 @@ class VectorRLToyEnv:
                     out["truncated"][0], {"state": out["obs"][0]})
 
         step_fn.graph = graph
+        step_fn.actions = static_a[0]  # the graph's input buffer, [N(, ...)]
         return step_fn
 
     def rollout_host(self, n_steps, actions_host, out_host, chunk_steps=100):
