@@ -179,3 +179,33 @@ def test_continuous_renderer_random_states_vs_pillow():
         assert np.array_equal(imgs[k], ref._image_continuous(st[k])), k
     for k in range(60):
         assert np.array_equal(imgs[k], ref._image_continuous(st[k])), k
+
+
+@pytest.mark.parametrize("W,H", [(50, 50), (60, 50), (50, 60), (64, 52), (200, 120)])
+def test_discrete_renderer_other_image_sizes(W, H):
+    """Sizes off the 100 x 100 default: 50 x 50 and 60 x 50 take the byte-wise
+    path (W*H or H not a multiple of 16 / 4), the others the vector path with
+    different strides; shift + rotate + flip, every pixel against Pillow."""
+    cfg = dict(gu.case_config("c4_img_all"), image_width=W, image_height=H,
+               image_transforms="shift,rotate,flip", image_sh_quant=1)
+    cfg.pop("image_scale_range")
+    n = 1200
+    env = make_env(n, noise="replay", **cfg)
+    rng = np.random.default_rng(W * 1000 + H)
+    states = rng.integers(0, 8, size=n)
+    R = 20
+    mw, mh = W // 2 - R, H // 2 - R
+    params = np.stack([np.full(n, R), W // 2 + rng.integers(-mw + 1, mw, size=n),
+                       H // 2 + rng.integers(-mh + 1, mh, size=n),
+                       rng.integers(-1, 360, size=n), rng.integers(3, size=n)],
+                      axis=1).astype(np.int32)
+    imgs = env.render_observation(torch.as_tensor(states, device="cuda"),
+                                  image_params=params).cpu().numpy()
+    assert imgs.shape == (n, W, H, 1)
+    E = type("E", (), dict(image_width=W, image_height=H))
+    for k in range(n):
+        Rk, sw, sh, rot, flip = (int(v) for v in params[k])
+        want = oracle_image(E, int(states[k]), dict(
+            R=Rk, shift_w=sw, shift_h=sh, rotation=None if rot < 0 else rot,
+            flip=flip))
+        assert np.array_equal(imgs[k, :, :, 0], want), (k, params[k])
