@@ -4,7 +4,7 @@ numbers and run against (a) the scalar oracle on CPU and (b) the CUDA path
 (`VectorRLToyEnv(1, noise="numpy")`, i.e. same seeds => same streams) on GPU.
 Each test cites the reference test it restates.  Only the 14 reference tests
 that pass at HEAD are ported (the other 6 are stale), and
-of those the ones on the supported path (no grid / move_along_a_line)."""
+of those the ones on the supported path (no move_along_a_line)."""
 import warnings
 
 import numpy as np
@@ -233,3 +233,115 @@ def test_continuous_image_representations(impl):
         obs, r, done, s = env.step(np.array([-0.45, -0.8], dtype=np.float32))
         assert obs.shape == (100, 100, 3) and int(obs.sum()) == sums[i]
     assert np.linalg.norm(s - np.array(cfg["target_point"])) < 0.172
+
+
+# --------------------------------------------------------------------------
+# grid environments: test_grid_image_representations :792-860 (passes at HEAD).
+# test_grid_env :1057-1190 is stale upstream -- at HEAD the reference itself
+# returns reward 0 (wall bounce) where that test expects -3 in its first step,
+# and its delay = 1 part raises ValueError (:1950) -- and is not ported; the
+# grid step path is pinned by the goldens of tests/test_grid.py instead.
+# --------------------------------------------------------------------------
+class GridOracle:
+    def __init__(self, **cfg):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            self.env = ScalarRLToyEnv(**cfg)
+
+    def step(self, a):
+        obs, r, done, _, _ = self.env.step(list(a))
+        return obs, float(r), done, [int(v) for v in self.env.curr_state]
+
+
+class GridCuda:
+    def __init__(self, **cfg):
+        from mdp_playground_b200 import VectorRLToyEnv
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            self.env = VectorRLToyEnv(1, noise="numpy", **cfg)
+
+    def step(self, a):
+        obs, r, term, _, info = self.env.step(np.array([a]))
+        return (obs[0].cpu().numpy(), float(r[0]), bool(term[0]),
+                info["state"][0].tolist())
+
+
+GRID_IMPLS = [pytest.param(GridOracle, id="oracle"),
+              pytest.param(GridCuda, id="cuda", marks=pytest.mark.gpu)]
+
+
+def _grid(**kw):
+    cfg = dict(seed=0, state_space_type="grid", grid_shape=(8, 8), delay=0,
+               sequence_length=1, reward_function="move_to_a_point",
+               target_point=[5, 5])
+    cfg.update(kw)
+    return cfg
+
+
+@pytest.mark.parametrize("impl", GRID_IMPLS)
+def test_grid_image_representations(impl):
+    """test_mdp_playground.py:792-860: sparse reward x 2, invalid actions are
+    no-ops, pixel sums of the first four observations, six bounces off the
+    wall; final cell [6, 7], total reward 6."""
+    env = impl(**_grid(make_denser=False, reward_scale=2.0,
+                       image_representations=True))
+    actions = [[0, 1], [-1, 0], [0, -1], [0, -1], [0.5, -0.5], [1, 2], [1, 0],
+               [0, -1], [0, -1]]
+    sums = [6371313, 6372018, 6372018, 6407811]
+    tot, state = 0.0, None
+    for i, a in enumerate(actions):
+        if isinstance(env, GridCuda) and any(isinstance(v, float) for v in a):
+            # a float action is an invalid action in the reference (dtype test
+            # :1730); the batched API takes integer tensors only
+            a = [2, 2]
+        obs, r, done, state = env.step(a)
+        if i < len(sums):
+            assert int(obs.sum()) == sums[i], (i, int(obs.sum()))
+        tot += r
+    for _ in range(6):
+        tot += env.step([0, 1])[1]
+    assert tot == 6.0 and state is not None
+    assert env.step([0, 0])[3] == [6, 7]
+
+
+@pytest.mark.parametrize("impl", GRID_IMPLS)
+def test_grid_image_representations_dense_terminal_irrelevant_noise(impl):
+    """test_mdp_playground.py:862-1053 (tests 2-5 of the same reference test):
+    dense reward (total 4), terminal cells + term_state_reward (total 3), the
+    irrelevant sub-grid with the pixel sums of the stacked images (total 4),
+    and transition noise 0.5 with reward_scale 1 (total 1)."""
+    floaty = lambda a: any(isinstance(v, float) for v in a)  # noqa: E731
+    acts = [[0, 1], [-1, 0], [0, 0], [1, 0], [0.5, -0.5], [1, 2], [-1, -1], [0, -1],
+            [0, -1]]
+
+    def run(env, actions, pad_front=False, pad_back=False, sums=()):
+        tot = 0.0
+        for i, a in enumerate(actions):
+            if isinstance(env, GridCuda) and floaty(a):
+                # a float action is an INVALID action in the reference (dtype
+                # test :1730): no-op and no noise draw; the batched API takes
+                # integer tensors only, so feed an invalid integer action
+                a = [2, 2]
+            a = ([0, 0] if pad_front else []) + list(a) + ([0, 0] if pad_back else [])
+            obs, r, _, _ = env.step(a)
+            if i < len(sums):
+                assert int(obs.sum()) == sums[i], (i, int(obs.sum()))
+            tot += r
+        return tot
+
+    cfg = _grid(make_denser=True, reward_scale=2.0, image_representations=True)
+    assert run(impl(**cfg), acts) == 4.0
+    cfg.update(terminal_states=[[5, 5], [2, 3], [2, 4], [3, 3], [3, 4]],
+               term_state_reward=-0.25)
+    assert run(impl(**cfg), [[0, 1], [-1, 0], [1, 0], [1, 0], [0, -1], [0, -1],
+                             [0, -1], [0, 1], [-1, 0], [0, 1], [-1, 0], [0, -1],
+                             [1, 0]]) == 3
+    cfg.update(irrelevant_features=True)
+    env = impl(**cfg)
+    tot = run(env, acts, pad_back=True, sums=[12271695, 12272400])
+    tot += run(env, acts, pad_front=True)
+    assert tot == 4
+    cfg.update(transition_noise=0.5, reward_scale=1.0)
+    assert run(impl(**cfg), [[0, 1], [-1, 1], [-1, 0], [1, -1], [0.5, -0.5], [1, 2],
+                             [1, 1], [0, -1], [1, 0], [0, -1], [1, 0], [0, -1],
+                             [0, -1]], pad_back=True) == 1.0
