@@ -374,9 +374,12 @@ def run_gpu_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL logs its version banner (and any NCCL_DEBUG output) to stdout:
-        # keep stdout for the ONE JSON line of the bench contract
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL prints its version banner (and any NCCL_DEBUG output) to the
+        # process's stdout from C: keep file descriptor 1 for the ONE JSON
+        # line of the bench contract and send everything else to stderr
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -540,7 +543,11 @@ def run_gpu_arm(args):
             "episode_stats_allreduced": stats,
             "other_configs": others,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        if world > 1:
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
