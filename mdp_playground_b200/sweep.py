@@ -9,7 +9,8 @@ static `env_config["env_config"]` and hands each to a separate Ray trial
 configuration group of a single batched env, stepped by one kernel launch,
 and the per-cell episode statistics are written in the reference's CSV layout
 (config_processor.py:241-259, :340-373) so its analysis code can read them.
-No agent is trained: the policy is uniform random (or supplied by the caller).
+Continuous and grid experiment files (single-configuration kernels) get one
+batched env per cell instead.  No agent is trained: the policy is uniform random (or supplied by the caller).
 """
 import copy
 import importlib.util
@@ -110,11 +111,29 @@ class Sweep:
         if horizon is None:
             horizon = int(self.module.env_config.get("horizon", 100))
         self.envs_per_cell = int(envs_per_cell)
-        self.env = VectorRLToyEnv(
-            self.n_cells * self.envs_per_cell, device=device, autoreset=True,
-            horizon=horizon, config_groups=self.cell_configs,
-            group_sizes=[self.envs_per_cell] * self.n_cells, shard=shard,
-            **env_kwargs)
+        kinds = {str(c.get("state_space_type", "")).lower()
+                 for c in self.cell_configs}
+        assert len(kinds) == 1, "one state_space_type per experiment file"
+        self.kind = kinds.pop()
+        if self.kind == "discrete":
+            # the whole grid is ONE heterogeneous env: one launch per rollout
+            self.env = VectorRLToyEnv(
+                self.n_cells * self.envs_per_cell, device=device, autoreset=True,
+                horizon=horizon, config_groups=self.cell_configs,
+                group_sizes=[self.envs_per_cell] * self.n_cells, shard=shard,
+                **env_kwargs)
+            self.envs = [self.env]
+        else:
+            # continuous / grid kernels take one configuration per context:
+            # one env per cell, launched back to back on the same stream
+            rank, world = shard
+            self.envs = [VectorRLToyEnv(
+                self.envs_per_cell, device=device, autoreset=True,
+                horizon=horizon,
+                env_id_offset=(i * world + rank) * self.envs_per_cell,
+                **env_kwargs, **copy.deepcopy(c))
+                for i, c in enumerate(self.cell_configs)]
+            self.env = self.envs[0]
         self.timesteps = 0
         self._returned = np.zeros(self.n_cells)
 
@@ -124,16 +143,50 @@ class Sweep:
         done = 0
         while done < steps_per_env:
             T = min(chunk, steps_per_env - done)
-            acts = None if actions_fn is None else actions_fn(done, T)
-            out = self.env.rollout(T, actions=acts, want_final_obs=False)
-            r = out["reward"].sum(dim=0).reshape(self.n_cells, self.envs_per_cell)
-            self._returned += r.sum(dim=1).to(torch.float64).cpu().numpy()
+            if self.kind == "discrete":
+                acts = None if actions_fn is None else actions_fn(done, T)
+                out = self.env.rollout(T, actions=acts, want_final_obs=False)
+                r = out["reward"].sum(dim=0).reshape(self.n_cells,
+                                                     self.envs_per_cell)
+                self._returned += r.sum(dim=1).to(torch.float64).cpu().numpy()
+            else:
+                for i, env in enumerate(self.envs):
+                    acts = self._random_actions(env, T, done) \
+                        if actions_fn is None else actions_fn(done, T, i)
+                    out = env.rollout(T, actions=acts, want_final_obs=False)
+                    self._returned[i] += float(out["reward"].sum())
             done += T
         self.timesteps += steps_per_env
         return self.results()
 
+    def _random_actions(self, env, T, t0):
+        """Uniform random policy for the per-cell envs (continuous: uniform
+        in the action box, or N(0, 1) when it is unbounded; grid: one unit
+        move or the no-op), seeded per env and chunk."""
+        import torch
+        N, dev = env.num_envs, env.device
+        gen = torch.Generator(dev).manual_seed(
+            (env.philox_seed + 7919 * env.env_id_offset + t0) % (2**63))
+        if self.kind == "grid":
+            nd = env._nd
+            acts = torch.zeros((T, N, nd), dtype=torch.int64, device=dev)
+            dim = torch.randint(0, nd, (T, N, 1), device=dev, generator=gen)
+            acts.scatter_(2, dim, torch.randint(-1, 2, (T, N, 1), device=dev,
+                                                generator=gen))
+            return acts
+        D, amax = env.spec.state_space_dim, env.spec.action_space_max
+        if np.isfinite(amax):
+            u = torch.rand((T, N, D), device=dev, generator=gen, dtype=env._real)
+            return (u * 2 - 1) * amax
+        return torch.randn((T, N, D), device=dev, generator=gen, dtype=env._real)
+
     def results(self, reduce=False):
-        st = self.env.episode_stats(reduce=reduce)
+        if self.kind == "discrete":
+            st = self.env.episode_stats(reduce=reduce)
+        else:  # one single-group env per cell
+            per = [e.episode_stats(reduce=reduce) for e in self.envs]
+            st = {k: np.array([float(np.asarray(p[k]).reshape(-1)[0]) for p in per])
+                  for k in ("episodes", "transitions", "noisy_transitions")}
         ep = np.maximum(st["episodes"], 1)
         return {"episodes": st["episodes"], "transitions": st["transitions"],
                 "episode_reward_mean": self._returned / ep,

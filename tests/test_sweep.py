@@ -127,3 +127,26 @@ def test_every_rltoy_experiment_of_the_reference_is_accepted():
                                irrelevant_features=True))
         tb = build_discrete_tables(sp)
     assert tb.transition_irr.shape == (8, 8)
+
+
+@pytest.mark.gpu
+def test_sweep_over_a_continuous_experiment_grid(tmp_path):
+    """Continuous experiment files: one batched env per grid cell; larger
+    time units move further per step, so random-walk episodes end (leave the
+    target's surroundings / hit the box) differently per cell."""
+    fixture = os.path.join(HERE, "fixtures", "ddpg_move_to_a_point_like.py")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sw = sweep.Sweep(fixture, envs_per_cell=256)
+    assert sw.kind == "continuous" and sw.n_cells == 3 * 2 * 2 == len(sw.envs)
+    res = sw.run(300, chunk=100)
+    assert np.all(res["transitions"] == 256 * 300)
+    assert np.all(res["episodes"] > 0) and np.all(np.isfinite(res["episode_reward_mean"]))
+    tu = np.array([c["time_unit"] for c in sw.cell_configs])
+    # random policy: the longer the time unit, the sooner a walk reaches the
+    # target ball (radius 0.5) or is clipped at the box: shorter episodes
+    assert res["episode_len_mean"][tu == 4.0].mean() < res["episode_len_mean"][tu == 0.2].mean()
+    # the two dummy seeds of a cell are different envs (different Philox ids)
+    assert not np.allclose(res["episode_reward_mean"][0::2], res["episode_reward_mean"][1::2])
+    lines = open(sw.write_csv(str(tmp_path / "cont.csv"))).read().splitlines()
+    assert len(lines) == 13 and "time_unit" in lines[0]
