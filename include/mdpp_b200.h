@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MDPP_ABI_VERSION 2
+#define MDPP_ABI_VERSION 3
 
 #define MDPP_OK 0
 #define MDPP_EINVAL (-1)   /* bad argument / unsupported configuration      */
@@ -54,6 +54,11 @@ int mdpp_abi_version(void);
 int mdpp_create(int device, mdpp_ctx** out_ctx);
 void mdpp_destroy(mdpp_ctx* ctx);
 const char* mdpp_last_error(const mdpp_ctx* ctx);
+/* Host copies of the ziggurat tables behind MDPP_NORMAL_ZIGGURAT (numpy's
+ * ki_double / wi_double / fi_double, doubles as bit patterns), 256 entries
+ * each; for tests -- no GPU needed.                                         */
+void mdpp_ziggurat_tables(const uint64_t** ki, const uint64_t** wi_bits,
+                          const uint64_t** fi_bits);
 #endif
 
 /* Runtime specialisation (NVRTC) of the rollout kernel for single-group
@@ -179,6 +184,11 @@ typedef struct mdpp_discrete_io {
 /* How the Philox mode turns words into N(0,1) reward noise.                 */
 #define MDPP_NORMAL_F64 0   /* Box-Muller in fp64 (log, sqrt, sincospi)      */
 #define MDPP_NORMAL_FAST 1  /* Box-Muller on the SFU in fp32 (~1e-6 rel.)    */
+#define MDPP_NORMAL_ZIGGURAT 2 /* fp64, numpy's 256-layer ziggurat (the
+                                  algorithm behind Generator.normal, which the
+                                  reference calls at rl_toy_env.py:1982) on
+                                  Philox words; discrete kernels only, the
+                                  others treat it as MDPP_NORMAL_F64          */
 
 /* mdpp_render_discrete only: the launch may START before the previous kernel
  * of the stream has finished (programmatic dependent launch): its prologue --

@@ -10,11 +10,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # MDPP_LIB: A/B timing of two builds (tools/); the default is the in-tree library
 LIB_PATH = os.environ.get("MDPP_LIB") or os.path.join(HERE, "libmdpp_b200.so")
 
-ABI_VERSION = 2  # MDPP_ABI_VERSION of include/mdpp_b200.h
+ABI_VERSION = 3  # MDPP_ABI_VERSION of include/mdpp_b200.h
 MDPP_NOISE_OFF, MDPP_NOISE_REPLAY, MDPP_NOISE_PHILOX = 0, 1, 2
 MDPP_N_STATS = 8
 STATS_SLOTS = 64  # copies of the counter rows the kernels spread their atomics over
-MDPP_NORMAL_F64, MDPP_NORMAL_FAST = 0, 1
+MDPP_NORMAL_F64, MDPP_NORMAL_FAST, MDPP_NORMAL_ZIGGURAT = 0, 1, 2
 MDPP_LAUNCH_OVERLAP_PREVIOUS = 1
 STAT_NAMES = ("episodes", "transitions", "reward", "noisy_transitions",
               "abs_reward_noise", "abs_transition_noise", "reserved",
@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = (
     "mdpp_set_continuous_config", "mdpp_continuous_rollout",
     "mdpp_continuous_reset", "mdpp_render_discrete", "mdpp_render_continuous",
     "mdpp_set_grid_config", "mdpp_grid_rollout", "mdpp_grid_reset",
+    "mdpp_ziggurat_tables",
 )
 MDPP_MAX_DIM, MDPP_MAX_ORDER, MDPP_MAX_TERM_BOXES = 16, 4, 8
 
@@ -224,6 +225,8 @@ def load():
     lib.mdpp_discrete_reset.argtypes = [
         P, C.POINTER(DiscreteState), P, P, P, P, C.POINTER(StepOpts), P]
     lib.mdpp_set_jit.argtypes = [P, C.c_int]
+    lib.mdpp_ziggurat_tables.argtypes = [C.POINTER(P), C.POINTER(P), C.POINTER(P)]
+    lib.mdpp_ziggurat_tables.restype = None
     lib.mdpp_set_jit.restype = None
     lib.mdpp_jit_last_used.argtypes = [P]
     lib.mdpp_jit_log.argtypes = [P]

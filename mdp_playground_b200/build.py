@@ -12,15 +12,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmdpp_b200.so")
 SOURCES = ["context.cu", "discrete.cu", "discrete_off.cu", "discrete_replay.cu",
-           "discrete_philox_f64.cu", "discrete_philox_fast.cu", "continuous.cu",
+           "discrete_philox_f64.cu", "discrete_philox_fast.cu",
+           "discrete_philox_zig.cu", "continuous.cu",
            "render.cu", "grid.cu",
            "jit.cu"]
 HEADERS = ["internal.h", "device_types.h", "philox.cuh", "discrete_kernels.cuh",
-           "continuous_kernels.cuh",
+           "continuous_kernels.cuh", "ziggurat.cuh", "ziggurat_tables.h",
            "discrete_launch.h", "../../include/mdpp_b200.h"]
 # device-side sources embedded into the library for the NVRTC specialisation
 EMBEDDED = ["discrete_kernels.cuh", "continuous_kernels.cuh", "device_types.h",
-            "philox.cuh",
+            "philox.cuh", "ziggurat.cuh",
             "../../include/mdpp_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",

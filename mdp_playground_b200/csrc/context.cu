@@ -5,6 +5,8 @@
 #include <cstring>
 
 #include "internal.h"
+#include "ziggurat.cuh"
+#include "ziggurat_tables.h"
 
 namespace {
 thread_local std::string g_create_error;
@@ -30,6 +32,13 @@ extern "C" const char* mdpp_last_error(const mdpp_ctx* ctx) {
   return ctx ? ctx->error.c_str() : g_create_error.c_str();
 }
 
+extern "C" void mdpp_ziggurat_tables(const uint64_t** ki, const uint64_t** wi_bits,
+                                     const uint64_t** fi_bits) {
+  if (ki) *ki = kZigKi;
+  if (wi_bits) *wi_bits = kZigWiBits;
+  if (fi_bits) *fi_bits = kZigFiBits;
+}
+
 extern "C" int mdpp_create(int device, mdpp_ctx** out_ctx) {
   if (!out_ctx) return fail(nullptr, MDPP_EINVAL, "out_ctx is NULL");
   *out_ctx = nullptr;
@@ -50,6 +59,23 @@ extern "C" int mdpp_create(int device, mdpp_ctx** out_ctx) {
   ctx->jit_enabled = !(jit_env && jit_env[0] == '0');
   ctx->sm_count = prop.multiProcessorCount;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  {  // ziggurat tables: {wi, (double)ki}[256] for the fast path, then fi[256]
+    std::vector<uint64_t> z(kZigBytes / 8);
+    for (int i = 0; i < kZigLayers; ++i) {
+      z[kZigOffFast / 8 + 2 * i] = kZigWiBits[i];
+      const double kid = (double)kZigKi[i];  // exact: ki < 2^52
+      std::memcpy(&z[kZigOffFast / 8 + 2 * i + 1], &kid, 8);
+      z[kZigOffFi / 8 + i] = kZigFiBits[i];
+    }
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_zig, kZigBytes);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(ctx->d_zig, z.data(), kZigBytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      delete ctx;
+      return cuda_fail(nullptr, e, "ziggurat table upload");
+    }
+  }
   *out_ctx = ctx;
   return MDPP_OK;
 }
@@ -70,6 +96,7 @@ extern "C" void mdpp_destroy(mdpp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   jit_release(ctx);
   free_discrete(ctx);
+  if (ctx->d_zig) cudaFree(ctx->d_zig);
   delete ctx;
 }
 
@@ -160,8 +187,11 @@ extern "C" int mdpp_set_discrete_groups(mdpp_ctx* ctx,
     for (int i = 0; i < S * A; ++i)
       if (in.transition[i] < 0 || in.transition[i] >= S)
         return fail(ctx, MDPP_EINVAL, "transition table entry out of range");
-    d.off_P = reserve(S * A * 2, 16);
-    {
+    d.p_is_u8 = S <= 256 && in.n_states_irr <= 256;
+    d.off_P = reserve(S * A * (d.p_is_u8 ? 1 : 2), 16);
+    if (d.p_is_u8) {
+      for (int i = 0; i < S * A; ++i) gb[d.off_P + i] = (uint8_t)in.transition[i];
+    } else {
       uint16_t* P = reinterpret_cast<uint16_t*>(gb.data() + d.off_P);
       for (int i = 0; i < S * A; ++i) P[i] = (uint16_t)in.transition[i];
     }
@@ -189,10 +219,11 @@ extern "C" int mdpp_set_discrete_groups(mdpp_ctx* ctx,
     // distribution (rl_toy_env.py:1606-1617) is P(P[s,a]) = 1 - p and p / (S-1)
     // for each other state, so a 32-bit word w decides: noisy iff w < T with
     // T = round(p 2^32); given that, w is uniform on [0, T) and
-    // k = floor(w M / 2^sh), M = floor((S-1) 2^sh / T), picks one of the S-1
-    // other states (every state within 2^-32 of its probability; k <= S-2
-    // because M is rounded down).  The noisy state is k + (k >= P[s,a]).  Only
-    // that last step depends on the env state; the rest is drawn ahead.
+    // k = floor(w M / 2^sh), M = floor((S-1) 2^sh / T), is uniform on [0, S-2]
+    // (every value within 2^-32 of its probability; k <= S-2 because M is
+    // rounded down).  The noisy state is (P[s,a] + 1 + k) mod S, i.e. one of
+    // the S-1 other states.  Only that last add depends on the env state; the
+    // rest is drawn ahead.
     auto noise_params = [&](int n_states, uint32_t* pn_M, int32_t* pn_shift) {
       double t = std::floor(in.transition_noise * 4294967296.0 + 0.5);
       uint64_t T = t <= 0.0 ? 0ull : t >= 4294967296.0 ? (1ull << 32) : (uint64_t)t;
@@ -213,8 +244,11 @@ extern "C" int mdpp_set_discrete_groups(mdpp_ctx* ctx,
       for (int i = 0; i < S1 * A1; ++i)
         if (in.transition_irr[i] < 0 || in.transition_irr[i] >= S1)
           return fail(ctx, MDPP_EINVAL, "irrelevant transition entry out of range");
-      d.off_P_irr = reserve(S1 * A1 * 2, 16);
-      {
+      d.off_P_irr = reserve(S1 * A1 * (d.p_is_u8 ? 1 : 2), 16);
+      if (d.p_is_u8) {
+        for (int i = 0; i < S1 * A1; ++i)
+          gb[d.off_P_irr + i] = (uint8_t)in.transition_irr[i];
+      } else {
         uint16_t* P = reinterpret_cast<uint16_t*>(gb.data() + d.off_P_irr);
         for (int i = 0; i < S1 * A1; ++i) P[i] = (uint16_t)in.transition_irr[i];
       }

@@ -22,7 +22,8 @@ struct DiscreteGroupDev {
   int32_t off_lut, off_hash_keys, off_hash_vals, off_values, off_R, off_guide;
   int32_t blob_bytes;
   // Philox-mode transition noise in closed form (context.cu, noise_params):
-  // noisy iff w < pn_T; index among the S-1 other states = (w * pn_M) >> (32 + pn_shift)
+  // noisy iff w < pn_T; then k = (w * pn_M) >> (32 + pn_shift) in [0, S-2] and
+  // the noisy state is (P[s,a] + 1 + k) mod S: uniform over the S-1 others
   uint32_t pn_M;
   int32_t pn_shift;
   uint64_t pn_T;
@@ -35,7 +36,9 @@ struct DiscreteGroupDev {
   int32_t off_P_irr, off_init_cdf_irr, off_noise_cdf_irr;
   int32_t irr_pn_shift;
   uint32_t irr_pn_M;  // noisy iff w < pn_T (same p); index among the S1-1 others
-  uint32_t pad0;
+  // transition tables stored as u8 (S, S1 <= 256: one LEA + LDS.U8 per lookup)
+  // instead of u16
+  uint32_t p_is_u8;
 };
 
 struct CtaMapEntry {
@@ -65,6 +68,7 @@ struct RolloutParams {
   mdpp_discrete_io io;
   int32_t T, autoreset, horizon;
   int32_t ring_smem_bytes;
+  int32_t tab_smem_bytes;  // shared-memory bytes reserved for the group tables
   uint32_t k0, k1;
   uint32_t rk[20];  // Philox round keys expanded from (k0, k1) by the host
   uint64_t step_index;
@@ -72,6 +76,7 @@ struct RolloutParams {
   int64_t env_id_offset;
   int32_t irr;  // every group has an irrelevant sub-MDP: I/O rows of 2
   int32_t n_groups;
+  const uint8_t* zig;  // ziggurat tables (ziggurat.cuh), MDPP_NORMAL_ZIGGURAT
 };
 
 struct ResetParams {

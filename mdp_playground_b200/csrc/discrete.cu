@@ -11,6 +11,7 @@ int launch_rollout_off(mdpp_ctx*, RolloutParams&, cudaStream_t);
 int launch_rollout_replay(mdpp_ctx*, RolloutParams&, cudaStream_t);
 int launch_rollout_philox_f64(mdpp_ctx*, RolloutParams&, cudaStream_t);
 int launch_rollout_philox_fast(mdpp_ctx*, RolloutParams&, cudaStream_t);
+int launch_rollout_philox_zig(mdpp_ctx*, RolloutParams&, cudaStream_t);
 
 
 __global__ void __launch_bounds__(kBlock)
@@ -158,6 +159,8 @@ extern "C" int mdpp_discrete_rollout(mdpp_ctx* ctx,
   p.env_id_offset = opts->env_id_offset;
   p.irr = ctx->d_irr;
   p.n_groups = (int32_t)ctx->d_groups_host.size();
+  p.zig = ctx->d_zig;
+  p.tab_smem_bytes = 0;
   cudaStream_t s = (cudaStream_t)cuda_stream;
   if (opts->noise_mode < MDPP_NOISE_OFF || opts->noise_mode > MDPP_NOISE_PHILOX)
     return fail(ctx, MDPP_EINVAL, "unknown noise_mode");
@@ -170,7 +173,9 @@ extern "C" int mdpp_discrete_rollout(mdpp_ctx* ctx,
     case MDPP_NOISE_PHILOX:
       return opts->normal_mode == MDPP_NORMAL_FAST
                  ? launch_rollout_philox_fast(ctx, p, s)
-                 : launch_rollout_philox_f64(ctx, p, s);
+                 : opts->normal_mode == MDPP_NORMAL_ZIGGURAT
+                       ? launch_rollout_philox_zig(ctx, p, s)
+                       : launch_rollout_philox_f64(ctx, p, s);
   }
   return fail(ctx, MDPP_EINVAL, "unknown noise_mode");
 }

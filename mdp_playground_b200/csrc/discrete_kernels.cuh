@@ -21,6 +21,7 @@
 #pragma once
 #include "device_types.h"
 #include "philox.cuh"
+#include "ziggurat.cuh"
 
 namespace mdpp {
 
@@ -132,6 +133,14 @@ __device__ __forceinline__ int cdf_search(const double* cdf, int log2n, int n,
   return min(pos, n - 1);
 }
 
+// Philox-mode noisy transition: (nxt + kk) mod S with kk = 0 (keep P[s,a]) or
+// the pre-drawn rotation 1..S-1 -- uniform over the S-1 other states.
+__device__ __forceinline__ int32_t rotate_state(int32_t nxt, int32_t kk, int S) {
+  const int32_t t = nxt + kk;
+  if ((S & (S - 1)) == 0) return t & (S - 1);
+  return t >= S ? t - S : t;
+}
+
 // Identities a specialised build may use (see chain_step).
 #if defined(MDPP_SCALE) && defined(MDPP_SHIFT) && defined(MDPP_TERM_REWARD)
 constexpr bool kScaleIsOne = (MDPP_SCALE) == 1.0;
@@ -145,7 +154,7 @@ constexpr bool kScaleIsOne = false, kShiftIsZero = false, kTermRewardIsZero = fa
 struct GroupView {  // per-thread copy of the scalars + table pointers
   int S, A, L, delay, every_n, lookup_kind, key_bits, hash_shift;
   int cdf_log2, cdf_stride;
-  bool has_pnoise, has_rnoise, has_guide;
+  bool has_pnoise, has_rnoise, has_guide, p8;
   const uint8_t* guide;
   uint32_t hash_mask;
   uint64_t key_mask;
@@ -168,17 +177,21 @@ struct GroupView {  // per-thread copy of the scalars + table pointers
   const uint16_t* P_irr;
   const double* init_cdf_irr;
   const double* noise_cdf_irr;
+  const uint4* zig_kw;  // {wi, (double)ki}[256] of the ziggurat, in shared memory
 };
 
 __device__ __forceinline__ GroupView make_view(const DiscreteGroupDev& g,
-                                               const uint8_t* tab) {
+                                               const uint8_t* tab,
+                                               const uint4* zig_kw) {
   GroupView v;
+  v.zig_kw = zig_kw;
   v.S = g.S; v.A = g.A; v.L = g.L; v.delay = g.delay; v.every_n = g.every_n;
   v.lookup_kind = g.lookup_kind; v.key_bits = g.key_bits;
   v.hash_shift = g.hash_shift; v.hash_mask = g.hash_mask;
   v.has_pnoise = g.has_pnoise != 0; v.has_rnoise = g.has_rnoise != 0;
   v.cdf_log2 = g.cdf_log2; v.cdf_stride = g.cdf_stride;
   v.has_guide = g.has_guide != 0;
+  v.p8 = g.p_is_u8 != 0;
   v.guide = tab + g.off_guide;
   v.key_mask = g.key_mask;
   v.r_std = g.r_std; v.scale = g.scale; v.shift = g.shift;
@@ -248,6 +261,9 @@ __device__ __forceinline__ GroupView make_view(const DiscreteGroupDev& g,
 #ifdef MDPP_HAS_GUIDE
   v.has_guide = MDPP_HAS_GUIDE;
 #endif
+#ifdef MDPP_P8
+  v.p8 = MDPP_P8;
+#endif
 #ifdef MDPP_PN_T
   v.pn_T = MDPP_PN_T; v.pn_M = MDPP_PN_M; v.pn_shift = MDPP_PN_SHIFT;
 #endif
@@ -265,6 +281,12 @@ __device__ __forceinline__ GroupView make_view(const DiscreteGroupDev& g,
 #endif
 #endif
   return v;
+}
+
+// P[idx]: u8 entries when every group table has <= 256 states, else u16
+__device__ __forceinline__ int32_t table_next(const GroupView& v,
+                                              const uint16_t* P, int32_t idx) {
+  return v.p8 ? (int32_t)reinterpret_cast<const uint8_t*>(P)[idx] : (int32_t)P[idx];
 }
 
 __device__ __forceinline__ double sequence_reward(const GroupView& v,
@@ -306,28 +328,46 @@ struct EnvRegs {
 //   STREAM_AUTORESET word j       -> 32-bit uniform of the auto-reset after
 //                                    step 4q+j
 template <int NORMAL>
-__device__ __forceinline__ void philox_quad_draws(
+__device__ __forceinline__ uint32_t philox_quad_draws(
     uint32_t gid, uint64_t quad, const uint32_t* rk, bool want_u,
-    bool want_normal, bool want_reset, uint32_t* w_tr, double* z, uint32_t* w_rs) {
+    bool want_normal, bool want_reset, uint32_t* w_tr, double* z, uint32_t* w_rs,
+    const uint4* zig_kw) {
   const uint32_t q0 = (uint32_t)quad, q1 = (uint32_t)(quad >> 32);
+  uint32_t rejected = 0;  // NORMAL == 2: bit j = step 4q+j needs zig_slow()
   if (want_u) {
     U4 w = philox4x32_10_rk(gid, q0, q1, STREAM_STEP, rk);
     w_tr[0] = w.x; w_tr[1] = w.y; w_tr[2] = w.z; w_tr[3] = w.w;
   }
   if (want_normal) {
-    U4 w = philox4x32_10_rk(gid, q0, q1, STREAM_NORMAL, rk);
-    if (NORMAL == 0) {
-      normal_pair_f64(w.x, w.y, &z[0], &z[1]);
-      normal_pair_f64(w.z, w.w, &z[2], &z[3]);
+    if (NORMAL == MDPP_NORMAL_ZIGGURAT) {
+      // one 64-bit word per normal: pair counter = step >> 1 = 2 quad (+ 1)
+      const uint64_t pair = quad << 1;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t pr = pair + h;
+        U4 w = philox4x32_10_rk(gid, (uint32_t)pr, (uint32_t)(pr >> 32), STREAM_ZIG, rk);
+        bool ok0, ok1;
+        z[2 * h] = zig_first(w.x, w.y, zig_kw, &ok0);
+        z[2 * h + 1] = zig_first(w.z, w.w, zig_kw, &ok1);
+        if (!ok0) rejected |= 1u << (2 * h);
+        if (!ok1) rejected |= 2u << (2 * h);
+      }
     } else {
-      normal_pair_fast(w.x, w.y, &z[0], &z[1]);
-      normal_pair_fast(w.z, w.w, &z[2], &z[3]);
+      U4 w = philox4x32_10_rk(gid, q0, q1, STREAM_NORMAL, rk);
+      if (NORMAL == MDPP_NORMAL_F64) {
+        normal_pair_f64(w.x, w.y, &z[0], &z[1]);
+        normal_pair_f64(w.z, w.w, &z[2], &z[3]);
+      } else {
+        normal_pair_fast(w.x, w.y, &z[0], &z[1]);
+        normal_pair_fast(w.z, w.w, &z[2], &z[3]);
+      }
     }
   }
   if (want_reset) {
     U4 w = philox4x32_10_rk(gid, q0, q1, STREAM_AUTORESET, rk);
     w_rs[0] = w.x; w_rs[1] = w.y; w_rs[2] = w.z; w_rs[3] = w.w;
   }
+  return rejected;
 }
 
 // Compile-time configuration of a rollout kernel.
@@ -414,8 +454,8 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
       act[j] = (int32_t)__umulhi(w.x, (uint32_t)v.A);
       q.act[j] = irr ? (int32_t)__umulhi(w.y, (uint32_t)v.A1) : 0;
     }
-    u_tr[j] = 0.0; k_tr[j] = -1; n_rw[j] = 0.0; u_rs[j] = 0.0; s0[j] = 0;
-    q.u_tr[j] = 0.0; q.k_tr[j] = -1; q.s0[j] = 0; u_rs_i[j] = 0.0;
+    u_tr[j] = 0.0; k_tr[j] = 0; n_rw[j] = 0.0; u_rs[j] = 0.0; s0[j] = 0;
+    q.u_tr[j] = 0.0; q.k_tr[j] = 0; q.s0[j] = 0; u_rs_i[j] = 0.0;
     if (NOISE == MDPP_NOISE_REPLAY && j < n_valid) {
       if (irr) {  // rows (relevant, irrelevant)
         if (v.has_pnoise) {
@@ -443,32 +483,50 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
     if (U == 1) {
       double z4[4] = {0, 0, 0, 0};
       uint32_t u4[4] = {0, 0, 0, 0}, r4[4] = {0, 0, 0, 0};
-      philox_quad_draws<NORMAL>(gid, step0 >> 2, p.rk, want_u, want_z,
-                                want_r, u4, z4, r4);
+      const uint32_t rej = philox_quad_draws<NORMAL>(
+          gid, step0 >> 2, p.rk, want_u, want_z, want_r, u4, z4, r4, v.zig_kw);
       const int q4 = (int)(step0 & 3);
       w_tr[0] = q4 == 0 ? u4[0] : q4 == 1 ? u4[1] : q4 == 2 ? u4[2] : u4[3];
       double z = q4 == 0 ? z4[0] : q4 == 1 ? z4[1] : q4 == 2 ? z4[2] : z4[3];
       w_rs[0] = q4 == 0 ? r4[0] : q4 == 1 ? r4[1] : q4 == 2 ? r4[2] : r4[3];
+      if (NORMAL == MDPP_NORMAL_ZIGGURAT && ((rej >> q4) & 1u))
+        z = zig_slow(gid, step0, p.rk, p.zig);
       n_rw[0] = __dmul_rn(v.r_std, z);
     } else {  // chunks start on a multiple-of-4 step (see the callers)
+      uint32_t rej = 0;
 #pragma unroll
       for (int j = 0; j + 3 < U; j += 4) {
         double z4[4] = {0, 0, 0, 0};
-        philox_quad_draws<NORMAL>(gid, (step0 + j) >> 2, p.rk, want_u,
-                                  want_z, want_r, &w_tr[j], z4, &w_rs[j]);
+        rej |= philox_quad_draws<NORMAL>(gid, (step0 + j) >> 2, p.rk, want_u,
+                                         want_z, want_r, &w_tr[j], z4, &w_rs[j],
+                                         v.zig_kw) << j;
         // numpy: normal(0, sigma) = 0 + sigma * z
 #pragma unroll
         for (int k = 0; k < 4; ++k) n_rw[j + k] = __dmul_rn(v.r_std, z4[k]);
       }
+      if (NORMAL == MDPP_NORMAL_ZIGGURAT) {
+        // the 1.5 % of draws whose first ziggurat attempt was rejected: one
+        // out-of-line call per draw, lanes without one wait
+#pragma unroll 1
+        while (rej) {
+          const int jb = __ffs((int)rej) - 1;
+          rej &= rej - 1;
+          const double nz = __dmul_rn(v.r_std, zig_slow(gid, step0 + jb, p.rk, p.zig));
+#pragma unroll
+          for (int j = 0; j < U; ++j)
+            if (j == jb) n_rw[j] = nz;
+        }
+      }
     }
   }
   if (NOISE == MDPP_NOISE_PHILOX && v.has_pnoise) {
-    // closed-form noisy draw (device_types.h): -1 = keep P[s,a], else the
-    // index among the S-1 other states; state-independent, so done here
+    // closed-form noisy draw (device_types.h): 0 = keep P[s,a], else the
+    // rotation 1..S-1 that picks one of the S-1 other states;
+    // state-independent, so done here
 #pragma unroll
     for (int j = 0; j < U; ++j) {
       const uint32_t k = __umulhi(w_tr[j], v.pn_M) >> v.pn_shift;
-      k_tr[j] = ((uint64_t)w_tr[j] < v.pn_T) ? (int32_t)k : -1;
+      k_tr[j] = ((uint64_t)w_tr[j] < v.pn_T) ? (int32_t)k + 1 : 0;
     }
   }
   if (autoreset) {  // candidate initial states, also state-independent
@@ -538,7 +596,7 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
       for (int j = 0; j < U; ++j) {
         if (want_u) {
           const uint32_t k = __umulhi(wi_tr[j], v.irr_pn_M) >> v.irr_pn_shift;
-          q.k_tr[j] = ((uint64_t)wi_tr[j] < v.pn_T) ? (int32_t)k : -1;
+          q.k_tr[j] = ((uint64_t)wi_tr[j] < v.pn_T) ? (int32_t)k + 1 : 0;
         }
         u_rs_i[j] = uniform32(wi_rs[j]);
       }
@@ -573,18 +631,18 @@ __device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupVi
     // noisy redraw, no reward, no terminal states
     uint32_t ai = (uint32_t)act_i;
     if (ai >= (uint32_t)v.A1) ai = (uint32_t)v.A1 - 1;  // memory safety only
-    int32_t nxt_i = v.P_irr[e.s_irr * v.A1 + (int32_t)ai];
+    int32_t nxt_i = table_next(v, v.P_irr, e.s_irr * v.A1 + (int32_t)ai);
     if (NOISE == MDPP_NOISE_REPLAY && v.has_pnoise) {
       nxt_i = cdf_search<-1>(v.noise_cdf_irr + nxt_i * v.irr_cdf_stride,
                              v.irr_cdf_log2, v.S1, u_tr_i);
     } else if (NOISE == MDPP_NOISE_PHILOX && v.has_pnoise) {
-      if (k_tr_i >= 0) nxt_i = k_tr_i + (k_tr_i >= nxt_i);
+      nxt_i = rotate_state(nxt_i, k_tr_i, v.S1);
     }
     e.s_irr = nxt_i;
   }
   uint32_t a = (uint32_t)act;
   if (a >= (uint32_t)v.A) a = (uint32_t)v.A - 1;  // memory safety only
-  int32_t nxt = v.P[e.s * v.A + (int32_t)a];
+  int32_t nxt = table_next(v, v.P, e.s * v.A + (int32_t)a);
   if (NOISE == MDPP_NOISE_REPLAY && v.has_pnoise) {
     // the recorded fp64 uniform against the fp64 cdf, like the reference
     const int32_t noisy = cdf_search<C::CDF_LOG2>(
@@ -592,10 +650,8 @@ __device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupVi
     e.n_noisy += (noisy != nxt);
     nxt = noisy;
   } else if (NOISE == MDPP_NOISE_PHILOX && v.has_pnoise) {
-    if (k_tr >= 0) {  // one of the S-1 other states: skip over P[s,a]
-      nxt = k_tr + (k_tr >= nxt);
-      e.n_noisy += 1;
-    }
+    nxt = rotate_state(nxt, k_tr, v.S);  // one of the S-1 other states
+    e.n_noisy += (k_tr != 0);
   }
   e.key = ((e.key << v.key_bits) | (uint64_t)nxt) & v.key_mask;
   e.tl += 1;
@@ -651,8 +707,7 @@ __device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupVi
     e.key = (uint64_t)e.s;
     e.tl = 0;
     e.phase = 0;
-    e.ep += 1;
-    e.n_episodes += 1;
+    e.n_episodes += 1;  // (the episode counter advances by the same amount)
   }
   if (!FAST && p.st.history) {
     p.st.history[(int64_t)e.hist_pos * N + env] = e.s;
@@ -753,7 +808,17 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
     __syncthreads();
     tab = smem_tab;
   }
-  const GroupView v = make_view(C::SINGLE ? p.group0 : grp, tab);
+  // ziggurat fast-path table behind the ring and the tables
+  const uint4* zig_kw = nullptr;
+  if (C::NORMAL == MDPP_NORMAL_ZIGGURAT && C::NOISE == MDPP_NOISE_PHILOX) {
+    uint4* dst = reinterpret_cast<uint4*>(smem_dyn + p.ring_smem_bytes +
+                                          (SMEM ? p.tab_smem_bytes : 0));
+    const uint4* src = reinterpret_cast<const uint4*>(p.zig + kZigOffFast);
+    for (int i = threadIdx.x; i < kZigLayers; i += kBlock) dst[i] = src[i];
+    __syncthreads();
+    zig_kw = dst;
+  }
+  const GroupView v = make_view(C::SINGLE ? p.group0 : grp, tab, zig_kw);
   const int64_t local = (int64_t)me.chunk * kBlock + threadIdx.x;
   const bool active = local < grp.env_count;
   const int64_t env = grp.env_begin + (active ? local : 0);
@@ -839,7 +904,7 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
     if (irr) p.st.cur_state_irr[env] = e.s_irr;
     p.st.seq_key[env] = e.key;
     p.st.t_episode[env] = e.tl;
-    p.st.episode[env] = e.ep;
+    p.st.episode[env] = e.ep + e.n_episodes;
     if (C::RING_REGS > 0) {
       const int pos_end = (int)((step_base + (uint64_t)p.T) % (uint64_t)C::RING_REGS);
 #pragma unroll

@@ -25,6 +25,7 @@ struct mdpp_ctx {
   int max_delay = 0;
   int64_t d_total_envs = 0;
   int d_irr = 0;  // groups carry an irrelevant sub-MDP
+  uint8_t* d_zig = nullptr;  // ziggurat tables (ziggurat.cuh layout), per context
   // CTA -> (group, chunk) map, one per supported block size
   mdpp::CtaMapEntry* d_cta_map = nullptr;
   int cta_map_block = 0;

@@ -126,6 +126,7 @@ std::vector<std::string> defines_for(const std::vector<DiscreteGroupDev>& groups
   if (UNIFORM(has_rnoise)) d.push_back(D("RNOISE", g.has_rnoise ? "true" : "false"));
   if (UNIFORM(cdf_log2)) d.push_back(D("CDF_LOG2", I(g.cdf_log2)));
   if (UNIFORM(has_guide)) d.push_back(D("HAS_GUIDE", g.has_guide ? "true" : "false"));
+  if (UNIFORM(p_is_u8)) d.push_back(D("P8", g.p_is_u8 ? "true" : "false"));
   if (UNIFORM(r_std)) d.push_back(D("R_STD", hexf(g.r_std)));
   if (UNIFORM(scale)) d.push_back(D("SCALE", hexf(g.scale)));
   if (UNIFORM(shift)) d.push_back(D("SHIFT", hexf(g.shift)));
@@ -181,11 +182,12 @@ typedef unsigned long long uint64_t;
 
 const char* kHeaderNames[] = {"discrete_kernels.cuh", "continuous_kernels.cuh",
                               "device_types.h", "philox.cuh", "mdpp_b200.h",
-                              "stdint.h"};
+                              "stdint.h", "ziggurat.cuh"};
 const char* kHeaderSources[] = {kSrc_discrete_kernels_cuh,
                                 kSrc_continuous_kernels_cuh, kSrc_device_types_h,
-                                kSrc_philox_cuh, kSrc_mdpp_b200_h, kStdintShim};
-constexpr int kNumHeaders = 6;
+                                kSrc_philox_cuh, kSrc_mdpp_b200_h, kStdintShim,
+                                kSrc_ziggurat_cuh};
+constexpr int kNumHeaders = 7;
 
 void* compile(mdpp_ctx* ctx, const char* entry_source, const char* entry_name,
               const std::vector<std::string>& defs, void** module_out) {
@@ -356,7 +358,10 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
   constexpr int kRingSmemMaxDelay = 16;
   const bool ring_ok = ctx->max_delay <= kRingSmemMaxDelay;
   const int ring_bytes = ring_ok ? ctx->max_delay * kBlock * 8 : 0;
-  if (!ring_ok || ctx->max_group_blob + ring_bytes > ctx->max_smem_optin - 1024) {
+  const int zig_bytes = (noise_mode == MDPP_NOISE_PHILOX &&
+                         normal_mode == MDPP_NORMAL_ZIGGURAT) ? kZigFastBytes : 0;
+  if (!ring_ok ||
+      ctx->max_group_blob + ring_bytes + zig_bytes > ctx->max_smem_optin - 1024) {
     ctx->jit_log = "tables or delay ring do not fit shared memory";
     return 0;
   }
@@ -379,14 +384,26 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
       defs.push_back(std::string("-DMDPP_JIT_CHUNK=") + ch);
     if (const char* mb = std::getenv("MDPP_JIT_MINBLOCKS"))  // tuning knob
       defs.push_back(std::string("-DMDPP_JIT_MINBLOCKS=") + mb);
+    if (const char* ex = std::getenv("MDPP_JIT_EXTRA")) {  // experiments: "-DX=1 -DY"
+      std::string all(ex), tok;
+      for (size_t i = 0; i <= all.size(); ++i) {
+        if (i == all.size() || all[i] == ' ') {
+          if (!tok.empty()) defs.push_back(tok);
+          tok.clear();
+        } else {
+          tok += all[i];
+        }
+      }
+    }
     fn = get_function(ctx, kEntrySource, "mdpp_jit_rollout", defs);
     std::memcpy(ctx->jit_sig_discrete, sig, sizeof sig);
     ctx->jit_fn_discrete = fn;
   }
   if (!fn) return 0;
   p.ring_smem_bytes = ring_bytes;
+  p.tab_smem_bytes = ctx->max_group_blob;
   return launch(ctx, fn, (unsigned)ctx->n_ctas, kBlock,
-                ring_bytes + ctx->max_group_blob, stream, &p);
+                ring_bytes + ctx->max_group_blob + zig_bytes, stream, &p);
 }
 
 void jit_release(mdpp_ctx* ctx) {
@@ -409,7 +426,7 @@ extern "C" int mdpp_jit_selftest(char* log, int log_bytes) {
   std::memset(&g, 0, sizeof g);
   g.S = 8; g.A = 8; g.L = 3; g.delay = 2; g.every_n = 1; g.key_bits = 3;
   g.key_mask = 511; g.has_pnoise = 1; g.has_rnoise = 1; g.cdf_log2 = 3;
-  g.has_guide = 1; g.r_std = 0.25; g.scale = 1.0;
+  g.has_guide = 1; g.r_std = 0.25; g.scale = 1.0; g.p_is_u8 = 1;
   g.pn_T = 429496730ull; g.pn_M = 2348810237u; g.pn_shift = 25;
   RolloutParams p;
   std::memset(&p, 0, sizeof p);

@@ -17,6 +17,8 @@ enum PhiloxStream : uint32_t {
   STREAM_IMAGE = 3,      // image transform draws
   STREAM_NORMAL = 4,     // (w0,w1),(w2,w3) -> two Box-Muller pairs (reward noise)
   STREAM_AUTORESET = 5,  // 32-bit uniforms of the same-step auto-reset
+  STREAM_ZIG = 6,        // counter = step >> 1: (w0,w1) / (w2,w3) = the 64-bit
+                         // first ziggurat word of the even / odd step
   STREAM_STATE_NOISE = 8,  // + pair index: continuous transition noise
   STREAM_IRR_STEP = 32,       // like STREAM_STEP / STREAM_AUTORESET, for the
   STREAM_IRR_AUTORESET = 33,  // irrelevant sub-MDP (irrelevant_features)
@@ -29,6 +31,8 @@ enum PhiloxStream : uint32_t {
   STREAM_GRID_RESET = 42,
   STREAM_GRID_NORMAL = 43,
   STREAM_RESET_BOX = 64,   // + attempt*16 + dim/4 (continuous reset sampling)
+  STREAM_ZIG_RETRY = 0x100,  // + c, counter = step: ziggurat words after a
+                             // rejected first attempt (ziggurat.cuh)
 };
 
 struct U4 { uint32_t x, y, z, w; };

@@ -59,9 +59,15 @@ class VectorRLToyEnv:
         self.autoreset = bool(autoreset)
         self.horizon = int(horizon)
         self.env_id_offset = int(env_id_offset)
-        assert normal_precision in ("fp64", "fast")
-        self.normal_mode = (_lib.MDPP_NORMAL_FAST if normal_precision == "fast"
-                            else _lib.MDPP_NORMAL_F64)
+        # reward-noise normals of the Philox mode: "fp64" (default) = numpy's
+        # 256-layer ziggurat in fp64 on Philox words (discrete kernels; the
+        # continuous / grid kernels run fp64 Box-Muller), "boxmuller" = fp64
+        # Box-Muller everywhere, "fast" = fp32 Box-Muller on the SFU
+        assert normal_precision in ("fp64", "boxmuller", "fast")
+        self.normal_precision = normal_precision
+        self.normal_mode = {"fast": _lib.MDPP_NORMAL_FAST,
+                            "boxmuller": _lib.MDPP_NORMAL_F64,
+                            "fp64": _lib.MDPP_NORMAL_ZIGGURAT}[normal_precision]
         # the state history behind get_augmented_state() costs one extra
         # store per step; on by default for gym-style (non-autoreset) use
         self.track_history = (not self.autoreset) if track_history is None \

@@ -9,6 +9,7 @@ import numpy as np
 
 STREAM_STEP, STREAM_RESET, STREAM_ACTION, STREAM_IMAGE = 0, 1, 2, 3
 STREAM_NORMAL, STREAM_AUTORESET = 4, 5
+STREAM_ZIG, STREAM_ZIG_RETRY = 6, 0x100
 STREAM_STATE_NOISE, STREAM_RESET_BOX = 8, 64
 STREAM_IRR_STEP, STREAM_IRR_AUTORESET = 32, 33
 
@@ -78,28 +79,52 @@ def transition_noise_params(p, n_states):
     reference's noisy distribution (rl_toy_env.py:1606-1617) gives P[s,a]
     probability 1 - p and each of the S-1 other states p / (S-1).  A 32-bit
     word w is noisy iff w < T = round(p 2^32); then floor(w M / 2^sh) with
-    M = floor((S-1) 2^sh / T) < 2^32 (largest such sh) indexes the others."""
+    M = floor((S-1) 2^sh / T) < 2^32 (largest such sh) is uniform on [0, S-2]
+    and the noisy state is (P[s,a] + 1 + k) mod S -- one of the S-1 others."""
     T = min(max(int(np.floor(float(p) * 4294967296.0 + 0.5)), 0), 1 << 32)
     if T == 0 or n_states < 2:
-        return 0, 0, 32
+        return 0, 0, 32, n_states
     sh = 63
     while sh > 32 and (((n_states - 1) << sh) // T) >> 32:
         sh -= 1
     # T < S-1 (p below ~S 2^-32) cannot be uniform over the others anyway
-    return T, min(((n_states - 1) << sh) // T, 0xFFFFFFFF), sh
+    return T, min(((n_states - 1) << sh) // T, 0xFFFFFFFF), sh, n_states
 
 
 def noisy_next_state(w, nxt, params):
     """Philox-mode noisy transition: words `w`, noise-free next states `nxt`."""
-    T, M, sh = params
+    T, M, sh, S = params
     w = np.asarray(w).astype(np.uint64)
     nxt = np.asarray(nxt, dtype=np.int64)
     # (w * M) >> sh with sh >= 32, as the device does: mulhi, then shift
     k = (((w * np.uint64(M)) >> np.uint64(32)) >> np.uint64(sh - 32)).astype(np.int64)
-    return np.where(w < np.uint64(T), k + (k >= nxt), nxt)
+    return np.where(w < np.uint64(T), (nxt + 1 + k) % S, nxt)
 
 
-def step_noise(seed, env_ids, step, want_normal=True, fast=False, raw=False):
+def ziggurat_normal(seed, env_ids, step):
+    """N(0,1) of global step `step` by csrc/ziggurat.cuh's scheme: the first
+    64-bit word is (w1:w0) / (w3:w2) of Philox(env, step >> 1, STREAM_ZIG) for
+    even / odd steps; a rejected first attempt continues numpy's algorithm on
+    the words (q_2c, q_2c+1) = Philox(env, step, STREAM_ZIG_RETRY + c)."""
+    from . import ziggurat as zg
+    step = int(step)
+    env_ids = np.asarray(env_ids, dtype=np.uint32)
+    pair = step >> 1
+    w = philox4x32_10(env_ids, pair & 0xFFFFFFFF, (pair >> 32) & 0xFFFFFFFF,
+                      STREAM_ZIG, seed)
+    lo, hi = (w[2], w[3]) if step & 1 else (w[0], w[1])
+    main = (hi.astype(np.uint64) << np.uint64(32)) | lo.astype(np.uint64)
+
+    def retry(i, k):
+        q = philox4x32_10(env_ids[i:i + 1], step & 0xFFFFFFFF,
+                          (step >> 32) & 0xFFFFFFFF, STREAM_ZIG_RETRY + (k >> 1), seed)
+        a, b = (q[2], q[3]) if k & 1 else (q[0], q[1])
+        return (int(b[0]) << 32) | int(a[0])
+    return zg.standard_normal_counter(main, retry)
+
+
+def step_noise(seed, env_ids, step, want_normal=True, fast=False, raw=False,
+               normal=None):
     """(transition uniform, N(0,1)) of global step `step` (`raw`: the 32-bit
     transition word instead of the uniform).  The draws come in
     groups of 4 steps (counter = step >> 2): STREAM_STEP word j is the 32-bit
@@ -110,7 +135,9 @@ def step_noise(seed, env_ids, step, want_normal=True, fast=False, raw=False):
     if not raw:
         u = uniform32(u)
     z = None
-    if want_normal:
+    if want_normal and normal == "ziggurat":
+        z = ziggurat_normal(seed, env_ids, step)
+    elif want_normal:
         w = _quad_words(seed, env_ids, step, STREAM_NORMAL)
         pair = normal_pair_fast if fast else normal_pair_f64
         z = pair(w[0], w[1])[j] if j < 2 else pair(w[2], w[3])[j - 2]

@@ -16,7 +16,7 @@ from . import philox as px
 
 class VectorDiscreteOracle:
     def __init__(self, scalar_env, num_envs, autoreset=False, horizon=0,
-                 seed=0, env_id_offset=0, fast_normal=False):
+                 seed=0, env_id_offset=0, fast_normal=False, normal="ziggurat"):
         e = scalar_env
         assert e.kind == "discrete"
         self.N = int(num_envs)
@@ -54,6 +54,9 @@ class VectorDiscreteOracle:
         self.autoreset, self.horizon = autoreset, int(horizon)
         self.seed = int(seed)
         self.fast_normal = fast_normal
+        # reward normals: "ziggurat" (the API default, normal_precision="fp64"),
+        # "boxmuller" (fp64 Box-Muller) or fast_normal=True (fp32 SFU form)
+        self.normal = None if fast_normal or normal == "boxmuller" else normal
         self.gid = (np.arange(self.N, dtype=np.int64) + env_id_offset).astype(
             np.uint32)
         self.step_index = 0
@@ -149,7 +152,8 @@ class VectorDiscreteOracle:
             elif self.has_pnoise or self.has_rnoise:
                 u_tr, z = px.step_noise(self.seed, self.gid, step,
                                         want_normal=self.has_rnoise,
-                                        fast=self.fast_normal, raw=True)
+                                        fast=self.fast_normal, raw=True,
+                                        normal=self.normal)
                 if self.has_rnoise:
                     n_rw = self.r_std * z
             nxt = self.P[self.cur, a]

@@ -197,9 +197,10 @@ def run_case(name, spec):
                 obs_r, _ = env.reset()
                 rec["reset_state"][k, t] = env.curr_state
                 us = [e[2] for e in log if e[1] == "choice_u" and e[0] == "env"]
-                rec["reset_u"][k, t] = us[0]
-                if irr:
-                    rec["irr_reset_u"][k, t] = us[1]
+                if us:  # (continuous resets draw from the feature space, not E)
+                    rec["reset_u"][k, t] = us[0]
+                    if irr:
+                        rec["irr_reset_u"][k, t] = us[1]
                 if image:
                     rec["reset_image"][k, t] = obs_r
                     if not cont:

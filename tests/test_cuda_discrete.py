@@ -306,3 +306,86 @@ def test_set_augmented_state_round_trip_and_bare_state():
         o1, r1, d1, _, _ = ref.step(act)
         o2, r2, d2, _, _ = c.step([act])
         assert int(o2[0]) == int(o1) and float(r2[0]) == float(r1), t
+
+
+# ---------------------------------------------------------------------------
+# the exact bench.py call (headline kernel) against the oracle
+# ---------------------------------------------------------------------------
+_BENCH_CFG = dict(seed=0, state_space_type="discrete", action_space_type="discrete",
+                  state_space_size=8, action_space_size=8, sequence_length=3,
+                  delay=2, transition_noise=0.1, reward_noise=0.25,
+                  reward_density=0.25, terminal_state_density=0.25,
+                  generate_random_mdp=True, reward_every_n_steps=True)
+_bench_oracle_cache = {}
+
+
+def _bench_oracle(normal, prologue, T, N):
+    key = (normal, prologue, T, N)
+    if key not in _bench_oracle_cache:
+        ora = VectorDiscreteOracle(
+            scalar_oracle(dict(_BENCH_CFG)), N, autoreset=True, horizon=100,
+            seed=0, env_id_offset=5 * N, fast_normal=normal == "fast",
+            normal="boxmuller" if normal == "boxmuller" else "ziggurat")
+        ora.reset()
+        acts = np.random.default_rng(0xC0FFEE).integers(0, 8, size=(prologue + T, N))
+        if prologue:
+            ora.rollout(prologue, actions=acts[:prologue])
+        _bench_oracle_cache[key] = (acts, ora.rollout(T, actions=acts[prologue:]),
+                                    dict(ora.stats))
+    return _bench_oracle_cache[key]
+
+
+@pytest.mark.parametrize("jit", [True, False])
+@pytest.mark.parametrize("normal", ["fp64", "boxmuller", "fast"])
+@pytest.mark.parametrize("prologue,T", [(0, 107), (3, 110)])
+def test_bench_signature_matches_oracle(jit, normal, prologue, T):
+    """BASELINE config #2 through the call bench.py times -- int32 actions
+    given, `out` given, no final_obs: the FAST / standard-signature kernel
+    with the chunk-8 action-prefetch loop -- against the batched oracle with
+    noise ON.  (0, 107): 13 full chunks + 3 single steps; (3, 110): 1 peeled
+    step, 13 full chunks, a half chunk and a single step.  States and flags
+    bit-exact; rewards 1e-12 (fp64 normals; the ziggurat's 98.5 % fast path is
+    exact, its tail goes through log1p) or 1e-5 (fp32 SFU normals)."""
+    N = 4096
+    acts, want, stats = _bench_oracle(normal, prologue, T, N)
+    env = make_env(N, autoreset=True, horizon=100, env_id_offset=5 * N,
+                   normal_precision=normal, **dict(_BENCH_CFG))
+    env.set_jit(jit)
+    a = torch.as_tensor(acts, dtype=torch.int32, device="cuda")
+    if prologue:
+        env.rollout(prologue, actions=a[:prologue])
+    out = {"obs": torch.empty((T, N), dtype=torch.int64, device="cuda"),
+           "reward": torch.empty((T, N), dtype=torch.float64, device="cuda"),
+           "terminated": torch.empty((T, N), dtype=torch.bool, device="cuda"),
+           "truncated": torch.empty((T, N), dtype=torch.bool, device="cuda")}
+    got = env.rollout(T, actions=a[prologue:].contiguous(), out=out)
+    assert env.jit_last_used == jit, env.jit_log
+    for k in ("obs", "terminated", "truncated"):
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+    tol = 1e-5 if normal == "fast" else 1e-12
+    np.testing.assert_allclose(got["reward"].cpu().numpy(), want["reward"],
+                               rtol=0 if normal == "fast" else tol, atol=tol)
+    assert want["terminated"].sum() > 1000 and want["truncated"].sum() > 0
+    st = env.episode_stats()
+    for k in ("episodes", "transitions", "noisy_transitions", "terminated"):
+        assert st[k][0] == stats[k], k
+
+
+def test_ziggurat_reward_noise_is_standard_normal():
+    """KS test of the native fp64 (ziggurat) reward noise, 2M draws incl. the
+    wedge / tail path: (reward - noise-free reward) / sigma ~ N(0, 1)."""
+    from scipy import stats
+    N, T = 8192, 256
+    cfg = dict(_BENCH_CFG, transition_noise=0)
+    a = torch.randint(0, 8, (T, N), dtype=torch.int32, device="cuda",
+                      generator=torch.Generator("cuda").manual_seed(2))
+    noisy = make_env(N, autoreset=True, horizon=50, philox_seed=4, **cfg)
+    clean = make_env(N, autoreset=True, horizon=50, philox_seed=4,
+                     **dict(cfg, reward_noise=0))
+    r1 = noisy.rollout(T, actions=a, want_final_obs=False)
+    r0 = clean.rollout(T, actions=a, want_final_obs=False)
+    assert torch.equal(r1["obs"], r0["obs"])
+    z = ((r1["reward"] - r0["reward"]) / 0.25).flatten().cpu().numpy()
+    assert stats.kstest(z, "norm").pvalue > 1e-4
+    assert abs(z.mean()) < 4e-3 and abs(z.std() - 1) < 3e-3
+    assert (np.abs(z) > 3.6541528853610088).sum() > 300   # tail draws present

@@ -75,7 +75,7 @@ def test_closed_form_transition_noise_is_exact_to_2_pow_minus_32(p, S):
     = T / 2^32 with T = round(p 2^32), and the S-1 other states share [0, T)
     in bins whose sizes differ from T / (S-1) by less than 2 words."""
     from oracle import philox as px
-    T, M, sh = px.transition_noise_params(p, S)
+    T, M, sh, _ = px.transition_noise_params(p, S)
     assert T == int(np.floor(p * 2.0 ** 32 + 0.5)) and 0 < M < 2 ** 32 and 32 <= sh <= 63
     assert ((T - 1) * M) >> sh <= S - 2          # the index never overflows
     n = S - 1
@@ -88,6 +88,6 @@ def test_closed_form_transition_noise_is_exact_to_2_pow_minus_32(p, S):
         assert abs((hi - lo) - T / n) < 2, (k, lo, hi)
     w = np.array([0, T // 2, T - 1, T, min(T + 5, 2 ** 32 - 1), 2 ** 32 - 1], dtype=np.uint64)
     for nxt in (0, S // 2, S - 1):
-        out = px.noisy_next_state(w, np.full(w.shape, nxt), (T, M, sh))
+        out = px.noisy_next_state(w, np.full(w.shape, nxt), (T, M, sh, S))
         assert ((out != nxt) == (w < T)).all()   # noisy <=> state changed
         assert ((0 <= out) & (out < S)).all()

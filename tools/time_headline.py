@@ -3,7 +3,7 @@ sys.path.insert(0, '.')
 from mdp_playground_b200 import VectorRLToyEnv
 cfg = dict(seed=0, state_space_type="discrete", action_space_type="discrete", state_space_size=8, action_space_size=8, sequence_length=3, delay=2, transition_noise=0.1, reward_noise=0.25, reward_density=0.25, terminal_state_density=0.25, reward_every_n_steps=True)
 N, T = 65536, 1000
-for name, c, kw in (("C2 fast", cfg, dict(normal_precision="fast")), ("C2 f64", cfg, {}), ("C1", dict({k: v for k, v in cfg.items() if k not in ("transition_noise", "reward_noise")}, sequence_length=1, delay=0), {})):
+for name, c, kw in (("C2 fast", cfg, dict(normal_precision="fast")), ("C2 fp64 ziggurat", cfg, {}), ("C2 fp64 boxmuller", cfg, dict(normal_precision="boxmuller")), ("C1", dict({k: v for k, v in cfg.items() if k not in ("transition_noise", "reward_noise")}, sequence_length=1, delay=0), {})):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         env = VectorRLToyEnv(N, autoreset=True, horizon=100, **c, **kw)
