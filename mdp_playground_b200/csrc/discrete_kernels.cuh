@@ -77,6 +77,18 @@ __device__ __forceinline__ bool irr_of(const RolloutParams& p) {
 #endif
 }
 
+// cache hint of the output stores (tuning knob of the NVRTC build):
+// default .cs (streaming / evict first)
+#if defined(MDPP_ST_POLICY) && MDPP_ST_POLICY == 1
+#define MDPP_ST_HINT ""
+#elif defined(MDPP_ST_POLICY) && MDPP_ST_POLICY == 2
+#define MDPP_ST_HINT ".wt"
+#elif defined(MDPP_ST_POLICY) && MDPP_ST_POLICY == 3
+#define MDPP_ST_HINT ".cg"
+#else
+#define MDPP_ST_HINT ".cs"
+#endif
+
 __device__ __forceinline__ int2 ld_stream_i32x2(const int32_t* p) {
   int2 v;
   asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];"
@@ -90,7 +102,7 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double* p) {
   return v;
 }
 __device__ __forceinline__ void st_stream_x2(int64_t* p, int64_t a, int64_t b) {
-  asm volatile("st.global.cs.v2.s64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+  asm volatile("st.global" MDPP_ST_HINT ".v2.s64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 
 __device__ __forceinline__ int32_t ld_stream_i32(const int32_t* p) {
@@ -103,14 +115,20 @@ __device__ __forceinline__ double ld_stream_f64(const double* p) {
   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+#ifndef MDPP_EXP_SKIP  // timing experiments only: drop classes of memory ops
+#define MDPP_EXP_SKIP 0
+#endif
 __device__ __forceinline__ void st_stream(int64_t* p, int64_t v) {
-  asm volatile("st.global.cs.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  if (MDPP_EXP_SKIP & 2) return;
+  asm volatile("st.global" MDPP_ST_HINT ".s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void st_stream(double* p, double v) {
-  asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+  if (MDPP_EXP_SKIP & 2) return;
+  asm volatile("st.global" MDPP_ST_HINT ".f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 __device__ __forceinline__ void st_stream(uint8_t* p, uint8_t v) {
-  asm volatile("st.global.cs.u8 [%0], %1;" ::"l"(p), "r"((uint32_t)v) : "memory");
+  if (MDPP_EXP_SKIP & 1) return;
+  asm volatile("st.global" MDPP_ST_HINT ".u8 [%0], %1;" ::"l"(p), "r"((uint32_t)v) : "memory");
 }
 
 // numpy searchsorted(cdf, u, side='right') = number of entries <= u, as a
@@ -423,13 +441,15 @@ __device__ __forceinline__ void load_action(const RolloutParams& p, int64_t off,
   }
 }
 
-template <typename C, int U, bool PRELOADED = false>
+// `zs` (STAGED): this thread's column of staged ziggurat normals, sigma
+// applied, zs[j * kBlock] = step t0 + j (zig_fill); else drawn here.
+template <typename C, int U, bool PRELOADED = false, bool STAGED = false>
 __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView& v,
                                         int64_t env, uint32_t gid,
                                         uint64_t step_base, int t0,
                                         int n_valid, int32_t* act, double* u_tr,
                                         int32_t* k_tr, double* n_rw, int32_t* s0,
-                                        IrrDraws<U>& q) {
+                                        IrrDraws<U>& q, const double* zs = nullptr) {
   constexpr int NOISE = C::NOISE;
   constexpr int NORMAL = C::NORMAL;
   constexpr bool FAST = C::FAST;
@@ -478,8 +498,12 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
   for (int j = 0; j < U; ++j) w_rs[j] = w_tr[j] = 0;
   if (NOISE != MDPP_NOISE_REPLAY) {
     const bool want_u = NOISE == MDPP_NOISE_PHILOX && v.has_pnoise;
-    const bool want_z = NOISE == MDPP_NOISE_PHILOX && v.has_rnoise;
+    const bool want_z = NOISE == MDPP_NOISE_PHILOX && v.has_rnoise && !STAGED;
     const bool want_r = autoreset;
+    if (STAGED && v.has_rnoise) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) n_rw[j] = zs[j * kBlock];
+    }
     if (U == 1) {
       double z4[4] = {0, 0, 0, 0};
       uint32_t u4[4] = {0, 0, 0, 0}, r4[4] = {0, 0, 0, 0};
@@ -490,8 +514,8 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
       double z = q4 == 0 ? z4[0] : q4 == 1 ? z4[1] : q4 == 2 ? z4[2] : z4[3];
       w_rs[0] = q4 == 0 ? r4[0] : q4 == 1 ? r4[1] : q4 == 2 ? r4[2] : r4[3];
       if (NORMAL == MDPP_NORMAL_ZIGGURAT && ((rej >> q4) & 1u))
-        z = zig_slow(gid, step0, p.rk, p.zig);
-      n_rw[0] = __dmul_rn(v.r_std, z);
+        z = zig_slow(gid, step0, p.rk, reinterpret_cast<const uint8_t*>(v.zig_kw));
+      if (!STAGED) n_rw[0] = __dmul_rn(v.r_std, z);
     } else {  // chunks start on a multiple-of-4 step (see the callers)
       uint32_t rej = 0;
 #pragma unroll
@@ -501,17 +525,20 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
                                          want_z, want_r, &w_tr[j], z4, &w_rs[j],
                                          v.zig_kw) << j;
         // numpy: normal(0, sigma) = 0 + sigma * z
+        if (!STAGED) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) n_rw[j + k] = __dmul_rn(v.r_std, z4[k]);
+          for (int k = 0; k < 4; ++k) n_rw[j + k] = __dmul_rn(v.r_std, z4[k]);
+        }
       }
-      if (NORMAL == MDPP_NORMAL_ZIGGURAT) {
+      if (NORMAL == MDPP_NORMAL_ZIGGURAT && !STAGED) {
         // the 1.5 % of draws whose first ziggurat attempt was rejected: one
         // out-of-line call per draw, lanes without one wait
 #pragma unroll 1
         while (rej) {
           const int jb = __ffs((int)rej) - 1;
           rej &= rej - 1;
-          const double nz = __dmul_rn(v.r_std, zig_slow(gid, step0 + jb, p.rk, p.zig));
+          const double nz = __dmul_rn(v.r_std, zig_slow(gid, step0 + jb, p.rk,
+                                       reinterpret_cast<const uint8_t*>(v.zig_kw)));
 #pragma unroll
           for (int j = 0; j < U; ++j)
             if (j == jb) n_rw[j] = nz;
@@ -742,34 +769,109 @@ __device__ __forceinline__ void phase_b(const RolloutParams& p, const GroupView&
 }
 
 // A full chunk whose actions were prefetched into act[] (and act_i[]).
-template <typename C, int U>
+template <typename C, int U, bool STAGED = false>
 __device__ __forceinline__ void run_chunk_preloaded(
     const RolloutParams& p, const GroupView& v, EnvRegs& e, double* ring_smem,
     int64_t env, uint32_t gid, uint64_t step_base, int t0, int32_t* act,
-    const int32_t* act_i) {
+    const int32_t* act_i, const double* zs = nullptr) {
   int32_t s0[U], k_tr[U];
   double u_tr[U], n_rw[U];
   IrrDraws<U> q;
 #pragma unroll
   for (int j = 0; j < U; ++j) q.act[j] = act_i[j];
-  phase_a<C, U, true>(p, v, env, gid, step_base, t0, U, act, u_tr, k_tr,
-                            n_rw, s0, q);
+  phase_a<C, U, true, STAGED>(p, v, env, gid, step_base, t0, U, act, u_tr, k_tr,
+                              n_rw, s0, q, zs);
   phase_b<C, U, false>(p, v, e, ring_smem, kBlock, env, t0, U, act, u_tr, k_tr,
                        n_rw, s0, q);
 }
 
-template <typename C, int U>
+template <typename C, int U, bool STAGED = false>
 __device__ __forceinline__ void run_chunk(const RolloutParams& p,
                                           const GroupView& v, EnvRegs& e,
                                           double* ring_smem, int64_t env,
-                                          uint32_t gid, uint64_t step_base, int t0) {
+                                          uint32_t gid, uint64_t step_base, int t0,
+                                          const double* zs = nullptr) {
   int32_t act[U], s0[U];
   int32_t k_tr[U];
   double u_tr[U], n_rw[U];
   IrrDraws<U> q;
-  phase_a<C, U>(p, v, env, gid, step_base, t0, U, act, u_tr, k_tr, n_rw, s0, q);
+  phase_a<C, U, false, STAGED>(p, v, env, gid, step_base, t0, U, act, u_tr, k_tr,
+                               n_rw, s0, q, zs);
   phase_b<C, U, false>(p, v, e, ring_smem, kBlock, env, t0, U, act, u_tr, k_tr,
                        n_rw, s0, q);
+}
+
+// ---- staged ziggurat normals ------------------------------------------------
+// The rejected first attempts (1.5 % of the draws) are what makes a ziggurat
+// expensive on a SIMT machine: resolved where they occur, nearly every warp
+// runs the ~170-instruction slow path for one or two lanes per chunk.  So the
+// reward normals of kZigWindow steps are drawn AHEAD into shared memory
+// (state-independent, like all draws of the Philox mode), the rejected ones of
+// the whole warp (~15 of 1024) are pooled in a queue, and the warp resolves
+// them side by side, one per lane: one pass per window.
+#ifdef MDPP_ZIG_FILL_UNROLL
+constexpr int kZigFillUnroll = MDPP_ZIG_FILL_UNROLL;
+#else
+constexpr int kZigFillUnroll = 4;  // pairs per unrolled body of zig_fill
+#endif
+struct ZigStage {
+  double* zs;        // this thread's column: zs[k * kBlock] = window step k
+  uint32_t* qcnt;    // per warp: number of queued items
+  uint16_t* queue;   // per warp: items (owner lane << 8 | k)
+  unsigned amask;    // the warp's lanes that own an environment
+  int rank, n_act;   // this lane's rank among them, and their number
+};
+
+__device__ __forceinline__ void zig_fill(const RolloutParams& p, const GroupView& v,
+                                         const ZigStage& zst, uint32_t gid,
+                                         uint64_t g0) {  // g0: even global step
+  const int lane = threadIdx.x & 31;
+  const uint8_t* zt = reinterpret_cast<const uint8_t*>(v.zig_kw);  // smem copy
+  if (zst.rank == 0) *zst.qcnt = 0;
+  __syncwarp(zst.amask);
+  uint32_t rej = 0;
+  const uint64_t pair0 = g0 >> 1;
+#pragma unroll 1
+  for (int hb = 0; hb < kZigWindow / 2; hb += kZigFillUnroll) {
+    uint32_t r8 = 0;
+    double* zcol = zst.zs + 2 * hb * kBlock;
+#pragma unroll
+    for (int h = 0; h < kZigFillUnroll; ++h) {
+      const uint64_t pr = pair0 + (uint64_t)(hb + h);
+      const U4 w = philox4x32_10_rk(gid, (uint32_t)pr, (uint32_t)(pr >> 32),
+                                    STREAM_ZIG, p.rk);
+      bool ok0, ok1;
+      const double z0 = zig_first(w.x, w.y, v.zig_kw, &ok0);
+      const double z1 = zig_first(w.z, w.w, v.zig_kw, &ok1);
+      // numpy: normal(0, sigma) = 0 + sigma * z
+      zcol[(2 * h) * kBlock] = __dmul_rn(v.r_std, z0);
+      zcol[(2 * h + 1) * kBlock] = __dmul_rn(v.r_std, z1);
+      if (!ok0) r8 |= 1u << (2 * h);      // (immediates: one predicated LOP3)
+      if (!ok1) r8 |= 2u << (2 * h);
+    }
+    rej |= r8 << (2 * hb);
+  }
+  uint32_t slot = 0;
+  if (rej) slot = atomicAdd(zst.qcnt, (uint32_t)__popc(rej));
+  while (rej) {
+    const int k = __ffs((int)rej) - 1;
+    rej &= rej - 1;
+    if (slot < (uint32_t)kZigQueueCap)
+      zst.queue[slot] = (uint16_t)((lane << 8) | k);
+    else  // queue full (practically never): resolve it here
+      zst.zs[k * kBlock] = __dmul_rn(v.r_std, zig_slow(gid, g0 + (uint64_t)k, p.rk, zt));
+    ++slot;
+  }
+  __syncwarp(zst.amask);
+  const int total = min((int)*zst.qcnt, kZigQueueCap);
+  for (int i = zst.rank; i < total; i += zst.n_act) {
+    const uint32_t item = zst.queue[i];
+    const int owner = (int)(item >> 8), k = (int)(item & 0xffu);
+    zst.zs[k * kBlock + owner - lane] = __dmul_rn(
+        v.r_std, zig_slow(gid - (uint32_t)lane + (uint32_t)owner, g0 + (uint64_t)k,
+                          p.rk, zt));
+  }
+  __syncwarp(zst.amask);
 }
 
 __device__ __forceinline__ double warp_sum(double x) {
@@ -813,14 +915,29 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
   if (C::NORMAL == MDPP_NORMAL_ZIGGURAT && C::NOISE == MDPP_NOISE_PHILOX) {
     uint4* dst = reinterpret_cast<uint4*>(smem_dyn + p.ring_smem_bytes +
                                           (SMEM ? p.tab_smem_bytes : 0));
-    const uint4* src = reinterpret_cast<const uint4*>(p.zig + kZigOffFast);
-    for (int i = threadIdx.x; i < kZigLayers; i += kBlock) dst[i] = src[i];
+    const uint4* src = reinterpret_cast<const uint4*>(p.zig);
+    for (int i = threadIdx.x; i < kZigBytes / 16; i += kBlock) dst[i] = src[i];
     __syncthreads();
     zig_kw = dst;
   }
   const GroupView v = make_view(C::SINGLE ? p.group0 : grp, tab, zig_kw);
   const int64_t local = (int64_t)me.chunk * kBlock + threadIdx.x;
   const bool active = local < grp.env_count;
+  constexpr bool ZIG = C::NORMAL == MDPP_NORMAL_ZIGGURAT && C::NOISE == MDPP_NOISE_PHILOX;
+  ZigStage zst;
+  if (ZIG) {
+    uint8_t* st = smem_dyn + p.ring_smem_bytes + (SMEM ? p.tab_smem_bytes : 0) +
+                  kZigBytes;
+    zst.zs = reinterpret_cast<double*>(st) + threadIdx.x;
+    uint8_t* qb = st + kZigWindow * kBlock * 8 + (threadIdx.x >> 5) * kZigQueueBytes;
+    zst.qcnt = reinterpret_cast<uint32_t*>(qb);
+    zst.queue = reinterpret_cast<uint16_t*>(qb + 16);
+    zst.amask = __ballot_sync(0xffffffffu, active);
+    zst.rank = __popc(zst.amask & ((1u << (threadIdx.x & 31)) - 1u));
+    zst.n_act = __popc(zst.amask);
+  }
+  const bool staged = ZIG && v.has_rnoise;
+  int zs_t0 = -kZigWindow;  // local step at which the staged window starts
   const int64_t env = grp.env_begin + (active ? local : 0);
   const int64_t N = n_envs_of(p);
   const DiscreteGroupDev& gsel = C::SINGLE ? p.group0 : grp;
@@ -863,6 +980,14 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
       run_chunk<C, 1>(p, v, e, ring_smem, env, gid, step_base, t0);
       ++t0;
     }
+#ifdef MDPP_STAGGER
+    // de-synchronise the warps of an SM: odd warps run a half chunk first
+    if (kChunk > 4 && ((blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) & 1) &&
+        t0 + 4 <= p.T) {
+      run_chunk<C, 4>(p, v, e, ring_smem, env, gid, step_base, t0);
+      t0 += 4;
+    }
+#endif
     if (C::FAST) {
       // Action rows are fetched one chunk ahead: under a write-heavy DRAM
       // stream a read takes longer than phase A (ncu: 28 % of all stall
@@ -878,6 +1003,10 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
           load_action<C>(p, (int64_t)(t0 + j) * N + env, act_next[j], act_next_i[j]);
       }
       for (; t0 <= t_last; t0 += kChunk) {
+        if (staged && t0 >= zs_t0 + kZigWindow) {
+          zs_t0 = t0;
+          zig_fill(p, v, zst, gid, step_base + (uint64_t)t0);
+        }
         int32_t act[kChunk], act_i[kChunk];
         const int tn = min(t0 + kChunk, t_last);
 #pragma unroll
@@ -886,12 +1015,19 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
           act_i[j] = act_next_i[j];
           load_action<C>(p, (int64_t)(tn + j) * N + env, act_next[j], act_next_i[j]);
         }
-        run_chunk_preloaded<C, kChunk>(p, v, e, ring_smem, env, gid, step_base,
-                                       t0, act, act_i);
+        run_chunk_preloaded<C, kChunk, ZIG>(p, v, e, ring_smem, env, gid, step_base,
+                                            t0, act, act_i,
+                                            zst.zs + (t0 - zs_t0) * kBlock);
       }
     } else {
-      for (; t0 + kChunk <= p.T; t0 += kChunk)
-        run_chunk<C, kChunk>(p, v, e, ring_smem, env, gid, step_base, t0);
+      for (; t0 + kChunk <= p.T; t0 += kChunk) {
+        if (staged && t0 >= zs_t0 + kZigWindow) {
+          zs_t0 = t0;
+          zig_fill(p, v, zst, gid, step_base + (uint64_t)t0);
+        }
+        run_chunk<C, kChunk, ZIG>(p, v, e, ring_smem, env, gid, step_base, t0,
+                                  zst.zs + (t0 - zs_t0) * kBlock);
+      }
     }
     // remainder: a half chunk first (t0 is still quad-aligned here; single
     // steps pay a whole Philox quad each), then single steps

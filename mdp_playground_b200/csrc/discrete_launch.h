@@ -15,7 +15,8 @@ inline int launch_one(mdpp_ctx* ctx, RolloutParams& p, int smem_tab,
   p.ring_smem_bytes = C::RING_SMEM ? ctx->max_delay * kBlock * 8 : 0;
   p.tab_smem_bytes = C::SMEM ? smem_tab : 0;
   const bool zig = C::NORMAL == MDPP_NORMAL_ZIGGURAT && C::NOISE == MDPP_NOISE_PHILOX;
-  const int smem = p.ring_smem_bytes + p.tab_smem_bytes + (zig ? kZigFastBytes : 0);
+  const int smem = p.ring_smem_bytes + p.tab_smem_bytes +
+                   (zig ? kZigBytes + zig_stage_bytes(kBlock) : 0);
   if (smem > 48 * 1024 - 512)
     MDPP_CUDA(ctx, cudaFuncSetAttribute(
                        kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -35,7 +36,8 @@ inline int launch_rollout(mdpp_ctx* ctx, RolloutParams& p, cudaStream_t stream) 
   const bool ring_ok = ctx->max_delay <= kRingSmemMaxDelay;
   const int ring_bytes = ring_ok ? ctx->max_delay * kBlock * 8 : 0;
   const bool smem_ok =
-      smem_tab + ring_bytes + kZigFastBytes <= ctx->max_smem_optin - 1024;
+      smem_tab + ring_bytes + kZigBytes + zig_stage_bytes(kBlock) <=
+      ctx->max_smem_optin - 1024;
   const bool fast_io = p.io.actions && p.io.obs && p.io.reward &&
                        p.io.terminated && p.io.truncated && !p.io.final_obs &&
                        !p.st.history && !p.irr;  // (FAST kernels: no sub-MDP)

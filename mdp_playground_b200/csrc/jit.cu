@@ -357,9 +357,15 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
   const auto& groups = ctx->d_groups_host;
   constexpr int kRingSmemMaxDelay = 16;
   const bool ring_ok = ctx->max_delay <= kRingSmemMaxDelay;
-  const int ring_bytes = ring_ok ? ctx->max_delay * kBlock * 8 : 0;
+  // (the delay FIFO lives in registers when every group has the same small
+  // delay -- MDPP_CFG_RING_REGS in defines_for -- and needs no shared memory)
+  bool ring_in_regs = groups[0].delay >= 1 && groups[0].delay <= kMaxRingRegs;
+  for (auto& g : groups) ring_in_regs &= g.delay == groups[0].delay;
+  const int ring_bytes =
+      ring_ok && !ring_in_regs ? ctx->max_delay * kBlock * 8 : 0;
   const int zig_bytes = (noise_mode == MDPP_NOISE_PHILOX &&
-                         normal_mode == MDPP_NORMAL_ZIGGURAT) ? kZigFastBytes : 0;
+                         normal_mode == MDPP_NORMAL_ZIGGURAT)
+                            ? kZigBytes + zig_stage_bytes(kBlock) : 0;
   if (!ring_ok ||
       ctx->max_group_blob + ring_bytes + zig_bytes > ctx->max_smem_optin - 1024) {
     ctx->jit_log = "tables or delay ring do not fit shared memory";

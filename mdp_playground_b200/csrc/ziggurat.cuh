@@ -30,6 +30,15 @@ constexpr int kZigFastBytes = kZigLayers * 16;
 constexpr int kZigOffFast = 0;                       // {wi, (double)ki}[256]
 constexpr int kZigOffFi = kZigFastBytes;             // fi[256]
 constexpr int kZigBytes = kZigFastBytes + kZigLayers * 8;
+// Staging of the rollout kernels (discrete_kernels.cuh, zig_fill): normals of
+// kZigWindow consecutive steps per thread in shared memory, and per warp a
+// queue of the draws whose first attempt was rejected.
+constexpr int kZigWindow = 32;
+constexpr int kZigQueueCap = 64;
+constexpr int kZigQueueBytes = 16 + 2 * kZigQueueCap;  // count, then u16 items
+__host__ __device__ constexpr int zig_stage_bytes(int block) {
+  return kZigWindow * block * 8 + (block / 32) * kZigQueueBytes;
+}
 
 // First attempt.  `kw` -> {wi, (double)ki}[256]; returns x, sets *accepted.
 __device__ __forceinline__ double zig_first(uint32_t lo, uint32_t hi, const uint4* kw,
@@ -53,7 +62,8 @@ __device__ __forceinline__ double zig_u53(uint64_t w) {  // numpy next_double
 }
 
 // Everything after a rejected first attempt of (env gid, step).  Out of line:
-// 1.5 % of the draws get here.  `zig` -> the context's ziggurat buffer (global).
+// 1.5 % of the draws get here.  `zig` -> a copy of the context's ziggurat
+// buffer (kZigBytes: the rollout kernels stage all of it in shared memory).
 static __device__ __noinline__ double zig_slow(uint32_t gid, uint64_t step,
                                         const uint32_t* rk, const uint8_t* zig) {
   const uint4* kw = reinterpret_cast<const uint4*>(zig + kZigOffFast);

