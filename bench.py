@@ -600,7 +600,7 @@ def run_gpu_arm(args):
     # rows of the timed output buffers, for the oracle comparison below
     parity = None
     if snap is not None:
-        budget = 1_300_000  # oracle env-steps (~10 s of Python)
+        budget = 640_000  # oracle env-steps (~20 s of Python)
         n_s = int(min(64, max(8, budget // (args.steps * T))))
         idx = np.unique(np.linspace(0, N - 1, n_s).astype(np.int64))
         sel = torch.as_tensor(idx, device=dev)

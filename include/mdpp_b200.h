@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MDPP_ABI_VERSION 3
+#define MDPP_ABI_VERSION 4
 
 #define MDPP_OK 0
 #define MDPP_EINVAL (-1)   /* bad argument / unsupported configuration      */
@@ -179,7 +179,17 @@ typedef struct mdpp_discrete_io {
   const double* replay_transition_u; /* [T*N] uniform of choice(p=) (:1612)  */
   const double* replay_reward_noise; /* [T*N] value of normal(0,sigma) :1982 */
   const double* replay_reset_u;      /* [T*N] uniform of the reset choice    */
+  int32_t obs_dtype;                 /* element type of obs / final_obs: the
+                                        reference's dtype_o (rl_toy_env.py:571,
+                                        :611-614); MDPP_OBS_I64 (default, the
+                                        pointers above), _I32 or _U8: the same
+                                        pointers then address int32_t / uint8_t
+                                        arrays of the same shape              */
+  int32_t reserved0;
 } mdpp_discrete_io;
+#define MDPP_OBS_I64 0
+#define MDPP_OBS_I32 1
+#define MDPP_OBS_U8 2
 
 /* How the Philox mode turns words into N(0,1) reward noise.                 */
 #define MDPP_NORMAL_F64 0   /* Box-Muller in fp64 (log, sqrt, sincospi)      */

@@ -10,11 +10,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # MDPP_LIB: A/B timing of two builds (tools/); the default is the in-tree library
 LIB_PATH = os.environ.get("MDPP_LIB") or os.path.join(HERE, "libmdpp_b200.so")
 
-ABI_VERSION = 3  # MDPP_ABI_VERSION of include/mdpp_b200.h
+ABI_VERSION = 4  # MDPP_ABI_VERSION of include/mdpp_b200.h
 MDPP_NOISE_OFF, MDPP_NOISE_REPLAY, MDPP_NOISE_PHILOX = 0, 1, 2
 MDPP_N_STATS = 8
 STATS_SLOTS = 64  # copies of the counter rows the kernels spread their atomics over
 MDPP_NORMAL_F64, MDPP_NORMAL_FAST, MDPP_NORMAL_ZIGGURAT = 0, 1, 2
+MDPP_OBS_I64, MDPP_OBS_I32, MDPP_OBS_U8 = 0, 1, 2
 MDPP_LAUNCH_OVERLAP_PREVIOUS = 1
 STAT_NAMES = ("episodes", "transitions", "reward", "noisy_transitions",
               "abs_reward_noise", "abs_transition_noise", "reserved",
@@ -74,6 +75,7 @@ class DiscreteIO(C.Structure):
         ("reward", C.c_void_p), ("terminated", C.c_void_p),
         ("truncated", C.c_void_p), ("replay_transition_u", C.c_void_p),
         ("replay_reward_noise", C.c_void_p), ("replay_reset_u", C.c_void_p),
+        ("obs_dtype", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

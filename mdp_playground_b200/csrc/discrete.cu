@@ -127,6 +127,12 @@ extern "C" int mdpp_discrete_rollout(mdpp_ctx* ctx,
   if (rc) return rc;
   if (!io || !opts || opts->n_steps < 1)
     return fail(ctx, MDPP_EINVAL, "bad io/opts");
+  if (io->obs_dtype < MDPP_OBS_I64 || io->obs_dtype > MDPP_OBS_U8)
+    return fail(ctx, MDPP_EINVAL, "unknown obs_dtype");
+  if (io->obs_dtype == MDPP_OBS_U8)
+    for (auto& g : ctx->d_groups_host)
+      if (g.S > 256 || g.S1 > 256)
+        return fail(ctx, MDPP_EINVAL, "obs_dtype u8 needs <= 256 states");
   if (opts->noise_mode == MDPP_NOISE_REPLAY) {
     bool need_p = false, need_r = false;
     for (auto& g : ctx->d_groups_host) {

@@ -65,6 +65,15 @@ __device__ __forceinline__ int horizon_of(const RolloutParams& p) {
 #endif
 }
 
+// element type of obs / final_obs (the reference's dtype_o): launch-wide
+__device__ __forceinline__ int obs_dtype_of(const RolloutParams& p) {
+#ifdef MDPP_JIT
+  return MDPP_OBS_DTYPE;
+#else
+  return p.io.obs_dtype;
+#endif
+}
+
 // irrelevant_features: launch-wide (all groups agree, context.cu).  The
 // ahead-of-time FAST kernels never see it (discrete_launch.h routes such
 // launches to the generic variants), a specialised build gets a literal.
@@ -126,9 +135,32 @@ __device__ __forceinline__ void st_stream(double* p, double v) {
   if (MDPP_EXP_SKIP & 2) return;
   asm volatile("st.global" MDPP_ST_HINT ".f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+__device__ __forceinline__ void st_stream(int32_t* p, int32_t v) {
+  if (MDPP_EXP_SKIP & 2) return;
+  asm volatile("st.global" MDPP_ST_HINT ".s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_stream(uint8_t* p, uint8_t v) {
   if (MDPP_EXP_SKIP & 1) return;
   asm volatile("st.global" MDPP_ST_HINT ".u8 [%0], %1;" ::"l"(p), "r"((uint32_t)v) : "memory");
+}
+
+// one observation (row of 2 with an irrelevant sub-state) in the caller's dtype_o
+__device__ __forceinline__ void store_obs(const RolloutParams& p, int64_t* base,
+                                          int64_t off, bool irr, int32_t s,
+                                          int32_t s_irr) {
+  const int dt = obs_dtype_of(p);
+  if (dt == MDPP_OBS_I64) {
+    if (irr) st_stream_x2(base + 2 * off, (int64_t)s, (int64_t)s_irr);
+    else st_stream(base + off, (int64_t)s);
+  } else if (dt == MDPP_OBS_I32) {
+    int32_t* b = reinterpret_cast<int32_t*>(base);
+    if (irr) { st_stream(b + 2 * off, s); st_stream(b + 2 * off + 1, s_irr); }
+    else st_stream(b + off, s);
+  } else {
+    uint8_t* b = reinterpret_cast<uint8_t*>(base);
+    if (irr) { st_stream(b + 2 * off, (uint8_t)s); st_stream(b + 2 * off + 1, (uint8_t)s_irr); }
+    else st_stream(b + off, (uint8_t)s);
+  }
 }
 
 // numpy searchsorted(cdf, u, side='right') = number of entries <= u, as a
@@ -724,10 +756,7 @@ __device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupVi
   const bool trunc = horizon > 0 && e.tl >= horizon;
   e.n_terminated += done;
   e.s = nxt;
-  if (!FAST && p.io.final_obs) {
-    if (irr) st_stream_x2(p.io.final_obs + 2 * off, (int64_t)nxt, (int64_t)e.s_irr);
-    else st_stream(p.io.final_obs + off, (int64_t)nxt);
-  }
+  if (!FAST && p.io.final_obs) store_obs(p, p.io.final_obs, off, irr, nxt, e.s_irr);
   if (autoreset && (done || trunc)) {
     e.s = s0;
     if (irr) e.s_irr = s0_i;
@@ -740,10 +769,7 @@ __device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupVi
     p.st.history[(int64_t)e.hist_pos * N + env] = e.s;
     e.hist_pos = (e.hist_pos + 1 == p.st.history_depth) ? 0 : e.hist_pos + 1;
   }
-  if (FAST || p.io.obs) {
-    if (irr) st_stream_x2(p.io.obs + 2 * off, (int64_t)e.s, (int64_t)e.s_irr);
-    else st_stream(p.io.obs + off, (int64_t)e.s);
-  }
+  if (FAST || p.io.obs) store_obs(p, p.io.obs, off, irr, e.s, e.s_irr);
   if (FAST || p.io.reward) st_stream(p.io.reward + off, r);
   if (FAST || p.io.terminated) st_stream(p.io.terminated + off, (uint8_t)done);
   if (FAST || p.io.truncated) st_stream(p.io.truncated + off, (uint8_t)trunc);
@@ -824,15 +850,18 @@ struct ZigStage {
 
 __device__ __forceinline__ void zig_fill(const RolloutParams& p, const GroupView& v,
                                          const ZigStage& zst, uint32_t gid,
-                                         uint64_t g0) {  // g0: even global step
+                                         uint64_t g0,    // even global step
+                                         int n_steps) {  // steps the launch still needs
   const int lane = threadIdx.x & 31;
   const uint8_t* zt = reinterpret_cast<const uint8_t*>(v.zig_kw);  // smem copy
   if (zst.rank == 0) *zst.qcnt = 0;
   __syncwarp(zst.amask);
   uint32_t rej = 0;
   const uint64_t pair0 = g0 >> 1;
+  // (a short launch -- or the last window of one -- only draws what it uses)
+  const int n_pairs = min(kZigWindow / 2, (n_steps + 1) >> 1);
 #pragma unroll 1
-  for (int hb = 0; hb < kZigWindow / 2; hb += kZigFillUnroll) {
+  for (int hb = 0; hb < n_pairs; hb += kZigFillUnroll) {
     uint32_t r8 = 0;
     double* zcol = zst.zs + 2 * hb * kBlock;
 #pragma unroll
@@ -1005,7 +1034,7 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
       for (; t0 <= t_last; t0 += kChunk) {
         if (staged && t0 >= zs_t0 + kZigWindow) {
           zs_t0 = t0;
-          zig_fill(p, v, zst, gid, step_base + (uint64_t)t0);
+          zig_fill(p, v, zst, gid, step_base + (uint64_t)t0, p.T - t0);
         }
         int32_t act[kChunk], act_i[kChunk];
         const int tn = min(t0 + kChunk, t_last);
@@ -1023,7 +1052,7 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
       for (; t0 + kChunk <= p.T; t0 += kChunk) {
         if (staged && t0 >= zs_t0 + kZigWindow) {
           zs_t0 = t0;
-          zig_fill(p, v, zst, gid, step_base + (uint64_t)t0);
+          zig_fill(p, v, zst, gid, step_base + (uint64_t)t0, p.T - t0);
         }
         run_chunk<C, kChunk, ZIG>(p, v, e, ring_smem, env, gid, step_base, t0,
                                   zst.zs + (t0 - zs_t0) * kBlock);

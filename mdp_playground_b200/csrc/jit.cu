@@ -145,6 +145,7 @@ std::vector<std::string> defines_for(const std::vector<DiscreteGroupDev>& groups
                 I(UNIFORM(delay) && g.delay >= 1 && g.delay <= kMaxRingRegs ? g.delay : 0)));
 #undef UNIFORM
   d.push_back(D("IRR", I(p.irr)));
+  d.push_back(D("OBS_DTYPE", I(p.io.obs_dtype)));
   d.push_back(D("N_ENVS", I(p.st.n_envs) + "ll"));
   d.push_back(D("AUTORESET", I(p.autoreset)));
   d.push_back(D("HORIZON", I(p.horizon)));
@@ -376,7 +377,7 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
   // everything the -D list depends on besides the (versioned) group tables
   const long long sig[10] = {ctx->d_groups_version, noise_mode, normal_mode, fast,
                              (long long)p.st.n_envs, p.autoreset, p.horizon, p.irr,
-                             0, 0};
+                             p.io.obs_dtype, 0};
   void* fn = nullptr;
   if (std::memcmp(sig, ctx->jit_sig_discrete, sizeof sig) == 0) {
     fn = ctx->jit_fn_discrete;

@@ -36,12 +36,21 @@ class VectorRLToyEnv:
     def __init__(self, num_envs, device=None, noise="philox", autoreset=False,
                  horizon=0, env_id_offset=0, philox_seed=None,
                  normal_precision="fp64", track_history=None,
-                 config_groups=None, group_sizes=None, shard=(0, 1), **config):
+                 config_groups=None, group_sizes=None, shard=(0, 1),
+                 step_buffers=2, **config):
         """config_groups: optional list of config dicts (a heterogeneous
         sweep: each entry is merged over **config); envs are laid out
         group-major, `group_sizes` per group (default: as equal as possible).
         shard=(rank, world): this object holds rank's share of a job that
-        runs the same groups on `world` GPUs (global Philox ids follow)."""
+        runs the same groups on `world` GPUs (global Philox ids follow).
+        step_buffers: step() writes into this many rotating, pre-allocated
+        output sets (the tensors it returns stay valid until `step_buffers`
+        further step() calls; 0 = allocate fresh tensors on every call).
+        A 65 536-env step is a ~5 us kernel: allocating and marshalling five
+        tensors per call would cost several times that."""
+        self._step_buffers = int(step_buffers)
+        self._step_sets = None
+        self._step_flip = 0
         if not torch.cuda.is_available():
             raise RuntimeError(
                 "VectorRLToyEnv needs a CUDA device: the step path is CUDA "
@@ -602,16 +611,49 @@ class VectorRLToyEnv:
             self._stream()))
         return out
 
+    _OBS_CODES = {torch.int64: _lib.MDPP_OBS_I64, torch.int32: _lib.MDPP_OBS_I32,
+                  torch.uint8: _lib.MDPP_OBS_U8}
+
+    def _obs_torch_dtype(self):
+        """dtype the discrete kernels write observations in: the config's
+        dtype_o (rl_toy_env.py:571, :611-614) when it is int64 / int32 / uint8
+        (written in-kernel), else int64 followed by a cast."""
+        forced = getattr(self, "_obs_dtype_override", None)
+        if forced is not None:
+            return forced
+        if self.spec.image_representations:
+            return torch.int64  # states feed the renderer, not the caller
+        dt = getattr(torch, np.dtype(self.spec.dtype_o).name, None)
+        if dt == torch.uint8 and self.tables.n_states > 256:
+            dt = None
+        return dt if dt in self._OBS_CODES else torch.int64
+
+    def set_obs_dtype(self, dtype):
+        """Override dtype_o for the observations rollout() / step() write
+        (torch.int64 / int32 / uint8): 8 -> 1 byte per env-step of output for
+        the toy state spaces."""
+        assert dtype in self._OBS_CODES
+        if dtype == torch.uint8:
+            assert max(self.tables.n_states, self.tables.n_states_irr or 0) <= 256
+        self._obs_dtype_override = dtype
+        self._io_cache = None
+        self._step_sets = None
+
     def _cast_obs(self, obs):
-        dt = np.dtype(self.spec.dtype_o)
-        if dt == np.int64:
-            return obs
-        return obs.to(getattr(torch, dt.name))
+        target = getattr(self, "_obs_dtype_override", None) or getattr(
+            torch, np.dtype(self.spec.dtype_o).name)
+        return obs if obs.dtype == target else obs.to(target)
 
     def step(self, actions, replay=None):
         """(obs, reward, terminated, truncated, info) like RLToyEnv.step
         (:1992).  `replay`: dict with "transition_u", "reward_noise",
-        "reset_u" float64[N] arrays (noise='replay')."""
+        "reset_u" float64[N] arrays (noise='replay').  info["state"] is the
+        underlying state, info["final_obs"] (autoreset only) the state before
+        the same-step reset."""
+        if (replay is None and self.noise == "philox" and self._step_buffers > 0
+                and not self.spec.image_representations
+                and not getattr(self, "_use_dev_counter", False)):
+            return self._step_fast(actions)
         N = self.num_envs
         actions = torch.as_tensor(actions)
         if self.spec.kind == "continuous":
@@ -635,6 +677,89 @@ class VectorRLToyEnv:
                 out["truncated"][0],
                 {"final_obs": out["final_obs"][0], "state": state})
 
+    # -- step() without per-call allocation / marshalling -------------------
+    def _build_step_sets(self):
+        """`step_buffers` output sets, each with its I/O struct marshalled once
+        and the tuple step() returns built once."""
+        N, dev, kind = self.num_envs, self.device, self.spec.kind
+        if kind == "continuous":
+            row, odt, rdt = (1, N, self.spec.state_space_dim), self._real, self._real
+            io_cls, self._step_fn = _lib.ContinuousIO, self._lib.mdpp_continuous_rollout
+            self._step_adt = self._real
+        elif kind == "grid":
+            row, odt, rdt = (1, N, self._nd), torch.int64, torch.float64
+            io_cls, self._step_fn = _lib.GridIO, self._lib.mdpp_grid_rollout
+            self._step_adt = torch.int64
+        else:
+            row = (1, N, 2) if self._irr else (1, N)
+            odt, rdt = self._obs_torch_dtype(), torch.float64
+            io_cls, self._step_fn = _lib.DiscreteIO, self._lib.mdpp_discrete_rollout
+            self._step_adt = torch.int32
+        self._step_arow = row
+        sets = []
+        for _ in range(self._step_buffers):
+            out = {"obs": torch.empty(row, dtype=odt, device=dev),
+                   "reward": torch.empty((1, N), dtype=rdt, device=dev),
+                   "terminated": torch.empty((1, N), dtype=torch.bool, device=dev),
+                   "truncated": torch.empty((1, N), dtype=torch.bool, device=dev)}
+            if self.autoreset:
+                out["final_obs"] = torch.empty(row, dtype=odt, device=dev)
+            io = io_cls()
+            io.obs, io.reward = _ptr(out["obs"]), _ptr(out["reward"])
+            io.final_obs = _ptr(out.get("final_obs"))
+            io.terminated, io.truncated = _ptr(out["terminated"]), _ptr(out["truncated"])
+            if kind == "discrete":
+                io.obs_dtype = self._OBS_CODES[odt]
+            state = out["obs"][0]
+            obs = state  # (replaced per call when dtype_o needs a cast)
+            info = {"state": state}
+            if self.autoreset:
+                info["final_obs"] = out["final_obs"][0]
+            ret = (obs, out["reward"][0], out["terminated"][0], out["truncated"][0], info)
+            sets.append((io, C.byref(io), ret, out))
+        self._step_sets = sets
+        self._step_opts = self._opts(1)
+        if kind == "continuous" and not (self.has_pnoise or self.has_rnoise) \
+                and not self.autoreset:
+            self._step_opts.noise_mode = _lib.MDPP_NOISE_OFF
+        self._step_opts_ref = C.byref(self._step_opts)
+        self._step_state_ref = C.byref(self._state)
+        # dtype_o values the kernels do not write (e.g. int16): cast per call
+        self._step_cast = kind == "discrete" and \
+            self._cast_obs(sets[0][3]["obs"][0]).dtype != odt
+
+    def _step_fast(self, actions):
+        sets = self._step_sets
+        if sets is None:
+            self._build_step_sets()
+            sets = self._step_sets
+        if not (torch.is_tensor(actions) and actions.dtype == self._step_adt
+                and actions.is_cuda and actions.is_contiguous()):
+            actions = torch.as_tensor(actions, device=self.device)
+            if self.spec.kind == "continuous" and actions.dtype != self._real:
+                raise TypeError(f"actions must be {self._real}, got {actions.dtype}")
+            if self.spec.kind == "grid" and actions.dtype.is_floating_point:
+                raise TypeError(f"grid actions must be integers, got {actions.dtype}")
+            actions = actions.to(self._step_adt).contiguous()
+        if actions.numel() != self._step_arow[1] * (
+                self._step_arow[2] if len(self._step_arow) == 3 else 1):
+            raise AssertionError((tuple(actions.shape), self._step_arow))
+        io, io_ref, ret, _ = sets[self._step_flip]
+        self._step_flip = (self._step_flip + 1) % len(sets)
+        io.actions = actions.data_ptr()
+        o = self._step_opts
+        o.step_index = self._step_index
+        o.seed = self.philox_seed
+        rc = self._step_fn(self._ctx, self._step_state_ref, io_ref, self._step_opts_ref,
+                           torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            self._check(rc)
+        self._step_index += 1
+        if self._step_cast:
+            ret = (self._cast_obs(ret[4]["state"]),) + ret[1:]
+        self.curr_obs = ret[0]
+        return ret
+
     def rollout(self, n_steps, actions=None, replay=None, out=None,
                 want_final_obs=True):
         """T fused steps in ONE kernel launch.  actions: int[T, N] tensor or
@@ -656,7 +781,7 @@ class VectorRLToyEnv:
                 and actions.dtype == torch.int32 and actions.is_cuda
                 and actions.is_contiguous()):
             fast_key = (T, actions.data_ptr(), tuple(actions.shape)) + tuple(
-                (k, v.data_ptr()) for k, v in out.items())
+                (k, v.data_ptr(), v.dtype) for k, v in out.items())
             hit = getattr(self, "_io_cache", None)
             if hit is not None and hit[0] == fast_key:
                 opts = self._opts(T)
@@ -674,16 +799,22 @@ class VectorRLToyEnv:
             assert actions.shape == row, (actions.shape, row)
         io = _lib.DiscreteIO()
         if out is None:
+            odt = self._obs_torch_dtype()
             out = {
-                "obs": torch.empty(row, dtype=torch.int64, device=dev),
+                "obs": torch.empty(row, dtype=odt, device=dev),
                 "reward": torch.empty((T, N), dtype=torch.float64, device=dev),
                 "terminated": torch.empty((T, N), dtype=torch.bool, device=dev),
                 "truncated": torch.empty((T, N), dtype=torch.bool, device=dev),
             }
             if want_final_obs:
-                out["final_obs"] = torch.empty(row, dtype=torch.int64,
-                                               device=dev)
+                out["final_obs"] = torch.empty(row, dtype=odt, device=dev)
         io.actions = _ptr(actions)
+        # the kernels write observations in the dtype of the caller's buffer
+        odt = out["obs"].dtype if out.get("obs") is not None else torch.int64
+        if odt not in self._OBS_CODES or (
+                out.get("final_obs") is not None and out["final_obs"].dtype != odt):
+            raise TypeError("obs / final_obs buffers must both be int64, int32 or uint8")
+        io.obs_dtype = self._OBS_CODES[odt]
         io.obs, io.reward = _ptr(out.get("obs")), _ptr(out.get("reward"))
         io.final_obs = _ptr(out.get("final_obs"))
         io.terminated = _ptr(out.get("terminated"))

@@ -415,3 +415,58 @@ def test_oracle_adopts_device_state_mid_run():
     np.testing.assert_allclose(got["reward"].cpu().numpy()[:, idx], want["reward"],
                                rtol=1e-12, atol=1e-12)
     assert (want["reward"] != 0).sum() > 100
+
+
+@pytest.mark.parametrize("dtype_o", [np.uint8, np.int32, np.int16])
+def test_dtype_o_written_in_kernel(dtype_o):
+    """The reference's dtype_o (rl_toy_env.py:571, :611-614): rollout() and
+    step() return observations in it -- uint8 / int32 straight from the kernel
+    (JIT and AOT), other dtypes through a cast -- equal to the int64 ones."""
+    cfg = dict(_BENCH_CFG)
+    N, T = 1000, 30
+    a = torch.randint(0, 8, (T, N), dtype=torch.int32, device="cuda",
+                      generator=torch.Generator("cuda").manual_seed(3))
+    ref = make_env(N, autoreset=True, horizon=13, **cfg).rollout(T, actions=a)
+    want_t = getattr(torch, np.dtype(dtype_o).name)
+    for jit in (True, False):
+        env = make_env(N, autoreset=True, horizon=13, dtype_o=dtype_o, **cfg)
+        env.set_jit(jit)
+        if dtype_o is np.int16:
+            got = env.rollout(T, actions=a)        # kernel writes int64 ...
+            assert got["obs"].dtype == torch.int64
+        else:
+            got = env.rollout(T, actions=a)
+            assert got["obs"].dtype == want_t and got["final_obs"].dtype == want_t
+        for k in ("obs", "final_obs"):
+            assert torch.equal(got[k].to(torch.int64), ref[k]), k
+        assert torch.equal(got["reward"], ref["reward"])
+        env2 = make_env(N, autoreset=True, horizon=13, dtype_o=dtype_o, **cfg)
+        env2.set_jit(jit)
+        for t in range(5):
+            obs, r, term, trunc, info = env2.step(a[t])
+            assert obs.dtype == want_t                 # ... step() casts it
+            assert torch.equal(obs.to(torch.int64), ref["obs"][t])
+            assert torch.equal(info["final_obs"].to(torch.int64), ref["final_obs"][t])
+            assert torch.equal(r, ref["reward"][t])
+
+
+def test_step_buffers_rotate_and_match_unbuffered_step():
+    """step() writes into `step_buffers` rotating pre-marshalled output sets:
+    same values as the allocate-per-call path, and a returned tensor stays
+    valid for step_buffers - 1 further calls."""
+    cfg = dict(_BENCH_CFG)
+    N = 513
+    a = torch.randint(0, 8, (12, N), dtype=torch.int32, device="cuda",
+                      generator=torch.Generator("cuda").manual_seed(8))
+    fast = make_env(N, autoreset=True, horizon=7, step_buffers=3, **cfg)
+    slow = make_env(N, autoreset=True, horizon=7, step_buffers=0, **cfg)
+    kept = []
+    for t in range(12):
+        f, s = fast.step(a[t]), slow.step(a[t])
+        for x, y in zip(f[:4], s[:4]):
+            assert torch.equal(x, y)
+        assert torch.equal(f[4]["final_obs"], s[4]["final_obs"])
+        kept.append((f[0], s[0].clone()))
+        if t >= 2:  # the tensors of two calls ago are still intact
+            assert torch.equal(kept[t - 2][0], kept[t - 2][1])
+    assert fast.step(a[0].to(torch.int64))[0].shape == (N,)   # converted on the fly

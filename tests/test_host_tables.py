@@ -98,7 +98,7 @@ def test_struct_layouts_match_header_sizes():
     # sizes computed from the header's field lists (LP64)
     assert ctypes.sizeof(_lib.DiscreteGroup) == 10 * 4 + 5 * 8 + 7 * 8 + 3 * 8 + 2 * 4 + 3 * 8
     assert ctypes.sizeof(_lib.DiscreteState) == 8 + 5 * 8 + 2 * 4 + 3 * 8 + 2 * 4
-    assert ctypes.sizeof(_lib.DiscreteIO) == 9 * 8
+    assert ctypes.sizeof(_lib.DiscreteIO) == 9 * 8 + 2 * 4
     assert ctypes.sizeof(_lib.StepOpts) == 6 * 4 + 4 * 8
 
 
