@@ -74,6 +74,16 @@ __device__ __forceinline__ int obs_dtype_of(const RolloutParams& p) {
 #endif
 }
 
+// Ziggurat normals staged a window ahead (zig_fill) only when the launch
+// covers at least one window; shorter launches draw them chunk by chunk.
+__device__ __forceinline__ bool stage_of(const RolloutParams& p) {
+#ifdef MDPP_JIT
+  return MDPP_CFG_STAGE;
+#else
+  return p.T >= kZigWindow;
+#endif
+}
+
 // irrelevant_features: launch-wide (all groups agree, context.cu).  The
 // ahead-of-time FAST kernels never see it (discrete_launch.h routes such
 // launches to the generic variants), a specialised build gets a literal.
@@ -539,14 +549,22 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
     if (U == 1) {
       double z4[4] = {0, 0, 0, 0};
       uint32_t u4[4] = {0, 0, 0, 0}, r4[4] = {0, 0, 0, 0};
-      const uint32_t rej = philox_quad_draws<NORMAL>(
-          gid, step0 >> 2, p.rk, want_u, want_z, want_r, u4, z4, r4, v.zig_kw);
+      constexpr bool ZIG1 = NORMAL == MDPP_NORMAL_ZIGGURAT;
+      philox_quad_draws<NORMAL>(gid, step0 >> 2, p.rk, want_u, want_z && !ZIG1,
+                                want_r, u4, z4, r4, v.zig_kw);
       const int q4 = (int)(step0 & 3);
       w_tr[0] = q4 == 0 ? u4[0] : q4 == 1 ? u4[1] : q4 == 2 ? u4[2] : u4[3];
       double z = q4 == 0 ? z4[0] : q4 == 1 ? z4[1] : q4 == 2 ? z4[2] : z4[3];
       w_rs[0] = q4 == 0 ? r4[0] : q4 == 1 ? r4[1] : q4 == 2 ? r4[2] : r4[3];
-      if (NORMAL == MDPP_NORMAL_ZIGGURAT && ((rej >> q4) & 1u))
-        z = zig_slow(gid, step0, p.rk, reinterpret_cast<const uint8_t*>(v.zig_kw));
+      if (ZIG1 && want_z) {  // a single step: only the pair word that holds it
+        const uint64_t pr = step0 >> 1;
+        const U4 w = philox4x32_10_rk(gid, (uint32_t)pr, (uint32_t)(pr >> 32),
+                                      STREAM_ZIG, p.rk);
+        bool ok;
+        z = zig_first((step0 & 1) ? w.z : w.x, (step0 & 1) ? w.w : w.y, v.zig_kw, &ok);
+        if (!ok)
+          z = zig_slow(gid, step0, p.rk, reinterpret_cast<const uint8_t*>(v.zig_kw));
+      }
       if (!STAGED) n_rw[0] = __dmul_rn(v.r_std, z);
     } else {  // chunks start on a multiple-of-4 step (see the callers)
       uint32_t rej = 0;
@@ -850,18 +868,18 @@ struct ZigStage {
 
 __device__ __forceinline__ void zig_fill(const RolloutParams& p, const GroupView& v,
                                          const ZigStage& zst, uint32_t gid,
-                                         uint64_t g0,    // even global step
-                                         int n_steps) {  // steps the launch still needs
+                                         uint64_t g0) {  // even global step
   const int lane = threadIdx.x & 31;
   const uint8_t* zt = reinterpret_cast<const uint8_t*>(v.zig_kw);  // smem copy
   if (zst.rank == 0) *zst.qcnt = 0;
   __syncwarp(zst.amask);
   uint32_t rej = 0;
   const uint64_t pair0 = g0 >> 1;
-  // (a short launch -- or the last window of one -- only draws what it uses)
-  const int n_pairs = min(kZigWindow / 2, (n_steps + 1) >> 1);
+  // (always a whole window: a compile-time trip count measured 9 % faster than
+  // drawing only what the last window needs; launches shorter than a window
+  // do not stage at all, see stage_of)
 #pragma unroll 1
-  for (int hb = 0; hb < n_pairs; hb += kZigFillUnroll) {
+  for (int hb = 0; hb < kZigWindow / 2; hb += kZigFillUnroll) {
     uint32_t r8 = 0;
     double* zcol = zst.zs + 2 * hb * kBlock;
 #pragma unroll
@@ -939,24 +957,34 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
     __syncthreads();
     tab = smem_tab;
   }
-  // ziggurat fast-path table behind the ring and the tables
+  // ziggurat tables behind the ring and the group tables (SMEM builds; the
+  // others -- short launches, oversized tables -- read them from global memory)
   const uint4* zig_kw = nullptr;
   if (C::NORMAL == MDPP_NORMAL_ZIGGURAT && C::NOISE == MDPP_NOISE_PHILOX) {
-    uint4* dst = reinterpret_cast<uint4*>(smem_dyn + p.ring_smem_bytes +
-                                          (SMEM ? p.tab_smem_bytes : 0));
-    const uint4* src = reinterpret_cast<const uint4*>(p.zig);
-    for (int i = threadIdx.x; i < kZigBytes / 16; i += kBlock) dst[i] = src[i];
-    __syncthreads();
-    zig_kw = dst;
+    if (SMEM) {
+      uint4* dst = reinterpret_cast<uint4*>(smem_dyn + p.ring_smem_bytes +
+                                            p.tab_smem_bytes);
+      const uint4* src = reinterpret_cast<const uint4*>(p.zig);
+      for (int i = threadIdx.x; i < kZigBytes / 16; i += kBlock) dst[i] = src[i];
+      __syncthreads();
+      zig_kw = dst;
+    } else {
+      zig_kw = reinterpret_cast<const uint4*>(p.zig);
+    }
   }
   const GroupView v = make_view(C::SINGLE ? p.group0 : grp, tab, zig_kw);
+  // Everything above read immutable tables only, so under a programmatic
+  // dependent launch (discrete_launch.h, jit.cu) it overlapped the previous
+  // kernel of the stream; wait for that kernel before touching the env state,
+  // the actions, the device step counter or the outputs.  Returns at once in an
+  // ordinary launch.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int64_t local = (int64_t)me.chunk * kBlock + threadIdx.x;
   const bool active = local < grp.env_count;
   constexpr bool ZIG = C::NORMAL == MDPP_NORMAL_ZIGGURAT && C::NOISE == MDPP_NOISE_PHILOX;
   ZigStage zst;
-  if (ZIG) {
-    uint8_t* st = smem_dyn + p.ring_smem_bytes + (SMEM ? p.tab_smem_bytes : 0) +
-                  kZigBytes;
+  if (ZIG && SMEM) {
+    uint8_t* st = smem_dyn + p.ring_smem_bytes + p.tab_smem_bytes + kZigBytes;
     zst.zs = reinterpret_cast<double*>(st) + threadIdx.x;
     uint8_t* qb = st + kZigWindow * kBlock * 8 + (threadIdx.x >> 5) * kZigQueueBytes;
     zst.qcnt = reinterpret_cast<uint32_t*>(qb);
@@ -965,7 +993,8 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
     zst.rank = __popc(zst.amask & ((1u << (threadIdx.x & 31)) - 1u));
     zst.n_act = __popc(zst.amask);
   }
-  const bool staged = ZIG && v.has_rnoise;
+  const bool staged = ZIG && SMEM && v.has_rnoise && stage_of(p);
+  const bool stage_path = ZIG && SMEM && stage_of(p);  // (group-independent)
   int zs_t0 = -kZigWindow;  // local step at which the staged window starts
   const int64_t env = grp.env_begin + (active ? local : 0);
   const int64_t N = n_envs_of(p);
@@ -1034,7 +1063,7 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
       for (; t0 <= t_last; t0 += kChunk) {
         if (staged && t0 >= zs_t0 + kZigWindow) {
           zs_t0 = t0;
-          zig_fill(p, v, zst, gid, step_base + (uint64_t)t0, p.T - t0);
+          zig_fill(p, v, zst, gid, step_base + (uint64_t)t0);
         }
         int32_t act[kChunk], act_i[kChunk];
         const int tn = min(t0 + kChunk, t_last);
@@ -1044,18 +1073,25 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
           act_i[j] = act_next_i[j];
           load_action<C>(p, (int64_t)(tn + j) * N + env, act_next[j], act_next_i[j]);
         }
-        run_chunk_preloaded<C, kChunk, ZIG>(p, v, e, ring_smem, env, gid, step_base,
-                                            t0, act, act_i,
-                                            zst.zs + (t0 - zs_t0) * kBlock);
+        if (stage_path)
+          run_chunk_preloaded<C, kChunk, ZIG && SMEM>(p, v, e, ring_smem, env, gid,
+                                                      step_base, t0, act, act_i,
+                                                      zst.zs + (t0 - zs_t0) * kBlock);
+        else
+          run_chunk_preloaded<C, kChunk, false>(p, v, e, ring_smem, env, gid,
+                                                step_base, t0, act, act_i);
       }
     } else {
       for (; t0 + kChunk <= p.T; t0 += kChunk) {
         if (staged && t0 >= zs_t0 + kZigWindow) {
           zs_t0 = t0;
-          zig_fill(p, v, zst, gid, step_base + (uint64_t)t0, p.T - t0);
+          zig_fill(p, v, zst, gid, step_base + (uint64_t)t0);
         }
-        run_chunk<C, kChunk, ZIG>(p, v, e, ring_smem, env, gid, step_base, t0,
-                                  zst.zs + (t0 - zs_t0) * kBlock);
+        if (stage_path)
+          run_chunk<C, kChunk, ZIG && SMEM>(p, v, e, ring_smem, env, gid, step_base, t0,
+                                            zst.zs + (t0 - zs_t0) * kBlock);
+        else
+          run_chunk<C, kChunk, false>(p, v, e, ring_smem, env, gid, step_base, t0);
       }
     }
     // remainder: a half chunk first (t0 is still quad-aligned here; single

@@ -16,11 +16,25 @@ inline int launch_one(mdpp_ctx* ctx, RolloutParams& p, int smem_tab,
   p.tab_smem_bytes = C::SMEM ? smem_tab : 0;
   const bool zig = C::NORMAL == MDPP_NORMAL_ZIGGURAT && C::NOISE == MDPP_NOISE_PHILOX;
   const int smem = p.ring_smem_bytes + p.tab_smem_bytes +
-                   (zig ? kZigBytes + zig_stage_bytes(kBlock) : 0);
+                   (zig && C::SMEM ? kZigBytes + zig_stage_bytes(kBlock) : 0);
   if (smem > 48 * 1024 - 512)
     MDPP_CUDA(ctx, cudaFuncSetAttribute(
                        kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<(unsigned)ctx->n_ctas, kBlock, smem, stream>>>(p);
+  // programmatic dependent launch for step()-granularity launches: the table
+  // staging overlaps the tail of the previous kernel of the stream
+  // (rollout_body waits with griddepcontrol.wait before it touches anything
+  // mutable).  Long rollouts gain nothing and measured 2-3 % slower with it.
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctx->n_ctas);
+  cfg.blockDim = dim3(kBlock);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.T < kChunk ? 1 : 0;
+  MDPP_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, p));
   MDPP_CUDA(ctx, cudaGetLastError());
   return MDPP_OK;
 }
@@ -36,8 +50,8 @@ inline int launch_rollout(mdpp_ctx* ctx, RolloutParams& p, cudaStream_t stream) 
   const bool ring_ok = ctx->max_delay <= kRingSmemMaxDelay;
   const int ring_bytes = ring_ok ? ctx->max_delay * kBlock * 8 : 0;
   const bool smem_ok =
-      smem_tab + ring_bytes + kZigBytes + zig_stage_bytes(kBlock) <=
-      ctx->max_smem_optin - 1024;
+      p.T >= smem_min_steps() && smem_tab + ring_bytes + kZigBytes + zig_stage_bytes(kBlock) <=
+                           ctx->max_smem_optin - 1024;
   const bool fast_io = p.io.actions && p.io.obs && p.io.reward &&
                        p.io.terminated && p.io.truncated && !p.io.final_obs &&
                        !p.st.history && !p.irr;  // (FAST kernels: no sub-MDP)

@@ -60,6 +60,7 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
 struct ContinuousParams;
 int jit_try_continuous(mdpp_ctx* ctx, ContinuousParams& p, cudaStream_t stream);
 void jit_release(mdpp_ctx* ctx);
+int smem_min_steps();  // MDPP_SMEM_MIN_T (default 1): shorter launches skip the smem staging
 int fail(mdpp_ctx* ctx, int code, const std::string& msg);
 int cuda_fail(mdpp_ctx* ctx, cudaError_t e, const char* what);
 }  // namespace mdpp

@@ -12,6 +12,7 @@
 // libnvrtc / libcuda are dlopen()ed lazily so the library still loads on
 // machines without a driver (the CPU-side ABI tests).  If either is missing,
 // or MDPP_JIT=0 is set, the caller falls back to the AOT kernels.
+#include <cuda.h>  // driver API types only; the symbols are dlsym()ed
 #include <dlfcn.h>
 
 #include <cmath>
@@ -29,10 +30,6 @@ namespace {
 
 typedef int nvrtcResult;
 typedef struct _nvrtcProgram* nvrtcProgram;
-typedef int CUresult;
-typedef struct CUmod_st* CUmodule;
-typedef struct CUfunc_st* CUfunction;
-typedef struct CUstream_st* CUstream;
 
 struct Api {
   bool tried = false, ok = false;
@@ -52,6 +49,7 @@ struct Api {
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned,
                            unsigned, unsigned, unsigned, CUstream, void**,
                            void**);
+  CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**);
 };
 
 Api& api() {
@@ -82,6 +80,7 @@ Api& api() {
   LOAD(drv, ModuleGetFunction, "cuModuleGetFunction")
   LOAD(drv, FuncSetAttribute, "cuFuncSetAttribute")
   LOAD(drv, LaunchKernel, "cuLaunchKernel")
+  LOAD(drv, LaunchKernelEx, "cuLaunchKernelEx")
 #undef LOAD
   a.ok = true;
   return a;
@@ -98,7 +97,8 @@ std::string hexf(double x) {
 std::vector<std::string> defines_for(const std::vector<DiscreteGroupDev>& groups,
                                      const RolloutParams& p, int noise,
                                      int normal, bool fast, bool ring_smem,
-                                     int cdf_log2_tpl) {
+                                     int cdf_log2_tpl, bool smem = true,
+                                     bool stage = true) {
   auto D = [](const char* k, const std::string& v) {
     return std::string("-DMDPP_") + k + "=" + v;
   };
@@ -153,6 +153,8 @@ std::vector<std::string> defines_for(const std::vector<DiscreteGroupDev>& groups
   d.push_back(D("CFG_NORMAL", I(normal)));
   d.push_back(D("CFG_FAST", fast ? "true" : "false"));
   d.push_back(D("CFG_RING", ring_smem ? "true" : "false"));
+  d.push_back(D("CFG_SMEM", smem ? "true" : "false"));
+  d.push_back(D("CFG_STAGE", stage ? "true" : "false"));
   d.push_back(D("CFG_CDF", I(cdf_log2_tpl)));
   d.push_back(D("CFG_SINGLE", groups.size() == 1 ? "true" : "false"));
   return d;
@@ -160,7 +162,7 @@ std::vector<std::string> defines_for(const std::vector<DiscreteGroupDev>& groups
 
 const char* kEntrySource = R"SRC(
 #include "discrete_kernels.cuh"
-using JitCfg = mdpp::Cfg<MDPP_CFG_NOISE, MDPP_CFG_NORMAL, true, MDPP_CFG_RING,
+using JitCfg = mdpp::Cfg<MDPP_CFG_NOISE, MDPP_CFG_NORMAL, MDPP_CFG_SMEM, MDPP_CFG_RING,
                          MDPP_CFG_FAST, MDPP_CFG_CDF, MDPP_CFG_SINGLE,
                          MDPP_CFG_RING_REGS>;
 extern "C" __global__ void __launch_bounds__(mdpp::kBlock, mdpp::kMinBlocksPerSM)
@@ -264,7 +266,7 @@ void* get_function(mdpp_ctx* ctx, const char* entry_source,
 }
 
 int launch(mdpp_ctx* ctx, void* fn, unsigned grid, unsigned block, int smem,
-           cudaStream_t stream, void* param) {
+           cudaStream_t stream, void* param, bool pdl = false) {
   Api& a = api();
   if (smem > 48 * 1024 - 512) {
     // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8
@@ -272,8 +274,22 @@ int launch(mdpp_ctx* ctx, void* fn, unsigned grid, unsigned block, int smem,
       return fail(ctx, MDPP_ECUDA, "cuFuncSetAttribute(max dynamic smem) failed");
   }
   void* args[] = {param};
-  CUresult rc = a.LaunchKernel((CUfunction)fn, grid, 1, 1, block, 1, 1,
-                               (unsigned)smem, (CUstream)stream, args, nullptr);
+  // programmatic dependent launch: the kernel may start while the previous
+  // kernel of the stream drains; everything it does before its
+  // griddepcontrol.wait touches only immutable tables (rollout_body)
+  CUlaunchAttribute attr;
+  std::memset(&attr, 0, sizeof attr);
+  attr.id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+  attr.value.programmaticStreamSerializationAllowed = 1;
+  CUlaunchConfig cfg;
+  std::memset(&cfg, 0, sizeof cfg);
+  cfg.gridDimX = grid; cfg.gridDimY = 1; cfg.gridDimZ = 1;
+  cfg.blockDimX = block; cfg.blockDimY = 1; cfg.blockDimZ = 1;
+  cfg.sharedMemBytes = (unsigned)smem;
+  cfg.hStream = (CUstream)stream;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  CUresult rc = a.LaunchKernelEx(&cfg, (CUfunction)fn, args, nullptr);
   if (rc != 0)
     return fail(ctx, MDPP_ECUDA, "cuLaunchKernel(jit) failed: " + std::to_string(rc));
   ctx->jit_last_used = 1;
@@ -350,6 +366,14 @@ int jit_try_continuous(mdpp_ctx* ctx, ContinuousParams& p, cudaStream_t stream) 
   return launch(ctx, fn, grid, kCBlock, 0, stream, &p);
 }
 
+int smem_min_steps() {
+  static const int v = [] {
+    const char* e = std::getenv("MDPP_SMEM_MIN_T");
+    return e ? std::atoi(e) : 1;
+  }();
+  return v;
+}
+
 int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
                     int normal_mode, cudaStream_t stream) {
   ctx->jit_last_used = 0;
@@ -377,7 +401,12 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
   // everything the -D list depends on besides the (versioned) group tables
   const long long sig[10] = {ctx->d_groups_version, noise_mode, normal_mode, fast,
                              (long long)p.st.n_envs, p.autoreset, p.horizon, p.irr,
-                             p.io.obs_dtype, 0};
+                             p.io.obs_dtype,
+                             (p.T >= smem_min_steps()) + 2 * (p.T >= kZigWindow)};
+  // tables staged in shared memory (always, unless MDPP_SMEM_MIN_T says that
+  // launches shorter than that read them from global memory: measured slower,
+  // the staging overlaps the previous kernel under programmatic launch)
+  const bool smem = p.T >= smem_min_steps();
   void* fn = nullptr;
   if (std::memcmp(sig, ctx->jit_sig_discrete, sizeof sig) == 0) {
     fn = ctx->jit_fn_discrete;
@@ -386,7 +415,8 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
     for (auto& g : groups)
       if (g.cdf_log2 != groups[0].cdf_log2) cdf_tpl = -1;
     std::vector<std::string> defs =
-        defines_for(groups, p, noise_mode, normal_mode, fast, true, cdf_tpl);
+        defines_for(groups, p, noise_mode, normal_mode, fast, true, cdf_tpl, smem,
+                    p.T >= kZigWindow);
     if (const char* ch = std::getenv("MDPP_JIT_CHUNK"))  // tuning knob (4/8/16)
       defs.push_back(std::string("-DMDPP_JIT_CHUNK=") + ch);
     if (const char* mb = std::getenv("MDPP_JIT_MINBLOCKS"))  // tuning knob
@@ -408,9 +438,10 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
   }
   if (!fn) return 0;
   p.ring_smem_bytes = ring_bytes;
-  p.tab_smem_bytes = ctx->max_group_blob;
+  p.tab_smem_bytes = smem ? ctx->max_group_blob : 0;
   return launch(ctx, fn, (unsigned)ctx->n_ctas, kBlock,
-                ring_bytes + ctx->max_group_blob + zig_bytes, stream, &p);
+                ring_bytes + (smem ? ctx->max_group_blob + zig_bytes : 0), stream, &p,
+                /*pdl=*/p.T < kChunk);
 }
 
 void jit_release(mdpp_ctx* ctx) {

@@ -1,5 +1,3 @@
 python tools/time_one.py fp64
-MDPP_JIT_EXTRA="-DMDPP_ZIG_FILL_UNROLL=8" python tools/time_one.py fp64
-MDPP_JIT_EXTRA="-DMDPP_ZIG_FILL_UNROLL=2" python tools/time_one.py fp64
-MDPP_JIT_EXTRA="-DMDPP_ZIG_FILL_UNROLL=16" python tools/time_one.py fp64
-python tools/time_one.py fast
+python tools/time_one.py fp64 1048576 100 5
+python tools/time_one.py fast 1048576 100 5

@@ -9,7 +9,7 @@ OUT=${1:-/tmp/sass}; shift || true
 mkdir -p "$OUT"
 cat > "$OUT/entry.cu" <<'SRC'
 #include "discrete_kernels.cuh"
-using JitCfg = mdpp::Cfg<MDPP_CFG_NOISE, MDPP_CFG_NORMAL, true, MDPP_CFG_RING,
+using JitCfg = mdpp::Cfg<MDPP_CFG_NOISE, MDPP_CFG_NORMAL, MDPP_CFG_SMEM, MDPP_CFG_RING,
                          MDPP_CFG_FAST, MDPP_CFG_CDF, MDPP_CFG_SINGLE,
                          MDPP_CFG_RING_REGS>;
 extern "C" __global__ void __launch_bounds__(mdpp::kBlock, mdpp::kMinBlocksPerSM)
@@ -24,7 +24,7 @@ DEFS="-DMDPP_JIT -DMDPP_S=8 -DMDPP_A=8 -DMDPP_L=3 -DMDPP_DELAY=2 -DMDPP_EVERY_N=
  -DMDPP_PN_T=429496730ull -DMDPP_PN_M=2348810239u -DMDPP_PN_SHIFT=25 -DMDPP_CFG_RING_REGS=2
  -DMDPP_N_ENVS=65536ll -DMDPP_AUTORESET=1 -DMDPP_HORIZON=100 -DMDPP_CFG_NOISE=2
  -DMDPP_CFG_NORMAL=${NORMAL:-1} -DMDPP_CFG_FAST=true -DMDPP_CFG_RING=true -DMDPP_CFG_CDF=3
- -DMDPP_CFG_SINGLE=true -DMDPP_IRR=0 -DMDPP_OBS_DTYPE=0"
+ -DMDPP_CFG_SINGLE=true -DMDPP_CFG_SMEM=${SMEM:-true} -DMDPP_CFG_STAGE=${STAGE:-true} -DMDPP_IRR=0 -DMDPP_OBS_DTYPE=0"
 nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xptxas -v \
   -I mdp_playground_b200/csrc -I include $DEFS "$@" -cubin -o "$OUT/jit.cubin" "$OUT/entry.cu"
 cuobjdump -sass "$OUT/jit.cubin" > "$OUT/jit.sass"
