@@ -276,6 +276,14 @@ typedef struct mdpp_continuous_config {
   double target_point[MDPP_MAX_DIM];          /* [n_relevant]                */
   double term_low[MDPP_MAX_TERM_BOXES * MDPP_MAX_DIM];   /* [box][relevant], */
   double term_high[MDPP_MAX_TERM_BOXES * MDPP_MAX_DIM];  /* cast to dtype_s  */
+  /* per-dimension inertia (rl_toy_env.py:519-537, `action / self.inertia` at
+   * :1654): 0 = the scalar `inertia` above; 1 = `inertia_vec`, an array of
+   * dtype_s (the division stays in dtype_s); 2 = `inertia_vec` given as a list
+   * / float64 array: numpy promotes the quotient, so the top derivative and
+   * every Taylor term that reads it are float64                             */
+  int32_t inertia_mode;
+  int32_t reserved_cfg;
+  double inertia_vec[MDPP_MAX_DIM];
 } mdpp_continuous_config;
 
 #ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
@@ -290,7 +298,9 @@ typedef struct mdpp_continuous_state {
   int32_t* t_episode;  /* [N]                                                */
   uint32_t* episode;   /* [N]                                                */
   uint8_t* reached;    /* [N] sticky reached_terminal (:1725)                */
-  void* ring;          /* real [delay][N] reward FIFO, or NULL               */
+  void* ring;          /* real [delay][N] reward FIFO, or NULL; DOUBLE when
+                          real = float, target_is_f64 and dense (the reward
+                          is a python float there, rl_toy_env.py:1915-1923) */
   double* stats;       /* [stats_slots][MDPP_N_STATS], summed over slots      */
   int32_t stats_slots; /* >= 1 (0 reads as 1), see mdpp_discrete_state        */
   int32_t reserved1;

@@ -107,6 +107,8 @@ class ContinuousConfig(C.Structure):
         ("target_point", C.c_double * MDPP_MAX_DIM),
         ("term_low", C.c_double * (MDPP_MAX_TERM_BOXES * MDPP_MAX_DIM)),
         ("term_high", C.c_double * (MDPP_MAX_TERM_BOXES * MDPP_MAX_DIM)),
+        ("inertia_mode", C.c_int32), ("reserved_cfg", C.c_int32),
+        ("inertia_vec", C.c_double * MDPP_MAX_DIM),
     ]
 
 

@@ -291,6 +291,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   const R amax = (R)MDPP_C_F64(AMAX, p.cfg.action_space_max);
   const R smax = (R)MDPP_C_F64(SMAX, p.cfg.state_space_max);
   const R inertia = (R)MDPP_C_F64(INERTIA, p.cfg.inertia);
+  const int IMODE = MDPP_C_CONST(IMODE, p.cfg.inertia_mode);  // per-dimension inertia
   const double radius64 = MDPP_C_F64(RADIUS, p.cfg.target_radius);
   const R radius_r = (R)radius64;
   const double alw = MDPP_C_F64(ALW, p.cfg.action_loss_weight);
@@ -381,9 +382,23 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
 
     // ---- transition -----------------------------------------------------
     if (in_range) {
+      // top derivative = action / inertia (:1654).  A list / float64-array
+      // inertia (IMODE 2, fp32 env) promotes it to float64: kept in top64 for
+      // the Taylor terms that read it, stored rounded to dtype_s
+      double top64[MDPP_MAX_DIM];
+      const bool TOP64 = IMODE == 2 && sizeof(R) == 4;
 #pragma unroll
       for (int d = 0; d < MDPP_MAX_DIM; ++d)
-        if (d < D) sd[ORDER][d] = div_inertia(a[d], inertia);
+        if (d < D) {
+          if (IMODE == 0) {
+            sd[ORDER][d] = div_inertia(a[d], inertia);
+          } else if (!TOP64) {
+            sd[ORDER][d] = O::div(a[d], (R)p.cfg.inertia_vec[d]);
+          } else {
+            top64[d] = __ddiv_rn((double)a[d], p.cfg.inertia_vec[d]);
+            sd[ORDER][d] = (R)top64[d];
+          }
+        }
 #pragma unroll
       for (int i = 0; i < MDPP_MAX_ORDER; ++i)
 #pragma unroll
@@ -395,6 +410,13 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
 #pragma unroll
             for (int d = 0; d < MDPP_MAX_DIM; ++d)
               if (d < D) {
+                if (TOP64 && i + j + 1 == ORDER) {
+                  // float64 array * python float / float64, added into fp32
+                  sd[i][d] = (R)__dadd_rn(
+                      (double)sd[i][d],
+                      __ddiv_rn(__dmul_rn(top64[d], tu_pow[j]), fact));
+                  continue;
+                }
                 const R term = O::mul(sd[i + j + 1][d], tu);
                 if (sizeof(R) == 4 && j <= 1) {
                   // f32(f64(x) + f64(t) / {1,2}): the quotient is exact and a
@@ -499,12 +521,24 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
       else { rr = O::add((R)rd, -loss); is_real = true; }
     }
     if (DELAY > 0) {
-      R* slot = ring + (int64_t)ring_pos * N + env;
       const bool have = tl > DELAY;
-      const R delayed = have ? *slot : (R)0;
-      *slot = is_real ? rr : (R)rd;
-      if (have) { rr = delayed; is_real = true; }
-      else { rd = 0.0; is_real = false; }  // zero-initialised python floats
+      if (sizeof(R) == 4 && TARGET64 && DENSE) {
+        // the reward is a python float here (float64 norms), and the
+        // reference's reward_buffer keeps it one: the FIFO holds doubles and
+        // the tail below stays on the float64 path (the caller allocates the
+        // ring as float64 for this configuration)
+        double* slot = reinterpret_cast<double*>(p.st.ring) + (int64_t)ring_pos * N + env;
+        const double delayed = have ? *slot : 0.0;
+        *slot = rd;
+        rd = delayed;
+        is_real = false;
+      } else {
+        R* slot = ring + (int64_t)ring_pos * N + env;
+        const R delayed = have ? *slot : (R)0;
+        *slot = is_real ? rr : (R)rd;
+        if (have) { rr = delayed; is_real = true; }
+        else { rd = 0.0; is_real = false; }  // zero-initialised python floats
+      }
       ring_pos = (ring_pos + 1 == DELAY) ? 0 : ring_pos + 1;
     }
     if (phase != 0) { rd = 0.0; is_real = false; }

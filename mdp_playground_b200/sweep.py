@@ -188,8 +188,19 @@ class Sweep:
             st = {k: np.array([float(np.asarray(p[k]).reshape(-1)[0]) for p in per])
                   for k in ("episodes", "transitions", "noisy_transitions")}
         ep = np.maximum(st["episodes"], 1)
+        returned = self._returned
+        if reduce:  # the reward sums are rank-local like the counters
+            import torch
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dev = self.env.device if self.kind == "discrete" else self.envs[0].device
+                use_cuda = dist.get_backend() == "nccl"
+                t = torch.as_tensor(returned, dtype=torch.float64,
+                                    device=dev if use_cuda else "cpu").clone()
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                returned = t.cpu().numpy()
         return {"episodes": st["episodes"], "transitions": st["transitions"],
-                "episode_reward_mean": self._returned / ep,
+                "episode_reward_mean": returned / ep,
                 "episode_len_mean": st["transitions"] / ep,
                 "noisy_transitions": st["noisy_transitions"]}
 

@@ -43,7 +43,7 @@ class VectorRLToyEnv:
                  horizon=0, env_id_offset=0, philox_seed=None,
                  normal_precision="fp64", track_history=None,
                  config_groups=None, group_sizes=None, shard=(0, 1),
-                 step_buffers=2, **config):
+                 step_buffers=2, strict=True, **config):
         """config_groups: optional list of config dicts (a heterogeneous
         sweep: each entry is merged over **config); envs are laid out
         group-major, `group_sizes` per group (default: as equal as possible).
@@ -54,6 +54,11 @@ class VectorRLToyEnv:
         further step() calls; 0 = allocate fresh tensors on every call).
         A 65 536-env step is a ~5 us kernel: allocating and marshalling five
         tensors per call would cost several times that."""
+        # strict=False reproduces what the reference does with actions of a
+        # dtype its action space does not contain (rl_toy_env.py:1640,
+        # :1671-1679, :1730-1733) instead of raising: continuous envs freeze
+        # the state for that step, grid envs apply a no-op
+        self.strict = bool(strict)
         self._step_buffers = int(step_buffers)
         self._step_sets = None
         self._step_flip = 0
@@ -117,6 +122,12 @@ class VectorRLToyEnv:
         self._ctx = C.c_void_p()
         _lib.check(self._lib, None,
                    self._lib.mdpp_create(self.device.index, C.byref(self._ctx)))
+        if self.spec.kind != "discrete" and self._shard[1] > 1:
+            # the discrete path derives global Philox ids from `shard` per group
+            # (sharding.group_id_bases); continuous / grid envs are one group:
+            # rank r owns the ids [offset + r N, offset + (r + 1) N)
+            self.env_id_offset += self._shard[0] * self.num_envs
+        self._seed_epoch = 0
         if self.spec.kind == "discrete":
             self._init_discrete()
         elif self.spec.kind == "grid":
@@ -156,6 +167,21 @@ class VectorRLToyEnv:
 
     def _check(self, rc):
         _lib.check(self._lib, self._ctx, rc)
+
+    def _reseed(self, seed, mask=None):
+        """reset(seed=s) / seed(s) in Philox mode: re-key the streams AND
+        rewind what they are indexed by (global step, episode counters of the
+        envs being reset), so that the same seed gives the same trajectory --
+        the gym reset(seed) contract the reference meets by re-seeding
+        `_np_random`.  CUDA graphs captured before keep the old key baked into
+        their kernel parameters: they refuse to replay (make_graphed_step)."""
+        self.philox_seed = int(seed) & (2**64 - 1)
+        self._step_index = 0
+        if mask is None:
+            self._episode.zero_()
+        else:
+            self._episode.masked_fill_(mask.to(torch.bool), 0)
+        self._seed_epoch += 1
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -356,6 +382,7 @@ class VectorRLToyEnv:
         init = options.get("init_state")
         if init is not None:
             init = torch.as_tensor(init, device=dev).to(torch.int32).contiguous()
+            self._check_state_range(init)
         reset_u = options.get("reset_u")
         if self.noise == "numpy" and init is None:
             if seed is not None:
@@ -373,7 +400,7 @@ class VectorRLToyEnv:
         elif (seed is not None and self.noise == "philox"
               and not options.get("_ctor")):
             # re-keying the counter-based streams is the analogue of re-seeding
-            self.philox_seed = int(seed) & (2**64 - 1)
+            self._reseed(seed, mask)
         if reset_u is not None:
             reset_u = torch.as_tensor(reset_u, dtype=torch.float64,
                                       device=dev).contiguous()
@@ -396,6 +423,19 @@ class VectorRLToyEnv:
         self.curr_obs = self._observe(obs, options.get("image_params"), reset=True,
                                       ctor=bool(options.get("_ctor")))
         return self.curr_obs, {}
+
+    def _check_state_range(self, states):
+        """Caller-supplied discrete states index the tables on the device:
+        reject anything outside [0, S) (rows (relevant, irrelevant) with
+        irrelevant_features) instead of reading out of bounds."""
+        hi = [max(t.n_states for t in self.group_tables)]
+        if self._irr:
+            hi.append(max(t.n_states_irr for t in self.group_tables))
+        st = states.reshape(self.num_envs, -1)
+        for k, n in enumerate(hi):
+            col = st[:, k]
+            if bool(((col < 0) | (col >= n)).any()):
+                raise ValueError(f"state out of range [0, {n}) in column {k}")
 
     def _observe(self, state, image_params=None, reset=False, ctor=False):
         """Underlying state -> observation (identity, dtype_o cast, or the
@@ -744,11 +784,12 @@ class VectorRLToyEnv:
         if not (torch.is_tensor(actions) and actions.dtype == self._step_adt
                 and actions.is_cuda and actions.is_contiguous()):
             actions = torch.as_tensor(actions, device=self.device)
-            if self.spec.kind == "continuous" and actions.dtype != self._real:
-                raise TypeError(f"actions must be {self._real}, got {actions.dtype}")
-            if self.spec.kind == "grid" and actions.dtype.is_floating_point:
-                raise TypeError(f"grid actions must be integers, got {actions.dtype}")
-            actions = actions.to(self._step_adt).contiguous()
+            if self.spec.kind == "continuous":
+                actions = self._continuous_actions(actions)
+            elif self.spec.kind == "grid":
+                actions = self._grid_actions(actions)
+            else:
+                actions = actions.to(self._step_adt).contiguous()
         if actions.numel() != self._step_numel:
             raise AssertionError((tuple(actions.shape), self._step_arow))
         flip = self._step_flip
@@ -929,8 +970,14 @@ class VectorRLToyEnv:
         self._step_index = host_index
         self._step_ctr.fill_(host_index)
         mirror = [host_index]
+        epoch = self._seed_epoch
 
         def step_fn(actions):
+            if epoch != self._seed_epoch:
+                raise RuntimeError(
+                    "the environment was re-seeded after this graphed step was "
+                    "captured (its Philox key is baked into the graph): call "
+                    "make_graphed_step() again")
             if mirror[0] != self._step_index:  # eager calls happened in between
                 self._step_ctr.fill_(self._step_index)
             if not (torch.is_tensor(actions)
@@ -1033,8 +1080,6 @@ class VectorRLToyEnv:
         np_dt = np.dtype(sp.dtype_s)
         if np_dt not in (np.dtype(np.float32), np.dtype(np.float64)):
             raise NotImplementedError("continuous dtype_s must be float32/64")
-        if not np.isscalar(sp.inertia):
-            raise NotImplementedError("per-dimension inertia is not supported")
         self._real = torch.float64 if np_dt == np.float64 else torch.float32
         self._np_real = np_dt.type
         self.observation_space = BoxSpace(
@@ -1055,7 +1100,19 @@ class VectorRLToyEnv:
         c.image_mode = int(sp.image_representations)
         c.target_is_f64 = int("target_point" not in self.config)
         c.is_f64 = int(np_dt == np.float64)
-        c.inertia, c.time_unit = float(sp.inertia), float(sp.time_unit)
+        # inertia: float, or one value per dimension (rl_toy_env.py:519-537); a
+        # list / float64 array promotes `action / inertia` to float64 (:1654)
+        if np.ndim(sp.inertia) == 0:
+            c.inertia, c.inertia_mode = float(sp.inertia), 0
+        else:
+            iv = np.asarray(sp.inertia)
+            if iv.shape != (D,):
+                raise ValueError(f"inertia must be a scalar or have shape ({D},)")
+            c.inertia = 1.0
+            c.inertia_mode = 1 if iv.dtype == np_dt else 2
+            for k in range(D):
+                c.inertia_vec[k] = float(iv[k])
+        c.time_unit = float(sp.time_unit)
         c.state_space_max = float(sp.state_space_max)
         c.action_space_max = float(sp.action_space_max)
         c.target_radius = float(sp.target_radius)
@@ -1094,7 +1151,11 @@ class VectorRLToyEnv:
         self._t = torch.zeros(N, dtype=torch.int32, device=dev)
         self._episode = torch.zeros(N, dtype=torch.int32, device=dev)
         self._reached = torch.zeros(N, dtype=torch.uint8, device=dev)
-        self._ring = torch.zeros((sp.delay, N), dtype=real, device=dev) \
+        # (fp32 env + default float64 target_point + dense reward: the reward is
+        # a python float all the way through the reference's reward_buffer)
+        ring_dt = torch.float64 if (real == torch.float32 and c.target_is_f64
+                                    and c.dense) else real
+        self._ring = torch.zeros((sp.delay, N), dtype=ring_dt, device=dev) \
             if sp.delay > 0 else None
         self._stats = torch.zeros((_lib.STATS_SLOTS, 1, _lib.MDPP_N_STATS),
                                   dtype=torch.float64, device=dev)
@@ -1150,7 +1211,7 @@ class VectorRLToyEnv:
                     init[i] = self._host_box_sample(self._rng_F[i])
         elif (seed is not None and self.noise == "philox"
               and not options.get("_ctor")):
-            self.philox_seed = int(seed) & (2**64 - 1)
+            self._reseed(seed, mask)
         if init is not None:
             init = torch.as_tensor(init, device=dev).to(self._real).reshape(
                 N, D).contiguous()
@@ -1165,17 +1226,46 @@ class VectorRLToyEnv:
                                       ctor=bool(options.get("_ctor")))
         return self.curr_obs, {}
 
+    def _continuous_actions(self, actions):
+        """Box.contains needs np.can_cast(action dtype, dtype_s): anything else
+        (float64 actions for a float32 env, int32 / int64) is 'not in the
+        action space' and the reference freezes the state for that step
+        (:1640, :1671-1679).  strict (default): raise instead."""
+        real = self._real
+        if actions.dtype == real:
+            return actions.contiguous()
+        np_from = np.dtype(str(actions.dtype).replace("torch.", ""))
+        if np.can_cast(np_from, np.dtype(self.spec.dtype_s)):
+            return actions.to(real).contiguous()
+        if self.strict:
+            raise TypeError(f"actions must be {real}, got {actions.dtype} "
+                            "(strict=False freezes the state like the reference)")
+        if self.spec.action_loss_weight:
+            raise NotImplementedError(
+                "strict=False with action_loss_weight: the reference still "
+                "charges the norm of the rejected action")
+        # NaN fails every bound test in the kernel: frozen state, derivatives kept
+        return torch.full(actions.shape, float("nan"), dtype=real,
+                          device=actions.device)
+
+    def _grid_actions(self, actions):
+        """Non-integer grid actions: the reference applies a no-op and still
+        tests the target (:1730-1733).  strict (default): raise instead."""
+        if not actions.dtype.is_floating_point:
+            return actions.to(torch.int64).contiguous()
+        if self.strict:
+            raise TypeError(f"grid actions must be integers, got {actions.dtype} "
+                            "(strict=False applies a no-op like the reference)")
+        noop = torch.zeros(actions.shape, dtype=torch.int64, device=actions.device)
+        noop[..., 0] = 2  # out of range: the kernel's no-op that tests the target
+        return noop
+
     def _rollout_continuous(self, n_steps, actions, replay, out, want_final_obs):
         T, N, dev = int(n_steps), self.num_envs, self.device
         D, real = self.spec.state_space_dim, self._real
         if actions is None:
             raise ValueError("continuous rollout needs an actions tensor [T,N,D]")
-        actions = torch.as_tensor(actions, device=dev)
-        if actions.dtype != real:
-            # the reference freezes the state (and warns) on a dtype that does
-            # not cast safely to dtype_s (:1640); failing loudly is safer here
-            raise TypeError(f"actions must be {real}, got {actions.dtype}")
-        actions = actions.contiguous()
+        actions = self._continuous_actions(torch.as_tensor(actions, device=dev))
         assert actions.shape == (T, N, D), (actions.shape, (T, N, D))
         if out is None:
             out = {
@@ -1310,7 +1400,7 @@ class VectorRLToyEnv:
                         low=np.zeros(nd), high=hi, size=(nd,))).astype(np.int64)
         elif (seed is not None and self.noise == "philox"
               and not options.get("_ctor")):
-            self.philox_seed = int(seed) & (2**64 - 1)
+            self._reseed(seed, mask)
         if init is not None:
             init = torch.as_tensor(init, device=dev).to(torch.int64).reshape(
                 N, nd).contiguous()
@@ -1356,12 +1446,7 @@ class VectorRLToyEnv:
         T, N, dev, nd = int(n_steps), self.num_envs, self.device, self._nd
         if actions is None:
             raise ValueError("grid rollout needs an actions tensor [T, N, n_dims]")
-        actions = torch.as_tensor(actions, device=dev)
-        if actions.dtype.is_floating_point:
-            # the reference applies a no-op (and warns) for non-int64 actions
-            # (:1730-1733); a float tensor is most likely a caller bug
-            raise TypeError(f"grid actions must be integers, got {actions.dtype}")
-        actions = actions.to(torch.int64).contiguous()
+        actions = self._grid_actions(torch.as_tensor(actions, device=dev))
         assert actions.shape == (T, N, nd), (actions.shape, (T, N, nd))
         if out is None:
             out = {
@@ -1481,6 +1566,9 @@ class VectorRLToyEnv:
         if self._irr:
             full = torch.as_tensor(state["curr_state"] if isinstance(state, dict)
                                    else state, device=dev).reshape(N, 2)
+            n_irr = max(t.n_states_irr for t in self.group_tables)
+            if bool(((full[:, 1] < 0) | (full[:, 1] >= n_irr)).any()):
+                raise ValueError(f"irrelevant state out of range [0, {n_irr})")
             self._cur_irr.copy_(full[:, 1].to(torch.int32))
             if not isinstance(state, dict):
                 state = full[:, 0]
@@ -1493,6 +1581,9 @@ class VectorRLToyEnv:
         valid = ~torch.isnan(aug)
         n_valid = valid.to(torch.int32).sum(dim=1)          # trailing entries
         states = torch.nan_to_num(aug, nan=0.0).to(torch.int64)
+        n_rel = max(t.n_states for t in self.group_tables)
+        if bool(((states < 0) | (states >= n_rel)).any()):
+            raise ValueError(f"augmented_state entry out of range [0, {n_rel})")
         self._cur.copy_(states[:, -1].to(torch.int32))
         bits = max(1, int(np.ceil(np.log2(max(self.tables.n_states, 2)))))
         key = torch.zeros(N, dtype=torch.int64, device=dev)
@@ -1518,7 +1609,7 @@ class VectorRLToyEnv:
             for i in range(self.num_envs):
                 self._rng_E[i], _ = np_random(None if seed is None else seed + i)
         elif seed is not None:
-            self.philox_seed = int(seed) & (2**64 - 1)
+            self._reseed(seed)
         return seed
 
     def episode_stats(self, reduce=False):

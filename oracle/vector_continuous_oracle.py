@@ -40,6 +40,7 @@ class VectorContinuousOracle:
         self.episode = np.zeros(self.N, dtype=np.int64)
         self.reached = np.zeros(self.N, dtype=bool)
         self.ring = np.zeros((max(self.delay, 1), self.N), dtype=self.R)
+        self.ring64 = np.zeros((max(self.delay, 1), self.N), dtype=np.float64)
         self.has_pnoise = e.has_transition_noise and e.transition_noise is not None
         self.has_rnoise = e.has_reward_noise and e.reward_noise_std is not None
 
@@ -128,13 +129,26 @@ class VectorContinuousOracle:
             in_range = np.all((a >= -amax) & (a <= amax), axis=1)
             dist_old = self._dist(self.em)
             sd = self.sd.copy()
-            sd[n] = (a / R(e.inertia)).astype(R)
+            # a / inertia (:1654): scalar or dtype_s vector -> dtype_s division;
+            # a list / float64 vector -> float64 top derivative (numpy promotion)
+            top64 = None
+            if np.ndim(e.inertia) == 0:
+                sd[n] = (a / R(e.inertia)).astype(R)
+            elif np.asarray(e.inertia).dtype == np.dtype(R):
+                sd[n] = (a / np.asarray(e.inertia)[None, :]).astype(R)
+            else:
+                top64 = (a.astype(np.float64)
+                         / np.asarray(e.inertia, dtype=np.float64)[None, :])
+                sd[n] = top64.astype(R)
             for i in range(n):
                 for j in range(n - i):
-                    term_ = (sd[i + j + 1] * R(e.time_unit ** (j + 1))).astype(R)
+                    if top64 is not None and i + j + 1 == n:
+                        term64 = top64 * (e.time_unit ** (j + 1))
+                    else:
+                        term64 = (sd[i + j + 1] * R(e.time_unit ** (j + 1))).astype(
+                            R).astype(np.float64)
                     sd[i] = (sd[i].astype(np.float64)
-                             + term_.astype(np.float64)
-                             / float(math.factorial(j + 1))).astype(R)
+                             + term64 / float(math.factorial(j + 1))).astype(R)
             self.sd[:, in_range] = sd[:, in_range]
             nxt = np.where(in_range[:, None], self.sd[0], self.em).astype(R)
             if self.has_pnoise:
@@ -184,11 +198,18 @@ class VectorContinuousOracle:
             if self.delay > 0:
                 pos = step % self.delay
                 have = self.t > self.delay
-                delayed = self.ring[pos].copy()
-                self.ring[pos] = np.where(is_real, rr, r64.astype(R))
-                rr = np.where(have, delayed, rr)
-                r64 = np.where(have, r64, 0.0)
-                is_real = have.copy()
+                if e.make_denser and self.target64 and R is np.float32:
+                    # python floats all the way through reward_buffer (:1968-1977)
+                    delayed = self.ring64[pos].copy()
+                    self.ring64[pos] = r64
+                    r64 = np.where(have, delayed, 0.0)
+                    is_real = np.zeros(N, dtype=bool)
+                else:
+                    delayed = self.ring[pos].copy()
+                    self.ring[pos] = np.where(is_real, rr, r64.astype(R))
+                    rr = np.where(have, delayed, rr)
+                    r64 = np.where(have, r64, 0.0)
+                    is_real = have.copy()
             gated = (self.t % self.every_n) != 0
             r64 = np.where(gated, 0.0, r64)
             is_real = is_real & ~gated

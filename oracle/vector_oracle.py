@@ -249,3 +249,37 @@ class VectorDiscreteOracle:
         self.step_index += T
         return dict(obs=obs, final_obs=final_obs, reward=reward,
                     terminated=term, truncated=trunc)
+
+
+class VectorGroupedOracle:
+    """A heterogeneous launch (BASELINE config #5): envs laid out group-major,
+    group g = `sizes[g]` envs with the tables of `scalar_envs[g]`; global Philox
+    ids follow mdp_playground_b200/sharding.py (every group's envs contiguous
+    over ranks, groups one after the other).  One VectorDiscreteOracle per
+    group, outputs concatenated along the env axis."""
+
+    def __init__(self, scalar_envs, sizes, autoreset=False, horizon=0, seed=0,
+                 env_id_offset=0, rank=0, world=1, **kw):
+        assert len(scalar_envs) == len(sizes)
+        self.sizes = [int(n) for n in sizes]
+        self.parts, gbegin = [], 0
+        for e, n in zip(scalar_envs, self.sizes):
+            gids = env_id_offset + gbegin + rank * n + np.arange(n, dtype=np.int64)
+            gbegin += world * n
+            self.parts.append(VectorDiscreteOracle(
+                e, n, autoreset=autoreset, horizon=horizon, seed=seed, gids=gids, **kw))
+
+    def reset(self):
+        return np.concatenate([p.reset() for p in self.parts])
+
+    def rollout(self, T, actions=None):
+        outs, begin = [], 0
+        for p, n in zip(self.parts, self.sizes):
+            a = None if actions is None else np.asarray(actions)[:, begin:begin + n]
+            outs.append(p.rollout(T, actions=a))
+            begin += n
+        return {k: np.concatenate([o[k] for o in outs], axis=1) for k in outs[0]}
+
+    @property
+    def stats(self):
+        return [dict(p.stats) for p in self.parts]

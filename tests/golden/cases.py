@@ -145,6 +145,30 @@ CASES = {
     "cont_unbounded": dict(config={
         k: v for k, v in _C.items()
         if k not in ("state_space_max", "action_space_max")}),
+    # per-dimension inertia (rl_toy_env.py:519-537, :1654): a list / float64
+    # array makes `action / inertia` float64 (the top derivative leaves fp32),
+    # an array of dtype_s keeps the division in fp32
+    "cont_inertia_list": dict(config=dict(
+        _C, transition_dynamics_order=3, time_unit=0.4,
+        inertia=[1.0, 2.0, 0.5, 3.0, 1.5, 0.7], state_space_max=4.0)),
+    "cont_inertia_f32": dict(config=dict(
+        _C, inertia=np.array([1.0, 2.0, 0.5, 3.0, 1.5, 0.7], dtype=np.float32),
+        state_space_max=4.0)),
+    # fp32 env, default (float64) target_point, dense reward through the delay
+    # FIFO: the reference keeps Python floats in reward_buffer
+    "cont_delay_default_target": dict(config={
+        k: v for k, v in dict(_C, state_space_dim=2, action_space_dim=2,
+                              irrelevant_features=False, delay=3,
+                              reward_noise=0.2, reward_scale=1.5,
+                              state_space_max=2.0).items()
+        if k not in ("target_point", "relevant_indices")}),
+    # round 2: longer / wider replays of the two headline shapes
+    "c2_big": dict(config=dict(
+        _D, sequence_length=3, delay=2, transition_noise=0.1,
+        reward_noise=0.25, reward_every_n_steps=True),
+        lanes=32, steps=200, horizon=25),
+    "c3_big": dict(config=dict(_C, transition_noise=0.02, reward_noise=0.05),
+                   lanes=32, steps=200, horizon=40),
     "cont_img": dict(config=dict(
         _C, state_space_dim=4, action_space_dim=4,
         image_representations=True, state_space_max=5.0,

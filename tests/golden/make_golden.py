@@ -80,8 +80,12 @@ def run_case(name, spec):
     )
     if cont:
         rec["state_noise"] = np.full((K, T, D), np.nan)
+        # (a list / float64 `inertia` makes the top derivative float64, :1654)
+        f64_top = np.asarray(cfg.get("inertia", 1.0)).dtype == np.float64 \
+            and np.ndim(cfg.get("inertia", 1.0)) > 0
         rec["derivs"] = np.zeros(
-            (K, T, env.dynamics_order + 1, D), dtype=np.float32)
+            (K, T, env.dynamics_order + 1, D),
+            dtype=np.float64 if f64_top else np.float32)
     if irr:  # draws of the irrelevant sub-space (S' stream / second E draw)
         rec["irr_transition_u"] = np.full((K, T), np.nan)
         rec["irr_reset_u"] = np.full((K, T), np.nan)

@@ -131,3 +131,104 @@ def test_invalid_arguments_fail_loudly():
     c = make_env(4, state_space_type="continuous", state_space_dim=2)
     with pytest.raises(TypeError):        # the reference wants dtype_s actions
         c.step(torch.zeros((4, 2), dtype=torch.float64))
+
+
+def test_reset_with_the_same_seed_reproduces_the_rollout():
+    """gym's reset(seed) contract in Philox mode: the streams are
+    re-keyed AND rewound, so reset(seed=s) twice gives the same initial states
+    and the same noisy trajectory; a graphed step captured before refuses."""
+    import torch
+    from tests.test_cuda_discrete import _BENCH_CFG, make_env
+    env = make_env(777, autoreset=True, horizon=9, **dict(_BENCH_CFG))
+    a = torch.randint(0, 8, (40, 777), dtype=torch.int32, device="cuda")
+    gstep = env.make_graphed_step()
+    runs = []
+    for _ in range(2):
+        obs0, _ = env.reset(seed=5)
+        out = env.rollout(40, actions=a, want_final_obs=False)
+        runs.append((obs0.clone(), {k: v.clone() for k, v in out.items()}))
+        env.rollout(3, actions=a[:3], want_final_obs=False)   # (drift in between)
+    assert torch.equal(runs[0][0], runs[1][0])
+    for k in runs[0][1]:
+        assert torch.equal(runs[0][1][k], runs[1][1][k]), k
+    other, _ = env.reset(seed=6)
+    assert not torch.equal(other, runs[0][0])
+    with pytest.raises(RuntimeError, match="re-seeded"):
+        gstep(a[0])
+
+
+def test_out_of_range_states_are_rejected_host_side():
+    import torch
+    from tests.test_cuda_discrete import _BENCH_CFG, make_env
+    env = make_env(16, track_history=True, **dict(_BENCH_CFG))
+    bad = torch.zeros(16, dtype=torch.int64)
+    bad[3] = 8
+    with pytest.raises(ValueError, match="out of range"):
+        env.reset(options={"init_state": bad})
+    with pytest.raises(ValueError, match="out of range"):
+        env.set_augmented_state(bad.cuda())
+    env.reset(options={"init_state": torch.full((16,), 7)})
+
+
+@pytest.mark.parametrize("kind", ["continuous", "grid"])
+def test_two_shards_equal_the_unsplit_job_continuous_and_grid(kind):
+    """shard=(rank, world) for the single-group env kinds: rank r
+    owns the global ids [r N, (r + 1) N) -- two shards == the unsplit batch."""
+    import torch
+    from tests.test_cuda_discrete import make_env
+    if kind == "continuous":
+        cfg = dict(seed=0, state_space_type="continuous", state_space_dim=2,
+                   transition_dynamics_order=1, inertia=1.0, time_unit=1.0,
+                   target_point=[0.0, 0.0], state_space_max=5.0, action_space_max=1.0,
+                   transition_noise=0.1, reward_noise=0.5)
+        acts = torch.rand((20, 600, 2), device="cuda") * 2 - 1
+    else:
+        cfg = dict(seed=0, state_space_type="grid", grid_shape=(8, 8), delay=0,
+                   sequence_length=1, reward_function="move_to_a_point",
+                   target_point=[5, 5], make_denser=True, transition_noise=0.2,
+                   reward_noise=0.5)
+        acts = torch.zeros((20, 600, 2), dtype=torch.int64, device="cuda")
+        acts[..., 1] = torch.randint(-1, 2, (20, 600), device="cuda")
+    whole = make_env(600, autoreset=True, horizon=7, **cfg)
+    ref = whole.rollout(20, actions=acts, want_final_obs=False)
+    for r in range(2):
+        part = make_env(300, autoreset=True, horizon=7, shard=(r, 2), **cfg)
+        out = part.rollout(20, actions=acts[:, 300 * r:300 * (r + 1)].contiguous(),
+                           want_final_obs=False)
+        for k in ref:
+            assert torch.equal(out[k], ref[k][:, 300 * r:300 * (r + 1)]), (k, r)
+
+
+def test_strict_false_treats_foreign_action_dtypes_like_the_reference():
+    """Box.contains needs can_cast(action dtype, dtype_s): float64 actions for
+    a float32 env freeze the state (rl_toy_env.py:1640, :1671-1679), float
+    grid actions are no-ops (:1730-1733).  Default (strict) raises."""
+    import torch
+    from tests.test_cuda_discrete import make_env
+    cfg = dict(seed=0, state_space_type="continuous", state_space_dim=2,
+               transition_dynamics_order=2, inertia=1.0, time_unit=0.5,
+               target_point=[0.0, 0.0], state_space_max=5.0, action_space_max=1.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = ScalarRLToyEnv(**dict(cfg))
+    env = make_env(1, noise="numpy", strict=False, **dict(cfg))
+    assert np.array_equal(env.curr_obs[0].cpu().numpy(), ref.curr_obs)
+    rng = np.random.default_rng(2)
+    for t in range(12):
+        a = rng.uniform(-1, 1, size=2)
+        a = a.astype(np.float32) if t % 3 else a      # every third: float64
+        o1, r1, d1, _, _ = ref.step(a)
+        o2, r2, d2, _, _ = env.step(torch.as_tensor(a)[None])
+        assert np.array_equal(o2[0].cpu().numpy(), o1), t
+        assert float(r2[0]) == float(np.float32(r1)), t
+    strict = make_env(1, **dict(cfg))
+    with pytest.raises(TypeError, match="strict=False"):
+        strict.step(torch.zeros((1, 2), dtype=torch.float64))
+    strict.step(torch.zeros((1, 2), dtype=torch.float16))   # castable: accepted
+    g = make_env(4, strict=False, seed=0, state_space_type="grid", grid_shape=(8, 8),
+                 delay=0, sequence_length=1, reward_function="move_to_a_point",
+                 target_point=[5, 5], make_denser=True)
+    before = g.get_augmented_state()["curr_state"].clone()
+    obs, r, term, trunc, _ = g.step(torch.ones((4, 2), dtype=torch.float32))
+    # a no-op: cells only clamp back into the grid (reset draws one past it)
+    assert torch.equal(obs, before.clamp(max=7))

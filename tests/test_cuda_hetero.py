@@ -114,3 +114,57 @@ def test_sweep_grid_smoke_1000_groups():
     ratio = st["abs_reward_noise"][rn == 25].mean() / st["abs_reward_noise"][rn == 5].mean()
     assert abs(ratio - 5) < 0.3
     assert int(out["obs"].max()) < 8
+
+
+def _mixed_groups():
+    """40 cells of the BASELINE config #5 grid (delay x sequence_length x noise
+    x make_denser; experiments/dqn_seq_del.py:7-20, dqn_p_r_noises.py:7-20)."""
+    base = dict(seed=0, state_space_type="discrete", action_space_type="discrete",
+                state_space_size=8, action_space_size=8, reward_density=0.25,
+                terminal_state_density=0.25, reward_every_n_steps=True)
+    rng = np.random.default_rng(40)
+    cells = [(d, L, pn, rn, md) for d in (0, 1, 2, 4, 8) for L in (1, 2, 3, 4)
+             for pn in (0, 0.01, 0.1, 0.25) for rn in (0, 1, 5, 25)
+             for md in (False, True)]
+    pick = rng.choice(len(cells), size=40, replace=False)
+    return [dict(base, delay=cells[i][0], sequence_length=cells[i][1],
+                 transition_noise=cells[i][2], reward_noise=cells[i][3],
+                 make_denser=cells[i][4]) for i in pick]
+
+
+@pytest.mark.parametrize("jit", [True, False])
+@pytest.mark.parametrize("normal", ["fp64", "fast"])
+def test_mixed_40_group_launch_matches_grouped_oracle(jit, normal):
+    """ONE heterogeneous launch against the CPU oracle directly (not against
+    other CUDA envs): 40 mixed groups of 37 envs (partially filled CTAs),
+    given actions, auto-reset + horizon; T = 75 covers two staged ziggurat
+    windows + a chunk drawn directly.  States / flags bit-exact, rewards 1e-12
+    (1e-5 x sigma for the fp32 SFU normals)."""
+    from oracle.scalar_env import ScalarRLToyEnv
+    from oracle.vector_oracle import VectorGroupedOracle
+    cfgs = _mixed_groups()
+    sizes = [37] * len(cfgs)
+    N, T = sum(sizes), 75
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        scalars = [ScalarRLToyEnv(**dict(c)) for c in cfgs]
+    ora = VectorGroupedOracle(scalars, sizes, autoreset=True, horizon=23, seed=3,
+                              env_id_offset=1000, fast_normal=normal == "fast")
+    ora.reset()
+    env = make_env(N, autoreset=True, horizon=23, philox_seed=3, env_id_offset=1000,
+                   config_groups=[dict(c) for c in cfgs], group_sizes=sizes,
+                   normal_precision=normal)
+    env.set_jit(jit)
+    acts = np.random.default_rng(1).integers(0, 8, size=(T, N))
+    got = env.rollout(T, actions=torch.as_tensor(acts, dtype=torch.int32, device="cuda"))
+    assert env.jit_last_used == jit, env.jit_log
+    want = ora.rollout(T, actions=acts)
+    for k in ("obs", "final_obs", "terminated", "truncated"):
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+    tol = 1e-5 * 25 if normal == "fast" else 1e-12
+    np.testing.assert_allclose(got["reward"].cpu().numpy(), want["reward"],
+                               rtol=0 if normal == "fast" else 1e-12, atol=tol)
+    st = env.episode_stats()
+    for g, s in enumerate(ora.stats):
+        for k in ("episodes", "transitions", "noisy_transitions", "terminated"):
+            assert st[k][g] == s[k], (g, k)

@@ -38,7 +38,7 @@ def replay_continuous_golden(vec_reset, vec_step, g, exact=True, rtol=1e-5):
             assert np.array_equal(obs, g["state"][:, t]), t
             assert np.array_equal(r, want_r), (t, r, want_r)
             if derivs is not None:
-                assert np.array_equal(derivs, g["derivs"][:, t]), t
+                assert np.array_equal(derivs, g["derivs"][:, t].astype(derivs.dtype)), t
         else:
             np.testing.assert_allclose(obs, g["state"][:, t], rtol=rtol, atol=1e-7)
             np.testing.assert_allclose(r, want_r, rtol=rtol, atol=1e-6)
