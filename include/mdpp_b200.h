@@ -282,9 +282,18 @@ typedef struct mdpp_continuous_config {
    * / float64 array: numpy promotes the quotient, so the top derivative and
    * every Taylor term that reads it are float64                             */
   int32_t inertia_mode;
-  int32_t reserved_cfg;
+  /* reward_function: MDPP_REWARD_POINT = move_to_a_point (the target fields
+   * above); MDPP_REWARD_LINE = move_along_a_line (rl_toy_env.py:1865-1910,
+   * :2546-2576): minus the mean distance of the last `sequence_length`
+   * relevant states from the line fitted through them (principal direction);
+   * no target, no reached_terminal; state.hist holds the window             */
+  int32_t reward_kind;
   double inertia_vec[MDPP_MAX_DIM];
+  int32_t sequence_length;      /* MDPP_REWARD_LINE: 1..128                  */
+  int32_t reserved_cfg;
 } mdpp_continuous_config;
+#define MDPP_REWARD_POINT 0
+#define MDPP_REWARD_LINE 1
 
 #ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
 int mdpp_set_continuous_config(mdpp_ctx* ctx, const mdpp_continuous_config* cfg);
@@ -304,6 +313,8 @@ typedef struct mdpp_continuous_state {
   double* stats;       /* [stats_slots][MDPP_N_STATS], summed over slots      */
   int32_t stats_slots; /* >= 1 (0 reads as 1), see mdpp_discrete_state        */
   int32_t reserved1;
+  void* hist;          /* MDPP_REWARD_LINE: real [sequence_length][n_relevant][N],
+                          the last emitted relevant states, slot = step % L  */
 } mdpp_continuous_state;
 
 /* T steps, time-major; actions / obs are env-major rows of `dim` reals

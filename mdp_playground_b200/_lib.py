@@ -16,6 +16,7 @@ MDPP_N_STATS = 8
 STATS_SLOTS = 64  # copies of the counter rows the kernels spread their atomics over
 MDPP_NORMAL_F64, MDPP_NORMAL_FAST, MDPP_NORMAL_ZIGGURAT = 0, 1, 2
 MDPP_OBS_I64, MDPP_OBS_I32, MDPP_OBS_U8 = 0, 1, 2
+MDPP_REWARD_POINT, MDPP_REWARD_LINE = 0, 1
 MDPP_LAUNCH_OVERLAP_PREVIOUS = 1
 STAT_NAMES = ("episodes", "transitions", "reward", "noisy_transitions",
               "abs_reward_noise", "abs_transition_noise", "reserved",
@@ -107,8 +108,9 @@ class ContinuousConfig(C.Structure):
         ("target_point", C.c_double * MDPP_MAX_DIM),
         ("term_low", C.c_double * (MDPP_MAX_TERM_BOXES * MDPP_MAX_DIM)),
         ("term_high", C.c_double * (MDPP_MAX_TERM_BOXES * MDPP_MAX_DIM)),
-        ("inertia_mode", C.c_int32), ("reserved_cfg", C.c_int32),
+        ("inertia_mode", C.c_int32), ("reward_kind", C.c_int32),
         ("inertia_vec", C.c_double * MDPP_MAX_DIM),
+        ("sequence_length", C.c_int32), ("reserved_cfg", C.c_int32),
     ]
 
 
@@ -118,6 +120,7 @@ class ContinuousState(C.Structure):
         ("t_episode", C.c_void_p), ("episode", C.c_void_p),
         ("reached", C.c_void_p), ("ring", C.c_void_p), ("stats", C.c_void_p),
         ("stats_slots", C.c_int32), ("reserved1", C.c_int32),
+        ("hist", C.c_void_p),
     ]
 
 

@@ -70,6 +70,7 @@ class EnvSpec:
     target_radius: float = 0.05
     relevant_indices: List[int] = field(default_factory=list)
     target_point: Any = None
+    reward_function: str = "move_to_a_point"
     state_space_max: float = float("inf")
     action_space_max: float = float("inf")
     terminal_centres: Any = None
@@ -173,10 +174,9 @@ def parse_config(config):
     else:
         sp.state_space_dim = int(config["state_space_dim"])
         config.setdefault("reward_function", "move_to_a_point")
-        if config["reward_function"] != "move_to_a_point":
-            raise NotImplementedError(
-                "only move_to_a_point is on the B200 step path "
-                "(move_along_a_line: SURVEY.md 8f row N2)")
+        if config["reward_function"] not in ("move_to_a_point", "move_along_a_line"):
+            raise ValueError("unknown reward_function " + str(config["reward_function"]))
+        sp.reward_function = config["reward_function"]
         sp.dynamics_order = int(g("transition_dynamics_order", 1))
         sp.inertia = g("inertia", 1.0)
         sp.time_unit = g("time_unit", 1.0)
@@ -228,8 +228,11 @@ def parse_config(config):
     assert sp.sequence_length > 0, \
         'config["sequence_length"] <= 0. Set to: ' + str(sp.sequence_length)
     if kind == "continuous":  # :641-654
-        assert sp.sequence_length == 1
-        if "target_point" in config:
+        if sp.reward_function == "move_to_a_point":
+            assert sp.sequence_length == 1
+        if sp.reward_function == "move_along_a_line":
+            sp.target_point = None  # (no target: nothing to reach, :1719)
+        elif "target_point" in config:
             sp.target_point = np.array(config["target_point"], dtype=sp.dtype_s)
             assert sp.target_point.shape == (len(sp.relevant_indices),), (
                 "target_point should have dimensionality = relevant_state_space"

@@ -29,6 +29,13 @@ extern "C" int mdpp_set_continuous_config(mdpp_ctx* ctx,
     return fail(ctx, MDPP_EINVAL, "at most 8 terminal boxes");
   if (cfg->image_mode && !std::isfinite(cfg->state_space_max))
     return fail(ctx, MDPP_EINVAL, "image observations need a bounded space");
+  if (cfg->inertia_mode < 0 || cfg->inertia_mode > 2)
+    return fail(ctx, MDPP_EINVAL, "bad inertia_mode");
+  if (cfg->reward_kind != MDPP_REWARD_POINT && cfg->reward_kind != MDPP_REWARD_LINE)
+    return fail(ctx, MDPP_EINVAL, "unknown reward_kind");
+  if (cfg->reward_kind == MDPP_REWARD_LINE &&
+      (cfg->sequence_length < 1 || cfg->sequence_length > kLineMaxSeq))
+    return fail(ctx, MDPP_EINVAL, "move_along_a_line: sequence_length must be in 1..128");
   ctx->c_cfg = *cfg;
   ctx->have_continuous = true;
   return MDPP_OK;
@@ -44,6 +51,8 @@ static int fill_params(mdpp_ctx* ctx, const mdpp_continuous_state* st,
     return fail(ctx, MDPP_EINVAL, "continuous state has NULL arrays");
   if (ctx->c_cfg.delay > 0 && !st->ring)
     return fail(ctx, MDPP_EINVAL, "delay ring missing");
+  if (ctx->c_cfg.reward_kind == MDPP_REWARD_LINE && !st->hist)
+    return fail(ctx, MDPP_EINVAL, "move_along_a_line: state.hist is NULL");
   if (!opts) return fail(ctx, MDPP_EINVAL, "opts is NULL");
   std::memset(p, 0, sizeof(*p));
   p->cfg = ctx->c_cfg;

@@ -261,6 +261,127 @@ constexpr int kActionPrefetch = MDPP_C_PREFETCH;
 constexpr int kActionPrefetch = 4;  // action rows in flight per env
 #endif
 
+// ---- move_along_a_line (rl_toy_env.py:1865-1910, :2546-2576) ----------------
+// Reward = - (1 / L) sum of the distances of the last L emitted relevant states
+// from the line fitted through them.  The reference takes the direction from a
+// float32 SVD (numpy / LAPACK sgesdd) of the centred window and does
+// everything after it in float64 (the end points are a float64 linspace times
+// the direction).  Here: window mean in R with numpy's summation order (the
+// reference's window is F-ordered, so `mean(axis=0)` runs the pairwise sum:
+// sequential below 8 rows, 8 accumulators up to 128), principal direction from
+// the float64 covariance (closed form for 2 relevant dimensions, cyclic Jacobi
+// above), rounded to R like the SVD's output, distances by the reference's
+// Pythagoras formula in float64.  Agreement with the reference is bounded by
+// the fp32 direction (~1e-7 relative): the contract's 1e-5, not bit-exactness.
+constexpr int kLineMaxSeq = 128;
+
+template <typename R>
+__device__ __noinline__ double line_reward(const R* hist, int64_t N, int64_t env,
+                                           int NREL, int L, uint64_t step) {
+  typedef RealOps<R> O;
+  auto row = [&](int k) { return (int)((step + 1 + (uint64_t)k) % (uint64_t)L); };
+  auto at = [&](int k, int d) { return hist[((int64_t)row(k) * NREL + d) * N + env]; };
+  R mean[MDPP_MAX_DIM];
+  for (int d = 0; d < NREL; ++d) {
+    R s;
+    if (L < 8) {
+      s = (R)0;
+      for (int k = 0; k < L; ++k) s = O::add(s, at(k, d));
+    } else {  // numpy pairwise_sum for 8 <= n <= 128
+      R r[8];
+      for (int j = 0; j < 8; ++j) r[j] = at(j, d);
+      int i = 8;
+      for (; i < L - (L % 8); i += 8)
+        for (int j = 0; j < 8; ++j) r[j] = O::add(r[j], at(i + j, d));
+      s = O::add(O::add(O::add(r[0], r[1]), O::add(r[2], r[3])),
+                 O::add(O::add(r[4], r[5]), O::add(r[6], r[7])));
+      for (; i < L; ++i) s = O::add(s, at(i, d));
+    }
+    mean[d] = (R)((double)s / (double)L);  // true_divide in float64, cast back
+  }
+  // covariance of the centred (R-rounded) window, float64
+  double C[MDPP_MAX_DIM][MDPP_MAX_DIM];
+  for (int a = 0; a < NREL; ++a)
+    for (int b = 0; b < NREL; ++b) C[a][b] = 0.0;
+  for (int k = 0; k < L; ++k) {
+    double c[MDPP_MAX_DIM];
+    for (int d = 0; d < NREL; ++d) c[d] = (double)O::add(at(k, d), -mean[d]);
+    for (int a = 0; a < NREL; ++a)
+      for (int b = a; b < NREL; ++b) C[a][b] += c[a] * c[b];
+  }
+  double v[MDPP_MAX_DIM];
+  for (int d = 0; d < NREL; ++d) v[d] = d == 0 ? 1.0 : 0.0;
+  if (NREL == 2) {
+    const double th = 0.5 * atan2(2.0 * C[0][1], C[0][0] - C[1][1]);
+    if (C[0][1] != 0.0 || C[0][0] != C[1][1]) { v[0] = cos(th); v[1] = sin(th); }
+  } else if (NREL > 2) {
+    double V[MDPP_MAX_DIM][MDPP_MAX_DIM];
+    for (int a = 0; a < NREL; ++a)
+      for (int b = 0; b < NREL; ++b) {
+        V[a][b] = a == b ? 1.0 : 0.0;
+        if (b < a) C[a][b] = C[b][a];
+      }
+    for (int sweep = 0; sweep < 12; ++sweep) {
+      double off = 0.0;
+      for (int a = 0; a < NREL; ++a)
+        for (int b = a + 1; b < NREL; ++b) off += C[a][b] * C[a][b];
+      if (off == 0.0) break;
+      for (int pi = 0; pi < NREL; ++pi)
+        for (int q = pi + 1; q < NREL; ++q) {
+          if (C[pi][q] == 0.0) continue;
+          const double tau = (C[q][q] - C[pi][pi]) / (2.0 * C[pi][q]);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          const double cs = 1.0 / sqrt(1.0 + t * t), sn = t * cs;
+          for (int k = 0; k < NREL; ++k) {
+            const double akp = C[k][pi], akq = C[k][q];
+            C[k][pi] = cs * akp - sn * akq;
+            C[k][q] = sn * akp + cs * akq;
+          }
+          for (int k = 0; k < NREL; ++k) {
+            const double apk = C[pi][k], aqk = C[q][k];
+            C[pi][k] = cs * apk - sn * aqk;
+            C[q][k] = sn * apk + cs * aqk;
+          }
+          for (int k = 0; k < NREL; ++k) {
+            const double vkp = V[k][pi], vkq = V[k][q];
+            V[k][pi] = cs * vkp - sn * vkq;
+            V[k][q] = sn * vkp + cs * vkq;
+          }
+        }
+    }
+    int best = 0;
+    for (int a = 1; a < NREL; ++a)
+      if (C[a][a] > C[best][best]) best = a;
+    for (int d = 0; d < NREL; ++d) v[d] = V[d][best];
+  }
+  // the reference's float64 distance arithmetic on the R-typed direction / mean
+  double A[MDPP_MAX_DIM], AB[MDPP_MAX_DIM];
+  double nAB2 = 0.0;
+  for (int d = 0; d < NREL; ++d) {
+    const double vd = (double)(R)v[d], md = (double)mean[d];
+    A[d] = __dadd_rn(-vd, md);                       // vv[0] * -1 + mean
+    AB[d] = __dadd_rn(A[d], -__dadd_rn(vd, md));     // ptA - ptB
+    nAB2 = __dadd_rn(nAB2, __dmul_rn(AB[d], AB[d]));
+  }
+  const double nAB = sqrt(nAB2);
+  double total = 0.0;
+  if (!(nAB < 1e-13)) {
+    for (int k = 0; k < L; ++k) {
+      double dot = 0.0, n2 = 0.0;
+      for (int d = 0; d < NREL; ++d) {
+        const double ap = __dadd_rn(A[d], -(double)at(k, d));
+        dot = __dadd_rn(dot, __dmul_rn(AB[d], ap));
+        n2 = __dadd_rn(n2, __dmul_rn(ap, ap));
+      }
+      const double proj = __ddiv_rn(dot, nAB), nap = sqrt(n2);
+      double sq = __dadd_rn(__dmul_rn(nap, nap), -__dmul_rn(proj, proj));
+      if (sq < 0.0) sq = 0.0;
+      total = __dadd_rn(total, sqrt(sq));
+    }
+  }
+  return __dadd_rn(0.0, __ddiv_rn(-total, (double)L));
+}
+
 template <typename R, int NOISE>
 __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   using O = RealOps<R>;
@@ -292,6 +413,8 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   const R smax = (R)MDPP_C_F64(SMAX, p.cfg.state_space_max);
   const R inertia = (R)MDPP_C_F64(INERTIA, p.cfg.inertia);
   const int IMODE = MDPP_C_CONST(IMODE, p.cfg.inertia_mode);  // per-dimension inertia
+  const bool LINE = MDPP_C_CONST(LINE, p.cfg.reward_kind == MDPP_REWARD_LINE);
+  const int SEQ = MDPP_C_CONST(SEQ, p.cfg.sequence_length);
   const double radius64 = MDPP_C_F64(RADIUS, p.cfg.target_radius);
   const R radius_r = (R)radius64;
   const double alw = MDPP_C_F64(ALW, p.cfg.action_loss_weight);
@@ -334,6 +457,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   // would use: R when target_point was given (cast to dtype_s :646), float64
   // for the default float64 zeros (:654)
   auto dist_to_target = [&](const R* x) -> double {
+    if (LINE) return 0.0;  // (no target point)
     if (TARGET64) {
       return seq_norm<double>(NREL, [&](int k) {
         return __dadd_rn((double)x[rel_index(p, k)], -p.cfg.target_point[k]);
@@ -489,7 +613,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
     const double dist_new = dist_to_target(nxt);
     dist_prev = dist_new;
     const double radius = TARGET64 ? radius64 : (double)radius_r;
-    if (dist_new < radius) reached = true;
+    if (!LINE && dist_new < radius) reached = true;
     tl += 1;
     phase = (phase + 1 == EVERY_N) ? 0 : phase + 1;
 
@@ -499,7 +623,17 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
     R rr;
     double rd = 0.0;
     bool is_real = true;
-    if (DENSE) {
+    if (LINE) {
+      R* hist = reinterpret_cast<R*>(p.st.hist);
+      const int slot = (int)(step % (uint64_t)SEQ);
+#pragma unroll
+      for (int k = 0; k < MDPP_MAX_DIM; ++k)
+        if (k < NREL) hist[((int64_t)slot * NREL + k) * N + env] = nxt[rel_index(p, k)];
+      // NaN gate of the window (:1858): sequence_length + 1 states since the reset
+      if (tl >= SEQ) rd = line_reward<R>(hist, N, env, NREL, SEQ, step);
+      is_real = false;
+      rr = (R)0;
+    } else if (DENSE) {
       if (TARGET64) {  // float64 norms make the reward float64
         rd = __dadd_rn(-dist_new, dist_old);
         is_real = false;
@@ -510,7 +644,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
       rd = dist_new < radius ? 1.0 : 0.0;
       is_real = false;
     }
-    {  // reward -= action_loss_weight * ||action||  (always makes it dtype_s)
+    if (!LINE) {  // reward -= action_loss_weight * ||action||  (always makes it dtype_s)
       // weight 0: 0 * ||a|| = 0 (finite actions); the subtraction still
       // happens for its dtype effect, the norm is skipped
       const R loss = alw == 0.0 ? (R)0
@@ -522,7 +656,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
     }
     if (DELAY > 0) {
       const bool have = tl > DELAY;
-      if (sizeof(R) == 4 && TARGET64 && DENSE) {
+      if (sizeof(R) == 4 && ((TARGET64 && DENSE) || LINE)) {
         // the reward is a python float here (float64 norms), and the
         // reference's reward_buffer keeps it one: the FIFO holds doubles and
         // the tail below stays on the float64 path (the caller allocates the

@@ -331,6 +331,7 @@ int jit_try_continuous(mdpp_ctx* ctx, ContinuousParams& p, cudaStream_t stream) 
       D("PNOISE", B(c.has_transition_noise)), D("RNOISE", B(c.has_reward_noise)),
       D("IMAGE", B(c.image_mode)), D("TARGET64", B(c.target_is_f64)),
       D("NORMAL", I(p.normal_mode)), D("IMODE", I(c.inertia_mode)),
+      D("LINE", B(c.reward_kind == MDPP_REWARD_LINE)), D("SEQ", I(c.sequence_length)),
       D("NBOX", I(c.n_term_boxes)), D("HORIZON", I(p.horizon)),
       D("AUTORESET", B(p.autoreset != 0)), D("N_ENVS", I(p.st.n_envs) + "ll"),
       D("FAST", B(p.io.obs && p.io.reward && p.io.terminated && p.io.truncated &&
@@ -495,7 +496,7 @@ extern "C" int mdpp_jit_selftest(char* log, int log_bytes) {
         "-DMDPP_C_ORDER=2", "-DMDPP_C_NREL=2", "-DMDPP_C_DELAY=0",
         "-DMDPP_C_EVERY_N=1", "-DMDPP_C_DENSE=true", "-DMDPP_C_PNOISE=false",
         "-DMDPP_C_RNOISE=false", "-DMDPP_C_IMAGE=false", "-DMDPP_C_TARGET64=false",
-        "-DMDPP_C_NORMAL=0", "-DMDPP_C_IMODE=0", "-DMDPP_C_NBOX=0", "-DMDPP_C_HORIZON=100", "-DMDPP_C_AUTORESET=true",
+        "-DMDPP_C_NORMAL=0", "-DMDPP_C_IMODE=0", "-DMDPP_C_LINE=false", "-DMDPP_C_SEQ=1", "-DMDPP_C_NBOX=0", "-DMDPP_C_HORIZON=100", "-DMDPP_C_AUTORESET=true",
         "-DMDPP_C_N_ENVS=1048576ll", "-DMDPP_C_FAST=true",
         "-DMDPP_C_REL0=0", "-DMDPP_C_REL1=1"};
     for (int k = 2; k < MDPP_MAX_DIM; ++k)

@@ -902,7 +902,8 @@ class VectorRLToyEnv:
     # ------------------------------------------------------------------
     def _state_tensors(self):
         names = ("_cur", "_cur_irr", "_key", "_t", "_episode", "_ring", "_history",
-                 "_stats", "_derivs", "_emitted", "_reached", "_pos", "_prev")
+                 "_stats", "_derivs", "_emitted", "_reached", "_pos", "_prev",
+                 "_hist_line")
         return [getattr(self, n) for n in names
                 if getattr(self, n, None) is not None]
 
@@ -1098,7 +1099,8 @@ class VectorRLToyEnv:
         c.has_transition_noise = int(self.has_pnoise)
         c.has_reward_noise = int(self.has_rnoise)
         c.image_mode = int(sp.image_representations)
-        c.target_is_f64 = int("target_point" not in self.config)
+        c.target_is_f64 = int("target_point" not in self.config
+                              and sp.reward_function == "move_to_a_point")
         c.is_f64 = int(np_dt == np.float64)
         # inertia: float, or one value per dimension (rl_toy_env.py:519-537); a
         # list / float64 array promotes `action / inertia` to float64 (:1654)
@@ -1123,11 +1125,20 @@ class VectorRLToyEnv:
         c.term_state_reward = sp.term_state_reward
         for k, i in enumerate(sp.relevant_indices):
             c.relevant_indices[k] = i
-        tp = np.asarray(sp.target_point, dtype=np.float64)
-        assert tp.shape[0] == c.n_relevant, \
-            "target_point must have one entry per relevant index"
-        for k in range(c.n_relevant):
-            c.target_point[k] = float(tp[k])
+        line = sp.reward_function == "move_along_a_line"
+        c.reward_kind = _lib.MDPP_REWARD_LINE if line else _lib.MDPP_REWARD_POINT
+        c.sequence_length = sp.sequence_length
+        if line:
+            if sp.sequence_length > 128:
+                raise NotImplementedError("move_along_a_line: sequence_length <= 128")
+            if sp.image_representations:
+                raise NotImplementedError("move_along_a_line with image observations")
+        else:
+            tp = np.asarray(sp.target_point, dtype=np.float64)
+            assert tp.shape[0] == c.n_relevant, \
+                "target_point must have one entry per relevant index"
+            for k in range(c.n_relevant):
+                c.target_point[k] = float(tp[k])
         # terminal hypercubes (:895-952); Box casts its bounds to dtype_s
         self._term_lows, self._term_highs = [], []
         for centre in (sp.terminal_centres or []):
@@ -1153,8 +1164,11 @@ class VectorRLToyEnv:
         self._reached = torch.zeros(N, dtype=torch.uint8, device=dev)
         # (fp32 env + default float64 target_point + dense reward: the reward is
         # a python float all the way through the reference's reward_buffer)
-        ring_dt = torch.float64 if (real == torch.float32 and c.target_is_f64
-                                    and c.dense) else real
+        ring_dt = torch.float64 if (real == torch.float32 and (
+            (c.target_is_f64 and c.dense) or line)) else real
+        # move_along_a_line: the last sequence_length emitted relevant states
+        self._hist_line = torch.zeros((sp.sequence_length, c.n_relevant, N),
+                                      dtype=real, device=dev) if line else None
         self._ring = torch.zeros((sp.delay, N), dtype=ring_dt, device=dev) \
             if sp.delay > 0 else None
         self._stats = torch.zeros((_lib.STATS_SLOTS, 1, _lib.MDPP_N_STATS),
@@ -1166,6 +1180,7 @@ class VectorRLToyEnv:
         st.reached, st.ring = _ptr(self._reached), _ptr(self._ring)
         st.stats = _ptr(self._stats)
         st.stats_slots = _lib.STATS_SLOTS
+        st.hist = _ptr(self._hist_line)
         self._state = st
         self._history = None
         if self.noise == "numpy":

@@ -23,7 +23,7 @@ Third-party arithmetic restated: gymnasium 1.x `seeding.np_random`,
 Pillow (12.2.0 in this image) is called directly for polygon/ellipse/rotate,
 exactly as the reference does.
 
-Not covered (SURVEY.md section 8f "next" rows): grid envs, move_along_a_line,
+Not covered (SURVEY.md section 8f "next" rows):
 callable P/R/noise.
 """
 import math
@@ -128,6 +128,22 @@ class ReplayDraws:
         return int(self._pop("image_int"))
 
 
+def dist_of_pt_from_line(pt, ptA, ptB):
+    """rl_toy_env.py:2546-2576: distance of `pt` from the line through ptA and
+    ptB by Pythagoras (float64 here: the end points are float64)."""
+    tolerance = 1e-13
+    lineAB = ptA - ptB
+    lineApt = ptA - pt
+    dot_product = np.dot(lineAB, lineApt)
+    if np.linalg.norm(lineAB) < tolerance:
+        return 0
+    proj = dot_product / np.linalg.norm(lineAB)
+    sq_dist = np.linalg.norm(lineApt) ** 2 - proj ** 2
+    if sq_dist < 0:
+        sq_dist = 0
+    return np.sqrt(sq_dist)
+
+
 def choice_from_uniform(cdf, u):
     """numpy Generator.choice(p=...) given its one uniform draw
     (discrete_extended.py:17; SURVEY.md 8a row A1')."""
@@ -198,8 +214,7 @@ class ScalarRLToyEnv:
         elif kind == "continuous":
             self.state_space_dim = cfg["state_space_dim"]
             cfg.setdefault("reward_function", "move_to_a_point")
-            assert cfg["reward_function"] == "move_to_a_point", \
-                "move_along_a_line: next row"
+            assert cfg["reward_function"] in ("move_to_a_point", "move_along_a_line")
             self.dynamics_order = g("transition_dynamics_order", 1)
             self.inertia = g("inertia", 1.0)
             self.time_unit = g("time_unit", 1.0)
@@ -254,8 +269,8 @@ class ScalarRLToyEnv:
         if "init_state_dist" in cfg and "relevant_init_state_dist" not in cfg:
             cfg["relevant_init_state_dist"] = cfg["init_state_dist"]
         assert self.sequence_length > 0
-        if kind == "continuous":  # :641-654
-            assert self.sequence_length == 1
+        if kind == "continuous" and cfg["reward_function"] == "move_to_a_point":
+            assert self.sequence_length == 1  # :641-654
             if "target_point" in cfg:
                 self.target_point = np.array(cfg["target_point"],
                                              dtype=self.dtype_s)
@@ -657,9 +672,10 @@ class ScalarRLToyEnv:
             zero = np.array([0.0] * self.state_space_dim, dtype=self.dtype_s)
             self.state_derivatives = [zero.copy() for _ in range(n + 1)]
             self.state_derivatives[0] = nxt.copy()
-        rel = np.array(nxt, dtype=self.dtype_s)[self.relevant_indices]
-        if np.linalg.norm(rel - self.target_point) < self.target_radius:
-            self.reached_terminal = True
+        if self.config["reward_function"] == "move_to_a_point":  # :1719-1725
+            rel = np.array(nxt, dtype=self.dtype_s)[self.relevant_indices]
+            if np.linalg.norm(rel - self.target_point) < self.target_radius:
+                self.reached_terminal = True
         return nxt
 
     @staticmethod
@@ -722,7 +738,24 @@ class ScalarRLToyEnv:
             elif list(new) == list(self.target_point):
                 reward += 1.0
         else:
-            if not np.isnan(aug[d][0]):
+            if not np.isnan(aug[d][0]) and \
+                    self.config["reward_function"] == "move_along_a_line":
+                # :1865-1910: fit a line (first right singular vector) through
+                # the last sequence_length relevant states, reward = - mean
+                # distance of those states from it.  The fp32 SVD gives the
+                # direction; the end points (a float64 linspace times it) and
+                # every distance are float64
+                data = np.array(aug, dtype=self.dtype_s)[
+                    1 + d:self.augmented_state_length, self.relevant_indices]
+                mean = data.mean(axis=0)
+                _, _, vv = np.linalg.svd(data - mean)
+                ends = vv[0] * np.linspace(-1, 1, 2)[:, np.newaxis]
+                ends += mean
+                total = 0
+                for pt in data:
+                    total += dist_of_pt_from_line(pt, ends[0], ends[-1])
+                reward += -total / self.sequence_length
+            elif not np.isnan(aug[d][0]):
                 window = np.array(aug, dtype=self.dtype_s)
                 new_rel = window[-1, self.relevant_indices]
                 if self.make_denser:

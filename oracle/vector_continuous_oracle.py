@@ -33,7 +33,11 @@ class VectorContinuousOracle:
         self.gid = (np.arange(self.N, dtype=np.int64) + env_id_offset).astype(
             np.uint32)
         self.step_index = 0
-        self.target64 = "target_point" not in e.config
+        self.line = e.config["reward_function"] == "move_along_a_line"
+        self.L = int(e.sequence_length)
+        self.target64 = "target_point" not in e.config and not self.line
+        # last L emitted relevant states (move_along_a_line), slot = step % L
+        self.hist = np.zeros((max(self.L, 1), self.N, len(self.rel)), dtype=self.R)
         self.sd = np.zeros((self.order + 1, self.N, self.D), dtype=self.R)
         self.em = np.zeros((self.N, self.D), dtype=self.R)
         self.t = np.zeros(self.N, dtype=np.int64)
@@ -53,8 +57,30 @@ class VectorContinuousOracle:
             s = (s + (x[:, k] * x[:, k]).astype(dtype)).astype(dtype)
         return np.sqrt(s).astype(dtype)
 
+    def _line_reward(self, step):
+        """rl_toy_env.py:1865-1910 per env, with numpy's own float32 SVD like
+        oracle/scalar_env.py: python-float (float64) rewards."""
+        from .scalar_env import dist_of_pt_from_line
+        L, out = self.L, np.zeros(self.N)
+        order = [(step - L + 1 + k) % L for k in range(L)]   # oldest first
+        for i in np.nonzero(self.t >= L)[0]:
+            # (the reference's window is F-ordered -- a slice combined with an
+            # index list -- so its mean runs numpy's pairwise summation)
+            data = np.asfortranarray(self.hist[order, i, :])
+            mean = data.mean(axis=0)
+            _, _, vv = np.linalg.svd(data - mean)
+            ends = vv[0] * np.linspace(-1, 1, 2)[:, np.newaxis]
+            ends += mean
+            total = 0
+            for pt in data:
+                total += dist_of_pt_from_line(pt, ends[0], ends[-1])
+            out[i] = 0.0 + -total / L
+        return out
+
     def _dist(self, x):
         R = self.R
+        if self.line:
+            return np.full(x.shape[0], np.inf)   # no target, nothing to reach
         if self.target64:
             diff = x[:, self.rel].astype(np.float64) - self.e.target_point
             return self._norm(diff, np.float64)
@@ -178,7 +204,11 @@ class VectorContinuousOracle:
             self.reached |= dist_new < radius
             self.t += 1
             # reward, carried as (value, is_real) like numpy's scalar typing
-            if e.make_denser:
+            if self.line:
+                self.hist[step % self.L] = nxt[:, self.rel]
+                r64, is_real = self._line_reward(step), np.zeros(N, dtype=bool)
+                rr = np.zeros(N, dtype=R)
+            elif e.make_denser:
                 if self.target64:
                     r64, is_real = -dist_new + dist_old, np.zeros(N, dtype=bool)
                     rr = np.zeros(N, dtype=R)
@@ -189,7 +219,9 @@ class VectorContinuousOracle:
                 r64 = (dist_new < radius).astype(np.float64)
                 rr, is_real = np.zeros(N, dtype=R), np.zeros(N, dtype=bool)
             loss = (R(e.action_loss_weight) * self._norm(a, R)).astype(R)
-            if e.make_denser and self.target64 and R is np.float32:
+            if self.line:
+                pass  # (the action loss belongs to move_to_a_point, :1943)
+            elif e.make_denser and self.target64 and R is np.float32:
                 r64 = r64 - loss.astype(np.float64)
             else:
                 rr = np.where(is_real, rr, r64.astype(R))
@@ -198,7 +230,7 @@ class VectorContinuousOracle:
             if self.delay > 0:
                 pos = step % self.delay
                 have = self.t > self.delay
-                if e.make_denser and self.target64 and R is np.float32:
+                if (self.line or (e.make_denser and self.target64)) and R is np.float32:
                     # python floats all the way through reward_buffer (:1968-1977)
                     delayed = self.ring64[pos].copy()
                     self.ring64[pos] = r64

@@ -162,6 +162,29 @@ CASES = {
                               reward_noise=0.2, reward_scale=1.5,
                               state_space_max=2.0).items()
         if k not in ("target_point", "relevant_indices")}),
+    # move_along_a_line (rl_toy_env.py:1865-1910, :2546-2576): reward = - mean
+    # distance of the last sequence_length relevant states from their fitted line
+    "cont_line_seq10": dict(config=dict(
+        seed=0, state_space_type="continuous", action_space_type="continuous",
+        state_space_dim=4, action_space_dim=4, transition_dynamics_order=1,
+        inertia=1.0, time_unit=1.0, delay=0, sequence_length=10,
+        reward_scale=1.0, reward_function="move_along_a_line",
+        action_space_max=1.0), steps=60, horizon=30),
+    "cont_line_seq3_delay": dict(config=dict(
+        seed=3, state_space_type="continuous", action_space_type="continuous",
+        state_space_dim=6, action_space_dim=6, relevant_indices=[0, 2, 3],
+        irrelevant_features=True, transition_dynamics_order=2, inertia=2.0,
+        time_unit=0.5, delay=2, sequence_length=3, reward_scale=2.0,
+        reward_shift=-0.5, reward_noise=0.1, transition_noise=0.02,
+        reward_function="move_along_a_line", state_space_max=3.0,
+        action_space_max=1.0, terminal_states=[[2.5, 2.5, 2.5]],
+        term_state_edge=1.0), steps=60, horizon=20),
+    "cont_line_2d": dict(config=dict(
+        seed=5, state_space_type="continuous", action_space_type="continuous",
+        state_space_dim=2, action_space_dim=2, transition_dynamics_order=1,
+        time_unit=0.25, sequence_length=4, reward_every_n_steps=2,
+        reward_function="move_along_a_line", state_space_max=2.0,
+        action_space_max=1.0), steps=60, horizon=30),
     # round 2: longer / wider replays of the two headline shapes
     "c2_big": dict(config=dict(
         _D, sequence_length=3, delay=2, transition_noise=0.1,

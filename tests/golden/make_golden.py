@@ -33,7 +33,7 @@ def _take(log, tag, kind):
     return vals
 
 
-def run_case(name, spec):
+def run_case(name, spec, out_dir=HERE):
     cfg = materialise(spec["config"])
     K, T, H = spec.get("lanes", 6), spec.get("steps", 48), spec.get("horizon", 12)
     env = make_reference_env(cfg)
@@ -210,11 +210,11 @@ def run_case(name, spec):
                     if not cont:
                         rec["reset_image_params"][k, t] = image_params_from(log)
     out.update(rec)
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), **out)
     return out
 
 
-def run_grid_case(name, spec):
+def run_grid_case(name, spec, out_dir=HERE):
     """Grid envs (rl_toy_env.py:1727-1778, :1947-1965, :2325-2345): actions are
     unit moves, the draws are the E-stream uniform that decides whether the
     action is replaced, the accepted replacement (GridActionSpace.sample, A
@@ -301,7 +301,7 @@ def run_grid_case(name, spec):
     flat = [(k, t, i, v) for k, t, ps in attempts_log for i, v in ps]
     out["grid_attempts"] = np.array(flat, dtype=np.int64).reshape(-1, 4)
     out.update(rec)
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), **out)
     return out
 
 

@@ -56,7 +56,10 @@ def test_cuda_replays_reference_golden(name, jit):
         return (info["state"].cpu().numpy(), r.cpu().numpy(),
                 term.cpu().numpy(), derivs)
 
-    replay_continuous_golden(vec_reset, vec_step, g, exact=is_exact_case(name))
+    # move_along_a_line: the fitted direction is fp32-accurate, not LAPACK's bits
+    line = CASES[name]["config"].get("reward_function") == "move_along_a_line"
+    replay_continuous_golden(vec_reset, vec_step, g,
+                             exact=is_exact_case(name) and not line)
 
 
 @pytest.mark.parametrize("name", ["c3_order2", "cont_noise_delay",
@@ -99,6 +102,10 @@ def test_same_seed_drop_in_numpy_streams(name):
     ("cont_term_boxes", 2000, 60, True, 25),
     ("cont_sparse", 1500, 40, True, 0),
     ("cont_unbounded", 1000, 30, True, 10),
+    ("cont_line_seq10", 600, 45, True, 25),       # move_along_a_line, 4 dims
+    ("cont_line_seq3_delay", 600, 40, True, 15),  # 3 of 6 dims, delay, noise
+    ("cont_line_2d", 800, 40, True, 0),           # closed-form 2-D direction
+    ("cont_inertia_list", 500, 30, True, 10),
 ])
 def test_philox_rollout_matches_oracle(name, N, T, autoreset, horizon):
     """Native Philox noise / reset sampling vs the oracle's restatement of the
@@ -172,7 +179,7 @@ def test_fp64_build_matches_oracle_1e12():
     np.testing.assert_allclose(got["obs"].cpu().numpy(), want["obs"],
                                rtol=1e-12, atol=1e-13)
     np.testing.assert_allclose(got["reward"].cpu().numpy(), want["reward"],
-                               rtol=1e-10, atol=1e-12)
+                               rtol=1e-12, atol=1e-12)  # the contract's fp64 bar
 
 
 def test_full_size_config3_properties():

@@ -3,8 +3,7 @@
 numbers and run against (a) the scalar oracle on CPU and (b) the CUDA path
 (`VectorRLToyEnv(1, noise="numpy")`, i.e. same seeds => same streams) on GPU.
 Each test cites the reference test it restates.  Only the 14 reference tests
-that pass at HEAD are ported (the other 6 are stale), and
-of those the ones on the supported path (no move_along_a_line)."""
+that pass at HEAD are ported (the other 6 are stale)."""
 import warnings
 
 import numpy as np
@@ -25,6 +24,10 @@ class OracleAdapter:
     def step(self, a):
         obs, r, done, _, _ = self.env.step(a)
         return obs, r, done, self.env.curr_state
+
+    def derivatives(self):
+        return np.array([np.asarray(d, dtype=np.float64)
+                         for d in self.env.state_derivatives])
 
 
 class CudaAdapter:
@@ -48,6 +51,11 @@ class CudaAdapter:
         r = r[0].cpu().numpy()
         return (obs[0].cpu().numpy(), r.item(), bool(term[0]),
                 st if self.cont else int(st))
+
+
+    def derivatives(self):
+        return self.env.get_augmented_state()["state_derivatives"][0].cpu().numpy()\
+            .astype(np.float64)
 
 
 IMPLS = [pytest.param(OracleAdapter, id="oracle"),
@@ -345,3 +353,137 @@ def test_grid_image_representations_dense_terminal_irrelevant_noise(impl):
     assert run(impl(**cfg), [[0, 1], [-1, 1], [-1, 0], [1, -1], [0.5, -0.5], [1, 2],
                              [1, 1], [0, -1], [1, 0], [0, -1], [1, 0], [0, -1],
                              [0, -1]], pad_back=True) == 1.0
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_discrete_diameter(impl):
+    """test_mdp_playground.py:2222-2391: diameter 3 (24 states in 3 independent
+    sets of 8), structure of the rewardable sequences and the reward KATs for
+    sequence_length 3 and 5 (> diameter)."""
+    cfg = dict(seed=0, state_space_type="discrete", action_space_type="discrete",
+               state_space_size=24, action_space_size=8, reward_density=0.05,
+               make_denser=False, terminal_state_density=0.25,
+               maximally_connected=True, repeats_in_sequences=False, delay=0,
+               diameter=3, sequence_length=3, reward_every_n_steps=1,
+               reward_scale=1.0, reward_shift=0.0, generate_random_mdp=True)
+    env = impl(**cfg)
+    e = env.env
+    A, S, n_term = 8, 24, 2
+    seqs = list(e.rewardable_sequences)
+    for seq in seqs:
+        for state in seq:
+            assert state not in (6, 7, 14, 15, 22, 23)
+            assert state % A < A - n_term
+    assert len(seqs) == int(0.05 * 6 * 6 * 6) * 3
+    np.testing.assert_allclose(np.sum(e.config["relevant_init_state_dist"]), 1.0,
+                               rtol=1e-5)
+    for a, want in zip([7, 1, 1, 7, 0, 7, 1], [0, 0, 1, 0, 1, 0, 0]):
+        _, r, _, _ = env.step(a)
+        np.testing.assert_allclose(r, want, rtol=1e-5)
+
+    # sub-test 2: sequence length greater than the diameter
+    cfg.update(sequence_length=5, reward_density=0.01)
+    env = impl(**cfg)
+    e = env.env
+    seqs = list(e.rewardable_sequences)
+    for seq_num, seq in enumerate(seqs):
+        for j in range(3):
+            if j / 3 < seq_num / len(seqs) < (j + 1) / 3:
+                for i, state in enumerate(seq):
+                    lo = ((i + j) * A) % S
+                    hi = ((i + j + 1) * A) % S
+                    if hi < lo:
+                        hi += S
+                    assert lo <= state < hi, (lo, state, hi)
+        for state in seq:
+            assert state % A < A - n_term
+    assert len(seqs) == int(0.01 * 6 * 6 * 6 * 5 * 5) * 3
+    # from the first state 13 the actions lead through 19, 1, 10, 21, 4
+    for a, want in zip([2, 5, 5, 1, 0, 7, 1], [0, 0, 0, 0, 1, 0, 0]):
+        _, r, _, _ = env.step(a)
+        np.testing.assert_allclose(r, want, rtol=1e-5)
+
+
+def _line(**kw):
+    cfg = dict(seed={"env": 0, "state_space": 10, "action_space": 11},
+               state_space_type="continuous", action_space_type="continuous",
+               state_space_dim=4, action_space_dim=4, transition_dynamics_order=1,
+               inertia=1, time_unit=1, delay=0, sequence_length=10,
+               reward_scale=1.0, reward_function="move_along_a_line")
+    cfg.update(kw)
+    return cfg
+
+
+def _action_sampler(D, seed=11):
+    """The reference's `env.action_space.sample()` for an unbounded float32 Box
+    (gymnasium: normal(size) cast to the dtype) on the action-space seed."""
+    from oracle.scalar_env import np_random
+    rng, _ = np_random(seed)
+    return lambda: rng.normal(size=(D,)).astype(np.float32)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_continuous_dynamics_move_along_a_line(impl):
+    """test_mdp_playground.py:31-300 (tests 1, 3, 4, 6, 7, 8; test 5 uses a
+    callable reward_noise, test 9 is stale at HEAD), the reference's own
+    tolerances: acting along a line gives reward 0 within 1e-5, random actions
+    a reward below -0.9, and the window / delay bookkeeping in between."""
+    ones = np.ones(4, dtype=np.float32)
+    env = impl(**_line())                                            # test 1
+    for i in range(20):
+        _, r, _, s = env.step(ones)
+        np.testing.assert_allclose(0.0, r, atol=1e-5, err_msg=f"step {i}")
+    np.testing.assert_allclose(s, [18.896662, 19.274975, 19.218195, 20.266975],
+                               rtol=1e-6)
+    for delay, (t_zero, t_up, t_bad) in ((0, (29, 20, 9)), (1, (30, 21, 10))):
+        env, sample, prev = impl(**_line(delay=delay)), _action_sampler(4), None
+        for i in range(40):                                          # tests 3, 4
+            _, r, _, s = env.step(sample() if i < 20 else ones)
+            if i >= t_zero:
+                np.testing.assert_allclose(0.0, r, atol=1e-5, err_msg=f"step {i}")
+            elif i >= t_up:
+                assert prev < r + 0.05, (i, prev, r)
+            elif i >= t_bad:
+                assert r < -0.9, (i, r)
+            prev = r
+    irr = _line(state_space_dim=7, action_space_dim=7, relevant_indices=[0, 1, 2, 6],
+                action_space_relevant_indices=[0, 1, 2, 6])
+    env, sample = impl(**irr), _action_sampler(7)                    # test 6
+    for i in range(20):
+        a = sample()
+        a[[0, 1, 2, 6]] = 1.0
+        _, r, _, s = env.step(a)
+        np.testing.assert_allclose(0.0, r, atol=1e-5, err_msg=f"step {i}")
+    np.testing.assert_allclose(np.asarray(s)[[0, 1, 2, 6]],
+                               [18.8967, 19.275, 19.2182, 20.843], atol=1e-4)
+    env, sample = impl(**irr), _action_sampler(7)                    # test 7
+    for i in range(20):
+        a = sample()
+        a[[3, 4, 5]] = 1.0
+        _, r, _, _ = env.step(a)
+        if i > 10:
+            assert r < -0.8, (i, r)
+    env = impl(**dict(irr, state_space_max=5, action_space_max=1))   # test 8
+    for i in range(20):
+        _, _, _, s = env.step(-np.ones(7, dtype=np.float32))
+    np.testing.assert_allclose(s, [-5] * 7)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_continuous_dynamics_order(impl):
+    """test_mdp_playground.py:415-487: third-order dynamics (time unit 0.01,
+    inertia 2) under the move_along_a_line reward: increments of the state
+    and of its first two derivatives over two steps."""
+    env = impl(**_line(state_space_dim=2, action_space_dim=2,
+                       transition_dynamics_order=3, inertia=2.0, time_unit=0.01,
+                       sequence_length=3))
+    s0, d0 = np.asarray(env.state(), dtype=np.float64).copy(), env.derivatives()
+    a = np.array([2.0, 1.0], dtype=np.float32)
+    for k1, k2 in ((1 / 6, 1 / 2), (7 / 6, 3 / 2)):
+        _, _, _, s = env.step(a)
+        s, d = np.asarray(s, dtype=np.float64), env.derivatives()
+        np.testing.assert_allclose(s - s0, k1 * np.array([1, 0.5]) * 1e-6, atol=1e-7)
+        np.testing.assert_allclose(d[1] - d0[1], k2 * np.array([1, 0.5]) * 1e-4,
+                                   rtol=1e-5)
+        np.testing.assert_allclose(d[2] - d0[2], np.array([1, 0.5]) * 1e-2, rtol=1e-6)
+        s0, d0 = s.copy(), d
