@@ -490,6 +490,68 @@ int mdpp_render_continuous(mdpp_ctx* ctx, const mdpp_image_continuous_config* cf
                            void* cuda_stream);
 #endif
 
+/* ------------------------------------------------------------------------
+ * GymEnvWrapper's post-processing tail for EXTERNAL vector environments
+ * (replaces envs/gym_env_wrapper.py:350-439 and get_transformed_image
+ * :523-618).  The caller steps its own environments in
+ * between: mdpp_tail_actions before, mdpp_tail_post / mdpp_tail_image_shift
+ * after.  Noise comes from replay arrays (opts->noise_mode == REPLAY) or from
+ * Philox streams keyed by (seed, env, step_index) like the step kernels.
+ * --------------------------------------------------------------------- */
+typedef struct mdpp_tail_config {
+  int32_t discrete;             /* state_space_type == "discrete" (:353)     */
+  int32_t n_actions;            /* env.action_space.n (discrete)             */
+  int32_t obs_dim;              /* continuous: length of the observation     */
+  int32_t obs_is_f64;           /* continuous: observations are double       */
+  int32_t delay;                /* reward delay FIFO depth (:91-96)          */
+  int32_t has_transition_noise; /* "transition_noise" given and truthy       */
+  int32_t has_reward_noise;     /* "reward_noise" key present                */
+  int32_t image_side;           /* image shift: side of the (square) images  */
+  int32_t image_channels;       /* 3 (the reference's RGB path)              */
+  int32_t image_padding;        /* :161-164, default 20                      */
+  int32_t sh_quant;             /* image_sh_quant                            */
+  int32_t has_shift;            /* "shift" in image_transforms               */
+  double transition_noise;      /* discrete: probability; continuous: sigma  */
+  double reward_noise_std;
+  double reward_scale, reward_shift, term_state_reward;
+} mdpp_tail_config;
+
+typedef struct mdpp_tail_state {
+  int64_t n_envs;
+  double* ring;        /* [delay][N] delayed rewards, slot = step % delay     */
+  int32_t* t_episode;  /* [N] steps since the FIFO was cleared                */
+} mdpp_tail_state;
+
+#ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
+/* :353-366: applied[i] = actions[i], or one of the other n_actions - 1 with
+ * probability transition_noise.  Replay: `replay_u` [N] is the uniform numpy's
+ * choice(n, p=probs) consumed (cumsum / searchsorted restated in fp64).       */
+int mdpp_tail_actions(mdpp_ctx* ctx, const mdpp_tail_config* cfg,
+                      const int32_t* actions, int32_t* applied,
+                      const double* replay_u, int64_t n_envs,
+                      const mdpp_step_opts* opts, void* cuda_stream);
+/* :405-436: continuous observations get N(0, sigma) noise (out_obs = obs +
+ * noise, NULL obs / out_obs skips it); rewards go through the delay FIFO, the
+ * flush at `done`, noise, scale, shift.  At done the FIFO is cleared.  The
+ * reference raises TypeError on every terminal step (:414 multiplies a list by
+ * a float); the flush implements the line with the buffer read as an array.  */
+int mdpp_tail_post(mdpp_ctx* ctx, const mdpp_tail_config* cfg,
+                   const mdpp_tail_state* st, const void* obs, void* out_obs,
+                   const double* reward, const uint8_t* done, double* out_reward,
+                   const double* replay_reward_noise, const double* replay_obs_noise,
+                   const mdpp_step_opts* opts, void* cuda_stream);
+/* :523-618: img uint8 [N][side][side][3] -> out uint8 [N][tot][tot][3], tot =
+ * side + 2 padding, out[x][y] = canvas[y][x]; the shift is drawn
+ * (integers(-padding + 1, padding) per axis, truncated to sh_quant) or replayed
+ * from `replay_shift` int32 [N][2] (the two raw integers); `shift_out` [N][2]
+ * (optional) receives the raw draws.                                         */
+int mdpp_tail_image_shift(mdpp_ctx* ctx, const mdpp_tail_config* cfg,
+                          const uint8_t* img, uint8_t* out,
+                          const int32_t* replay_shift, int32_t* shift_out,
+                          int64_t n_envs, const mdpp_step_opts* opts,
+                          void* cuda_stream);
+#endif
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "mdpp_continuous_reset", "mdpp_render_discrete", "mdpp_render_continuous",
     "mdpp_set_grid_config", "mdpp_grid_rollout", "mdpp_grid_reset",
     "mdpp_ziggurat_tables",
+    "mdpp_tail_actions", "mdpp_tail_post", "mdpp_tail_image_shift",
 )
 MDPP_MAX_DIM, MDPP_MAX_ORDER, MDPP_MAX_TERM_BOXES = 16, 4, 8
 
@@ -202,6 +203,25 @@ class GridIO(C.Structure):
     ]
 
 
+class TailConfig(C.Structure):
+    _fields_ = [
+        ("discrete", C.c_int32), ("n_actions", C.c_int32), ("obs_dim", C.c_int32),
+        ("obs_is_f64", C.c_int32), ("delay", C.c_int32),
+        ("has_transition_noise", C.c_int32), ("has_reward_noise", C.c_int32),
+        ("image_side", C.c_int32), ("image_channels", C.c_int32),
+        ("image_padding", C.c_int32), ("sh_quant", C.c_int32),
+        ("has_shift", C.c_int32),
+        ("transition_noise", C.c_double), ("reward_noise_std", C.c_double),
+        ("reward_scale", C.c_double), ("reward_shift", C.c_double),
+        ("term_state_reward", C.c_double),
+    ]
+
+
+class TailState(C.Structure):
+    _fields_ = [("n_envs", C.c_int64), ("ring", C.c_void_p),
+                ("t_episode", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -255,6 +275,13 @@ def load():
         P, C.POINTER(GridState), C.POINTER(GridIO), C.POINTER(StepOpts), P]
     lib.mdpp_grid_reset.argtypes = [
         P, C.POINTER(GridState), P, P, P, C.POINTER(StepOpts), P]
+    lib.mdpp_tail_actions.argtypes = [
+        P, C.POINTER(TailConfig), P, P, P, C.c_int64, C.POINTER(StepOpts), P]
+    lib.mdpp_tail_post.argtypes = [
+        P, C.POINTER(TailConfig), C.POINTER(TailState), P, P, P, P, P, P, P,
+        C.POINTER(StepOpts), P]
+    lib.mdpp_tail_image_shift.argtypes = [
+        P, C.POINTER(TailConfig), P, P, P, P, C.c_int64, C.POINTER(StepOpts), P]
     if lib.mdpp_abi_version() != ABI_VERSION:
         raise RuntimeError("libmdpp_b200.so ABI version mismatch; rebuild")
     _lib = lib

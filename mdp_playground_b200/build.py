@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libmdpp_b200.so")
 SOURCES = ["context.cu", "discrete.cu", "discrete_off.cu", "discrete_replay.cu",
            "discrete_philox_f64.cu", "discrete_philox_fast.cu",
            "discrete_philox_zig.cu", "continuous.cu",
-           "render.cu", "grid.cu",
+           "render.cu", "grid.cu", "wrapper_tail.cu",
            "jit.cu"]
 HEADERS = ["internal.h", "device_types.h", "philox.cuh", "discrete_kernels.cuh",
            "continuous_kernels.cuh", "ziggurat.cuh", "ziggurat_tables.h",

@@ -55,3 +55,34 @@ def make_reference_env(config):
         logging.disable(logging.NOTSET)
     env.logger.setLevel(logging.ERROR)
     return env
+
+
+def load_reference_wrapper():
+    """The reference's GymEnvWrapper class (envs/gym_env_wrapper.py).  Its
+    module imports Atari machinery at the top (`gymnasium.wrappers.
+    AtariPreprocessing`, `ale_py`, `gym.register_envs`) that the wrapper tail
+    never touches: stubbed here, for this import only."""
+    import importlib
+    import types
+    load_reference()
+    import gymnasium
+    saved = {k: sys.modules.get(k) for k in ("gymnasium.wrappers", "ale_py")}
+    wrappers = types.ModuleType("gymnasium.wrappers")
+    wrappers.AtariPreprocessing = type("AtariPreprocessing", (), {})
+    sys.modules["gymnasium.wrappers"] = wrappers
+    sys.modules["ale_py"] = types.ModuleType("ale_py")
+    had = hasattr(gymnasium, "register_envs")
+    if not had:
+        gymnasium.register_envs = lambda module: None
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            mod = importlib.import_module("mdp_playground.envs.gym_env_wrapper")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        if not had:
+            del gymnasium.register_envs
+    return mod.GymEnvWrapper
