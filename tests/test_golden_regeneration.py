@@ -29,3 +29,18 @@ def test_fixture_regenerates_identically(name, tmp_path):
     for k in committed:
         assert fresh[k].dtype == committed[k].dtype, k
         assert np.array_equal(fresh[k], committed[k], equal_nan=fresh[k].dtype.kind == "f"), k
+
+
+def test_wrapper_fixtures_regenerate_identically(tmp_path):
+    """Same for the GymEnvWrapper tail fixtures (tests/golden/wrap_*.npz)."""
+    from tests.golden.make_wrapper_golden import WRAPPER_CASES, run_wrapper_case
+    for name, spec in WRAPPER_CASES.items():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            run_wrapper_case(name, spec, out_dir=str(tmp_path))
+        fresh = dict(np.load(tmp_path / (name + ".npz"), allow_pickle=False))
+        committed = gu.load(name)
+        assert sorted(fresh) == sorted(committed)
+        for k in committed:
+            assert np.array_equal(fresh[k], committed[k],
+                                  equal_nan=fresh[k].dtype.kind == "f"), (name, k)
