@@ -420,6 +420,11 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
                     p.T >= kZigWindow);
     if (const char* ch = std::getenv("MDPP_JIT_CHUNK"))  // tuning knob (4/8/16)
       defs.push_back(std::string("-DMDPP_JIT_CHUNK=") + ch);
+    else if (groups.size() > 1)
+      // multi-group builds keep L / delay / noise flags run-time: a chunk of 4
+      // halves the hot loop's code (ncu: no_instruction 2.4 stalls per issue
+      // with chunks of 8 and fp64 normals); measured +6 % (fast) / +9 % (fp64)
+      defs.push_back("-DMDPP_JIT_CHUNK=4");
     if (const char* mb = std::getenv("MDPP_JIT_MINBLOCKS"))  // tuning knob
       defs.push_back(std::string("-DMDPP_JIT_MINBLOCKS=") + mb);
     if (const char* ex = std::getenv("MDPP_JIT_EXTRA")) {  // experiments: "-DX=1 -DY"

@@ -12,7 +12,7 @@ cfgs = [dict(base, delay=d, sequence_length=L, transition_noise=pn, reward_noise
 N, T = 1 << 20, 100
 with warnings.catch_warnings():
     warnings.simplefilter("ignore")
-    env = VectorRLToyEnv(N, autoreset=True, horizon=100, config_groups=cfgs, normal_precision="fast")
+    env = VectorRLToyEnv(N, autoreset=True, horizon=100, config_groups=cfgs, normal_precision=(sys.argv[1] if len(sys.argv) > 1 else "fast"))
 acts = torch.randint(0, 8, (T, N), dtype=torch.int32, device="cuda")
 out = env.rollout(T, actions=acts, want_final_obs=False)
 for _ in range(3): env.rollout(T, actions=acts, out=out)
