@@ -697,7 +697,8 @@ class VectorRLToyEnv:
         underlying state, info["final_obs"] (autoreset only) the state before
         the same-step reset."""
         if (replay is None and self.noise == "philox" and self._step_buffers > 0
-                and not self.spec.image_representations
+                and (not self.spec.image_representations
+                     or self.spec.kind == "discrete")
                 and not getattr(self, "_use_dev_counter", False)):
             return self._step_fast(actions)
         N = self.num_envs
@@ -760,20 +761,36 @@ class VectorRLToyEnv:
                 io.obs_dtype = self._OBS_CODES[odt]
             state = out["obs"][0]
             obs = state  # (replaced per call when dtype_o needs a cast)
+            render = None
+            if kind == "discrete" and self.spec.image_representations:
+                # the renderer runs as a programmatic dependent of the step
+                # kernel (its zero fill overlaps it), marshalled once as well
+                M = state.numel()
+                img = torch.empty(tuple(state.shape[:1]) + self.obs_shape,
+                                  dtype=torch.uint8, device=dev)
+                prm = torch.empty((M, 5), dtype=torch.int32, device=dev)
+                ropts = self._opts(1)
+                ropts.flags = _lib.MDPP_LAUNCH_OVERLAP_PREVIOUS
+                render = (ropts, C.byref(ropts), _ptr(state), _ptr(prm), _ptr(img),
+                          M, prm)
+                obs = img
             info = {"state": state}
             if self.autoreset:
                 info["final_obs"] = out["final_obs"][0]
             ret = (obs, out["reward"][0], out["terminated"][0], out["truncated"][0], info)
-            sets.append((io, C.byref(io), ret, out))
+            sets.append((io, C.byref(io), ret, out, render))
         self._step_sets = sets
         self._step_opts = self._opts(1)
         if kind == "continuous" and not (self.has_pnoise or self.has_rnoise) \
                 and not self.autoreset:
             self._step_opts.noise_mode = _lib.MDPP_NOISE_OFF
         self._step_opts_ref = C.byref(self._step_opts)
+        if self.spec.image_representations and kind == "discrete":
+            self._img_cfg_ref = C.byref(self._img_cfg)
         self._step_state_ref = C.byref(self._state)
         # dtype_o values the kernels do not write (e.g. int16): cast per call
         self._step_cast = kind == "discrete" and \
+            not self.spec.image_representations and \
             self._cast_obs(sets[0][3]["obs"][0]).dtype != odt
 
     def _step_fast(self, actions):
@@ -793,7 +810,7 @@ class VectorRLToyEnv:
         if actions.numel() != self._step_numel:
             raise AssertionError((tuple(actions.shape), self._step_arow))
         flip = self._step_flip
-        io, io_ref, ret, _ = sets[flip]
+        io, io_ref, ret, _, render = sets[flip]
         self._step_flip = flip + 1 if flip + 1 < len(sets) else 0
         io.actions = actions.data_ptr()
         o = self._step_opts
@@ -804,6 +821,16 @@ class VectorRLToyEnv:
         if rc:
             self._check(rc)
         self._step_index += 1
+        if render is not None:
+            ropts, ropts_ref, st_p, prm_p, img_p, M, prm = render
+            ropts.step_index = self._step_index  # the observation AFTER the step
+            ropts.seed = self.philox_seed
+            rc = self._lib.mdpp_render_discrete(
+                self._ctx, self._img_cfg_ref, st_p, None, prm_p, img_p, M,
+                self.num_envs, 3, ropts_ref, _raw_stream(self._dev_index))
+            if rc:
+                self._check(rc)
+            self.last_image_params = prm
         if self._step_cast:
             ret = (self._cast_obs(ret[4]["state"]),) + ret[1:]
         self.curr_obs = ret[0]

@@ -209,3 +209,31 @@ def test_discrete_renderer_other_image_sizes(W, H):
             R=Rk, shift_w=sw, shift_h=sh, rotation=None if rot < 0 else rot,
             flip=flip))
         assert np.array_equal(imgs[k, :, :, 0], want), (k, params[k])
+
+
+@pytest.mark.parametrize("transforms", ["shift", "shift,scale,rotate,flip"])
+def test_buffered_image_step_equals_unbuffered(transforms):
+    """step() of an image env through the pre-marshalled buffers (step kernel +
+    renderer launched as its programmatic dependent) == the allocate-per-call
+    path, pixel for pixel, incl. the irrelevant sub-image."""
+    import torch
+    for irr in (False, True):
+        cfg = dict(seed=0, state_space_type="discrete", action_space_type="discrete",
+                   state_space_size=[8, 8] if irr else 8,
+                   action_space_size=[8, 8] if irr else 8,
+                   irrelevant_features=irr, reward_density=0.25,
+                   terminal_state_density=0.25, image_representations=True,
+                   image_transforms=transforms, image_sh_quant=2, image_ro_quant=1,
+                   image_scale_range=(0.5, 1.5))
+        N = 257
+        fast = make_env(N, autoreset=True, horizon=5, **cfg)
+        slow = make_env(N, autoreset=True, horizon=5, step_buffers=0, **cfg)
+        shape = (6, N, 2) if irr else (6, N)
+        a = torch.randint(0, 8, shape, dtype=torch.int32, device="cuda",
+                          generator=torch.Generator("cuda").manual_seed(4))
+        for t in range(6):
+            f, s = fast.step(a[t]), slow.step(a[t])
+            assert f[0].shape == s[0].shape and f[0].dtype == torch.uint8
+            assert torch.equal(f[0], s[0]), (irr, t)
+            assert torch.equal(f[1], s[1]) and torch.equal(f[2], s[2])
+            assert torch.equal(fast.last_image_params, slow.last_image_params)
