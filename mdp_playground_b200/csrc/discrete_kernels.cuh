@@ -866,7 +866,12 @@ struct ZigStage {
   int rank, n_act;   // this lane's rank among them, and their number
 };
 
-__device__ __forceinline__ void zig_fill(const RolloutParams& p, const GroupView& v,
+#ifdef MDPP_ZIG_FILL_NOINLINE
+#define MDPP_ZIG_FILL_ATTR __noinline__
+#else
+#define MDPP_ZIG_FILL_ATTR __forceinline__
+#endif
+static __device__ MDPP_ZIG_FILL_ATTR void zig_fill(const RolloutParams& p, const GroupView& v,
                                          const ZigStage& zst, uint32_t gid,
                                          uint64_t g0) {  // even global step
   const int lane = threadIdx.x & 31;

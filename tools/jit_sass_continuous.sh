@@ -16,7 +16,7 @@ SRC
 bits() { python3 -c "import struct,sys; print('0x%xll' % struct.unpack('<Q', struct.pack('<d', float(sys.argv[1])))[0])" "$1"; }
 DEFS="-DMDPP_JIT -DMDPP_C_REAL=float -DMDPP_C_NOISE=2 -DMDPP_C_DIM=6 -DMDPP_C_ORDER=2 -DMDPP_C_NREL=2
  -DMDPP_C_DELAY=0 -DMDPP_C_EVERY_N=1 -DMDPP_C_DENSE=true -DMDPP_C_PNOISE=false -DMDPP_C_RNOISE=false
- -DMDPP_C_IMAGE=false -DMDPP_C_TARGET64=false -DMDPP_C_NORMAL=0 -DMDPP_C_NBOX=0 -DMDPP_C_HORIZON=100
+ -DMDPP_C_IMAGE=false -DMDPP_C_TARGET64=false -DMDPP_C_NORMAL=0 -DMDPP_C_IMODE=0 -DMDPP_C_LINE=false -DMDPP_C_SEQ=1 -DMDPP_C_NBOX=0 -DMDPP_C_HORIZON=100
  -DMDPP_C_AUTORESET=true -DMDPP_C_N_ENVS=1048576ll -DMDPP_C_FAST=true -DMDPP_C_REL0=0 -DMDPP_C_REL1=1"
 for k in 2 3 4 5 6 7 8 9 10 11 12 13 14 15; do DEFS="$DEFS -DMDPP_C_REL$k=0"; done
 DEFS="$DEFS -DMDPP_C_AMAX_BITS=$(bits 1.0) -DMDPP_C_SMAX_BITS=$(bits 10.0) -DMDPP_C_INERTIA_BITS=$(bits 1.0)
