@@ -295,8 +295,23 @@ typedef struct mdpp_continuous_config {
 #define MDPP_REWARD_POINT 0
 #define MDPP_REWARD_LINE 1
 
+/* One configuration group of a heterogeneous continuous launch (a sweep over
+ * time_unit / action_space_max / noise / delay / ... cells in ONE launch, like
+ * mdpp_set_discrete_groups): groups tile the env range contiguously and must
+ * agree on dim, relevant_indices, dtype, reward function and image mode --
+ * what shapes the state arrays and I/O rows (`derivs` then has max(order) + 1
+ * planes).  The delay ring has the
+ * depth of the largest delay; statistics rows are [slot][group][MDPP_N_STATS]. */
+typedef struct mdpp_continuous_group {
+  mdpp_continuous_config cfg;
+  int64_t env_begin, env_count;
+  int64_t global_id_base;  /* global Philox id of the group's first env      */
+} mdpp_continuous_group;
+
 #ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
 int mdpp_set_continuous_config(mdpp_ctx* ctx, const mdpp_continuous_config* cfg);
+int mdpp_set_continuous_groups(mdpp_ctx* ctx, const mdpp_continuous_group* groups,
+                               int32_t n_groups);
 #endif
 
 /* Persistent state, struct-of-arrays over envs (DEVICE pointers, `real`).   */

@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "mdpp_set_grid_config", "mdpp_grid_rollout", "mdpp_grid_reset",
     "mdpp_ziggurat_tables",
     "mdpp_tail_actions", "mdpp_tail_post", "mdpp_tail_image_shift",
+    "mdpp_set_continuous_groups",
 )
 MDPP_MAX_DIM, MDPP_MAX_ORDER, MDPP_MAX_TERM_BOXES = 16, 4, 8
 
@@ -113,6 +114,11 @@ class ContinuousConfig(C.Structure):
         ("inertia_vec", C.c_double * MDPP_MAX_DIM),
         ("sequence_length", C.c_int32), ("reserved_cfg", C.c_int32),
     ]
+
+
+class ContinuousGroup(C.Structure):
+    _fields_ = [("cfg", ContinuousConfig), ("env_begin", C.c_int64),
+                ("env_count", C.c_int64), ("global_id_base", C.c_int64)]
 
 
 class ContinuousState(C.Structure):
@@ -260,6 +266,7 @@ def load():
     lib.mdpp_jit_log.restype = C.c_char_p
     lib.mdpp_jit_selftest.argtypes = [C.c_char_p, C.c_int]
     lib.mdpp_set_continuous_config.argtypes = [P, C.POINTER(ContinuousConfig)]
+    lib.mdpp_set_continuous_groups.argtypes = [P, C.POINTER(ContinuousGroup), C.c_int32]
     lib.mdpp_continuous_rollout.argtypes = [
         P, C.POINTER(ContinuousState), C.POINTER(ContinuousIO),
         C.POINTER(StepOpts), P]

@@ -97,6 +97,8 @@ extern "C" void mdpp_destroy(mdpp_ctx* ctx) {
   jit_release(ctx);
   free_discrete(ctx);
   if (ctx->d_zig) cudaFree(ctx->d_zig);
+  if (ctx->c_groups) cudaFree(ctx->c_groups);
+  if (ctx->c_cta_map) cudaFree(ctx->c_cta_map);
   delete ctx;
 }
 

@@ -47,6 +47,21 @@ struct ContinuousParams {
   const uint8_t* mask;
   const void* init_states;
   void* reset_obs;
+  // heterogeneous launches (mdpp_set_continuous_groups): CTA -> (group, chunk
+  // of kCBlock envs); every CTA reads its group's configuration from `groups`.
+  // NULL / 0 for the single-configuration launch (cfg / tu_pow above).
+  const struct ContinuousGroupDev* groups;
+  const CtaMapEntry* cta_map;
+  int32_t n_groups, reserved1;
+};
+
+// One configuration group of a heterogeneous continuous launch: the groups
+// share dim / order / relevant indices / dtype (the state arrays' shape) and
+// differ in their scalars.
+struct ContinuousGroupDev {
+  mdpp_continuous_config cfg;
+  double tu_pow[MDPP_MAX_ORDER];
+  int64_t env_begin, env_count, gid_base;
 };
 
 template <typename R> struct RealOps;
@@ -74,7 +89,7 @@ template <> struct RealOps<double> {
 
 // relevant_indices[k]: a literal table in the specialised build so that
 // indexing the register-resident state with it stays static.
-__device__ __forceinline__ int rel_index(const ContinuousParams& p, int k) {
+__device__ __forceinline__ int rel_index(const mdpp_continuous_config& cfg, int k) {
 #ifdef MDPP_JIT
   constexpr int kRel[MDPP_MAX_DIM] = {
       MDPP_C_REL0, MDPP_C_REL1, MDPP_C_REL2, MDPP_C_REL3, MDPP_C_REL4, MDPP_C_REL5,
@@ -82,7 +97,7 @@ __device__ __forceinline__ int rel_index(const ContinuousParams& p, int k) {
       MDPP_C_REL11, MDPP_C_REL12, MDPP_C_REL13, MDPP_C_REL14, MDPP_C_REL15};
   return kRel[k];
 #else
-  return p.cfg.relevant_indices[k];
+  return cfg.relevant_indices[k];
 #endif
 }
 
@@ -196,11 +211,12 @@ __device__ __forceinline__ R seq_norm(int n, F elem) {
 // Philox Box sample of one env (gymnasium Box.sample: uniform in [-max, max]
 // when bounded, N(0,1) when unbounded, cast to dtype_s).
 template <typename R>
-__device__ __forceinline__ void box_sample(const ContinuousParams& p, int D,
+__device__ __forceinline__ void box_sample(const ContinuousParams& p,
+                                           const mdpp_continuous_config& cfg, int D,
                                            uint32_t gid, uint32_t ep,
                                            int attempt, R* out) {
-  const bool bounded = isfinite(p.cfg.state_space_max);
-  const double hi = (double)(R)p.cfg.state_space_max, lo = -hi;
+  const bool bounded = isfinite(cfg.state_space_max);
+  const double hi = (double)(R)cfg.state_space_max, lo = -hi;
 #pragma unroll
   for (int c = 0; c < MDPP_MAX_DIM / 2; ++c) {
     if (2 * c < D) {
@@ -220,17 +236,17 @@ __device__ __forceinline__ void box_sample(const ContinuousParams& p, int D,
 }
 
 template <typename R>
-__device__ __forceinline__ bool in_term_box(const ContinuousParams& p, int NREL,
+__device__ __forceinline__ bool in_term_box(const mdpp_continuous_config& cfg, int NREL,
                                             const R* x /* full state */) {
   bool any = false;
-  for (int b = 0; b < p.cfg.n_term_boxes; ++b) {
+  for (int b = 0; b < cfg.n_term_boxes; ++b) {
     bool in = true;
 #pragma unroll
     for (int k = 0; k < MDPP_MAX_DIM; ++k)
       if (k < NREL) {
-        const R v = x[rel_index(p, k)];
-        in = in && v >= (R)p.cfg.term_low[b * MDPP_MAX_DIM + k] &&
-             v <= (R)p.cfg.term_high[b * MDPP_MAX_DIM + k];
+        const R v = x[rel_index(cfg, k)];
+        in = in && v >= (R)cfg.term_low[b * MDPP_MAX_DIM + k] &&
+             v <= (R)cfg.term_high[b * MDPP_MAX_DIM + k];
       }
     any = any || in;
   }
@@ -243,14 +259,15 @@ template <typename R> struct RowVal { R v[MDPP_MAX_DIM]; };
 // falls into a terminal box.  Rare and big (Philox + fp64), so out of line;
 // the row comes back by value and the caller's state stays in registers.
 template <typename R>
-__device__ __noinline__ RowVal<R> sample_reset_state(const ContinuousParams& p, int D,
-                                                     int NREL, int NBOX,
+__device__ __noinline__ RowVal<R> sample_reset_state(const ContinuousParams& p,
+                                                     const mdpp_continuous_config& cfg,
+                                                     int D, int NREL, int NBOX,
                                                      uint32_t gid, uint32_t ep) {
   RowVal<R> s0;
 #pragma unroll 1
   for (int attempt = 0; attempt < 64; ++attempt) {
-    box_sample<R>(p, D, gid, ep, attempt, s0.v);
-    if (!(NBOX > 0 && in_term_box<R>(p, NREL, s0.v))) break;
+    box_sample<R>(p, cfg, D, gid, ep, attempt, s0.v);
+    if (!(NBOX > 0 && in_term_box<R>(cfg, NREL, s0.v))) break;
   }
   return s0;
 }
@@ -382,51 +399,99 @@ __device__ __noinline__ double line_reward(const R* hist, int64_t N, int64_t env
   return __dadd_rn(0.0, __ddiv_rn(-total, (double)L));
 }
 
-template <typename R, int NOISE>
+// The configuration a thread works under: the launch's (kernel parameters,
+// constant bank) or, in a heterogeneous launch, its CTA's group staged in
+// shared memory, with the env range and Philox id base of that group.
+struct ContinuousGroupSel {
+  int64_t env;      // index into the state arrays
+  int64_t local;    // index inside the group
+  uint32_t gid;
+  bool active;
+  int group;
+};
+
+// (shared-memory copy of the CTA's group; empty in single-configuration builds)
+template <bool G> struct GroupSmem { ContinuousGroupDev g; };
+template <> struct GroupSmem<false> { int unused; };
+__device__ __forceinline__ ContinuousGroupDev* group_ptr(GroupSmem<true>& s) { return &s.g; }
+__device__ __forceinline__ ContinuousGroupDev* group_ptr(GroupSmem<false>&) { return nullptr; }
+
+template <bool GROUPS>
+__device__ __forceinline__ ContinuousGroupSel select_group(
+    const ContinuousParams& p, ContinuousGroupDev* gsm, int64_t N) {
+  ContinuousGroupSel s;
+  if (GROUPS) {
+    const CtaMapEntry me = p.cta_map[blockIdx.x];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.groups + me.group);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(gsm);
+    for (int i = threadIdx.x; i < (int)(sizeof(ContinuousGroupDev) / 4); i += kCBlock)
+      dst[i] = src[i];
+    __syncthreads();
+    s.local = (int64_t)me.chunk * kCBlock + threadIdx.x;
+    s.active = s.local < gsm->env_count;
+    s.env = gsm->env_begin + (s.active ? s.local : 0);
+    s.gid = (uint32_t)(p.env_id_offset + gsm->gid_base + (s.active ? s.local : 0));
+    s.group = me.group;
+  } else {
+    const int64_t env_raw = (int64_t)blockIdx.x * kCBlock + threadIdx.x;
+    s.active = env_raw < N;
+    s.env = s.active ? env_raw : 0;
+    s.local = s.env;
+    s.gid = (uint32_t)(p.env_id_offset + s.env);
+    s.group = 0;
+  }
+  return s;
+}
+
+template <typename R, int NOISE, bool GROUPS = false>
 __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   using O = RealOps<R>;
-  const int D = MDPP_C_CONST(DIM, p.cfg.dim);
-  const int ORDER = MDPP_C_CONST(ORDER, p.cfg.order);
-  const int NREL = MDPP_C_CONST(NREL, p.cfg.n_relevant);
-  const int DELAY = MDPP_C_CONST(DELAY, p.cfg.delay);
-  const int EVERY_N = MDPP_C_CONST(EVERY_N, p.cfg.reward_every_n_steps);
-  const bool DENSE = MDPP_C_CONST(DENSE, p.cfg.dense != 0);
-  const bool PNOISE = MDPP_C_CONST(PNOISE, p.cfg.has_transition_noise != 0);
-  const bool RNOISE = MDPP_C_CONST(RNOISE, p.cfg.has_reward_noise != 0);
-  const bool IMAGE = MDPP_C_CONST(IMAGE, p.cfg.image_mode != 0);
-  const bool TARGET64 = MDPP_C_CONST(TARGET64, p.cfg.target_is_f64 != 0);
+  __shared__ GroupSmem<GROUPS> gsm_store;
+  ContinuousGroupDev* gsm = group_ptr(gsm_store);
+  const int64_t N = MDPP_C_CONST(N_ENVS, p.st.n_envs);
+  const ContinuousGroupSel sel = select_group<GROUPS>(p, gsm, N);
+  const mdpp_continuous_config& cfg = GROUPS ? gsm->cfg : p.cfg;
+  const double* tu_rt = GROUPS ? gsm->tu_pow : p.tu_pow;
+  const int D = MDPP_C_CONST(DIM, cfg.dim);
+  const int ORDER = MDPP_C_CONST(ORDER, cfg.order);
+  const int NREL = MDPP_C_CONST(NREL, cfg.n_relevant);
+  const int DELAY = MDPP_C_CONST(DELAY, cfg.delay);
+  const int EVERY_N = MDPP_C_CONST(EVERY_N, cfg.reward_every_n_steps);
+  const bool DENSE = MDPP_C_CONST(DENSE, cfg.dense != 0);
+  const bool PNOISE = MDPP_C_CONST(PNOISE, cfg.has_transition_noise != 0);
+  const bool RNOISE = MDPP_C_CONST(RNOISE, cfg.has_reward_noise != 0);
+  const bool IMAGE = MDPP_C_CONST(IMAGE, cfg.image_mode != 0);
+  const bool TARGET64 = MDPP_C_CONST(TARGET64, cfg.target_is_f64 != 0);
   // launch shape: literals in the specialised build.  FAST = the standard
   // rollout signature (obs, reward, terminated, truncated written, no
   // final_obs), so no per-step NULL tests survive in the loop.
-  const int NBOX = MDPP_C_CONST(NBOX, p.cfg.n_term_boxes);
+  const int NBOX = MDPP_C_CONST(NBOX, cfg.n_term_boxes);
   const int HORIZON = MDPP_C_CONST(HORIZON, p.horizon);
   const bool AUTORESET = MDPP_C_CONST(AUTORESET, p.autoreset != 0);
   const bool FAST = MDPP_C_CONST(FAST, false);
   const bool FAST_NORMAL = MDPP_C_CONST(NORMAL, p.normal_mode) == MDPP_NORMAL_FAST;
-  const int64_t N = MDPP_C_CONST(N_ENVS, p.st.n_envs);
-  const int64_t env_raw = (int64_t)blockIdx.x * kCBlock + threadIdx.x;
-  const bool active = env_raw < N;
-  const int64_t env = active ? env_raw : 0;
-  const uint32_t gid = (uint32_t)(p.env_id_offset + env);
+  const bool active = sel.active;
+  const int64_t env = sel.env;
+  const uint32_t gid = sel.gid;
 
-  const R amax = (R)MDPP_C_F64(AMAX, p.cfg.action_space_max);
-  const R smax = (R)MDPP_C_F64(SMAX, p.cfg.state_space_max);
-  const R inertia = (R)MDPP_C_F64(INERTIA, p.cfg.inertia);
-  const int IMODE = MDPP_C_CONST(IMODE, p.cfg.inertia_mode);  // per-dimension inertia
-  const bool LINE = MDPP_C_CONST(LINE, p.cfg.reward_kind == MDPP_REWARD_LINE);
-  const int SEQ = MDPP_C_CONST(SEQ, p.cfg.sequence_length);
-  const double radius64 = MDPP_C_F64(RADIUS, p.cfg.target_radius);
+  const R amax = (R)MDPP_C_F64(AMAX, cfg.action_space_max);
+  const R smax = (R)MDPP_C_F64(SMAX, cfg.state_space_max);
+  const R inertia = (R)MDPP_C_F64(INERTIA, cfg.inertia);
+  const int IMODE = MDPP_C_CONST(IMODE, cfg.inertia_mode);  // per-dimension inertia
+  const bool LINE = MDPP_C_CONST(LINE, cfg.reward_kind == MDPP_REWARD_LINE);
+  const int SEQ = MDPP_C_CONST(SEQ, cfg.sequence_length);
+  const double radius64 = MDPP_C_F64(RADIUS, cfg.target_radius);
   const R radius_r = (R)radius64;
-  const double alw = MDPP_C_F64(ALW, p.cfg.action_loss_weight);
-  const double r_scale = MDPP_C_F64(SCALE, p.cfg.reward_scale);
-  const double r_shift = MDPP_C_F64(SHIFT, p.cfg.reward_shift);
+  const double alw = MDPP_C_F64(ALW, cfg.action_loss_weight);
+  const double r_scale = MDPP_C_F64(SCALE, cfg.reward_scale);
+  const double r_shift = MDPP_C_F64(SHIFT, cfg.reward_shift);
   const double term_add = MDPP_C_F64(
-      TERM_ADD, __dmul_rn(p.cfg.term_state_reward, p.cfg.reward_scale));
-  const double p_std = MDPP_C_F64(P_STD, p.cfg.transition_noise_std);
-  const double r_std = MDPP_C_F64(R_STD, p.cfg.reward_noise_std);
+      TERM_ADD, __dmul_rn(cfg.term_state_reward, cfg.reward_scale));
+  const double p_std = MDPP_C_F64(P_STD, cfg.transition_noise_std);
+  const double r_std = MDPP_C_F64(R_STD, cfg.reward_noise_std);
   const double tu_pow[MDPP_MAX_ORDER] = {
-      MDPP_C_F64(TU1, p.tu_pow[0]), MDPP_C_F64(TU2, p.tu_pow[1]),
-      MDPP_C_F64(TU3, p.tu_pow[2]), MDPP_C_F64(TU4, p.tu_pow[3])};
+      MDPP_C_F64(TU1, tu_rt[0]), MDPP_C_F64(TU2, tu_rt[1]),
+      MDPP_C_F64(TU3, tu_rt[2]), MDPP_C_F64(TU4, tu_rt[3])};
 
   R sd[MDPP_MAX_ORDER + 1][MDPP_MAX_DIM];
   R em[MDPP_MAX_DIM];
@@ -460,11 +525,11 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
     if (LINE) return 0.0;  // (no target point)
     if (TARGET64) {
       return seq_norm<double>(NREL, [&](int k) {
-        return __dadd_rn((double)x[rel_index(p, k)], -p.cfg.target_point[k]);
+        return __dadd_rn((double)x[rel_index(cfg, k)], -cfg.target_point[k]);
       });
     }
     return (double)seq_norm<R>(NREL, [&](int k) {
-      return O::add(x[rel_index(p, k)], -(R)p.cfg.target_point[k]);
+      return O::add(x[rel_index(cfg, k)], -(R)cfg.target_point[k]);
     });
   };
 
@@ -517,9 +582,9 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
           if (IMODE == 0) {
             sd[ORDER][d] = div_inertia(a[d], inertia);
           } else if (!TOP64) {
-            sd[ORDER][d] = O::div(a[d], (R)p.cfg.inertia_vec[d]);
+            sd[ORDER][d] = O::div(a[d], (R)cfg.inertia_vec[d]);
           } else {
-            top64[d] = __ddiv_rn((double)a[d], p.cfg.inertia_vec[d]);
+            top64[d] = __ddiv_rn((double)a[d], cfg.inertia_vec[d]);
             sd[ORDER][d] = (R)top64[d];
           }
         }
@@ -628,7 +693,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
       const int slot = (int)(step % (uint64_t)SEQ);
 #pragma unroll
       for (int k = 0; k < MDPP_MAX_DIM; ++k)
-        if (k < NREL) hist[((int64_t)slot * NREL + k) * N + env] = nxt[rel_index(p, k)];
+        if (k < NREL) hist[((int64_t)slot * NREL + k) * N + env] = nxt[rel_index(cfg, k)];
       // NaN gate of the window (:1858): sequence_length + 1 states since the reset
       if (tl >= SEQ) rd = line_reward<R>(hist, N, env, NREL, SEQ, step);
       is_real = false;
@@ -691,7 +756,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
       }
       sum_abs_rnoise += fabs(nrw);
     }
-    const bool box = NBOX > 0 && in_term_box<R>(p, NREL, nxt);
+    const bool box = NBOX > 0 && in_term_box<R>(cfg, NREL, nxt);
     const bool done = box || reached;
     R out_r;
     if (is_real) {  // np.float32 op python-float: the scalar is cast first
@@ -722,7 +787,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
         for (int d = 0; d < MDPP_MAX_DIM; ++d)
           if (d < D) s0[d] = rs[d];
       } else {
-        const RowVal<R> fresh = sample_reset_state<R>(p, D, NREL, NBOX, gid, ep);
+        const RowVal<R> fresh = sample_reset_state<R>(p, cfg, D, NREL, NBOX, gid, ep);
 #pragma unroll
         for (int d = 0; d < MDPP_MAX_DIM; ++d)
           if (d < D) s0[d] = fresh.v[d];
@@ -789,21 +854,32 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
       double v = 0.0;
 #pragma unroll
       for (int w = 0; w < kCBlock / 32; ++w) v += red[threadIdx.x][w];
-      if (blockIdx.x == 0 && threadIdx.x == 1) v = (double)N * (double)p.T;
-      // CTAs spread their atomics over the `stats_slots` copies of the row
+      if (!GROUPS && blockIdx.x == 0 && threadIdx.x == 1) v = (double)N * (double)p.T;
+      if (GROUPS && threadIdx.x == 1)  // this CTA's envs x T
+        v = (double)max((int64_t)0, min((int64_t)kCBlock,
+                                        gsm->env_count - (sel.local - threadIdx.x))) *
+            (double)p.T;
+      // CTAs spread their atomics over the `stats_slots` copies of the rows
+      // [slot][group][MDPP_N_STATS]
+      const int n_groups = GROUPS ? p.n_groups : 1;
       if (v != 0.0)
-        atomicAdd(p.st.stats + (blockIdx.x % (unsigned)max(p.st.stats_slots, 1)) *
-                                   MDPP_N_STATS + slots[threadIdx.x], v);
+        atomicAdd(p.st.stats + ((int64_t)(blockIdx.x % (unsigned)max(p.st.stats_slots, 1)) *
+                                    n_groups + sel.group) * MDPP_N_STATS +
+                      slots[threadIdx.x], v);
     }
   }
 }
 
-template <typename R>
+template <typename R, bool GROUPS = false>
 __device__ __forceinline__ void continuous_reset_body(const ContinuousParams& p) {
-  const int D = p.cfg.dim, ORDER = p.cfg.order, NREL = p.cfg.n_relevant;
+  __shared__ GroupSmem<GROUPS> gsm_store;
+  ContinuousGroupDev* gsm = group_ptr(gsm_store);
   const int64_t N = p.st.n_envs;
-  const int64_t env = (int64_t)blockIdx.x * kCBlock + threadIdx.x;
-  if (env >= N) return;
+  const ContinuousGroupSel sel = select_group<GROUPS>(p, gsm, N);
+  const mdpp_continuous_config& cfg = GROUPS ? gsm->cfg : p.cfg;
+  const int D = cfg.dim, ORDER = cfg.order, NREL = cfg.n_relevant;
+  if (!sel.active) return;
+  const int64_t env = sel.env;
   R* derivs = reinterpret_cast<R*>(p.st.derivs);
   R* emitted = reinterpret_cast<R*>(p.st.emitted);
   R* obs = reinterpret_cast<R*>(p.reset_obs);
@@ -812,7 +888,7 @@ __device__ __forceinline__ void continuous_reset_body(const ContinuousParams& p)
       for (int d = 0; d < D; ++d) obs[env * D + d] = emitted[(int64_t)d * N + env];
     return;
   }
-  const uint32_t gid = (uint32_t)(p.env_id_offset + env);
+  const uint32_t gid = sel.gid;
   const uint32_t ep = p.st.episode[env];
   R s0[MDPP_MAX_DIM];
   if (p.init_states) {
@@ -820,13 +896,14 @@ __device__ __forceinline__ void continuous_reset_body(const ContinuousParams& p)
     for (int d = 0; d < D; ++d) s0[d] = src[d];
   } else {
     for (int attempt = 0; attempt < 64; ++attempt) {
-      box_sample<R>(p, D, gid, ep, attempt, s0);
-      if (!(p.cfg.n_term_boxes > 0 && in_term_box<R>(p, NREL, s0))) break;
+      box_sample<R>(p, cfg, D, gid, ep, attempt, s0);
+      if (!(cfg.n_term_boxes > 0 && in_term_box<R>(cfg, NREL, s0))) break;
     }
   }
   if (p.st.stats && p.st.t_episode[env] > 0)
-    atomicAdd(p.st.stats + (blockIdx.x % (unsigned)max(p.st.stats_slots, 1)) *
-                               MDPP_N_STATS + MDPP_STAT_EPISODES, 1.0);
+    atomicAdd(p.st.stats + ((int64_t)(blockIdx.x % (unsigned)max(p.st.stats_slots, 1)) *
+                                (GROUPS ? p.n_groups : 1) + sel.group) * MDPP_N_STATS +
+                  MDPP_STAT_EPISODES, 1.0);
   for (int d = 0; d < D; ++d) {
     emitted[(int64_t)d * N + env] = s0[d];
     for (int k = 0; k <= ORDER; ++k)
@@ -838,16 +915,16 @@ __device__ __forceinline__ void continuous_reset_body(const ContinuousParams& p)
   p.st.reached[env] = 0;
 }
 
-template <typename R, int NOISE>
+template <typename R, int NOISE, bool GROUPS = false>
 __global__ void __launch_bounds__(kCBlock)
 continuous_rollout_kernel(const __grid_constant__ ContinuousParams p) {
-  continuous_body<R, NOISE>(p);
+  continuous_body<R, NOISE, GROUPS>(p);
 }
 
-template <typename R>
+template <typename R, bool GROUPS = false>
 __global__ void __launch_bounds__(kCBlock)
 continuous_reset_kernel(const __grid_constant__ ContinuousParams p) {
-  continuous_reset_body<R>(p);
+  continuous_reset_body<R, GROUPS>(p);
 }
 
 }  // namespace mdpp

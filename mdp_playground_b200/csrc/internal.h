@@ -33,6 +33,11 @@ struct mdpp_ctx {
   // continuous configuration (one per context)
   bool have_continuous = false;
   mdpp_continuous_config c_cfg;
+  // heterogeneous continuous launches (mdpp_set_continuous_groups)
+  void* c_groups = nullptr;   // ContinuousGroupDev[n]
+  void* c_cta_map = nullptr;  // CtaMapEntry[c_n_ctas]
+  int c_n_groups = 0;
+  int64_t c_n_ctas = 0, c_total_envs = 0;
   bool have_grid = false;
   mdpp_grid_config g_cfg;
   // runtime-specialised kernels (jit.cu), keyed by their define string

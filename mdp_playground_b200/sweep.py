@@ -123,9 +123,13 @@ class Sweep:
                 group_sizes=[self.envs_per_cell] * self.n_cells, shard=shard,
                 **env_kwargs)
             self.envs = [self.env]
+        elif self.kind == "continuous" and self._try_grouped_continuous(
+                VectorRLToyEnv, device, horizon, shard, env_kwargs):
+            pass  # the whole grid is ONE heterogeneous env here too
         else:
-            # continuous / grid kernels take one configuration per context:
-            # one env per cell, launched back to back on the same stream
+            # grid envs (and continuous grids whose cells differ in dimension,
+            # order or dtype) take one configuration per context: one env per
+            # cell, launched back to back on the same stream
             rank, world = shard
             self.envs = [VectorRLToyEnv(
                 self.envs_per_cell, device=device, autoreset=True,
@@ -137,14 +141,36 @@ class Sweep:
         self.timesteps = 0
         self._returned = np.zeros(self.n_cells)
 
+    def _try_grouped_continuous(self, Env, device, horizon, shard, env_kwargs):
+        """Continuous cells that share dim / order / dtype / reward function run
+        as config groups of one env: one launch per rollout for the whole grid
+        (e.g. experiments/sac_move_to_a_point_p_order_2.py:10-30)."""
+        try:
+            self.env = Env(
+                self.n_cells * self.envs_per_cell, device=device, autoreset=True,
+                horizon=horizon, config_groups=copy.deepcopy(self.cell_configs),
+                group_sizes=[self.envs_per_cell] * self.n_cells, shard=shard,
+                **env_kwargs)
+        except (ValueError, NotImplementedError):
+            return False
+        self.envs = [self.env]
+        self.grouped = True
+        import torch
+        amax = torch.tensor([float(c.get("action_space_max", np.inf))
+                             for c in self.cell_configs], device=self.env.device)
+        self._amax = amax.repeat_interleave(self.envs_per_cell).to(self.env._real)
+        return True
+
     def run(self, steps_per_env, chunk=256, actions_fn=None):
         """Random-policy (or `actions_fn(t0, T) -> int32[T, N]`) rollouts."""
         import torch
         done = 0
         while done < steps_per_env:
             T = min(chunk, steps_per_env - done)
-            if self.kind == "discrete":
+            if self.kind == "discrete" or getattr(self, "grouped", False):
                 acts = None if actions_fn is None else actions_fn(done, T)
+                if acts is None and self.kind == "continuous":
+                    acts = self._random_actions_grouped(T, done)
                 out = self.env.rollout(T, actions=acts, want_final_obs=False)
                 r = out["reward"].sum(dim=0).reshape(self.n_cells,
                                                      self.envs_per_cell)
@@ -180,8 +206,20 @@ class Sweep:
             return (u * 2 - 1) * amax
         return torch.randn((T, N, D), device=dev, generator=gen, dtype=env._real)
 
+    def _random_actions_grouped(self, T, t0):
+        """Uniform in every cell's own action box (N(0, 1) where unbounded)."""
+        import torch
+        env = self.env
+        N, D, dev = env.num_envs, env.spec.state_space_dim, env.device
+        gen = torch.Generator(dev).manual_seed(
+            (env.philox_seed + 7919 * (env._shard[0] + 1) + t0) % (2**63))
+        u = torch.rand((T, N, D), device=dev, generator=gen, dtype=env._real) * 2 - 1
+        z = torch.randn((T, N, D), device=dev, generator=gen, dtype=env._real)
+        bounded = torch.isfinite(self._amax)[None, :, None]
+        return torch.where(bounded, u * torch.nan_to_num(self._amax, posinf=1.0)[None, :, None], z)
+
     def results(self, reduce=False):
-        if self.kind == "discrete":
+        if self.kind == "discrete" or getattr(self, "grouped", False):
             st = self.env.episode_stats(reduce=reduce)
         else:  # one single-group env per cell
             per = [e.episode_stats(reduce=reduce) for e in self.envs]

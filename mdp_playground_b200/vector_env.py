@@ -98,8 +98,9 @@ class VectorRLToyEnv:
                     for c in config_groups]
             self._group_specs = [parse_config(c) for c in cfgs]
             kinds = {s_.kind for s_ in self._group_specs}
-            if kinds != {"discrete"}:
-                raise NotImplementedError("config_groups: discrete envs only")
+            if len(kinds) != 1 or kinds == {"grid"}:
+                raise NotImplementedError(
+                    "config_groups: all discrete or all continuous envs")
             G = len(cfgs)
             if group_sizes is None:
                 from .sharding import even_group_sizes
@@ -1100,33 +1101,18 @@ class VectorRLToyEnv:
     # ------------------------------------------------------------------
     # continuous backend (move_to_a_point)
     # ------------------------------------------------------------------
-    def _init_continuous(self):
-        sp = self.spec
-        D, N, dev = sp.state_space_dim, self.num_envs, self.device
-        if D > _lib.MDPP_MAX_DIM or sp.dynamics_order > _lib.MDPP_MAX_ORDER:
-            raise NotImplementedError("state_space_dim <= 16 and order <= 4")
-        np_dt = np.dtype(sp.dtype_s)
-        if np_dt not in (np.dtype(np.float32), np.dtype(np.float64)):
-            raise NotImplementedError("continuous dtype_s must be float32/64")
-        self._real = torch.float64 if np_dt == np.float64 else torch.float32
-        self._np_real = np_dt.type
-        self.observation_space = BoxSpace(
-            -sp.state_space_max, sp.state_space_max, (D,), np_dt,
-            seed=self.seed_dict.get("state_space"))
-        self.action_space = BoxSpace(
-            -sp.action_space_max, sp.action_space_max, (D,), np_dt,
-            seed=self.seed_dict.get("action_space"))
-        self.has_pnoise = sp.has_transition_noise
-        self.has_rnoise = sp.has_reward_noise
+    def _continuous_cfg(self, sp, config, np_dt):
+        """mdpp_continuous_config of one parsed config (one group)."""
+        D = sp.state_space_dim
         c = _lib.ContinuousConfig()
         c.dim, c.order = D, sp.dynamics_order
         c.n_relevant = len(sp.relevant_indices)
         c.delay, c.reward_every_n_steps = sp.delay, sp.reward_every_n_steps
         c.dense = int(sp.make_denser)
-        c.has_transition_noise = int(self.has_pnoise)
-        c.has_reward_noise = int(self.has_rnoise)
+        c.has_transition_noise = int(sp.has_transition_noise)
+        c.has_reward_noise = int(sp.has_reward_noise)
         c.image_mode = int(sp.image_representations)
-        c.target_is_f64 = int("target_point" not in self.config
+        c.target_is_f64 = int("target_point" not in config
                               and sp.reward_function == "move_to_a_point")
         c.is_f64 = int(np_dt == np.float64)
         # inertia: float, or one value per dimension (rl_toy_env.py:519-537); a
@@ -1167,23 +1153,91 @@ class VectorRLToyEnv:
             for k in range(c.n_relevant):
                 c.target_point[k] = float(tp[k])
         # terminal hypercubes (:895-952); Box casts its bounds to dtype_s
-        self._term_lows, self._term_highs = [], []
+        term_lows, term_highs = [], []
         for centre in (sp.terminal_centres or []):
             lo = np.array([x - sp.term_state_edge / 2 for x in centre]).astype(np_dt)
             hi = np.array([x + sp.term_state_edge / 2 for x in centre]).astype(np_dt)
-            self._term_lows.append(lo)
-            self._term_highs.append(hi)
-        if len(self._term_lows) > _lib.MDPP_MAX_TERM_BOXES:
+            term_lows.append(lo)
+            term_highs.append(hi)
+        if len(term_lows) > _lib.MDPP_MAX_TERM_BOXES:
             raise NotImplementedError("at most 8 terminal regions")
-        c.n_term_boxes = len(self._term_lows)
-        for b, (lo, hi) in enumerate(zip(self._term_lows, self._term_highs)):
+        c.n_term_boxes = len(term_lows)
+        for b, (lo, hi) in enumerate(zip(term_lows, term_highs)):
             for k in range(c.n_relevant):
                 c.term_low[b * _lib.MDPP_MAX_DIM + k] = float(lo[k])
                 c.term_high[b * _lib.MDPP_MAX_DIM + k] = float(hi[k])
-        self._check(self._lib.mdpp_set_continuous_config(self._ctx, C.byref(c)))
-        self.n_groups = 1
+        return c, term_lows, term_highs
+
+    def _init_continuous(self):
+        sp = self.spec
+        D, N, dev = sp.state_space_dim, self.num_envs, self.device
+        if D > _lib.MDPP_MAX_DIM or sp.dynamics_order > _lib.MDPP_MAX_ORDER:
+            raise NotImplementedError("state_space_dim <= 16 and order <= 4")
+        np_dt = np.dtype(sp.dtype_s)
+        if np_dt not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise NotImplementedError("continuous dtype_s must be float32/64")
+        self._real = torch.float64 if np_dt == np.float64 else torch.float32
+        self._np_real = np_dt.type
+        self.observation_space = BoxSpace(
+            -sp.state_space_max, sp.state_space_max, (D,), np_dt,
+            seed=self.seed_dict.get("state_space"))
+        self.action_space = BoxSpace(
+            -sp.action_space_max, sp.action_space_max, (D,), np_dt,
+            seed=self.seed_dict.get("action_space"))
+        specs = self._group_specs
+        G = len(specs)
+        cfgs = []
+        for gi, s_ in enumerate(specs):
+            if (s_.state_space_dim != D
+                    or list(s_.relevant_indices) != list(sp.relevant_indices)
+                    or np.dtype(s_.dtype_s) != np_dt
+                    or s_.reward_function != sp.reward_function
+                    or s_.image_representations != sp.image_representations):
+                raise ValueError(
+                    "config_groups of continuous envs must agree on state_space_dim, "
+                    "relevant_indices, dtype_s, "
+                    "reward_function and image_representations (group %d)" % gi)
+            cfgs.append(self._continuous_cfg(s_, s_.config, np_dt))
+        c, self._term_lows, self._term_highs = cfgs[0]
+        line = sp.reward_function == "move_along_a_line"
+        self.has_pnoise = any(s_.has_transition_noise for s_ in specs)
+        self.has_rnoise = any(s_.has_reward_noise for s_ in specs)
+        max_delay = max(s_.delay for s_ in specs)
+
+        def ring64(cc):
+            return bool(self._real == torch.float32 and (
+                (cc.target_is_f64 and cc.dense) or line))
+        if G > 1:
+            if sp.image_representations or self.noise == "numpy":
+                raise NotImplementedError(
+                    "config_groups of continuous envs: no images, no noise='numpy'")
+            if len({ring64(cc) for cc, _, _ in cfgs}) != 1 or (
+                    line and len({s_.sequence_length for s_ in specs}) != 1):
+                raise ValueError(
+                    "config_groups of continuous envs must agree on make_denser / "
+                    "default target_point (the reward FIFO's dtype) and, for "
+                    "move_along_a_line, on sequence_length")
+            from .sharding import group_id_bases
+            id_bases = group_id_bases(self._group_sizes, *self._shard)
+            groups = (_lib.ContinuousGroup * G)()
+            begin = 0
+            self.group_slices = []
+            for gi, (cc, _, _) in enumerate(cfgs):
+                groups[gi].cfg = cc
+                groups[gi].env_begin, groups[gi].env_count = begin, self._group_sizes[gi]
+                groups[gi].global_id_base = id_bases[gi]
+                self.group_slices.append(slice(begin, begin + self._group_sizes[gi]))
+                begin += self._group_sizes[gi]
+            assert begin == N
+            if self._shard[1] > 1:  # (ids come from the groups, not from the offset)
+                self.env_id_offset -= self._shard[0] * self.num_envs
+            self._check(self._lib.mdpp_set_continuous_groups(self._ctx, groups, G))
+        else:
+            self._check(self._lib.mdpp_set_continuous_config(self._ctx, C.byref(c)))
+        self.n_groups = G
         real = self._real
-        self._derivs = torch.zeros((sp.dynamics_order + 1, D, N), dtype=real,
+        self._max_order = max(s_.dynamics_order for s_ in specs)
+        self._derivs = torch.zeros((self._max_order + 1, D, N), dtype=real,
                                    device=dev)
         self._emitted = torch.zeros((D, N), dtype=real, device=dev)
         self._t = torch.zeros(N, dtype=torch.int32, device=dev)
@@ -1191,14 +1245,13 @@ class VectorRLToyEnv:
         self._reached = torch.zeros(N, dtype=torch.uint8, device=dev)
         # (fp32 env + default float64 target_point + dense reward: the reward is
         # a python float all the way through the reference's reward_buffer)
-        ring_dt = torch.float64 if (real == torch.float32 and (
-            (c.target_is_f64 and c.dense) or line)) else real
+        ring_dt = torch.float64 if ring64(c) else real
         # move_along_a_line: the last sequence_length emitted relevant states
         self._hist_line = torch.zeros((sp.sequence_length, c.n_relevant, N),
                                       dtype=real, device=dev) if line else None
-        self._ring = torch.zeros((sp.delay, N), dtype=ring_dt, device=dev) \
-            if sp.delay > 0 else None
-        self._stats = torch.zeros((_lib.STATS_SLOTS, 1, _lib.MDPP_N_STATS),
+        self._ring = torch.zeros((max_delay, N), dtype=ring_dt, device=dev) \
+            if max_delay > 0 else None
+        self._stats = torch.zeros((_lib.STATS_SLOTS, G, _lib.MDPP_N_STATS),
                                   dtype=torch.float64, device=dev)
         st = _lib.ContinuousState()
         st.n_envs = N
@@ -1588,7 +1641,7 @@ class VectorRLToyEnv:
             self.curr_obs = self._observe(cells.to(torch.int64), reset=True, ctor=True)
             return
         if self.spec.kind == "continuous":
-            D, order = self.spec.state_space_dim, self.spec.dynamics_order
+            D, order = self.spec.state_space_dim, self._max_order
             if isinstance(state, dict):
                 cur = torch.as_tensor(state["curr_state"], device=dev).to(self._real)
                 sd = torch.as_tensor(state["state_derivatives"], device=dev).to(

@@ -168,3 +168,82 @@ def test_mixed_40_group_launch_matches_grouped_oracle(jit, normal):
     for g, s in enumerate(ora.stats):
         for k in ("episodes", "transitions", "noisy_transitions", "terminated"):
             assert st[k][g] == s[k], (g, k)
+
+
+def _continuous_cells():
+    """A sac_move_to_a_point_* style grid: time_unit x action_space_max x noise
+    x delay x target_radius cells of one continuous env (same dim / order)."""
+    base = dict(seed=0, state_space_type="continuous", action_space_type="continuous",
+                state_space_dim=4, action_space_dim=4, relevant_indices=[0, 1],
+                irrelevant_features=True, transition_dynamics_order=2, inertia=1.0,
+                target_point=[0.0, 0.0], state_space_max=4.0, make_denser=True)
+    cells = []
+    for tu, amax, pn, rn, d, rad, alw, order in [
+            (0.1, 1.0, 0, 0, 0, 0.5, 0.0, 2), (0.5, 0.25, 0.05, 0, 2, 0.5, 0.0, 1),
+            (1.0, 0.5, 0, 0.2, 1, 1.0, 0.0, 2), (0.25, 1.0, 0.1, 0.1, 4, 0.25, 0.5, 3),
+            (0.05, 0.1, 0, 0, 0, 0.5, 0.0, 2), (0.5, 1.0, 0.02, 0.3, 3, 2.0, 0.0, 1)]:
+        c = dict(base, time_unit=tu, action_space_max=amax, delay=d,
+                 target_radius=rad, action_loss_weight=alw, reward_scale=1.0 + d,
+                 transition_dynamics_order=order)
+        if pn:
+            c["transition_noise"] = pn
+        if rn:
+            c["reward_noise"] = rn
+        cells.append(c)
+    return cells
+
+
+def test_continuous_multi_group_launch_equals_single_group_envs_and_oracle():
+    """config_groups for continuous envs (one launch per sweep): the
+    heterogeneous launch == one env per cell (CUDA, bit-exact) == the grouped
+    CPU oracle (1e-5, the continuous contract); 2 shards == unsplit."""
+    from oracle.scalar_env import ScalarRLToyEnv
+    from oracle.vector_continuous_oracle import VectorGroupedContinuousOracle
+    cells = _continuous_cells()
+    sizes = [150, 130, 128, 64, 200, 97]
+    N, T = sum(sizes), 40
+    acts = (torch.rand((T, N, 4), device="cuda",
+                       generator=torch.Generator("cuda").manual_seed(6)) * 2.2 - 1.1)
+    het = make_env(N, autoreset=True, horizon=17, philox_seed=9,
+                   config_groups=[dict(c) for c in cells], group_sizes=sizes)
+    obs0 = het.curr_obs.clone()
+    out = het.rollout(T, actions=acts)
+    begin = 0
+    for c, n, sl in zip(cells, sizes, het.group_slices):
+        one = make_env(n, autoreset=True, horizon=17, philox_seed=9,
+                       env_id_offset=begin, **dict(c))
+        one.set_jit(False)   # (the group launch runs the ahead-of-time kernel)
+        assert torch.equal(one.curr_obs, obs0[sl])
+        ref = one.rollout(T, actions=acts[:, sl].contiguous())
+        for k in ref:
+            assert torch.equal(out[k][:, sl], ref[k]), (k, begin)
+        begin += n
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        scalars = [ScalarRLToyEnv(**dict(c)) for c in cells]
+    ora = VectorGroupedContinuousOracle(scalars, sizes, autoreset=True, horizon=17, seed=9)
+    ora.reset()
+    want = ora.rollout(T, acts.cpu().numpy())
+    for k in ("terminated", "truncated"):
+        assert np.array_equal(out[k].cpu().numpy(), want[k]), k
+    np.testing.assert_allclose(out["obs"].cpu().numpy(), want["obs"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out["reward"].cpu().numpy(), want["reward"],
+                               rtol=1e-4, atol=1e-5)
+    st = het.episode_stats()
+    assert st["transitions"].tolist() == [n * T for n in sizes]
+    # two shards of the same job
+    half = [n // 2 for n in [128, 128, 256, 64, 192, 128]]
+    whole = make_env(2 * sum(half), autoreset=True, horizon=17, philox_seed=9,
+                     config_groups=[dict(c) for c in cells],
+                     group_sizes=[2 * n for n in half])
+    a2 = (torch.rand((T, 2 * sum(half), 4), device="cuda") * 2 - 1)
+    ref = whole.rollout(T, actions=a2)
+    for r in range(2):
+        part = make_env(sum(half), autoreset=True, horizon=17, philox_seed=9,
+                        config_groups=[dict(c) for c in cells], group_sizes=half,
+                        shard=(r, 2))
+        cols = torch.cat([torch.arange(sl.start + r * n, sl.start + (r + 1) * n)
+                          for sl, n in zip(whole.group_slices, half)]).cuda()
+        got = part.rollout(T, actions=a2[:, cols].contiguous())
+        for k in ref:
+            assert torch.equal(got[k], ref[k][:, cols]), (k, r)

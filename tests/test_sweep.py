@@ -131,14 +131,16 @@ def test_every_rltoy_experiment_of_the_reference_is_accepted():
 
 @pytest.mark.gpu
 def test_sweep_over_a_continuous_experiment_grid(tmp_path):
-    """Continuous experiment files: one batched env per grid cell; larger
-    time units move further per step, so random-walk episodes end (leave the
-    target's surroundings / hit the box) differently per cell."""
+    """Continuous experiment files: the whole grid is ONE env with config
+    groups (one launch per rollout); larger time units move further per step,
+    so random-walk episodes end (leave the target's surroundings / hit the box)
+    differently per cell."""
     fixture = os.path.join(HERE, "fixtures", "ddpg_move_to_a_point_like.py")
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         sw = sweep.Sweep(fixture, envs_per_cell=256)
-    assert sw.kind == "continuous" and sw.n_cells == 3 * 2 * 2 == len(sw.envs)
+    assert sw.kind == "continuous" and sw.n_cells == 3 * 2 * 2
+    assert len(sw.envs) == 1 and sw.env.n_groups == 12   # one heterogeneous env
     res = sw.run(300, chunk=100)
     assert np.all(res["transitions"] == 256 * 300)
     assert np.all(res["episodes"] > 0) and np.all(np.isfinite(res["episode_reward_mean"]))
