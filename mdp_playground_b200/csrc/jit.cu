@@ -389,9 +389,21 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
   for (auto& g : groups) ring_in_regs &= g.delay == groups[0].delay;
   const int ring_bytes =
       ring_ok && !ring_in_regs ? ctx->max_delay * kBlock * 8 : 0;
-  const int zig_bytes = (noise_mode == MDPP_NOISE_PHILOX &&
-                         normal_mode == MDPP_NORMAL_ZIGGURAT)
-                            ? kZigBytes + zig_stage_bytes(kBlock) : 0;
+  // staged ziggurat window: 32 steps (16 KB per CTA) unless that costs a CTA per
+  // SM below the 7 the register file allows anyway -- then 16 steps (measured
+  // on the 1000-group launch: 6 -> 7 CTAs / SM)
+  const bool zig = noise_mode == MDPP_NOISE_PHILOX && normal_mode == MDPP_NORMAL_ZIGGURAT;
+  int zig_window = 32;
+  if (zig) {
+    auto ctas = [&](int window) {
+      const int per_cta = ring_bytes + ctx->max_group_blob + kZigBytes +
+                          zig_stage_bytes(kBlock, window) + 1024 + 256;
+      return (228 * 1024) / per_cta;
+    };
+    if (ctas(32) < 7 && ctas(16) > ctas(32)) zig_window = 16;
+    if (const char* w = std::getenv("MDPP_ZIG_WINDOW")) zig_window = std::atoi(w);  // tuning knob
+  }
+  const int zig_bytes = zig ? kZigBytes + zig_stage_bytes(kBlock, zig_window) : 0;
   if (!ring_ok ||
       ctx->max_group_blob + ring_bytes + zig_bytes > ctx->max_smem_optin - 1024) {
     ctx->jit_log = "tables or delay ring do not fit shared memory";
@@ -403,7 +415,8 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
   const long long sig[10] = {ctx->d_groups_version, noise_mode, normal_mode, fast,
                              (long long)p.st.n_envs, p.autoreset, p.horizon, p.irr,
                              p.io.obs_dtype,
-                             (p.T >= smem_min_steps()) + 2 * (p.T >= kZigWindow)};
+                             (p.T >= smem_min_steps()) + 2 * (p.T >= zig_window) +
+                                 4 * zig_window};
   // tables staged in shared memory (always, unless MDPP_SMEM_MIN_T says that
   // launches shorter than that read them from global memory: measured slower,
   // the staging overlaps the previous kernel under programmatic launch)
@@ -417,7 +430,8 @@ int jit_try_rollout(mdpp_ctx* ctx, RolloutParams& p, int noise_mode,
       if (g.cdf_log2 != groups[0].cdf_log2) cdf_tpl = -1;
     std::vector<std::string> defs =
         defines_for(groups, p, noise_mode, normal_mode, fast, true, cdf_tpl, smem,
-                    p.T >= kZigWindow);
+                    p.T >= zig_window);
+    defs.push_back("-DMDPP_ZIG_WINDOW=" + std::to_string(zig_window));
     if (const char* ch = std::getenv("MDPP_JIT_CHUNK"))  // tuning knob (4/8/16)
       defs.push_back(std::string("-DMDPP_JIT_CHUNK=") + ch);
     else if (groups.size() > 1)

@@ -33,11 +33,15 @@ constexpr int kZigBytes = kZigFastBytes + kZigLayers * 8;
 // Staging of the rollout kernels (discrete_kernels.cuh, zig_fill): normals of
 // kZigWindow consecutive steps per thread in shared memory, and per warp a
 // queue of the draws whose first attempt was rejected.
+#ifdef MDPP_ZIG_WINDOW  // (16 in specialisations whose tables leave no room for 32)
+constexpr int kZigWindow = MDPP_ZIG_WINDOW;
+#else
 constexpr int kZigWindow = 32;
+#endif
 constexpr int kZigQueueCap = 64;
 constexpr int kZigQueueBytes = 16 + 2 * kZigQueueCap;  // count, then u16 items
-__host__ __device__ constexpr int zig_stage_bytes(int block) {
-  return kZigWindow * block * 8 + (block / 32) * kZigQueueBytes;
+__host__ __device__ constexpr int zig_stage_bytes(int block, int window = kZigWindow) {
+  return window * block * 8 + (block / 32) * kZigQueueBytes;
 }
 
 // First attempt.  `kw` -> {wi, (double)ki}[256]; returns x, sets *accepted.

@@ -1,6 +1,5 @@
 python tools/time_one.py fp64
-MDPP_JIT_MINBLOCKS=7 python tools/time_one.py fp64
-MDPP_JIT_EXTRA="-DMDPP_ZIG_FILL_NOINLINE" python tools/time_one.py fp64
-MDPP_JIT_MINBLOCKS=7 MDPP_JIT_EXTRA="-DMDPP_ZIG_FILL_NOINLINE" python tools/time_one.py fp64
-MDPP_JIT_MINBLOCKS=7 python tools/time_one.py fast
-MDPP_JIT_MINBLOCKS=6 python tools/time_one.py fp64
+python tools/time_hetero.py fp64
+MDPP_ZIG_WINDOW=32 python tools/time_hetero.py fp64
+python tools/time_one.py fp64 1048576 100 5
+MDPP_ZIG_WINDOW=16 python tools/time_one.py fp64 1048576 100 5
