@@ -660,7 +660,8 @@ def run_gpu_arm(args):
                 "roofline_frac": sps / world * ALGO_BYTES_STEP / 1e9 / peak}
     step_api = {"step": dict(timed(lambda: env.step(a1)),
                              what="env.step(actions): the gym-style call itself "
-                                  "(allocates its outputs, returns final_obs)")}
+                                  "(rotating pre-marshalled output sets, returns "
+                                  "final_obs; step_buffers=2)")}
     a1r = actions[0:1]
     o1 = {k: v[0:1] for k, v in out.items()}
     step_api["rollout_1"] = dict(

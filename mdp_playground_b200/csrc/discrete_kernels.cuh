@@ -475,6 +475,7 @@ struct IrrDraws {
 template <typename C>
 __device__ __forceinline__ void load_action(const RolloutParams& p, int64_t off,
                                             int32_t& a, int32_t& a_irr) {
+  if (MDPP_EXP_SKIP & 4) { a = (int32_t)(off & 7); a_irr = 0; return; }  // (timing experiment)
   if (irr_of<C>(p)) {  // rows (relevant, irrelevant): one 8-byte load
     const int2 v = ld_stream_i32x2(p.io.actions + 2 * off);
     a = v.x; a_irr = v.y;

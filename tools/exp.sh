@@ -1,5 +1,5 @@
-python tools/time_one.py fp64
-python tools/time_hetero.py fp64
-MDPP_ZIG_WINDOW=32 python tools/time_hetero.py fp64
-python tools/time_one.py fp64 1048576 100 5
-MDPP_ZIG_WINDOW=16 python tools/time_one.py fp64 1048576 100 5
+for n in fp64 fast; do
+python tools/time_one.py $n
+MDPP_JIT_EXTRA="-DMDPP_EXP_SKIP=4" python tools/time_one.py $n
+MDPP_JIT_EXTRA="-DMDPP_EXP_SKIP=7" python tools/time_one.py $n
+done
