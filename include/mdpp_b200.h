@@ -419,8 +419,22 @@ typedef struct mdpp_grid_io {      /* T steps, time-major, rows of n_dims    */
   const int64_t* replay_reset_state; /* [T][N][n_dims] cell of an auto-reset  */
 } mdpp_grid_io;
 
+/* A heterogeneous grid launch (the `config_groups` of a sweep, like
+ * mdpp_set_discrete_groups / mdpp_set_continuous_groups): group g owns the
+ * envs [env_begin, env_begin + env_count) of the state arrays and steps them
+ * under its own configuration; groups tile the env range in order and agree
+ * on n_dims.  Statistics rows are [slot][group][MDPP_N_STATS].  Replaces any
+ * earlier mdpp_set_grid_config (and vice versa).                            */
+typedef struct mdpp_grid_group {
+  mdpp_grid_config cfg;
+  int64_t env_begin, env_count;
+  int64_t global_id_base;  /* global Philox id of the group's first env      */
+} mdpp_grid_group;
+
 #ifndef __CUDACC_RTC__ /* NVRTC sees the types only */
 int mdpp_set_grid_config(mdpp_ctx* ctx, const mdpp_grid_config* cfg);
+int mdpp_set_grid_groups(mdpp_ctx* ctx, const mdpp_grid_group* groups,
+                         int32_t n_groups);
 int mdpp_grid_rollout(mdpp_ctx* ctx, const mdpp_grid_state* st,
                       const mdpp_grid_io* io, const mdpp_step_opts* opts,
                       void* cuda_stream);

@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = (
     "mdpp_ziggurat_tables",
     "mdpp_tail_actions", "mdpp_tail_post", "mdpp_tail_image_shift",
     "mdpp_set_continuous_groups",
+    "mdpp_set_grid_groups",
 )
 MDPP_MAX_DIM, MDPP_MAX_ORDER, MDPP_MAX_TERM_BOXES = 16, 4, 8
 
@@ -190,6 +191,11 @@ class GridConfig(C.Structure):
     ]
 
 
+class GridGroup(C.Structure):
+    _fields_ = [("cfg", GridConfig), ("env_begin", C.c_int64),
+                ("env_count", C.c_int64), ("global_id_base", C.c_int64)]
+
+
 class GridState(C.Structure):
     _fields_ = [
         ("n_envs", C.c_int64), ("pos", C.c_void_p), ("t_episode", C.c_void_p),
@@ -278,6 +284,7 @@ def load():
     lib.mdpp_render_continuous.argtypes = [
         P, C.POINTER(ImageContinuousConfig), P, P, C.c_int64, P]
     lib.mdpp_set_grid_config.argtypes = [P, C.POINTER(GridConfig)]
+    lib.mdpp_set_grid_groups.argtypes = [P, C.POINTER(GridGroup), C.c_int32]
     lib.mdpp_grid_rollout.argtypes = [
         P, C.POINTER(GridState), C.POINTER(GridIO), C.POINTER(StepOpts), P]
     lib.mdpp_grid_reset.argtypes = [

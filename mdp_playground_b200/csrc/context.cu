@@ -99,6 +99,8 @@ extern "C" void mdpp_destroy(mdpp_ctx* ctx) {
   if (ctx->d_zig) cudaFree(ctx->d_zig);
   if (ctx->c_groups) cudaFree(ctx->c_groups);
   if (ctx->c_cta_map) cudaFree(ctx->c_cta_map);
+  if (ctx->g_groups) cudaFree(ctx->g_groups);
+  if (ctx->g_cta_map) cudaFree(ctx->g_cta_map);
   delete ctx;
 }
 

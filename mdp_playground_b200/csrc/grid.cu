@@ -13,6 +13,7 @@
 // prefetched a step ahead).  Integer arithmetic and fp64 rewards in the
 // reference's operation order: bit-exact.
 #include <cstring>
+#include <vector>
 
 #include "internal.h"
 #include "philox.cuh"
@@ -34,7 +35,58 @@ struct GridParams {
   const uint8_t* mask;
   const int64_t* init_states;
   int64_t* reset_obs;
+  // heterogeneous launches (mdpp_set_grid_groups): CTA -> (group, chunk of
+  // kGBlock envs); every CTA reads its group's configuration from `groups`.
+  const struct GridGroupDev* groups;
+  const CtaMapEntry* cta_map;
+  int32_t n_groups, reserved1;
 };
+
+// One configuration group of a heterogeneous grid launch (all groups share
+// n_dims, i.e. the row layout of the state arrays and of the I/O).
+struct GridGroupDev {
+  mdpp_grid_config cfg;
+  int64_t env_begin, env_count, gid_base;
+};
+
+struct GridSel {
+  int64_t env;   // index into the state arrays
+  uint32_t gid;
+  bool active;
+  int group;
+};
+
+// (shared-memory copy of the CTA's group; empty in single-configuration builds)
+template <bool G> struct GridGroupSmem { GridGroupDev g; };
+template <> struct GridGroupSmem<false> { int unused; };
+__device__ __forceinline__ const mdpp_grid_config* group_cfg(const GridGroupSmem<true>& s) { return &s.g.cfg; }
+__device__ __forceinline__ const mdpp_grid_config* group_cfg(const GridGroupSmem<false>&) { return nullptr; }
+
+template <bool GROUPS>
+__device__ __forceinline__ GridSel select_group(const GridParams& p,
+                                                GridGroupSmem<GROUPS>& gsm) {
+  GridSel s;
+  if constexpr (GROUPS) {
+    const CtaMapEntry me = p.cta_map[blockIdx.x];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.groups + me.group);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&gsm.g);
+    for (int i = threadIdx.x; i < (int)(sizeof(GridGroupDev) / 4); i += kGBlock)
+      dst[i] = src[i];
+    __syncthreads();
+    const int64_t local = (int64_t)me.chunk * kGBlock + threadIdx.x;
+    s.active = local < gsm.g.env_count;
+    s.env = gsm.g.env_begin + (s.active ? local : 0);
+    s.gid = (uint32_t)(p.env_id_offset + gsm.g.gid_base + (s.active ? local : 0));
+    s.group = me.group;
+  } else {
+    const int64_t env = (int64_t)blockIdx.x * kGBlock + threadIdx.x;
+    s.active = env < p.st.n_envs;
+    s.env = s.active ? env : 0;
+    s.gid = (uint32_t)(p.env_id_offset + s.env);
+    s.group = 0;
+  }
+  return s;
+}
 
 template <int ND>
 struct Row { int64_t v[ND]; };
@@ -130,10 +182,10 @@ struct GridEnv {
 // One environment step.  FAST: the standard rollout signature (obs, reward,
 // terminated, truncated written, no final_obs), so no per-step NULL tests.
 template <int ND, int NOISE, bool FAST>
-__device__ __forceinline__ void grid_step(const GridParams& p, GridEnv<ND>& g,
+__device__ __forceinline__ void grid_step(const GridParams& p, const mdpp_grid_config& c,
+                                          GridEnv<ND>& g,
                                           uint32_t code, int64_t off, uint64_t step,
                                           uint32_t gid, uint32_t pn_T, double term_add) {
-  const mdpp_grid_config& c = p.cfg;
   // GridActionSpace.contains: entries in {-1, 0, 1}, at most one move
   const bool valid = (code >> 31) == 0;
   int32_t a[ND];
@@ -247,16 +299,17 @@ __device__ __forceinline__ void grid_step(const GridParams& p, GridEnv<ND>& g,
   if (FAST || p.io.truncated) __stcs(p.io.truncated + off, (uint8_t)trunc);
 }
 
-template <int ND, int NOISE, bool FAST>
+template <int ND, int NOISE, bool FAST, bool GROUPS = false>
 __global__ void __launch_bounds__(kGBlock, ND == 2 ? 5 : 4)
 grid_rollout_kernel(const __grid_constant__ GridParams p) {
   __shared__ double red[kGBlock / 32];
-  const mdpp_grid_config& c = p.cfg;
+  __shared__ GridGroupSmem<GROUPS> gsm;
+  const GridSel sel = select_group<GROUPS>(p, gsm);
+  const mdpp_grid_config& c = GROUPS ? *group_cfg(gsm) : p.cfg;
   const int64_t N = p.st.n_envs;
-  const int64_t env = (int64_t)blockIdx.x * kGBlock + threadIdx.x;
-  const bool active = env < N;
-  const int64_t e = active ? env : 0;
-  const uint32_t gid = (uint32_t)(p.env_id_offset + e);
+  const bool active = sel.active;
+  const int64_t e = sel.env;
+  const uint32_t gid = sel.gid;
   const uint64_t step_base =
       p.step_index + (p.step_index_dev ? *p.step_index_dev : 0ull);
   GridEnv<ND> g;
@@ -301,13 +354,13 @@ grid_rollout_kernel(const __grid_constant__ GridParams p) {
       }
 #pragma unroll
       for (int j = 0; j < kAhead; ++j)
-        grid_step<ND, NOISE, FAST>(p, g, cur[j], (int64_t)(t0 + j) * N + e,
+        grid_step<ND, NOISE, FAST>(p, c, g, cur[j], (int64_t)(t0 + j) * N + e,
                                    step_base + (uint64_t)(t0 + j), gid, pn_T, term_add);
     }
 #pragma unroll
     for (int j = 0; j < kAhead - 1; ++j)  // the last T % 4 steps
       if (t0 + j < p.T)
-        grid_step<ND, NOISE, FAST>(p, g, pack_action<ND>(ring[j]),
+        grid_step<ND, NOISE, FAST>(p, c, g, pack_action<ND>(ring[j]),
                                    (int64_t)(t0 + j) * N + e,
                                    step_base + (uint64_t)(t0 + j), gid, pn_T, term_add);
 #pragma unroll
@@ -328,19 +381,23 @@ grid_rollout_kernel(const __grid_constant__ GridParams p) {
     for (int k = 0; k < MDPP_N_STATS; ++k) {
       if (k == MDPP_STAT_ABS_TRANSITION_NOISE || k == MDPP_STAT_RESERVED) continue;
       const double s = block_sum(vals[k], red);
-      if (threadIdx.x == 0 && s != 0.0)
-        atomicAdd(p.st.stats + (blockIdx.x % (unsigned)max(p.st.stats_slots, 1)) *
+      if (threadIdx.x == 0 && s != 0.0)  // rows [slot][group]
+        atomicAdd(p.st.stats + ((int64_t)(blockIdx.x % (unsigned)max(p.st.stats_slots, 1)) *
+                                    (GROUPS ? p.n_groups : 1) + sel.group) *
                                    MDPP_N_STATS + k, s);
     }
   }
 }
 
-template <int ND>
+template <int ND, bool GROUPS = false>
 __global__ void __launch_bounds__(kGBlock)
 grid_reset_kernel(const __grid_constant__ GridParams p) {
+  __shared__ GridGroupSmem<GROUPS> gsm;
+  const GridSel sel = select_group<GROUPS>(p, gsm);
+  const mdpp_grid_config& c = GROUPS ? *group_cfg(gsm) : p.cfg;
   const int64_t N = p.st.n_envs;
-  const int64_t env = (int64_t)blockIdx.x * kGBlock + threadIdx.x;
-  if (env >= N) return;
+  const int64_t env = sel.env;
+  if (!sel.active) return;
   int32_t pos[ND];
   if (p.mask && !p.mask[env]) {
     if (p.reset_obs)
@@ -352,14 +409,14 @@ grid_reset_kernel(const __grid_constant__ GridParams p) {
   if (p.init_states) {
     for (int k = 0; k < ND; ++k) pos[k] = (int32_t)p.init_states[env * ND + k];
   } else {
-    const uint32_t gid = (uint32_t)(p.env_id_offset + env);
-    U4 w = philox4x32_10(gid, ep, 0u, STREAM_GRID_RESET, p.k0, p.k1);
+    U4 w = philox4x32_10(sel.gid, ep, 0u, STREAM_GRID_RESET, p.k0, p.k1);
     const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
     for (int k = 0; k < ND; ++k)
-      pos[k] = (int32_t)__umulhi(ww[k], (uint32_t)p.cfg.shape[k] + 1u);
+      pos[k] = (int32_t)__umulhi(ww[k], (uint32_t)c.shape[k] + 1u);
   }
   if (p.st.stats && p.st.t_episode[env] > 0)
-    atomicAdd(p.st.stats + (blockIdx.x % (unsigned)max(p.st.stats_slots, 1)) *
+    atomicAdd(p.st.stats + ((int64_t)(blockIdx.x % (unsigned)max(p.st.stats_slots, 1)) *
+                                (GROUPS ? p.n_groups : 1) + sel.group) *
                                MDPP_N_STATS + MDPP_STAT_EPISODES, 1.0);
   for (int k = 0; k < ND; ++k) {
     p.st.pos[(int64_t)k * N + env] = pos[k];
@@ -375,8 +432,17 @@ grid_reset_kernel(const __grid_constant__ GridParams p) {
 
 using namespace mdpp;
 
-extern "C" int mdpp_set_grid_config(mdpp_ctx* ctx, const mdpp_grid_config* cfg) {
-  if (!ctx) return MDPP_EINVAL;
+static void free_grid_groups(mdpp_ctx* ctx) {
+  if (ctx->g_groups) cudaFree(ctx->g_groups);
+  if (ctx->g_cta_map) cudaFree(ctx->g_cta_map);
+  ctx->g_groups = nullptr;
+  ctx->g_cta_map = nullptr;
+  ctx->g_n_groups = 0;
+  ctx->g_n_ctas = 0;
+  ctx->g_total_envs = 0;
+}
+
+static int check_grid_config(mdpp_ctx* ctx, const mdpp_grid_config* cfg) {
   if (!cfg) return fail(ctx, MDPP_EINVAL, "cfg is NULL");
   if (cfg->n_dims != 2 && cfg->n_dims != 4)
     return fail(ctx, MDPP_EINVAL, "grid: n_dims must be 2 or 4");
@@ -388,7 +454,63 @@ extern "C" int mdpp_set_grid_config(mdpp_ctx* ctx, const mdpp_grid_config* cfg) 
   if (cfg->has_transition_noise &&
       !(cfg->transition_noise > 0.0 && cfg->transition_noise <= 1.0))
     return fail(ctx, MDPP_EINVAL, "grid: transition_noise must be in (0, 1]");
+  return MDPP_OK;
+}
+
+extern "C" int mdpp_set_grid_config(mdpp_ctx* ctx, const mdpp_grid_config* cfg) {
+  if (!ctx) return MDPP_EINVAL;
+  int rc = check_grid_config(ctx, cfg);
+  if (rc) return rc;
+  free_grid_groups(ctx);
   ctx->g_cfg = *cfg;
+  ctx->have_grid = true;
+  return MDPP_OK;
+}
+
+extern "C" int mdpp_set_grid_groups(mdpp_ctx* ctx, const mdpp_grid_group* groups,
+                                    int32_t n_groups) {
+  if (!ctx) return MDPP_EINVAL;
+  if (!groups || n_groups < 1)
+    return fail(ctx, MDPP_EINVAL, "need at least one grid group");
+  std::vector<GridGroupDev> dev(n_groups);
+  std::vector<CtaMapEntry> map;
+  int64_t next_env = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    const mdpp_grid_config& c = groups[g].cfg;
+    int rc = check_grid_config(ctx, &c);
+    if (rc) return rc;
+    if (c.n_dims != groups[0].cfg.n_dims)  // the row layout of state and I/O
+      return fail(ctx, MDPP_EINVAL, "grid groups must agree on n_dims");
+    if (groups[g].env_begin != next_env || groups[g].env_count < 0)
+      return fail(ctx, MDPP_EINVAL,
+                  "groups must tile the env range contiguously, in order");
+    next_env += groups[g].env_count;
+    std::memset(&dev[g], 0, sizeof dev[g]);
+    dev[g].cfg = c;
+    dev[g].env_begin = groups[g].env_begin;
+    dev[g].env_count = groups[g].env_count;
+    dev[g].gid_base = groups[g].global_id_base;
+    const int64_t chunks = (groups[g].env_count + kGBlock - 1) / kGBlock;
+    for (int64_t k = 0; k < chunks; ++k) map.push_back(CtaMapEntry{g, (int32_t)k});
+  }
+  if (map.empty()) return fail(ctx, MDPP_EINVAL, "no environments");
+  MDPP_CUDA(ctx, cudaSetDevice(ctx->device));
+  free_grid_groups(ctx);
+  MDPP_CUDA(ctx, cudaMalloc(&ctx->g_groups, dev.size() * sizeof(GridGroupDev)));
+  MDPP_CUDA(ctx, cudaMemcpy(ctx->g_groups, dev.data(), dev.size() * sizeof(GridGroupDev),
+                            cudaMemcpyHostToDevice));
+  MDPP_CUDA(ctx, cudaMalloc(&ctx->g_cta_map, map.size() * sizeof(CtaMapEntry)));
+  MDPP_CUDA(ctx, cudaMemcpy(ctx->g_cta_map, map.data(), map.size() * sizeof(CtaMapEntry),
+                            cudaMemcpyHostToDevice));
+  ctx->g_n_groups = n_groups;
+  ctx->g_n_ctas = (int64_t)map.size();
+  ctx->g_total_envs = next_env;
+  // the launch-wide view: flags any group has (which replay arrays are needed)
+  ctx->g_cfg = groups[0].cfg;
+  for (int g = 1; g < n_groups; ++g) {
+    ctx->g_cfg.has_transition_noise |= groups[g].cfg.has_transition_noise;
+    ctx->g_cfg.has_reward_noise |= groups[g].cfg.has_reward_noise;
+  }
   ctx->have_grid = true;
   return MDPP_OK;
 }
@@ -415,21 +537,29 @@ static int fill_grid(mdpp_ctx* ctx, const mdpp_grid_state* st,
   p->step_index = opts->step_index;
   p->step_index_dev = opts->step_index_dev;
   p->env_id_offset = opts->env_id_offset;
+  if (ctx->g_n_groups > 0) {
+    if (st->n_envs != ctx->g_total_envs)
+      return fail(ctx, MDPP_EINVAL, "state arrays do not match the grid groups");
+    p->groups = reinterpret_cast<const GridGroupDev*>(ctx->g_groups);
+    p->cta_map = reinterpret_cast<const CtaMapEntry*>(ctx->g_cta_map);
+    p->n_groups = ctx->g_n_groups;
+  }
   return MDPP_OK;
 }
 
-template <int ND, bool FAST>
+template <int ND, bool FAST, bool GROUPS>
 static int launch_grid(mdpp_ctx* ctx, const GridParams& p, cudaStream_t s) {
-  const unsigned grid = (unsigned)((p.st.n_envs + kGBlock - 1) / kGBlock);
+  const unsigned grid = GROUPS ? (unsigned)ctx->g_n_ctas
+                               : (unsigned)((p.st.n_envs + kGBlock - 1) / kGBlock);
   switch (p.noise_mode) {
     case MDPP_NOISE_OFF:
-      grid_rollout_kernel<ND, MDPP_NOISE_OFF, FAST><<<grid, kGBlock, 0, s>>>(p);
+      grid_rollout_kernel<ND, MDPP_NOISE_OFF, FAST, GROUPS><<<grid, kGBlock, 0, s>>>(p);
       break;
     case MDPP_NOISE_REPLAY:
-      grid_rollout_kernel<ND, MDPP_NOISE_REPLAY, FAST><<<grid, kGBlock, 0, s>>>(p);
+      grid_rollout_kernel<ND, MDPP_NOISE_REPLAY, FAST, GROUPS><<<grid, kGBlock, 0, s>>>(p);
       break;
     default:
-      grid_rollout_kernel<ND, MDPP_NOISE_PHILOX, FAST><<<grid, kGBlock, 0, s>>>(p);
+      grid_rollout_kernel<ND, MDPP_NOISE_PHILOX, FAST, GROUPS><<<grid, kGBlock, 0, s>>>(p);
   }
   MDPP_CUDA(ctx, cudaGetLastError());
   return MDPP_OK;
@@ -460,9 +590,18 @@ extern "C" int mdpp_grid_rollout(mdpp_ctx* ctx, const mdpp_grid_state* st,
   cudaStream_t s = (cudaStream_t)cuda_stream;
   const bool fast = io->obs && io->reward && io->terminated && io->truncated &&
                     !io->final_obs;
+  if (p.groups) {  // heterogeneous launch: every CTA under its own group's scalars
+    if (ctx->g_cfg.n_dims == 4)
+      return fast ? launch_grid<4, true, true>(ctx, p, s)
+                  : launch_grid<4, false, true>(ctx, p, s);
+    return fast ? launch_grid<2, true, true>(ctx, p, s)
+                : launch_grid<2, false, true>(ctx, p, s);
+  }
   if (ctx->g_cfg.n_dims == 4)
-    return fast ? launch_grid<4, true>(ctx, p, s) : launch_grid<4, false>(ctx, p, s);
-  return fast ? launch_grid<2, true>(ctx, p, s) : launch_grid<2, false>(ctx, p, s);
+    return fast ? launch_grid<4, true, false>(ctx, p, s)
+                : launch_grid<4, false, false>(ctx, p, s);
+  return fast ? launch_grid<2, true, false>(ctx, p, s)
+              : launch_grid<2, false, false>(ctx, p, s);
 }
 
 extern "C" int mdpp_grid_reset(mdpp_ctx* ctx, const mdpp_grid_state* st,
@@ -478,9 +617,12 @@ extern "C" int mdpp_grid_reset(mdpp_ctx* ctx, const mdpp_grid_state* st,
   p.init_states = init_states;
   p.reset_obs = obs;
   MDPP_CUDA(ctx, cudaSetDevice(ctx->device));
-  const unsigned grid = (unsigned)((p.st.n_envs + kGBlock - 1) / kGBlock);
+  const unsigned grid = p.groups ? (unsigned)ctx->g_n_ctas
+                                 : (unsigned)((p.st.n_envs + kGBlock - 1) / kGBlock);
   cudaStream_t s = (cudaStream_t)cuda_stream;
-  if (ctx->g_cfg.n_dims == 4) grid_reset_kernel<4><<<grid, kGBlock, 0, s>>>(p);
+  if (p.groups && ctx->g_cfg.n_dims == 4) grid_reset_kernel<4, true><<<grid, kGBlock, 0, s>>>(p);
+  else if (p.groups) grid_reset_kernel<2, true><<<grid, kGBlock, 0, s>>>(p);
+  else if (ctx->g_cfg.n_dims == 4) grid_reset_kernel<4><<<grid, kGBlock, 0, s>>>(p);
   else grid_reset_kernel<2><<<grid, kGBlock, 0, s>>>(p);
   MDPP_CUDA(ctx, cudaGetLastError());
   return MDPP_OK;

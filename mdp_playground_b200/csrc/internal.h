@@ -40,6 +40,11 @@ struct mdpp_ctx {
   int64_t c_n_ctas = 0, c_total_envs = 0;
   bool have_grid = false;
   mdpp_grid_config g_cfg;
+  // heterogeneous grid launches (mdpp_set_grid_groups)
+  void* g_groups = nullptr;   // GridGroupDev[n]
+  void* g_cta_map = nullptr;  // CtaMapEntry[g_n_ctas]
+  int g_n_groups = 0;
+  int64_t g_n_ctas = 0, g_total_envs = 0;
   // runtime-specialised kernels (jit.cu), keyed by their define string
   std::map<std::string, void*> jit_functions;   // CUfunction
   std::vector<void*> jit_modules;               // CUmodule

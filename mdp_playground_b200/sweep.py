@@ -9,8 +9,9 @@ static `env_config["env_config"]` and hands each to a separate Ray trial
 configuration group of a single batched env, stepped by one kernel launch,
 and the per-cell episode statistics are written in the reference's CSV layout
 (config_processor.py:241-259, :340-373) so its analysis code can read them.
-Continuous and grid experiment files (single-configuration kernels) get one
-batched env per cell instead.  No agent is trained: the policy is uniform random (or supplied by the caller).
+Continuous and grid experiment files whose cells cannot share one launch
+(different state dimension / dtype) get one batched env per cell instead.  No
+agent is trained: the policy is uniform random (or supplied by the caller).
 """
 import copy
 import importlib.util
@@ -123,13 +124,13 @@ class Sweep:
                 group_sizes=[self.envs_per_cell] * self.n_cells, shard=shard,
                 **env_kwargs)
             self.envs = [self.env]
-        elif self.kind == "continuous" and self._try_grouped_continuous(
-                VectorRLToyEnv, device, horizon, shard, env_kwargs):
+        elif self._try_grouped(VectorRLToyEnv, device, horizon, shard, env_kwargs):
             pass  # the whole grid is ONE heterogeneous env here too
         else:
-            # grid envs (and continuous grids whose cells differ in dimension,
-            # order or dtype) take one configuration per context: one env per
-            # cell, launched back to back on the same stream
+            # cells that differ in what shapes the state arrays (continuous:
+            # dimension or dtype; grid: irrelevant_features) take one
+            # configuration per context: one env per cell, launched back to
+            # back on the same stream
             rank, world = shard
             self.envs = [VectorRLToyEnv(
                 self.envs_per_cell, device=device, autoreset=True,
@@ -141,9 +142,10 @@ class Sweep:
         self.timesteps = 0
         self._returned = np.zeros(self.n_cells)
 
-    def _try_grouped_continuous(self, Env, device, horizon, shard, env_kwargs):
-        """Continuous cells that share dim / order / dtype / reward function run
-        as config groups of one env: one launch per rollout for the whole grid
+    def _try_grouped(self, Env, device, horizon, shard, env_kwargs):
+        """Continuous cells that share dim / dtype / reward function, and grid
+        cells that share the number of coordinates, run as config groups of
+        one env: one launch per rollout for the whole grid
         (e.g. experiments/sac_move_to_a_point_p_order_2.py:10-30)."""
         try:
             self.env = Env(
@@ -155,6 +157,8 @@ class Sweep:
             return False
         self.envs = [self.env]
         self.grouped = True
+        if self.kind == "grid":
+            return True
         import torch
         amax = torch.tensor([float(c.get("action_space_max", np.inf))
                              for c in self.cell_configs], device=self.env.device)
@@ -171,6 +175,8 @@ class Sweep:
                 acts = None if actions_fn is None else actions_fn(done, T)
                 if acts is None and self.kind == "continuous":
                     acts = self._random_actions_grouped(T, done)
+                elif acts is None and self.kind == "grid":
+                    acts = self._random_actions(self.env, T, done)
                 out = self.env.rollout(T, actions=acts, want_final_obs=False)
                 r = out["reward"].sum(dim=0).reshape(self.n_cells,
                                                      self.envs_per_cell)

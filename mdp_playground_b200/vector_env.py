@@ -98,9 +98,9 @@ class VectorRLToyEnv:
                     for c in config_groups]
             self._group_specs = [parse_config(c) for c in cfgs]
             kinds = {s_.kind for s_ in self._group_specs}
-            if len(kinds) != 1 or kinds == {"grid"}:
+            if len(kinds) != 1:
                 raise NotImplementedError(
-                    "config_groups: all discrete or all continuous envs")
+                    "config_groups: one state_space_type per launch")
             G = len(cfgs)
             if group_sizes is None:
                 from .sharding import even_group_sizes
@@ -125,8 +125,9 @@ class VectorRLToyEnv:
                    self._lib.mdpp_create(self.device.index, C.byref(self._ctx)))
         if self.spec.kind != "discrete" and self._shard[1] > 1:
             # the discrete path derives global Philox ids from `shard` per group
-            # (sharding.group_id_bases); continuous / grid envs are one group:
-            # rank r owns the ids [offset + r N, offset + (r + 1) N)
+            # (sharding.group_id_bases), and so do continuous / grid
+            # config_groups (which undo this); a single configuration is one
+            # group: rank r owns the ids [offset + r N, offset + (r + 1) N)
             self.env_id_offset += self._shard[0] * self.num_envs
         self._seed_epoch = 0
         if self.spec.kind == "discrete":
@@ -1432,27 +1433,59 @@ class VectorRLToyEnv:
                                      np.ones(nd, dtype=np.int64), (nd,),
                                      np.dtype(np.int64),
                                      seed=self.seed_dict.get("action_space"))
-        self.has_pnoise = bool(sp.transition_noise)
-        self.has_rnoise = sp.has_reward_noise
-        c = _lib.GridConfig()
-        c.n_dims, c.dense = nd, int(sp.make_denser)
-        c.reward_every_n_steps = sp.reward_every_n_steps
-        c.has_transition_noise = int(self.has_pnoise)
-        c.has_reward_noise = int(self.has_rnoise)
-        for k in range(nd):
-            c.shape[k] = sp.grid_shape[k]
-        c.target[0], c.target[1] = sp.target_point[0], sp.target_point[1]
-        c.transition_noise = sp.transition_noise
-        c.reward_noise_std = sp.reward_noise_std
-        c.reward_scale, c.reward_shift = sp.reward_scale, sp.reward_shift
-        c.term_state_reward = sp.term_state_reward
-        self._check(self._lib.mdpp_set_grid_config(self._ctx, C.byref(c)))
-        self.n_groups = 1
+        specs = self._group_specs
+        G = len(specs)
+        self.has_pnoise = any(bool(s_.transition_noise) for s_ in specs)
+        self.has_rnoise = any(s_.has_reward_noise for s_ in specs)
+
+        def grid_cfg(s_):
+            c = _lib.GridConfig()
+            c.n_dims, c.dense = nd, int(s_.make_denser)
+            c.reward_every_n_steps = s_.reward_every_n_steps
+            c.has_transition_noise = int(bool(s_.transition_noise))
+            c.has_reward_noise = int(s_.has_reward_noise)
+            for k in range(nd):
+                c.shape[k] = s_.grid_shape[k]
+            c.target[0], c.target[1] = s_.target_point[0], s_.target_point[1]
+            c.transition_noise = s_.transition_noise
+            c.reward_noise_std = s_.reward_noise_std
+            c.reward_scale, c.reward_shift = s_.reward_scale, s_.reward_shift
+            c.term_state_reward = s_.term_state_reward
+            return c
+        if G > 1:
+            # one launch for a whole sweep: every CTA steps its group's envs
+            # under that group's scalars (csrc/grid.cu GROUPS); the groups may
+            # differ in everything but the number of coordinates per cell
+            if any(len(s_.grid_shape) != nd for s_ in specs):
+                raise ValueError("config_groups of grid envs must agree on the "
+                                 "number of grid dimensions (irrelevant_features)")
+            if sp.image_representations or self.noise == "numpy":
+                raise NotImplementedError(
+                    "config_groups of grid envs: no images, no noise='numpy'")
+            from .sharding import group_id_bases
+            id_bases = group_id_bases(self._group_sizes, *self._shard)
+            groups = (_lib.GridGroup * G)()
+            begin = 0
+            self.group_slices = []
+            for gi, s_ in enumerate(specs):
+                groups[gi].cfg = grid_cfg(s_)
+                groups[gi].env_begin, groups[gi].env_count = begin, self._group_sizes[gi]
+                groups[gi].global_id_base = id_bases[gi]
+                self.group_slices.append(slice(begin, begin + self._group_sizes[gi]))
+                begin += self._group_sizes[gi]
+            assert begin == N
+            if self._shard[1] > 1:  # (ids come from the groups, not from the offset)
+                self.env_id_offset -= self._shard[0] * self.num_envs
+            self._check(self._lib.mdpp_set_grid_groups(self._ctx, groups, G))
+        else:
+            c = grid_cfg(sp)
+            self._check(self._lib.mdpp_set_grid_config(self._ctx, C.byref(c)))
+        self.n_groups = G
         self._pos = torch.zeros((nd, N), dtype=torch.int32, device=dev)
         self._t = torch.zeros(N, dtype=torch.int32, device=dev)
         self._episode = torch.zeros(N, dtype=torch.int32, device=dev)
         self._reached = torch.zeros(N, dtype=torch.uint8, device=dev)
-        self._stats = torch.zeros((_lib.STATS_SLOTS, 1, _lib.MDPP_N_STATS),
+        self._stats = torch.zeros((_lib.STATS_SLOTS, G, _lib.MDPP_N_STATS),
                                   dtype=torch.float64, device=dev)
         st = _lib.GridState()
         st.n_envs = N

@@ -161,3 +161,29 @@ class VectorGridOracle:
         self.step_index += T
         return dict(obs=obs, final_obs=final_obs, reward=reward,
                     terminated=term, truncated=trunc)
+
+
+class VectorGroupedGridOracle:
+    """A heterogeneous grid launch (mdpp_set_grid_groups): group g = `sizes[g]`
+    envs under the configuration of `scalar_envs[g]`, env-major; global Philox
+    ids like mdp_playground_b200/sharding.py.  One VectorGridOracle per group."""
+
+    def __init__(self, scalar_envs, sizes, autoreset=False, horizon=0, seed=0,
+                 env_id_offset=0, rank=0, world=1, **kw):
+        self.sizes = [int(n) for n in sizes]
+        self.parts, gbegin = [], 0
+        for e, n in zip(scalar_envs, self.sizes):
+            self.parts.append(VectorGridOracle(
+                e, n, autoreset=autoreset, horizon=horizon, seed=seed,
+                env_id_offset=env_id_offset + gbegin + rank * n, **kw))
+            gbegin += world * n
+
+    def reset(self):
+        return np.concatenate([p.reset() for p in self.parts])
+
+    def rollout(self, T, actions):
+        outs, begin = [], 0
+        for p, n in zip(self.parts, self.sizes):
+            outs.append(p.rollout(T, np.asarray(actions)[:, begin:begin + n]))
+            begin += n
+        return {k: np.concatenate([o[k] for o in outs], axis=1) for k in outs[0]}

@@ -247,3 +247,97 @@ def test_continuous_multi_group_launch_equals_single_group_envs_and_oracle():
         got = part.rollout(T, actions=a2[:, cols].contiguous())
         for k in ref:
             assert torch.equal(got[k], ref[k][:, cols]), (k, r)
+
+
+def _grid_cells():
+    base = dict(seed=0, state_space_type="grid", delay=0, sequence_length=1,
+                reward_function="move_to_a_point")
+    return [
+        dict(base, grid_shape=(8, 8), target_point=[5, 5], make_denser=True,
+             reward_scale=3.0, term_state_reward=-0.25, terminal_states=[[5, 5]]),
+        dict(base, grid_shape=(8, 8), target_point=[5, 5], make_denser=False,
+             transition_noise=0.3, reward_noise=1.0, reward_scale=2.0,
+             reward_shift=0.5, term_state_reward=2.0),
+        dict(base, grid_shape=(5, 9), target_point=[1, 7], make_denser=True,
+             transition_noise=0.2, reward_every_n_steps=2),
+        dict(base, grid_shape=(3, 4), target_point=[0, 0], make_denser=False,
+             reward_noise=0.5),
+        dict(base, grid_shape=(12, 6), target_point=[11, 2], make_denser=True,
+             transition_noise=1.0, reward_shift=-1.0),
+    ]
+
+
+def test_grid_multi_group_launch_equals_single_group_envs_and_oracle():
+    """config_groups for grid envs (one launch per sweep): the heterogeneous
+    launch == one env per cell (CUDA, bit-exact) == the grouped CPU oracle
+    (cells exact, rewards 1e-12); per-group statistics; 2 shards == unsplit."""
+    from oracle.scalar_env import ScalarRLToyEnv
+    from oracle.vector_grid_oracle import VectorGroupedGridOracle
+    cells = _grid_cells()
+    sizes = [150, 130, 128, 64, 200]
+    N, T = sum(sizes), 40
+    gen = torch.Generator("cuda").manual_seed(6)
+    acts = torch.zeros((T, N, 2), dtype=torch.int64, device="cuda")
+    dim = torch.randint(0, 2, (T, N, 1), device="cuda", generator=gen)
+    acts.scatter_(2, dim, torch.randint(-1, 2, (T, N, 1), device="cuda", generator=gen))
+    bad = torch.rand((T, N), device="cuda", generator=gen) < 0.05   # invalid: no-ops
+    acts[bad] = torch.randint(-2, 3, (int(bad.sum()), 2), device="cuda", generator=gen)
+    het = make_env(N, autoreset=True, horizon=17, philox_seed=9,
+                   config_groups=[dict(c) for c in cells], group_sizes=sizes)
+    assert het.n_groups == 5
+    obs0 = het.curr_obs.clone()
+    out = het.rollout(T, actions=acts, want_final_obs=True)
+    begin = 0
+    for c, n, sl in zip(cells, sizes, het.group_slices):
+        one = make_env(n, autoreset=True, horizon=17, philox_seed=9,
+                       env_id_offset=begin, **dict(c))
+        assert torch.equal(one.curr_obs, obs0[sl])
+        ref = one.rollout(T, actions=acts[:, sl].contiguous(), want_final_obs=True)
+        for k in ref:
+            assert torch.equal(out[k][:, sl], ref[k]), (k, begin)
+        begin += n
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        scalars = [ScalarRLToyEnv(**dict(c)) for c in cells]
+    ora = VectorGroupedGridOracle(scalars, sizes, autoreset=True, horizon=17, seed=9)
+    assert np.array_equal(ora.reset(), obs0.cpu().numpy())
+    want = ora.rollout(T, acts.cpu().numpy())
+    for k in ("obs", "final_obs", "terminated", "truncated"):
+        assert np.array_equal(out[k].cpu().numpy(), want[k]), k
+    np.testing.assert_allclose(out["reward"].cpu().numpy(), want["reward"],
+                               rtol=1e-12, atol=1e-12)
+    st = het.episode_stats()
+    assert st["transitions"].tolist() == [n * T for n in sizes]
+    for k in ("episodes", "noisy_transitions", "terminated"):
+        assert st[k].tolist() == [p.stats[k] for p in ora.parts], k
+    # the fast path (no final_obs) and single steps run the same kernels
+    het2 = make_env(N, autoreset=True, horizon=17, philox_seed=9,
+                    config_groups=[dict(c) for c in cells], group_sizes=sizes)
+    for t in range(5):
+        o, r, te, tr, _ = het2.step(acts[t])
+        assert torch.equal(o, out["obs"][t]) and torch.equal(r, out["reward"][t])
+        assert torch.equal(te, out["terminated"][t]) and torch.equal(tr, out["truncated"][t])
+    # two shards of the same job
+    half = [64, 64, 128, 32, 96]
+    whole = make_env(2 * sum(half), autoreset=True, horizon=17, philox_seed=9,
+                     config_groups=[dict(c) for c in cells],
+                     group_sizes=[2 * n for n in half])
+    a2 = torch.zeros((T, 2 * sum(half), 2), dtype=torch.int64, device="cuda")
+    a2[..., 1] = torch.randint(-1, 2, (T, 2 * sum(half)), device="cuda", generator=gen)
+    ref = whole.rollout(T, actions=a2)
+    for r in range(2):
+        part = make_env(sum(half), autoreset=True, horizon=17, philox_seed=9,
+                        config_groups=[dict(c) for c in cells], group_sizes=half,
+                        shard=(r, 2))
+        cols = torch.cat([torch.arange(sl.start + r * n, sl.start + (r + 1) * n)
+                          for sl, n in zip(whole.group_slices, half)]).cuda()
+        got = part.rollout(T, actions=a2[:, cols].contiguous())
+        for k in ref:
+            assert torch.equal(got[k], ref[k][:, cols]), (k, r)
+
+
+def test_grid_groups_must_agree_on_the_number_of_coordinates():
+    cells = _grid_cells()[:2]
+    cells[1] = dict(cells[1], irrelevant_features=True)
+    with pytest.raises(ValueError, match="number of grid dimensions"):
+        make_env(64, config_groups=cells)

@@ -152,3 +152,26 @@ def test_sweep_over_a_continuous_experiment_grid(tmp_path):
     assert not np.allclose(res["episode_reward_mean"][0::2], res["episode_reward_mean"][1::2])
     lines = open(sw.write_csv(str(tmp_path / "cont.csv"))).read().splitlines()
     assert len(lines) == 13 and "time_unit" in lines[0]
+
+
+@pytest.mark.gpu
+def test_sweep_over_a_grid_world_experiment_grid(tmp_path):
+    """Grid-world experiment files: the whole grid is ONE env with config
+    groups (one launch per rollout)."""
+    fixture = os.path.join(HERE, "fixtures", "grid_noises_like.py")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sw = sweep.Sweep(fixture, envs_per_cell=256)
+    assert sw.kind == "grid" and sw.n_cells == 2 * 3 * 2 * 2
+    assert len(sw.envs) == 1 and sw.env.n_groups == 24   # one heterogeneous env
+    res = sw.run(200, chunk=64)
+    assert np.all(res["transitions"] == 256 * 200)
+    assert np.all(res["episodes"] > 0) and np.all(np.isfinite(res["episode_reward_mean"]))
+    pn = np.array([c["transition_noise"] for c in sw.cell_configs])
+    noisy = res["noisy_transitions"] / res["transitions"]
+    assert np.all(noisy[pn == 0] == 0)
+    # (a substituted action needs a valid one: the random policy's are all valid)
+    np.testing.assert_allclose(noisy[pn == 0.25], 0.25, atol=0.01)
+    np.testing.assert_allclose(noisy[pn == 0.5], 0.5, atol=0.01)
+    lines = open(sw.write_csv(str(tmp_path / "grid.csv"))).read().splitlines()
+    assert len(lines) == 25 and "transition_noise" in lines[0]
