@@ -12,6 +12,8 @@
 // streaming stores first; the shape is then assembled as column bitmaps of the
 // FINAL image in shared memory and only its non-empty 4-byte words are stored
 // again.  K5: one CTA per (sub-)image, 16 output bytes per thread and store.
+#include <cstdlib>
+
 #include "internal.h"
 #include "philox.cuh"
 
@@ -21,6 +23,10 @@ constexpr int kRBlock = 128;
 constexpr int kMaskRows = 64;
 constexpr int kMaskCentre = 31;
 constexpr int kRotCols = 80;  // bounding box of the rotated polygon: <= 2*30+7+2
+// zero columns either side of the polygon mask: the rotation gather reads up to
+// 15 samples past the mask box (see the segment test) without a bounds test
+constexpr int kMaskPad = 24;
+constexpr int kMaskCols = kMaskRows + 2 * kMaskPad;
 
 struct RenderDParams {
   mdpp_image_discrete_tables tb;
@@ -35,9 +41,10 @@ struct RenderDParams {
   int64_t env_id_offset;
 };
 
-__device__ __forceinline__ int floor_div(int a, int b) {
-  int q = a / b;
-  return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+// floor(a / b) for |a| < 2^15, 0 < b < 2^15: (a + 0.5) / b is at least 0.5 / b
+// away from every integer, far more than the error of the fp32 product.
+__device__ __forceinline__ int floor_div_small(int a, int b, float inv_b) {
+  return b == 1 ? a : (int)floorf(((float)a + 0.5f) * inv_b);
 }
 
 // One WARP renders one image (4 images per CTA): the kernel is issue-bound
@@ -50,14 +57,15 @@ constexpr int kImagesPerCta = kRBlock / 32;
 
 // (12 CTAs = 48 images per SM at 40 registers; capping the registers at 32 for
 // 16 CTAs spills and measured 20 % slower.)
+template <int V>  // experiment switches (MDPP_RENDER_VARIANT); none at present
 __global__ void __launch_bounds__(kRBlock, 12)
 render_discrete_kernel(const __grid_constant__ RenderDParams p) {
-  __shared__ uint64_t mask_s[kImagesPerCta][kMaskRows];    // polygon column bitmaps
+  __shared__ uint64_t mask_s[kImagesPerCta][kMaskCols];    // polygon column bitmaps
   __shared__ uint64_t fmask_s[kImagesPerCta][kRotCols][2];  // ... of the final image
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * kImagesPerCta + warp;
   if (m >= p.n_images) return;  // whole warp; only warp-level barriers below
-  uint64_t* mask = mask_s[warp];
+  uint64_t* mask = mask_s[warp] + kMaskPad;
   uint64_t (*fmask)[2] = fmask_s[warp];
   const mdpp_image_discrete_tables& tb = p.tb;
   const int W = tb.width, H = tb.height;
@@ -70,18 +78,24 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
   // dependent loads of the set-up below (state -> Philox -> variant maps ->
   // mask id -> mask bits) are in flight.  The warp barriers of the set-up
   // order them before the box stores of phase 2.
+  uint4* out4 = reinterpret_cast<uint4*>(out);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  const int n16 = total / 16;
+  int zi = lane;  // next 16-byte word this lane zeroes
+  // (rotated images: only a third of the fill up front, the rest is issued
+  // between the gather iterations so that the stores drain under the math:
+  // 68 -> 62 us per 16 384 images against the whole fill first)
+  const int n_first = p.tb.has_rotate ? n16 / 3 : n16;
   if (fast) {
-    uint4* out4 = reinterpret_cast<uint4*>(out);
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    const int n16 = total / 16;
-    int i = lane;
-    for (; i + 96 < n16; i += 128) {
-      __stcs(out4 + i, z); __stcs(out4 + i + 32, z);
-      __stcs(out4 + i + 64, z); __stcs(out4 + i + 96, z);
+    for (; zi + 96 < n_first; zi += 128) {
+      __stcs(out4 + zi, z); __stcs(out4 + zi + 32, z);
+      __stcs(out4 + zi + 64, z); __stcs(out4 + zi + 96, z);
     }
-    for (; i < n16; i += 32) __stcs(out4 + i, z);
+    if (n_first == n16)
+      for (; zi < n16; zi += 32) __stcs(out4 + zi, z);
   }
   for (int w = lane; w < 2 * kRotCols; w += 32) (&fmask[0][0])[w] = 0ull;
+  if (lane < kMaskPad) { mask[-1 - lane] = 0ull; mask[kMaskRows + lane] = 0ull; }
   // launched with MDPP_LAUNCH_OVERLAP_PREVIOUS: everything above overlapped the
   // previous kernel of the stream (the step that produces `states`); wait for
   // it now.  Returns at once in an ordinary launch.
@@ -97,13 +111,18 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
   } else {
     // draw order of the reference (:149-181, :251, :258-259); one Philox
     // call per image: w0 scale, w1 / w2 shifts, w3 rotation + flip bits
-    const int n_sub = max(tb.n_sub_images, 1);
-    const int64_t e = m / n_sub;  // (step, env); sub-image m % n_sub of it
-    const uint32_t gid = (uint32_t)(p.env_id_offset + e % p.n_envs);
-    const uint64_t step = p.step_index + (uint64_t)(e / p.n_envs) +
+    // (n_images < 2^31, checked by the caller: 32-bit arithmetic; the usual
+    // shapes -- one or two sub-images, one step per launch -- divide nothing)
+    uint32_t e = (uint32_t)m, sub = 0;  // (step, env); sub-image `sub` of it
+    if (tb.n_sub_images == 2) { sub = e & 1u; e >>= 1; }
+    else if (tb.n_sub_images > 2) { sub = e % (uint32_t)tb.n_sub_images; e /= (uint32_t)tb.n_sub_images; }
+    uint32_t t_rel = 0;
+    if (e >= (uint32_t)p.n_envs) { t_rel = e / (uint32_t)p.n_envs; e -= t_rel * (uint32_t)p.n_envs; }
+    const uint32_t gid = (uint32_t)p.env_id_offset + e;
+    const uint64_t step = p.step_index + (uint64_t)t_rel +
                           (p.step_index_dev ? *p.step_index_dev : 0ull);
     U4 w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
-                         p.stream + 16u * (uint32_t)(m % n_sub), p.k0, p.k1);
+                         p.stream + 16u * sub, p.k0, p.k1);
     R = tb.r_min;
     if (tb.has_scale) {  // R = r_min + #{thresholds <= u}, one lane each
       const double u = uniform32(w.x);
@@ -118,12 +137,15 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
       const int mw = W / 2 - R, mh = H / 2 - R;
       const int aw = -mw + 1 + (int)__umulhi(w.y, (uint32_t)max(2 * mw - 1, 1));
       const int ah = -mh + 1 + (int)__umulhi(w.z, (uint32_t)max(2 * mh - 1, 1));
-      sw += floor_div(aw, tb.sh_quant) * tb.sh_quant;
-      sh += floor_div(ah, tb.sh_quant) * tb.sh_quant;
+      const float inv_q = 1.0f / (float)tb.sh_quant;
+      sw += floor_div_small(aw, tb.sh_quant, inv_q) * tb.sh_quant;
+      sh += floor_div_small(ah, tb.sh_quant, inv_q) * tb.sh_quant;
     }
     rot = -1;
-    if (tb.has_rotate)
-      rot = ((int)__umulhi(w.w, 360u) / tb.ro_quant) * tb.ro_quant;
+    if (tb.has_rotate) {
+      rot = (int)__umulhi(w.w, 360u);
+      rot = floor_div_small(rot, tb.ro_quant, 1.0f / (float)tb.ro_quant) * tb.ro_quant;
+    }
     flip = 0;
     if (tb.has_flip && (w.w & 1u) == 0) flip = (w.w & 2u) == 0 ? 1 : 2;
   }
@@ -145,14 +167,15 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
     c_lo = max(kMaskCentre - R - 2, 0); c_hi = min(kMaskCentre + R + 3, kMaskRows - 1);
     b_lo = c_lo + s; b_hi = c_hi + s;
   } else {
-    const int32_t* c = tb.rot_coeff + (rot % 360) * 6;
+    const int32_t* c = tb.rot_coeff + (rot >= 360 ? rot % 360 : rot) * 6;
     a0 = c[0]; a1 = c[1]; a2 = c[2]; a3 = c[3]; a4 = c[4]; a5 = c[5];
     // bounding box of the polygon (disc of radius R around the centre) in the
     // FINAL image: forward-map the centre through the rotation and the flip
     const float X = (float)sw * 65536.f - (float)a2, Y = (float)sh * 65536.f - (float)a5;
-    const float det = (float)a0 * (float)a4 - (float)a1 * (float)a3;
-    float cx = ((float)a4 * X - (float)a1 * Y) / det;
-    float cy = ((float)a0 * Y - (float)a3 * X) / det;
+    // (a bounding box with 3 pixels of slack: an approximate reciprocal will do)
+    const float inv_det = __frcp_rn((float)a0 * (float)a4 - (float)a1 * (float)a3);
+    float cx = ((float)a4 * X - (float)a1 * Y) * inv_det;
+    float cy = ((float)a0 * Y - (float)a3 * X) * inv_det;
     if (flip == 1) cx = (float)(W - 1) - cx;
     if (flip == 2) cy = (float)(H - 1) - cy;
     const int bx0 = max((int)floorf(cx) - R - 3, 0);
@@ -198,43 +221,66 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
   // NEAREST rotation (16.16 fixed point) is stepped incrementally along y.
   if (rot >= 0 && c_hi >= 0 && b_hi >= 0) {
     const int ncols = c_hi + 1, nrows = b_hi + 1;
+    // (rows per work item; 8 measured 8 % slower: more per-item set-up than
+    // the tighter fit to the box saves)
+    constexpr int kSeg = 16;
     uint16_t* slots = reinterpret_cast<uint16_t*>(&fmask[0][0]);
-    const int segs = (nrows + 15) >> 4;  // slots past it stay zero (cleared above)
+    const int segs = (nrows + kSeg - 1) / kSeg;  // slots past it stay zero (cleared above)
     const int m_lo = kMaskCentre - R - 2, m_hi = kMaskCentre + R + 3;  // set mask bits
     const int sy = flip == 2 ? -1 : 1;                      // d(fy) / d(y)
     const int dX = a1 * sy, dY = a4 * sy;
+    const float inv_segs = 1.0f / (float)segs;
+    // 16.16 source coordinates, pre-shifted into mask space (mx = X >> 16,
+    // my = Y >> 16), as linear forms of the box-local (column c, row k):
+    //   X = X00 + c cX + k dX,  Y = Y00 + c cY + k dY
+    // Mask bits outside the image were cleared at load, so the image-bounds
+    // test of the rotation is implied by the mask lookup.
+    const int sx = flip == 1 ? -1 : 1;
+    const int fx0 = flip == 1 ? W - 1 - xbase : xbase;
+    const int fy0 = flip == 2 ? H - 1 - ybase : ybase;
+    const int cX = a0 * sx, cY = a3 * sx;
+    const int X00 = a2 + a1 * fy0 + a0 * fx0 + (kMaskCentre - sw) * 65536;
+    const int Y00 = a5 + a4 * fy0 + a3 * fx0 + (kMaskCentre - sh) * 65536;
     for (int w = lane; w < ncols * segs; w += 32) {
-      const int c = w / segs, sgm = w - c * segs;
-      const int k0 = sgm * 16;                              // box-local rows
-      const int x = xbase + c;
-      const int fx = flip == 1 ? W - 1 - x : x;
-      const int fy = flip == 2 ? H - 1 - (ybase + k0) : ybase + k0;
-      // 16.16 source coordinates, pre-shifted into mask space (mx = X >> 16,
-      // my = Y >> 16).  Mask bits outside the image were cleared at load, so
-      // the image-bounds test of the rotation is implied by the mask-bounds
-      // test -- one compare on (mx | my).
-      int X = a2 + a1 * fy + a0 * fx + (kMaskCentre - sw) * 65536;
-      int Y = a5 + a4 * fy + a3 * fx + (kMaskCentre - sh) * 65536;
+      // (w + 0.5) / segs is at least 0.5 / segs away from an integer: exact
+      const int c = (int)(((float)w + 0.5f) * inv_segs);
+      const int sgm = w - c * segs;
+      const int k0 = sgm * kSeg;                            // box-local rows
+      int X = X00 + c * cX + k0 * dX;
+      int Y = Y00 + c * cY + k0 * dY;
       // the 16 samples lie on a segment: if both ends are on the same outer
       // side of the polygon's mask box, none of them can hit a set bit
-      const int mxa = X >> 16, mxb = (X + 15 * dX) >> 16;
-      const int mya = Y >> 16, myb = (Y + 15 * dY) >> 16;
+      const int mxa = X >> 16, mxb = (X + (kSeg - 1) * dX) >> 16;
+      const int mya = Y >> 16, myb = (Y + (kSeg - 1) * dY) >> 16;
       uint32_t bits = 0;
       if (!(max(mxa, mxb) < m_lo || min(mxa, mxb) > m_hi ||
             max(mya, myb) < m_lo || min(mya, myb) > m_hi)) {
+        // every sample lies between the two ends, i.e. at most 15 columns
+        // outside [m_lo, m_hi]: inside the zero padding of `mask`; a row
+        // outside 0..63 shifts everything out (shr.b64 clamps its amount).
+        // Bit k enters at the top and slides down.
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {  // bit k enters at the top and slides down
-          const int mx = X >> 16, my = Y >> 16;
-          uint32_t v = 0;
-          if ((unsigned)(mx | my) < 64u) v = (uint32_t)(mask[mx] >> my);
-          bits = __funnelshift_r(bits, v, 1);
+        for (int k = 0; k < kSeg; ++k) {
+          uint64_t v;
+          asm("shr.b64 %0, %1, %2;" : "=l"(v) : "l"(mask[X >> 16]), "r"(Y >> 16));
+          bits = __funnelshift_r(bits, (uint32_t)v, 1);
           X += dX; Y += dY;
         }
-        bits >>= 16;
-        if (k0 + 16 > nrows) bits &= (1u << (nrows - k0)) - 1u;
+        bits >>= 32 - kSeg;
+        // (rows past the box need no masking: they are exact samples too, and
+        // phase 2 stores whole 4-row words up to b_hi only -- inside the image)
       }
       slots[c * 8 + sgm] = (uint16_t)bits;  // little-endian: slot s = bits 16s..
+      if (fast) {  // the next slice of the zero fill
+#pragma unroll
+        for (int q = 0; q < 4; ++q, zi += 32)
+          if (zi < n16) __stcs(out4 + zi, z);
+      }
     }
+    __syncwarp();
+  }
+  if (fast && n_first != n16) {  // what is left of the zero fill
+    for (; zi < n16; zi += 32) __stcs(out4 + zi, z);
     __syncwarp();
   }
   if (fast) {
@@ -245,17 +291,23 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
     // of one column, lanes 16-31 those of the next.
     const uint8_t* fb = reinterpret_cast<const uint8_t*>(&fmask[0][0]);
     uint8_t* obase = out + ((int64_t)xbase * H + ybase);
-    const int j_hi = min(b_hi >> 2, 31);
-    for (int j = (b_lo >> 2) + (lane & 15); j <= j_hi; j += 16) {
-      const int nsh = (j & 1) * 4;
-      const uint8_t* src = fb + (j >> 1);
-      for (int c = c_lo + (lane >> 4); c <= c_hi; c += 2) {
-        const uint32_t nib = ((uint32_t)src[c * 16] >> nsh) & 0xFu;
-        if (nib) {
-          // 4 bits -> 4 bytes of 0 / 255: bit k of b lands on bit 8k of
-          // b * (1 + 2^7 + 2^14 + 2^21); the isolated 0/1 bytes times 255 fill up
-          const uint32_t word = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;
-          __stcs(reinterpret_cast<uint32_t*>(obase + (c * H + 4 * j)), word);
+    {
+      // 8 lanes per column (a byte of the bitmap = 8 rows = 2 words each), 4
+      // columns per pass; boxes taller than 64 rows take a second round
+      const int sub = lane & 7;
+      for (int jb = (b_lo >> 3) + sub; jb <= min(b_hi >> 3, 15); jb += 8) {
+        const uint8_t* src = fb + jb;
+        uint8_t* dst = obase + 8 * jb;
+        for (int c = c_lo + (lane >> 3); c <= c_hi; c += 4) {
+          const uint32_t byte = src[c * 16];
+          if (byte) {
+            uint32_t* q = reinterpret_cast<uint32_t*>(dst + c * H);
+            const uint32_t lo = byte & 0xFu, hi = byte >> 4;
+            if (lo) __stcs(q, ((lo * 0x00204081u) & 0x01010101u) * 0xFFu);
+            // (rows past b_hi hold samples too, possibly below the image)
+            if (hi && 8 * jb + 4 <= b_hi)
+              __stcs(q + 1, ((hi * 0x00204081u) & 0x01010101u) * 0xFFu);
+          }
         }
       }
     }
@@ -393,7 +445,14 @@ extern "C" int mdpp_render_discrete(mdpp_ctx* ctx,
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (opts->flags & MDPP_LAUNCH_OVERLAP_PREVIOUS) ? 1 : 0;
-  MDPP_CUDA(ctx, cudaLaunchKernelEx(&cfg, render_discrete_kernel, p));
+  static const int variant = [] {  // experiment knob
+    const char* e = std::getenv("MDPP_RENDER_VARIANT");
+    return e ? std::atoi(e) : 0;
+  }();
+  switch (variant) {
+    case 1: MDPP_CUDA(ctx, cudaLaunchKernelEx(&cfg, render_discrete_kernel<1>, p)); break;
+    default: MDPP_CUDA(ctx, cudaLaunchKernelEx(&cfg, render_discrete_kernel<0>, p));
+  }
   MDPP_CUDA(ctx, cudaGetLastError());
   return MDPP_OK;
 }
