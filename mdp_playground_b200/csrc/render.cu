@@ -55,10 +55,12 @@ __device__ __forceinline__ int floor_div_small(int a, int b, float inv_b) {
 // the rotation gather and the box stores.
 constexpr int kImagesPerCta = kRBlock / 32;
 
-// (12 CTAs = 48 images per SM at 40 registers; capping the registers at 32 for
-// 16 CTAs spills and measured 20 % slower.)
+// (10 CTAs = 40 images per SM at 48 registers: the rotation gather keeps more
+// shared-memory loads in flight than at 40 registers / 12 CTAs, and 16 384
+// images are 2.8 instead of 2.3 waves: 43.0 -> 40.4 us rotated, 33.4 -> 31.2
+// us unrotated; 8 CTAs at 59 registers: 39.9 / 32.6 us.)
 template <int V>  // experiment switches (MDPP_RENDER_VARIANT); none at present
-__global__ void __launch_bounds__(kRBlock, 12)
+__global__ void __launch_bounds__(kRBlock, 10)
 render_discrete_kernel(const __grid_constant__ RenderDParams p) {
   __shared__ uint64_t mask_s[kImagesPerCta][kMaskCols];    // polygon column bitmaps
   __shared__ uint64_t fmask_s[kImagesPerCta][kRotCols][2];  // ... of the final image
@@ -287,13 +289,14 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
     // phase 2: the 4-byte words of the box whose nibble is not empty (the
     // barriers above order these stores after the zero fill of phase 1).  No
     // set bit lies outside the image (see the mask load / the gather bounds),
-    // so the nibble test is also the bounds test.  Lanes 0-15 take the words
-    // of one column, lanes 16-31 those of the next.
+    // so the nibble test is also the bounds test.
     const uint8_t* fb = reinterpret_cast<const uint8_t*>(&fmask[0][0]);
     uint8_t* obase = out + ((int64_t)xbase * H + ybase);
     {
       // 8 lanes per column (a byte of the bitmap = 8 rows = 2 words each), 4
-      // columns per pass; boxes taller than 64 rows take a second round
+      // columns per pass; boxes taller than 64 rows take a second round.
+      // (Two lanes per column with 8 words each: same speed rotated, 25 %
+      // slower unrotated.)
       const int sub = lane & 7;
       for (int jb = (b_lo >> 3) + sub; jb <= min(b_hi >> 3, 15); jb += 8) {
         const uint8_t* src = fb + jb;
