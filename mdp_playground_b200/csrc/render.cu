@@ -48,12 +48,158 @@ __device__ __forceinline__ int floor_div_small(int a, int b, float inv_b) {
 }
 
 // One WARP renders one image (4 images per CTA): the kernel is issue-bound
-// -- a few hundred scalar instructions of per-image set-up against 625 vector
-// stores -- so the set-up must not be replicated over several warps, and warp
-// barriers replace CTA barriers.  All lanes compute the (uniform) transform
-// parameters redundantly; lane-parallel work is the zero fill, the mask load,
-// the rotation gather and the box stores.
+// -- several hundred scalar instructions of per-image set-up against 625
+// vector stores -- so the set-up must not be replicated over several warps,
+// and warp barriers replace CTA barriers.  All lanes compute the (uniform)
+// transform parameters redundantly; lane-parallel work is the zero fill, the
+// mask load, the rotation gather and the box stores.  (Computing the set-up of
+// the CTA's four images once, in lanes 0-3 of warp 0, saves ~250 of ~1900 warp
+// instructions per image but measured 8 % SLOWER: three warps wait at a CTA
+// barrier for the dependent loads of the fourth.)
 constexpr int kImagesPerCta = kRBlock / 32;
+
+// Everything the lane-parallel phases need to know about one image.
+struct ImageSetup {
+  int32_t R, sw, sh, rot, flip;  // transform parameters (rot < 0: unrotated)
+  int32_t id;                    // mask of (state, R, vertex variants)
+  // Final-image geometry of the box-local column bitmaps `fmask`: bit b of
+  // column c is final pixel (xbase + c, ybase + b), ybase a multiple of 4 so
+  // that a nibble of the bitmap is one aligned 4-byte word of the output;
+  // columns c_lo..c_hi / bits b_lo..b_hi can be set (c_hi < 0: nothing).
+  int32_t xbase, ybase, c_lo, c_hi, b_lo, b_hi;
+  // rotation gather: 16.16 source coordinates, pre-shifted into mask space
+  // (mx = X >> 16, my = Y >> 16), as linear forms of the box-local (column c,
+  // row k):  X = X00 + c cX + k dX,  Y = Y00 + c cY + k dY
+  int32_t X00, Y00, cX, cY, dX, dY;
+  uint32_t rows_lo, rows_hi;     // mask rows whose pixel lies inside the image
+};
+
+// R = r_min + #{thresholds <= u}: one threshold per lane and a ballot (all 32
+// lanes hold the same u).  `thr0` = this lane's threshold of the first 32,
+// loaded by the caller ahead of the dependent chain (+inf past the end).
+__device__ __forceinline__ int scaled_radius(const mdpp_image_discrete_tables& tb,
+                                             uint32_t word, int lane, double thr0) {
+  int R = tb.r_min;
+  if (!tb.has_scale) return R;
+  const double u = uniform32(word);
+  R += __popc(__ballot_sync(0xffffffffu, thr0 <= u));
+  for (int base = 32; base < tb.n_radii - 1; base += 32) {
+    const int k = base + lane;
+    const bool le = k < tb.n_radii - 1 && tb.r_thresholds[k] <= u;
+    R += __popc(__ballot_sync(0xffffffffu, le));
+  }
+  return R;
+}
+
+// The scalar set-up of image m (see ImageSetup).  Restates the draw order of
+// the reference (:149-181, :251, :258-259): one Philox call per image, w0
+// scale, w1 / w2 shifts, w3 rotation + flip bits.  Uniform over the warp.
+__device__ __forceinline__ ImageSetup image_setup(const RenderDParams& p, int64_t m,
+                                                  int lane, double thr0) {
+  const mdpp_image_discrete_tables& tb = p.tb;
+  const int W = tb.width, H = tb.height;
+  ImageSetup g;
+  int state = (int)p.states[m];
+  state = min(max(state, 0), tb.n_states - 1);
+  int R, sw, sh, rot, flip;
+  if (p.params_in) {
+    const int32_t* q = p.params_in + m * 5;
+    R = q[0]; sw = q[1]; sh = q[2]; rot = q[3]; flip = q[4];
+  } else {
+    // (n_images < 2^31, checked by the caller: 32-bit arithmetic; the usual
+    // shapes -- one or two sub-images, one step per launch -- divide nothing)
+    uint32_t e = (uint32_t)m, sub = 0;  // (step, env); sub-image `sub` of it
+    if (tb.n_sub_images == 2) { sub = e & 1u; e >>= 1; }
+    else if (tb.n_sub_images > 2) { sub = e % (uint32_t)tb.n_sub_images; e /= (uint32_t)tb.n_sub_images; }
+    uint32_t t_rel = 0;
+    if (e >= (uint32_t)p.n_envs) { t_rel = e / (uint32_t)p.n_envs; e -= t_rel * (uint32_t)p.n_envs; }
+    const uint32_t gid = (uint32_t)p.env_id_offset + e;
+    const uint64_t step = p.step_index + (uint64_t)t_rel +
+                          (p.step_index_dev ? *p.step_index_dev : 0ull);
+    U4 w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
+                         p.stream + 16u * sub, p.k0, p.k1);
+    R = scaled_radius(tb, w.x, lane, thr0);
+    sw = W / 2; sh = H / 2;
+    if (tb.has_shift) {  // integers(-m + 1, m), m = W/2 - R, then quantise
+      const int mw = W / 2 - R, mh = H / 2 - R;
+      const int aw = -mw + 1 + (int)__umulhi(w.y, (uint32_t)max(2 * mw - 1, 1));
+      const int ah = -mh + 1 + (int)__umulhi(w.z, (uint32_t)max(2 * mh - 1, 1));
+      const float inv_q = 1.0f / (float)tb.sh_quant;
+      sw += floor_div_small(aw, tb.sh_quant, inv_q) * tb.sh_quant;
+      sh += floor_div_small(ah, tb.sh_quant, inv_q) * tb.sh_quant;
+    }
+    rot = -1;
+    if (tb.has_rotate) {
+      rot = (int)__umulhi(w.w, 360u);
+      rot = floor_div_small(rot, tb.ro_quant, 1.0f / (float)tb.ro_quant) * tb.ro_quant;
+    }
+    flip = 0;
+    if (tb.has_flip && (w.w & 1u) == 0) flip = (w.w & 2u) == 0 ? 1 : 2;
+  }
+  if (lane == 0 && p.params_out) {
+    int32_t* q = p.params_out + m * 5;
+    q[0] = R; q[1] = sw; q[2] = sh; q[3] = rot; q[4] = flip;
+  }
+  g.R = R; g.sw = sw; g.sh = sh; g.rot = rot; g.flip = flip;
+  g.X00 = g.Y00 = g.cX = g.cY = g.dX = g.dY = 0;
+  if (rot < 0) {
+    // unrotated: the mask itself, mirrored for the flips and shifted by s bits
+    const int y_off = flip == 2 ? H - 33 - sh : sh - kMaskCentre;
+    g.ybase = y_off & ~3;
+    const int s = y_off - g.ybase;
+    g.xbase = flip == 1 ? W - 33 - sw : sw - kMaskCentre;
+    g.c_lo = max(kMaskCentre - R - 2, 0); g.c_hi = min(kMaskCentre + R + 3, kMaskRows - 1);
+    g.b_lo = g.c_lo + s; g.b_hi = g.c_hi + s;
+  } else {
+    const int32_t* c = tb.rot_coeff + (rot >= 360 ? rot % 360 : rot) * 6;
+    const int a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3], a4 = c[4], a5 = c[5];
+    // bounding box of the polygon (disc of radius R around the centre) in the
+    // FINAL image: forward-map the centre through the rotation and the flip
+    const float X = (float)sw * 65536.f - (float)a2, Y = (float)sh * 65536.f - (float)a5;
+    // (a bounding box with 3 pixels of slack: an approximate reciprocal will do)
+    const float inv_det = __frcp_rn((float)a0 * (float)a4 - (float)a1 * (float)a3);
+    float cx = ((float)a4 * X - (float)a1 * Y) * inv_det;
+    float cy = ((float)a0 * Y - (float)a3 * X) * inv_det;
+    if (flip == 1) cx = (float)(W - 1) - cx;
+    if (flip == 2) cy = (float)(H - 1) - cy;
+    const int bx0 = max((int)floorf(cx) - R - 3, 0);
+    const int bx1 = min(min((int)ceilf(cx) + R + 3, W - 1), bx0 + kRotCols - 1);
+    const int by0 = max((int)floorf(cy) - R - 3, 0) & ~3;
+    const int by1 = min(min((int)ceilf(cy) + R + 3, H - 1), by0 + 127);
+    g.xbase = bx0; g.ybase = by0;
+    g.c_lo = 0; g.c_hi = bx1 - bx0;  // may be negative: nothing to draw
+    g.b_lo = 0; g.b_hi = by1 - by0;
+    const int sx = flip == 1 ? -1 : 1, sy = flip == 2 ? -1 : 1;  // d(fx)/d(x), d(fy)/d(y)
+    const int fx0 = flip == 1 ? W - 1 - bx0 : bx0;
+    const int fy0 = flip == 2 ? H - 1 - by0 : by0;
+    g.dX = a1 * sy; g.dY = a4 * sy;
+    g.cX = a0 * sx; g.cY = a3 * sx;
+    g.X00 = a2 + a1 * fy0 + a0 * fx0 + (kMaskCentre - sw) * 65536;
+    g.Y00 = a5 + a4 * fy0 + a3 * fx0 + (kMaskCentre - sh) * 65536;
+  }
+  {
+    const int ri = min(max(R - tb.r_min, 0), tb.n_radii - 1);
+    const int cell = state * tb.n_radii + ri;
+    // (the mask ids of ALL vertex variants of the cell, one per lane, are
+    // fetched together with the two variant maps instead of after them: one
+    // dependent global load less per image)
+    const int n_var = tb.n_xvar * tb.n_yvar;
+    int cand = 0;
+    if (n_var <= 32 && lane < n_var) cand = tb.mask_index[(int64_t)cell * n_var + lane];
+    const int xv = tb.xvar[(int64_t)cell * W + min(max(sw, 0), W - 1)];
+    const int yv = tb.yvar[(int64_t)cell * H + min(max(sh, 0), H - 1)];
+    if (n_var <= 32) g.id = __shfl_sync(0xffffffffu, cand, xv * tb.n_yvar + yv);
+    else g.id = tb.mask_index[((int64_t)cell * tb.n_xvar + xv) * tb.n_yvar + yv];
+    // A quantised shift can push the polygon up to q-1 pixels over the image
+    // edge (Pillow clips it there): clear the mask bits whose pixel lies
+    // outside the image, so "inside the mask" implies "inside the image".
+    const int lo = max(0, kMaskCentre - sh), hi = min(63, H - 1 + kMaskCentre - sh);
+    uint64_t rows = 0;
+    if (hi >= lo) rows = (hi - lo == 63 ? ~0ull : ((1ull << (hi - lo + 1)) - 1ull)) << lo;
+    g.rows_lo = (uint32_t)rows; g.rows_hi = (uint32_t)(rows >> 32);
+  }
+  return g;
+}
 
 // (10 CTAs = 40 images per SM at 48 registers: the rotation gather keeps more
 // shared-memory loads in flight than at 40 registers / 12 CTAs, and 16 384
@@ -98,113 +244,25 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
   }
   for (int w = lane; w < 2 * kRotCols; w += 32) (&fmask[0][0])[w] = 0ull;
   if (lane < kMaskPad) { mask[-1 - lane] = 0ull; mask[kMaskRows + lane] = 0ull; }
+  // (static tables may be read ahead of the wait below)
+  const double thr0 = tb.has_scale && lane < tb.n_radii - 1 ? tb.r_thresholds[lane]
+                                                            : __longlong_as_double(0x7ff0000000000000ll);
   // launched with MDPP_LAUNCH_OVERLAP_PREVIOUS: everything above overlapped the
   // previous kernel of the stream (the step that produces `states`); wait for
   // it now.  Returns at once in an ordinary launch.
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  // ---- transform parameters (uniform over the warp) ------------------------
-  int state = (int)p.states[m];
-  state = min(max(state, 0), tb.n_states - 1);
-  int R, sw, sh, rot, flip;
-  if (p.params_in) {
-    const int32_t* q = p.params_in + m * 5;
-    R = q[0]; sw = q[1]; sh = q[2]; rot = q[3]; flip = q[4];
-  } else {
-    // draw order of the reference (:149-181, :251, :258-259); one Philox
-    // call per image: w0 scale, w1 / w2 shifts, w3 rotation + flip bits
-    // (n_images < 2^31, checked by the caller: 32-bit arithmetic; the usual
-    // shapes -- one or two sub-images, one step per launch -- divide nothing)
-    uint32_t e = (uint32_t)m, sub = 0;  // (step, env); sub-image `sub` of it
-    if (tb.n_sub_images == 2) { sub = e & 1u; e >>= 1; }
-    else if (tb.n_sub_images > 2) { sub = e % (uint32_t)tb.n_sub_images; e /= (uint32_t)tb.n_sub_images; }
-    uint32_t t_rel = 0;
-    if (e >= (uint32_t)p.n_envs) { t_rel = e / (uint32_t)p.n_envs; e -= t_rel * (uint32_t)p.n_envs; }
-    const uint32_t gid = (uint32_t)p.env_id_offset + e;
-    const uint64_t step = p.step_index + (uint64_t)t_rel +
-                          (p.step_index_dev ? *p.step_index_dev : 0ull);
-    U4 w = philox4x32_10(gid, (uint32_t)step, (uint32_t)(step >> 32),
-                         p.stream + 16u * sub, p.k0, p.k1);
-    R = tb.r_min;
-    if (tb.has_scale) {  // R = r_min + #{thresholds <= u}, one lane each
-      const double u = uniform32(w.x);
-      for (int base = 0; base < tb.n_radii - 1; base += 32) {
-        const int k = base + lane;
-        const bool le = k < tb.n_radii - 1 && tb.r_thresholds[k] <= u;
-        R += __popc(__ballot_sync(0xffffffffu, le));
-      }
-    }
-    sw = W / 2; sh = H / 2;
-    if (tb.has_shift) {  // integers(-m + 1, m), m = W/2 - R, then quantise
-      const int mw = W / 2 - R, mh = H / 2 - R;
-      const int aw = -mw + 1 + (int)__umulhi(w.y, (uint32_t)max(2 * mw - 1, 1));
-      const int ah = -mh + 1 + (int)__umulhi(w.z, (uint32_t)max(2 * mh - 1, 1));
-      const float inv_q = 1.0f / (float)tb.sh_quant;
-      sw += floor_div_small(aw, tb.sh_quant, inv_q) * tb.sh_quant;
-      sh += floor_div_small(ah, tb.sh_quant, inv_q) * tb.sh_quant;
-    }
-    rot = -1;
-    if (tb.has_rotate) {
-      rot = (int)__umulhi(w.w, 360u);
-      rot = floor_div_small(rot, tb.ro_quant, 1.0f / (float)tb.ro_quant) * tb.ro_quant;
-    }
-    flip = 0;
-    if (tb.has_flip && (w.w & 1u) == 0) flip = (w.w & 2u) == 0 ? 1 : 2;
-  }
-  if (lane == 0 && p.params_out) {
-    int32_t* q = p.params_out + m * 5;
-    q[0] = R; q[1] = sw; q[2] = sh; q[3] = rot; q[4] = flip;
-  }
-  // Final-image geometry of the box-local column bitmaps `fmask`: bit b of
-  // column c is final pixel (xbase + c, ybase + b), ybase a multiple of 4 so
-  // that a nibble of the bitmap is one aligned 4-byte word of the output.
-  int xbase, ybase, c_lo, c_hi, b_lo, b_hi;  // columns / bits that can be set
-  int a0 = 65536, a1 = 0, a2 = 0, a3 = 0, a4 = 65536, a5 = 0;
-  if (rot < 0) {
-    // unrotated: the mask itself, mirrored for the flips and shifted by s bits
-    const int y_off = flip == 2 ? H - 33 - sh : sh - kMaskCentre;
-    ybase = y_off & ~3;
-    const int s = y_off - ybase;
-    xbase = flip == 1 ? W - 33 - sw : sw - kMaskCentre;
-    c_lo = max(kMaskCentre - R - 2, 0); c_hi = min(kMaskCentre + R + 3, kMaskRows - 1);
-    b_lo = c_lo + s; b_hi = c_hi + s;
-  } else {
-    const int32_t* c = tb.rot_coeff + (rot >= 360 ? rot % 360 : rot) * 6;
-    a0 = c[0]; a1 = c[1]; a2 = c[2]; a3 = c[3]; a4 = c[4]; a5 = c[5];
-    // bounding box of the polygon (disc of radius R around the centre) in the
-    // FINAL image: forward-map the centre through the rotation and the flip
-    const float X = (float)sw * 65536.f - (float)a2, Y = (float)sh * 65536.f - (float)a5;
-    // (a bounding box with 3 pixels of slack: an approximate reciprocal will do)
-    const float inv_det = __frcp_rn((float)a0 * (float)a4 - (float)a1 * (float)a3);
-    float cx = ((float)a4 * X - (float)a1 * Y) * inv_det;
-    float cy = ((float)a0 * Y - (float)a3 * X) * inv_det;
-    if (flip == 1) cx = (float)(W - 1) - cx;
-    if (flip == 2) cy = (float)(H - 1) - cy;
-    const int bx0 = max((int)floorf(cx) - R - 3, 0);
-    const int bx1 = min(min((int)ceilf(cx) + R + 3, W - 1), bx0 + kRotCols - 1);
-    const int by0 = max((int)floorf(cy) - R - 3, 0) & ~3;
-    const int by1 = min(min((int)ceilf(cy) + R + 3, H - 1), by0 + 127);
-    xbase = bx0; ybase = by0;
-    c_lo = 0; c_hi = bx1 - bx0;  // may be negative: nothing to draw
-    b_lo = 0; b_hi = by1 - by0;
-  }
+  const ImageSetup g = image_setup(p, m, lane, thr0);
   __syncwarp();  // fmask is cleared
+  const int sw = g.sw, sh = g.sh, rot = g.rot, flip = g.flip;
+  const int xbase = g.xbase, ybase = g.ybase;
+  const int c_lo = g.c_lo, c_hi = g.c_hi, b_lo = g.b_lo, b_hi = g.b_hi;
   {
-    const int ri = min(max(R - tb.r_min, 0), tb.n_radii - 1);
-    const int cell = state * tb.n_radii + ri;
-    const int xv = tb.xvar[(int64_t)cell * W + min(max(sw, 0), W - 1)];
-    const int yv = tb.yvar[(int64_t)cell * H + min(max(sh, 0), H - 1)];
-    const int id = tb.mask_index[((int64_t)cell * tb.n_xvar + xv) * tb.n_yvar + yv];
-    // A quantised shift can push the polygon up to q-1 pixels over the image
-    // edge (Pillow clips it there): clear the mask bits whose pixel lies
-    // outside the image, so "inside the mask" implies "inside the image".
-    const int lo = max(0, kMaskCentre - sh), hi = min(63, H - 1 + kMaskCentre - sh);
-    uint64_t rows = 0;
-    if (hi >= lo) rows = (hi - lo == 63 ? ~0ull : ((1ull << (hi - lo + 1)) - 1ull)) << lo;
+    const uint64_t rows = ((uint64_t)g.rows_hi << 32) | g.rows_lo;
     const int s = (flip == 2 ? H - 33 - sh : sh - kMaskCentre) & 3;
 #pragma unroll
     for (int mc = lane; mc < kMaskRows; mc += 32) {
-      uint64_t col = tb.mask_bits[(int64_t)id * kMaskRows + mc] & rows;
+      uint64_t col = tb.mask_bits[(int64_t)g.id * kMaskRows + mc] & rows;
       if ((unsigned)(mc + sw - kMaskCentre) >= (unsigned)W) col = 0;
       if (rot >= 0) {
         mask[mc] = col;  // source of the rotation gather below
@@ -228,28 +286,18 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
     constexpr int kSeg = 16;
     uint16_t* slots = reinterpret_cast<uint16_t*>(&fmask[0][0]);
     const int segs = (nrows + kSeg - 1) / kSeg;  // slots past it stay zero (cleared above)
-    const int m_lo = kMaskCentre - R - 2, m_hi = kMaskCentre + R + 3;  // set mask bits
-    const int sy = flip == 2 ? -1 : 1;                      // d(fy) / d(y)
-    const int dX = a1 * sy, dY = a4 * sy;
+    const int m_lo = kMaskCentre - g.R - 2, m_hi = kMaskCentre + g.R + 3;  // set mask bits
+    const int dX = g.dX, dY = g.dY;
     const float inv_segs = 1.0f / (float)segs;
-    // 16.16 source coordinates, pre-shifted into mask space (mx = X >> 16,
-    // my = Y >> 16), as linear forms of the box-local (column c, row k):
-    //   X = X00 + c cX + k dX,  Y = Y00 + c cY + k dY
     // Mask bits outside the image were cleared at load, so the image-bounds
     // test of the rotation is implied by the mask lookup.
-    const int sx = flip == 1 ? -1 : 1;
-    const int fx0 = flip == 1 ? W - 1 - xbase : xbase;
-    const int fy0 = flip == 2 ? H - 1 - ybase : ybase;
-    const int cX = a0 * sx, cY = a3 * sx;
-    const int X00 = a2 + a1 * fy0 + a0 * fx0 + (kMaskCentre - sw) * 65536;
-    const int Y00 = a5 + a4 * fy0 + a3 * fx0 + (kMaskCentre - sh) * 65536;
     for (int w = lane; w < ncols * segs; w += 32) {
       // (w + 0.5) / segs is at least 0.5 / segs away from an integer: exact
       const int c = (int)(((float)w + 0.5f) * inv_segs);
       const int sgm = w - c * segs;
       const int k0 = sgm * kSeg;                            // box-local rows
-      int X = X00 + c * cX + k0 * dX;
-      int Y = Y00 + c * cY + k0 * dY;
+      int X = g.X00 + c * g.cX + k0 * dX;
+      int Y = g.Y00 + c * g.cY + k0 * dY;
       // the 16 samples lie on a segment: if both ends are on the same outer
       // side of the polygon's mask box, none of them can hit a set bit
       const int mxa = X >> 16, mxb = (X + (kSeg - 1) * dX) >> 16;
@@ -292,25 +340,23 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
     // so the nibble test is also the bounds test.
     const uint8_t* fb = reinterpret_cast<const uint8_t*>(&fmask[0][0]);
     uint8_t* obase = out + ((int64_t)xbase * H + ybase);
-    {
-      // 8 lanes per column (a byte of the bitmap = 8 rows = 2 words each), 4
-      // columns per pass; boxes taller than 64 rows take a second round.
-      // (Two lanes per column with 8 words each: same speed rotated, 25 %
-      // slower unrotated.)
-      const int sub = lane & 7;
-      for (int jb = (b_lo >> 3) + sub; jb <= min(b_hi >> 3, 15); jb += 8) {
-        const uint8_t* src = fb + jb;
-        uint8_t* dst = obase + 8 * jb;
-        for (int c = c_lo + (lane >> 3); c <= c_hi; c += 4) {
-          const uint32_t byte = src[c * 16];
-          if (byte) {
-            uint32_t* q = reinterpret_cast<uint32_t*>(dst + c * H);
-            const uint32_t lo = byte & 0xFu, hi = byte >> 4;
-            if (lo) __stcs(q, ((lo * 0x00204081u) & 0x01010101u) * 0xFFu);
-            // (rows past b_hi hold samples too, possibly below the image)
-            if (hi && 8 * jb + 4 <= b_hi)
-              __stcs(q + 1, ((hi * 0x00204081u) & 0x01010101u) * 0xFFu);
-          }
+    // 8 lanes per column (a byte of the bitmap = 8 rows = 2 words each), 4
+    // columns per pass; boxes taller than 64 rows take a second round.
+    // (Two lanes per column with 8 words each: same speed rotated, 25 %
+    // slower unrotated.)
+    const int sub = lane & 7;
+    for (int jb = (b_lo >> 3) + sub; jb <= min(b_hi >> 3, 15); jb += 8) {
+      const uint8_t* src = fb + jb;
+      uint8_t* dst = obase + 8 * jb;
+      for (int c = c_lo + (lane >> 3); c <= c_hi; c += 4) {
+        const uint32_t byte = src[c * 16];
+        if (byte) {
+          uint32_t* q = reinterpret_cast<uint32_t*>(dst + c * H);
+          const uint32_t lo = byte & 0xFu, hi = byte >> 4;
+          if (lo) __stcs(q, ((lo * 0x00204081u) & 0x01010101u) * 0xFFu);
+          // (rows past b_hi hold samples too, possibly below the image)
+          if (hi && 8 * jb + 4 <= b_hi)
+            __stcs(q + 1, ((hi * 0x00204081u) & 0x01010101u) * 0xFFu);
         }
       }
     }
