@@ -204,7 +204,9 @@ __device__ __forceinline__ ImageSetup image_setup(const RenderDParams& p, int64_
 // (10 CTAs = 40 images per SM at 48 registers: the rotation gather keeps more
 // shared-memory loads in flight than at 40 registers / 12 CTAs, and 16 384
 // images are 2.8 instead of 2.3 waves: 43.0 -> 40.4 us rotated, 33.4 -> 31.2
-// us unrotated; 8 CTAs at 59 registers: 39.9 / 32.6 us.)
+// us unrotated; 8 CTAs at 59 registers: 39.9 / 32.6 us.  Two warps or one per
+// CTA instead of four, so that a slow image does not hold its neighbours'
+// slots: 39.7 / 39.5 us rotated, i.e. within 1-2 %.)
 template <int V>  // experiment switches (MDPP_RENDER_VARIANT); none at present
 __global__ void __launch_bounds__(kRBlock, 10)
 render_discrete_kernel(const __grid_constant__ RenderDParams p) {
