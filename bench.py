@@ -756,6 +756,11 @@ def run_gpu_arm(args):
         barrier()
     probe["bytes_per_env_step"] = 22
     probe["e2e_ceiling_env_steps_per_s"] = probe["both_gbs_all_ranks"] * 1e9 / 22
+    # the job ends with its slowest rank (max over ranks), and 18 of the 22
+    # bytes of an env-step travel device -> host: what the slowest rank's D2H
+    # rate allows, all ranks copying at once
+    probe["e2e_ceiling_slowest_rank_d2h"] = world * probe["d2h_gbs_per_rank_min"] * 1e9 / 18
+    probe["e2e_frac_of_slowest_rank_d2h"] = e2e_value / probe["e2e_ceiling_slowest_rank_d2h"]
     probe["what"] = ("pinned 256 MiB copies, every rank at once; 'both' = H2D and "
                      "D2H on two streams (sum of directions)")
     del hb, db
