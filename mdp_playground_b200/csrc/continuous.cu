@@ -146,6 +146,7 @@ static int fill_params(mdpp_ctx* ctx, const mdpp_continuous_state* st,
   p->k0 = (uint32_t)opts->seed;
   p->k1 = (uint32_t)(opts->seed >> 32);
   philox_round_keys(p->k0, p->k1, p->rk);
+  p->zig = ctx->d_zig;
   p->step_index = opts->step_index;
   p->step_index_dev = opts->step_index_dev;
   p->env_id_offset = opts->env_id_offset;

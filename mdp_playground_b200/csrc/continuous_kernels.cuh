@@ -26,6 +26,7 @@
 #pragma once
 #include "device_types.h"
 #include "philox.cuh"
+#include "ziggurat.cuh"
 
 namespace mdpp {
 
@@ -37,7 +38,8 @@ struct ContinuousParams {
   mdpp_continuous_state st;
   mdpp_continuous_io io;
   int32_t T, autoreset, horizon, noise_mode;
-  int32_t normal_mode, reserved0;  // MDPP_NORMAL_*: Box-Muller in fp64 or on the SFU
+  int32_t normal_mode, reserved0;  // MDPP_NORMAL_*: ziggurat / Box-Muller in fp64 / on the SFU
+  const uint8_t* zig;              // the context's ziggurat tables (ziggurat.cuh layout)
   uint32_t k0, k1;
   uint32_t rk[20];  // Philox round keys expanded from (k0, k1) by the host
   uint64_t step_index;
@@ -470,6 +472,13 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   const bool AUTORESET = MDPP_C_CONST(AUTORESET, p.autoreset != 0);
   const bool FAST = MDPP_C_CONST(FAST, false);
   const bool FAST_NORMAL = MDPP_C_CONST(NORMAL, p.normal_mode) == MDPP_NORMAL_FAST;
+  // numpy's Generator.normal algorithm (what the reference's noise calls run,
+  // rl_toy_env.py:1690 / :1982) on Philox words.  Opt-in for this kernel
+  // (normal_precision="ziggurat"): with 7 normals per step the direct draws
+  // below measured 5.6 ms against 4.3 ms with fp64 Box-Muller (1 M envs x 100
+  // steps, D = 6) -- twice the Philox calls and an out-of-line slow path; the
+  // staged design of the discrete rollout kernel has not been ported here
+  const bool ZIG_NORMAL = MDPP_C_CONST(NORMAL, p.normal_mode) == MDPP_NORMAL_ZIGGURAT;
   const bool active = sel.active;
   const int64_t env = sel.env;
   const uint32_t gid = sel.gid;
@@ -633,6 +642,35 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
 #pragma unroll
         for (int d = 0; d < MDPP_MAX_DIM; ++d)
           if (d < D) nz[d] = p.io.replay_state_noise[row * D + d];
+      } else if (ZIG_NORMAL) {
+        // one 64-bit word per normal: dimensions (2c, 2c + 1) share a call;
+        // the 1.5 % of first attempts that are rejected go through ONE
+        // out-of-line call site afterwards
+        const uint4* kw = reinterpret_cast<const uint4*>(p.zig + kZigOffFast);
+        uint32_t rej = 0;
+#pragma unroll
+        for (int c = 0; c < MDPP_MAX_DIM / 2; ++c)
+          if (2 * c < D) {
+            const U4 w = philox4x32_10_rk(gid, (uint32_t)step, (uint32_t)(step >> 32),
+                                          STREAM_STATE_NOISE + (uint32_t)c, p.rk);
+            bool ok0, ok1 = true;
+            nz[2 * c] = zig_first(w.x, w.y, kw, &ok0);
+            if (2 * c + 1 < D) nz[2 * c + 1] = zig_first(w.z, w.w, kw, &ok1);
+            if (!ok0) rej |= 1u << (2 * c);
+            if (!ok1) rej |= 2u << (2 * c);
+          }
+#pragma unroll 1
+        while (rej) {
+          const int jb = __ffs((int)rej) - 1;
+          rej &= rej - 1;
+          const double zz = zig_resolve_draw(gid, step, (uint32_t)jb, p.rk, p.zig);
+#pragma unroll
+          for (int d = 0; d < MDPP_MAX_DIM; ++d)
+            if (d < D && d == jb) nz[d] = zz;
+        }
+#pragma unroll
+        for (int d = 0; d < MDPP_MAX_DIM; ++d)
+          if (d < D) nz[d] = __dmul_rn(p_std, nz[d]);  // numpy: 0 + sigma * z
       } else {
 #pragma unroll
         for (int c = 0; c < MDPP_MAX_DIM / 4; ++c)
@@ -750,7 +788,11 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
         U4 w = philox4x32_10_rk(gid, (uint32_t)step, (uint32_t)(step >> 32),
                                 STREAM_NORMAL, p.rk);
         double z0, z1;
-        if (FAST_NORMAL) normal_pair_fast(w.x, w.y, &z0, &z1);
+        if (ZIG_NORMAL) {
+          bool ok;
+          z0 = zig_first(w.x, w.y, reinterpret_cast<const uint4*>(p.zig + kZigOffFast), &ok);
+          if (!ok) z0 = zig_resolve_draw(gid, step, kZigDrawReward, p.rk, p.zig);
+        } else if (FAST_NORMAL) normal_pair_fast(w.x, w.y, &z0, &z1);
         else normal_pair_f64(w.x, w.y, &z0, &z1);
         nrw = __dmul_rn(r_std, z0);
       }

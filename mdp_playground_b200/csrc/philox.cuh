@@ -33,6 +33,14 @@ enum PhiloxStream : uint32_t {
   STREAM_RESET_BOX = 64,   // + attempt*16 + dim/4 (continuous reset sampling)
   STREAM_ZIG_RETRY = 0x100,  // + c, counter = step: ziggurat words after a
                              // rejected first attempt (ziggurat.cuh)
+  // ziggurat normals of the continuous and grid kernels: the first word of
+  // state-noise dimensions (2c, 2c+1) = (w0,w1) / (w2,w3) of STREAM_STATE_NOISE
+  // + c, of the continuous reward normal = (w0,w1) of STREAM_NORMAL (counter =
+  // step); of the grid reward normal = the STREAM_GRID_ZIG word pair of the
+  // step's parity (counter = step >> 1).  Retries of draw j of a step (j =
+  // dimension, 16 = continuous reward, 17 = grid reward): + 64 j + c
+  STREAM_GRID_ZIG = 44,
+  STREAM_ZIG_DRAW_RETRY = 0x1000,
 };
 
 struct U4 { uint32_t x, y, z, w; };

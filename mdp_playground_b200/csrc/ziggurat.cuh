@@ -65,28 +65,20 @@ __device__ __forceinline__ double zig_u53(uint64_t w) {  // numpy next_double
   return (double)(w >> 11) * (1.0 / 9007199254740992.0);
 }
 
-// Everything after a rejected first attempt of (env gid, step).  Out of line:
-// 1.5 % of the draws get here.  `zig` -> a copy of the context's ziggurat
-// buffer (kZigBytes: the rollout kernels stage all of it in shared memory).
-static __device__ __noinline__ double zig_slow(uint32_t gid, uint64_t step,
-                                        const uint32_t* rk, const uint8_t* zig) {
+// Everything after a rejected first attempt hi:lo, numpy's loop verbatim.
+// Fresh words q_0, q_1, ...: (q_2c, q_2c+1) = Philox(gid, s0, s1, retry_stream + c).
+__device__ __forceinline__ double zig_resolve_body(uint32_t lo, uint32_t hi, uint32_t gid,
+                                                   uint32_t s0, uint32_t s1,
+                                                   uint32_t retry_stream,
+                                                   const uint32_t* rk, const uint8_t* zig) {
   const uint4* kw = reinterpret_cast<const uint4*>(zig + kZigOffFast);
   const double* fi = reinterpret_cast<const double*>(zig + kZigOffFi);
-  const uint32_t s0 = (uint32_t)step, s1 = (uint32_t)(step >> 32);
-  uint32_t lo, hi;
-  {
-    const uint64_t pair = step >> 1;
-    const U4 w = philox4x32_10_rk(gid, (uint32_t)pair, (uint32_t)(pair >> 32),
-                                  STREAM_ZIG, rk);
-    lo = (step & 1) ? w.z : w.x;
-    hi = (step & 1) ? w.w : w.y;
-  }
   uint32_t call = 0;
   bool have = false;
   U4 q = {0, 0, 0, 0};
   auto next_word = [&]() -> uint64_t {
     if (!have) {
-      q = philox4x32_10_rk(gid, s0, s1, STREAM_ZIG_RETRY + call, rk);
+      q = philox4x32_10_rk(gid, s0, s1, retry_stream + call, rk);
       ++call;
       have = true;
       return ((uint64_t)q.y << 32) | q.x;
@@ -122,6 +114,54 @@ static __device__ __noinline__ double zig_slow(uint32_t gid, uint64_t step,
     lo = (uint32_t)r;
     hi = (uint32_t)(r >> 32);
   }
+}
+
+// Everything after a rejected first attempt of (env gid, step) of the discrete
+// rollout's reward normal.  Out of line: 1.5 % of the draws get here.  `zig`
+// -> a copy of the context's ziggurat buffer (kZigBytes: the rollout kernels
+// stage all of it in shared memory).
+static __device__ __noinline__ double zig_slow(uint32_t gid, uint64_t step,
+                                        const uint32_t* rk, const uint8_t* zig) {
+  const uint32_t s0 = (uint32_t)step, s1 = (uint32_t)(step >> 32);
+  const uint64_t pair = step >> 1;
+  const U4 w = philox4x32_10_rk(gid, (uint32_t)pair, (uint32_t)(pair >> 32),
+                                STREAM_ZIG, rk);
+  return zig_resolve_body((step & 1) ? w.z : w.x, (step & 1) ? w.w : w.y, gid, s0, s1,
+                          STREAM_ZIG_RETRY, rk, zig);
+}
+
+// Kernels with several normals per (env, step) -- the continuous transition
+// noise, the continuous and grid reward noise.  Draw j of a step: j < 16 =
+// state-noise dimension j, first word = (w0,w1) / (w2,w3) of
+// Philox(env, step, STREAM_STATE_NOISE + j / 2) for even / odd j; 16 = the
+// continuous reward normal, (w0,w1) of Philox(env, step, STREAM_NORMAL); 17 =
+// the grid reward normal, the word pair of the step's parity of
+// Philox(env, step >> 1, STREAM_GRID_ZIG).  After a rejected first attempt the
+// draw continues on the words of STREAM_ZIG_DRAW_RETRY + 64 j + c.
+constexpr uint32_t kZigDrawReward = 16, kZigDrawGridReward = 17;
+
+// The rejected draw `draw` of (env gid, step), from scratch (the first word is
+// recomputed: the call site passes three scalars and keeps nothing else alive
+// for it).  Out of line: 1.5 % of the draws.  `zig` -> the context's buffer.
+static __device__ __noinline__ double zig_resolve_draw(uint32_t gid, uint64_t step,
+                                                       uint32_t draw, const uint32_t* rk,
+                                                       const uint8_t* zig) {
+  const uint32_t s0 = (uint32_t)step, s1 = (uint32_t)(step >> 32);
+  U4 w;
+  bool second;
+  if (draw == kZigDrawGridReward) {
+    const uint64_t pair = step >> 1;
+    w = philox4x32_10_rk(gid, (uint32_t)pair, (uint32_t)(pair >> 32), STREAM_GRID_ZIG, rk);
+    second = step & 1;
+  } else if (draw == kZigDrawReward) {
+    w = philox4x32_10_rk(gid, s0, s1, STREAM_NORMAL, rk);
+    second = false;
+  } else {
+    w = philox4x32_10_rk(gid, s0, s1, STREAM_STATE_NOISE + (draw >> 1), rk);
+    second = draw & 1;
+  }
+  return zig_resolve_body(second ? w.z : w.x, second ? w.w : w.y, gid, s0, s1,
+                          STREAM_ZIG_DRAW_RETRY + 64u * draw, rk, zig);
 }
 
 }  // namespace mdpp

@@ -79,15 +79,15 @@ class VectorRLToyEnv:
         self.autoreset = bool(autoreset)
         self.horizon = int(horizon)
         self.env_id_offset = int(env_id_offset)
-        # reward-noise normals of the Philox mode: "fp64" (default) = numpy's
-        # 256-layer ziggurat in fp64 on Philox words (discrete kernels; the
-        # continuous / grid kernels run fp64 Box-Muller), "boxmuller" = fp64
-        # Box-Muller everywhere, "fast" = fp32 Box-Muller on the SFU
-        assert normal_precision in ("fp64", "boxmuller", "fast")
+        # noise normals of the Philox mode (reward noise; the continuous
+        # transition noise): "ziggurat" = numpy's 256-layer ziggurat in fp64 on
+        # Philox words -- the algorithm behind the reference's np_random.normal
+        # calls --, "boxmuller" = fp64 Box-Muller, "fast" = fp32 Box-Muller on
+        # the SFU; "fp64" (default) = the faster of the two fp64 generators
+        # for the kernel: ziggurat for discrete envs (staged a window ahead in
+        # shared memory), Box-Muller for continuous / grid envs
+        assert normal_precision in ("fp64", "ziggurat", "boxmuller", "fast")
         self.normal_precision = normal_precision
-        self.normal_mode = {"fast": _lib.MDPP_NORMAL_FAST,
-                            "boxmuller": _lib.MDPP_NORMAL_F64,
-                            "fp64": _lib.MDPP_NORMAL_ZIGGURAT}[normal_precision]
         # the state history behind get_augmented_state() costs one extra
         # store per step; on by default for gym-style (non-autoreset) use
         self.track_history = (not self.autoreset) if track_history is None \
@@ -112,6 +112,11 @@ class VectorRLToyEnv:
             self.spec = parse_config(config)
             self._group_specs = [self.spec]
             self._group_sizes = [self.num_envs]
+        self.normal_mode = {
+            "fast": _lib.MDPP_NORMAL_FAST, "boxmuller": _lib.MDPP_NORMAL_F64,
+            "ziggurat": _lib.MDPP_NORMAL_ZIGGURAT,
+            "fp64": _lib.MDPP_NORMAL_ZIGGURAT if self.spec.kind == "discrete"
+            else _lib.MDPP_NORMAL_F64}[normal_precision]
         self.config = self.spec.config
         self.seed_dict = self.spec.seed_dict
         if philox_seed is None:

@@ -10,6 +10,7 @@ import numpy as np
 STREAM_STEP, STREAM_RESET, STREAM_ACTION, STREAM_IMAGE = 0, 1, 2, 3
 STREAM_NORMAL, STREAM_AUTORESET = 4, 5
 STREAM_ZIG, STREAM_ZIG_RETRY = 6, 0x100
+STREAM_GRID_ZIG, STREAM_ZIG_DRAW_RETRY = 44, 0x1000
 STREAM_STATE_NOISE, STREAM_RESET_BOX = 8, 64
 STREAM_IRR_STEP, STREAM_IRR_AUTORESET = 32, 33
 
@@ -118,6 +119,24 @@ def ziggurat_normal(seed, env_ids, step):
     def retry(i, k):
         q = philox4x32_10(env_ids[i:i + 1], step & 0xFFFFFFFF,
                           (step >> 32) & 0xFFFFFFFF, STREAM_ZIG_RETRY + (k >> 1), seed)
+        a, b = (q[2], q[3]) if k & 1 else (q[0], q[1])
+        return (int(b[0]) << 32) | int(a[0])
+    return zg.standard_normal_counter(main, retry)
+
+
+def ziggurat_draw(seed, env_ids, lo, hi, step, draw):
+    """N(0,1) from the first 64-bit words hi:lo (uint32 arrays, one per env) by
+    csrc/ziggurat.cuh's zig_resolve_draw: draw `draw` of global step `step` continues,
+    after a rejected first attempt, on the words (q_2c, q_2c+1) =
+    Philox(env, step, STREAM_ZIG_DRAW_RETRY + 64 draw + c)."""
+    from . import ziggurat as zg
+    step = int(step)
+    env_ids = np.asarray(env_ids, dtype=np.uint32)
+    main = (np.asarray(hi).astype(np.uint64) << np.uint64(32)) | np.asarray(lo).astype(np.uint64)
+
+    def retry(i, k):
+        q = philox4x32_10(env_ids[i:i + 1], step & 0xFFFFFFFF, (step >> 32) & 0xFFFFFFFF,
+                          STREAM_ZIG_DRAW_RETRY + 64 * int(draw) + (k >> 1), seed)
         a, b = (q[2], q[3]) if k & 1 else (q[0], q[1])
         return (int(b[0]) << 32) | int(a[0])
     return zg.standard_normal_counter(main, retry)

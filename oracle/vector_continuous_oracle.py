@@ -18,9 +18,14 @@ from . import philox as px
 
 class VectorContinuousOracle:
     def __init__(self, scalar_env, num_envs, autoreset=False, horizon=0,
-                 seed=0, env_id_offset=0, fast_normal=False):
+                 seed=0, env_id_offset=0, fast_normal=False, normal="boxmuller"):
         e = scalar_env
         assert e.kind == "continuous"
+        # noise normals: "boxmuller" (fp64, what normal_precision="fp64" runs
+        # in this kernel), "ziggurat" or, with fast_normal, the fp32 SFU
+        # restatement
+        self.normal = "fast" if fast_normal else normal
+        assert self.normal in ("ziggurat", "boxmuller", "fast")
         self._pair = px.normal_pair_fast if fast_normal else px.normal_pair_f64
         self.e = e
         self.N, self.D = int(num_envs), e.state_space_dim
@@ -182,7 +187,15 @@ class VectorContinuousOracle:
                     nz = np.asarray(replay["state_noise"][t], dtype=np.float64)
                 else:
                     nz = np.zeros((N, D))
-                    for c in range((D + 3) // 4):
+                    for c in range((D + 1) // 2 if self.normal == "ziggurat" else 0):
+                        w = px.step_words(self.seed, self.gid, step,
+                                          px.STREAM_STATE_NOISE + c)
+                        nz[:, 2 * c] = e.transition_noise * px.ziggurat_draw(
+                            self.seed, self.gid, w[0], w[1], step, 2 * c)
+                        if 2 * c + 1 < D:
+                            nz[:, 2 * c + 1] = e.transition_noise * px.ziggurat_draw(
+                                self.seed, self.gid, w[2], w[3], step, 2 * c + 1)
+                    for c in range(0 if self.normal == "ziggurat" else (D + 3) // 4):
                         w = px.step_words(self.seed, self.gid, step,
                                           px.STREAM_STATE_NOISE + c)
                         z01 = self._pair(w[0], w[1])
@@ -250,7 +263,11 @@ class VectorContinuousOracle:
                     nrw = np.asarray(replay["reward_noise"][t], dtype=np.float64)
                 else:
                     w = px.step_words(self.seed, self.gid, step, px.STREAM_NORMAL)
-                    nrw = e.reward_noise_std * self._pair(w[0], w[1])[0]
+                    if self.normal == "ziggurat":
+                        nrw = e.reward_noise_std * px.ziggurat_draw(
+                            self.seed, self.gid, w[0], w[1], step, 16)
+                    else:
+                        nrw = e.reward_noise_std * self._pair(w[0], w[1])[0]
             else:
                 nrw = np.zeros(N)
             done = self._in_box(nxt) | self.reached

@@ -14,7 +14,7 @@ import numpy as np
 from . import philox as px
 
 STREAM_GRID_STEP, STREAM_GRID_AUTORESET, STREAM_GRID_RESET = 40, 41, 42
-STREAM_GRID_NORMAL = 43
+STREAM_GRID_NORMAL, STREAM_GRID_ZIG = 43, 44
 
 
 def substitute_action(w, a):
@@ -36,9 +36,14 @@ def substitute_action(w, a):
 
 class VectorGridOracle:
     def __init__(self, scalar_env, num_envs, autoreset=False, horizon=0, seed=0,
-                 env_id_offset=0, fast_normal=False):
+                 env_id_offset=0, fast_normal=False, normal="boxmuller"):
         e = scalar_env
         assert e.kind == "grid"
+        # reward normals: "boxmuller" (fp64, what normal_precision="fp64" runs
+        # in this kernel), "ziggurat" or, with fast_normal, the fp32 SFU
+        # restatement
+        self.normal = "fast" if fast_normal else normal
+        assert self.normal in ("ziggurat", "boxmuller", "fast")
         self.N = int(num_envs)
         self.shape = [int(n) for n in e.grid_shape]
         self.nd = len(self.shape)
@@ -97,7 +102,11 @@ class VectorGridOracle:
             wp = px.step_words(self.seed, self.gid, step >> 1, STREAM_GRID_STEP)
             w = (wp[2], wp[3]) if step & 1 else (wp[0], wp[1])
             z0 = None
-            if self.has_rnoise:
+            if self.has_rnoise and self.normal == "ziggurat":
+                wz = px.step_words(self.seed, self.gid, step >> 1, STREAM_GRID_ZIG)
+                lo, hi = (wz[2], wz[3]) if step & 1 else (wz[0], wz[1])
+                z0 = px.ziggurat_draw(self.seed, self.gid, lo, hi, step, 17)
+            elif self.has_rnoise:
                 wn = px.step_words(self.seed, self.gid, step >> 2, STREAM_GRID_NORMAL)
                 pair = px.normal_pair_fast if self.fast_normal else px.normal_pair_f64
                 j = step & 3

@@ -133,6 +133,67 @@ def test_philox_rollout_matches_oracle(name, N, T, autoreset, horizon):
                                rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("jit", [True, False])
+def test_ziggurat_noise_matches_oracle(jit):
+    """normal_precision='ziggurat': numpy's Generator.normal algorithm on
+    Philox words for the transition and the reward noise of the continuous
+    kernels, against the oracle's restatement of the same streams; its draws
+    differ from the default's (fp64 Box-Muller in this kernel)."""
+    cfg = gu.case_config("cont_noise_delay")
+    N, T = 1500, 30
+    ora = VectorContinuousOracle(scalar_oracle(gu.case_config("cont_noise_delay")), N,
+                                 autoreset=True, horizon=15, seed=9,
+                                 env_id_offset=50, normal="ziggurat")
+    env = make_env(N, autoreset=True, horizon=15, philox_seed=9, env_id_offset=50,
+                   normal_precision="ziggurat", **cfg)
+    env.set_jit(jit)
+    ora.reset()
+    D = cfg["state_space_dim"]
+    amax = cfg.get("action_space_max", 1.0)
+    acts = np.random.default_rng(2).uniform(-amax, amax, size=(T, N, D)).astype(np.float32)
+    want = ora.rollout(T, acts)
+    got = env.rollout(T, torch.as_tensor(acts))
+    assert env.jit_last_used == jit
+    for k in ("terminated", "truncated"):
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+    np.testing.assert_allclose(got["obs"].cpu().numpy(), want["obs"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(got["reward"].cpu().numpy(), want["reward"],
+                               rtol=1e-4, atol=1e-5)
+    dflt = make_env(N, autoreset=True, horizon=15, philox_seed=9, env_id_offset=50, **cfg)
+    other = dflt.rollout(T, torch.as_tensor(acts))
+    assert not torch.equal(other["obs"], got["obs"])
+
+
+def test_continuous_ziggurat_noise_is_standard_normal():
+    """normal_precision='ziggurat' on the continuous kernels (numpy's
+    ziggurat on Philox words): with zero actions the integrated state
+    stays where reset() put it (the noise is added to the emitted state only,
+    rl_toy_env.py:1683-1700), so obs - initial obs = the noise of that step;
+    the per-dimension draws pass a KS test against N(0, sigma) and are
+    uncorrelated."""
+    from scipy import stats
+    cfg = dict(seed=0, state_space_type="continuous", state_space_dim=3,
+               transition_dynamics_order=1, inertia=1.0, time_unit=1.0,
+               target_point=[0.0, 0.0, 0.0], target_radius=1e-9,
+               state_space_max=1e6, action_space_max=1.0, transition_noise=0.5,
+               reward_noise=2.0, make_denser=True, reward_scale=1.0, dtype_s=np.float64)
+    N, T = 20000, 8
+    env = make_env(N, autoreset=False, philox_seed=3, normal_precision="ziggurat", **cfg)
+    acts = torch.zeros((T, N, 3), dtype=torch.float64, device="cuda")
+    obs0 = env.curr_obs.clone()
+    out = env.rollout(T, actions=acts)
+    prev = torch.cat([obs0[None], out["obs"][:-1]])
+    noise = (out["obs"] - obs0[None]).cpu().numpy().reshape(-1, 3)  # zero action: pure noise
+    for d in range(3):
+        assert stats.kstest(noise[:, d] / 0.5, "norm").pvalue > 1e-3, d
+    assert abs(np.corrcoef(noise.T)[0, 1]) < 0.01
+    # dense reward = distance moved towards the target + N(0, 2): the noise part
+    d_prev = np.linalg.norm(prev.cpu().numpy(), axis=-1)
+    d_new = np.linalg.norm(out["obs"].cpu().numpy(), axis=-1)
+    rn = out["reward"].cpu().numpy() - (d_prev - d_new)
+    assert stats.kstest(rn.reshape(-1) / 2.0, "norm").pvalue > 1e-3
+
+
 def test_fast_normal_noise_matches_oracle():
     """normal_precision='fast' (SFU Box-Muller) on the continuous path: the
     oracle restates the same fp32 Box-Muller; 1e-5 contract tolerance (the SFU

@@ -245,6 +245,40 @@ def test_philox_rollout_matches_oracle(name, N, T, autoreset, horizon):
 
 
 @pytest.mark.gpu
+def test_ziggurat_normal_matches_oracle_and_differs_from_the_default():
+    """normal_precision='ziggurat': numpy's Generator.normal algorithm on
+    Philox words for the grid reward noise (the default here is fp64
+    Box-Muller)."""
+    cfg = gu.case_config("grid_sparse_noise")
+    N, T = 1000, 24
+    ora = VectorGridOracle(scalar_oracle(gu.case_config("grid_sparse_noise")), N,
+                           autoreset=True, horizon=10, seed=5, normal="ziggurat")
+    env = make_env(N, autoreset=True, horizon=10, philox_seed=5,
+                   normal_precision="ziggurat", **cfg)
+    ora.reset()
+    acts = np.zeros((T, N, 2), dtype=np.int64)
+    acts[..., 1] = np.random.default_rng(1).integers(-1, 2, size=(T, N))
+    want, got = ora.rollout(T, acts), env.rollout(T, actions=acts)
+    for k in ("obs", "final_obs", "terminated", "truncated"):
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+    np.testing.assert_allclose(got["reward"].cpu().numpy(), want["reward"],
+                               rtol=1e-12, atol=1e-12)
+    dflt = make_env(N, autoreset=True, horizon=10, philox_seed=5, **cfg)
+    other = dflt.rollout(T, actions=acts)
+    assert np.array_equal(other["obs"].cpu().numpy(), want["obs"])   # same transitions
+    r = other["reward"].cpu().numpy()
+    assert not np.allclose(r, want["reward"])
+    from scipy import stats
+    # sparse reward: r = (1[at target] + N(0, 1)) * 2 + 0.5 (+ 2 * 2 once terminal)
+    z_zg = (want["reward"] - 0.5) / 2.0
+    z_bm = (r - 0.5) / 2.0
+    # the noise-free parts agree, so the difference of the two is a difference
+    # of two independent N(0, 1): variance 2
+    diff = (z_zg - z_bm).reshape(-1)
+    assert stats.kstest(diff / np.sqrt(2.0), "norm").pvalue > 1e-3
+
+
+@pytest.mark.gpu
 def test_fast_normal_matches_oracle_within_1e5():
     """normal_precision='fast' (SFU Box-Muller): cells exact, rewards within
     1e-5 absolute of the oracle's fp32 restatement."""

@@ -21,5 +21,6 @@ def timeit(N, T, cfg, reps=5, **kw):
 timeit(1 << 20, 100, cfg)
 timeit(1 << 20, 1, cfg, reps=20)
 timeit(1 << 20, 100, dict(cfg, transition_noise=0.05, reward_noise=0.1))
+timeit(1 << 20, 100, dict(cfg, transition_noise=0.05, reward_noise=0.1), normal_precision="boxmuller")
 timeit(1 << 20, 100, dict(cfg, transition_noise=0.05, reward_noise=0.1), normal_precision="fast")
 timeit(1 << 22, 50, cfg)
