@@ -212,6 +212,11 @@ __global__ void __launch_bounds__(kRBlock, 10)
 render_discrete_kernel(const __grid_constant__ RenderDParams p) {
   __shared__ uint64_t mask_s[kImagesPerCta][kMaskCols];    // polygon column bitmaps
   __shared__ uint64_t fmask_s[kImagesPerCta][kRotCols][2];  // ... of the final image
+  // The next kernel of the stream, when launched with programmatic stream
+  // serialisation (the next step kernel), may start its prologue now; it
+  // still waits for this grid to complete before touching the env state.
+  // (image step(): 45.7 -> 43.3 us rotated, 37.6 -> 36.3 us unrotated)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * kImagesPerCta + warp;
   if (m >= p.n_images) return;  // whole warp; only warp-level barriers below
