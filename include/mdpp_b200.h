@@ -191,14 +191,18 @@ typedef struct mdpp_discrete_io {
 #define MDPP_OBS_I32 1
 #define MDPP_OBS_U8 2
 
-/* How the Philox mode turns words into N(0,1) reward noise.                 */
+/* How the Philox mode turns words into N(0,1) noise (reward noise; the
+ * transition noise of continuous envs).                                     */
 #define MDPP_NORMAL_F64 0   /* Box-Muller in fp64 (log, sqrt, sincospi)      */
 #define MDPP_NORMAL_FAST 1  /* Box-Muller on the SFU in fp32 (~1e-6 rel.)    */
 #define MDPP_NORMAL_ZIGGURAT 2 /* fp64, numpy's 256-layer ziggurat (the
                                   algorithm behind Generator.normal, which the
-                                  reference calls at rl_toy_env.py:1982) on
-                                  Philox words; discrete kernels only, the
-                                  others treat it as MDPP_NORMAL_F64          */
+                                  reference calls at rl_toy_env.py:1683 and
+                                  :1982) on Philox words.  The fastest fp64
+                                  generator of the discrete kernels (staged in
+                                  shared memory); the continuous and grid
+                                  kernels run it too, but slower than
+                                  MDPP_NORMAL_F64 (direct draws)              */
 
 /* mdpp_render_discrete only: the launch may START before the previous kernel
  * of the stream has finished (programmatic dependent launch): its prologue --

@@ -473,7 +473,7 @@ __device__ __forceinline__ void continuous_body(const ContinuousParams& p) {
   const bool FAST = MDPP_C_CONST(FAST, false);
   const bool FAST_NORMAL = MDPP_C_CONST(NORMAL, p.normal_mode) == MDPP_NORMAL_FAST;
   // numpy's Generator.normal algorithm (what the reference's noise calls run,
-  // rl_toy_env.py:1690 / :1982) on Philox words.  Opt-in for this kernel
+  // rl_toy_env.py:413 via :1683, :403 via :1982) on Philox words.  Opt-in for this kernel
   // (normal_precision="ziggurat"): with 7 normals per step the direct draws
   // below measured 5.6 ms against 4.3 ms with fp64 Box-Muller (1 M envs x 100
   // steps, D = 6) -- twice the Philox calls and an out-of-line slow path; the
