@@ -293,7 +293,10 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
     constexpr int kSeg = 16;
     uint16_t* slots = reinterpret_cast<uint16_t*>(&fmask[0][0]);
     const int segs = (nrows + kSeg - 1) / kSeg;  // slots past it stay zero (cleared above)
-    const int m_lo = kMaskCentre - g.R - 2, m_hi = kMaskCentre + g.R + 3;  // set mask bits
+    // set mask bits (R clamped: replayed parameters are caller-supplied, and
+    // the padding of `mask` covers 15 columns beyond this box only)
+    const int Rc = min(max(g.R, 0), kMaskCentre - 1);
+    const int m_lo = kMaskCentre - Rc - 2, m_hi = kMaskCentre + Rc + 3;
     const int dX = g.dX, dY = g.dY;
     const float inv_segs = 1.0f / (float)segs;
     // Mask bits outside the image were cleared at load, so the image-bounds
