@@ -356,18 +356,19 @@ render_discrete_kernel(const __grid_constant__ RenderDParams p) {
     // slower unrotated.)
     const int sub = lane & 7;
     for (int jb = (b_lo >> 3) + sub; jb <= min(b_hi >> 3, 15); jb += 8) {
-      const uint8_t* src = fb + jb;
-      uint8_t* dst = obase + 8 * jb;
-      for (int c = c_lo + (lane >> 3); c <= c_hi; c += 4) {
-        const uint32_t byte = src[c * 16];
-        if (byte) {
-          uint32_t* q = reinterpret_cast<uint32_t*>(dst + c * H);
-          const uint32_t lo = byte & 0xFu, hi = byte >> 4;
-          if (lo) __stcs(q, ((lo * 0x00204081u) & 0x01010101u) * 0xFFu);
-          // (rows past b_hi hold samples too, possibly below the image)
-          if (hi && 8 * jb + 4 <= b_hi)
-            __stcs(q + 1, ((hi * 0x00204081u) & 0x01010101u) * 0xFFu);
-        }
+      // (rows past b_hi hold samples too, possibly below the image: the upper
+      // word of the last byte is dropped when it starts past b_hi)
+      const uint32_t keep = 8 * jb + 4 <= b_hi ? 0xFFu : 0x0Fu;
+      const int c0 = c_lo + (lane >> 3);
+      const uint8_t* src = fb + jb + c0 * 16;
+      uint32_t* q = reinterpret_cast<uint32_t*>(obase + 8 * jb + (int64_t)c0 * H);
+      // (no "byte != 0" branch around the two predicated stores, running
+      // pointers instead of per-column address arithmetic: 40.1 -> 39.1 us)
+      for (int c = c0; c <= c_hi; c += 4, src += 64, q += H) {
+        const uint32_t byte = *src & keep;
+        const uint32_t lo = byte & 0xFu, hi = byte >> 4;
+        if (lo) __stcs(q, ((lo * 0x00204081u) & 0x01010101u) * 0xFFu);
+        if (hi) __stcs(q + 1, ((hi * 0x00204081u) & 0x01010101u) * 0xFFu);
       }
     }
   } else {  // odd image sizes: one byte per lane and step
