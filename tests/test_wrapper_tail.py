@@ -127,3 +127,33 @@ def test_cuda_tail_philox_statistics():
     sh = img.last_shift.cpu().numpy()
     assert sh.min() == -5 and sh.max() == 5
     assert stats.chisquare(np.bincount(sh[:, 0] + 5, minlength=11)).pvalue > 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("side,pad,quant", [
+    (84, 20, 2),   # Atari frames: shared-memory kernel, word-wise tile load
+    (10, 5, 1),    # rows of 30 bytes: byte-wise tile load
+    (12, 7, 3),    # quantised shifts, even canvas
+    (300, 4, 2),   # tile larger than shared memory: the byte-wise kernel
+    (16, 1, 1),    # one pixel of padding: the only shift is 0
+])
+def test_cuda_image_shift_equals_the_oracle_for_every_kernel_path(side, pad, quant):
+    """Random images and the kernel's own (Philox) shifts against the CPU
+    restatement of get_transformed_image (gym_env_wrapper.py:523-618)."""
+    import torch
+    from mdp_playground_b200 import VectorGymEnvTail
+    from oracle.wrapper_tail import ScalarWrapperTail
+    N = 64 if side < 100 else 6
+    cfg = dict(state_space_type="discrete", image_transforms="shift",
+               image_padding=pad, image_sh_quant=quant)
+    tail = VectorGymEnvTail(N, seed=3, n_actions=4, image_side=side, **cfg)
+    ora = ScalarWrapperTail(n_actions=4, **cfg)
+    imgs = torch.randint(0, 256, (N, side, side, 3), dtype=torch.uint8, device="cuda",
+                         generator=torch.Generator("cuda").manual_seed(side))
+    got = tail.shift_images(imgs).cpu().numpy()
+    shifts = tail.last_shift.cpu().numpy()
+    lo, hi = ora.shift_draw_bounds(side)
+    assert shifts.min() >= lo and shifts.max() < hi
+    x = imgs.cpu().numpy()
+    for i in range(N):
+        assert np.array_equal(got[i], ora.shift_image(x[i], shifts[i])), i
