@@ -207,12 +207,11 @@ tail_image_shift_kernel(const __grid_constant__ TailParams p, const uint8_t* img
   }
 }
 
-// The same paste for even canvas sides, HBM-friendly: the env image goes into
-// shared memory with coalesced loads (rows padded to an odd byte stride: the
-// transposed reads below then hit 32 different banks), and every thread
-// assembles 4 consecutive pixels of the transposed canvas = 12 contiguous
-// output bytes, stored as three 32-bit words.  2.7x the byte-wise kernel above
-// at 84x84x3 -> 124x124x3.
+// The same paste for even canvas sides, HBM-friendly: the env image goes
+// TRANSPOSED into shared memory (coalesced global loads), and every thread
+// emits 4 consecutive pixels of the transposed canvas = 12 contiguous output
+// bytes, read from the tile as four aligned words and funnel-shifted, stored
+// as three 32-bit words.
 __device__ __forceinline__ void tail_shift_params(const TailParams& p, int64_t i,
                                                   const int32_t* replay_shift,
                                                   int32_t* shift_out, int* top, int* left) {
@@ -244,61 +243,122 @@ __device__ __forceinline__ void tail_shift_params(const TailParams& p, int64_t i
   *left = sw - side / 2;
 }
 
+// Bytes of the shared-memory tile: the env image TRANSPOSED, tile[col][4 + row][3]
+// with 4 zero rows before and after each column (an item that the image's first
+// or last row cuts through reads its zeros from there), an odd number of 32-bit
+// words per column (conflict-free in both phases) and 16 bytes of slack for the
+// 4-word reads of the last item.
+constexpr int kTailRowPad = 4;
+__host__ __device__ inline int tail_tile_col_bytes(int side) {
+  const int words = ((side + 2 * kTailRowPad) * 3 + 3) / 4;
+  return 4 * (words | 1);
+}
+__host__ __device__ inline size_t tail_tile_bytes(int side) {
+  return (size_t)side * tail_tile_col_bytes(side) + 16;
+}
+
 __global__ void __launch_bounds__(256)
 tail_image_shift_smem_kernel(const __grid_constant__ TailParams p, const uint8_t* img,
                              uint8_t* out, const int32_t* replay_shift,
                              int32_t* shift_out) {
-  extern __shared__ __align__(16) uint8_t tile[];  // [side][row_bytes | 1]
+  extern __shared__ __align__(16) uint8_t tile[];  // [col][4 + row][3], see above
   const int64_t i = blockIdx.x;
   const mdpp_tail_config& c = p.cfg;
-  const int side = c.image_side, tot = side + 2 * c.image_padding;
-  const int row_bytes = side * 3, stride = row_bytes | 1;
-  const uint8_t* src = img + i * (int64_t)side * row_bytes;
-  if ((row_bytes & 3) == 0 && ((side * row_bytes) & 3) == 0) {
-    const int words = row_bytes >> 2;
-    const float inv_words = 1.0f / (float)words;
-    const uint32_t* src4 = reinterpret_cast<const uint32_t*>(src);  // (16 B aligned rows)
-    for (int idx = threadIdx.x; idx < side * words; idx += blockDim.x) {
-      const int r = (int)(((float)idx + 0.5f) * inv_words);  // exact: see render.cu
-      const int w = idx - r * words;
-      const uint32_t v = __ldcs(src4 + idx);
-      uint8_t* d = tile + r * stride + 4 * w;
-      d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8);
-      d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24);
+  const int side = c.image_side, tot = side + 2 * c.image_padding;  // (side is even)
+  const int cstride = tail_tile_col_bytes(side);
+  const uint8_t* src = img + i * (int64_t)side * side * 3;
+  // the zero rows of every column
+  for (int k = threadIdx.x; k < side * 2 * kTailRowPad * 3; k += blockDim.x) {
+    const int col = k / (2 * kTailRowPad * 3), b = k - col * (2 * kTailRowPad * 3);
+    tile[col * cstride + (b < kTailRowPad * 3 ? b : b + side * 3)] = 0;
+  }
+  // phase 1: consecutive lanes read consecutive pixels and write them a column
+  // apart (an odd number of words: 32 different banks).  Sides that are a
+  // multiple of 4: four pixels = three aligned words per thread, two such
+  // groups in flight.
+  const float inv_side = 1.0f / (float)side;
+  if ((side & 3) == 0) {
+    const uint32_t* src4 = reinterpret_cast<const uint32_t*>(src);
+    const int groups = side * side / 4;
+    auto scatter = [&](int g, uint32_t a0, uint32_t a1, uint32_t a2) {
+      const int px = 4 * g;
+      const int r = (int)(((float)px + 0.5f) * inv_side);  // exact: see render.cu
+      const int col = px - r * side;                       // col .. col + 3: one row
+      uint8_t* d = tile + col * cstride + 3 * (r + kTailRowPad);
+      d[0] = (uint8_t)a0; d[1] = (uint8_t)(a0 >> 8); d[2] = (uint8_t)(a0 >> 16);
+      d += cstride;
+      d[0] = (uint8_t)(a0 >> 24); d[1] = (uint8_t)a1; d[2] = (uint8_t)(a1 >> 8);
+      d += cstride;
+      d[0] = (uint8_t)(a1 >> 16); d[1] = (uint8_t)(a1 >> 24); d[2] = (uint8_t)a2;
+      d += cstride;
+      d[0] = (uint8_t)(a2 >> 8); d[1] = (uint8_t)(a2 >> 16); d[2] = (uint8_t)(a2 >> 24);
+    };
+    int g = threadIdx.x;
+    for (; g + (int)blockDim.x < groups; g += 2 * blockDim.x) {
+      const int h = g + blockDim.x;
+      const uint32_t a0 = __ldcs(src4 + 3 * g), a1 = __ldcs(src4 + 3 * g + 1),
+                     a2 = __ldcs(src4 + 3 * g + 2);
+      const uint32_t b0 = __ldcs(src4 + 3 * h), b1 = __ldcs(src4 + 3 * h + 1),
+                     b2 = __ldcs(src4 + 3 * h + 2);
+      scatter(g, a0, a1, a2);
+      scatter(h, b0, b1, b2);
     }
+    if (g < groups)
+      scatter(g, __ldcs(src4 + 3 * g), __ldcs(src4 + 3 * g + 1), __ldcs(src4 + 3 * g + 2));
   } else {
-    const float inv_row = 1.0f / (float)row_bytes;
-    for (int idx = threadIdx.x; idx < side * row_bytes; idx += blockDim.x) {
-      const int r = (int)(((float)idx + 0.5f) * inv_row);
-      tile[r * stride + (idx - r * row_bytes)] = src[idx];
+    for (int px = threadIdx.x; px < side * side; px += blockDim.x) {
+      const int r = (int)(((float)px + 0.5f) * inv_side);
+      const int col = px - r * side;
+      const uint8_t* s3 = src + 3 * px;
+      const uint8_t v0 = __ldcs(s3), v1 = __ldcs(s3 + 1), v2 = __ldcs(s3 + 2);
+      uint8_t* d = tile + col * cstride + 3 * (r + kTailRowPad);
+      d[0] = v0; d[1] = v1; d[2] = v2;
     }
   }
   int top, left;
   tail_shift_params(p, i, replay_shift, shift_out, &top, &left);
-  const int half2 = 2 * (side / 2);  // rows / columns actually pasted
   __syncthreads();
+  // phase 2: 4 consecutive pixels of the transposed canvas per thread = 12
+  // contiguous output bytes = three 32-bit stores.  out[x][y] = canvas[y][x],
+  // flat pixel index e = x tot + y.
   uint32_t* dst = reinterpret_cast<uint32_t*>(out + i * (int64_t)tot * tot * 3);
   const float inv_tot = 1.0f / (float)tot;
   for (int e4 = threadIdx.x; e4 < tot * tot / 4; e4 += blockDim.x) {
-    const int e = 4 * e4;                 // out[x][y] = canvas[y][x], e = x tot + y
-    int x = (int)(((float)e + 0.5f) * inv_tot);
-    int y = e - x * tot;
-    uint32_t b[12];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int r = y - top, col = x - left;
-      uint32_t v0 = 0, v1 = 0, v2 = 0;
-      if ((unsigned)r < (unsigned)half2 && (unsigned)col < (unsigned)half2) {
-        const uint8_t* px = tile + r * stride + col * 3;
-        v0 = px[0]; v1 = px[1]; v2 = px[2];
+    const int e = 4 * e4;
+    const int x = (int)(((float)e + 0.5f) * inv_tot);
+    const int y = e - x * tot;
+    const int r = y - top, col = x - left;
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+    if (y + 3 < tot) {  // the four pixels share column x of the output
+      if ((unsigned)col < (unsigned)side && r + 3 >= 0 && r < side) {
+        // 12 contiguous tile bytes (zero rows included) at any alignment: four
+        // aligned words, funnel-shifted
+        const uint32_t a = (uint32_t)(col * cstride + 3 * (r + kTailRowPad));
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(tile + (a & ~3u));
+        const uint32_t sh = (a & 3u) * 8u;
+        const uint32_t t0 = q[0], t1 = q[1], t2 = q[2], t3 = q[3];
+        w0 = __funnelshift_r(t0, t1, sh);
+        w1 = __funnelshift_r(t1, t2, sh);
+        w2 = __funnelshift_r(t2, t3, sh);
       }
-      b[3 * k] = v0; b[3 * k + 1] = v1; b[3 * k + 2] = v2;
-      if (++y == tot) { y = 0; ++x; }
+    } else {  // (canvas sides that are not a multiple of 4: the item wraps)
+      uint32_t b[12];
+      int xx = x, yy = y;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int rr = yy - top, cc = xx - left;
+        const bool in = (unsigned)rr < (unsigned)side && (unsigned)cc < (unsigned)side;
+        const uint8_t* px = tile + (in ? cc * cstride + 3 * (rr + kTailRowPad) : 0);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) b[3 * k + ch] = in ? px[ch] : 0u;
+        if (++yy == tot) { yy = 0; ++xx; }
+      }
+      w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+      w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+      w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
     }
     uint32_t* o = dst + 3 * e4;
-    __stcs(o, b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24));
-    __stcs(o + 1, b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24));
-    __stcs(o + 2, b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24));
+    __stcs(o, w0); __stcs(o + 1, w1); __stcs(o + 2, w2);
   }
 }
 
@@ -393,8 +453,8 @@ extern "C" int mdpp_tail_image_shift(mdpp_ctx* ctx, const mdpp_tail_config* cfg,
     return fail(ctx, MDPP_EINVAL, "tail_image_shift: replay mode needs replay_shift");
   MDPP_CUDA(ctx, cudaSetDevice(ctx->device));
   const int tot = cfg->image_side + 2 * cfg->image_padding;
-  const size_t tile_bytes = (size_t)cfg->image_side * ((cfg->image_side * 3) | 1) + 16;
-  if (tot % 2 == 0 && tile_bytes <= (size_t)ctx->max_smem_optin - 1024 &&
+  const size_t tile_bytes = tail_tile_bytes(cfg->image_side);
+  if (cfg->image_side % 2 == 0 && tile_bytes <= (size_t)ctx->max_smem_optin - 1024 &&
       ((uintptr_t)img & 3) == 0 && ((uintptr_t)out & 3) == 0) {
     if (tile_bytes > 48 * 1024 - 512)
       MDPP_CUDA(ctx, cudaFuncSetAttribute(tail_image_shift_smem_kernel,
