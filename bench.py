@@ -420,7 +420,17 @@ def other_configs(torch, Env, dev, rank, world, barrier, max_over_ranks, peak,
         line("N3_wrapper_tail[mujoco-like: 17-dim fp32 observations]", Nm, 1, ms,
              17 * 4 * 2 + 17 + 16,
              "VectorGymEnvTail.post per step: observation noise, reward delay 1 + noise "
-             "(bytes: obs in + out, reward in + out, done, FIFO slot read + write)")
+             "(bytes: obs in + out, reward in + out, done, FIFO slot read + write); "
+             "fp64 Box-Muller normals (18 per env-step)")
+        del tail
+        tail = VectorGymEnvTail(Nm, device=dev, seed=0, env_id_offset=rank * Nm,
+                                obs_dim=17, state_space_type="continuous", delay=1,
+                                transition_noise=0.05, reward_noise=0.1,
+                                normal_precision="fast")
+        ms = _time_launches(torch, lambda: tail.post(obs, r, d), 20, barrier,
+                            max_over_ranks)
+        line("N3_wrapper_tail[mujoco-like, fast normals]", Nm, 1, ms, 17 * 4 * 2 + 17 + 16,
+             "the same with normal_precision='fast' (fp32 SFU Box-Muller)")
         del tail, obs, r, d
         # C3: continuous move_to_a_point, 1M envs
         N, T = 1 << 20, 100

@@ -12,11 +12,16 @@
 namespace mdpp {
 namespace {
 
+// Noise normals: Box-Muller on Philox words, in fp64 (MDPP_NORMAL_F64, the
+// default) or on the SFU in fp32 (MDPP_NORMAL_FAST).  (numpy's ziggurat was
+// tried here too: with one or two draws per thread, half of all warps run its
+// slow path for a single lane -- 346 instead of 230 instructions per pair.)
 enum : uint32_t {
   STREAM_TAIL_ACTION = 48,   // counter = (env, step): w0 decides / picks
   STREAM_TAIL_NORMAL = 49,   // (w0, w1) -> reward normal
   STREAM_TAIL_SHIFT = 50,    // w0, w1 -> the two shift integers
-  STREAM_TAIL_OBS = 52,      // + pair index: observation noise
+  STREAM_TAIL_OBS = 0x10000, // + pair index: (w0, w1) -> the normals of
+                             // dimensions 2 pair, 2 pair + 1
 };
 constexpr int kTBlock = 128;
 
@@ -24,8 +29,9 @@ struct TailParams {
   mdpp_tail_config cfg;
   mdpp_tail_state st;
   int64_t n;
-  int32_t noise_mode;
+  int32_t noise_mode, normal_mode;
   uint32_t k0, k1;
+  uint32_t rk[20];     // Philox round keys
   uint64_t step_index;
   int64_t env_id_offset;
 };
@@ -68,38 +74,48 @@ tail_actions_kernel(const __grid_constant__ TailParams p, const int32_t* actions
   applied[i] = a;
 }
 
+// Observation noise (:367-376, :405-406): next_obs += noise, a float64 draw
+// added into the observation's dtype.  One thread per (env, pair of
+// dimensions): consecutive threads touch consecutive elements.
 template <typename R>
 __global__ void __launch_bounds__(kTBlock)
-tail_post_kernel(const __grid_constant__ TailParams p, const R* obs, R* out_obs,
-                 const double* reward, const uint8_t* done, double* out_reward,
-                 const double* replay_rn, const double* replay_on) {
+tail_obs_kernel(const __grid_constant__ TailParams p, const R* obs, R* out_obs,
+                const double* replay_on) {
+  const mdpp_tail_config& c = p.cfg;
+  const int D = c.obs_dim, P = (D + 1) / 2;
+  const int64_t idx = (int64_t)blockIdx.x * kTBlock + threadIdx.x;
+  if (idx >= p.n * P) return;
+  const int64_t i = idx / P;
+  const int pr = (int)(idx - i * P), d0 = 2 * pr;
+  const bool two = d0 + 1 < D;
+  const int64_t at = i * D + d0;
+  double z0 = 0.0, z1 = 0.0;
+  if (c.has_transition_noise) {
+    if (p.noise_mode == MDPP_NOISE_REPLAY) {
+      z0 = replay_on[at];
+      if (two) z1 = replay_on[at + 1];
+    } else {
+      const uint32_t gid = (uint32_t)(p.env_id_offset + i);
+      const uint32_t s0 = (uint32_t)p.step_index, s1 = (uint32_t)(p.step_index >> 32);
+      const U4 w = philox4x32_10_rk(gid, s0, s1, STREAM_TAIL_OBS + (uint32_t)pr, p.rk);
+      if (p.normal_mode == MDPP_NORMAL_FAST) normal_pair_fast(w.x, w.y, &z0, &z1);
+      else normal_pair_f64(w.x, w.y, &z0, &z1);
+      z0 = __dmul_rn(c.transition_noise, z0);
+      z1 = __dmul_rn(c.transition_noise, z1);
+    }
+  }
+  out_obs[at] = (R)__dadd_rn((double)obs[at], z0);
+  if (two) out_obs[at + 1] = (R)__dadd_rn((double)obs[at + 1], z1);
+}
+
+__global__ void __launch_bounds__(kTBlock)
+tail_post_kernel(const __grid_constant__ TailParams p, const double* reward,
+                 const uint8_t* done, double* out_reward, const double* replay_rn) {
   const int64_t i = (int64_t)blockIdx.x * kTBlock + threadIdx.x;
   if (i >= p.n) return;
   const mdpp_tail_config& c = p.cfg;
   const uint32_t gid = (uint32_t)(p.env_id_offset + i);
   const uint32_t s0 = (uint32_t)p.step_index, s1 = (uint32_t)(p.step_index >> 32);
-  // ---- observation noise (:367-376, :405-406): next_obs += noise, a float64
-  // draw added into the observation's dtype
-  if (!c.discrete && obs && out_obs) {
-    const int D = c.obs_dim;
-    for (int d0 = 0; d0 < D; d0 += 2) {
-      double z0 = 0.0, z1 = 0.0;
-      if (c.has_transition_noise) {
-        if (p.noise_mode == MDPP_NOISE_REPLAY) {
-          z0 = replay_on[i * D + d0];
-          if (d0 + 1 < D) z1 = replay_on[i * D + d0 + 1];
-        } else {
-          const U4 w = philox4x32_10(gid, s0, s1, STREAM_TAIL_OBS + (uint32_t)(d0 >> 1),
-                                     p.k0, p.k1);
-          normal_pair_f64(w.x, w.y, &z0, &z1);
-          z0 = __dmul_rn(c.transition_noise, z0);
-          z1 = __dmul_rn(c.transition_noise, z1);
-        }
-      }
-      out_obs[i * D + d0] = (R)__dadd_rn((double)obs[i * D + d0], z0);
-      if (d0 + 1 < D) out_obs[i * D + d0 + 1] = (R)__dadd_rn((double)obs[i * D + d0 + 1], z1);
-    }
-  }
   // ---- reward tail (:411-436) ---------------------------------------------
   double r = reward[i];
   const int delay = c.delay;
@@ -148,9 +164,10 @@ tail_post_kernel(const __grid_constant__ TailParams p, const R* obs, R* out_obs,
     if (p.noise_mode == MDPP_NOISE_REPLAY) {
       nz = replay_rn[i];
     } else {
-      const U4 w = philox4x32_10(gid, s0, s1, STREAM_TAIL_NORMAL, p.k0, p.k1);
+      const U4 w = philox4x32_10_rk(gid, s0, s1, STREAM_TAIL_NORMAL, p.rk);
       double z0, z1;
-      normal_pair_f64(w.x, w.y, &z0, &z1);
+      if (p.normal_mode == MDPP_NORMAL_FAST) normal_pair_fast(w.x, w.y, &z0, &z1);
+      else normal_pair_f64(w.x, w.y, &z0, &z1);
       nz = __dmul_rn(c.reward_noise_std, z0);
     }
     r = __dadd_rn(r, nz);
@@ -375,6 +392,8 @@ int fill(mdpp_ctx* ctx, const mdpp_tail_config* cfg, const mdpp_step_opts* opts,
   p->noise_mode = opts->noise_mode;
   p->k0 = (uint32_t)opts->seed;
   p->k1 = (uint32_t)(opts->seed >> 32);
+  philox_round_keys(p->k0, p->k1, p->rk);
+  p->normal_mode = opts->normal_mode == MDPP_NORMAL_FAST ? MDPP_NORMAL_FAST : MDPP_NORMAL_F64;
   p->step_index = opts->step_index;
   p->env_id_offset = opts->env_id_offset;
   return MDPP_OK;
@@ -426,14 +445,21 @@ extern "C" int mdpp_tail_post(mdpp_ctx* ctx, const mdpp_tail_config* cfg,
   MDPP_CUDA(ctx, cudaSetDevice(ctx->device));
   const unsigned grid = (unsigned)((st->n_envs + kTBlock - 1) / kTBlock);
   cudaStream_t s = (cudaStream_t)cuda_stream;
-  if (cfg->obs_is_f64)
-    tail_post_kernel<double><<<grid, kTBlock, 0, s>>>(
-        p, (const double*)obs, (double*)out_obs, reward, done, out_reward,
-        replay_reward_noise, replay_obs_noise);
-  else
-    tail_post_kernel<float><<<grid, kTBlock, 0, s>>>(
-        p, (const float*)obs, (float*)out_obs, reward, done, out_reward,
-        replay_reward_noise, replay_obs_noise);
+  if (!cfg->discrete && obs && out_obs) {
+    if (cfg->obs_dim < 1) return fail(ctx, MDPP_EINVAL, "tail_post: obs_dim < 1");
+    const int64_t pairs = st->n_envs * ((cfg->obs_dim + 1) / 2);
+    if (pairs > 0x7fffffffLL * kTBlock)
+      return fail(ctx, MDPP_EINVAL, "tail_post: too many observation elements per call");
+    const unsigned og = (unsigned)((pairs + kTBlock - 1) / kTBlock);
+    if (cfg->obs_is_f64)
+      tail_obs_kernel<double><<<og, kTBlock, 0, s>>>(p, (const double*)obs,
+                                                     (double*)out_obs, replay_obs_noise);
+    else
+      tail_obs_kernel<float><<<og, kTBlock, 0, s>>>(p, (const float*)obs, (float*)out_obs,
+                                                    replay_obs_noise);
+  }
+  tail_post_kernel<<<grid, kTBlock, 0, s>>>(p, reward, done, out_reward,
+                                            replay_reward_noise);
   MDPP_CUDA(ctx, cudaGetLastError());
   return MDPP_OK;
 }

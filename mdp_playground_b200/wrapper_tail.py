@@ -36,11 +36,16 @@ def _ptr(t):
 class VectorGymEnvTail:
     def __init__(self, num_envs, device=None, noise="philox", seed=0,
                  env_id_offset=0, n_actions=None, obs_dim=None,
-                 obs_dtype=torch.float32, image_side=None, **config):
+                 obs_dtype=torch.float32, image_side=None, normal_precision="fp64",
+                 **config):
         if not torch.cuda.is_available():
             raise RuntimeError("VectorGymEnvTail needs a CUDA device: there is "
                                "no CPU fallback")
         assert noise in ("philox", "replay")
+        # native noise normals: fp64 Box-Muller (default) or fp32 on the SFU
+        assert normal_precision in ("fp64", "fast")
+        self._normal_mode = _lib.MDPP_NORMAL_FAST if normal_precision == "fast" \
+            else _lib.MDPP_NORMAL_F64
         self._lib = _lib.load()
         self.num_envs, self.noise = int(num_envs), noise
         self.device = torch.device("cuda", torch.cuda.current_device()) \
@@ -110,6 +115,7 @@ class VectorGymEnvTail:
             else _lib.MDPP_NOISE_PHILOX
         o.seed, o.step_index = self.seed, self._step_index
         o.env_id_offset = self.env_id_offset
+        o.normal_mode = self._normal_mode
         return o
 
     def _stream(self):

@@ -157,3 +157,34 @@ def test_cuda_image_shift_equals_the_oracle_for_every_kernel_path(side, pad, qua
     x = imgs.cpu().numpy()
     for i in range(N):
         assert np.array_equal(got[i], ora.shift_image(x[i], shifts[i])), i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_cuda_tail_observation_noise_statistics(dtype):
+    """Native observation noise of continuous envs (:367-376): every dimension
+    N(0, sigma) (KS), dimensions and steps uncorrelated, odd obs_dim handled;
+    without transition_noise the observations pass through."""
+    import torch
+    from scipy import stats
+    from mdp_playground_b200 import VectorGymEnvTail
+    N, D = 100_000, 5
+    dt = getattr(torch, dtype)
+    tail = VectorGymEnvTail(N, seed=11, obs_dim=D, obs_dtype=dt, state_space_type="continuous",
+                            transition_noise=0.5, reward_noise=1.0)
+    base = torch.arange(D, dtype=dt, device="cuda").repeat(N, 1)
+    r = torch.zeros(N, dtype=torch.float64, device="cuda")
+    d = torch.zeros(N, dtype=torch.bool, device="cuda")
+    o1, r1 = tail.post(base, r, d)
+    o2, _ = tail.post(base, r, d)
+    assert o1.dtype == dt and o1.shape == (N, D)
+    z1 = ((o1 - base) / 0.5).double().cpu().numpy()
+    z2 = ((o2 - base) / 0.5).double().cpu().numpy()
+    for k in range(D):
+        assert stats.kstest(z1[:, k], "norm").pvalue > 1e-4, k
+    cc = np.corrcoef(np.concatenate([z1, z2], axis=1).T)
+    assert np.abs(cc - np.eye(2 * D)).max() < 0.02
+    assert stats.kstest(r1.cpu().numpy(), "norm").pvalue > 1e-4
+    quiet = VectorGymEnvTail(N, seed=11, obs_dim=D, obs_dtype=dt, state_space_type="continuous")
+    o3, r3 = quiet.post(base, r + 2.0, d)
+    assert torch.equal(o3, base) and torch.equal(r3, r + 2.0)
