@@ -1,0 +1,153 @@
+"""Randomised configurations on the GPU: the CUDA kernels (through the C ABI)
+against the batched CPU oracles on the configurations of tests/fuzz_configs.py
+-- the same ones tests/test_fuzz_reference.py pins the oracle on against the
+unmodified reference.  Native Philox noise on both sides, device-drawn and
+given actions, ragged batch sizes, both the run-time specialised (NVRTC) and
+the ahead-of-time kernels, the standard bench signature (out=, no final_obs)
+as well as the generic one.
+
+Bars: discrete / grid -- states, flags bit-exact, fp64 rewards 1e-12;
+continuous -- states 1e-5 relative (north_star), rewards 1e-4, flags equal.
+"""
+import copy
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.scalar_env import ScalarRLToyEnv
+from oracle.vector_continuous_oracle import VectorContinuousOracle
+from oracle.vector_grid_oracle import VectorGridOracle
+from oracle.vector_oracle import VectorDiscreteOracle
+from tests.fuzz_configs import (CONTINUOUS_SEEDS, DISCRETE_SEEDS, GRID_SEEDS,
+                                continuous_fuzz_config, discrete_fuzz_config,
+                                grid_fuzz_config)
+from tests.golden.cases import materialise
+
+pytestmark = pytest.mark.gpu
+
+
+def make_env(*a, **k):
+    from mdp_playground_b200 import VectorRLToyEnv
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return VectorRLToyEnv(*a, **k)
+
+
+def scalar_oracle(cfg):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return ScalarRLToyEnv(**cfg)
+
+
+def _shape_of(seed):
+    """Batch size (ragged on purpose), rollout length, horizon, JIT on/off."""
+    r = np.random.default_rng(77 + seed)
+    N = int(r.choice([1, 31, 65, 257, 700, 1500]))
+    T = int(r.choice([9, 24, 41]))
+    horizon = int(r.choice([0, 5, 13]))
+    return N, T, horizon, bool(seed % 2)
+
+
+@pytest.mark.parametrize("seed", DISCRETE_SEEDS)
+def test_discrete_fuzz_cuda_vs_oracle(seed):
+    cfg = discrete_fuzz_config(seed)
+    N, T, horizon, jit = _shape_of(seed)
+    irr = bool(cfg.get("irrelevant_features"))
+    ora = VectorDiscreteOracle(scalar_oracle(materialise(copy.deepcopy(cfg))), N,
+                               autoreset=True, horizon=horizon, seed=seed,
+                               env_id_offset=12345)
+    env = make_env(N, autoreset=True, horizon=horizon, philox_seed=seed,
+                   env_id_offset=12345, **materialise(copy.deepcopy(cfg)))
+    env.set_jit(jit)
+    first = ora.reset()  # mirrors the reset at the end of the env constructor
+    cur = (np.stack([env._cur.cpu().numpy(), env._cur_irr.cpu().numpy()], -1)
+           if irr else env._cur.cpu().numpy())
+    assert np.array_equal(cur, first)
+    r = np.random.default_rng(seed)
+    for part, given in ((T, False), (7, True), (1, True)):
+        actions = None
+        if given:
+            actions = r.integers(0, ora.A, size=(part, N))
+            if irr:
+                actions = np.stack([actions, r.integers(0, ora.A1, size=(part, N))], -1)
+        want = ora.rollout(part, actions=actions)
+        got = env.rollout(part, actions=actions)
+        for k in ("obs", "final_obs", "terminated", "truncated"):
+            assert np.array_equal(got[k].cpu().numpy(), want[k]), (k, cfg)
+        np.testing.assert_allclose(got["reward"].cpu().numpy(), want["reward"],
+                                   rtol=1e-12, atol=1e-12, err_msg=str(cfg))
+    # the standard signature of the bench (actions and out= given, no final_obs):
+    # the FAST kernel with its action-prefetch loop
+    part = 21
+    actions = r.integers(0, ora.A, size=(part, N))
+    if irr:
+        actions = np.stack([actions, r.integers(0, ora.A1, size=(part, N))], -1)
+    want = ora.rollout(part, actions=actions)
+    acts_dev = torch.as_tensor(actions, dtype=torch.int32, device="cuda")
+    out = env.rollout(part, actions=acts_dev, want_final_obs=False)
+    for k in ("obs", "terminated", "truncated"):
+        assert np.array_equal(out[k].cpu().numpy(), want[k]), (k, cfg)
+    np.testing.assert_allclose(out["reward"].cpu().numpy(), want["reward"],
+                               rtol=1e-12, atol=1e-12, err_msg=str(cfg))
+    st = env.episode_stats()
+    for k in ("episodes", "transitions", "noisy_transitions", "terminated"):
+        assert st[k][0] == ora.stats[k], (k, cfg)
+
+
+@pytest.mark.parametrize("seed", CONTINUOUS_SEEDS)
+def test_continuous_fuzz_cuda_vs_oracle(seed):
+    cfg = continuous_fuzz_config(seed)
+    N, T, horizon, jit = _shape_of(seed)
+    ora = VectorContinuousOracle(scalar_oracle(materialise(copy.deepcopy(cfg))), N,
+                                 autoreset=True, horizon=horizon, seed=seed,
+                                 env_id_offset=777)
+    env = make_env(N, autoreset=True, horizon=horizon, philox_seed=seed,
+                   env_id_offset=777, **materialise(copy.deepcopy(cfg)))
+    env.set_jit(jit)
+    ora.reset()
+    np.testing.assert_allclose(env.curr_obs.cpu().numpy(), ora.em, rtol=1e-6)
+    D, amax = cfg["state_space_dim"], cfg["action_space_max"]
+    # a few percent of the actions leave the action space (the reference
+    # freezes the state for those, rl_toy_env.py:1640-1679)
+    acts = np.random.default_rng(seed).uniform(
+        -1.03 * amax, 1.03 * amax, size=(T, N, D)).astype(np.float32)
+    want = ora.rollout(T, acts)
+    got = env.rollout(T, torch.as_tensor(acts))
+    for k in ("terminated", "truncated"):
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), (k, cfg)
+    for k in ("obs", "final_obs"):
+        np.testing.assert_allclose(got[k].cpu().numpy(), want[k], rtol=1e-5,
+                                   atol=1e-6, err_msg=str(cfg))
+    np.testing.assert_allclose(got["reward"].cpu().numpy(), want["reward"],
+                               rtol=1e-4, atol=1e-5, err_msg=str(cfg))
+
+
+@pytest.mark.parametrize("seed", GRID_SEEDS)
+def test_grid_fuzz_cuda_vs_oracle(seed):
+    cfg = grid_fuzz_config(seed)
+    N, T, horizon, _ = _shape_of(seed)
+    ora = VectorGridOracle(scalar_oracle(materialise(copy.deepcopy(cfg))), N,
+                           autoreset=True, horizon=horizon, seed=seed,
+                           env_id_offset=99)
+    env = make_env(N, autoreset=True, horizon=horizon, philox_seed=seed,
+                   env_id_offset=99, **materialise(copy.deepcopy(cfg)))
+    first = ora.reset()
+    assert np.array_equal(env.get_augmented_state()["curr_state"].cpu().numpy(), first)
+    rng = np.random.default_rng(seed)
+    for part in (T, 1):
+        acts = np.zeros((part, N, ora.nd), dtype=np.int64)
+        d = rng.integers(ora.nd, size=(part, N))
+        np.put_along_axis(acts, d[..., None], rng.integers(-1, 2, size=(part, N, 1)), -1)
+        bad = rng.random((part, N)) < 0.05  # not unit moves: no-ops in the reference
+        acts[bad] = rng.integers(-2, 3, size=(int(bad.sum()), ora.nd))
+        want = ora.rollout(part, acts)
+        got = env.rollout(part, actions=acts)
+        for k in ("obs", "final_obs", "terminated", "truncated"):
+            assert np.array_equal(got[k].cpu().numpy(), want[k]), (k, cfg)
+        np.testing.assert_allclose(got["reward"].cpu().numpy(), want["reward"],
+                                   rtol=1e-12, atol=1e-12, err_msg=str(cfg))
+    st = env.episode_stats()
+    for k in ("episodes", "transitions", "noisy_transitions", "terminated"):
+        assert st[k][0] == ora.stats[k], (k, cfg)

@@ -45,7 +45,12 @@ def _check_lane(env, g, k, H, image):
 
 @pytest.mark.parametrize("name", gu.GRID_CASES)
 def test_oracle_numpy_streams_match_reference_golden(name):
-    g, cfg = gu.load(name), gu.case_config(name)
+    grid_numpy_leg(gu.load(name), gu.case_config(name),
+                   CASES[name].get("horizon", 12))
+
+
+def grid_numpy_leg(g, cfg, H):
+    """(also run on freshly recorded cases by tests/test_fuzz_reference.py)"""
     env = scalar_oracle(cfg)
     image = bool(cfg.get("image_representations"))
     for k in range(g["done"].shape[0]):
@@ -56,7 +61,7 @@ def test_oracle_numpy_streams_match_reference_golden(name):
         assert np.array_equal(env.curr_state, g["init_state"][k])
         if image:
             assert np.array_equal(obs0, g["init_image"][k])
-        _check_lane(env, g, k, CASES[name].get("horizon", 12), image)
+        _check_lane(env, g, k, H, image)
 
 
 @pytest.mark.parametrize("name", [n for n in gu.GRID_CASES

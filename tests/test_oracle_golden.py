@@ -64,11 +64,9 @@ def _check_lane(env, g, k, cfg, H):
 NOT_GRID = [n for n in CASES if n not in gu.GRID_CASES]  # grid: tests/test_grid.py
 
 
-@pytest.mark.parametrize("name", NOT_GRID)
-def test_oracle_numpy_streams_match_reference_golden(name):
-    g = gu.load(name)
-    cfg = gu.case_config(name)
-    H = CASES[name].get("horizon", 12)
+def numpy_leg(g, cfg, H):
+    """The oracle on its own PCG64 streams against one golden record `g`
+    (also used on freshly generated records by tests/test_fuzz_reference.py)."""
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         env = ScalarRLToyEnv(**cfg)
@@ -89,6 +87,12 @@ def test_oracle_numpy_streams_match_reference_golden(name):
         if cfg.get("image_representations"):
             assert np.array_equal(obs0, g["init_image"][k])
         _check_lane(env, g, k, cfg, H)
+
+
+@pytest.mark.parametrize("name", NOT_GRID)
+def test_oracle_numpy_streams_match_reference_golden(name):
+    numpy_leg(gu.load(name), gu.case_config(name),
+              CASES[name].get("horizon", 12))
 
 
 def _lane_feed(g, k, cont, image_params=None):
@@ -127,9 +131,14 @@ def _lane_feed(g, k, cont, image_params=None):
                                   if not CASES[n]["config"].get(
                                       "image_representations")])
 def test_oracle_replay_of_recorded_draws(name):
-    g = gu.load(name)
-    cfg = gu.case_config(name)
-    H = CASES[name].get("horizon", 12)
+    replay_leg(gu.load(name), lambda: gu.case_config(name),
+               CASES[name].get("horizon", 12))
+
+
+def replay_leg(g, make_cfg, H):
+    """The oracle fed with the draws recorded in `g`; `make_cfg()` returns a
+    fresh config dict (the constructor edits it in place)."""
+    cfg = make_cfg()
     cont = cfg["state_space_type"] == "continuous"
     for k in range(g["done"].shape[0]):
         feed = _lane_feed(g, k, cont)
@@ -142,7 +151,7 @@ def test_oracle_replay_of_recorded_draws(name):
                 feed["irr_reset_u"].insert(0, 0.0)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            env = ScalarRLToyEnv(draws=ReplayDraws(feed), **gu.case_config(name))
+            env = ScalarRLToyEnv(draws=ReplayDraws(feed), **make_cfg())
         env.reset()
         assert np.array_equal(env.curr_state, g["init_state"][k])
         _check_lane(env, g, k, cfg, H)
