@@ -500,26 +500,32 @@ def other_configs(torch, Env, dev, rank, world, barrier, max_over_ranks, peak,
                 for d in (0, 1, 2, 4, 8) for L in (1, 2, 3, 4)
                 for pn in (0, 0.01, 0.02, 0.1, 0.25) for rn in (0, 1, 5, 10, 25)
                 for md in (False, True)]
-        N, T = 1 << 20, 100
-        for prec in ("fp64", "fast"):
-            env = Env(N, device=dev, autoreset=True, horizon=100, config_groups=cfgs,
-                      shard=(rank, world), normal_precision=prec)
-            acts = torch.randint(0, 8, (T, N), dtype=torch.int32, device=dev)
-            out = env.rollout(T, actions=acts, want_final_obs=False)
-            ms = _time_launches(torch, lambda: env.rollout(T, actions=acts, out=out),
-                                5, barrier, max_over_ranks)
-            name = "C5_heterogeneous_1000_groups_rollout" + (
-                "" if prec == "fp64" else "[fast normals]")
-            line(name, N, T, ms, 22,
-                 "fused rollout, one multi-group launch (scalars shared by all "
-                 "groups specialised); reward normals: " + NORMAL_NAMES[prec])
-            if prec == "fp64":
-                s5 = env.episode_stats(reduce=True)
-                res[name]["stats_allreduce"] = {
-                    "groups": len(cfgs),
-                    "episode_len_mean_min_max": [float(np.min(s5["episode_len_mean"])),
-                                                 float(np.max(s5["episode_len_mean"]))]}
-            del env, acts, out
+        N = 1 << 20
+        # 100 steps per launch (round 1's shape, 2.3 GB of I/O buffers) and the
+        # 1000 steps per launch SURVEY.md 8d specifies (23 GB: prologue and the
+        # last partial ziggurat window amortised over ten times the steps)
+        for T in (100, 1000):
+            for prec in ("fp64", "fast"):
+                env = Env(N, device=dev, autoreset=True, horizon=100, config_groups=cfgs,
+                          shard=(rank, world), normal_precision=prec)
+                acts = torch.randint(0, 8, (T, N), dtype=torch.int32, device=dev)
+                out = env.rollout(T, actions=acts, want_final_obs=False)
+                ms = _time_launches(torch, lambda: env.rollout(T, actions=acts, out=out),
+                                    5, barrier, max_over_ranks)
+                name = "C5_heterogeneous_1000_groups_rollout" + (
+                    "" if prec == "fp64" else "[fast normals]") + (
+                    "" if T == 100 else "[1000 steps per launch]")
+                line(name, N, T, ms, 22,
+                     "fused rollout, one multi-group launch (scalars shared by all "
+                     "groups specialised); reward normals: " + NORMAL_NAMES[prec])
+                if prec == "fp64" and T == 100:
+                    s5 = env.episode_stats(reduce=True)
+                    res[name]["stats_allreduce"] = {
+                        "groups": len(cfgs),
+                        "episode_len_mean_min_max": [float(np.min(s5["episode_len_mean"])),
+                                                     float(np.max(s5["episode_len_mean"]))]}
+                del env, acts, out
+                torch.cuda.empty_cache()
     return res
 
 

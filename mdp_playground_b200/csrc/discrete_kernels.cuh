@@ -874,7 +874,8 @@ struct ZigStage {
 #endif
 static __device__ MDPP_ZIG_FILL_ATTR void zig_fill(const RolloutParams& p, const GroupView& v,
                                          const ZigStage& zst, uint32_t gid,
-                                         uint64_t g0) {  // even global step
+                                         uint64_t g0,    // even global step
+                                         int n_need) {   // steps the caller will read
   const int lane = threadIdx.x & 31;
   const uint8_t* zt = reinterpret_cast<const uint8_t*>(v.zig_kw);  // smem copy
   if (zst.rank == 0) *zst.qcnt = 0;
@@ -884,8 +885,13 @@ static __device__ MDPP_ZIG_FILL_ATTR void zig_fill(const RolloutParams& p, const
   // (always a whole window: a compile-time trip count measured 9 % faster than
   // drawing only what the last window needs; launches shorter than a window
   // do not stage at all, see stage_of)
+#ifdef MDPP_ZIG_FILL_DYN  // short launches: the last window only as far as it is read
+  const int hb_end = min(kZigWindow / 2, (n_need + 1) / 2);
+#else
+  constexpr int hb_end = kZigWindow / 2;
+#endif
 #pragma unroll 1
-  for (int hb = 0; hb < kZigWindow / 2; hb += kZigFillUnroll) {
+  for (int hb = 0; hb < hb_end; hb += kZigFillUnroll) {
     uint32_t r8 = 0;
     double* zcol = zst.zs + 2 * hb * kBlock;
 #pragma unroll
@@ -1069,7 +1075,8 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
       for (; t0 <= t_last; t0 += kChunk) {
         if (staged && t0 >= zs_t0 + kZigWindow) {
           zs_t0 = t0;
-          zig_fill(p, v, zst, gid, step_base + (uint64_t)t0);
+          zig_fill(p, v, zst, gid, step_base + (uint64_t)t0,
+                   (p.T - t0) / kChunk * kChunk);
         }
         int32_t act[kChunk], act_i[kChunk];
         const int tn = min(t0 + kChunk, t_last);
@@ -1091,7 +1098,8 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
       for (; t0 + kChunk <= p.T; t0 += kChunk) {
         if (staged && t0 >= zs_t0 + kZigWindow) {
           zs_t0 = t0;
-          zig_fill(p, v, zst, gid, step_base + (uint64_t)t0);
+          zig_fill(p, v, zst, gid, step_base + (uint64_t)t0,
+                   (p.T - t0) / kChunk * kChunk);
         }
         if (stage_path)
           run_chunk<C, kChunk, ZIG && SMEM>(p, v, e, ring_smem, env, gid, step_base, t0,
