@@ -151,6 +151,62 @@ def grid_fuzz_config(seed):
     return cfg
 
 
+def image_fuzz_config(seed):
+    """Image observations (rl_toy_env.py:705-717, :767-776): discrete envs with
+    random transform subsets / quantisations / scale ranges / image sizes
+    (also of both sub-states with irrelevant_features), continuous envs with
+    target, terminal boxes and the irrelevant sub-image."""
+    r = np.random.default_rng(13000 + seed)
+    if r.random() < 0.7:
+        A = int(r.integers(3, 9))
+        cfg = dict(seed=int(r.integers(0, 1000)), state_space_type="discrete",
+                   action_space_type="discrete", action_space_size=A,
+                   state_space_size=A, sequence_length=1, delay=0,
+                   terminal_state_density=0.25, reward_density=0.25,
+                   generate_random_mdp=True, image_representations=True)
+        tr = [t for t in ("shift", "scale", "rotate", "flip") if r.random() < 0.6]
+        if tr:
+            cfg["image_transforms"] = ",".join(tr)
+        W, H = int(r.choice([64, 100, 128])), int(r.choice([64, 100, 120]))
+        cfg["image_width"], cfg["image_height"] = W, H
+        if r.random() < 0.7:
+            cfg["image_sh_quant"] = int(r.choice([1, 2, 4, 8]))
+        if r.random() < 0.7:
+            cfg["image_ro_quant"] = int(r.choice([1, 5, 30, 90]))
+        if r.random() < 0.7:
+            lo = float(r.choice([0.5, 0.8, 1.0]))
+            cfg["image_scale_range"] = (lo, float(lo + r.choice([0.0, 0.3, 0.5])))
+        if r.random() < 0.3:
+            cfg["transition_noise"] = 0.1
+        if r.random() < 0.25:
+            cfg["irrelevant_features"] = True
+            cfg["action_space_size"] = [A, int(r.integers(2, 7))]
+            cfg["state_space_size"] = list(cfg["action_space_size"])
+        return cfg
+    D = int(r.choice([2, 4]))
+    smax = float(r.choice([2.0, 5.0]))
+    cfg = dict(seed=int(r.integers(0, 1000)), state_space_type="continuous",
+               action_space_type="continuous", state_space_dim=D, action_space_dim=D,
+               transition_dynamics_order=int(r.integers(1, 3)), inertia=1.0,
+               time_unit=float(r.choice([0.5, 1.0])), state_space_max=smax,
+               action_space_max=1.0, reward_function="move_to_a_point",
+               target_point=[float(x) for x in np.round(r.uniform(-smax, smax, size=2), 2)],
+               target_radius=0.5, image_representations=True)
+    if D == 4:
+        cfg["relevant_indices"] = [0, 1]
+        cfg["irrelevant_features"] = True
+    if r.random() < 0.6:
+        cfg["terminal_states"] = [
+            [float(x) for x in np.round(r.uniform(-smax, smax, size=2), 2)]
+            for _ in range(int(r.integers(1, 3)))]
+        cfg["term_state_edge"] = float(r.choice([0.5, 1.5]))
+    if r.random() < 0.5:
+        cfg["image_width"], cfg["image_height"] = int(r.choice([64, 100])), int(r.choice([48, 100]))
+    if r.random() < 0.3:
+        cfg["transition_noise"] = 0.05
+    return cfg
+
+
 # Screened with tools/screen_fuzz_seeds.py: the first seeds of each generator
 # that the reference accepts and runs 40 steps of without raising (it rejects
 # discrete seeds 3, 11, 14, 22, 27, 34, 40: too few rewardable sequences for
@@ -158,3 +214,4 @@ def grid_fuzz_config(seed):
 DISCRETE_SEEDS = [0, 1, 2, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15, 16, 17, 18, 19, 20, 21, 23, 24, 25, 26, 28, 29, 30, 31, 32, 33, 35, 36, 37, 38, 39, 41, 42, 43, 44, 45, 46]
 CONTINUOUS_SEEDS = list(range(40))
 GRID_SEEDS = list(range(24))
+IMAGE_SEEDS = list(range(24))

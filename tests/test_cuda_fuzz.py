@@ -21,8 +21,9 @@ from oracle.vector_continuous_oracle import VectorContinuousOracle
 from oracle.vector_grid_oracle import VectorGridOracle
 from oracle.vector_oracle import VectorDiscreteOracle
 from tests.fuzz_configs import (CONTINUOUS_SEEDS, DISCRETE_SEEDS, GRID_SEEDS,
-                                continuous_fuzz_config, discrete_fuzz_config,
-                                grid_fuzz_config)
+                                IMAGE_SEEDS, continuous_fuzz_config,
+                                discrete_fuzz_config, grid_fuzz_config,
+                                image_fuzz_config)
 from tests.golden.cases import materialise
 
 pytestmark = pytest.mark.gpu
@@ -151,3 +152,38 @@ def test_grid_fuzz_cuda_vs_oracle(seed):
     st = env.episode_stats()
     for k in ("episodes", "transitions", "noisy_transitions", "terminated"):
         assert st[k][0] == ora.stats[k], (k, cfg)
+
+
+@pytest.mark.parametrize("seed", IMAGE_SEEDS)
+def test_image_fuzz_same_seed_drop_in(seed):
+    """noise='numpy': one env with the configuration and seed of the (oracle of
+    the) reference consumes the reference's own numpy streams => the same
+    trajectory and the same pixels, constructor included."""
+    cfg = image_fuzz_config(seed)
+    cont = cfg["state_space_type"] == "continuous"
+    ref = scalar_oracle(materialise(copy.deepcopy(cfg)))
+    env = make_env(1, noise="numpy", **materialise(copy.deepcopy(cfg)))
+    assert np.array_equal(env.curr_obs[0].cpu().numpy(), ref.curr_obs)
+    rng = np.random.default_rng(seed)
+    irr = (not cont) and bool(cfg.get("irrelevant_features"))
+    for t in range(30):
+        if cont:
+            a = rng.uniform(-1, 1, size=cfg["state_space_dim"]).astype(np.float32)
+            o2, r2, d2, _, _ = env.step(torch.as_tensor(a.copy())[None])
+        elif irr:
+            a = [int(rng.integers(n)) for n in cfg["action_space_size"]]
+            o2, r2, d2, _, _ = env.step([a])
+        else:
+            a = int(rng.integers(cfg["action_space_size"]))
+            o2, r2, d2, _, _ = env.step([a])
+        o1, r1, d1, _, _ = ref.step(a)
+        assert np.array_equal(o2[0].cpu().numpy(), o1), (t, cfg)
+        assert bool(d2[0]) == d1
+        if cont:
+            np.testing.assert_allclose(float(r2[0]), float(r1), rtol=1e-5, atol=1e-6)
+        else:
+            assert float(r2[0]) == float(r1)
+        if d1 or t % 10 == 9:
+            o1, _ = ref.reset()
+            o2, _ = env.reset()
+            assert np.array_equal(o2[0].cpu().numpy(), o1), (t, cfg)

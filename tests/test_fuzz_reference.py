@@ -15,8 +15,9 @@ import numpy as np
 import pytest
 
 from tests.fuzz_configs import (continuous_fuzz_config, discrete_fuzz_config,
-                                grid_fuzz_config, DISCRETE_SEEDS,
-                                CONTINUOUS_SEEDS, GRID_SEEDS)
+                                grid_fuzz_config, image_fuzz_config,
+                                DISCRETE_SEEDS, CONTINUOUS_SEEDS, GRID_SEEDS,
+                                IMAGE_SEEDS)
 from tests.golden.cases import materialise
 from tests.test_oracle_golden import numpy_leg, replay_leg
 
@@ -56,3 +57,12 @@ def test_grid_fuzz_reference_vs_oracle(seed, tmp_path):
     g = _record("fuzz_g%d" % seed, cfg, tmp_path, lanes=3, steps=40, horizon=9,
                 grid=True)
     grid_numpy_leg(g, materialise(cfg), 9)
+
+
+@pytest.mark.parametrize("seed", IMAGE_SEEDS)
+def test_image_fuzz_reference_vs_oracle(seed, tmp_path):
+    """Image observations (Pillow on the reference side, the oracle's
+    restatement of its rasteriser on ours): every pixel of every step."""
+    cfg = image_fuzz_config(seed)
+    g = _record("fuzz_i%d" % seed, cfg, tmp_path, lanes=2, steps=16, horizon=6)
+    numpy_leg(g, materialise(cfg), 6)

@@ -49,7 +49,8 @@ def accepted(cfg):
 
 for name, gen, n in (("DISCRETE", fz.discrete_fuzz_config, 60),
                      ("CONTINUOUS", fz.continuous_fuzz_config, 60),
-                     ("GRID", fz.grid_fuzz_config, 40)):
+                     ("GRID", fz.grid_fuzz_config, 40),
+                     ("IMAGE", fz.image_fuzz_config, 40)):
     ok = []
     for s in range(n):
         good, why = accepted(gen(s))
