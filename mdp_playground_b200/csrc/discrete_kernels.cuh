@@ -910,6 +910,9 @@ static __device__ MDPP_ZIG_FILL_ATTR void zig_fill(const RolloutParams& p, const
     }
     rej |= r8 << (2 * hb);
   }
+#ifdef MDPP_EXP_NO_SLOW  // (timing experiment: wrong normals, no slow path)
+  rej = 0;
+#endif
   uint32_t slot = 0;
   if (rej) slot = atomicAdd(zst.qcnt, (uint32_t)__popc(rej));
   while (rej) {
