@@ -77,7 +77,9 @@ __device__ __forceinline__ int obs_dtype_of(const RolloutParams& p) {
 // Ziggurat normals staged a window ahead (zig_fill) only when the launch
 // covers at least one window; shorter launches draw them chunk by chunk.
 __device__ __forceinline__ bool stage_of(const RolloutParams& p) {
-#ifdef MDPP_JIT
+#ifdef MDPP_EXP_NO_STAGE  // (timing experiment: draw chunk by chunk)
+  return false;
+#elif defined(MDPP_JIT)
   return MDPP_CFG_STAGE;
 #else
   return p.T >= kZigWindow;
@@ -394,8 +396,14 @@ __device__ __forceinline__ uint32_t philox_quad_draws(
     const uint4* zig_kw) {
   const uint32_t q0 = (uint32_t)quad, q1 = (uint32_t)(quad >> 32);
   uint32_t rejected = 0;  // NORMAL == 2: bit j = step 4q+j needs zig_slow()
+#ifdef MDPP_EXP_NO_CHAIN_PHILOX  // (timing experiment: a multiplicative hash instead)
+#define MDPP_CHAIN_WORDS(stream) \
+  U4{(gid ^ q0) * 2654435761u + stream, (gid + q0) * 2246822519u, (gid ^ (q0 << 7)) * 3266489917u, (gid - q0) * 668265263u}
+#else
+#define MDPP_CHAIN_WORDS(stream) philox4x32_10_rk(gid, q0, q1, stream, rk)
+#endif
   if (want_u) {
-    U4 w = philox4x32_10_rk(gid, q0, q1, STREAM_STEP, rk);
+    U4 w = MDPP_CHAIN_WORDS(STREAM_STEP);
     w_tr[0] = w.x; w_tr[1] = w.y; w_tr[2] = w.z; w_tr[3] = w.w;
   }
   if (want_normal) {
@@ -424,7 +432,7 @@ __device__ __forceinline__ uint32_t philox_quad_draws(
     }
   }
   if (want_reset) {
-    U4 w = philox4x32_10_rk(gid, q0, q1, STREAM_AUTORESET, rk);
+    U4 w = MDPP_CHAIN_WORDS(STREAM_AUTORESET);
     w_rs[0] = w.x; w_rs[1] = w.y; w_rs[2] = w.z; w_rs[3] = w.w;
   }
   return rejected;
@@ -581,6 +589,9 @@ __device__ __forceinline__ void phase_a(const RolloutParams& p, const GroupView&
           for (int k = 0; k < 4; ++k) n_rw[j + k] = __dmul_rn(v.r_std, z4[k]);
         }
       }
+#ifdef MDPP_EXP_NO_SLOW
+      rej = 0;
+#endif
       if (NORMAL == MDPP_NORMAL_ZIGGURAT && !STAGED) {
         // the 1.5 % of draws whose first ziggurat attempt was rejected: one
         // out-of-line call per draw, lanes without one wait
@@ -729,7 +740,9 @@ __device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupVi
     nxt = noisy;
   } else if (NOISE == MDPP_NOISE_PHILOX && v.has_pnoise) {
     nxt = rotate_state(nxt, k_tr, v.S);  // one of the S-1 other states
+#ifndef MDPP_EXP_NO_STATS  // (timing experiment)
     e.n_noisy += (k_tr != 0);
+#endif
   }
   e.key = ((e.key << v.key_bits) | (uint64_t)nxt) & v.key_mask;
   e.tl += 1;
@@ -757,9 +770,13 @@ __device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupVi
     e.ring_pos = (e.ring_pos + 1 == v.delay) ? 0 : e.ring_pos + 1;
   }
   if (e.phase != 0) r = 0.0;
+#ifndef MDPP_EXP_NO_STATS
   e.sum_reward += r;
+#endif
   if (NOISE != MDPP_NOISE_OFF && v.has_rnoise) {
+#ifndef MDPP_EXP_NO_STATS
     e.sum_abs_rnoise += fabs(n_rw);
+#endif
     r = __dadd_rn(r, n_rw);
   }
   // `* 1.0` is the identity; `+ 0.0` only turns -0.0 into +0.0, and no -0.0
@@ -773,7 +790,9 @@ __device__ __forceinline__ void chain_step(const RolloutParams& p, const GroupVi
   if (!kTermRewardIsZero)
     if (done) r = __dadd_rn(r, v.term_reward_scaled);
   const bool trunc = horizon > 0 && e.tl >= horizon;
+#ifndef MDPP_EXP_NO_STATS
   e.n_terminated += done;
+#endif
   e.s = nxt;
   if (!FAST && p.io.final_obs) store_obs(p, p.io.final_obs, off, irr, nxt, e.s_irr);
   if (autoreset && (done || trunc)) {
@@ -1078,8 +1097,10 @@ __device__ __forceinline__ void rollout_body(const RolloutParams& p) {
       for (; t0 <= t_last; t0 += kChunk) {
         if (staged && t0 >= zs_t0 + kZigWindow) {
           zs_t0 = t0;
+#ifndef MDPP_EXP_NO_FILL  // (timing experiment: stale normals)
           zig_fill(p, v, zst, gid, step_base + (uint64_t)t0,
                    (p.T - t0) / kChunk * kChunk);
+#endif
         }
         int32_t act[kChunk], act_i[kChunk];
         const int tn = min(t0 + kChunk, t_last);

@@ -371,6 +371,37 @@ def test_bench_signature_matches_oracle(jit, normal, prologue, T):
         assert st[k][0] == stats[k], k
 
 
+@pytest.mark.parametrize("prologue,T", [(0, 300), (3, 427)])
+def test_long_launch_standard_signature_matches_oracle(prologue, T):
+    """The bench signature over MANY staged ziggurat windows (T = 300 / 427:
+    9 / 13 windows of 32 steps, peeled prologue step, partial last window),
+    run-time specialised and ahead-of-time kernel, against the oracle: states
+    / flags exact, rewards 1e-12, and JIT == AOT bit for bit.  (Written for the
+    pipelined-staging experiment, tools/experiments/: any restructuring of
+    where the normals are drawn must keep the Philox words per (env, step).)"""
+    N = 2048
+    acts, want, stats = _bench_oracle("fp64", prologue, T, N)
+    a = torch.as_tensor(acts, dtype=torch.int32, device="cuda")
+    outs = []
+    for jit in (True, False):
+        env = make_env(N, autoreset=True, horizon=100, env_id_offset=5 * N,
+                       normal_precision="fp64", **dict(_BENCH_CFG))
+        env.set_jit(jit)
+        if prologue:
+            env.rollout(prologue, actions=a[:prologue])
+        got = env.rollout(T, actions=a[prologue:].contiguous(), want_final_obs=False)
+        assert env.jit_last_used == jit, env.jit_log
+        for k in ("obs", "terminated", "truncated"):
+            assert np.array_equal(got[k].cpu().numpy(), want[k]), (jit, k)
+        np.testing.assert_allclose(got["reward"].cpu().numpy(), want["reward"],
+                                   rtol=1e-12, atol=1e-12)
+        st = env.episode_stats()
+        for k in ("episodes", "transitions", "noisy_transitions", "terminated"):
+            assert st[k][0] == stats[k], (jit, k)
+        outs.append(got["reward"])
+    assert torch.equal(outs[0], outs[1])  # NVRTC-specialised == ahead-of-time
+
+
 def test_ziggurat_reward_noise_is_standard_normal():
     """KS test of the native fp64 (ziggurat) reward noise, 2M draws incl. the
     wedge / tail path: (reward - noise-free reward) / sigma ~ N(0, 1)."""

@@ -170,6 +170,40 @@ def test_mixed_40_group_launch_matches_grouped_oracle(jit, normal):
             assert st[k][g] == s[k], (g, k)
 
 
+def test_mixed_40_group_long_launch_standard_signature():
+    """The same 40 groups through the standard signature (no final_obs: the
+    FAST multi-group kernel, chunks of 4, 16-step ziggurat windows) with T = 150,
+    i.e. nine windows and a partial one, against the grouped oracle and against
+    the ahead-of-time kernel."""
+    from oracle.scalar_env import ScalarRLToyEnv
+    from oracle.vector_oracle import VectorGroupedOracle
+    cfgs = _mixed_groups()
+    sizes = [37] * len(cfgs)
+    N, T = sum(sizes), 150
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        scalars = [ScalarRLToyEnv(**dict(c)) for c in cfgs]
+    ora = VectorGroupedOracle(scalars, sizes, autoreset=True, horizon=23, seed=3,
+                              env_id_offset=1000)
+    ora.reset()
+    acts = np.random.default_rng(1).integers(0, 8, size=(T, N))
+    want = ora.rollout(T, actions=acts)
+    rewards = []
+    for jit in (True, False):
+        env = make_env(N, autoreset=True, horizon=23, philox_seed=3, env_id_offset=1000,
+                       config_groups=[dict(c) for c in cfgs], group_sizes=sizes)
+        env.set_jit(jit)
+        got = env.rollout(T, actions=torch.as_tensor(acts, dtype=torch.int32, device="cuda"),
+                          want_final_obs=False)
+        assert env.jit_last_used == jit, env.jit_log
+        for k in ("obs", "terminated", "truncated"):
+            assert np.array_equal(got[k].cpu().numpy(), want[k]), (jit, k)
+        np.testing.assert_allclose(got["reward"].cpu().numpy(), want["reward"],
+                                   rtol=1e-12, atol=1e-12)
+        rewards.append(got["reward"])
+    assert torch.equal(rewards[0], rewards[1])
+
+
 def _continuous_cells():
     """A sac_move_to_a_point_* style grid: time_unit x action_space_max x noise
     x delay x target_radius cells of one continuous env (same dim / order)."""
