@@ -207,6 +207,39 @@ def image_fuzz_config(seed):
     return cfg
 
 
+def wrapper_fuzz_spec(seed):
+    """GymEnvWrapper tail (gym_env_wrapper.py:350-439, :523-618) around the
+    deterministic stand-in base envs of tests/golden/make_wrapper_golden.py:
+    discrete / Box / image bases, delay, action / observation noise, reward
+    noise / scale / shift, terminal reward, padded image shift."""
+    r = np.random.default_rng(17000 + seed)
+    kind = str(r.choice(["discrete", "box", "image"]))
+    cfg = dict(delay=int(r.choice([0, 1, 2, 4])))
+    if r.random() < 0.6:
+        cfg["reward_noise"] = float(r.choice([0.1, 0.5, 2.0]))
+    if r.random() < 0.5:
+        cfg["reward_scale"] = float(r.choice([0.5, 2.0, -1.0]))
+    if r.random() < 0.5:
+        cfg["reward_shift"] = float(r.choice([-1.0, 0.75]))
+    if r.random() < 0.4:
+        cfg["term_state_reward"] = float(r.choice([0.5, -2.0]))
+    if kind == "box":
+        cfg["state_space_type"] = "continuous"
+        if r.random() < 0.7:
+            cfg["transition_noise"] = float(r.choice([0.05, 0.1, 0.3]))
+        return dict(base="box", dim=int(r.integers(1, 7)), config=cfg)
+    cfg["state_space_type"] = "discrete"
+    if r.random() < 0.6:
+        cfg["transition_noise"] = float(r.choice([0.1, 0.2, 0.5]))
+    spec = dict(base=kind, n_actions=int(r.integers(2, 9)), config=cfg)
+    if kind == "image":
+        spec["side"] = int(r.choice([8, 12, 16]))
+        cfg["image_transforms"] = "shift"
+        cfg["image_padding"] = int(r.choice([2, 5, 8]))
+        cfg["image_sh_quant"] = int(r.choice([1, 2, 4]))
+    return spec
+
+
 # Screened with tools/screen_fuzz_seeds.py: the first seeds of each generator
 # that the reference accepts and runs 40 steps of without raising (it rejects
 # discrete seeds 3, 11, 14, 22, 27, 34, 40: too few rewardable sequences for
@@ -215,3 +248,4 @@ DISCRETE_SEEDS = [0, 1, 2, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15, 16, 17, 18, 19, 20,
 CONTINUOUS_SEEDS = list(range(40))
 GRID_SEEDS = list(range(24))
 IMAGE_SEEDS = list(range(24))
+WRAPPER_SEEDS = list(range(16))

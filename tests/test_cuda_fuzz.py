@@ -187,3 +187,65 @@ def test_image_fuzz_same_seed_drop_in(seed):
             o1, _ = ref.reset()
             o2, _ = env.reset()
             assert np.array_equal(o2[0].cpu().numpy(), o1), (t, cfg)
+
+
+def _synthetic_wrapper_record(spec, K, T, seed):
+    """Inputs of the GymEnvWrapper tail in the layout of the wrap_*.npz
+    records (what make_wrapper_golden records from the reference), drawn from a
+    seeded generator instead: the GPU box has no reference to record from."""
+    from oracle.wrapper_tail import ScalarWrapperTail
+    r = np.random.default_rng(seed)
+    cfg = spec["config"]
+    cont = cfg["state_space_type"] == "continuous"
+    image = spec["base"] == "image"
+    dim = spec.get("dim", 1)
+    g = {}
+    if cont:
+        g["action"] = r.uniform(-1, 1, (K, T, dim)).astype(np.float32)
+        g["base_obs"] = r.uniform(-3, 3, (K, T, dim)).astype(np.float32)
+    else:
+        g["action"] = r.integers(spec["n_actions"], size=(K, T))
+        if image:
+            s = spec["side"]
+            g["base_obs"] = r.integers(0, 256, (K, T, s, s, 3)).astype(np.uint8)
+        else:
+            g["base_obs"] = r.integers(50, size=(K, T))
+    pn = cfg.get("transition_noise")
+    g["choice_u"] = r.random((K, T)) if (pn and not cont) else np.full((K, T), np.nan)
+    g["obs_noise"] = (r.normal(0, pn, (K, T, dim)) if (pn and cont)
+                      else np.full((K, T, dim), np.nan))
+    g["reward_noise"] = (r.normal(0, cfg["reward_noise"], (K, T))
+                         if "reward_noise" in cfg else np.full((K, T), np.nan))
+    if image:
+        lo, hi = ScalarWrapperTail(n_actions=spec["n_actions"], **cfg).shift_draw_bounds(
+            spec["side"])
+        g["shift"] = r.integers(lo, hi, size=(K, T, 2))
+    else:
+        g["shift"] = np.zeros((K, T, 2), dtype=np.int64)
+    g["base_reward"] = np.round(r.normal(size=(K, T)), 3)
+    g["base_done"] = r.random((K, T)) < 0.08
+    return g
+
+
+@pytest.mark.parametrize("seed", __import__("tests.fuzz_configs", fromlist=["x"]).WRAPPER_SEEDS)
+def test_wrapper_tail_fuzz_cuda_vs_oracle(seed):
+    """VectorGymEnvTail (replayed draws) against the oracle's tail on the
+    configurations tests/test_fuzz_reference.py pins the oracle on against the
+    reference wrapper; terminal steps included (the reference raises there,
+    gym_env_wrapper.py:414, so they are CUDA-vs-oracle only)."""
+    from tests.fuzz_configs import wrapper_fuzz_spec
+    from tests.test_wrapper_tail import CudaLanes, OracleLanes
+    spec = wrapper_fuzz_spec(seed)
+    K, T = 37, 40
+    g = _synthetic_wrapper_record(spec, K, T, seed)
+    ora, dev = OracleLanes(K, spec), CudaLanes(K, spec)
+    for t in range(T):
+        a1 = ora.actions(g["action"][:, t], g["choice_u"][:, t])
+        a2 = dev.actions(g["action"][:, t], g["choice_u"][:, t])
+        assert np.array_equal(np.asarray(a1), np.asarray(a2)), (t, spec)
+        args = (g["base_obs"][:, t], g["base_reward"][:, t], g["base_done"][:, t],
+                g["reward_noise"][:, t], g["obs_noise"][:, t], g["shift"][:, t])
+        o1, r1 = ora.post(*args)
+        o2, r2 = dev.post(*args)
+        assert np.array_equal(np.asarray(r1), np.asarray(r2)), (t, spec)
+        assert np.array_equal(np.asarray(o1), np.asarray(o2)), (t, spec)

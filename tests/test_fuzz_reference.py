@@ -66,3 +66,20 @@ def test_image_fuzz_reference_vs_oracle(seed, tmp_path):
     cfg = image_fuzz_config(seed)
     g = _record("fuzz_i%d" % seed, cfg, tmp_path, lanes=2, steps=16, horizon=6)
     numpy_leg(g, materialise(cfg), 6)
+
+
+@pytest.mark.parametrize("seed", __import__("tests.fuzz_configs", fromlist=["x"]).WRAPPER_SEEDS)
+def test_wrapper_tail_fuzz_reference_vs_oracle(seed, tmp_path):
+    """The reference GymEnvWrapper around the stand-in base envs, recorded with
+    the recipe of the wrap_*.npz fixtures, against the oracle's tail on every
+    non-terminal step (the reference raises on terminal ones, :414)."""
+    from tests.fuzz_configs import wrapper_fuzz_spec
+    from tests.golden.make_wrapper_golden import run_wrapper_case
+    from tests.test_wrapper_tail import OracleLanes, replay_wrapper_record
+    spec = wrapper_fuzz_spec(seed)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        run_wrapper_case("fuzz_w%d" % seed, spec, out_dir=str(tmp_path), lanes=3, steps=40)
+    g = dict(np.load(tmp_path / ("fuzz_w%d.npz" % seed), allow_pickle=False))
+    replay_wrapper_record(g, spec, OracleLanes)
+    assert (~g["raised"]).sum() > 60

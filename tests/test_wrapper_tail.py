@@ -15,7 +15,15 @@ from tests.golden.make_wrapper_golden import WRAPPER_CASES
 def replay_wrapper_golden(name, make_tail):
     """Drive a batched tail implementation (K lanes) through a golden case;
     returns (rewards [K, T], raised [K, T]) for further checks."""
-    g, spec = gu.load(name), WRAPPER_CASES[name]
+    g = gu.load(name)
+    out = replay_wrapper_record(g, WRAPPER_CASES[name], make_tail)
+    assert g["raised"].sum() > 10 and (~g["raised"]).sum() > 150
+    return out
+
+
+def replay_wrapper_record(g, spec, make_tail):
+    """The same for any record made by make_wrapper_golden.run_wrapper_case
+    (the fuzz tests record fresh ones)."""
     K, T = g["raised"].shape
     tail = make_tail(K, spec)
     got_r = np.zeros((K, T))
@@ -29,7 +37,6 @@ def replay_wrapper_golden(name, make_tail):
         assert np.array_equal(np.asarray(r)[ok], g["out_reward"][ok, t]), t
         assert np.array_equal(np.asarray(obs)[ok], g["out_obs"][ok, t]), t
         got_r[:, t] = r
-    assert g["raised"].sum() > 10 and (~g["raised"]).sum() > 150
     return got_r, g["raised"]
 
 
