@@ -76,12 +76,17 @@ __host__ __device__ __forceinline__ void philox_round_keys(uint32_t k0, uint32_t
     rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u;
   }
 }
+#ifdef MDPP_EXP_PHILOX_ROUNDS  // (timing experiment only: NOT the contract's generator)
+constexpr int kPhiloxRounds = MDPP_EXP_PHILOX_ROUNDS;
+#else
+constexpr int kPhiloxRounds = 10;
+#endif
 __host__ __device__ __forceinline__ U4 philox4x32_10_rk(uint32_t c0, uint32_t c1,
                                                         uint32_t c2, uint32_t c3,
                                                         const uint32_t* rk) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < kPhiloxRounds; ++r) {
     uint64_t p0 = (uint64_t)M0 * c0;
     uint64_t p1 = (uint64_t)M1 * c2;
     uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk[2 * r];
